@@ -1,0 +1,484 @@
+// rb_engine.cu -- kernels and host driver of the wavefront ray engine (sm_100a).
+//
+// Kernels (all hand-written, launched on one stream):
+//   k_init    one thread per input ray: primary ray into the queue, or, for -I
+//             sensors, the pretend Lambertian hit of rt/rtrace.c:415-432 /
+//             rt/rcontrib.c:321-339 / rt/RtraceSimulManager.cpp:315-335, which
+//             emits one hemisphere record and the sensor's shadow rays
+//   k_expand  one CTA per hemisphere record: the n*n stratified Shirley-Chiu
+//             samples of rt/ambcomp.c:350-422 become queue rays
+//   k_wave    one thread per queued ray: octree walk + intersection
+//             (rb_geom.cuh), then shading, contribution accumulation and
+//             child-ray emission (rb_shade.cuh)
+//   k_finish  accumulators (double) -> output rows (float32), rc2.c:293-335
+// The host loops wave after wave until the queues are empty; batches of
+// records are sized so that a wave fits the two ray queues in HBM.
+#include "rb_engine.cuh"
+#include "rb_shade.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace rb {
+
+#define WAVE_THREADS 128
+
+#define CK(call)                                                                     \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call; \
+            return false;                                                            \
+        }                                                                            \
+    } while (0)
+
+// ------------------------------------------------------------- kernels -----
+__device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws, unsigned nr) {
+    unsigned a = __reduce_add_sync(__activemask(), ws.nodes);
+    unsigned b = __reduce_add_sync(__activemask(), ws.leafents);
+    unsigned c = __reduce_add_sync(__activemask(), ws.prims);
+    unsigned d = __reduce_add_sync(__activemask(), nr);
+    unsigned lane = threadIdx.x & 31;
+    unsigned leader = __ffs(__activemask()) - 1;
+    if (lane == leader) {
+        atomicAdd(&C->nodes, (unsigned long long)a);
+        atomicAdd(&C->leafents, (unsigned long long)b);
+        atomicAdd(&C->prims, (unsigned long long)c);
+        atomicAdd(&C->nrays, (unsigned long long)d);
+    }
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS) k_wave(const WaveArgs A) {
+    __shared__ int stk[RB_STACK * WAVE_THREADS];
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.nin) return;
+    const QRay q = A.qin[i];
+    RayCtx r;
+    for (int k = 0; k < 3; k++) { r.org[k] = q.org[k]; r.dir[k] = q.dir[k]; r.coef[k] = q.coef[k]; }
+    r.rmax = q.rmax; r.rweight = q.rweight; r.row = q.row;
+    r.crtype = q.info & 0x3ff; r.rlvl = (q.info >> 10) & 0x3f; r.rdepth = (q.info >> 16) & 0x3f;
+    r.rsrc = q.rsrc;
+    r.key = ((unsigned long long)q.key_hi << 32) | q.key_lo;
+    r.nchild = 0;
+    Hit h;
+    WalkStats ws = {0, 0, 0};
+    bool hit = localhit(A.S, r.org, r.dir, r.rmax, h, stk + threadIdx.x, WAVE_THREADS, ws,
+                        &A.C->errflag, &A.C->errobj);
+    flush_stats(A.C, ws, 1);
+    r.robj = -1; r.flat = false;
+    if (hit) {
+        r.robj = h.robj; r.rot = h.rot; r.rod = h.rod;
+        hit_frame(A.S, h, r.org, r.dir, r.rop, r.ron);
+        int kind = __ldg(&A.S.objhdr[h.robj]).x & 0xff;
+        r.flat = (kind == PK_FACE) | (kind == PK_RING);
+    } else {
+        r.rot = RB_FHUGE; r.rod = 1.0;
+        for (int k = 0; k < 3; k++) { r.rop[k] = r.org[k]; r.ron[k] = -r.dir[k]; }
+        if (!(r.rmax > RB_FTINY)) {              // aft-clipped rays never see sources
+            int sn = sourcehit(A.S, r.dir, r.rsrc, r.crtype);
+            if (sn >= 0) r.robj = A.S.srcs[sn].so;
+        }
+    }
+    if (A.res && r.crtype == RT_PRIMARY) {
+        RayResult& o = A.res[r.row - A.row0];
+        for (int k = 0; k < 3; k++) { o.rop[k] = r.rop[k]; o.ron[k] = r.ron[k]; }
+        o.rot = r.rot; o.rod = r.rod; o.robj = r.robj;
+        o.omod = r.robj >= 0 ? __ldg(&A.S.objhdr[r.robj]).y : -1;
+        o.rweight = r.rweight; o.pad = 0;
+    }
+    if (r.robj < 0) return;
+    shade_ray(A, r);
+}
+
+struct InitArgs {
+    const double* rays;     // [n][6] for this batch
+    unsigned nrays;
+    unsigned long long ray0;     // global index of the batch's first ray
+    int accum;
+    int irrad;
+    int lim_dist;
+};
+
+__global__ void __launch_bounds__(WAVE_THREADS) k_init(const WaveArgs A, const InitArgs I) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= I.nrays) return;
+    const double* v = I.rays + (size_t)i * 6;
+    double org[3] = {v[0], v[1], v[2]}, dir[3] = {v[3], v[4], v[5]};
+    unsigned row = I.accum > 0 ? (unsigned)((I.ray0 + i) / I.accum - I.ray0 / I.accum) + A.row0 : A.row0;
+    double d = normalize3(dir);
+    if (d == 0.0) {                                  // dummy ray: blank record
+        if (A.res) { RayResult& o = A.res[i]; memset(&o, 0, sizeof(o)); o.robj = -1; o.omod = -1; }
+        return;
+    }
+    unsigned long long key = mix64(A.P.seed ^ mix64(I.ray0 + i));
+    if (I.irrad == IRR_NONE) {
+        unsigned slot = reserve_slot(&A.C->nq_out);
+        if (slot >= A.qcap) { A.C->overflow = 1; return; }
+        QRay q;
+        for (int k = 0; k < 3; k++) { q.org[k] = org[k]; q.dir[k] = dir[k]; q.coef[k] = 1.f; }
+        q.rmax = I.lim_dist ? d : 0.0;
+        q.rweight = 1.f;
+        q.row = A.res ? A.row0 + i : row;           // rtrace reports per ray
+        q.info = pack_info(RT_PRIMARY, 0, 0);
+        q.rsrc = -1;
+        q.key_lo = (unsigned)key; q.key_hi = (unsigned)(key >> 32); q.pad = 0;
+        A.qout[slot] = q;
+        return;
+    }
+    RayCtx r;
+    r.coef[0] = r.coef[1] = r.coef[2] = 1.f;
+    r.rweight = 1.f; r.row = A.res ? A.row0 + i : row;
+    r.crtype = RT_PRIMARY; r.rlvl = 0; r.rdepth = 0; r.rsrc = -1;
+    r.robj = -1; r.flat = false; r.key = key; r.nchild = 0; r.rmax = 0.0;
+    r.rod = 1.0;
+    for (int k = 0; k < 3; k++) { r.ron[k] = dir[k]; r.dir[k] = -dir[k]; }
+    if (I.irrad == IRR_RTRACE) {                     // rtrace.c:443-448,415-432
+        r.rot = 1e-5;
+        for (int k = 0; k < 3; k++) { r.org[k] = org[k] + 1.1e-4 * dir[k]; r.rop[k] = r.org[k] + r.dir[k] * r.rot; }
+        for (int k = 0; k < 3; k++) r.ron[k] = -r.dir[k];
+    } else if (I.irrad == IRR_RCONTRIB) {            // rcontrib.c:321-339
+        r.rot = 1e-5;
+        for (int k = 0; k < 3; k++) { r.org[k] = org[k] + 1.1e-4 * dir[k]; r.rop[k] = org[k] + 1e-4 * dir[k]; }
+    } else {                                         // RtraceSimulManager.cpp:315-335
+        r.rot = 1e-4;
+        for (int k = 0; k < 3; k++) { r.rop[k] = org[k] + r.ron[k] * r.rot; r.org[k] = r.rop[k] + r.ron[k] * r.rot; }
+    }
+    if (A.res) {
+        RayResult& o = A.res[i];
+        for (int k = 0; k < 3; k++) { o.rop[k] = r.rop[k]; o.ron[k] = r.ron[k]; }
+        o.rot = r.rot; o.rod = r.rod; o.robj = -1; o.omod = -1; o.rweight = 1.f; o.pad = 0;
+    }
+    const float lamb[5] = {(float)RB_PI, (float)RB_PI, (float)RB_PI, 0.f, 0.f};
+    m_normal(A, r, MK_PLASTIC, lamb);
+}
+
+struct ExpandArgs {
+    const QHemi* hin;
+    unsigned nh;
+};
+
+__global__ void __launch_bounds__(256) k_expand(const WaveArgs A, const ExpandArgs E) {
+    for (unsigned job = blockIdx.x; job < E.nh; job += gridDim.x) {
+        const QHemi h = E.hin[job];
+        unsigned long long hkey = ((unsigned long long)h.key_hi << 32) | h.key_lo;
+        double onrm[3] = {h.onrm[0], h.onrm[1], h.onrm[2]}, ux[3], uy[3];
+        if (!getperpendicular_rand(ux, onrm, hkey)) continue;
+        uy[0] = onrm[1] * ux[2] - onrm[2] * ux[1];
+        uy[1] = onrm[2] * ux[0] - onrm[0] * ux[2];
+        uy[2] = onrm[0] * ux[1] - onrm[1] * ux[0];
+        RayCtx par;
+        for (int k = 0; k < 3; k++) { par.rop[k] = h.rop[k]; par.coef[k] = h.ccoef[k]; par.ron[k] = onrm[k]; }
+        par.rot = 0.0; par.rmax = h.rmax_rem; par.rod = 1.0;
+        par.rweight = h.rweight; par.row = h.row;
+        par.crtype = h.info & 0x3ff; par.rlvl = (h.info >> 10) & 0x3f; par.rdepth = (h.info >> 16) & 0x3f;
+        par.rsrc = h.rsrc; par.robj = -1; par.flat = false; par.key = hkey;
+        const float acoef[3] = {h.acoef[0], h.acoef[1], h.acoef[2]};
+        const int n = h.n, nn = n * n;
+        for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
+            par.nchild = (unsigned)idx;
+            QRay q;
+            if (ambsample(A.P, par, h.atype, acoef, onrm, ux, uy, n, idx / n, idx % n, q)) push_ray(A, q);
+        }
+    }
+}
+
+// rc2.c:293-335 put_contrib(): record value = accumulated sum / accumulate count
+__global__ void k_finish(const double* __restrict__ acc, float* __restrict__ out, size_t n, double scale) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = (float)(acc[i] * scale);
+}
+
+// ---------------------------------------------------------------- host -----
+Engine::Engine(int device) : dev_(device) {
+    cudaSetDevice(dev_);
+    cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking);
+    cudaEventCreate(&ev0_);
+    cudaEventCreate(&ev1_);
+    cudaMalloc(&d_cnt_, sizeof(DCounters));
+    cudaMallocHost(&h_cnt_, sizeof(DCounters));
+}
+
+Engine::~Engine() {
+    cudaSetDevice(dev_);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {d_nodes_, d_leaf_, d_hdr_, d_geom_, d_mats_, d_srcs_, d_otrack_, d_bins_, q_[0], q_[1],
+                    h_[0], h_[1], d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    if (h_cnt_) cudaFreeHost(h_cnt_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_ && !user_stream_) cudaStreamDestroy(stream_);
+}
+
+template <class T>
+static bool upload(void*& dptr, const std::vector<T>& v, std::string& err) {
+    if (dptr) { cudaFree(dptr); dptr = nullptr; }
+    size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    CK(cudaMalloc(&dptr, bytes));
+    if (!v.empty()) CK(cudaMemcpy(dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return true;
+}
+
+bool Engine::upload_scene(const FlatScene& fs, const Scene& sc, std::string& err) {
+    CK(cudaSetDevice(dev_));
+    if (sc.maxdepth > RB_MAXDEPTH) {
+        err = "octree is " + std::to_string(sc.maxdepth) + " levels deep; this engine walks at most " +
+              std::to_string(RB_MAXDEPTH);
+        return false;
+    }
+    if (!upload(d_nodes_, fs.nodes, err) || !upload(d_leaf_, fs.leafpool, err) ||
+        !upload(d_hdr_, fs.objhdr, err) || !upload(d_geom_, fs.geom, err) ||
+        !upload(d_mats_, fs.mats, err) || !upload(d_srcs_, fs.srcs, err))
+        return false;
+    std::vector<int> ot(sc.objs.size(), -1);
+    if (!upload(d_otrack_, ot, err)) return false;
+    for (int k = 0; k < 3; k++) S_.cuorg[k] = sc.cuorg[k];
+    S_.cusize = sc.cusize;
+    S_.root = sc.root; S_.nobjs = (int)sc.objs.size(); S_.nsrcs = (int)fs.srcs.size();
+    S_.maxdepth = sc.maxdepth;
+    S_.nodes = (const int*)d_nodes_; S_.leafpool = (const int*)d_leaf_;
+    S_.objhdr = (const int4*)d_hdr_; S_.geom = (const double*)d_geom_;
+    S_.mats = (const MatRec*)d_mats_; S_.srcs = (const SrcRec*)d_srcs_;
+    S_.otrack = (const int*)d_otrack_;
+    has_local_sources_ = false;
+    for (const auto& s : fs.srcs)
+        if (!(s.flags & SF_DISTANT)) { has_local_sources_ = true; local_source_note_ = fs.unsupported_note; }
+    objdesc.clear();
+    for (const auto& o : sc.objs) objdesc.push_back(o.tname + " \"" + o.name + "\"");
+    nbins_ = 0; ncols_ = 0;
+    return true;
+}
+
+std::string Engine::describe_obj(unsigned idx) const {
+    if (idx < objdesc.size()) return objdesc[idx];
+    return "object #" + std::to_string(idx);
+}
+
+bool Engine::set_bins(const std::vector<DBinSpec>& bins, const std::vector<int>& otrack, int ncols,
+                      std::string& err) {
+    CK(cudaSetDevice(dev_));
+    if (!upload(d_bins_, bins, err)) return false;
+    if ((int)otrack.size() != S_.nobjs) { err = "internal: otrack size"; return false; }
+    if (!otrack.empty()) CK(cudaMemcpy(d_otrack_, otrack.data(), otrack.size() * sizeof(int), cudaMemcpyHostToDevice));
+    nbins_ = (int)bins.size();
+    ncols_ = ncols;
+    return true;
+}
+
+bool Engine::ensure_queues(std::string& err) {
+    if (q_[0]) return true;
+    size_t freeb = 0, totalb = 0;
+    CK(cudaMemGetInfo(&freeb, &totalb));
+    size_t want = qcap_req_ ? qcap_req_ : (size_t)48 << 20;     // rays per queue
+    size_t maxq = (freeb / 3) / (2 * sizeof(QRay));              // at most a third of free HBM
+    if (want > maxq) want = maxq;
+    if (want < 4096) { err = "not enough device memory for ray queues"; return false; }
+    qcap_ = want;
+    hcap_ = std::max<size_t>(qcap_ / 16, 4096);
+    CK(cudaMalloc(&q_[0], qcap_ * sizeof(QRay)));
+    CK(cudaMalloc(&q_[1], qcap_ * sizeof(QRay)));
+    CK(cudaMalloc(&h_[0], hcap_ * sizeof(QHemi)));
+    CK(cudaMalloc(&h_[1], hcap_ * sizeof(QHemi)));
+    return true;
+}
+
+template <class T>
+static bool ensure_buf(T*& p, size_t& have, size_t bytes, std::string& err) {
+    if (bytes <= have && p) return true;
+    if (p) cudaFree(p);
+    p = nullptr; have = 0;
+    CK(cudaMalloc(&p, std::max<size_t>(bytes, 256)));
+    have = bytes;
+    return true;
+}
+
+bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_t nrec, std::string& err,
+                       bool& overflow) {
+    overflow = false;
+    const int accum = job.accum;
+    const size_t ray0 = accum > 0 ? rec0 * accum : 0;
+    const size_t nray = accum > 0 ? std::min(job.nrays - ray0, nrec * (size_t)accum) : job.nrays;
+    const bool per_ray = job.results != nullptr || (job.values != nullptr && job.cmat == nullptr);
+    // rtrace-style jobs report per input ray: rows == rays
+    const size_t nrows = per_ray ? nray : nrec;
+    const bool want_c = job.cmat != nullptr && ncols_ > 0;
+    const bool want_v = job.values != nullptr;
+    // ---- stage inputs ----
+    const double* d_rays = nullptr;
+    if (job.rays_on_device) d_rays = job.rays + ray0 * 6;
+    else {
+        if (!ensure_buf(d_rays_, rays_bytes_, nray * 6 * sizeof(double), err)) return false;
+        CK(cudaMemcpyAsync(d_rays_, job.rays + ray0 * 6, nray * 6 * sizeof(double), cudaMemcpyHostToDevice, stream_));
+        d_rays = d_rays_;
+    }
+    size_t accn = want_c ? nrows * (size_t)ncols_ * 3 : 0;
+    if (want_c) {
+        if (!ensure_buf(d_acc_, acc_bytes_, accn * sizeof(double), err)) return false;
+        CK(cudaMemsetAsync(d_acc_, 0, accn * sizeof(double), stream_));
+    }
+    if (want_v) {
+        if (!ensure_buf(d_vacc_, vacc_bytes_, nrows * 3 * sizeof(double), err)) return false;
+        CK(cudaMemsetAsync(d_vacc_, 0, nrows * 3 * sizeof(double), stream_));
+    }
+    if (job.results) {
+        if (!ensure_buf(d_res_, res_bytes_, nray * sizeof(RayResult), err)) return false;
+    }
+    CK(cudaMemsetAsync(d_cnt_, 0, sizeof(DCounters), stream_));
+
+    WaveArgs A;
+    A.S = S_; A.P = P;
+    A.bins = (const DBinSpec*)d_bins_; A.nbinspecs = nbins_;
+    A.acc = want_c ? d_acc_ : nullptr; A.ncols = ncols_;
+    A.vacc = want_v ? d_vacc_ : nullptr;
+    A.row0 = 0;
+    A.res = job.results ? d_res_ : nullptr;
+    A.C = d_cnt_;
+    A.inline_hemi_max = 16;
+    A.qcap = (unsigned)qcap_; A.hcap = (unsigned)hcap_;
+
+    auto sync_counters = [&](std::string& err) -> bool {
+        CK(cudaMemcpyAsync(h_cnt_, d_cnt_, sizeof(DCounters), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        return true;
+    };
+    auto timed = [&](double& bucket, std::string& err) -> bool {   // call after sync
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+        bucket += ms;
+        return true;
+    };
+
+    int cur = 0;
+    // ---- k_init ----
+    {
+        InitArgs I;
+        I.rays = d_rays; I.nrays = (unsigned)nray;
+        I.ray0 = job.row_base * (unsigned long long)(accum > 0 ? accum : 1) + ray0;
+        I.accum = per_ray ? 1 : accum; I.irrad = job.irrad; I.lim_dist = job.lim_dist;
+        if (per_ray) I.accum = 1;
+        A.qin = nullptr; A.nin = 0; A.qout = q_[cur]; A.hout = h_[cur];
+        unsigned grid = (unsigned)((nray + WAVE_THREADS - 1) / WAVE_THREADS);
+        CK(cudaEventRecord(ev0_, stream_));
+        k_init<<<grid, WAVE_THREADS, 0, stream_>>>(A, I);
+        CK(cudaEventRecord(ev1_, stream_));
+        stats.launches++;
+        CK(cudaGetLastError());
+        if (!sync_counters(err) || !timed(stats.kernel_ms, err)) return false;
+    }
+    unsigned nq = h_cnt_->nq_out, nh = h_cnt_->nh_out;
+    for (int wave = 0; wave < 4096; wave++) {
+        if (h_cnt_->overflow || (size_t)nq + h_cnt_->hemi_rays > qcap_) { overflow = true; return true; }
+        if (h_cnt_->errflag) break;
+        if (nh > 0) {                         // expand hemispheres into the current queue
+            ExpandArgs E; E.hin = h_[cur]; E.nh = nh;
+            A.qout = q_[cur];
+            unsigned grid = std::min<unsigned>(nh, 148u * 8u);
+            CK(cudaEventRecord(ev0_, stream_));
+            k_expand<<<grid, 256, 0, stream_>>>(A, E);
+            CK(cudaEventRecord(ev1_, stream_));
+            stats.launches++;
+            CK(cudaGetLastError());
+            if (!sync_counters(err) || !timed(stats.kernel_ms, err)) return false;
+            if (h_cnt_->overflow) { overflow = true; return true; }
+            nq = h_cnt_->nq_out;
+        }
+        if (nq == 0) break;
+        // reset the out counters, keep the statistics
+        CK(cudaMemsetAsync(&d_cnt_->nq_out, 0, 3 * sizeof(unsigned), stream_));
+        A.qin = q_[cur]; A.nin = nq; A.qout = q_[cur ^ 1]; A.hout = h_[cur ^ 1];
+        unsigned grid = (nq + WAVE_THREADS - 1) / WAVE_THREADS;
+        CK(cudaEventRecord(ev0_, stream_));
+        k_wave<<<grid, WAVE_THREADS, 0, stream_>>>(A);
+        CK(cudaEventRecord(ev1_, stream_));
+        stats.launches++; stats.wave_launches++; stats.waves++;
+        CK(cudaGetLastError());
+        if (!sync_counters(err)) return false;
+        { double ms = 0; if (!timed(ms, err)) return false; stats.kernel_ms += ms; stats.wave_ms += ms; }
+        cur ^= 1;
+        nq = h_cnt_->nq_out; nh = h_cnt_->nh_out;
+    }
+    if (h_cnt_->errflag) {
+        unsigned f = h_cnt_->errflag;
+        std::string what = describe_obj(h_cnt_->errobj);
+        if (f & RB_ERR_LOCAL_SRC) err = "unsupported: local light source material " + what + " (only distant sources are built)";
+        else if (f & RB_ERR_UNSUP_MAT) err = "unsupported material " + what + " reached by a ray (no CPU fallback)";
+        else if (f & RB_ERR_UNSUP_PRIM) err = "unsupported surface " + what + " reached by a ray (no CPU fallback)";
+        else err = "unsupported modifier on " + what + " reached by a ray (patterns/textures/mixtures are not built)";
+        return false;
+    }
+    stats.nrays += h_cnt_->nrays; stats.nodes += h_cnt_->nodes; stats.leafents += h_cnt_->leafents;
+    stats.prims += h_cnt_->prims; stats.contribs += h_cnt_->contribs; stats.badbin += h_cnt_->badbin;
+    // ---- outputs ----
+    if (want_c) {
+        double scale = accum > 1 ? 1.0 / accum : 1.0;
+        float* dst;
+        size_t off = rec0 * (size_t)ncols_ * 3;
+        if (job.cmat_on_device) dst = job.cmat + off;
+        else {
+            if (!ensure_buf(d_out_, out_bytes_, accn * sizeof(float), err)) return false;
+            dst = d_out_;
+        }
+        unsigned grid = (unsigned)std::min<size_t>((accn + 255) / 256, 148 * 16);
+        CK(cudaEventRecord(ev0_, stream_));
+        k_finish<<<grid, 256, 0, stream_>>>(d_acc_, dst, accn, scale);
+        CK(cudaEventRecord(ev1_, stream_));
+        stats.launches++;
+        if (!job.cmat_on_device)
+            CK(cudaMemcpyAsync(job.cmat + off, d_out_, accn * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        if (!timed(stats.kernel_ms, err)) return false;
+    }
+    if (want_v) {
+        size_t off = (per_ray ? ray0 : rec0) * 3;
+        CK(cudaMemcpyAsync(job.values + off, d_vacc_, nrows * 3 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    }
+    if (job.results)
+        CK(cudaMemcpyAsync(job.results + ray0, d_res_, nray * sizeof(RayResult), cudaMemcpyDeviceToHost, stream_));
+    CK(cudaStreamSynchronize(stream_));
+    stats.batches++;
+    return true;
+}
+
+bool Engine::run(const TraceJob& job, const DParams& P, std::string& err) {
+    CK(cudaSetDevice(dev_));
+    if (!d_nodes_) { err = "no octree loaded"; return false; }
+    if (has_local_sources_) {
+        err = "unsupported scene: " + local_source_note_;
+        return false;
+    }
+    if (!ensure_queues(err)) return false;
+    if (job.nrays == 0) return true;
+    const int accum = job.accum;
+    const size_t nrec_total = accum > 0 ? (job.nrays + accum - 1) / accum : 1;
+    // estimate rays per record of the largest wave to size batches
+    double per_rec = 1.0;
+    if (P.ambounce > 0 && P.ambdiv > 0) {
+        double wt = 1.0, d = RB_PI * 0.8 / (P.ambdiv * (double)P.minweight + 1e-20);
+        if (wt > d) wt = d;
+        int n = (int)(sqrt(P.ambdiv * wt) + .5);
+        if (n < 1) n = 1;
+        per_rec = (double)n * n;
+    }
+    per_rec += S_.nsrcs;
+    per_rec *= (accum > 0 ? accum : 1);
+    size_t batch = (size_t)std::max(1.0, (double)qcap_ * 0.45 / per_rec);
+    if (accum <= 0) batch = 1;
+    size_t rec = 0;
+    while (rec < nrec_total) {
+        size_t n = std::min(batch, nrec_total - rec);
+        bool ovf = false;
+        if (!run_batch(job, P, rec, n, err, ovf)) return false;
+        if (ovf) {
+            stats.retries++;
+            if (n <= 1) { err = "ray queue overflow on a single record; raise the queue capacity"; return false; }
+            batch = std::max<size_t>(1, n / 2);
+            continue;
+        }
+        rec += n;
+    }
+    return true;
+}
+
+}  // namespace rb

@@ -1,0 +1,77 @@
+// rb_engine.cuh -- host-side driver of the wavefront ray engine.
+#pragma once
+#include <string>
+#include <vector>
+#include "rb_device.cuh"
+
+namespace rb {
+
+struct EngineStats {
+    unsigned long long nrays = 0, nodes = 0, leafents = 0, prims = 0, contribs = 0;
+    unsigned long long launches = 0;     // kernels launched
+    unsigned long long waves = 0, batches = 0, retries = 0;
+    double kernel_ms = 0;                // device time of all kernels (CUDA events)
+    double wave_ms = 0;                  // device time of k_wave launches only
+    unsigned long long wave_launches = 0;
+    unsigned long long badbin = 0;
+};
+
+// how -I sensors are turned into a pretend hit (see SURVEY 8a "three entries")
+enum : int { IRR_NONE = 0, IRR_RTRACE = 1, IRR_RCONTRIB = 2, IRR_MANAGER = 3 };
+
+struct TraceJob {
+    const double* rays = nullptr;     // [nrays][6] origin, direction (host or device)
+    bool rays_on_device = false;
+    size_t nrays = 0;
+    int accum = 1;                    // rays per output record (0: all into one)
+    int irrad = IRR_NONE;
+    bool lim_dist = false;
+    // outputs (any may be null)
+    float* cmat = nullptr;            // [nrows][ncols][3] coefficients
+    bool cmat_on_device = false;
+    double* values = nullptr;         // [nrows][3] radiance/irradiance (host)
+    RayResult* results = nullptr;     // [nrays] primary-hit reports (host)
+    unsigned long long row_base = 0;  // global index of row 0 (RNG keys, multi-GPU shards)
+};
+
+class Engine {
+public:
+    explicit Engine(int device);
+    ~Engine();
+    bool upload_scene(const FlatScene& fs, const Scene& sc, std::string& err);
+    bool set_bins(const std::vector<DBinSpec>& bins, const std::vector<int>& otrack, int ncols, std::string& err);
+    bool run(const TraceJob& job, const DParams& P, std::string& err);
+    void set_stream(cudaStream_t s) { stream_ = s; user_stream_ = true; }
+    void set_queue_capacity(size_t nrays) { qcap_req_ = nrays; }
+    EngineStats stats;
+    int device() const { return dev_; }
+    const std::vector<std::string>* objnames = nullptr;
+    std::string describe_obj(unsigned idx) const;
+    std::vector<std::string> objdesc;      // "type \"name\"" per object, for messages
+
+private:
+    bool ensure_queues(std::string& err);
+    bool run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_t nrec, std::string& err, bool& overflow);
+    int dev_;
+    cudaStream_t stream_ = nullptr;
+    bool user_stream_ = false;
+    DScene S_{};
+    void *d_nodes_ = nullptr, *d_leaf_ = nullptr, *d_hdr_ = nullptr, *d_geom_ = nullptr,
+         *d_mats_ = nullptr, *d_srcs_ = nullptr, *d_otrack_ = nullptr, *d_bins_ = nullptr;
+    int nbins_ = 0, ncols_ = 0;
+    QRay* q_[2] = {nullptr, nullptr};
+    QHemi* h_[2] = {nullptr, nullptr};
+    size_t qcap_ = 0, hcap_ = 0, qcap_req_ = 0;
+    DCounters* d_cnt_ = nullptr;
+    DCounters* h_cnt_ = nullptr;          // pinned
+    double* d_acc_ = nullptr; size_t acc_bytes_ = 0;
+    double* d_vacc_ = nullptr; size_t vacc_bytes_ = 0;
+    double* d_rays_ = nullptr; size_t rays_bytes_ = 0;
+    float* d_out_ = nullptr; size_t out_bytes_ = 0;
+    RayResult* d_res_ = nullptr; size_t res_bytes_ = 0;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    bool has_local_sources_ = false;
+    std::string local_source_note_;
+};
+
+}  // namespace rb

@@ -1,0 +1,730 @@
+// rb_scene.cpp -- .oct loader, modifier resolution and flattening to
+// device-ready tables.  See rb_scene.hpp for the reference files restated.
+#include "rb_scene.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <fstream>
+#include <functional>
+#include <sstream>
+
+namespace rb {
+
+static const double FTINY = 1e-6;
+static const double PI = 3.14159265358979323846;
+
+// ---------------------------------------------------------------- types ----
+struct TypeInfo { const char* name; int ot; };
+static const TypeInfo kTypes[] = {
+    {"polygon", OT_POLYGON}, {"cone", OT_CONE}, {"sphere", OT_SPHERE},
+    {"ring", OT_RING}, {"cylinder", OT_CYLINDER}, {"cup", OT_CUP},
+    {"bubble", OT_BUBBLE}, {"tube", OT_TUBE}, {"source", OT_SOURCE},
+    {"instance", OT_INSTANCE}, {"mesh", OT_MESH}, {"alias", OT_ALIAS},
+    {"plastic", OT_PLASTIC}, {"metal", OT_METAL}, {"glass", OT_GLASS},
+    {"trans", OT_TRANS}, {"glow", OT_GLOW}, {"light", OT_LIGHT},
+    {"illum", OT_ILLUM}, {"spotlight", OT_SPOTLIGHT},
+    {"dielectric", OT_DIELECTRIC}, {"interface", OT_INTERFACE},
+    {"mist", OT_MIST}, {"aBSDF", OT_ABSDF}, {"trans2", OT_TRANS2},
+    {"antimatter", OT_ANTIMATTER},
+    // other materials (src/radiance/common/otypes.h:127-186, T_M entries)
+    {"plastic2", OT_OTHER_MATERIAL}, {"metal2", OT_OTHER_MATERIAL},
+    {"plasfunc", OT_OTHER_MATERIAL}, {"metfunc", OT_OTHER_MATERIAL},
+    {"mirror", OT_OTHER_MATERIAL}, {"transfunc", OT_OTHER_MATERIAL},
+    {"BRTDfunc", OT_OTHER_MATERIAL}, {"BSDF", OT_OTHER_MATERIAL},
+    {"WGMDfunc", OT_OTHER_MATERIAL}, {"plasdata", OT_OTHER_MATERIAL},
+    {"metdata", OT_OTHER_MATERIAL}, {"transdata", OT_OTHER_MATERIAL},
+    {"prism1", OT_OTHER_MATERIAL}, {"prism2", OT_OTHER_MATERIAL},
+    {"ashik2", OT_OTHER_MATERIAL},
+    // patterns
+    {"brightfunc", OT_PATTERN}, {"brightdata", OT_PATTERN},
+    {"brighttext", OT_PATTERN}, {"colorpict", OT_PATTERN},
+    {"colorfunc", OT_PATTERN}, {"colordata", OT_PATTERN},
+    {"colortext", OT_PATTERN}, {"spectrum", OT_PATTERN},
+    {"specfile", OT_PATTERN}, {"specfunc", OT_PATTERN},
+    {"specdata", OT_PATTERN}, {"specpict", OT_PATTERN},
+    // textures, mixtures
+    {"texfunc", OT_TEXTURE}, {"texdata", OT_TEXTURE},
+    {"mixfunc", OT_MIXTURE}, {"mixdata", OT_MIXTURE},
+    {"mixtext", OT_MIXTURE}, {"mixpict", OT_MIXTURE},
+};
+
+int ot_from_name(const std::string& s) {
+    for (const auto& t : kTypes)
+        if (s == t.name) return t.ot;
+    return OT_OTHER;
+}
+bool ot_is_surface(int t) {
+    return t == OT_POLYGON || t == OT_CONE || t == OT_SPHERE || t == OT_RING ||
+           t == OT_CYLINDER || t == OT_CUP || t == OT_BUBBLE || t == OT_TUBE ||
+           t == OT_SOURCE;
+}
+bool ot_is_volume(int t) { return t == OT_INSTANCE || t == OT_MESH; }
+bool ot_is_material(int t) {
+    switch (t) {
+    case OT_PLASTIC: case OT_METAL: case OT_GLASS: case OT_TRANS: case OT_GLOW:
+    case OT_LIGHT: case OT_ILLUM: case OT_SPOTLIGHT: case OT_DIELECTRIC:
+    case OT_INTERFACE: case OT_MIST: case OT_ABSDF: case OT_TRANS2:
+    case OT_ANTIMATTER: case OT_OTHER_MATERIAL:
+        return true;
+    }
+    return false;
+}
+bool ot_is_light(int t) {
+    return t == OT_GLOW || t == OT_LIGHT || t == OT_ILLUM || t == OT_SPOTLIGHT;
+}
+bool ot_is_modifier(int t) { return !ot_is_surface(t) && !ot_is_volume(t); }
+
+// ------------------------------------------------------ portable binary ----
+namespace {
+struct Rd {
+    const unsigned char* p;
+    const unsigned char* e;
+    bool bad = false;
+    int getc_() {
+        if (p >= e) { bad = true; return -1; }
+        return *p++;
+    }
+    // portio.c:116-133 getint(): big-endian, sign-extended from first byte
+    long getint(int siz) {
+        int c = getc_();
+        if (c < 0) return -1;
+        long r = c;
+        if (c & 0x80) r |= -256L;
+        while (--siz > 0) {
+            c = getc_();
+            if (c < 0) return -1;
+            r = (long)((unsigned long)r << 8);
+            r |= c;
+        }
+        return r;
+    }
+    // portio.c:136-152 getflt(): 4-byte mantissa + 1-byte exponent
+    double getflt() {
+        long l = getint(4);
+        if (bad) return 0;
+        if (l == 0) { getc_(); return 0.0; }
+        double d = (l + .5 - (l < 0)) * (1. / 0x7fffffff);
+        return ldexp(d, (int)getint(1));
+    }
+    bool getstr(std::string& s) {
+        s.clear();
+        for (;;) {
+            int c = getc_();
+            if (c < 0) return false;
+            if (c == 0) return true;
+            s.push_back((char)c);
+        }
+    }
+};
+}  // namespace
+
+// --------------------------------------------------------------- loader ----
+static int read_tree(Rd& rd, Scene& sc, int objsize, int depth, std::string& err) {
+    if (depth > sc.maxdepth) sc.maxdepth = depth;
+    int c = rd.getc_();
+    switch (c) {
+    case 0:  // OT_EMPTY
+        return -1;
+    case 1: {  // OT_FULL: readoct.c:153-168 getfullnode()
+        long n = rd.getint(objsize);
+        if (rd.bad || n < 0 || n > 8191) { err = "bad set in octree"; return -1; }
+        int off = (int)sc.leafpool.size();
+        sc.leafpool.push_back((int)n);
+        for (long i = 0; i < n; i++) sc.leafpool.push_back((int)rd.getint(objsize));
+        if (rd.bad) { err = "truncated octree"; return -1; }
+        return -(off) - 2;
+    }
+    case 2: {  // OT_TREE: readoct.c:195-218 gettree()
+        if (depth > 60) { err = "octree too deep"; return -1; }
+        int idx = (int)(sc.nodes.size() / 8);
+        sc.nodes.resize(sc.nodes.size() + 8, -1);
+        for (int i = 0; i < 8; i++) {
+            int k = read_tree(rd, sc, objsize, depth + 1, err);
+            if (!err.empty()) return -1;
+            sc.nodes[(size_t)idx * 8 + i] = k;
+        }
+        return idx;
+    }
+    default:
+        err = (c < 0) ? "truncated octree" : "damaged octree";
+        return -1;
+    }
+}
+
+bool Scene::load_octree(const std::string& path) {
+    error.clear();
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { error = "cannot open octree file \"" + path + "\""; return false; }
+    std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    const unsigned char* b = (const unsigned char*)data.data();
+    const unsigned char* e = b + data.size();
+    // ---- info header (common/header.c: lines until an empty line) ----
+    const unsigned char* p = b;
+    bool gotfmt = false, first = true;
+    header.clear();
+    for (;;) {
+        const unsigned char* nl = (const unsigned char*)memchr(p, '\n', e - p);
+        if (!nl) { error = "(" + path + "): not an octree"; return false; }
+        std::string line((const char*)p, nl - p);
+        p = nl + 1;
+        if (line.empty()) break;
+        if (first) {
+            first = false;
+            if (line.compare(0, 2, "#?") != 0) { error = "(" + path + "): not an octree"; return false; }
+            header.push_back(line);
+            continue;
+        }
+        if (line.compare(0, 7, "FORMAT=") == 0) {
+            gotfmt = (line.find("Radiance_octree") != std::string::npos);
+            continue;
+        }
+        header.push_back(line);
+    }
+    if (!gotfmt) { error = "(" + path + "): not an octree"; return false; }
+    Rd rd{p, e};
+    const int OCTMAGIC = 4 * 8 + 251;
+    int objsize = (int)rd.getint(2) - OCTMAGIC;
+    if (objsize <= 0 || objsize > 8) { error = "(" + path + "): incompatible octree format"; return false; }
+    std::string s;
+    for (int i = 0; i < 3; i++) { rd.getstr(s); cuorg[i] = atof(s.c_str()); }
+    rd.getstr(s); cusize = atof(s.c_str());
+    srcfiles.clear();
+    for (;;) {
+        if (!rd.getstr(s)) { error = "(" + path + "): truncated octree"; return false; }
+        if (s.empty()) break;
+        srcfiles.push_back(s);
+    }
+    frozen = srcfiles.empty();
+    long nobj = rd.getint(objsize);
+    if (rd.bad || nobj < 0) { error = "(" + path + "): truncated octree"; return false; }
+    nodes.clear(); leafpool.clear(); maxdepth = 0;
+    std::string terr;
+    root = read_tree(rd, *this, objsize, 0, terr);
+    if (!terr.empty()) { error = "(" + path + "): " + terr; return false; }
+    objs.clear();
+    if (frozen) {
+        // sceneio.c:90-109 readscene(): type-name table then objects
+        std::vector<int> tmap; std::vector<std::string> tnames;
+        for (;;) {
+            if (!rd.getstr(s)) { error = "(" + path + "): truncated octree"; return false; }
+            if (s.empty()) break;
+            tnames.push_back(s);
+            tmap.push_back(ot_from_name(s));
+        }
+        for (;;) {  // sceneio.c:20-87 getobj()
+            long ti = rd.getint(1);
+            if (rd.bad) { error = "(" + path + "): unexpected EOF in scene"; return false; }
+            if (ti == -1) break;
+            if (ti < 0 || ti >= (long)tmap.size()) { error = "(" + path + "): reference to unknown type"; return false; }
+            Object o;
+            o.otype = tmap[ti]; o.tname = tnames[ti];
+            o.omod = (int)rd.getint(objsize);
+            rd.getstr(o.name);
+            long ns = rd.getint(2);
+            for (long i = 0; i < ns; i++) { rd.getstr(s); o.sargs.push_back(s); }
+            long nf = rd.getint(2);
+            o.fargs.resize(nf > 0 ? nf : 0);
+            for (long i = 0; i < nf; i++) o.fargs[i] = rd.getflt();
+            if (rd.bad) { error = "(" + path + "): unexpected EOF in scene"; return false; }
+            objs.push_back(std::move(o));
+        }
+        if ((long)objs.size() != nobj) {
+            error = "(" + path + "): bad object count in frozen octree"; return false;
+        }
+    } else {
+        // octree refers to scene files: parse them as text (readoct.c:90-100)
+        std::string dir;
+        size_t sl = path.rfind('/');
+        if (sl != std::string::npos) dir = path.substr(0, sl + 1);
+        for (const auto& fn : srcfiles) {
+            std::string full = (fn[0] == '/' || fn[0] == '!') ? fn : fn;
+            if (!read_rad_text(full)) {
+                if (dir.empty() || !read_rad_text(dir + fn)) return false;
+                error.clear();
+            }
+        }
+        if ((long)objs.size() != nobj) {
+            error = "(" + path + "): bad object count; octree stale?"; return false;
+        }
+    }
+    index_modifiers();
+    return true;
+}
+
+// Plain-text scene parser (common/readobj.c:37-203 getobject, readfargs.c).
+// "!command" lines need external generators and are rejected explicitly.
+bool Scene::read_rad_text(const std::string& path) {
+    if (!path.empty() && path[0] == '!') {
+        error = "scene input from command \"" + path + "\" is not supported (freeze the octree with oconv -f)";
+        return false;
+    }
+    std::ifstream f(path);
+    if (!f) { error = "cannot open scene file \"" + path + "\""; return false; }
+    std::string text((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    // strip comments (# to end of line) and reject commands
+    std::string clean; clean.reserve(text.size());
+    bool bol = true;
+    for (size_t i = 0; i < text.size(); i++) {
+        char c = text[i];
+        if (c == '#') { while (i < text.size() && text[i] != '\n') i++; clean.push_back('\n'); bol = true; continue; }
+        if (bol && c == '!') {
+            error = "(" + path + "): \"!command\" lines are not supported (freeze the octree with oconv -f)";
+            return false;
+        }
+        if (c == '\n') bol = true; else if (!isspace((unsigned char)c)) bol = false;
+        clean.push_back(c);
+    }
+    std::istringstream in(clean);
+    std::string mod, typ, name;
+    while (in >> mod) {
+        if (!(in >> typ >> name)) { error = "(" + path + "): unexpected EOF"; return false; }
+        Object o;
+        o.tname = typ; o.otype = ot_from_name(typ); o.name = name;
+        if (mod == "void") o.omod = -1;
+        else {
+            auto mt = modtab.find(mod);
+            o.omod = (mt == modtab.end()) ? -1 : mt->second;
+            if (o.omod < 0) { error = "(" + path + "): undefined modifier \"" + mod + "\" for " + typ + " \"" + name + "\""; return false; }
+        }
+        if (o.otype == OT_ALIAS) {       // alias: "mod alias name target"
+            std::string tgt;
+            if (!(in >> tgt)) { error = "(" + path + "): bad alias"; return false; }
+            o.sargs.push_back(tgt);
+            modtab[o.name] = (int)objs.size();
+            objs.push_back(std::move(o));
+            continue;
+        }
+        long n;
+        if (!(in >> n) || n < 0) { error = "(" + path + "): bad arguments for " + typ + " \"" + name + "\""; return false; }
+        for (long i = 0; i < n; i++) { std::string s; in >> s; o.sargs.push_back(s); }
+        if (!(in >> n) || n != 0) { error = "(" + path + "): bad integer arguments for \"" + name + "\""; return false; }
+        if (!(in >> n) || n < 0) { error = "(" + path + "): bad real arguments for \"" + name + "\""; return false; }
+        o.fargs.resize(n);
+        for (long i = 0; i < n; i++) {
+            std::string s; in >> s;
+            char* ep; o.fargs[i] = strtod(s.c_str(), &ep);
+            if (ep == s.c_str()) { error = "(" + path + "): bad real argument for \"" + name + "\""; return false; }
+        }
+        if (ot_is_modifier(o.otype)) modtab[o.name] = (int)objs.size();
+        objs.push_back(std::move(o));
+    }
+    return true;
+}
+
+void Scene::index_modifiers() {
+    modtab.clear();
+    for (int i = 0; i < (int)objs.size(); i++)
+        if (ot_is_modifier(objs[i].otype)) modtab[objs[i].name] = i;   // last wins
+}
+
+int Scene::lastmod(int before, const std::string& name) const {
+    auto it = modtab.find(name);
+    int i = (it == modtab.end()) ? -1 : it->second;
+    if (before < 0 || i < before) return i;
+    for (i = before; i-- > 0;)
+        if (ot_is_modifier(objs[i].otype) && objs[i].name == name) return i;
+    return -1;
+}
+
+// initotypes.c:112-145
+int Scene::findmaterial(int oi) const {
+    int obj = -1;
+    int guard = 0;
+    while (!ot_is_material(objs[oi].otype)) {
+        if (++guard > 10000) return -1;
+        const Object* o = &objs[oi];
+        if (o->otype == OT_ALIAS && !o->sargs.empty()) {
+            int ao = oi;
+            if (obj < 0) obj = oi;
+            do {
+                if (objs[ao].sargs.empty()) obj = objs[ao].omod;
+                else obj = lastmod(obj, objs[ao].sargs[0]);
+                if (obj < 0) return -1;
+                ao = obj;
+            } while (objs[ao].otype == OT_ALIAS && ++guard < 10000);
+            if (ot_is_material(objs[ao].otype)) return ao;
+        }
+        if (o->omod < 0) {
+            if (o->otype == OT_MIXTURE) break;
+            return -1;
+        }
+        obj = o->omod;
+        oi = obj;
+    }
+    return oi;
+}
+
+// ------------------------------------------------------------- flatten ----
+static double vnormalize(double v[3]) {     // common/fvect.c:130-157
+    double d = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    if (d == 0.0) return 0.0;
+    double len;
+    if ((d <= 1.0 + FTINY) & (d >= 1.0 - FTINY)) {
+        len = 0.5 + 0.5 * d;
+        d = 2.0 - len;
+    } else {
+        len = sqrt(d);
+        d = 1.0 / len;
+    }
+    v[0] *= d; v[1] *= d; v[2] *= d;
+    return len;
+}
+static void vcross(double r[3], const double a[3], const double b[3]) {
+    double t[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    r[0] = t[0]; r[1] = t[1]; r[2] = t[2];
+}
+static double vdot(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// deterministic getperpendicular (fvect.c:159-196 with randomize=0)
+static bool getperp(double vp[3], const double v[3]) {
+    double v1[3] = {0, 0, 0};
+    int i;
+    for (i = 3; i--;)
+        if ((-0.6 < v[i]) & (v[i] < 0.6)) break;
+    if (i < 0) return false;
+    v1[i] = 1.0;
+    vcross(vp, v1, v);
+    return vnormalize(vp) > 0.0;
+}
+
+static void mat4_ident(double m[4][4]) {
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) m[i][j] = (i == j);
+}
+static void mat4_mul(double a[4][4], double b[4][4], double c[4][4]) {   // a = b*c
+    double t[4][4];
+    for (int i = 4; i--;)
+        for (int j = 4; j--;)
+            t[i][j] = b[i][0] * c[0][j] + b[i][1] * c[1][j] + b[i][2] * c[2][j] + b[i][3] * c[3][j];
+    memcpy(a, t, sizeof(t));
+}
+
+static size_t geom_alloc(FlatScene& fs, size_t n) {
+    if (fs.geom.size() & 1) fs.geom.push_back(0.0);   // keep 16-byte alignment
+    size_t off = fs.geom.size();
+    fs.geom.resize(off + n, 0.0);
+    return off;
+}
+
+// common/face.c:35-106 getface() -> plane + 2-D projected vertices
+static void flatten_face(const Object& o, FlatScene& fs, int32_t hdr[4], std::string& warn) {
+    int nf = (int)o.fargs.size();
+    if (nf < 9 || nf % 3) { hdr[0] = PK_UNSUPPORTED; warn = "bad # arguments for polygon \"" + o.name + "\""; return; }
+    const double* va = o.fargs.data();
+    int nv = nf / 3;
+    auto V = [&](int i) { return va + 3 * i; };
+    auto dist2 = [&](const double* a, const double* b) {
+        double d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
+        return d0 * d0 + d1 * d1 + d2 * d2;
+    };
+    if (nv > 3 && dist2(V(0), V(nv - 1)) <= FTINY * FTINY) nv--;
+    double norm[3] = {0, 0, 0}, v1[3], v2[3], v3[3];
+    for (int k = 0; k < 3; k++) v1[k] = V(1)[k] - V(0)[k];
+    for (int i = 2; i < nv; i++) {
+        for (int k = 0; k < 3; k++) v2[k] = V(i)[k] - V(0)[k];
+        vcross(v3, v1, v2);
+        norm[0] += v3[0]; norm[1] += v3[1]; norm[2] += v3[2];
+        for (int k = 0; k < 3; k++) v1[k] = v2[k];
+    }
+    double area = vnormalize(norm);
+    double offset = 0.0;
+    int ax = 0;
+    if (area == 0.0) {
+        warn = "zero area for polygon \"" + o.name + "\"";
+        norm[0] = norm[1] = norm[2] = 0.0;
+    } else {
+        offset = vdot(norm, V(0));
+        for (int i = 1; i < nv; i++) offset += vdot(norm, V(i));
+        offset /= (double)nv;
+        ax = (fabs(norm[1]) > fabs(norm[0]));
+        if (fabs(norm[2]) > fabs(norm[ax])) ax = 2;
+    }
+    if (nv > 65535) { hdr[0] = PK_UNSUPPORTED; warn = "too many vertices"; return; }
+    int xi = (ax + 1) % 3, yi = (xi + 1) % 3;
+    size_t off = geom_alloc(fs, 4 + 2 * (size_t)nv);
+    double* g = &fs.geom[off];
+    g[0] = norm[0]; g[1] = norm[1]; g[2] = norm[2]; g[3] = offset;
+    for (int i = 0; i < nv; i++) { g[4 + 2 * i] = V(i)[xi]; g[5 + 2 * i] = V(i)[yi]; }
+    hdr[0] = PK_FACE | (ax << 10) | (nv << 16);
+    hdr[3] = (int32_t)off;
+}
+
+// rt/sphere.c:27-36
+static void flatten_sphere(const Object& o, FlatScene& fs, int32_t hdr[4], std::string& warn) {
+    if (o.fargs.size() != 4) { hdr[0] = PK_UNSUPPORTED; warn = "bad # arguments for sphere \"" + o.name + "\""; return; }
+    int kind = (o.otype == OT_SPHERE) ? PK_SPHERE : PK_BUBBLE;
+    double r = o.fargs[3];
+    if (r < -FTINY) { kind = (kind == PK_SPHERE) ? PK_BUBBLE : PK_SPHERE; r = -r; }
+    else if (r <= FTINY) { hdr[0] = PK_UNSUPPORTED; warn = "zero radius for sphere \"" + o.name + "\""; return; }
+    size_t off = geom_alloc(fs, 4);
+    double* g = &fs.geom[off];
+    g[0] = o.fargs[0]; g[1] = o.fargs[1]; g[2] = o.fargs[2]; g[3] = r;
+    hdr[0] = kind; hdr[3] = (int32_t)off;
+}
+
+// common/cone.c:44-153 getcone() + :171-218 conexform()
+static void flatten_cone(const Object& o, FlatScene& fs, int32_t hdr[4], std::string& warn) {
+    int ot = o.otype;
+    std::vector<double> ca = o.fargs;
+    int p0, p1, r0, r1;
+    if (ot == OT_CYLINDER || ot == OT_TUBE) {
+        if (ca.size() != 7) goto argerr;
+        if (ca[6] < -FTINY) { ot = (ot == OT_CYLINDER) ? OT_TUBE : OT_CYLINDER; ca[6] = -ca[6]; }
+        else if (ca[6] <= FTINY) goto raderr;
+        p0 = 0; p1 = 3; r0 = r1 = 6;
+    } else {
+        if (ca.size() != 8) goto argerr;
+        int sgn0 = ca[6] < -FTINY ? -1 : ca[6] > FTINY ? 1 : 0;
+        int sgn1 = ca[7] < -FTINY ? -1 : ca[7] > FTINY ? 1 : 0;
+        if (sgn0 + sgn1 == 0) goto raderr;
+        if ((sgn0 < 0) | (sgn1 < 0)) {
+            if (ot == OT_RING) goto raderr;
+            ot = (ot == OT_CONE) ? OT_CUP : OT_CONE;
+        }
+        ca[6] = ca[6] * sgn0; ca[7] = ca[7] * sgn1;
+        if (ca[7] - ca[6] > FTINY) {
+            if (ot == OT_RING) p0 = p1 = 0; else { p0 = 0; p1 = 3; }
+            r0 = 6; r1 = 7;
+        } else if (ca[6] - ca[7] > FTINY) {
+            if (ot == OT_RING) p0 = p1 = 0; else { p0 = 3; p1 = 0; }
+            r0 = 7; r1 = 6;
+        } else {
+            if (ot == OT_RING) goto raderr;
+            ot = (ot == OT_CONE) ? OT_CYLINDER : OT_TUBE;
+            p0 = 0; p1 = 3; r0 = r1 = 6;
+        }
+    }
+    {
+        double ad[3], al, sl;
+        if (ot == OT_RING) { ad[0] = ca[3]; ad[1] = ca[4]; ad[2] = ca[5]; }
+        else for (int k = 0; k < 3; k++) ad[k] = ca[p1 + k] - ca[p0 + k];
+        al = vnormalize(ad);
+        if (al == 0.0) { hdr[0] = PK_UNSUPPORTED; warn = "unknown orientation for \"" + o.name + "\""; return; }
+        if (ot == OT_RING) { al = 0.0; sl = ca[r1] - ca[r0]; }
+        else if (ot == OT_CONE || ot == OT_CUP) { sl = ca[7] - ca[6]; sl = sqrt(sl * sl + al * al); }
+        else sl = al;
+        // conexform
+        double tm[4][4], m4[4][4], d;
+        mat4_ident(tm);
+        if (r0 == r1) d = 0.0; else d = ca[r0] / (ca[r1] - ca[r0]);
+        for (int i = 0; i < 3; i++) tm[3][i] = d * (ca[p1 + i] - ca[p0 + i]) - ca[p0 + i];
+        mat4_ident(m4);
+        d = ad[1] * ad[1] + ad[2] * ad[2];
+        if (d <= FTINY * FTINY) {
+            m4[0][0] = 0.0; m4[0][2] = ad[0]; m4[2][0] = -ad[0]; m4[2][2] = 0.0;
+        } else {
+            d = sqrt(d);
+            m4[0][0] = d; m4[1][0] = -ad[0] * ad[1] / d; m4[2][0] = -ad[0] * ad[2] / d;
+            m4[1][1] = ad[2] / d; m4[2][1] = -ad[1] / d;
+            m4[0][2] = ad[0]; m4[1][2] = ad[1]; m4[2][2] = ad[2];
+        }
+        mat4_mul(tm, tm, m4);
+        if ((p0 != p1) & (r0 != r1)) {
+            mat4_ident(m4);
+            m4[2][2] = (ca[r1] - ca[r0]) / al;
+            mat4_mul(tm, tm, m4);
+        }
+        size_t off = geom_alloc(fs, 24);
+        double* g = &fs.geom[off];
+        g[0] = ad[0]; g[1] = ad[1]; g[2] = ad[2]; g[3] = al;
+        g[4] = ca[p0]; g[5] = ca[p0 + 1]; g[6] = ca[p0 + 2]; g[7] = sl;
+        g[8] = ca[r0]; g[9] = ca[r1]; g[10] = 0; g[11] = 0;
+        for (int i = 0; i < 4; i++) for (int j = 0; j < 3; j++) g[12 + i * 3 + j] = tm[i][j];
+        int kind = ot == OT_CONE ? PK_CONE : ot == OT_CUP ? PK_CUP : ot == OT_CYLINDER ? PK_CYL
+                 : ot == OT_TUBE ? PK_TUBE : PK_RING;
+        hdr[0] = kind; hdr[3] = (int32_t)off;
+        return;
+    }
+argerr:
+    hdr[0] = PK_UNSUPPORTED; warn = "bad # arguments for \"" + o.name + "\""; return;
+raderr:
+    hdr[0] = PK_UNSUPPORTED; warn = "illegal radii for \"" + o.name + "\""; return;
+}
+
+// initotypes.c:45-61,70 + otspecial.h:13-20 istransp()
+static bool mat_is_transp(const Object& m) {
+    switch (m.otype) {
+    case OT_TRANS: case OT_TRANS2: case OT_DIELECTRIC: case OT_INTERFACE:
+    case OT_MIST: case OT_GLASS: case OT_ABSDF:
+        return true;
+    }
+    if (m.tname == "WGMDfunc" && m.sargs.size() > 5 && m.sargs[5] != "0") return true;
+    if (m.tname == "BRTDfunc" && m.sargs.size() > 5 &&
+        (m.sargs[3] != "0" || m.sargs[4] != "0" || m.sargs[5] != "0")) return true;
+    return false;
+}
+
+bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
+    const int n = (int)sc.objs.size();
+    fs = FlatScene();
+    fs.nodes = sc.nodes;
+    fs.leafpool = sc.leafpool;
+    fs.objhdr.assign((size_t)n * 4, 0);
+    std::vector<int> matslot(n, -2);    // object -> material slot (-2 unknown)
+    auto note_unsupported = [&](const std::string& s) {
+        if (fs.unsupported_note.empty()) fs.unsupported_note = s;
+    };
+    // material slot for a material object (by object index)
+    std::function<int(int)> slot_of;   // forward decl via std::function
+    slot_of = [&](int mi) -> int {
+        if (mi < 0) return -1;
+        if (matslot[mi] != -2) return matslot[mi];
+        const Object& m = sc.objs[mi];
+        MatRec r; memset(&r, 0, sizeof(r));
+        r.obj = mi; r.alt = -1;
+        r.nargs = (int)std::min<size_t>(m.fargs.size(), 8);
+        for (int i = 0; i < r.nargs; i++) r.a[i] = (float)m.fargs[i];
+        auto need = [&](size_t k) {
+            if (m.fargs.size() != k) {
+                r.kind = MK_UNSUPPORTED;
+                note_unsupported("bad number of arguments for " + m.tname + " \"" + m.name + "\"");
+                return false;
+            }
+            return true;
+        };
+        switch (m.otype) {
+        case OT_PLASTIC: r.kind = MK_PLASTIC; need(5); break;
+        case OT_METAL:   r.kind = MK_METAL; need(5); break;
+        case OT_TRANS:   r.kind = MK_TRANS; need(7); break;
+        case OT_GLASS:
+            r.kind = MK_GLASS;
+            if (m.fargs.size() != 3 && m.fargs.size() != 4) {
+                r.kind = MK_UNSUPPORTED; note_unsupported("bad arguments for glass \"" + m.name + "\"");
+            }
+            break;
+        case OT_LIGHT: r.kind = MK_LIGHT; need(3); break;
+        case OT_GLOW:  r.kind = MK_GLOW; need(4); break;
+        case OT_ILLUM: r.kind = MK_ILLUM; need(3); break;
+        case OT_SPOTLIGHT: r.kind = MK_SPOT; need(7); break;
+        default:
+            r.kind = MK_UNSUPPORTED;
+            note_unsupported("unsupported material type " + m.tname + " \"" + m.name + "\"");
+        }
+        // any pattern/texture/mixture under the material poisons it (raytexture)
+        for (int q = m.omod, g = 0; q >= 0 && g < 10000; q = sc.objs[q].omod, g++) {
+            int t = sc.objs[q].otype;
+            if (t == OT_ALIAS && sc.objs[q].sargs.empty()) continue;
+            r.flags |= 1;
+            note_unsupported("unsupported modifier type " + sc.objs[q].tname + " \"" + sc.objs[q].name +
+                             "\" (under " + m.tname + " \"" + m.name + "\")");
+        }
+        int slot = (int)fs.mats.size();
+        matslot[mi] = slot;
+        fs.mats.push_back(r);
+        if (m.otype == OT_ILLUM && !m.sargs.empty() && m.sargs[0] != "void") {
+            int alt = sc.lastmod(mi, m.sargs[0]);
+            int am = alt >= 0 ? sc.findmaterial(alt) : -1;
+            int as = slot_of(am);
+            fs.mats[slot].alt = as;
+            if (alt >= 0 && am != alt) {
+                fs.mats[slot].flags |= 1;
+                note_unsupported("illum \"" + m.name + "\" alternate is not a plain material");
+            }
+        }
+        return slot;
+    };
+
+    for (int i = 0; i < n; i++) {
+        const Object& o = sc.objs[i];
+        int32_t* hdr = &fs.objhdr[(size_t)i * 4];
+        hdr[0] = PK_NONE; hdr[1] = o.omod; hdr[2] = -1; hdr[3] = 0;
+        if (ot_is_volume(o.otype)) {
+            hdr[0] = PK_UNSUPPORTED;
+            fs.nsurf_unsupported++;
+            note_unsupported("unsupported object type " + o.tname + " \"" + o.name + "\"");
+            continue;
+        }
+        if (!ot_is_surface(o.otype)) continue;
+        std::string warn;
+        switch (o.otype) {
+        case OT_POLYGON: flatten_face(o, fs, hdr, warn); break;
+        case OT_SPHERE: case OT_BUBBLE: flatten_sphere(o, fs, hdr, warn); break;
+        case OT_CONE: case OT_CUP: case OT_CYLINDER: case OT_TUBE: case OT_RING:
+            flatten_cone(o, fs, hdr, warn); break;
+        case OT_SOURCE: hdr[0] = PK_NONE; break;       // never in the octree
+        }
+        if (!warn.empty()) fs.warnings.push_back(warn);
+        if ((hdr[0] & 0xff) == PK_UNSUPPORTED) { fs.nsurf_unsupported++; note_unsupported(warn); }
+        int flags = 0;
+        if (o.omod >= 0) {
+            int mi = sc.findmaterial(i);
+            if (mi >= 0) {
+                flags |= PF_HASMAT;
+                if (mat_is_transp(sc.objs[mi])) flags |= PF_TRANSP;
+                hdr[2] = slot_of(mi);
+                // the chain between the surface and its material must be plain
+                // (aliases only); patterns in between poison the material use
+                for (int q = o.omod, g = 0; q >= 0 && q != mi && g < 10000; g++) {
+                    int t = sc.objs[q].otype;
+                    if (t != OT_ALIAS) {
+                        fs.mats[hdr[2]].flags |= 1;
+                        note_unsupported("unsupported modifier type " + sc.objs[q].tname + " \"" +
+                                         sc.objs[q].name + "\"");
+                        q = sc.objs[q].omod;
+                    } else if (sc.objs[q].sargs.empty()) q = sc.objs[q].omod;
+                    else break;   // alias jumps: resolved by findmaterial
+                }
+            }
+        }
+        hdr[0] |= flags << 8;
+    }
+
+    // ---- sources: rt/source.c:46-142 marksources(), srcsupp.c:155-179 ----
+    for (int i = 0; i < n; i++) {
+        const Object& o = sc.objs[i];
+        if (!ot_is_surface(o.otype) || o.omod < 0) continue;
+        int mi = sc.findmaterial(i);
+        if (mi < 0) continue;
+        const Object& m = sc.objs[mi];
+        if (m.otype == OT_ANTIMATTER) { note_unsupported("unsupported material type antimatter \"" + m.name + "\""); continue; }
+        if (!ot_is_light(m.otype)) continue;
+        size_t want = m.otype == OT_GLOW ? 4 : m.otype == OT_SPOTLIGHT ? 7 : 3;
+        if (m.fargs.size() != want) { err = "bad # arguments for " + m.tname + " \"" + m.name + "\""; return false; }
+        if (m.fargs[0] <= FTINY && m.fargs[1] <= FTINY && m.fargs[2] <= FTINY) continue;
+        if (m.otype == OT_GLOW && o.otype != OT_SOURCE && m.fargs[3] <= FTINY) continue;
+        SrcRec s; memset(&s, 0, sizeof(s));
+        s.so = i; s.mat = slot_of(mi);
+        s.val[0] = (float)m.fargs[0]; s.val[1] = (float)m.fargs[1]; s.val[2] = (float)m.fargs[2];
+        if (o.otype == OT_SOURCE) {          // ssetsrc()
+            if (o.fargs.size() != 4) { err = "bad arguments for source \"" + o.name + "\""; return false; }
+            s.flags |= SF_DISTANT | SF_CIRC;
+            s.sloc[0] = o.fargs[0]; s.sloc[1] = o.fargs[1]; s.sloc[2] = o.fargs[2];
+            if (vnormalize(s.sloc) == 0.0) { err = "zero direction for source \"" + o.name + "\""; return false; }
+            double theta = PI / 180.0 / 2.0 * o.fargs[3];
+            if (theta <= FTINY) { err = "zero size for source \"" + o.name + "\""; return false; }
+            s.ss2 = 2.0 * PI * (1.0 - cos(theta));
+            s.srad = sqrt(s.ss2 / PI);
+            // setflatss() with deterministic perpendicular (rand_samp differs
+            // only in the orientation of the jitter frame)
+            double snorm[3] = {s.sloc[0], s.sloc[1], s.sloc[2]};
+            getperp(s.ss[0], snorm);
+            double mult = .5 * sqrt(s.ss2);
+            for (int k = 0; k < 3; k++) s.ss[0][k] *= mult;
+            vcross(s.ss[1], snorm, s.ss[0]);
+            s.ss[2][0] = s.ss[2][1] = s.ss[2][2] = 0.0;
+        } else {
+            // local emitters need fsetsrc/sphsetsrc/rsetsrc/cylsetsrc + source
+            // partitioning; not built yet -> explicit rejection when used.
+            s.flags |= SF_SKIP;
+            s.mat = slot_of(mi);
+            fs.mats[s.mat].flags |= 2;       // "local source not supported"
+            note_unsupported("local light source \"" + o.name + "\" (" + m.tname + " on " + o.tname +
+                             ") is not supported yet; only distant sources are");
+        }
+        if (m.otype == OT_GLOW) {
+            s.flags |= SF_PROX;
+            s.prox = m.fargs[3];
+            if (s.flags & SF_DISTANT) s.flags |= SF_SKIP;
+        } else if (m.otype == OT_SPOTLIGHT) {
+            s.flags |= SF_SPOT;
+            note_unsupported("spotlight \"" + m.name + "\" is not supported");
+            fs.mats[s.mat].flags |= 1;
+        }
+        fs.srcs.push_back(s);
+    }
+    return true;
+}
+
+}  // namespace rb

@@ -1,0 +1,132 @@
+// rb_scene.hpp -- host-side scene database for the B200 ray-tracing hot path.
+//
+// Replaces, for this path only, the reference's scene loader:
+//   .oct reader            src/radiance/common/readoct.c:35-141,195-218
+//   frozen scene decoder   src/radiance/common/sceneio.c:20-109
+//   portable int/float     src/radiance/common/portio.c:93-152
+//   modifier resolution    src/radiance/rt/initotypes.c:112-145 (findmaterial),
+//                          src/radiance/common/modobject.c:59-89 (lastmod)
+//   face / cone setup      src/radiance/common/face.c:35-106, cone.c:44-218
+// The output is a set of flat arrays ready to be copied to HBM (rb_device.hpp).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <unordered_map>
+
+namespace rb {
+
+// Object types we know by name (index into the file's own type table is
+// remapped to these at load; everything else is OT_OTHER and is rejected
+// lazily, only if a ray ever needs it).
+enum OType : int {
+    OT_OTHER = 0,
+    // surfaces
+    OT_POLYGON, OT_CONE, OT_SPHERE, OT_RING, OT_CYLINDER, OT_CUP, OT_BUBBLE,
+    OT_TUBE, OT_SOURCE, OT_INSTANCE, OT_MESH,
+    // modifiers
+    OT_ALIAS, OT_PLASTIC, OT_METAL, OT_GLASS, OT_TRANS, OT_GLOW, OT_LIGHT,
+    OT_ILLUM, OT_SPOTLIGHT,
+    // known but unsupported material / pattern families (for messages + flags)
+    OT_DIELECTRIC, OT_INTERFACE, OT_MIST, OT_ABSDF, OT_TRANS2, OT_ANTIMATTER,
+    OT_OTHER_MATERIAL, OT_PATTERN, OT_TEXTURE, OT_MIXTURE,
+    OT_NTYPES
+};
+
+bool ot_is_surface(int t);
+bool ot_is_volume(int t);
+bool ot_is_material(int t);
+bool ot_is_light(int t);
+bool ot_is_modifier(int t);
+int  ot_from_name(const std::string& s);
+
+struct Object {
+    int omod = -1;              // modifier object index, -1 = void
+    int otype = OT_OTHER;
+    std::string tname;          // type name as in the file
+    std::string name;
+    std::vector<std::string> sargs;
+    std::vector<double> fargs;
+};
+
+struct Scene {
+    std::vector<std::string> header;   // info header lines (without FORMAT=)
+    double cuorg[3] = {0, 0, 0};
+    double cusize = 0;
+    bool frozen = true;
+    std::vector<std::string> srcfiles;
+    std::vector<Object> objs;
+    // octree: children words, 8 per node.  word >= 0: node index;
+    // -1: empty; <= -2: leaf set at leafpool[-(w)-2] = count, ids ascending.
+    int root = -1;
+    std::vector<int> nodes;
+    std::vector<int> leafpool;
+    int maxdepth = 0;
+    std::string error;
+
+    bool load_octree(const std::string& path);
+    // last modifier named `name` defined before object `before` (-1: any)
+    int lastmod(int before, const std::string& name) const;
+    // findmaterial(): returns object index of the actual material or -1
+    int findmaterial(int obj) const;
+    std::unordered_map<std::string, int> modtab;   // name -> last modifier idx
+    void index_modifiers();
+    bool read_rad_text(const std::string& path);
+};
+
+// ---- flattened (device-ready) tables -------------------------------------
+
+// per-object header, 16 bytes: x = type | flags<<8 | nv<<16 ; y = omod ;
+// z = material slot (-1 none) ; w = offset into geom[] (doubles)
+enum : int { PF_TRANSP = 1, PF_HASMAT = 2 };
+enum : int {            // device primitive kinds (x & 0xff)
+    PK_NONE = 0, PK_FACE, PK_SPHERE, PK_BUBBLE, PK_CONE, PK_CUP, PK_CYL,
+    PK_TUBE, PK_RING, PK_UNSUPPORTED
+};
+
+// material kinds on device
+enum : int {
+    MK_NONE = 0, MK_PLASTIC, MK_METAL, MK_TRANS, MK_GLASS, MK_LIGHT, MK_GLOW,
+    MK_ILLUM, MK_SPOT, MK_UNSUPPORTED
+};
+
+struct MatRec {          // 64 bytes
+    int kind;
+    int flags;           // bit0: chain has unsupported pattern/texture
+    int obj;             // object index of the material
+    int nargs;
+    float a[8];          // real args (as given)
+    int alt;             // illum: alternate material slot (-1 = void/none)
+    int pad[3];
+};
+
+struct SrcRec {          // distant & local sources (source.h SRCREC subset)
+    double sloc[3];      // direction (distant) or position
+    double ss2;          // solid angle or projected area
+    double ss[3][3];     // u, v, w axes (size vectors)
+    double srad;         // maximum source radius
+    double prox;         // glow proximity
+    float  val[3];       // emitted radiance (material RGB)
+    int    so;           // source object index
+    int    flags;        // SF_*
+    int    mat;          // material slot
+    int    pad;
+};
+enum : int { SF_DISTANT = 1, SF_SKIP = 2, SF_PROX = 4, SF_SPOT = 8, SF_FLAT = 16,
+             SF_CIRC = 32, SF_CYL = 64, SF_FOLLOW = 128 };
+
+struct FlatScene {
+    std::vector<int32_t> objhdr;     // 4 ints per object
+    std::vector<double>  geom;       // packed geometry records
+    std::vector<MatRec>  mats;
+    std::vector<SrcRec>  srcs;
+    std::vector<int>     nodes;      // same encoding as Scene
+    std::vector<int>     leafpool;
+    int nsurf_unsupported = 0;
+    std::string unsupported_note;    // first unsupported thing, for messages
+    std::vector<std::string> warnings;
+};
+
+bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err);
+
+}  // namespace rb

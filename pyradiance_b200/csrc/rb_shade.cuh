@@ -1,0 +1,691 @@
+// rb_shade.cuh -- material shading, ray spawning and contribution accumulation
+// on the device, written as a FORWARD expansion of the reference's recursive
+// ray tree: every spawned ray carries the product of rcoef from the primary
+// ray down to itself, so the value/coefficients the reference gathers on the
+// way back up its recursion (rt/raytrace.c:407-442 raycontrib, and the
+// saddscolor() chains in the materials) are added where a ray ends instead.
+//
+// Restated reference functions:
+//   rayorigin                 src/radiance/rt/raytrace.c:39-135
+//   raytrans / rayshade       src/radiance/rt/raytrace.c:182-256
+//   sourcehit                 src/radiance/rt/source.c:316-377
+//   m_light (+macros)         src/radiance/rt/source.c:678-793
+//   m_normal + dirnorm        src/radiance/rt/normal.c:71-360 (gaussamp :363-495)
+//   m_glass                   src/radiance/rt/glass.c:46-165
+//   multambient (aa=0)        src/radiance/rt/ambient.c:229-297
+//   samp_hemi / ambsample     src/radiance/rt/ambcomp.c:350-422,177-248
+//   direct / srcray / nextssamp  src/radiance/rt/source.c:219-257,398-556, srcsamp.c:36-144
+//   trace_contrib             src/radiance/rt/rcontrib.c:272-317
+//   square2disk               src/radiance/common/disk2square.c:43-79
+//   getperpendicular          src/radiance/common/fvect.c:159-196
+#pragma once
+#include <cooperative_groups.h>
+#include "rb_device.cuh"
+#include "rb_bins.cuh"
+#include "rb_geom.cuh"
+
+namespace rb {
+namespace cg = cooperative_groups;
+
+// ---------------------------------------------------------------- RNG ------
+// Counter-based: a 64-bit path key identifies a ray in the tree (derived from
+// the global record index, so results do not depend on batch or GPU count);
+// dimension d of a ray's random vector is mix64(key + d*C).
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z += 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ double rnd01(unsigned long long key, unsigned dim) {
+    return (double)(mix64(key + (unsigned long long)dim * 0xd1342543de82ef95ULL) >> 11) *
+           (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ unsigned long long child_key(unsigned long long key, unsigned long long idx) {
+    return mix64(key ^ mix64(idx + 0x632be59bd9b4e019ULL));
+}
+
+// ------------------------------------------------------------- context -----
+struct WaveArgs {
+    DScene S;
+    DParams P;
+    const DBinSpec* bins;
+    int nbinspecs;
+    const QRay* qin; unsigned nin;
+    QRay* qout; unsigned qcap;
+    QHemi* hout; unsigned hcap;
+    double* acc;            // [rows][ncols][3] contribution accumulators (or null)
+    int ncols;
+    double* vacc;           // [rows][3] value accumulators (or null)
+    unsigned row0;          // first row of this batch
+    RayResult* res;         // per-row primary-hit report (or null)
+    DCounters* C;
+    int inline_hemi_max;    // hemispheres with n*n <= this are expanded in-thread
+};
+
+struct RayCtx {             // the ray being shaded (a subset of RAY, rt/ray.h:48-83)
+    double org[3], dir[3], rmax;
+    double rot, rod, rop[3], ron[3];
+    float coef[3];          // cumulative coefficient incl. own rcoef
+    float rweight;
+    unsigned row;
+    int crtype, rlvl, rdepth, rsrc;
+    int robj;               // object hit (-1: none / fake irradiance hit)
+    bool flat;              // isflat(ro->otype)
+    unsigned long long key;
+    unsigned nchild;        // children spawned so far (for key derivation)
+};
+
+__device__ __forceinline__ float max3(const float c[3]) { return fmaxf(c[0], fmaxf(c[1], c[2])); }
+
+__device__ __forceinline__ unsigned pack_info(int crtype, int rlvl, int rdepth) {
+    return (unsigned)(crtype & 0x3ff) | ((unsigned)(rlvl & 0x3f) << 10) | ((unsigned)(rdepth & 0x3f) << 16);
+}
+
+// warp-aggregated slot reservation
+__device__ __forceinline__ unsigned reserve_slot(unsigned* ctr) {
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(ctr, g.size());
+    base = g.shfl(base, 0);
+    return base + g.thread_rank();
+}
+
+// raytrace.c:39-135.  `rc` is the child's coefficient w.r.t. the parent (may be
+// rescaled by Russian roulette); has_rc=false stands for rc==NULL.
+__device__ bool rayorigin(const DParams& P, RayCtx& par, int rt, float rc[3], bool has_rc, QRay& q) {
+    float rw = 1.0f;
+    if (has_rc) { rw = max3(rc); if (rw > 1.0f) rw = 1.0f; }
+    else rc[0] = rc[1] = rc[2] = 1.0f;
+    if (par.rot >= RB_FHUGE * .99) return false;        // illegal continuation
+    int rlvl = par.rlvl, rsrc = par.rsrc;
+    double rmax;
+    if (rt & RT_RAYREFL) {
+        rlvl++;
+        if (rsrc >= 0) rsrc = -1;
+        rmax = 0.0;
+    } else
+        rmax = (par.rmax > RB_FTINY) * (par.rmax - par.rot);
+    int crtype = par.crtype | rt;
+    float rweight = par.rweight * rw;
+    unsigned long long key = child_key(par.key, par.nchild++);
+    if (rweight <= 0.0f) return false;
+    if (!(crtype & RT_SHADOW)) {
+        if ((P.maxdepth <= 0) & has_rc) {               // Russian roulette
+            if ((P.maxdepth < 0) & (rlvl > -P.maxdepth)) return false;
+            if (rweight < P.minweight) {
+                if (rnd01(key, 7) > (double)(rweight / P.minweight)) return false;
+                float s = P.minweight / rweight;
+                rc[0] *= s; rc[1] *= s; rc[2] *= s;
+                rweight = P.minweight;
+            }
+        } else if (!((rweight >= P.minweight) & (rlvl <= abs(P.maxdepth))))
+            return false;
+    }
+    q.org[0] = par.rop[0]; q.org[1] = par.rop[1]; q.org[2] = par.rop[2];
+    q.rmax = rmax;
+    q.coef[0] = par.coef[0] * rc[0]; q.coef[1] = par.coef[1] * rc[1]; q.coef[2] = par.coef[2] * rc[2];
+    q.rweight = rweight;
+    q.row = par.row;
+    q.info = pack_info(crtype, rlvl, par.rdepth);
+    q.rsrc = rsrc;
+    q.key_lo = (unsigned)key; q.key_hi = (unsigned)(key >> 32);
+    q.pad = 0;
+    return true;
+}
+
+__device__ __forceinline__ void push_ray(const WaveArgs& A, const QRay& q) {
+    unsigned slot = reserve_slot(&A.C->nq_out);
+    if (slot >= A.qcap) { A.C->overflow = 1; return; }
+    A.qout[slot] = q;
+}
+
+// fvect.c:130-157
+__device__ __forceinline__ double normalize3(double v[3]) {
+    double d = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    if (d == 0.0) return 0.0;
+    double len;
+    if ((d <= 1.0 + RB_FTINY) & (d >= 1.0 - RB_FTINY)) { len = 0.5 + 0.5 * d; d = 2.0 - len; }
+    else { len = sqrt(d); d = 1.0 / len; }
+    v[0] *= d; v[1] *= d; v[2] *= d;
+    return len;
+}
+
+// disk2square.c:43-79
+__device__ __forceinline__ void square2disk(double ds[2], double seedx, double seedy) {
+    double phi, r;
+    double a = 2. * seedx - 1;
+    double b = 2. * seedy - 1;
+    const double PI4 = RB_PI / 4.;
+    if (a > -b) {
+        if (a > b) { r = a; phi = PI4 * (b / a); }
+        else { r = b; phi = PI4 * (2. - (a / b)); }
+    } else {
+        if (a < b) { r = -a; phi = PI4 * (4. + (b / a)); }
+        else { r = -b; phi = (b != 0.) ? PI4 * (6. - (a / b)) : 0.; }
+    }
+    r *= 0.9999999999999;
+    double s, c;
+    sincos(phi, &s, &c);
+    ds[0] = r * c; ds[1] = r * s;
+}
+
+// fvect.c:159-196 with randomize=1 (random numbers from the path key)
+__device__ __forceinline__ bool getperpendicular_rand(double vp[3], const double v[3],
+                                                       unsigned long long key) {
+    double v1[3];
+    v1[0] = 0.5 - rnd01(key, 11); v1[1] = 0.5 - rnd01(key, 12); v1[2] = 0.5 - rnd01(key, 13);
+    int ord[3];
+    switch ((int)(6 * rnd01(key, 14))) {
+    case 0: ord[0] = 0; ord[1] = 1; ord[2] = 2; break;
+    case 1: ord[0] = 0; ord[1] = 2; ord[2] = 1; break;
+    case 2: ord[0] = 1; ord[1] = 0; ord[2] = 2; break;
+    case 3: ord[0] = 1; ord[1] = 2; ord[2] = 0; break;
+    case 4: ord[0] = 2; ord[1] = 0; ord[2] = 1; break;
+    default: ord[0] = 2; ord[1] = 1; ord[2] = 0; break;
+    }
+    int i;
+    for (i = 3; i--;) {
+        double c = ord[i] == 0 ? v[0] : ord[i] == 1 ? v[1] : v[2];
+        if ((-0.6 < c) & (c < 0.6)) break;
+    }
+    if (i < 0) return false;
+    if (ord[i] == 0) v1[0] = 1.0; else if (ord[i] == 1) v1[1] = 1.0; else v1[2] = 1.0;
+    vp[0] = v1[1] * v[2] - v1[2] * v[1];
+    vp[1] = v1[2] * v[0] - v1[0] * v[2];
+    vp[2] = v1[0] * v[1] - v1[1] * v[0];
+    return normalize3(vp) > 0.0;
+}
+
+// One ambient division sample (ambcomp.c:177-248 ambsample, value-only part).
+// par describes the ray whose hit spawns the hemisphere.
+__device__ __forceinline__ bool ambsample(const DParams& P, RayCtx& par, int atyp, const float acoef[3],
+                                          const double onrm[3], const double ux[3], const double uy[3],
+                                          int n, int i, int j, QRay& q) {
+    float rc[3] = {acoef[0], acoef[1], acoef[2]};
+    if (!rayorigin(P, par, atyp, rc, true, q)) return false;
+    unsigned long long key = ((unsigned long long)q.key_hi << 32) | q.key_lo;
+    double ss0 = rnd01(key, 1), ss1 = rnd01(key, 2), spt[2];
+    square2disk(spt, (j + ss1) / n, (i + ss0) / n);
+    double zd = sqrt(1. - spt[0] * spt[0] - spt[1] * spt[1]);
+    for (int k = 0; k < 3; k++) q.dir[k] = spt[0] * ux[k] + spt[1] * uy[k] + zd * onrm[k];
+    normalize3(q.dir);                 // checknorm() is normalize() under -ffast-math (rt/ray.h:270-274)
+    unsigned info = q.info;            // ambient children are one bounce deeper
+    int rdepth = ((info >> 16) & 0x3f) + 1;
+    q.info = (info & 0xffc0ffffu) | ((unsigned)(rdepth & 0x3f) << 16);
+    return true;
+}
+
+// ------------------------------------------------------ accumulation -------
+__device__ __forceinline__ void add_value(const WaveArgs& A, unsigned row, const float c[3],
+                                          float r, float g, float b) {
+    if (!A.vacc) return;
+    double* v = A.vacc + (size_t)(row - A.row0) * 3;
+    atomicAdd(v + 0, (double)(c[0] * r));
+    atomicAdd(v + 1, (double)(c[1] * g));
+    atomicAdd(v + 2, (double)(c[2] * b));
+}
+
+// rcontrib.c:272-317.  `rcoef_ok`: the ray's own coefficient was not zeroed by
+// its material; rcol = the ray's returned radiance (emitters only).
+__device__ __forceinline__ void trace_contrib(const WaveArgs& A, const RayCtx& r, bool rcoef_zeroed,
+                                              const float rcol[3], bool have_rcol) {
+    if (!A.acc || r.robj < 0) return;
+    int4 hd = __ldg(&A.S.objhdr[r.robj]);
+    if (hd.y < 0) return;                                   // void modifier
+    if (r.rsrc >= 0 && A.S.srcs[r.rsrc].so != r.robj) return;   // shadow ray not on source
+    int slot = __ldg(&A.S.otrack[r.robj]);
+    if (slot < 0) return;
+    if (rcoef_zeroed) return;
+    float c[3] = {r.coef[0], r.coef[1], r.coef[2]};
+    if (A.P.contrib) {
+        if (!have_rcol) { atomicOr(&A.C->errflag, RB_ERR_UNSUP_MOD); A.C->errobj = (unsigned)r.robj; return; }
+        c[0] *= rcol[0]; c[1] *= rcol[1]; c[2] *= rcol[2];
+        // reference tests rcoef*rcol of the ray itself; the chain product has the same zero set
+        if (!(c[0] > 0.f || c[1] > 0.f || c[2] > 0.f)) return;
+    }
+    const DBinSpec& b = A.bins[slot];
+    double bval = rb_eval_bin(b, r.dir);
+    if (bval <= -.5) return;
+    int bn = (int)(bval + .5);
+    if (bn >= b.nbins) { atomicAdd(&A.C->badbin, 1u); return; }
+    double* d = A.acc + ((size_t)(r.row - A.row0) * A.ncols + b.col0 + bn) * 3;
+    atomicAdd(d + 0, (double)c[0]);
+    atomicAdd(d + 1, (double)c[1]);
+    atomicAdd(d + 2, (double)c[2]);
+    atomicAdd(&A.C->contribs, 1ULL);
+}
+
+// ----------------------------------------------------------- sources -------
+// source.c:316-377.  Returns the source index whose object becomes r->ro, or -1.
+__device__ __forceinline__ int sourcehit(const DScene& S, const double dir[3], int rsrc, int crtype) {
+    int glowsrc = -1, transrc = -1;
+    int first = 0, last = S.nsrcs - 1;
+    if (rsrc >= 0) first = last = rsrc;
+    for (int i = first; i <= last; i++) {
+        const SrcRec& s = S.srcs[i];
+        if (!(s.flags & SF_DISTANT)) continue;
+        if (2. * RB_PI * (1. - (s.sloc[0] * dir[0] + s.sloc[1] * dir[1] + s.sloc[2] * dir[2])) > s.ss2) continue;
+        if (i == rsrc) return i;
+        if (s.flags & SF_SKIP) { if (glowsrc < 0) glowsrc = i; continue; }
+        if (s.flags & 0x100) { if (transrc < 0) transrc = i; continue; }   // transparent illum
+        return i;
+    }
+    if (transrc >= 0 && (crtype & (RT_AMBIENT | RT_SPECULAR))) return -1;
+    return glowsrc;
+}
+
+// ------------------------------------------------------------ shading ------
+struct NormDat {           // normal.c:53-67 NORMDAT
+    int specfl;
+    float mcolor[3], scolor[3];
+    double prdir[3];
+    double alpha2, rdiff, rspec, trans, tdiff, tspec;
+    double pnorm[3], pdot;
+};
+enum : int { SP_REFL = 01, SP_TRAN = 02, SP_PURE = 04, SP_FLAT = 010, SP_RBLT = 020, SP_TBLT = 040 };
+
+// normal.c:71-173
+__device__ void dirnorm(float scval[3], const NormDat& np, const RayCtx& r, const double ldir[3],
+                        double omega, double dstrsrc) {
+    scval[0] = scval[1] = scval[2] = 0.f;
+    double ldot = dot3(np.pnorm, ldir);
+    if (ldot < 0.0 ? np.trans <= RB_FTINY : np.trans >= 1.0 - RB_FTINY) return;
+    double lrdiff = np.rdiff, ltdiff = np.tdiff;
+    if ((np.specfl & SP_PURE) && np.rspec >= 0.017999 && ((lrdiff > RB_FTINY) | (ltdiff > RB_FTINY))) {
+        double dtmp = 1. - (exp(-5.85 * fabs(ldot)) - 0.00202943064);
+        lrdiff *= dtmp; ltdiff *= dtmp;
+    }
+    if ((ldot > RB_FTINY) & (lrdiff > RB_FTINY)) {
+        double dtmp = ldot * omega * lrdiff * (1.0 / RB_PI);
+        for (int k = 0; k < 3; k++) scval[k] += (float)(np.mcolor[k] * dtmp);
+    }
+    if ((ldot < -RB_FTINY) & (ltdiff > RB_FTINY)) {
+        double dtmp = -ldot * omega * ltdiff * (1.0 / RB_PI);
+        for (int k = 0; k < 3; k++) scval[k] += (float)(np.mcolor[k] * dtmp);
+    }
+    if ((ldot > RB_FTINY) & ((np.specfl & (SP_REFL | SP_PURE)) == SP_REFL)) {
+        double dtmp = np.alpha2;
+        if (np.specfl & SP_FLAT) dtmp += (1. - dstrsrc) * omega * (0.25 / RB_PI);
+        double vtmp[3] = {ldir[0] - r.dir[0], ldir[1] - r.dir[1], ldir[2] - r.dir[2]};
+        double d2 = dot3(vtmp, np.pnorm);
+        d2 *= d2;
+        double d3 = dot3(vtmp, vtmp);
+        double d4 = (d3 - d2) / d2;
+        dtmp = exp(-d4 / dtmp) * d3 / (RB_PI * d2 * d2 * dtmp);
+        if (dtmp > RB_FTINY) {
+            dtmp *= ldot * omega;
+            for (int k = 0; k < 3; k++) scval[k] += (float)(np.scolor[k] * dtmp);
+        }
+    }
+    if ((ldot < -RB_FTINY) & ((np.specfl & (SP_TRAN | SP_PURE)) == SP_TRAN)) {
+        double dtmp = np.alpha2 + omega * (1.0 / RB_PI);
+        dtmp = exp((2. * dot3(np.prdir, ldir) - 2.) / dtmp) / (RB_PI * dtmp);
+        if (dtmp > RB_FTINY) {
+            dtmp *= np.tspec * omega * sqrt(-ldot / np.pdot);
+            for (int k = 0; k < 3; k++) scval[k] += (float)(np.mcolor[k] * dtmp);
+        }
+    }
+}
+
+// source.c:398-556 direct(), with every source tested (the reference's -dt 0
+// behaviour, which rcontrib forces: rcmain.c:164-171).
+__device__ void direct(const WaveArgs& A, RayCtx& r, const NormDat& nd) {
+    const DScene& S = A.S;
+    for (int sn = 0; sn < S.nsrcs; sn++) {
+        const SrcRec& s = S.srcs[sn];
+        if (s.flags & SF_SKIP) continue;                 // srcskip()
+        if (!(s.flags & SF_DISTANT)) continue;
+        // srcray(): rayorigin(sr, SHADOW, r, NULL) never fails for weight > 0
+        unsigned long long key = child_key(r.key, r.nchild++);
+        double vpos[3] = {0, 0, 0};
+        if (A.P.dstrsrc > RB_FTINY) {                    // srcsamp.c:67-79 jitter
+            for (int k = 0; k < 3; k++) vpos[k] = A.P.dstrsrc * (1. - 2. * rnd01(key, 20 + k));
+        }
+        if ((s.flags & SF_CIRC) && (A.P.dstrsrc > 0.7)) {   // srcsamp.c:83-107
+            double d = 1.12837917;
+            double t0 = d * sqrt(1.0 - 0.5 * vpos[1] * vpos[1]);
+            double t1 = d * sqrt(1.0 - 0.5 * vpos[0] * vpos[0]);
+            vpos[0] *= t0; vpos[1] *= t1; vpos[2] *= 0.0;
+        }
+        double ldir[3];
+        for (int k = 0; k < 3; k++)
+            ldir[k] = s.sloc[k] + vpos[0] * s.ss[0][k] + vpos[1] * s.ss[1][k] + vpos[2] * s.ss[2][k];
+        if (normalize3(ldir) == 0.0) continue;
+        double dom = s.ss2;                              // nopart: whole source
+        float scval[3];
+        dirnorm(scval, nd, r, ldir, dom, A.P.dstrsrc);
+        if (!(max3(scval) > 0.f)) continue;
+        // shadow test ray: TSHADOW if through the surface (ray.h:87 thrudir)
+        bool thru = (r.rod > 0) ^ (dot3(r.ron, ldir) > 0);
+        int rt = thru ? RT_TSHADOW : RT_RSHADOW;
+        QRay q;
+        RayCtx par = r; par.key = key; par.nchild = 0;
+        float rc[3];
+        if (!rayorigin(A.P, par, rt, rc, false, q)) continue;
+        q.coef[0] = r.coef[0] * scval[0]; q.coef[1] = r.coef[1] * scval[1]; q.coef[2] = r.coef[2] * scval[2];
+        q.dir[0] = ldir[0]; q.dir[1] = ldir[1]; q.dir[2] = ldir[2];
+        q.rsrc = sn;
+        push_ray(A, q);
+    }
+}
+
+// ambient.c:229-297 (aa = 0 branch) + ambcomp.c:350-422
+__device__ void multambient(const WaveArgs& A, RayCtx& r, const float aval[3], const double nrm[3]) {
+    const DParams& P = A.P;
+    bool dumb = (P.ambdiv <= 0) | (r.rdepth >= P.ambounce);
+    float d = max3(aval);
+    if (!dumb && d <= (float)RB_FTINY) dumb = true;      // samp_hemi insignificance -> !ok
+    if (dumb) {                                          // dumbamb: global ambient value
+        if (A.vacc && (P.ambval[0] > 0.f || P.ambval[1] > 0.f || P.ambval[2] > 0.f)) {
+            float c[3] = {r.coef[0] * aval[0], r.coef[1] * aval[1], r.coef[2] * aval[2]};
+            add_value(A, r.row, c, P.ambval[0], P.ambval[1], P.ambval[2]);
+        }
+        return;
+    }
+    double rdot = dot3(nrm, r.ron);
+    int sgn = 1 - 2 * (rdot < 0);
+    double wt = (double)r.rweight * sgn;
+    bool backside = (wt < 0);
+    if (backside) wt = -wt;
+    double dd = (double)d;
+    dd *= 0.8 * (double)r.rweight / ((double)P.ambdiv * (double)P.minweight + 1e-20);
+    if (wt > dd) wt = dd;
+    int n = (int)(sqrt(P.ambdiv * wt) + 0.5);
+    if (n < 1) n = 1;
+    float sc = (float)(1.0 / ((double)n * n));
+    float acoef[3] = {aval[0] * sc, aval[1] * sc, aval[2] * sc};
+    int atyp = backside ? RT_TAMBIENT : RT_RAMBIENT;
+    double onrm[3] = {r.ron[0], r.ron[1], r.ron[2]};
+    if (backside) { onrm[0] = -onrm[0]; onrm[1] = -onrm[1]; onrm[2] = -onrm[2]; }
+    unsigned long long hkey = child_key(r.key, r.nchild++);
+    if (n * n > A.inline_hemi_max) {                    // defer: expanded by k_expand
+        unsigned slot = reserve_slot(&A.C->nh_out);
+        if (slot >= A.hcap) { A.C->overflow = 1; return; }
+        atomicAdd(&A.C->hemi_rays, (unsigned)(n * n));
+        QHemi h;
+        for (int k = 0; k < 3; k++) { h.rop[k] = r.rop[k]; h.onrm[k] = onrm[k]; h.acoef[k] = acoef[k]; h.ccoef[k] = r.coef[k]; }
+        h.rweight = r.rweight; h.n = n; h.row = r.row;
+        h.info = pack_info(r.crtype, r.rlvl, r.rdepth);
+        h.key_lo = (unsigned)hkey; h.key_hi = (unsigned)(hkey >> 32);
+        h.atype = atyp; h.rsrc = r.rsrc;
+        h.rmax_rem = (r.rmax > RB_FTINY) * (r.rmax - r.rot);
+        A.hout[slot] = h;
+        return;
+    }
+    double ux[3], uy[3];
+    if (!getperpendicular_rand(ux, onrm, hkey)) return;
+    uy[0] = onrm[1] * ux[2] - onrm[2] * ux[1];
+    uy[1] = onrm[2] * ux[0] - onrm[0] * ux[2];
+    uy[2] = onrm[0] * ux[1] - onrm[1] * ux[0];
+    RayCtx par = r; par.key = hkey; par.nchild = 0;
+    for (int i = n; i--;)
+        for (int j = n; j--;) {
+            QRay q;
+            if (ambsample(P, par, atyp, acoef, onrm, ux, uy, n, i, j, q)) push_ray(A, q);
+        }
+}
+
+// raytrace.c:196-207 raytrans(): continue the ray unchanged
+__device__ void raytrans(const WaveArgs& A, RayCtx& r) {
+    QRay q; float rc[3];
+    if (!rayorigin(A.P, r, RT_TRANS, rc, false, q)) return;
+    q.dir[0] = r.dir[0]; q.dir[1] = r.dir[1]; q.dir[2] = r.dir[2];
+    push_ray(A, q);
+}
+
+// normal.c:176-360.  a[] = material reals; mkind = MK_PLASTIC / MK_METAL / MK_TRANS.
+__device__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind, const float* a) {
+    const DParams& P = A.P;
+    if ((r.crtype & RT_SHADOW) && mkind != MK_TRANS) return;      // easy shadow test
+    if (r.rod < 0.0) {
+        if (!P.backvis) { raytrans(A, r); return; }
+        r.rod = -r.rod; r.ron[0] = -r.ron[0]; r.ron[1] = -r.ron[1]; r.ron[2] = -r.ron[2];   // flipsurface
+    }
+    NormDat nd;
+    nd.mcolor[0] = a[0]; nd.mcolor[1] = a[1]; nd.mcolor[2] = a[2];
+    nd.specfl = 0;
+    nd.alpha2 = a[4];
+    if ((nd.alpha2 *= nd.alpha2) <= RB_FTINY) nd.specfl |= SP_PURE;
+    nd.pnorm[0] = r.ron[0]; nd.pnorm[1] = r.ron[1]; nd.pnorm[2] = r.ron[2];
+    nd.pdot = r.rod;
+    if (r.robj >= 0 && r.flat) nd.specfl |= SP_FLAT;
+    if (nd.pdot < .001) nd.pdot = .001;
+    nd.rspec = a[3];
+    double fest = 0.;
+    if ((nd.specfl & SP_PURE) && nd.rspec >= 0.017999) {
+        fest = exp(-5.85 * nd.pdot) - 0.00202943064;
+        nd.rspec += fest * (1. - nd.rspec);
+    }
+    if (mkind == MK_TRANS) {
+        nd.trans = a[5] * (1.0 - nd.rspec);
+        nd.tspec = nd.trans * a[6];
+        nd.tdiff = nd.trans - nd.tspec;
+        if (nd.tspec > RB_FTINY) {
+            nd.specfl |= SP_TRAN;
+            if (!(nd.specfl & SP_PURE) && P.specthresh >= nd.tspec - RB_FTINY) nd.specfl |= SP_TBLT;
+            nd.prdir[0] = r.dir[0]; nd.prdir[1] = r.dir[1]; nd.prdir[2] = r.dir[2];
+        }
+    } else
+        nd.tdiff = nd.tspec = nd.trans = 0.0;
+    nd.rdiff = 1.0 - nd.trans - nd.rspec;
+    // transmitted ray
+    if ((nd.specfl & (SP_TRAN | SP_PURE | SP_TBLT)) == (SP_TRAN | SP_PURE)) {
+        float rc[3] = {(float)(nd.mcolor[0] * nd.tspec), (float)(nd.mcolor[1] * nd.tspec), (float)(nd.mcolor[2] * nd.tspec)};
+        QRay q;
+        if (rayorigin(P, r, RT_TRANS, rc, true, q)) {
+            q.dir[0] = nd.prdir[0]; q.dir[1] = nd.prdir[1]; q.dir[2] = nd.prdir[2];
+            push_ray(A, q);
+        }
+    }
+    if (r.crtype & RT_SHADOW) return;
+    nd.scolor[0] = nd.scolor[1] = nd.scolor[2] = 0.f;
+    if (nd.rspec > RB_FTINY) {
+        nd.specfl |= SP_REFL;
+        if (mkind != MK_METAL) nd.scolor[0] = nd.scolor[1] = nd.scolor[2] = (float)nd.rspec;
+        else if (fest > RB_FTINY) {
+            double d = a[3] * (1. - fest);
+            for (int k = 0; k < 3; k++) nd.scolor[k] = (float)(fest + nd.mcolor[k] * d);
+        } else
+            for (int k = 0; k < 3; k++) nd.scolor[k] = (float)(nd.mcolor[k] * nd.rspec);
+        if (!(nd.specfl & SP_PURE) && P.specthresh >= nd.rspec - RB_FTINY) nd.specfl |= SP_RBLT;
+    }
+    // reflected ray
+    if ((nd.specfl & (SP_REFL | SP_PURE | SP_RBLT)) == (SP_REFL | SP_PURE)) {
+        float rc[3] = {nd.scolor[0], nd.scolor[1], nd.scolor[2]};
+        QRay q;
+        if (rayorigin(P, r, RT_REFLECTED, rc, true, q)) {
+            for (int k = 0; k < 3; k++) q.dir[k] = r.dir[k] + nd.pnorm[k] * (2. * nd.pdot);
+            normalize3(q.dir);
+            push_ray(A, q);
+        }
+    }
+    if ((nd.specfl & SP_PURE) && nd.rdiff <= RB_FTINY && nd.tdiff <= RB_FTINY) return;
+    if (!(nd.specfl & SP_PURE)) {
+        // gaussamp(), normal.c:363-495, single-sample form (-ss <= 1.5)
+        unsigned long long gkey = child_key(r.key, r.nchild++);
+        double u[3], v[3];
+        if (getperpendicular_rand(u, nd.pnorm, gkey)) {
+            v[0] = nd.pnorm[1] * u[2] - nd.pnorm[2] * u[1];
+            v[1] = nd.pnorm[2] * u[0] - nd.pnorm[0] * u[2];
+            v[2] = nd.pnorm[0] * u[1] - nd.pnorm[1] * u[0];
+            if ((nd.specfl & (SP_REFL | SP_RBLT)) == SP_REFL) {
+                float rc[3] = {nd.scolor[0], nd.scolor[1], nd.scolor[2]};
+                QRay q;
+                if (rayorigin(P, r, RT_RSPECULAR, rc, true, q)) {
+                    for (int ntr = 0; ntr < 10; ntr++) {
+                        double rv0 = rnd01(gkey, 30 + 2 * ntr), rv1 = rnd01(gkey, 31 + 2 * ntr);
+                        double s, c; sincos(2.0 * RB_PI * rv0, &s, &c);
+                        if ((0. <= P.specjitter) & (P.specjitter < 1.)) rv1 = 1.0 - P.specjitter * rv1;
+                        double d = (rv1 <= RB_FTINY) ? 1.0 : sqrt(nd.alpha2 * -log(rv1));
+                        double h[3];
+                        for (int k = 0; k < 3; k++) h[k] = nd.pnorm[k] + d * (c * u[k] + s * v[k]);
+                        d = -2.0 * dot3(h, r.dir) / (1.0 + d * d);
+                        for (int k = 0; k < 3; k++) q.dir[k] = r.dir[k] + h[k] * d;
+                        if (dot3(q.dir, r.ron) <= RB_FTINY) continue;
+                        normalize3(q.dir);
+                        push_ray(A, q);
+                        break;
+                    }
+                }
+            }
+            if ((nd.specfl & (SP_TRAN | SP_TBLT)) == SP_TRAN) {
+                float rc[3] = {(float)(nd.mcolor[0] * nd.tspec), (float)(nd.mcolor[1] * nd.tspec), (float)(nd.mcolor[2] * nd.tspec)};
+                QRay q;
+                if (rayorigin(P, r, RT_TSPECULAR, rc, true, q)) {
+                    for (int ntr = 0; ntr < 10; ntr++) {
+                        double rv0 = rnd01(gkey, 60 + 2 * ntr), rv1 = rnd01(gkey, 61 + 2 * ntr);
+                        double s, c; sincos(2.0 * RB_PI * rv0, &s, &c);
+                        if ((0. <= P.specjitter) & (P.specjitter < 1.)) rv1 = 1.0 - P.specjitter * rv1;
+                        double d = (rv1 <= RB_FTINY) ? 1.0 : sqrt(nd.alpha2 * -log(rv1));
+                        for (int k = 0; k < 3; k++) q.dir[k] = nd.prdir[k] + d * (c * u[k] + s * v[k]);
+                        if (dot3(q.dir, r.ron) >= -RB_FTINY) continue;
+                        normalize3(q.dir);
+                        push_ray(A, q);
+                        break;
+                    }
+                }
+            }
+        }
+    }
+    if (nd.rdiff > RB_FTINY) {
+        float sct[3];
+        for (int k = 0; k < 3; k++) sct[k] = (float)(nd.mcolor[k] * nd.rdiff);
+        if (nd.specfl & SP_RBLT) for (int k = 0; k < 3; k++) sct[k] += nd.scolor[k];
+        multambient(A, r, sct, nd.pnorm);
+    }
+    if (nd.tdiff > RB_FTINY) {
+        float sct[3];
+        double f = (nd.specfl & SP_TBLT) ? nd.trans : nd.tdiff;
+        for (int k = 0; k < 3; k++) sct[k] = (float)(nd.mcolor[k] * f);
+        double bn[3] = {-nd.pnorm[0], -nd.pnorm[1], -nd.pnorm[2]};
+        multambient(A, r, sct, bn);
+    }
+    direct(A, r, nd);
+}
+
+// glass.c:46-165
+__device__ void m_glass(const WaveArgs& A, RayCtx& r, const float* a, int nargs) {
+    const DParams& P = A.P;
+    double rindex = (nargs == 4) ? (double)a[3] : 1.52;
+    if (!P.backvis && r.rod <= 0.0) { raytrans(A, r); return; }
+    float mcolor[3] = {a[0], a[1], a[2]};
+    bool hastrans = max3(mcolor) > 1e-15f;
+    if (hastrans) { for (int k = 0; k < 3; k++) if (mcolor[k] < 1e-15f) mcolor[k] = 1e-15f; }
+    else if (r.crtype & RT_SHADOW) return;
+    if (r.rod < 0.0) { r.rod = -r.rod; r.ron[0] = -r.ron[0]; r.ron[1] = -r.ron[1]; r.ron[2] = -r.ron[2]; }
+    double pdot = r.rod;
+    double cos2 = sqrt((1.0 - 1.0 / (rindex * rindex)) + pdot * pdot / (rindex * rindex));
+    if (hastrans)
+        for (int k = 0; k < 3; k++) mcolor[k] = (float)pow((double)mcolor[k], 1.0 / cos2);
+    double r1e = (pdot - rindex * cos2) / (pdot + rindex * cos2);
+    r1e *= r1e;
+    double r1m = (1.0 / pdot - rindex / cos2) / (1.0 / pdot + rindex / cos2);
+    r1m *= r1m;
+    if (hastrans) {
+        float rc[3];
+        for (int k = 0; k < 3; k++) {
+            double d = mcolor[k];
+            rc[k] = (float)(.5 * (1.0 - r1e) * (1.0 - r1e) * d / (1.0 - r1e * r1e * d * d) +
+                            .5 * (1.0 - r1m) * (1.0 - r1m) * d / (1.0 - r1m * r1m * d * d));
+        }
+        QRay q;
+        if (rayorigin(P, r, RT_TRANS, rc, true, q)) {
+            q.dir[0] = r.dir[0]; q.dir[1] = r.dir[1]; q.dir[2] = r.dir[2];
+            push_ray(A, q);
+        }
+    }
+    if (r.crtype & RT_SHADOW) return;
+    float rc[3];
+    for (int k = 0; k < 3; k++) {
+        double d = mcolor[k];
+        d *= d;
+        rc[k] = (float)(.5 * r1e * (1.0 + (1.0 - 2.0 * r1e) * d) / (1.0 - r1e * r1e * d) +
+                        .5 * r1m * (1.0 + (1.0 - 2.0 * r1m) * d) / (1.0 - r1m * r1m * d));
+    }
+    QRay q;
+    if (rayorigin(P, r, RT_REFLECTED, rc, true, q)) {
+        for (int k = 0; k < 3; k++) q.dir[k] = r.dir[k] + r.ron[k] * (2. * pdot);
+        normalize3(q.dir);
+        push_ray(A, q);
+    }
+}
+
+// source.c:749-793 m_light.  Returns 1 and sets rcol when the ray sees the
+// emitter, 0 when its coefficient is zeroed / it is passed on.
+__device__ int m_light(const WaveArgs& A, RayCtx& r, const MatRec& m, float rcol[3], bool& zeroed) {
+    const DScene& S = A.S;
+    zeroed = false;
+    bool isglow = (m.kind == MK_GLOW);
+    // distglow(m, r, d): glow too far away to act as a source
+    auto distglow = [&](double d) { return isglow && m.a[3] >= -(float)RB_FTINY && d > (double)m.a[3]; };
+    // badcomponent
+    if ((r.crtype & (RT_AMBIENT | RT_SPECULAR)) &&
+        !((r.crtype & RT_SHADOW) || r.rod < 0.0 || distglow(r.rot))) { zeroed = true; return 0; }
+    // wrongsource
+    if (r.rsrc >= 0 && S.srcs[r.rsrc].so != r.robj) {
+        bool illumblock = false;
+        if (m.kind == MK_ILLUM) {
+            const MatRec& sm = S.mats[S.srcs[r.rsrc].mat];
+            illumblock = r.rod > 0.0 && (sm.kind == MK_ILLUM || sm.kind == MK_GLOW);
+        }
+        if (m.kind != MK_ILLUM || illumblock) { zeroed = true; return 0; }
+    }
+    // passillum
+    if (m.kind == MK_ILLUM && (r.rsrc < 0 || S.srcs[r.rsrc].so != r.robj)) return 2;
+    // srcignore (-dv-): path length approximated by this ray's own length
+    if (!(A.P.directvis || (r.crtype & RT_SHADOW) || distglow(r.rot))) { zeroed = true; return 0; }
+    if (r.rod < 0.0) {
+        if (!A.P.backvis) raytrans(A, r);
+        return 0;
+    }
+    if (m.kind == MK_SPOT) { atomicOr(&A.C->errflag, RB_ERR_UNSUP_MAT); A.C->errobj = (unsigned)m.obj; return 0; }
+    if ((m.flags & 1) && A.P.need_values) {       // pattern under an emitter only matters for values
+        atomicOr(&A.C->errflag, RB_ERR_UNSUP_MOD); A.C->errobj = (unsigned)m.obj;
+    }
+    rcol[0] = m.a[0]; rcol[1] = m.a[1]; rcol[2] = m.a[2];
+    return 1;
+}
+
+// rayshade() + trace callback for one traced ray (raytrace.c:162-179,210-256)
+__device__ void shade_ray(const WaveArgs& A, RayCtx& r) {
+    const DScene& S = A.S;
+    int4 hd = __ldg(&S.objhdr[r.robj]);
+    int ms = hd.z;
+    float rcol[3] = {0.f, 0.f, 0.f};
+    bool zeroed = false, have_rcol = false;
+    if (ms < 0) {                       // no material: rayshade() returns 0 -> raytrans
+        raytrans(A, r);
+        trace_contrib(A, r, false, rcol, false);
+        return;
+    }
+    const MatRec* m = &S.mats[ms];
+    bool tst_irrad = A.P.do_irrad && !(r.crtype & ~(RT_PRIMARY | RT_TRANS));
+    const float lamb[5] = {(float)RB_PI, (float)RB_PI, (float)RB_PI, 0.f, 0.f};
+    for (int guard = 0; guard < 8; guard++) {
+        int k = m->kind;
+        if (k == MK_UNSUPPORTED || ((m->flags & 1) && !(k >= MK_LIGHT && k <= MK_SPOT)) || (m->flags & 2)) {
+            atomicOr(&A.C->errflag, (m->flags & 2) ? RB_ERR_LOCAL_SRC : (k == MK_UNSUPPORTED ? RB_ERR_UNSUP_MAT : RB_ERR_UNSUP_MOD));
+            A.C->errobj = (unsigned)m->obj;
+            return;
+        }
+        if (tst_irrad) {                // raytirrad(), raytrace.c:210-228
+            if (k == MK_TRANS || k == MK_GLASS) { raytrans(A, r); break; }
+            if (!(k >= MK_LIGHT && k <= MK_SPOT)) { m_normal(A, r, MK_PLASTIC, lamb); break; }
+        }
+        if (k == MK_PLASTIC || k == MK_METAL || k == MK_TRANS) { m_normal(A, r, k, m->a); break; }
+        if (k == MK_GLASS) { m_glass(A, r, m->a, m->nargs); break; }
+        int rv = m_light(A, r, *m, rcol, zeroed);
+        if (rv == 1) {
+            have_rcol = true;
+            add_value(A, r.row, r.coef, rcol[0], rcol[1], rcol[2]);
+        } else if (rv == 2) {           // passed illum: alternate material or straight through
+            if (m->alt >= 0) { m = &S.mats[m->alt]; continue; }
+            raytrans(A, r);
+        }
+        break;
+    }
+    trace_contrib(A, r, zeroed, rcol, have_rcol);
+}
+
+}  // namespace rb
