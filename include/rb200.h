@@ -90,10 +90,11 @@ typedef struct rb_stats {
     uint64_t prims;        /* primitive intersection tests */
     uint64_t contribs;     /* contributions accumulated */
     uint64_t launches;     /* kernels launched */
-    uint64_t wave_launches;/* launches of the dominant trace+shade kernel */
+    uint64_t wave_launches;/* launches of the dominant (trace) kernel */
     uint64_t waves, batches, retries, badbin;
     double kernel_ms;      /* device time of all kernels (CUDA events) */
-    double wave_ms;        /* device time of the trace+shade kernel */
+    double wave_ms;        /* device time of the trace kernel (octree walk + intersection) */
+    double shade_ms;       /* device time of the shade kernel */
 } rb_stats;
 
 /* flags of rb_rcontrib / rb_rtrace */
@@ -142,6 +143,9 @@ int rb_clear_modifiers(rb_ctx* ctx);
 int rb_add_modifier(rb_ctx* ctx, const char* modname, const char* params,
                     const char* binexpr, int nbins);
 int rb_num_columns(rb_ctx* ctx);
+/* host evaluation of a tracked modifier's bin function for direction D (the
+ * same code the device runs; used by the CPU-side parity tests of the bins) */
+int rb_bin_of_direction(rb_ctx* ctx, int modifier_index, const double dir[3], double* binval);
 
 /* rays: [nrays][6] doubles, origin then direction (zero direction = dummy).
  * out:  [nrecords][ncols][3] float32, nrecords = ceil(nrays / accum).

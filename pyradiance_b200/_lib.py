@@ -37,7 +37,7 @@ class rb_stats(C.Structure):
         ("prims", C.c_uint64), ("contribs", C.c_uint64), ("launches", C.c_uint64),
         ("wave_launches", C.c_uint64), ("waves", C.c_uint64), ("batches", C.c_uint64),
         ("retries", C.c_uint64), ("badbin", C.c_uint64), ("kernel_ms", C.c_double),
-        ("wave_ms", C.c_double),
+        ("wave_ms", C.c_double), ("shade_ms", C.c_double),
     ]
 
 
@@ -78,6 +78,7 @@ SYMBOLS = [
     ("rb_clear_modifiers", C.c_int, [_P]),
     ("rb_add_modifier", C.c_int, [_P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
     ("rb_num_columns", C.c_int, [_P]),
+    ("rb_bin_of_direction", C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("rb_rcontrib", C.c_int, [_P, _P, C.c_size_t, C.c_int, C.c_uint, C.c_uint64, _P, C.c_size_t]),
     ("rb_rtrace", C.c_int, [_P, _P, C.c_size_t, C.c_uint, _P, _P]),
     ("rb_get_stats", C.c_int, [_P, C.POINTER(rb_stats)]),
@@ -230,6 +231,12 @@ class Context:
 
     def num_columns(self):
         return self.lib.rb_num_columns(self.h)
+
+    def bin_of_direction(self, modifier_index, d) -> float:
+        v = C.c_double()
+        dd = (C.c_double * 3)(*[float(x) for x in d])
+        self._ck(self.lib.rb_bin_of_direction(self.h, int(modifier_index), dd, C.byref(v)))
+        return v.value
 
     # ---- compute ----
     def rcontrib(self, rays, accum=1, flags=RB_IRRAD_NONE, row_base=0, out=None):

@@ -526,6 +526,12 @@ int rb_add_modifier(rb_ctx* c, const char* modname, const char* params, const ch
 
 int rb_num_columns(rb_ctx* c) { return c->ncols; }
 
+int rb_bin_of_direction(rb_ctx* c, int mi, const double dir[3], double* binval) {
+    if (mi < 0 || mi >= (int)c->mods.size()) return fail(c, "bad modifier index");
+    *binval = rb_eval_bin(c->mods[mi].spec, dir);
+    return 0;
+}
+
 int rb_rcontrib(rb_ctx* c, const double* rays, size_t nrays, int accum, unsigned flags, uint64_t row_base,
                 float* out, size_t out_floats) {
     if (!c->cuda_ok) return fail(c, c->cuda_err);
@@ -574,7 +580,7 @@ int rb_get_stats(rb_ctx* c, rb_stats* o) {
     const EngineStats& s = c->eng->stats;
     o->nrays = s.nrays; o->nodes = s.nodes; o->leafents = s.leafents; o->prims = s.prims; o->contribs = s.contribs;
     o->launches = s.launches; o->wave_launches = s.wave_launches; o->waves = s.waves; o->batches = s.batches;
-    o->retries = s.retries; o->badbin = s.badbin; o->kernel_ms = s.kernel_ms; o->wave_ms = s.wave_ms;
+    o->retries = s.retries; o->badbin = s.badbin; o->kernel_ms = s.kernel_ms; o->wave_ms = s.wave_ms; o->shade_ms = s.shade_ms;
     return 0;
 }
 int rb_reset_stats(rb_ctx* c) { if (c->eng) c->eng->stats = EngineStats(); return 0; }

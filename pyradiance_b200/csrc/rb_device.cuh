@@ -2,7 +2,7 @@
 //
 // HBM layout (all arrays resident for the life of the loaded octree):
 //   nodes[8*nnodes]  int32   child words; one node = 32 B = one sector
-//   leafpool[]       int32   [count, id0 < id1 < ...] per full leaf
+//   leafpool[]       int2    (count,0),(id, geom offset)... per full leaf, ids ascending
 //   objhdr[nobjs]    int4    kind|flags|nv, omod, material slot, geom offset
 //   geom[]           double  16-byte aligned primitive records (plane + 2-D
 //                            vertices for faces, centre+radius, cone frame)
@@ -95,6 +95,13 @@ struct __align__(16) QHemi {
     int rsrc;
 };
 static_assert(sizeof(QHemi) == 112, "QHemi must be 112 bytes");
+
+// what k_trace hands to k_shade for each queued ray
+struct HitRec {
+    double rot, rod;
+    int robj;               // object hit, source object for distant-source hits, -1 none
+    int local;              // 1: local surface hit, 0: distant source / nothing
+};
 
 // per-ray result for rtrace-style queries
 struct RayResult {

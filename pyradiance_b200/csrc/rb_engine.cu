@@ -35,6 +35,7 @@ namespace rb {
 
 // ------------------------------------------------------------- kernels -----
 __device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws, unsigned nr) {
+    if (!__any_sync(__activemask(), nr)) return;
     unsigned a = __reduce_add_sync(__activemask(), ws.nodes);
     unsigned b = __reduce_add_sync(__activemask(), ws.leafents);
     unsigned c = __reduce_add_sync(__activemask(), ws.prims);
@@ -49,11 +50,43 @@ __device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws, u
     }
 }
 
-__global__ void __launch_bounds__(WAVE_THREADS) k_wave(const WaveArgs A) {
+// Trace: octree walk + intersection only (small code, few registers).
+__global__ void __launch_bounds__(WAVE_THREADS) k_trace(const WaveArgs A) {
     __shared__ int stk[RB_STACK * WAVE_THREADS];
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < A.nin;
+    double org[3] = {0, 0, 0}, dir[3] = {0, 0, 0}, rmax = 0;
+    int rsrc = -1, crtype = 0;
+    if (active) {
+        const double2* q2 = reinterpret_cast<const double2*>(&A.qin[i]);
+        double2 a = __ldg(&q2[0]), b = __ldg(&q2[1]), c = __ldg(&q2[2]), d = __ldg(&q2[3]);
+        org[0] = a.x; org[1] = a.y; org[2] = b.x; dir[0] = b.y; dir[1] = c.x; dir[2] = c.y; rmax = d.x;
+        crtype = A.qin[i].info & 0x3ff; rsrc = A.qin[i].rsrc;
+    }
+    Hit h;
+    WalkStats ws = {0, 0, 0};
+    bool hit = localhit(A.S, active, org, dir, rmax, h, stk + threadIdx.x, WAVE_THREADS, ws,
+                        &A.C->errflag, &A.C->errobj);
+    flush_stats(A.C, ws, active ? 1u : 0u);
+    if (!active) return;
+    HitRec o;
+    o.rot = h.rot; o.rod = h.rod; o.robj = h.robj; o.local = 1;
+    if (!hit) {
+        o.rot = RB_FHUGE; o.rod = 1.0; o.robj = -1; o.local = 0;
+        if (!(rmax > RB_FTINY)) {                // aft-clipped rays never see sources
+            int sn = sourcehit(A.S, dir, rsrc, crtype);
+            if (sn >= 0) o.robj = A.S.srcs[sn].so;
+        }
+    }
+    A.hits[i] = o;
+}
+
+// Shade: material evaluation, contribution accumulation, child-ray emission.
+__global__ void __launch_bounds__(WAVE_THREADS) k_shade(const WaveArgs A) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.nin) return;
     const QRay q = A.qin[i];
+    const HitRec hr = A.hits[i];
     RayCtx r;
     for (int k = 0; k < 3; k++) { r.org[k] = q.org[k]; r.dir[k] = q.dir[k]; r.coef[k] = q.coef[k]; }
     r.rmax = q.rmax; r.rweight = q.rweight; r.row = q.row;
@@ -61,24 +94,14 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_wave(const WaveArgs A) {
     r.rsrc = q.rsrc;
     r.key = ((unsigned long long)q.key_hi << 32) | q.key_lo;
     r.nchild = 0;
-    Hit h;
-    WalkStats ws = {0, 0, 0};
-    bool hit = localhit(A.S, r.org, r.dir, r.rmax, h, stk + threadIdx.x, WAVE_THREADS, ws,
-                        &A.C->errflag, &A.C->errobj);
-    flush_stats(A.C, ws, 1);
-    r.robj = -1; r.flat = false;
-    if (hit) {
-        r.robj = h.robj; r.rot = h.rot; r.rod = h.rod;
+    r.robj = hr.robj; r.rot = hr.rot; r.rod = hr.rod; r.flat = false;
+    if (hr.local) {
+        Hit h; h.robj = hr.robj; h.rot = hr.rot; h.rod = hr.rod;
         hit_frame(A.S, h, r.org, r.dir, r.rop, r.ron);
         int kind = __ldg(&A.S.objhdr[h.robj]).x & 0xff;
         r.flat = (kind == PK_FACE) | (kind == PK_RING);
     } else {
-        r.rot = RB_FHUGE; r.rod = 1.0;
         for (int k = 0; k < 3; k++) { r.rop[k] = r.org[k]; r.ron[k] = -r.dir[k]; }
-        if (!(r.rmax > RB_FTINY)) {              // aft-clipped rays never see sources
-            int sn = sourcehit(A.S, r.dir, r.rsrc, r.crtype);
-            if (sn >= 0) r.robj = A.S.srcs[sn].so;
-        }
     }
     if (A.res && r.crtype == RT_PRIMARY) {
         RayResult& o = A.res[r.row - A.row0];
@@ -196,6 +219,8 @@ Engine::Engine(int device) : dev_(device) {
     cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking);
     cudaEventCreate(&ev0_);
     cudaEventCreate(&ev1_);
+    cudaEventCreate(&ev2_);
+    cudaEventCreate(&ev3_);
     cudaMalloc(&d_cnt_, sizeof(DCounters));
     cudaMallocHost(&h_cnt_, sizeof(DCounters));
 }
@@ -204,11 +229,13 @@ Engine::~Engine() {
     cudaSetDevice(dev_);
     cudaDeviceSynchronize();
     void* ptrs[] = {d_nodes_, d_leaf_, d_hdr_, d_geom_, d_mats_, d_srcs_, d_otrack_, d_bins_, q_[0], q_[1],
-                    h_[0], h_[1], d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_};
+                    h_[0], h_[1], d_hits_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_cnt_) cudaFreeHost(h_cnt_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
+    if (ev2_) cudaEventDestroy(ev2_);
+    if (ev3_) cudaEventDestroy(ev3_);
     if (stream_ && !user_stream_) cudaStreamDestroy(stream_);
 }
 
@@ -228,7 +255,7 @@ bool Engine::upload_scene(const FlatScene& fs, const Scene& sc, std::string& err
               std::to_string(RB_MAXDEPTH);
         return false;
     }
-    if (!upload(d_nodes_, fs.nodes, err) || !upload(d_leaf_, fs.leafpool, err) ||
+    if (!upload(d_nodes_, fs.nodes, err) || !upload(d_leaf_, fs.leaf2, err) ||
         !upload(d_hdr_, fs.objhdr, err) || !upload(d_geom_, fs.geom, err) ||
         !upload(d_mats_, fs.mats, err) || !upload(d_srcs_, fs.srcs, err))
         return false;
@@ -236,7 +263,7 @@ bool Engine::upload_scene(const FlatScene& fs, const Scene& sc, std::string& err
     if (!upload(d_otrack_, ot, err)) return false;
     for (int k = 0; k < 3; k++) S_.cuorg[k] = sc.cuorg[k];
     S_.cusize = sc.cusize;
-    S_.root = sc.root; S_.nobjs = (int)sc.objs.size(); S_.nsrcs = (int)fs.srcs.size();
+    S_.root = fs.root; S_.nobjs = (int)sc.objs.size(); S_.nsrcs = (int)fs.srcs.size();
     S_.maxdepth = sc.maxdepth;
     S_.nodes = (const int*)d_nodes_; S_.leafpool = (const int*)d_leaf_;
     S_.objhdr = (const int4*)d_hdr_; S_.geom = (const double*)d_geom_;
@@ -281,6 +308,7 @@ bool Engine::ensure_queues(std::string& err) {
     CK(cudaMalloc(&q_[1], qcap_ * sizeof(QRay)));
     CK(cudaMalloc(&h_[0], hcap_ * sizeof(QHemi)));
     CK(cudaMalloc(&h_[1], hcap_ * sizeof(QHemi)));
+    CK(cudaMalloc(&d_hits_, qcap_ * sizeof(HitRec)));
     return true;
 }
 
@@ -337,6 +365,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
     A.C = d_cnt_;
     A.inline_hemi_max = 16;
     A.qcap = (unsigned)qcap_; A.hcap = (unsigned)hcap_;
+    A.hits = d_hits_;
 
     auto sync_counters = [&](std::string& err) -> bool {
         CK(cudaMemcpyAsync(h_cnt_, d_cnt_, sizeof(DCounters), cudaMemcpyDeviceToHost, stream_));
@@ -390,12 +419,23 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         A.qin = q_[cur]; A.nin = nq; A.qout = q_[cur ^ 1]; A.hout = h_[cur ^ 1];
         unsigned grid = (nq + WAVE_THREADS - 1) / WAVE_THREADS;
         CK(cudaEventRecord(ev0_, stream_));
-        k_wave<<<grid, WAVE_THREADS, 0, stream_>>>(A);
+        k_trace<<<grid, WAVE_THREADS, 0, stream_>>>(A);
         CK(cudaEventRecord(ev1_, stream_));
-        stats.launches++; stats.wave_launches++; stats.waves++;
+        CK(cudaEventRecord(ev2_, stream_));
+        k_shade<<<grid, WAVE_THREADS, 0, stream_>>>(A);
+        CK(cudaEventRecord(ev3_, stream_));
+        stats.launches += 2; stats.wave_launches++; stats.waves++;
         CK(cudaGetLastError());
         if (!sync_counters(err)) return false;
-        { double ms = 0; if (!timed(ms, err)) return false; stats.kernel_ms += ms; stats.wave_ms += ms; }
+        {
+            float ms = 0, ms2 = 0;
+            CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+            CK(cudaEventElapsedTime(&ms2, ev2_, ev3_));
+            stats.kernel_ms += ms + ms2; stats.wave_ms += ms; stats.shade_ms += ms2;
+            if (getenv("RB_DEBUG_WAVES"))
+                fprintf(stderr, "[rb] wave %d: %u rays trace %.3f ms shade %.3f ms -> %u rays, %u hemis\n", wave, nq, ms, ms2,
+                        h_cnt_->nq_out, h_cnt_->nh_out);
+        }
         cur ^= 1;
         nq = h_cnt_->nq_out; nh = h_cnt_->nh_out;
     }

@@ -11,7 +11,8 @@ struct EngineStats {
     unsigned long long launches = 0;     // kernels launched
     unsigned long long waves = 0, batches = 0, retries = 0;
     double kernel_ms = 0;                // device time of all kernels (CUDA events)
-    double wave_ms = 0;                  // device time of k_wave launches only
+    double wave_ms = 0;                  // device time of k_trace launches only
+    double shade_ms = 0;                 // device time of k_shade launches
     unsigned long long wave_launches = 0;
     unsigned long long badbin = 0;
 };
@@ -69,7 +70,8 @@ private:
     double* d_rays_ = nullptr; size_t rays_bytes_ = 0;
     float* d_out_ = nullptr; size_t out_bytes_ = 0;
     RayResult* d_res_ = nullptr; size_t res_bytes_ = 0;
-    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev2_ = nullptr, ev3_ = nullptr;
+    HitRec* d_hits_ = nullptr;
     bool has_local_sources_ = false;
     std::string local_source_note_;
 };

@@ -266,11 +266,32 @@ __device__ __noinline__ void hit_frame(const DScene& S, const Hit& h, const doub
 
 struct WalkStats { unsigned nodes, leafents, prims; };
 
-// localhit(): returns true when a local surface was hit.  `stk` is this
-// thread's column of the shared-memory node stack (stride = blockDim.x).
-__device__ __forceinline__ bool localhit(const DScene& S, const double org[3], const double dir[3],
-                                         double rmax, Hit& h, volatile int* stk, int stride,
-                                         WalkStats& ws, unsigned* errflag, unsigned* errobj) {
+// The polygon test of o_face(), inlined in the walk (it is >95 % of all tests).
+__device__ __forceinline__ void hit_face(const DScene& S, int id, int4 hd, const double* __restrict__ g,
+                                         const double org[3], const double dir[3], Hit& h, bool aft) {
+    const double2* g2 = reinterpret_cast<const double2*>(g);
+    double2 n01 = __ldg(&g2[0]), n2o = __ldg(&g2[1]);
+    double rdot = -(dir[0] * n01.x + dir[1] * n01.y + dir[2] * n2o.x);
+    if ((rdot <= RB_FTINY) & (rdot >= -RB_FTINY)) return;
+    double t = ((org[0] * n01.x + org[1] * n01.y + org[2] * n2o.x) - n2o.y) / rdot;
+    if (rayreject(S, id, hd, h, aft, t, rdot)) return;
+    int ax = (hd.x >> 10) & 3;
+    double p0 = org[0] + t * dir[0], p1 = org[1] + t * dir[1], p2 = org[2] + t * dir[2];
+    double x = ax == 0 ? p1 : ax == 1 ? p2 : p0;      // xi = (ax+1)%3
+    double y = ax == 0 ? p2 : ax == 1 ? p0 : p1;      // yi = (ax+2)%3
+    if (!inface2d(g + 4, (hd.x >> 16) & 0xffff, x, y)) return;
+    h.robj = id; h.rot = t; h.rod = rdot;
+}
+
+// localhit(): returns true when a local surface was hit.  MUST be called by
+// all 32 lanes of a warp together (lanes without a ray pass active=false):
+// the walk is organised in warp-synchronous phases -- descend, test the leaf's
+// surfaces, step to the neighbour cube -- with a __syncwarp() after each, so
+// that lanes re-converge every phase instead of drifting apart for the whole
+// ray.  `stk` is this thread's column of the shared-memory node stack.
+__device__ __forceinline__ bool localhit(const DScene& S, bool active, const double org[3],
+                                         const double dir[3], double rmax, Hit& h, volatile int* stk,
+                                         int stride, WalkStats& ws, unsigned* errflag, unsigned* errobj) {
     int dirf = 0;
     double pos[3];
 #pragma unroll
@@ -280,12 +301,13 @@ __device__ __forceinline__ bool localhit(const DScene& S, const double org[3], c
         else if (dir[i] < -1e-7) dirf |= 0x10 << i;
     }
     h.robj = -1; h.rot = RB_FHUGE; h.rod = 1.0;
-    if (!dirf) return false;
+    bool done = !active || !dirf;
+    bool result = false;
     bool aft = false;
-    if (rmax > RB_FTINY) { aft = true; h.rot = rmax; }
+    if (!done && rmax > RB_FTINY) { aft = true; h.rot = rmax; }
     const double cs = S.cusize;
     // find global cube entrance point (raytrace.c:625-650)
-    {
+    if (!done) {
         bool in = !(S.cuorg[0] > pos[0] || pos[0] >= S.cuorg[0] + cs ||
                     S.cuorg[1] > pos[1] || pos[1] >= S.cuorg[1] + cs ||
                     S.cuorg[2] > pos[2] || pos[2] >= S.cuorg[2] + cs);
@@ -301,99 +323,116 @@ __device__ __forceinline__ bool localhit(const DScene& S, const double org[3], c
                 if (dt > t) t = dt;
             }
             t += RB_FTINY;
-            if (t >= h.rot) return false;
+            if (t >= h.rot) done = true;
+            else {
 #pragma unroll
-            for (int i = 0; i < 3; i++) pos[i] = pos[i] + dir[i] * t;
-            in = !(S.cuorg[0] > pos[0] || pos[0] >= S.cuorg[0] + cs ||
-                   S.cuorg[1] > pos[1] || pos[1] >= S.cuorg[1] + cs ||
-                   S.cuorg[2] > pos[2] || pos[2] >= S.cuorg[2] + cs);
-            if (!in) return false;
+                for (int i = 0; i < 3; i++) pos[i] = pos[i] + dir[i] * t;
+                in = !(S.cuorg[0] > pos[0] || pos[0] >= S.cuorg[0] + cs ||
+                       S.cuorg[1] > pos[1] || pos[1] >= S.cuorg[1] + cs ||
+                       S.cuorg[2] > pos[2] || pos[2] >= S.cuorg[2] + cs);
+                if (!in) done = true;
+            }
         }
     }
     int w = S.root, L = 0;
     unsigned ix = 0, iy = 0, iz = 0;
     double size = cs;                   // size of the current cube (level L)
-    for (;;) {
-        // ---- descend (raymove, raytrace.c:668-687) ----
-        while (w >= 0) {
-            stk[L * stride] = w;
-            double half = size * 0.5;
+    const int2* __restrict__ pool = reinterpret_cast<const int2*>(S.leafpool);
+    while (!__all_sync(0xffffffffu, done)) {
+        // ---- phase A: descend to a leaf (raymove, raytrace.c:668-687) ----
+        if (!done) {
+            while (w >= 0) {
+                stk[L * stride] = w;
+                double half = size * 0.5;
+                double lox = fma((double)ix, size, S.cuorg[0]);
+                double loy = fma((double)iy, size, S.cuorg[1]);
+                double loz = fma((double)iz, size, S.cuorg[2]);
+                int br = 0;
+                ix <<= 1; iy <<= 1; iz <<= 1;
+                if (pos[0] >= lox + half) { br |= 1; ix |= 1; }
+                if (pos[1] >= loy + half) { br |= 2; iy |= 1; }
+                if (pos[2] >= loz + half) { br |= 4; iz |= 1; }
+                w = __ldg(&S.nodes[(size_t)w * 8 + br]);
+                ws.nodes++;
+                size = half; L++;
+            }
+        }
+        __syncwarp();
+        // ---- phase B: test the leaf's surfaces, highest index first (rayhit) ----
+        {
+            int cnt = 0;
+            const int2* set = pool;
+            if (!done && w < -1) {
+                set = pool + (-w - 2);
+                cnt = __ldg(&set[0]).x;
+                ws.leafents += cnt + 1;
+                ws.prims += cnt;
+            }
+            for (int k = cnt; k > 0; k--) {
+                int2 ent = __ldg(&set[k]);
+                const double* g = S.geom + ent.y;
+                int4 hd = __ldg(reinterpret_cast<const int4*>(g - 2));
+                if ((hd.x & 0xff) == PK_FACE) hit_face(S, ent.x, hd, g, org, dir, h, aft);
+                else hit_object(S, ent.x, org, dir, h, aft, errflag, errobj);
+            }
+        }
+        __syncwarp();
+        // ---- phase C: accept the hit or step to the neighbour cube ----
+        if (!done) {
             double lox = fma((double)ix, size, S.cuorg[0]);
             double loy = fma((double)iy, size, S.cuorg[1]);
             double loz = fma((double)iz, size, S.cuorg[2]);
-            int br = 0;
-            ix <<= 1; iy <<= 1; iz <<= 1;
-            if (pos[0] >= lox + half) { br |= 1; ix |= 1; }
-            if (pos[1] >= loy + half) { br |= 2; iy |= 1; }
-            if (pos[2] >= loz + half) { br |= 4; iz |= 1; }
-            w = __ldg(&S.nodes[(size_t)w * 8 + br]);
-            ws.nodes++;
-            size = half; L++;
-        }
-        double lox = fma((double)ix, size, S.cuorg[0]);
-        double loy = fma((double)iy, size, S.cuorg[1]);
-        double loz = fma((double)iz, size, S.cuorg[2]);
-        double hix = lox + size, hiy = loy + size, hiz = loz + size;
-        if (w < -1) {                   // full leaf: checkhit (raytrace.c:743-760)
-            const int* set = S.leafpool + (-w - 2);
-            int cnt = __ldg(&set[0]);
-            ws.leafents += cnt + 1;
-            for (int k = cnt; k > 0; k--) {
-                int id = __ldg(&set[k]);
-                ws.prims++;
-                hit_object(S, id, org, dir, h, aft, errflag, errobj);
-            }
-            if (h.robj >= 0) {
+            double hix = lox + size, hiy = loy + size, hiz = loz + size;
+            if (w < -1 ? (h.robj >= 0) : (aft && h.robj < 0)) {
+                // checkhit (raytrace.c:756-759) / aft-plane point in an empty leaf (:709-710)
                 double px = org[0] + h.rot * dir[0];
                 double py = org[1] + h.rot * dir[1];
                 double pz = org[2] + h.rot * dir[2];
-                // sphere/cone rop are org + dir*t: same value
-                if (!(lox > px || px >= hix || loy > py || py >= hiy || loz > pz || pz >= hiz))
-                    return true;
+                if (!(lox > px || px >= hix || loy > py || py >= hiy || loz > pz || pz >= hiz)) {
+                    done = true; result = (w < -1);
+                }
             }
-        } else if (aft && h.robj < 0) { // empty leaf holding the aft-plane point
-            double px = org[0] + h.rot * dir[0];
-            double py = org[1] + h.rot * dir[1];
-            double pz = org[2] + h.rot * dir[2];
-            if (!(lox > px || px >= hix || loy > py || py >= hiy || loz > pz || pz >= hiz))
-                return false;
-        }
-        // ---- advance to next cube (raytrace.c:712-738) ----
-        int ax = 0;
-        double t;
-        if (dirf & 0x11) {
-            double dt = (dirf & 1) ? hix : lox;
-            t = (dt - pos[0]) / dir[0];
-            ax = 0;
-        } else t = RB_FHUGE;
-        if (dirf & 0x22) {
-            double dt = (dirf & 2) ? hiy : loy;
-            dt = (dt - pos[1]) / dir[1];
-            if (dt < t) { t = dt; ax = 1; }
-        }
-        if (dirf & 0x44) {
-            double dt = (dirf & 4) ? hiz : loz;
-            dt = (dt - pos[2]) / dir[2];
-            if (dt < t) { t = dt; ax = 2; }
-        }
+            if (!done) {
+                // advance to next cube (raytrace.c:712-738)
+                int ax = 0;
+                double t;
+                if (dirf & 0x11) {
+                    double dt = (dirf & 1) ? hix : lox;
+                    t = (dt - pos[0]) / dir[0];
+                    ax = 0;
+                } else t = RB_FHUGE;
+                if (dirf & 0x22) {
+                    double dt = (dirf & 2) ? hiy : loy;
+                    dt = (dt - pos[1]) / dir[1];
+                    if (dt < t) { t = dt; ax = 1; }
+                }
+                if (dirf & 0x44) {
+                    double dt = (dirf & 4) ? hiz : loz;
+                    dt = (dt - pos[2]) / dir[2];
+                    if (dt < t) { t = dt; ax = 2; }
+                }
 #pragma unroll
-        for (int i = 0; i < 3; i++) pos[i] = pos[i] + dir[i] * t;
-        // ---- step to the neighbour, ascending on overflow (raytrace.c:688-706) ----
-        bool positive = dirf & (1 << ax);
-        for (;;) {
-            if (L == 0) return (h.robj >= 0);     // left the scene cube
-            unsigned ia = ax == 0 ? ix : ax == 1 ? iy : iz;
-            if (positive != (bool)(ia & 1)) {     // sibling exists on that side
-                if (ax == 0) ix ^= 1; else if (ax == 1) iy ^= 1; else iz ^= 1;
-                break;
+                for (int i = 0; i < 3; i++) pos[i] = pos[i] + dir[i] * t;
+                // step to the neighbour, ascending on overflow (raytrace.c:688-706):
+                // climb while the cell coordinate along ax cannot move that way
+                bool positive = dirf & (1 << ax);
+                unsigned ia = ax == 0 ? ix : ax == 1 ? iy : iz;
+                unsigned blocked = positive ? ia : ~ia;            // trailing ones = levels to climb
+                int up = (~blocked) ? __ffs(~blocked) - 1 : 32;    // number of trailing one bits
+                if (up >= L) { done = true; result = (h.robj >= 0); }   // left the scene cube
+                else {
+                    ix >>= up; iy >>= up; iz >>= up; L -= up;
+                    size = ldexp(size, up);
+                    if (ax == 0) ix ^= 1; else if (ax == 1) iy ^= 1; else iz ^= 1;
+                    int br = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
+                    w = __ldg(&S.nodes[(size_t)stk[(L - 1) * stride] * 8 + br]);
+                    ws.nodes++;
+                }
             }
-            ix >>= 1; iy >>= 1; iz >>= 1; L--;
-            size = size + size;
         }
-        int br = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
-        w = __ldg(&S.nodes[(size_t)stk[(L - 1) * stride] * 8 + br]);
-        ws.nodes++;
+        __syncwarp();
     }
+    return result;
 }
 
 }  // namespace rb

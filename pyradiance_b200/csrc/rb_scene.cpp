@@ -401,9 +401,11 @@ static void mat4_mul(double a[4][4], double b[4][4], double c[4][4]) {   // a = 
     memcpy(a, t, sizeof(t));
 }
 
+// Every record is preceded by a 16-byte copy of the object header, so that the
+// walk reaches header + plane with one dependent load from the leaf entry.
 static size_t geom_alloc(FlatScene& fs, size_t n) {
     if (fs.geom.size() & 1) fs.geom.push_back(0.0);   // keep 16-byte alignment
-    size_t off = fs.geom.size();
+    size_t off = fs.geom.size() + 2;
     fs.geom.resize(off + n, 0.0);
     return off;
 }
@@ -632,6 +634,7 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
         hdr[0] = PK_NONE; hdr[1] = o.omod; hdr[2] = -1; hdr[3] = 0;
         if (ot_is_volume(o.otype)) {
             hdr[0] = PK_UNSUPPORTED;
+            hdr[3] = (int32_t)geom_alloc(fs, 0);
             fs.nsurf_unsupported++;
             note_unsupported("unsupported object type " + o.tname + " \"" + o.name + "\"");
             continue;
@@ -645,6 +648,7 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
             flatten_cone(o, fs, hdr, warn); break;
         case OT_SOURCE: hdr[0] = PK_NONE; break;       // never in the octree
         }
+        if (hdr[3] == 0) hdr[3] = (int32_t)geom_alloc(fs, 0);   // header-only record
         if (!warn.empty()) fs.warnings.push_back(warn);
         if ((hdr[0] & 0xff) == PK_UNSUPPORTED) { fs.nsurf_unsupported++; note_unsupported(warn); }
         int flags = 0;
@@ -669,6 +673,30 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
             }
         }
         hdr[0] |= flags << 8;
+    }
+    // header copies in front of the geometry records + (id, record) leaf entries
+    for (int i = 0; i < n; i++) {
+        const int32_t* hdr = &fs.objhdr[(size_t)i * 4];
+        if (hdr[3] >= 2) memcpy(&fs.geom[hdr[3] - 2], hdr, 16);
+    }
+    if (fs.geom.size() & 1) fs.geom.push_back(0.0);
+    {
+        std::vector<int> newoff(sc.leafpool.size(), -1);
+        fs.leaf2.clear();
+        for (size_t p = 0; p < sc.leafpool.size();) {
+            int cnt = sc.leafpool[p];
+            newoff[p] = (int)(fs.leaf2.size() / 2);
+            fs.leaf2.push_back(cnt); fs.leaf2.push_back(0);
+            for (int k = 1; k <= cnt; k++) {
+                int id = sc.leafpool[p + k];
+                if (id < 0 || id >= n) { err = "octree refers to object " + std::to_string(id) + " outside the scene"; return false; }
+                fs.leaf2.push_back(id);
+                fs.leaf2.push_back(fs.objhdr[(size_t)id * 4 + 3]);
+            }
+            p += cnt + 1;
+        }
+        for (auto& w : fs.nodes) if (w < -1) w = -newoff[-w - 2] - 2;
+        fs.root = sc.root < -1 ? -newoff[-sc.root - 2] - 2 : sc.root;
     }
 
     // ---- sources: rt/source.c:46-142 marksources(), srcsupp.c:155-179 ----

@@ -122,6 +122,8 @@ struct FlatScene {
     std::vector<SrcRec>  srcs;
     std::vector<int>     nodes;      // same encoding as Scene
     std::vector<int>     leafpool;
+    std::vector<int>     leaf2;      // (count,0),(id, geom offset)... pairs; nodes[] index these
+    int root = -1;
     int nsurf_unsupported = 0;
     std::string unsupported_note;    // first unsupported thing, for messages
     std::vector<std::string> warnings;

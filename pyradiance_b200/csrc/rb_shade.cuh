@@ -52,6 +52,7 @@ struct WaveArgs {
     const DBinSpec* bins;
     int nbinspecs;
     const QRay* qin; unsigned nin;
+    HitRec* hits;           // [qcap] k_trace -> k_shade
     QRay* qout; unsigned qcap;
     QHemi* hout; unsigned hcap;
     double* acc;            // [rows][ncols][3] contribution accumulators (or null)

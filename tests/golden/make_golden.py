@@ -1,0 +1,73 @@
+"""Regenerates the golden fixtures of tests/golden/ (run in the build container,
+where /root/reference and oracle/_ref exist):
+
+  * trace.oct, contrib.oct  -- the reference's own frozen test octrees
+    (/root/reference/tests/Resources), input fixtures only
+  * *.json                  -- known-answer outputs of the UNMODIFIED reference
+    rtrace / rcontrib (oracle/_ref/bin) on seeded inputs
+
+Usage: python tests/golden/make_golden.py
+"""
+import json
+import shutil
+import sys
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import refrun  # noqa: E402
+
+RES = Path("/root/reference/tests/Resources")
+
+
+def main():
+    for f in ("trace.oct", "contrib.oct"):
+        shutil.copyfile(RES / f, HERE / f)
+    g = {}
+    # SURVEY 8(c) known-answer vectors
+    rays = np.array([[1, 2, 3, 0, 0, 1], [4, 5, 6, 0, 1, 0], [10, 10, 3, 0, 0, -1]], dtype=float)
+    g["trace_ovposmNL"] = {"rays": rays.tolist(),
+                           "args": ["-ab", "0", "-ovposmNL"],
+                           "out": refrun.rtrace(HERE / "trace.oct", rays, ["-ab", "0", "-ovposmNL"])}
+    sens = np.array([[10, 10, .5, 0, 0, 1], [20, 20, .5, 0, 0, 1], [20, 20, 9.5, 0, 0, 1],
+                     [1, 2, 2.5, 0, 0, 1], [39, 45, 9.1, 0, 0, 1], [5, 40, 12, 0.3, 0.1, 0.9]], dtype=float)
+    g["trace_I_ab0"] = {"rays": sens.tolist(), "args": ["-I", "-ab", "0"],
+                        "out": refrun.rtrace(HERE / "trace.oct", sens, ["-I", "-ab", "0"])}
+    # 100x100 sensor grid of config 1 (S-small): values as float64
+    gx, gy = np.meshgrid(np.linspace(1, 39, 100), np.linspace(2, 45, 100))
+    grid = np.stack([gx.ravel(), gy.ravel(), np.full(10000, 2.5), np.zeros(10000), np.zeros(10000),
+                     np.ones(10000)], axis=1)
+    v = refrun.rtrace(HERE / "trace.oct", grid, ["-I", "-ab", "0", "-dt", "0", "-dj", "0", "-dc", "1"], outform="d")
+    v = v.reshape(-1, 3)
+    g["trace_grid_I_ab0"] = {"nonzero_rows": int((v[:, 0] > 0).sum()), "sum": float(v.sum()),
+                             "unique": sorted(set(np.round(v[:, 0], 6).tolist()))[:8]}
+    # deterministic rcontrib: -ab 0 from above the scene, one ray -> one bin (SURVEY 8a a19 check)
+    rng = np.random.default_rng(5)
+    d = rng.normal(size=(3000, 3))
+    d[:, 2] = np.abs(d[:, 2]) + 0.01
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    up = np.concatenate([np.tile([20., 20., 20.], (3000, 1)), d], axis=1)
+    cases = {
+        "reinhartb_mf1": ["-f", "reinhartb.cal", "-p", "MF=1,rNx=0,rNy=0,rNz=-1,Ux=0,Uy=1,Uz=0,RHS=+1", "-bn", "Nrbins", "-b", "rbin", "-m", "skyglow"],
+        "reinhartb_mf4": ["-f", "reinhartb.cal", "-p", "MF=4,rNx=0,rNy=0,rNz=-1,Ux=0,Uy=1,Uz=0,RHS=+1", "-bn", "Nrbins", "-b", "rbin", "-m", "skyglow"],
+        "reinhart_mf2": ["-e", "MF:2", "-f", "reinhart.cal", "-b", "rbin", "-bn", "Nrbins", "-m", "skyglow"],
+        "klems_full": ["-f", "klems_full.cal", "-p", "RHS=+1", "-bn", "Nkbins", "-b", "kbin(0,0,-1,0,1,0)", "-m", "skyglow"],
+        "klems_half": ["-f", "klems_half.cal", "-bn", "Nkhbins", "-b", "khbin(0,0,-1,0,1,0)", "-m", "skyglow"],
+        "klems_quarter": ["-f", "klems_quarter.cal", "-bn", "Nkqbins", "-b", "kqbin(0,0,-1,0,1,0)", "-m", "skyglow"],
+        "hemi": ["-b", "if(-Dx*0-Dy*0-Dz*-1,0,-1)", "-bn", "1", "-m", "skyglow"],
+    }
+    np.save(HERE / "bin_dirs.npy", up)
+    for name, args in cases.items():
+        m = refrun.rcontrib(HERE / "contrib.oct", up, ["-ab", "0"] + args)
+        m = m.reshape(3000, -1, 3)
+        bins = np.where(m[:, :, 0].sum(axis=1) > 0, m[:, :, 0].argmax(axis=1), -1)
+        g["bins_" + name] = {"args": args, "ncols": int(m.shape[1]), "bins": bins.astype(int).tolist()}
+    (HERE / "golden.json").write_text(json.dumps(g, indent=0))
+    print("wrote", HERE / "golden.json")
+
+
+if __name__ == "__main__":
+    main()
