@@ -107,6 +107,7 @@ typedef struct rb_stats {
 #define RB_FLAG_CONTRIB    8u  /* rcontrib -V+ */
 #define RB_FLAG_RAYS_ON_DEVICE 16u
 #define RB_FLAG_OUT_ON_DEVICE  32u
+#define RB_FLAG_OUT_DOUBLE     64u  /* out is float64 instead of float32 (rcontrib -fd) */
 
 #define RB_PROGRAM_RTRACE   0
 #define RB_PROGRAM_RCONTRIB 1
@@ -148,11 +149,12 @@ int rb_num_columns(rb_ctx* ctx);
 int rb_bin_of_direction(rb_ctx* ctx, int modifier_index, const double dir[3], double* binval);
 
 /* rays: [nrays][6] doubles, origin then direction (zero direction = dummy).
- * out:  [nrecords][ncols][3] float32, nrecords = ceil(nrays / accum).
+ * out:  [nrecords][ncols][3] float32 (float64 with RB_FLAG_OUT_DOUBLE),
+ *       nrecords = ceil(nrays / accum); out_floats = number of elements.
  * row_base: global index of the first record (keeps RNG streams independent
  * of how records are sharded across GPUs). */
 int rb_rcontrib(rb_ctx* ctx, const double* rays, size_t nrays, int accum,
-                unsigned flags, uint64_t row_base, float* out, size_t out_floats);
+                unsigned flags, uint64_t row_base, void* out, size_t out_floats);
 
 /* values: [nrays][3] doubles (may be NULL), results: [nrays] (may be NULL) */
 int rb_rtrace(rb_ctx* ctx, const double* rays, size_t nrays, unsigned flags,

@@ -1,0 +1,1205 @@
+/* rb_oracle.c -- TEST INFRASTRUCTURE (not product code).
+ *
+ * CPU restatement, in plain C and double precision, of the reference's
+ * rtrace / rcontrib hot path.  It follows the reference's RECURSIVE structure
+ * (a RAY with a parent pointer, rcoef per ray, the trace callback computing
+ * raycontrib() up the parent chain, a per-ray checked-object set), on purpose
+ * unlike the GPU code (iterative walk, forward coefficient products, re-tests
+ * instead of a checked set), so that agreement between the two is evidence.
+ *
+ * Reference functions restated (src/radiance/...):
+ *   readoct/gettree/getfullnode   common/readoct.c:35-141,153-168,195-218
+ *   readscene/getobj              common/sceneio.c:20-109
+ *   getint/getflt/getstr          common/portio.c:93-152
+ *   findmaterial                  rt/initotypes.c:112-145
+ *   getface/inface                common/face.c:35-106,121-162
+ *   getcone/conexform             common/cone.c:44-218
+ *   localhit/raymove/checkhit/checkset/rayhit/rayreject   rt/raytrace.c:535-793
+ *   incube                        common/octree.c:115-126
+ *   o_face, o_sphere, o_cone, quadratic   rt/o_face.c, rt/sphere.c, rt/o_cone.c, common/zeroes.c
+ *   rayorigin/rayclear/raytrace/raycont/raytrans/rayshade/raycontrib   rt/raytrace.c:39-442
+ *   marksources/ssetsrc/sourcehit/direct/srcray/nextssamp   rt/source.c, rt/srcsupp.c:155-179, rt/srcsamp.c:36-144
+ *   m_light, m_normal+dirnorm+gaussamp, m_glass   rt/source.c:749-793, rt/normal.c, rt/glass.c
+ *   multambient(aa=0)/doambient/samp_hemi/ambsample   rt/ambient.c:229-297, rt/ambcomp.c:177-248,350-422
+ *   trace_contrib, eval_irrad     rt/rcontrib.c:272-339
+ *   rbin/kbin bin functions       util/reinhartb.cal, cal/cal/reinhart.cal, util/klems_*.cal
+ * Unsupported things (other materials, patterns, instances, meshes, local
+ * light sources) make the call fail with a message: the oracle never guesses.
+ *
+ * Not restated (documented differences): ambcollision/trade_patchsamp
+ * re-jittering of close neighbours (ambcomp.c:81-173), multisamp()'s digit
+ * interleaving (independent uniforms are used), direct()'s -dt/-dc adaptive
+ * shadow-test cut-off (every source is tested, = -dt 0).
+ */
+#include "rb_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define FTINY 1e-6
+#define FHUGE 1e10
+#define PI 3.14159265358979323846
+#define MAXSET 8191
+#define MAXCSET ((MAXSET + 1) * 2 - 1)
+
+enum { PRIMARY = 01, RSHADOW = 02, REFLECTED = 04, REFRACTED = 010, TRANS = 020, RAMBIENT = 040, RSPECULAR = 0100,
+       TSHADOW = 0200, TAMBIENT = 0400, TSPECULAR = 01000 };
+#define SHADOW (RSHADOW | TSHADOW)
+#define AMBIENT (RAMBIENT | TAMBIENT)
+#define SPECULAR (RSPECULAR | TSPECULAR)
+#define RAYREFL (RSHADOW | REFLECTED | RAMBIENT | RSPECULAR)
+
+enum { T_OTHER = 0, T_POLYGON, T_CONE, T_SPHERE, T_RING, T_CYLINDER, T_CUP, T_BUBBLE, T_TUBE, T_SOURCE, T_INSTANCE,
+       T_MESH, T_ALIAS, T_PLASTIC, T_METAL, T_GLASS, T_TRANS, T_GLOW, T_LIGHT, T_ILLUM, T_SPOT, T_TRANSP_MAT,
+       T_OTHER_MAT, T_PATTERN };
+
+typedef struct {
+    int omod, otype;
+    char* name;
+    int nsargs; char** sargs;
+    int nfargs; double* fargs;
+    /* cached derived data */
+    int mat;                 /* findmaterial() object index or -1, -2 = not computed */
+    int nv, ax; double norm[3], offset, area;    /* face */
+    double ad[3], al, sl, p0[3], r0, r1, tm[4][4]; int ctype;   /* cone family (effective type) */
+    double rad; int stype;   /* sphere: radius, effective type */
+    int bad;                 /* unsupported / malformed */
+} OBJ;
+
+typedef struct { double sloc[3], ss2, ss[3][3]; int so, skip, distant; } SRC;
+
+typedef struct { char* name; int fn, mf, nbins, col0; double n[3], u[3], rhs; } MOD;
+
+struct orc_scene {
+    double cuorg[3], cusize;
+    int nobjs; OBJ* objs;
+    int root; int nnodes; int* nodes; int npool; int* pool;
+    int nsrcs; SRC* srcs;
+    int nmods; MOD* mods; int ncols; int* otrack;
+    orc_params P;
+    orc_counters C;
+    double* acc; size_t accrow;           /* current record accumulators */
+    char err[512];
+    int failed;
+    unsigned short xs[3];                 /* erand48 state */
+};
+
+typedef struct ray {
+    double rorg[3], rdir[3], rmax, rot, rop[3], ron[3], rod;
+    const struct ray* parent;
+    int ro, robj, rsrc, rlvl, rtype, crtype, aft, rflips;
+    double rweight;
+    float rcoef[3], rcol[3];
+    int rdepth;               /* ambient recursion depth (static rdepth in ambient.c:236) */
+} RAY;
+
+/* ------------------------------------------------------------- utils ---- */
+static double frandom(orc_scene* s) { return erand48(s->xs); }
+static double dot(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static void cross(double* r, const double* a, const double* b) {
+    double t[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    r[0] = t[0]; r[1] = t[1]; r[2] = t[2];
+}
+static double normalize(double* v) {
+    double len, d = dot(v, v);
+    if (d == 0.0) return 0.0;
+    if ((d <= 1.0 + FTINY) & (d >= 1.0 - FTINY)) { len = 0.5 + 0.5 * d; d = 2.0 - len; }
+    else { len = sqrt(d); d = 1.0 / len; }
+    v[0] *= d; v[1] *= d; v[2] *= d;
+    return len;
+}
+static void fail(orc_scene* s, const char* msg, const char* what) {
+    if (!s->failed) snprintf(s->err, sizeof(s->err), "%s%s%s", msg, what ? " " : "", what ? what : "");
+    s->failed = 1;
+}
+static float max3f(const float* c) { float m = c[0]; if (c[1] > m) m = c[1]; if (c[2] > m) m = c[2]; return m; }
+
+/* ---------------------------------------------------------- file i/o ---- */
+typedef struct { const unsigned char *p, *e; int bad; } RD;
+static int rgetc(RD* r) { if (r->p >= r->e) { r->bad = 1; return -1; } return *r->p++; }
+static long rgetint(RD* r, int siz) {
+    int c = rgetc(r); long v;
+    if (c < 0) return -1;
+    v = c; if (c & 0x80) v |= -256L;
+    while (--siz > 0) { c = rgetc(r); if (c < 0) return -1; v = (long)((unsigned long)v << 8); v |= c; }
+    return v;
+}
+static double rgetflt(RD* r) {
+    long l = rgetint(r, 4); double d;
+    if (r->bad) return 0;
+    if (l == 0) { rgetc(r); return 0.0; }
+    d = (l + .5 - (l < 0)) * (1. / 0x7fffffff);
+    return ldexp(d, (int)rgetint(r, 1));
+}
+static char* rgetstr(RD* r) {
+    const unsigned char* b = r->p;
+    while (r->p < r->e && *r->p) r->p++;
+    if (r->p >= r->e) { r->bad = 1; return strdup(""); }
+    r->p++;
+    return strdup((const char*)b);
+}
+
+static int type_of(const char* n) {
+    static const struct { const char* n; int t; } tab[] = {
+        {"polygon", T_POLYGON}, {"cone", T_CONE}, {"sphere", T_SPHERE}, {"ring", T_RING}, {"cylinder", T_CYLINDER},
+        {"cup", T_CUP}, {"bubble", T_BUBBLE}, {"tube", T_TUBE}, {"source", T_SOURCE}, {"instance", T_INSTANCE},
+        {"mesh", T_MESH}, {"alias", T_ALIAS}, {"plastic", T_PLASTIC}, {"metal", T_METAL}, {"glass", T_GLASS},
+        {"trans", T_TRANS}, {"glow", T_GLOW}, {"light", T_LIGHT}, {"illum", T_ILLUM}, {"spotlight", T_SPOT},
+        {"dielectric", T_TRANSP_MAT}, {"interface", T_TRANSP_MAT}, {"mist", T_TRANSP_MAT}, {"trans2", T_TRANSP_MAT},
+        {"aBSDF", T_TRANSP_MAT}, {"plastic2", T_OTHER_MAT}, {"metal2", T_OTHER_MAT}, {"plasfunc", T_OTHER_MAT},
+        {"metfunc", T_OTHER_MAT}, {"mirror", T_OTHER_MAT}, {"transfunc", T_OTHER_MAT}, {"BRTDfunc", T_OTHER_MAT},
+        {"BSDF", T_OTHER_MAT}, {"WGMDfunc", T_OTHER_MAT}, {"plasdata", T_OTHER_MAT}, {"metdata", T_OTHER_MAT},
+        {"transdata", T_OTHER_MAT}, {"antimatter", T_OTHER_MAT}, {"prism1", T_OTHER_MAT}, {"prism2", T_OTHER_MAT},
+        {"ashik2", T_OTHER_MAT}, {NULL, 0}};
+    int i;
+    for (i = 0; tab[i].n; i++) if (!strcmp(n, tab[i].n)) return tab[i].t;
+    return T_PATTERN;     /* patterns, textures, mixtures: anything else is a non-material modifier */
+}
+static int is_surface(int t) { return t >= T_POLYGON && t <= T_SOURCE; }
+static int is_material(int t) { return (t >= T_PLASTIC && t <= T_SPOT) || t == T_TRANSP_MAT || t == T_OTHER_MAT; }
+static int is_modifier(int t) { return !(t >= T_POLYGON && t <= T_MESH); }
+static int is_light(int t) { return t >= T_GLOW && t <= T_SPOT; }
+static int is_transp(int t) { return t == T_TRANS || t == T_GLASS || t == T_TRANSP_MAT; }
+
+static int lastmod(const orc_scene* s, int before, const char* name) {
+    int i;
+    for (i = (before < 0 ? s->nobjs : before); i-- > 0;)
+        if (is_modifier(s->objs[i].otype) && !strcmp(s->objs[i].name, name)) return i;
+    return -1;
+}
+
+static int findmaterial(orc_scene* s, int oi) {
+    int obj = -1, guard = 0;
+    while (!is_material(s->objs[oi].otype)) {
+        OBJ* o = &s->objs[oi];
+        if (++guard > 10000) return -1;
+        if (o->otype == T_ALIAS && o->nsargs) {
+            int ao = oi;
+            if (obj < 0) obj = oi;
+            do {
+                if (!s->objs[ao].nsargs) obj = s->objs[ao].omod;
+                else obj = lastmod(s, obj, s->objs[ao].sargs[0]);
+                if (obj < 0) return -1;
+                ao = obj;
+            } while (s->objs[ao].otype == T_ALIAS && ++guard < 10000);
+            if (is_material(s->objs[ao].otype)) return ao;
+        }
+        if (o->omod < 0) return -1;
+        obj = o->omod; oi = obj;
+    }
+    return oi;
+}
+static int matof(orc_scene* s, int oi) {
+    if (s->objs[oi].mat == -2) s->objs[oi].mat = findmaterial(s, oi);
+    return s->objs[oi].mat;
+}
+
+static int read_tree(RD* r, orc_scene* s, int objsize, int depth) {
+    int c = rgetc(r);
+    if (c == 0) return -1;
+    if (c == 1) {
+        long n = rgetint(r, objsize), i;
+        int off = s->npool;
+        if (n < 0 || n > MAXSET) { r->bad = 1; return -1; }
+        s->pool = (int*)realloc(s->pool, sizeof(int) * (s->npool + n + 1));
+        s->pool[s->npool++] = (int)n;
+        for (i = 0; i < n; i++) s->pool[s->npool++] = (int)rgetint(r, objsize);
+        return -off - 2;
+    }
+    if (c == 2 && depth < 64) {
+        int idx = s->nnodes++, i;
+        if ((s->nnodes & (s->nnodes - 1)) == 0 || s->nnodes == 1)
+            s->nodes = (int*)realloc(s->nodes, sizeof(int) * 8 * (size_t)(s->nnodes * 2 + 1));
+        for (i = 0; i < 8; i++) { int k = read_tree(r, s, objsize, depth + 1); s->nodes[(size_t)idx * 8 + i] = k; }
+        return idx;
+    }
+    r->bad = 1;
+    return -1;
+}
+
+static void setup_face(OBJ* o) {
+    int i, k; double v1[3], v2[3], v3[3], d;
+    const double* va = o->fargs;
+    if (o->nfargs < 9 || o->nfargs % 3) { o->bad = 1; return; }
+    o->nv = o->nfargs / 3;
+    for (d = 0, k = 0; k < 3; k++) d += (va[k] - va[3 * (o->nv - 1) + k]) * (va[k] - va[3 * (o->nv - 1) + k]);
+    if (o->nv > 3 && d <= FTINY * FTINY) o->nv--;
+    o->norm[0] = o->norm[1] = o->norm[2] = 0;
+    for (k = 0; k < 3; k++) v1[k] = va[3 + k] - va[k];
+    for (i = 2; i < o->nv; i++) {
+        for (k = 0; k < 3; k++) v2[k] = va[3 * i + k] - va[k];
+        cross(v3, v1, v2);
+        for (k = 0; k < 3; k++) { o->norm[k] += v3[k]; v1[k] = v2[k]; }
+    }
+    o->area = normalize(o->norm);
+    if (o->area == 0.0) { o->offset = 0; o->ax = 0; return; }
+    o->area *= 0.5;
+    o->offset = dot(o->norm, va);
+    for (i = 1; i < o->nv; i++) o->offset += dot(o->norm, va + 3 * i);
+    o->offset /= (double)o->nv;
+    o->ax = (fabs(o->norm[1]) > fabs(o->norm[0]));
+    if (fabs(o->norm[2]) > fabs(o->norm[o->ax])) o->ax = 2;
+}
+
+static void mat4_ident(double m[4][4]) { int i, j; for (i = 0; i < 4; i++) for (j = 0; j < 4; j++) m[i][j] = (i == j); }
+static void mat4_mul(double a[4][4], double b[4][4], double c[4][4]) {
+    double t[4][4]; int i, j;
+    for (i = 4; i--;) for (j = 4; j--;)
+        t[i][j] = b[i][0] * c[0][j] + b[i][1] * c[1][j] + b[i][2] * c[2][j] + b[i][3] * c[3][j];
+    memcpy(a, t, sizeof(t));
+}
+
+static void setup_cone(OBJ* o) {
+    double* ca = o->fargs; int ot = o->otype, p0, p1, r0, r1, i; double d, m4[4][4];
+    if (ot == T_CYLINDER || ot == T_TUBE) {
+        if (o->nfargs != 7) { o->bad = 1; return; }
+        if (ca[6] < -FTINY) { ot = ot == T_CYLINDER ? T_TUBE : T_CYLINDER; ca[6] = -ca[6]; }
+        else if (ca[6] <= FTINY) { o->bad = 1; return; }
+        p0 = 0; p1 = 3; r0 = r1 = 6;
+    } else {
+        int sgn0, sgn1;
+        if (o->nfargs != 8) { o->bad = 1; return; }
+        sgn0 = ca[6] < -FTINY ? -1 : ca[6] > FTINY ? 1 : 0;
+        sgn1 = ca[7] < -FTINY ? -1 : ca[7] > FTINY ? 1 : 0;
+        if (sgn0 + sgn1 == 0) { o->bad = 1; return; }
+        if ((sgn0 < 0) | (sgn1 < 0)) { if (ot == T_RING) { o->bad = 1; return; } ot = ot == T_CONE ? T_CUP : T_CONE; }
+        ca[6] = ca[6] * sgn0; ca[7] = ca[7] * sgn1;
+        if (ca[7] - ca[6] > FTINY) { if (ot == T_RING) p0 = p1 = 0; else { p0 = 0; p1 = 3; } r0 = 6; r1 = 7; }
+        else if (ca[6] - ca[7] > FTINY) { if (ot == T_RING) p0 = p1 = 0; else { p0 = 3; p1 = 0; } r0 = 7; r1 = 6; }
+        else { if (ot == T_RING) { o->bad = 1; return; } ot = ot == T_CONE ? T_CYLINDER : T_TUBE; p0 = 0; p1 = 3; r0 = r1 = 6; }
+    }
+    if (ot == T_RING) { o->ad[0] = ca[3]; o->ad[1] = ca[4]; o->ad[2] = ca[5]; }
+    else for (i = 0; i < 3; i++) o->ad[i] = ca[p1 + i] - ca[p0 + i];
+    o->al = normalize(o->ad);
+    if (o->al == 0.0) { o->bad = 1; return; }
+    if (ot == T_RING) { o->al = 0.0; o->sl = ca[r1] - ca[r0]; }
+    else if (ot == T_CONE || ot == T_CUP) { o->sl = ca[7] - ca[6]; o->sl = sqrt(o->sl * o->sl + o->al * o->al); }
+    else o->sl = o->al;
+    o->ctype = ot; o->r0 = ca[r0]; o->r1 = ca[r1];
+    for (i = 0; i < 3; i++) o->p0[i] = ca[p0 + i];
+    mat4_ident(o->tm);
+    d = (r0 == r1) ? 0.0 : ca[r0] / (ca[r1] - ca[r0]);
+    for (i = 0; i < 3; i++) o->tm[3][i] = d * (ca[p1 + i] - ca[p0 + i]) - ca[p0 + i];
+    mat4_ident(m4);
+    d = o->ad[1] * o->ad[1] + o->ad[2] * o->ad[2];
+    if (d <= FTINY * FTINY) { m4[0][0] = 0.0; m4[0][2] = o->ad[0]; m4[2][0] = -o->ad[0]; m4[2][2] = 0.0; }
+    else {
+        d = sqrt(d);
+        m4[0][0] = d; m4[1][0] = -o->ad[0] * o->ad[1] / d; m4[2][0] = -o->ad[0] * o->ad[2] / d;
+        m4[1][1] = o->ad[2] / d; m4[2][1] = -o->ad[1] / d;
+        m4[0][2] = o->ad[0]; m4[1][2] = o->ad[1]; m4[2][2] = o->ad[2];
+    }
+    mat4_mul(o->tm, o->tm, m4);
+    if ((p0 != p1) & (r0 != r1)) { mat4_ident(m4); m4[2][2] = (ca[r1] - ca[r0]) / o->al; mat4_mul(o->tm, o->tm, m4); }
+}
+
+static int getperp0(double* vp, const double* v) {      /* getperpendicular(randomize=0) */
+    double v1[3] = {0, 0, 0}; int i;
+    for (i = 3; i--;) if ((-0.6 < v[i]) & (v[i] < 0.6)) break;
+    if (i < 0) return 0;
+    v1[i] = 1.0; cross(vp, v1, v);
+    return normalize(vp) > 0.0;
+}
+
+static void mark_sources(orc_scene* s) {
+    int i, k;
+    for (i = 0; i < s->nobjs; i++) {
+        OBJ* o = &s->objs[i]; OBJ* m; int mi; SRC src;
+        if (!is_surface(o->otype) || o->omod < 0) continue;
+        mi = matof(s, i);
+        if (mi < 0) continue;
+        m = &s->objs[mi];
+        if (!is_light(m->otype)) continue;
+        if (m->nfargs != (m->otype == T_GLOW ? 4 : m->otype == T_SPOT ? 7 : 3)) { fail(s, "bad # arguments for", m->name); continue; }
+        if (m->fargs[0] <= FTINY && (m->fargs[1] <= FTINY) & (m->fargs[2] <= FTINY)) continue;
+        if (m->otype == T_GLOW && o->otype != T_SOURCE && m->fargs[3] <= FTINY) continue;
+        memset(&src, 0, sizeof(src));
+        src.so = i;
+        if (o->otype == T_SOURCE) {
+            double theta, snorm[3], mult;
+            if (o->nfargs != 4) { fail(s, "bad arguments for source", o->name); continue; }
+            src.distant = 1;
+            for (k = 0; k < 3; k++) src.sloc[k] = o->fargs[k];
+            if (normalize(src.sloc) == 0.0) { fail(s, "zero direction for", o->name); continue; }
+            theta = PI / 180.0 / 2.0 * o->fargs[3];
+            if (theta <= FTINY) { fail(s, "zero size for", o->name); continue; }
+            src.ss2 = 2.0 * PI * (1.0 - cos(theta));
+            for (k = 0; k < 3; k++) snorm[k] = src.sloc[k];
+            getperp0(src.ss[0], snorm);
+            mult = .5 * sqrt(src.ss2);
+            for (k = 0; k < 3; k++) src.ss[0][k] *= mult;
+            cross(src.ss[1], snorm, src.ss[0]);
+        } else {
+            fail(s, "local light source not supported by the oracle:", o->name);
+            continue;
+        }
+        if (m->otype == T_GLOW && src.distant) src.skip = 1;
+        if (m->otype == T_SPOT) { fail(s, "spotlight not supported by the oracle:", m->name); continue; }
+        s->srcs = (SRC*)realloc(s->srcs, sizeof(SRC) * (s->nsrcs + 1));
+        s->srcs[s->nsrcs++] = src;
+    }
+}
+
+orc_scene* orc_load(const char* path, char* err, size_t errlen) {
+    FILE* fp = fopen(path, "rb");
+    unsigned char* buf; long sz; RD r; orc_scene* s; char* str; int objsize, i, gotfmt = 0; long nobj;
+    const unsigned char* p;
+    if (!fp) { snprintf(err, errlen, "cannot open octree file \"%s\"", path); return NULL; }
+    fseek(fp, 0, SEEK_END); sz = ftell(fp); fseek(fp, 0, SEEK_SET);
+    buf = (unsigned char*)malloc(sz + 1);
+    if (fread(buf, 1, sz, fp) != (size_t)sz) { fclose(fp); free(buf); snprintf(err, errlen, "read error"); return NULL; }
+    fclose(fp);
+    p = buf;
+    for (;;) {          /* info header up to the empty line */
+        const unsigned char* nl = (const unsigned char*)memchr(p, '\n', buf + sz - p);
+        if (!nl) { free(buf); snprintf(err, errlen, "(%s): not an octree", path); return NULL; }
+        if (nl == p) { p = nl + 1; break; }
+        if (!strncmp((const char*)p, "FORMAT=", 7) && memmem(p, nl - p, "Radiance_octree", 15)) gotfmt = 1;
+        p = nl + 1;
+    }
+    if (!gotfmt) { free(buf); snprintf(err, errlen, "(%s): not an octree", path); return NULL; }
+    s = (orc_scene*)calloc(1, sizeof(orc_scene));
+    r.p = p; r.e = buf + sz; r.bad = 0;
+    objsize = (int)rgetint(&r, 2) - (4 * 8 + 251);
+    if (objsize <= 0 || objsize > 8) { free(buf); free(s); snprintf(err, errlen, "incompatible octree format"); return NULL; }
+    for (i = 0; i < 3; i++) { str = rgetstr(&r); s->cuorg[i] = atof(str); free(str); }
+    str = rgetstr(&r); s->cusize = atof(str); free(str);
+    str = rgetstr(&r);
+    if (*str) { free(str); free(buf); free(s); snprintf(err, errlen, "(%s): oracle reads frozen octrees only", path); return NULL; }
+    free(str);
+    nobj = rgetint(&r, objsize);
+    s->root = read_tree(&r, s, objsize, 0);
+    {
+        int ntypes = 0; int tmap[128];
+        for (;;) { str = rgetstr(&r); if (!*str || r.bad) { free(str); break; } if (ntypes < 128) tmap[ntypes++] = type_of(str); free(str); }
+        s->objs = (OBJ*)calloc(nobj > 0 ? nobj : 1, sizeof(OBJ));
+        for (;;) {
+            long ti = rgetint(&r, 1); OBJ* o;
+            if (r.bad || ti == -1) break;
+            if (ti < 0 || ti >= ntypes || s->nobjs >= nobj) { r.bad = 1; break; }
+            o = &s->objs[s->nobjs++];
+            o->otype = tmap[ti]; o->omod = (int)rgetint(&r, objsize); o->name = rgetstr(&r);
+            o->nsargs = (int)rgetint(&r, 2);
+            o->sargs = (char**)calloc(o->nsargs > 0 ? o->nsargs : 1, sizeof(char*));
+            for (i = 0; i < o->nsargs; i++) o->sargs[i] = rgetstr(&r);
+            o->nfargs = (int)rgetint(&r, 2);
+            o->fargs = (double*)calloc(o->nfargs > 0 ? o->nfargs : 1, sizeof(double));
+            for (i = 0; i < o->nfargs; i++) o->fargs[i] = rgetflt(&r);
+            o->mat = -2;
+        }
+    }
+    free(buf);
+    if (r.bad || s->nobjs != nobj) { snprintf(err, errlen, "(%s): truncated or damaged octree", path); orc_free(s); return NULL; }
+    for (i = 0; i < s->nobjs; i++) {
+        OBJ* o = &s->objs[i];
+        switch (o->otype) {
+        case T_POLYGON: setup_face(o); break;
+        case T_SPHERE: case T_BUBBLE:
+            if (o->nfargs != 4) { o->bad = 1; break; }
+            o->stype = o->otype; o->rad = o->fargs[3];
+            if (o->rad < -FTINY) { o->stype = o->otype == T_SPHERE ? T_BUBBLE : T_SPHERE; o->rad = -o->rad; }
+            else if (o->rad <= FTINY) o->bad = 1;
+            break;
+        case T_CONE: case T_CUP: case T_CYLINDER: case T_TUBE: case T_RING: setup_cone(o); break;
+        case T_INSTANCE: case T_MESH: o->bad = 1; break;
+        }
+    }
+    mark_sources(s);
+    orc_default_params(&s->P, 0);
+    s->otrack = (int*)malloc(sizeof(int) * (s->nobjs > 0 ? s->nobjs : 1));
+    for (i = 0; i < s->nobjs; i++) s->otrack[i] = -1;
+    s->xs[0] = 0x330e; s->xs[1] = 0x1234; s->xs[2] = 0x5678;
+    if (s->failed) { snprintf(err, errlen, "%s", s->err); orc_free(s); return NULL; }
+    return s;
+}
+
+void orc_free(orc_scene* s) {
+    int i, k;
+    if (!s) return;
+    for (i = 0; i < s->nobjs; i++) {
+        free(s->objs[i].name);
+        for (k = 0; k < s->objs[i].nsargs; k++) free(s->objs[i].sargs[k]);
+        free(s->objs[i].sargs); free(s->objs[i].fargs);
+    }
+    for (i = 0; i < s->nmods; i++) free(s->mods[i].name);
+    free(s->objs); free(s->nodes); free(s->pool); free(s->srcs); free(s->mods); free(s->otrack); free(s->acc);
+    free(s);
+}
+int orc_num_objects(const orc_scene* s) { return s->nobjs; }
+const char* orc_object_name(const orc_scene* s, int i) { return (i >= 0 && i < s->nobjs) ? s->objs[i].name : ""; }
+const char* orc_last_error(const orc_scene* s) { return s->err; }
+void orc_get_counters(const orc_scene* s, orc_counters* c) { *c = s->C; }
+void orc_reset_counters(orc_scene* s) { memset(&s->C, 0, sizeof(s->C)); }
+
+void orc_default_params(orc_params* p, int rcontrib) {
+    memset(p, 0, sizeof(*p));
+    p->backvis = 1; p->directvis = 1; p->maxdepth = -10; p->specjitter = 1.;
+    if (rcontrib) { p->ambounce = 1; p->ambdiv = 350; p->minweight = 2e-3; p->dstrsrc = 0.9; p->specthresh = .02; }
+    else { p->ambounce = 0; p->ambdiv = 1024; p->minweight = 1e-4; p->dstrsrc = 0.0; p->specthresh = .15; }
+    p->seed = 1;
+}
+void orc_set_params(orc_scene* s, const orc_params* p) {
+    s->P = *p;
+    s->xs[0] = (unsigned short)(p->seed); s->xs[1] = (unsigned short)(p->seed >> 16); s->xs[2] = (unsigned short)(p->seed >> 32) ^ 0x330e;
+}
+void orc_clear_modifiers(orc_scene* s) {
+    int i;
+    for (i = 0; i < s->nmods; i++) free(s->mods[i].name);
+    s->nmods = 0; s->ncols = 0;
+    for (i = 0; i < s->nobjs; i++) s->otrack[i] = -1;
+}
+int orc_add_modifier(orc_scene* s, const char* name, int fn, int mf, const double n[3], const double u[3], double rhs, int nbins) {
+    MOD* m; int i;
+    s->mods = (MOD*)realloc(s->mods, sizeof(MOD) * (s->nmods + 1));
+    m = &s->mods[s->nmods];
+    m->name = strdup(name); m->fn = fn; m->mf = mf; m->nbins = nbins; m->col0 = s->ncols; m->rhs = rhs;
+    for (i = 0; i < 3; i++) { m->n[i] = n ? n[i] : 0; m->u[i] = u ? u[i] : 0; }
+    s->ncols += nbins;
+    for (i = 0; i < s->nobjs; i++) {       /* tracked name = immediate modifier's name (rcontrib.c:287) */
+        int om = s->objs[i].omod;
+        if (om >= 0 && !strcmp(s->objs[om].name, name)) s->otrack[i] = s->nmods;
+    }
+    return s->mods[s->nmods++].col0;
+}
+int orc_num_columns(const orc_scene* s) { return s->ncols; }
+
+/* ------------------------------------------------------ bin functions ---- */
+/* written the way calcomp evaluates the .cal text: recursive raccum/kaccum */
+static double cal_if(double c, double a, double b) { return c > 0 ? a : b; }
+static double tnaz(int r) { static const double t[8] = {0, 30, 30, 24, 24, 18, 12, 6}; return (r >= 1 && r <= 7) ? t[r] : 0; }
+static double rnaz(double r, int mf) { return cal_if(r - (7 * mf - .5), 1, mf * tnaz((int)floor((r + .5) / mf) + 1)); }
+static double raccum(double r, int mf) { return r - .5 > 0 ? rnaz(r - 1, mf) + raccum(r - 1, mf) : 0; }
+static double deg_asin(double x) { return cal_if(x - 1, PI / 2, cal_if(-1 - x, -PI / 2, asin(x))) / (PI / 180); }
+static double deg_acos(double x) { return cal_if(x - 1, 0, cal_if(-1 - x, PI, acos(x))) / (PI / 180); }
+static double deg_atan2(double y, double x) { double a = atan2(y, x); return cal_if(-a, a + 2 * PI, a) / (PI / 180); }
+static double reinhart_patch(double alt, double azi, int mf) {
+    double alpha = 90. / (mf * 7 + .5);
+    double row = floor(alt / alpha);
+    double inc = 360. / rnaz(row, mf);
+    double azn = cal_if(359.9999 - .5 * inc - azi, floor((azi + .5 * inc) / inc), 0);
+    return raccum(row, mf) + azn;
+}
+static double klems(double pol, double azi, int fn) {
+    static const double pf[] = {5, 15, 25, 35, 45, 55, 65, 75, 90}, ph[] = {6.5, 19.5, 32.5, 45.5, 58.5, 71.5, 90},
+                        pq[] = {9, 27, 45, 63, 90};
+    static const int nf[] = {1, 8, 16, 20, 24, 24, 24, 16, 12}, nh[] = {1, 8, 12, 16, 20, 12, 8}, nq[] = {1, 8, 12, 12, 8};
+    const double* kp = fn == ORC_BIN_KLEMS_FULL ? pf : fn == ORC_BIN_KLEMS_HALF ? ph : pq;
+    const int* kn = fn == ORC_BIN_KLEMS_FULL ? nf : fn == ORC_BIN_KLEMS_HALF ? nh : nq;
+    int nrows = fn == ORC_BIN_KLEMS_FULL ? 9 : fn == ORC_BIN_KLEMS_HALF ? 7 : 5, r, k; double acc = 0, inc;
+    if (pol - 90 > 0) return -1;
+    for (r = 1; r < nrows && pol - kp[r - 1] > 0; r++);        /* kfindrow */
+    for (k = 1; k < r; k++) acc += kn[k - 1];                  /* kaccum(r-1) */
+    inc = 360. / kn[r - 1];
+    return acc + cal_if((360 - .5 * inc) - azi, floor((azi + .5 * inc) / inc), 0);
+}
+double orc_bin(int fn, int mf, const double N[3], const double U[3], double rhs, const double D[3]) {
+    switch (fn) {
+    case ORC_BIN_CONST: return 0;
+    case ORC_BIN_HEMI: return cal_if(-D[0] * N[0] - D[1] * N[1] - D[2] * N[2], 0, -1);
+    case ORC_BIN_REINHARTB: {
+        double dz = -D[0] * N[0] - D[1] * N[1] - D[2] * N[2];
+        double rx = -rhs * (D[0] * (U[1] * N[2] - U[2] * N[1]) + D[1] * (U[2] * N[0] - U[0] * N[2]) + D[2] * (U[0] * N[1] - U[1] * N[0]));
+        double ry = D[0] * U[0] + D[1] * U[1] + D[2] * U[2] + dz * (N[0] * U[0] + N[1] * U[1] + N[2] * U[2]);
+        double alt = deg_asin(dz), azi = deg_atan2(rx, ry);
+        return alt > 0 ? reinhart_patch(alt, azi, mf) : -1;
+    }
+    case ORC_BIN_REINHART: {
+        double alt = deg_asin(D[2]), azi = deg_atan2(D[0], D[1]);
+        return -alt > 0 ? 0 : reinhart_patch(alt, azi, mf) + 1;
+    }
+    default: {
+        double pol = deg_acos(-D[0] * N[0] - D[1] * N[1] - D[2] * N[2]);
+        double y = -D[0] * U[0] - D[1] * U[1] - D[2] * U[2] + (N[0] * D[0] + N[1] * D[1] + N[2] * D[2]) * (N[0] * U[0] + N[1] * U[1] + N[2] * U[2]);
+        double x = -rhs * (D[0] * (U[1] * N[2] - U[2] * N[1]) + D[1] * (U[2] * N[0] - U[0] * N[2]) + D[2] * (U[0] * N[1] - U[1] * N[0]));
+        return klems(pol, deg_atan2(y, x), fn);
+    }
+    }
+}
+
+/* ------------------------------------------------- intersection + walk ---- */
+static int rayreject(orc_scene* s, int oi, RAY* r, double t, double rod) {
+    int mnew, mray;
+    if ((t <= FTINY) | (t > r->rot + FTINY)) return 1;
+    if (t < r->rot - FTINY) return 0;
+    if (oi == r->ro) return 1;
+    if (r->ro < 0) return r->aft ? 1 : 0;
+    mnew = matof(s, oi); mray = matof(s, r->ro);
+    if (mnew < 0) { if (mray >= 0) return 1; }
+    else if (mray < 0) return 0;
+    else if (is_transp(s->objs[mnew].otype)) { if (!is_transp(s->objs[mray].otype)) return 1; }
+    else if (is_transp(s->objs[mray].otype)) return 0;
+    if (rod <= 0) { if (r->rod > 0) return 1; }
+    else if (r->rod <= 0) return 0;
+    return s->objs[r->ro].omod >= s->objs[oi].omod;
+}
+
+#define FABSEQ(a, b) (fabs((a) - (b)) <= FTINY)
+static int inface(const double* p, const OBJ* f) {
+    int ncross = 0, n = f->nv, tst, xi, yi; double x, y; const double *p0, *p1;
+    if ((xi = f->ax + 1) >= 3) xi -= 3;
+    if ((yi = xi + 1) >= 3) yi -= 3;
+    x = p[xi]; y = p[yi];
+    p0 = f->fargs + 3 * (n - 1); p1 = f->fargs;
+    while (n--) {
+        if (FABSEQ(p0[yi], y) && FABSEQ(p1[yi], y) && ((p0[xi] > x) ^ (p1[xi] > x))) return 1;
+        if ((p0[yi] > y) ^ (p1[yi] > y)) {
+            tst = (p0[xi] > x) + (p1[xi] > x);
+            if (tst == 2) ncross++;
+            else if (tst) {
+                double prodA = (p0[yi] - y) * (p1[xi] - x), prodB = (p0[xi] - x) * (p1[yi] - y);
+                if (FABSEQ(prodA, prodB)) return 1;
+                ncross += (p1[yi] > p0[yi]) ^ (prodA > prodB);
+            } else if (FABSEQ(p0[xi], x) && FABSEQ(p1[xi], x)) return 1;
+        }
+        p0 = p1; p1 += 3;
+    }
+    return ncross & 01;
+}
+
+static int quadratic(double* r, double a, double b, double c) {
+    double disc; int first;
+    if (a < -FTINY) first = 1; else if (a > FTINY) first = 0;
+    else if (fabs(b) > FTINY) { r[0] = -c / b; return 1; } else return 0;
+    b *= 0.5; disc = b * b - a * c;
+    if (disc < -FTINY * FTINY) return 0;
+    if (disc <= FTINY * FTINY) { r[0] = -b / a; return 1; }
+    disc = sqrt(disc);
+    r[first] = (-b - disc) / a; r[1 - first] = (-b + disc) / a;
+    return 2;
+}
+
+static int hit_obj(orc_scene* s, int oi, RAY* r) {
+    OBJ* o = &s->objs[oi]; int i;
+    s->C.prims++;
+    if (o->bad) { fail(s, "unsupported or malformed surface reached:", o->name); return 0; }
+    if (o->otype == T_POLYGON) {
+        double rdot = -dot(r->rdir, o->norm), t, p[3];
+        if ((rdot <= FTINY) & (rdot >= -FTINY)) return 0;
+        t = (dot(r->rorg, o->norm) - o->offset) / rdot;
+        if (rayreject(s, oi, r, t, rdot)) return 0;
+        for (i = 0; i < 3; i++) p[i] = r->rorg[i] + t * r->rdir[i];
+        if (!inface(p, o)) return 0;
+        r->ro = oi; r->rot = t; r->rod = rdot;
+        for (i = 0; i < 3; i++) { r->rop[i] = p[i]; r->ron[i] = o->norm[i]; }
+        return 1;
+    }
+    if (o->otype == T_SPHERE || o->otype == T_BUBBLE) {
+        double a = 0, b = 0, c = 0, root[2], t = 0; int nroots; const double* ap = o->fargs;
+        for (i = 0; i < 3; i++) { a += r->rdir[i] * r->rdir[i]; t = r->rorg[i] - ap[i]; b += 2.0 * r->rdir[i] * t; c += t * t; }
+        c -= o->rad * o->rad;
+        nroots = quadratic(root, a, b, c);
+        for (i = 0; i < nroots; i++) if ((t = root[i]) > FTINY) break;
+        if (i >= nroots) return 0;
+        if (rayreject(s, oi, r, t, 1 - 2 * ((i > 0) ^ (o->stype == T_BUBBLE)))) return 0;
+        r->ro = oi; r->rot = t;
+        a = o->rad * (1 - 2 * (o->stype == T_BUBBLE));
+        for (i = 0; i < 3; i++) { r->rop[i] = r->rorg[i] + r->rdir[i] * t; r->ron[i] = (r->rop[i] - ap[i]) / a; }
+        r->rod = -dot(r->rdir, r->ron);
+        return 1;
+    }
+    {   /* cone family */
+        double rox[3], rdx[3], a, b, c, root[2]; int nroots, rn, ct = o->ctype, j;
+        for (j = 0; j < 3; j++) {
+            rdx[j] = r->rdir[0] * o->tm[0][j] + r->rdir[1] * o->tm[1][j] + r->rdir[2] * o->tm[2][j];
+            rox[j] = r->rorg[0] * o->tm[0][j] + r->rorg[1] * o->tm[1][j] + r->rorg[2] * o->tm[2][j];
+            rox[j] += o->tm[3][j];
+        }
+        if ((ct == T_CONE) | (ct == T_CUP)) {
+            a = rdx[0] * rdx[0] + rdx[1] * rdx[1] - rdx[2] * rdx[2];
+            b = 2.0 * (rdx[0] * rox[0] + rdx[1] * rox[1] - rdx[2] * rox[2]);
+            c = rox[0] * rox[0] + rox[1] * rox[1] - rox[2] * rox[2];
+        } else if ((ct == T_CYLINDER) | (ct == T_TUBE)) {
+            a = rdx[0] * rdx[0] + rdx[1] * rdx[1];
+            b = 2.0 * (rdx[0] * rox[0] + rdx[1] * rox[1]);
+            c = rox[0] * rox[0] + rox[1] * rox[1] - o->r0 * o->r0;
+        } else {
+            if ((rdx[2] <= FTINY) & (rdx[2] >= -FTINY)) return 0;
+            root[0] = -rox[2] / rdx[2];
+            if (rayreject(s, oi, r, root[0], -rdx[2])) return 0;
+            b = root[0] * rdx[0] + rox[0]; c = root[0] * rdx[1] + rox[1]; a = b * b + c * c;
+            if (a > o->r1 * o->r1 || a < o->r0 * o->r0) return 0;
+            r->ro = oi; r->rot = root[0];
+            for (i = 0; i < 3; i++) { r->rop[i] = r->rorg[i] + r->rot * r->rdir[i]; r->ron[i] = o->ad[i]; }
+            r->rod = -rdx[2];
+            return 1;
+        }
+        nroots = quadratic(root, a, b, c);
+        for (rn = 0; rn < nroots; rn++) {
+            if (root[rn] <= FTINY) continue;
+            if (root[rn] > r->rot + FTINY) break;
+            for (i = 0; i < 3; i++) { rox[i] = r->rorg[i] + root[rn] * r->rdir[i]; rdx[i] = rox[i] - o->p0[i]; }
+            b = dot(rdx, o->ad);
+            if (b < 0.0) continue;
+            if (b > o->al) continue;
+            if (rayreject(s, oi, r, root[rn], 1 - 2 * ((rn > 0) ^ ((ct == T_CUP) | (ct == T_TUBE))))) break;
+            r->ro = oi; r->rot = root[rn];
+            for (i = 0; i < 3; i++) r->rop[i] = rox[i];
+            if (ct == T_CYLINDER) a = o->r0;
+            else if (ct == T_TUBE) a = -o->r0;
+            else { c = o->r1 - o->r0; a = o->r0 + b * c / o->al; if (ct == T_CUP) { c = -c; a = -a; } }
+            for (i = 0; i < 3; i++) r->ron[i] = (rdx[i] - b * o->ad[i]) / a;
+            if ((ct == T_CONE) | (ct == T_CUP)) for (i = 0; i < 3; i++) r->ron[i] = (o->al * r->ron[i] - c * o->ad[i]) / o->sl;
+            a = dot(r->ron, r->ron);
+            if ((a > 1. + FTINY) | (a < 1. - FTINY)) { c = 1. / (.5 + .5 * a); r->ron[0] *= c; r->ron[1] *= c; r->ron[2] *= c; }
+            r->rod = -dot(r->rdir, r->ron);
+            return 1;
+        }
+        return 0;
+    }
+}
+
+typedef struct { double org[3], size; int tree; } CUBE;
+static int incube(const CUBE* cu, const double* pt) {
+    int i;
+    for (i = 0; i < 3; i++) if (cu->org[i] > pt[i] || pt[i] >= cu->org[i] + cu->size) return 0;
+    return 1;
+}
+
+/* raytrace.c:764-793: os' = os - cs ; cs' = cs + os */
+static void checkset(int* os, int* cs) {
+    static int cset[MAXCSET + MAXSET + 1];
+    int i, j, k = 0;
+    cset[0] = 0;
+    for (i = j = 1; i <= os[0]; i++) {
+        while (j <= cs[0] && cs[j] < os[i]) cset[++cset[0]] = cs[j++];
+        if (j > cs[0] || os[i] != cs[j]) { os[++k] = os[i]; cset[++cset[0]] = os[i]; }
+    }
+    if (!(os[0] = k)) return;
+    while (j <= cs[0]) cset[++cset[0]] = cs[j++];
+    if (cset[0] > MAXCSET) cset[0] = MAXCSET;
+    for (i = 0; i <= cset[0]; i++) cs[i] = cset[i];
+}
+
+static int checkhit(orc_scene* s, RAY* r, const CUBE* cu, int* cxs) {
+    static int oset[MAXSET + 1];
+    const int* set = s->pool + (-cu->tree - 2);
+    int i;
+    for (i = 0; i <= set[0]; i++) oset[i] = set[i];
+    s->C.leafents += set[0] + 1;
+    checkset(oset, cxs);
+    for (i = oset[0]; i > 0; i--) if (hit_obj(s, oset[i], r)) r->robj = oset[i];
+    if (r->robj < 0) return 0;
+    return incube(cu, r->rop);
+}
+
+#define RAYHIT (-1)
+static int raymove(orc_scene* s, double* pos, int* cxs, int dirf, RAY* r, const CUBE* cu) {
+    int ax = 0; double dt, t;
+    if (cu->tree >= 0) {
+        CUBE kid; int br = 0, sgn, i;
+        kid.size = cu->size * 0.5;
+        for (i = 0; i < 3; i++) kid.org[i] = cu->org[i];
+        if (pos[0] >= kid.org[0] + kid.size) { kid.org[0] += kid.size; br |= 1; }
+        if (pos[1] >= kid.org[1] + kid.size) { kid.org[1] += kid.size; br |= 2; }
+        if (pos[2] >= kid.org[2] + kid.size) { kid.org[2] += kid.size; br |= 4; }
+        for (;;) {
+            kid.tree = s->nodes[(size_t)cu->tree * 8 + br];
+            s->C.nodes++;
+            if ((ax = raymove(s, pos, cxs, dirf, r, &kid)) == RAYHIT) return RAYHIT;
+            sgn = 1 << ax;
+            if (sgn & dirf) { if (sgn & br) return ax; kid.org[ax] += kid.size; br |= sgn; }
+            else { if (sgn & br) { kid.org[ax] -= kid.size; br &= ~sgn; } else return ax; }
+        }
+    }
+    if (cu->tree < -1) { if (checkhit(s, r, cu, cxs)) return RAYHIT; }
+    else if (r->aft && r->ro < 0 && incube(cu, r->rop)) return RAYHIT;
+    if (dirf & 0x11) { dt = dirf & 1 ? cu->org[0] + cu->size : cu->org[0]; t = (dt - pos[0]) / r->rdir[0]; ax = 0; }
+    else t = FHUGE;
+    if (dirf & 0x22) { dt = dirf & 2 ? cu->org[1] + cu->size : cu->org[1]; dt = (dt - pos[1]) / r->rdir[1]; if (dt < t) { t = dt; ax = 1; } }
+    if (dirf & 0x44) { dt = dirf & 4 ? cu->org[2] + cu->size : cu->org[2]; dt = (dt - pos[2]) / r->rdir[2]; if (dt < t) { t = dt; ax = 2; } }
+    pos[0] += r->rdir[0] * t; pos[1] += r->rdir[1] * t; pos[2] += r->rdir[2] * t;
+    return ax;
+}
+
+static int localhit(orc_scene* s, RAY* r) {
+    static int cxset[MAXCSET + 1];
+    double curpos[3], t, dt; int sflags = 0, i; CUBE scene;
+    s->C.nrays++;
+    for (i = 0; i < 3; i++) {
+        curpos[i] = r->rorg[i];
+        if (r->rdir[i] > 1e-7) sflags |= 1 << i; else if (r->rdir[i] < -1e-7) sflags |= 0x10 << i;
+        scene.org[i] = s->cuorg[i];
+    }
+    scene.size = s->cusize; scene.tree = s->root;
+    if (!sflags) return 0;
+    r->aft = 0;
+    if (r->rmax > FTINY) { r->aft = 1; r->rot = r->rmax; for (i = 0; i < 3; i++) r->rop[i] = r->rorg[i] + r->rdir[i] * r->rot; }
+    t = 0.0;
+    if (!incube(&scene, curpos)) {
+        for (i = 0; i < 3; i++) {
+            if (sflags & 1 << i) dt = scene.org[i]; else if (sflags & 0x10 << i) dt = scene.org[i] + scene.size; else continue;
+            dt = (dt - r->rorg[i]) / r->rdir[i];
+            if (dt > t) t = dt;
+        }
+        t += FTINY;
+        if (t >= r->rot) return 0;
+        for (i = 0; i < 3; i++) curpos[i] += r->rdir[i] * t;
+        if (!incube(&scene, curpos)) return 0;
+    }
+    cxset[0] = 0;
+    raymove(s, curpos, cxset, sflags, r, &scene);
+    return r->ro >= 0;
+}
+
+/* ----------------------------------------------------------- shading ---- */
+static void rayvalue(orc_scene* s, RAY* r);
+static int rayshade(orc_scene* s, RAY* r, int mod);
+
+static void rayclear(RAY* r) {
+    int i;
+    r->robj = -1; r->ro = -1; r->rot = FHUGE; r->rod = 1.0; r->aft = 0; r->rflips = 0;
+    for (i = 0; i < 3; i++) { r->rop[i] = r->rorg[i]; r->ron[i] = -r->rdir[i]; r->rcol[i] = 0; }
+}
+
+static int rayorigin(orc_scene* s, RAY* r, int rt, const RAY* ro, const float* rc) {
+    double rw; int i;
+    if (rc == NULL) { rw = 1.0; r->rcoef[0] = r->rcoef[1] = r->rcoef[2] = 1.f; }
+    else { rw = max3f(rc); if (rw > 1.0) rw = 1.0; if (rc != r->rcoef) for (i = 0; i < 3; i++) r->rcoef[i] = rc[i]; }
+    if ((r->parent = ro) == NULL) {
+        r->rlvl = 0; r->rweight = rw; r->crtype = r->rtype = rt; r->rsrc = -1; r->rdepth = 0;
+    } else {
+        if (ro->rot >= FHUGE * .99) { memset(r, 0, sizeof(RAY)); return -1; }
+        r->rlvl = ro->rlvl; r->rsrc = ro->rsrc; r->rdepth = ro->rdepth;
+        if (rt & RAYREFL) { r->rlvl++; if (r->rsrc >= 0) r->rsrc = -1; r->rmax = 0.0; }
+        else r->rmax = (ro->rmax > FTINY) * (ro->rmax - ro->rot);
+        r->crtype = ro->crtype | (r->rtype = rt);
+        for (i = 0; i < 3; i++) r->rorg[i] = ro->rop[i];
+        r->rweight = (float)(ro->rweight * rw);
+    }
+    rayclear(r);
+    if (r->rweight <= 0.0) return -1;
+    if (r->crtype & SHADOW) return 0;
+    if ((s->P.maxdepth <= 0) & (rc != NULL)) {
+        if ((s->P.maxdepth < 0) & (r->rlvl > -s->P.maxdepth)) return -1;
+        if (r->rweight >= s->P.minweight) return 0;
+        if (frandom(s) > r->rweight / s->P.minweight) return -1;
+        rw = s->P.minweight / r->rweight;
+        for (i = 0; i < 3; i++) r->rcoef[i] = (float)(r->rcoef[i] * rw);
+        r->rweight = (float)s->P.minweight;
+        return 0;
+    }
+    return ((r->rweight >= s->P.minweight) & (r->rlvl <= abs(s->P.maxdepth))) ? 0 : -1;
+}
+
+static void raycontrib(float* rc, const RAY* r) {
+    rc[0] = rc[1] = rc[2] = 1.f;
+    while (r != NULL && (r->crtype & PRIMARY)) { rc[0] *= r->rcoef[0]; rc[1] *= r->rcoef[1]; rc[2] *= r->rcoef[2]; r = r->parent; }
+}
+
+static void trace_contrib(orc_scene* s, RAY* r) {
+    int slot, bn, i; double bval; float contr[3]; MOD* m;
+    if (!s->acc || r->ro < 0 || s->objs[r->ro].omod < 0) return;
+    if (r->rsrc >= 0 && s->srcs[r->rsrc].so != r->ro) return;
+    slot = s->otrack[r->ro];
+    if (slot < 0) return;
+    if (s->P.contrib) {
+        for (i = 3; i--;) if (r->rcoef[i] * r->rcol[i] > FTINY) break;
+        if (i < 0) return;
+    } else if (max3f(r->rcoef) <= FTINY) return;
+    m = &s->mods[slot];
+    bval = orc_bin(m->fn, m->mf, m->n, m->u, m->rhs, r->rdir);
+    if (bval <= -.5) return;
+    if ((bn = (int)(bval + .5)) >= m->nbins) return;
+    raycontrib(contr, r);
+    if (s->P.contrib) for (i = 0; i < 3; i++) contr[i] *= r->rcol[i];
+    for (i = 0; i < 3; i++) s->acc[(size_t)(m->col0 + bn) * 3 + i] += contr[i];
+    s->C.contribs++;
+}
+
+static int sourcehit(orc_scene* s, RAY* r) {
+    int glowsrc = -1, first = 0, last = s->nsrcs - 1, i;
+    if (r->rsrc >= 0) first = last = r->rsrc;
+    for (i = first; i <= last; i++) {
+        if (!s->srcs[i].distant) continue;
+        if (2. * PI * (1. - dot(s->srcs[i].sloc, r->rdir)) > s->srcs[i].ss2) continue;
+        if (i == r->rsrc) { r->ro = s->srcs[i].so; break; }
+        if (s->srcs[i].skip) { if (glowsrc < 0) glowsrc = i; continue; }
+        r->ro = s->srcs[i].so;
+        break;
+    }
+    if (r->ro < 0) { if (glowsrc >= 0) r->ro = s->srcs[glowsrc].so; else return 0; }
+    r->robj = r->ro;
+    return 1;
+}
+
+static void raytrans(orc_scene* s, RAY* r) {
+    RAY tr; int i;
+    if (rayorigin(s, &tr, TRANS, r, NULL) < 0) return;
+    for (i = 0; i < 3; i++) tr.rdir[i] = r->rdir[i];
+    rayvalue(s, &tr);
+    for (i = 0; i < 3; i++) r->rcol[i] = tr.rcol[i];
+}
+
+static void raytrace(orc_scene* s, RAY* r) {
+    if (localhit(s, r)) { if (!rayshade(s, r, s->objs[r->ro].omod)) raytrans(s, r); }
+    else if (r->aft) { r->ro = -1; r->rot = FHUGE; }
+    else if (sourcehit(s, r)) rayshade(s, r, s->objs[r->ro].omod);
+    trace_contrib(s, r);
+}
+static void rayvalue(orc_scene* s, RAY* r) { raytrace(s, r); }
+
+typedef struct {
+    RAY* rp; int specfl; float mcolor[3], scolor[3]; double prdir[3], alpha2, rdiff, rspec, trans, tdiff, tspec, pnorm[3], pdot;
+} NORMDAT;
+enum { SP_REFL = 01, SP_TRAN = 02, SP_PURE = 04, SP_FLAT = 010, SP_RBLT = 020, SP_TBLT = 040 };
+#define FRESNE(ci) (exp(-5.85 * (ci)) - 0.00202943064)
+#define FRESTHRESH 0.017999
+
+static void dirnorm(orc_scene* s, float* scval, NORMDAT* np, const double* ldir, double omega) {
+    double ldot, lrdiff, ltdiff, dtmp, d2, d3, d4, vtmp[3]; int k;
+    scval[0] = scval[1] = scval[2] = 0;
+    ldot = dot(np->pnorm, ldir);
+    if (ldot < 0.0 ? np->trans <= FTINY : np->trans >= 1.0 - FTINY) return;
+    lrdiff = np->rdiff; ltdiff = np->tdiff;
+    if (np->specfl & SP_PURE && np->rspec >= FRESTHRESH && (lrdiff > FTINY) | (ltdiff > FTINY)) { dtmp = 1. - FRESNE(fabs(ldot)); lrdiff *= dtmp; ltdiff *= dtmp; }
+    if ((ldot > FTINY) & (lrdiff > FTINY)) { dtmp = ldot * omega * lrdiff * (1.0 / PI); for (k = 0; k < 3; k++) scval[k] += (float)(np->mcolor[k] * dtmp); }
+    if ((ldot < -FTINY) & (ltdiff > FTINY)) { dtmp = -ldot * omega * ltdiff * (1.0 / PI); for (k = 0; k < 3; k++) scval[k] += (float)(np->mcolor[k] * dtmp); }
+    if ((ldot > FTINY) & ((np->specfl & (SP_REFL | SP_PURE)) == SP_REFL)) {
+        dtmp = np->alpha2;
+        if (np->specfl & SP_FLAT) dtmp += (1. - s->P.dstrsrc) * omega * (0.25 / PI);
+        for (k = 0; k < 3; k++) vtmp[k] = ldir[k] - np->rp->rdir[k];
+        d2 = dot(vtmp, np->pnorm); d2 *= d2; d3 = dot(vtmp, vtmp); d4 = (d3 - d2) / d2;
+        dtmp = exp(-d4 / dtmp) * d3 / (PI * d2 * d2 * dtmp);
+        if (dtmp > FTINY) { dtmp *= ldot * omega; for (k = 0; k < 3; k++) scval[k] += (float)(np->scolor[k] * dtmp); }
+    }
+    if ((ldot < -FTINY) & ((np->specfl & (SP_TRAN | SP_PURE)) == SP_TRAN)) {
+        dtmp = np->alpha2 + omega * (1.0 / PI);
+        dtmp = exp((2. * dot(np->prdir, ldir) - 2.) / dtmp) / (PI * dtmp);
+        if (dtmp > FTINY) { dtmp *= np->tspec * omega * sqrt(-ldot / np->pdot); for (k = 0; k < 3; k++) scval[k] += (float)(np->mcolor[k] * dtmp); }
+    }
+}
+
+static void direct(orc_scene* s, RAY* r, NORMDAT* nd) {
+    int sn, k;
+    for (sn = 0; sn < s->nsrcs; sn++) {
+        SRC* src = &s->srcs[sn]; double vpos[3] = {0, 0, 0}, ldir[3]; float coef[3]; RAY sr; int thru;
+        if (src->skip || !src->distant) continue;
+        if (s->P.dstrsrc > FTINY) for (k = 0; k < 3; k++) vpos[k] = s->P.dstrsrc * (1. - 2. * frandom(s));
+        if (s->P.dstrsrc > 0.7) {
+            double d = 1.12837917, t0 = d * sqrt(1.0 - 0.5 * vpos[1] * vpos[1]), t1 = d * sqrt(1.0 - 0.5 * vpos[0] * vpos[0]);
+            vpos[0] *= t0; vpos[1] *= t1; vpos[2] = 0;
+        }
+        for (k = 0; k < 3; k++) ldir[k] = src->sloc[k] + vpos[0] * src->ss[0][k] + vpos[1] * src->ss[1][k] + vpos[2] * src->ss[2][k];
+        if (normalize(ldir) == 0.0) continue;
+        dirnorm(s, coef, nd, ldir, src->ss2);
+        if (max3f(coef) <= 0.0) continue;
+        thru = (r->rod > 0) ^ (dot(r->ron, ldir) > 0);
+        if (rayorigin(s, &sr, thru ? TSHADOW : RSHADOW, r, NULL) < 0) continue;
+        for (k = 0; k < 3; k++) { sr.rcoef[k] = coef[k]; sr.rdir[k] = ldir[k]; }
+        sr.rsrc = sn;
+        if (localhit(s, &sr)) {      /* SFOLLOW: follow entire path */
+            if (!rayshade(s, &sr, s->objs[sr.ro].omod)) raytrans(s, &sr);
+            trace_contrib(s, &sr);
+            if ((sr.rcol[0] + sr.rcol[1] + sr.rcol[2]) / 3. <= FTINY) continue;
+        } else if (sourcehit(s, &sr) && rayshade(s, &sr, s->objs[sr.ro].omod)) trace_contrib(s, &sr);
+        else continue;
+        for (k = 0; k < 3; k++) r->rcol[k] += sr.rcol[k] * coef[k];
+    }
+}
+
+static void square2disk(double* ds, double seedx, double seedy) {
+    double phi, rr, a = 2. * seedx - 1, b = 2. * seedy - 1;
+    if (a > -b) { if (a > b) { rr = a; phi = (PI / 4.) * (b / a); } else { rr = b; phi = (PI / 4.) * (2. - (a / b)); } }
+    else { if (a < b) { rr = -a; phi = (PI / 4.) * (4. + (b / a)); } else { rr = -b; phi = (b != 0.) ? (PI / 4.) * (6. - (a / b)) : 0.; } }
+    rr *= 0.9999999999999;
+    ds[0] = rr * cos(phi); ds[1] = rr * sin(phi);
+}
+
+static int getperp_rand(orc_scene* s, double* vp, const double* v) {
+    double v1[3]; int ord[3], i;
+    v1[0] = 0.5 - frandom(s); v1[1] = 0.5 - frandom(s); v1[2] = 0.5 - frandom(s);
+    switch ((int)(6 * frandom(s))) {
+    case 0: ord[0] = 0; ord[1] = 1; ord[2] = 2; break;
+    case 1: ord[0] = 0; ord[1] = 2; ord[2] = 1; break;
+    case 2: ord[0] = 1; ord[1] = 0; ord[2] = 2; break;
+    case 3: ord[0] = 1; ord[1] = 2; ord[2] = 0; break;
+    case 4: ord[0] = 2; ord[1] = 0; ord[2] = 1; break;
+    default: ord[0] = 2; ord[1] = 1; ord[2] = 0; break;
+    }
+    for (i = 3; i--;) if ((-0.6 < v[ord[i]]) & (v[ord[i]] < 0.6)) break;
+    if (i < 0) return 0;
+    v1[ord[i]] = 1.0; cross(vp, v1, v);
+    return normalize(vp) > 0.0;
+}
+
+static void multambient(orc_scene* s, float* aval, RAY* r, const double* nrm) {
+    double d, wt, rdot, onrm[3], ux[3], uy[3]; int n, i, j, k, sgn, atyp; float acoef[3], acol[3] = {0, 0, 0};
+    if (s->P.ambdiv <= 0 || r->rdepth >= s->P.ambounce) goto dumbamb;
+    rdot = dot(nrm, r->ron); sgn = 1 - 2 * (rdot < 0);
+    wt = r->rweight * sgn;
+    d = max3f(aval);
+    if (d <= FTINY) goto dumbamb;
+    atyp = RAMBIENT;
+    for (k = 0; k < 3; k++) onrm[k] = r->ron[k];
+    if (wt < 0) { wt = -wt; atyp = TAMBIENT; for (k = 0; k < 3; k++) onrm[k] = -onrm[k]; }
+    if (wt > (d *= 0.8 * r->rweight / (s->P.ambdiv * s->P.minweight + 1e-20))) wt = d;
+    n = (int)(sqrt(s->P.ambdiv * wt) + 0.5);
+    if (n < 1) n = 1;
+    d = 1.0 / (n * n);
+    for (k = 0; k < 3; k++) acoef[k] = (float)(aval[k] * d);
+    if (!getperp_rand(s, ux, onrm)) goto dumbamb;
+    cross(uy, onrm, ux);
+    for (i = n; i--;) for (j = n; j--;) {
+        RAY ar; double ss0, ss1, spt[2], zd;
+        for (k = 0; k < 3; k++) ar.rcoef[k] = acoef[k];
+        if (rayorigin(s, &ar, atyp, r, ar.rcoef) < 0) continue;
+        ar.rdepth = r->rdepth + 1;
+        ss0 = frandom(s); ss1 = frandom(s);
+        square2disk(spt, (j + ss1) / n, (i + ss0) / n);
+        zd = sqrt(1. - spt[0] * spt[0] - spt[1] * spt[1]);
+        for (k = 0; k < 3; k++) ar.rdir[k] = spt[0] * ux[k] + spt[1] * uy[k] + zd * onrm[k];
+        normalize(ar.rdir);
+        rayvalue(s, &ar);
+        for (k = 0; k < 3; k++) acol[k] += ar.rcol[k] * ar.rcoef[k];
+    }
+    for (k = 0; k < 3; k++) aval[k] = acol[k];
+    return;
+dumbamb:
+    for (k = 0; k < 3; k++) aval[k] = (float)(aval[k] * s->P.ambval[k]);
+}
+
+static int m_normal(orc_scene* s, int mtype, const double* a, RAY* r, int ro_flat) {
+    NORMDAT nd; double fest, d; float sctmp[3]; int i, k;
+    if (r->crtype & SHADOW && mtype != T_TRANS) return 1;
+    if (r->rod < 0.0) {
+        if (!s->P.backvis) { raytrans(s, r); return 1; }
+        r->rod = -r->rod; for (k = 0; k < 3; k++) r->ron[k] = -r->ron[k];
+        r->rflips++;
+    }
+    nd.rp = r;
+    for (k = 0; k < 3; k++) nd.mcolor[k] = (float)a[k];
+    nd.specfl = 0; nd.alpha2 = a[4];
+    if ((nd.alpha2 *= nd.alpha2) <= FTINY) nd.specfl |= SP_PURE;
+    for (k = 0; k < 3; k++) nd.pnorm[k] = r->ron[k];
+    nd.pdot = r->rod;
+    if (ro_flat) nd.specfl |= SP_FLAT;
+    if (nd.pdot < .001) nd.pdot = .001;
+    nd.rspec = a[3];
+    if (nd.specfl & SP_PURE && nd.rspec >= FRESTHRESH) { fest = FRESNE(nd.pdot); nd.rspec += fest * (1. - nd.rspec); } else fest = 0.;
+    if (mtype == T_TRANS) {
+        nd.trans = a[5] * (1.0 - nd.rspec); nd.tspec = nd.trans * a[6]; nd.tdiff = nd.trans - nd.tspec;
+        if (nd.tspec > FTINY) {
+            nd.specfl |= SP_TRAN;
+            if (!(nd.specfl & SP_PURE) && s->P.specthresh >= nd.tspec - FTINY) nd.specfl |= SP_TBLT;
+            for (k = 0; k < 3; k++) nd.prdir[k] = r->rdir[k];
+        }
+    } else nd.tdiff = nd.tspec = nd.trans = 0.0;
+    nd.rdiff = 1.0 - nd.trans - nd.rspec;
+    if ((nd.specfl & (SP_TRAN | SP_PURE | SP_TBLT)) == (SP_TRAN | SP_PURE)) {
+        RAY lr;
+        for (k = 0; k < 3; k++) lr.rcoef[k] = (float)(nd.mcolor[k] * nd.tspec);
+        if (rayorigin(s, &lr, TRANS, r, lr.rcoef) == 0) {
+            for (k = 0; k < 3; k++) lr.rdir[k] = nd.prdir[k];
+            rayvalue(s, &lr);
+            for (k = 0; k < 3; k++) r->rcol[k] += lr.rcol[k] * lr.rcoef[k];
+        }
+    }
+    if (r->crtype & SHADOW) return 1;
+    nd.scolor[0] = nd.scolor[1] = nd.scolor[2] = 0;
+    if (nd.rspec > FTINY) {
+        nd.specfl |= SP_REFL;
+        if (mtype != T_METAL) nd.scolor[0] = nd.scolor[1] = nd.scolor[2] = (float)nd.rspec;
+        else if (fest > FTINY) { d = a[3] * (1. - fest); for (i = 3; i--;) nd.scolor[i] = (float)(fest + nd.mcolor[i] * d); }
+        else for (k = 0; k < 3; k++) nd.scolor[k] = (float)(nd.mcolor[k] * nd.rspec);
+        if (!(nd.specfl & SP_PURE) && s->P.specthresh >= nd.rspec - FTINY) nd.specfl |= SP_RBLT;
+    }
+    if ((nd.specfl & (SP_REFL | SP_PURE | SP_RBLT)) == (SP_REFL | SP_PURE)) {
+        RAY lr;
+        if (rayorigin(s, &lr, REFLECTED, r, nd.scolor) == 0) {
+            for (k = 0; k < 3; k++) lr.rdir[k] = r->rdir[k] + nd.pnorm[k] * (2. * nd.pdot);
+            normalize(lr.rdir);
+            rayvalue(s, &lr);
+            for (k = 0; k < 3; k++) r->rcol[k] += lr.rcol[k] * lr.rcoef[k];
+        }
+    }
+    if (nd.specfl & SP_PURE && nd.rdiff <= FTINY && nd.tdiff <= FTINY) return 1;
+    if (!(nd.specfl & SP_PURE)) {      /* gaussamp(), single-sample form */
+        double u[3], v[3], h[3], rv0, rv1, cosp, sinp; RAY sr; int ntr;
+        if (getperp_rand(s, u, nd.pnorm)) {
+            cross(v, nd.pnorm, u);
+            if ((nd.specfl & (SP_REFL | SP_RBLT)) == SP_REFL && rayorigin(s, &sr, RSPECULAR, r, nd.scolor) == 0) {
+                for (ntr = 0; ntr < 10; ntr++) {
+                    rv0 = frandom(s); rv1 = frandom(s);
+                    cosp = cos(2.0 * PI * rv0); sinp = sin(2.0 * PI * rv0);
+                    if ((0. <= s->P.specjitter) & (s->P.specjitter < 1.)) rv1 = 1.0 - s->P.specjitter * rv1;
+                    d = (rv1 <= FTINY) ? 1.0 : sqrt(nd.alpha2 * -log(rv1));
+                    for (k = 0; k < 3; k++) h[k] = nd.pnorm[k] + d * (cosp * u[k] + sinp * v[k]);
+                    d = -2.0 * dot(h, r->rdir) / (1.0 + d * d);
+                    for (k = 0; k < 3; k++) sr.rdir[k] = r->rdir[k] + h[k] * d;
+                    if (dot(sr.rdir, r->ron) <= FTINY) continue;
+                    normalize(sr.rdir);
+                    rayvalue(s, &sr);
+                    for (k = 0; k < 3; k++) r->rcol[k] += sr.rcol[k] * sr.rcoef[k];
+                    break;
+                }
+            }
+            for (k = 0; k < 3; k++) sr.rcoef[k] = (float)(nd.mcolor[k] * nd.tspec);
+            if ((nd.specfl & (SP_TRAN | SP_TBLT)) == SP_TRAN && rayorigin(s, &sr, TSPECULAR, r, sr.rcoef) == 0) {
+                for (ntr = 0; ntr < 10; ntr++) {
+                    rv0 = frandom(s); rv1 = frandom(s);
+                    cosp = cos(2.0 * PI * rv0); sinp = sin(2.0 * PI * rv0);
+                    if ((0. <= s->P.specjitter) & (s->P.specjitter < 1.)) rv1 = 1.0 - s->P.specjitter * rv1;
+                    d = (rv1 <= FTINY) ? 1.0 : sqrt(nd.alpha2 * -log(rv1));
+                    for (k = 0; k < 3; k++) sr.rdir[k] = nd.prdir[k] + d * (cosp * u[k] + sinp * v[k]);
+                    if (dot(sr.rdir, r->ron) >= -FTINY) continue;
+                    normalize(sr.rdir);
+                    rayvalue(s, &sr);
+                    for (k = 0; k < 3; k++) r->rcol[k] += sr.rcol[k] * sr.rcoef[k];
+                    break;
+                }
+            }
+        }
+    }
+    if (nd.rdiff > FTINY) {
+        for (k = 0; k < 3; k++) sctmp[k] = (float)(nd.mcolor[k] * nd.rdiff);
+        if (nd.specfl & SP_RBLT) for (k = 0; k < 3; k++) sctmp[k] += nd.scolor[k];
+        multambient(s, sctmp, r, nd.pnorm);
+        for (k = 0; k < 3; k++) r->rcol[k] += sctmp[k];
+    }
+    if (nd.tdiff > FTINY) {
+        double bnorm[3];
+        for (k = 0; k < 3; k++) { sctmp[k] = (float)(nd.mcolor[k] * ((nd.specfl & SP_TBLT) ? nd.trans : nd.tdiff)); bnorm[k] = -nd.pnorm[k]; }
+        multambient(s, sctmp, r, bnorm);
+        for (k = 0; k < 3; k++) r->rcol[k] += sctmp[k];
+    }
+    direct(s, r, &nd);
+    return 1;
+}
+
+static int m_glass(orc_scene* s, const OBJ* m, RAY* r) {
+    double mcolor[3], ctemp[3], pdot, rindex, cos2, d, r1e, r1m; float scoef[3]; int hastrans, i; RAY p;
+    if (m->nfargs == 3) rindex = 1.52; else if (m->nfargs == 4) rindex = m->fargs[3]; else { fail(s, "bad arguments for glass", m->name); return 1; }
+    if (!s->P.backvis && r->rod <= 0.0) { raytrans(s, r); return 1; }
+    for (i = 0; i < 3; i++) mcolor[i] = (float)m->fargs[i];
+    hastrans = (mcolor[0] > mcolor[1] ? (mcolor[0] > mcolor[2] ? mcolor[0] : mcolor[2]) : (mcolor[1] > mcolor[2] ? mcolor[1] : mcolor[2])) > 1e-15;
+    if (hastrans) { for (i = 0; i < 3; i++) if (mcolor[i] < 1e-15) mcolor[i] = 1e-15; }
+    else if (r->crtype & SHADOW) return 1;
+    if (r->rod < 0.0) { r->rod = -r->rod; for (i = 0; i < 3; i++) r->ron[i] = -r->ron[i]; r->rflips++; }
+    pdot = r->rod;
+    cos2 = sqrt((1.0 - 1.0 / (rindex * rindex)) + pdot * pdot / (rindex * rindex));
+    if (hastrans) for (i = 0; i < 3; i++) mcolor[i] = (float)pow(mcolor[i], 1.0 / cos2);
+    r1e = (pdot - rindex * cos2) / (pdot + rindex * cos2); r1e *= r1e;
+    r1m = (1.0 / pdot - rindex / cos2) / (1.0 / pdot + rindex / cos2); r1m *= r1m;
+    if (hastrans) {
+        for (i = 0; i < 3; i++) {
+            d = mcolor[i];
+            ctemp[i] = .5 * (1.0 - r1e) * (1.0 - r1e) * d / (1.0 - r1e * r1e * d * d) + .5 * (1.0 - r1m) * (1.0 - r1m) * d / (1.0 - r1m * r1m * d * d);
+            scoef[i] = (float)ctemp[i];
+        }
+        if (rayorigin(s, &p, TRANS, r, scoef) == 0) {
+            for (i = 0; i < 3; i++) p.rdir[i] = r->rdir[i];
+            rayvalue(s, &p);
+            for (i = 0; i < 3; i++) r->rcol[i] += p.rcol[i] * p.rcoef[i];
+        }
+    }
+    if (r->crtype & SHADOW) return 1;
+    for (i = 0; i < 3; i++) {
+        d = mcolor[i]; d *= d;
+        ctemp[i] = .5 * r1e * (1.0 + (1.0 - 2.0 * r1e) * d) / (1.0 - r1e * r1e * d) + .5 * r1m * (1.0 + (1.0 - 2.0 * r1m) * d) / (1.0 - r1m * r1m * d);
+        scoef[i] = (float)ctemp[i];
+    }
+    if (rayorigin(s, &p, REFLECTED, r, scoef) == 0) {
+        for (i = 0; i < 3; i++) p.rdir[i] = r->rdir[i] + r->ron[i] * (2. * pdot);
+        normalize(p.rdir);
+        rayvalue(s, &p);
+        for (i = 0; i < 3; i++) r->rcol[i] += p.rcol[i] * p.rcoef[i];
+    }
+    return 1;
+}
+
+static int m_light(orc_scene* s, const OBJ* m, RAY* r) {
+    int isglow = m->otype == T_GLOW, k;
+#define distglow(d) (isglow && m->fargs[3] >= -FTINY && (d) > m->fargs[3])
+    if ((r->crtype & (AMBIENT | SPECULAR)) && !((r->crtype & SHADOW) || r->rod < 0.0 || distglow(r->rot))) { r->rcoef[0] = r->rcoef[1] = r->rcoef[2] = 0; return 1; }
+    if (r->rsrc >= 0 && s->srcs[r->rsrc].so != r->ro) {
+        int illumblock = 0;
+        if (m->otype == T_ILLUM) { int sm = matof(s, s->srcs[r->rsrc].so); illumblock = r->rod > 0.0 && sm >= 0 && (s->objs[sm].otype == T_ILLUM || s->objs[sm].otype == T_GLOW); }
+        if (m->otype != T_ILLUM || illumblock) { r->rcoef[0] = r->rcoef[1] = r->rcoef[2] = 0; return 1; }
+    }
+    if (m->otype == T_ILLUM && (r->rsrc < 0 || s->srcs[r->rsrc].so != r->ro)) {
+        if (m->nsargs && strcmp(m->sargs[0], "void")) return rayshade(s, r, lastmod(s, (int)(m - s->objs), m->sargs[0]));
+        raytrans(s, r); return 1;
+    }
+    if (!(s->P.directvis || (r->crtype & SHADOW) || distglow(r->rot))) { r->rcoef[0] = r->rcoef[1] = r->rcoef[2] = 0; return 1; }
+    if (r->rod < 0.0) { if (!s->P.backvis) raytrans(s, r); return 1; }
+    /* a pattern under an emitter (e.g. brightfunc sky) is ignored: the value is the plain
+       material RGB; coefficients (-V-) do not depend on it.  Tests compare geometry only there. */
+    for (k = 0; k < 3; k++) r->rcol[k] = (float)m->fargs[k];
+    return 1;
+#undef distglow
+}
+
+static int rayshade(orc_scene* s, RAY* r, int mod) {
+    int tst_irrad = s->P.do_irrad && !(r->crtype & ~(PRIMARY | TRANS));
+    static const double lamb[5] = {PI, PI, PI, 0, 0};
+    for (; mod >= 0; mod = s->objs[mod].omod) {
+        OBJ* m = &s->objs[mod]; int t = m->otype;
+        int flat = r->ro >= 0 && (s->objs[r->ro].otype == T_POLYGON || s->objs[r->ro].otype == T_RING);
+        if (t == T_ALIAS) { if (m->nsargs) { int tgt = findmaterial(s, mod); if (tgt < 0) return 0; m = &s->objs[tgt]; t = m->otype; } else continue; }
+        if (tst_irrad && is_material(t)) {
+            if (is_transp(t)) { raytrans(s, r); return 1; }
+            if (!is_light(t)) return m_normal(s, T_PLASTIC, lamb, r, flat);
+        }
+        switch (t) {
+        case T_PLASTIC: case T_METAL: if (m->nfargs != 5) { fail(s, "bad arguments for", m->name); return 1; } return m_normal(s, t, m->fargs, r, flat);
+        case T_TRANS: if (m->nfargs != 7) { fail(s, "bad arguments for", m->name); return 1; } return m_normal(s, t, m->fargs, r, flat);
+        case T_GLASS: return m_glass(s, m, r);
+        case T_GLOW: case T_LIGHT: case T_ILLUM: return m_light(s, m, r);
+        default: fail(s, "unsupported modifier reached by the oracle:", m->name); return 1;
+        }
+    }
+    return 0;
+}
+
+/* -I entries: 1 rtrace (rtrace.c:415-448), 2 rcontrib (rcontrib.c:321-339), 3 manager (RtraceSimulManager.cpp:315-335) */
+static void eval_ray(orc_scene* s, const double* org, const double* dir_in, int irrad, orc_result* out) {
+    RAY r; double dir[3] = {dir_in[0], dir_in[1], dir_in[2]}; int k;
+    static const double lamb[5] = {PI, PI, PI, 0, 0};
+    memset(&r, 0, sizeof(r));
+    if (normalize(dir) == 0.0) { if (out) { memset(out, 0, sizeof(*out)); out->robj = out->omod = -1; } return; }
+    if (!irrad) {
+        for (k = 0; k < 3; k++) { r.rorg[k] = org[k]; r.rdir[k] = dir[k]; }
+        r.rmax = 0; rayorigin(s, &r, PRIMARY, NULL, NULL);
+        rayvalue(s, &r);
+    } else {
+        for (k = 0; k < 3; k++) { r.rorg[k] = org[k] + 1.1e-4 * dir[k]; r.rdir[k] = -dir[k]; }
+        r.rmax = 0; rayorigin(s, &r, PRIMARY, NULL, NULL);
+        r.rod = 1.0;
+        if (irrad == 1) { r.rot = 1e-5; for (k = 0; k < 3; k++) { r.rop[k] = r.rorg[k] + r.rdir[k] * r.rot; r.ron[k] = -r.rdir[k]; } }
+        else if (irrad == 2) { r.rot = 1e-5; for (k = 0; k < 3; k++) { r.ron[k] = dir[k]; r.rop[k] = org[k] + 1e-4 * dir[k]; } }
+        else { r.rot = 1e-4; for (k = 0; k < 3; k++) { r.ron[k] = dir[k]; r.rop[k] = org[k] + r.ron[k] * r.rot; r.rorg[k] = r.rop[k] + r.ron[k] * r.rot; } }
+        m_normal(s, T_PLASTIC, lamb, &r, 0);
+    }
+    if (out) {
+        /* rtrace -oN undoes surface flips (rtrace.c oputN) */
+        for (k = 0; k < 3; k++) { out->rop[k] = r.rop[k]; out->ron[k] = (r.rflips & 1) ? -r.ron[k] : r.ron[k]; out->value[k] = r.rcol[k]; }
+        out->rot = r.rot; out->rod = (r.rflips & 1) ? -r.rod : r.rod; out->robj = r.ro;
+        out->omod = r.ro >= 0 ? s->objs[r.ro].omod : -1;
+    }
+}
+
+int orc_rtrace(orc_scene* s, const double* rays, size_t nrays, int irrad, orc_result* out) {
+    size_t i;
+    s->failed = 0; s->err[0] = 0;
+    free(s->acc); s->acc = NULL;
+    for (i = 0; i < nrays && !s->failed; i++) eval_ray(s, rays + 6 * i, rays + 6 * i + 3, irrad, out ? out + i : NULL);
+    return s->failed ? -1 : 0;
+}
+
+int orc_rcontrib(orc_scene* s, const double* rays, size_t nrays, int accum, int irrad, double* out) {
+    size_t i, nrec, ncv = (size_t)s->ncols * 3, k;
+    if (accum < 1) accum = 1;
+    nrec = (nrays + accum - 1) / accum;
+    s->failed = 0; s->err[0] = 0;
+    free(s->acc); s->acc = (double*)calloc(ncv ? ncv : 1, sizeof(double));
+    for (i = 0; i < nrec && !s->failed; i++) {
+        size_t j, n0 = i * accum, n1 = n0 + accum > nrays ? nrays : n0 + accum;
+        memset(s->acc, 0, sizeof(double) * ncv);
+        for (j = n0; j < n1; j++) eval_ray(s, rays + 6 * j, rays + 6 * j + 3, irrad, NULL);
+        for (k = 0; k < ncv; k++) out[i * ncv + k] = accum > 1 ? s->acc[k] / accum : s->acc[k];
+    }
+    free(s->acc); s->acc = NULL;
+    return s->failed ? -1 : 0;
+}

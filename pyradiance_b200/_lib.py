@@ -51,6 +51,7 @@ RB_FLAG_LIMDIST = 4
 RB_FLAG_CONTRIB = 8
 RB_FLAG_RAYS_ON_DEVICE = 16
 RB_FLAG_OUT_ON_DEVICE = 32
+RB_FLAG_OUT_DOUBLE = 64
 RB_PROGRAM_RTRACE, RB_PROGRAM_RCONTRIB = 0, 1
 
 # every symbol include/rb200.h declares: (name, restype, argtypes)
@@ -239,14 +240,16 @@ class Context:
         return v.value
 
     # ---- compute ----
-    def rcontrib(self, rays, accum=1, flags=RB_IRRAD_NONE, row_base=0, out=None):
+    def rcontrib(self, rays, accum=1, flags=RB_IRRAD_NONE, row_base=0, out=None, dtype=np.float32):
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
         n = rays.shape[0]
         nrec = (n + accum - 1) // accum
         ncols = self.num_columns()
         if out is None:
-            out = np.empty((nrec, ncols, 3), dtype=np.float32)
-        assert out.dtype == np.float32 and out.flags["C_CONTIGUOUS"] and out.size >= nrec * ncols * 3
+            out = np.empty((nrec, ncols, 3), dtype=dtype)
+        assert out.dtype in (np.float32, np.float64) and out.flags["C_CONTIGUOUS"] and out.size >= nrec * ncols * 3
+        if out.dtype == np.float64:
+            flags |= RB_FLAG_OUT_DOUBLE
         self._ck(self.lib.rb_rcontrib(self.h, rays.ctypes.data, n, int(accum), int(flags), int(row_base),
                                       out.ctypes.data, out.size))
         return out

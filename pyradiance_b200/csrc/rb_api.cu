@@ -533,7 +533,7 @@ int rb_bin_of_direction(rb_ctx* c, int mi, const double dir[3], double* binval) 
 }
 
 int rb_rcontrib(rb_ctx* c, const double* rays, size_t nrays, int accum, unsigned flags, uint64_t row_base,
-                float* out, size_t out_floats) {
+                void* out, size_t out_floats) {
     if (!c->cuda_ok) return fail(c, c->cuda_err);
     if (!c->loaded) return fail(c, "no octree loaded");
     if (c->mods.empty()) return fail(c, "missing required modifier argument");
@@ -547,6 +547,7 @@ int rb_rcontrib(rb_ctx* c, const double* rays, size_t nrays, int accum, unsigned
     job.rays = rays; job.nrays = nrays; job.accum = accum;
     job.rays_on_device = flags & RB_FLAG_RAYS_ON_DEVICE;
     job.cmat = out; job.cmat_on_device = flags & RB_FLAG_OUT_ON_DEVICE;
+    job.cmat_double = flags & RB_FLAG_OUT_DOUBLE;
     job.irrad = flags & RB_FLAG_IRRAD_MASK; job.lim_dist = flags & RB_FLAG_LIMDIST;
     job.row_base = row_base;
     // rcontrib overrides (rt/rcmain.c:164-171): -dt 0 -as 0 -aa 0

@@ -207,10 +207,11 @@ __global__ void __launch_bounds__(256) k_expand(const WaveArgs A, const ExpandAr
 }
 
 // rc2.c:293-335 put_contrib(): record value = accumulated sum / accumulate count
-__global__ void k_finish(const double* __restrict__ acc, float* __restrict__ out, size_t n, double scale) {
+template <class T>
+__global__ void k_finish(const double* __restrict__ acc, T* __restrict__ out, size_t n, double scale) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) out[i] = (float)(acc[i] * scale);
+    for (; i < n; i += stride) out[i] = (T)(acc[i] * scale);
 }
 
 // ---------------------------------------------------------------- host -----
@@ -453,20 +454,22 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
     // ---- outputs ----
     if (want_c) {
         double scale = accum > 1 ? 1.0 / accum : 1.0;
-        float* dst;
+        const size_t esz = job.cmat_double ? sizeof(double) : sizeof(float);
+        char* dst;
         size_t off = rec0 * (size_t)ncols_ * 3;
-        if (job.cmat_on_device) dst = job.cmat + off;
+        if (job.cmat_on_device) dst = (char*)job.cmat + off * esz;
         else {
-            if (!ensure_buf(d_out_, out_bytes_, accn * sizeof(float), err)) return false;
-            dst = d_out_;
+            if (!ensure_buf(d_out_, out_bytes_, accn * esz, err)) return false;
+            dst = (char*)d_out_;
         }
         unsigned grid = (unsigned)std::min<size_t>((accn + 255) / 256, 148 * 16);
         CK(cudaEventRecord(ev0_, stream_));
-        k_finish<<<grid, 256, 0, stream_>>>(d_acc_, dst, accn, scale);
+        if (job.cmat_double) k_finish<double><<<grid, 256, 0, stream_>>>(d_acc_, (double*)dst, accn, scale);
+        else k_finish<float><<<grid, 256, 0, stream_>>>(d_acc_, (float*)dst, accn, scale);
         CK(cudaEventRecord(ev1_, stream_));
         stats.launches++;
         if (!job.cmat_on_device)
-            CK(cudaMemcpyAsync(job.cmat + off, d_out_, accn * sizeof(float), cudaMemcpyDeviceToHost, stream_));
+            CK(cudaMemcpyAsync((char*)job.cmat + off * esz, d_out_, accn * esz, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
         if (!timed(stats.kernel_ms, err)) return false;
     }

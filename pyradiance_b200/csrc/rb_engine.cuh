@@ -28,7 +28,8 @@ struct TraceJob {
     int irrad = IRR_NONE;
     bool lim_dist = false;
     // outputs (any may be null)
-    float* cmat = nullptr;            // [nrows][ncols][3] coefficients
+    void* cmat = nullptr;             // [nrows][ncols][3] coefficients, float32 (or float64)
+    bool cmat_double = false;
     bool cmat_on_device = false;
     double* values = nullptr;         // [nrows][3] radiance/irradiance (host)
     RayResult* results = nullptr;     // [nrays] primary-hit reports (host)
@@ -68,7 +69,7 @@ private:
     double* d_acc_ = nullptr; size_t acc_bytes_ = 0;
     double* d_vacc_ = nullptr; size_t vacc_bytes_ = 0;
     double* d_rays_ = nullptr; size_t rays_bytes_ = 0;
-    float* d_out_ = nullptr; size_t out_bytes_ = 0;
+    char* d_out_ = nullptr; size_t out_bytes_ = 0;
     RayResult* d_res_ = nullptr; size_t res_bytes_ = 0;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev2_ = nullptr, ev3_ = nullptr;
     HitRec* d_hits_ = nullptr;

@@ -122,7 +122,7 @@ __device__ __noinline__ bool hit_object(const DScene& S, int id, const double or
         double p[3] = {org[0] + t * dir[0], org[1] + t * dir[1], org[2] + t * dir[2]};
         double x = xi == 0 ? p[0] : xi == 1 ? p[1] : p[2];
         double y = yi == 0 ? p[0] : yi == 1 ? p[1] : p[2];
-        if (!inface2d(g + 4, (hd.x >> 16) & 0xffff, x, y)) return false;
+        if (!inface2d(g + 8, (hd.x >> 16) & 0xffff, x, y)) return false;
         h.robj = id; h.rot = t; h.rod = rdot;
         return true;
     }
@@ -279,7 +279,15 @@ __device__ __forceinline__ void hit_face(const DScene& S, int id, int4 hd, const
     double p0 = org[0] + t * dir[0], p1 = org[1] + t * dir[1], p2 = org[2] + t * dir[2];
     double x = ax == 0 ? p1 : ax == 1 ? p2 : p0;      // xi = (ax+1)%3
     double y = ax == 0 ? p2 : ax == 1 ? p0 : p1;      // yi = (ax+2)%3
-    if (!inface2d(g + 4, (hd.x >> 16) & 0xffff, x, y)) return;
+    // 2-D bounding box first: outside by more than FTINY can never be "in"
+    // (no edge straddles y / all straddling edges on one side, and none of
+    // inface()'s three FABSEQ cases can fire); well inside an exact axis-aligned
+    // rectangle is always "in".  Only the FTINY border zone runs the edge loop.
+    double2 bx = __ldg(&g2[2]), by = __ldg(&g2[3]);
+    if ((x < bx.x - RB_FTINY) | (x > bx.y + RB_FTINY) | (y < by.x - RB_FTINY) | (y > by.y + RB_FTINY)) return;
+    bool in = ((hd.x >> 12) & 1) && (x > bx.x + RB_FTINY) & (x < bx.y - RB_FTINY) & (y > by.x + RB_FTINY) &
+                                        (y < by.y - RB_FTINY);
+    if (!in && !inface2d(g + 8, (hd.x >> 16) & 0xffff, x, y)) return;
     h.robj = id; h.rot = t; h.rod = rdot;
 }
 
@@ -338,61 +346,43 @@ __device__ __forceinline__ bool localhit(const DScene& S, bool active, const dou
     unsigned ix = 0, iy = 0, iz = 0;
     double size = cs;                   // size of the current cube (level L)
     const int2* __restrict__ pool = reinterpret_cast<const int2*>(S.leafpool);
+    bool need_adv = false;              // current leaf is finished: step to the neighbour first
     while (!__all_sync(0xffffffffu, done)) {
-        // ---- phase A: descend to a leaf (raymove, raytrace.c:668-687) ----
+        // ---- phase A: walk (descend / skip empty cubes) until standing in a
+        //      fresh full leaf.  One loop, two short bodies, so lanes re-join
+        //      every iteration (raymove, raytrace.c:668-738) ----
         if (!done) {
-            while (w >= 0) {
-                stk[L * stride] = w;
-                double half = size * 0.5;
+            for (;;) {
+                if (w >= 0) {                         // descend one level
+                    stk[L * stride] = w;
+                    double half = size * 0.5;
+                    double lox = fma((double)ix, size, S.cuorg[0]);
+                    double loy = fma((double)iy, size, S.cuorg[1]);
+                    double loz = fma((double)iz, size, S.cuorg[2]);
+                    int br = 0;
+                    ix <<= 1; iy <<= 1; iz <<= 1;
+                    if (pos[0] >= lox + half) { br |= 1; ix |= 1; }
+                    if (pos[1] >= loy + half) { br |= 2; iy |= 1; }
+                    if (pos[2] >= loz + half) { br |= 4; iz |= 1; }
+                    w = __ldg(&S.nodes[(size_t)w * 8 + br]);
+                    ws.nodes++;
+                    size = half; L++;
+                    continue;
+                }
+                if ((w < -1) & !need_adv) break;      // arrived at a full leaf
                 double lox = fma((double)ix, size, S.cuorg[0]);
                 double loy = fma((double)iy, size, S.cuorg[1]);
                 double loz = fma((double)iz, size, S.cuorg[2]);
-                int br = 0;
-                ix <<= 1; iy <<= 1; iz <<= 1;
-                if (pos[0] >= lox + half) { br |= 1; ix |= 1; }
-                if (pos[1] >= loy + half) { br |= 2; iy |= 1; }
-                if (pos[2] >= loz + half) { br |= 4; iz |= 1; }
-                w = __ldg(&S.nodes[(size_t)w * 8 + br]);
-                ws.nodes++;
-                size = half; L++;
-            }
-        }
-        __syncwarp();
-        // ---- phase B: test the leaf's surfaces, highest index first (rayhit) ----
-        {
-            int cnt = 0;
-            const int2* set = pool;
-            if (!done && w < -1) {
-                set = pool + (-w - 2);
-                cnt = __ldg(&set[0]).x;
-                ws.leafents += cnt + 1;
-                ws.prims += cnt;
-            }
-            for (int k = cnt; k > 0; k--) {
-                int2 ent = __ldg(&set[k]);
-                const double* g = S.geom + ent.y;
-                int4 hd = __ldg(reinterpret_cast<const int4*>(g - 2));
-                if ((hd.x & 0xff) == PK_FACE) hit_face(S, ent.x, hd, g, org, dir, h, aft);
-                else hit_object(S, ent.x, org, dir, h, aft, errflag, errobj);
-            }
-        }
-        __syncwarp();
-        // ---- phase C: accept the hit or step to the neighbour cube ----
-        if (!done) {
-            double lox = fma((double)ix, size, S.cuorg[0]);
-            double loy = fma((double)iy, size, S.cuorg[1]);
-            double loz = fma((double)iz, size, S.cuorg[2]);
-            double hix = lox + size, hiy = loy + size, hiz = loz + size;
-            if (w < -1 ? (h.robj >= 0) : (aft && h.robj < 0)) {
-                // checkhit (raytrace.c:756-759) / aft-plane point in an empty leaf (:709-710)
-                double px = org[0] + h.rot * dir[0];
-                double py = org[1] + h.rot * dir[1];
-                double pz = org[2] + h.rot * dir[2];
-                if (!(lox > px || px >= hix || loy > py || py >= hiy || loz > pz || pz >= hiz)) {
-                    done = true; result = (w < -1);
+                double hix = lox + size, hiy = loy + size, hiz = loz + size;
+                if ((w == -1) & aft & (h.robj < 0)) { // aft-plane point in an empty leaf (:709-710)
+                    double px = org[0] + h.rot * dir[0];
+                    double py = org[1] + h.rot * dir[1];
+                    double pz = org[2] + h.rot * dir[2];
+                    if (!(lox > px || px >= hix || loy > py || py >= hiy || loz > pz || pz >= hiz)) {
+                        done = true; result = false;
+                        break;
+                    }
                 }
-            }
-            if (!done) {
                 // advance to next cube (raytrace.c:712-738)
                 int ax = 0;
                 double t;
@@ -419,18 +409,51 @@ __device__ __forceinline__ bool localhit(const DScene& S, bool active, const dou
                 unsigned ia = ax == 0 ? ix : ax == 1 ? iy : iz;
                 unsigned blocked = positive ? ia : ~ia;            // trailing ones = levels to climb
                 int up = (~blocked) ? __ffs(~blocked) - 1 : 32;    // number of trailing one bits
-                if (up >= L) { done = true; result = (h.robj >= 0); }   // left the scene cube
-                else {
-                    ix >>= up; iy >>= up; iz >>= up; L -= up;
-                    size = ldexp(size, up);
-                    if (ax == 0) ix ^= 1; else if (ax == 1) iy ^= 1; else iz ^= 1;
-                    int br = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
-                    w = __ldg(&S.nodes[(size_t)stk[(L - 1) * stride] * 8 + br]);
-                    ws.nodes++;
-                }
+                if (up >= L) { done = true; result = (h.robj >= 0); break; }   // left the scene cube
+                ix >>= up; iy >>= up; iz >>= up; L -= up;
+                size = ldexp(size, up);
+                if (ax == 0) ix ^= 1; else if (ax == 1) iy ^= 1; else iz ^= 1;
+                int br = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
+                w = __ldg(&S.nodes[(size_t)stk[(L - 1) * stride] * 8 + br]);
+                ws.nodes++;
+                need_adv = false;
             }
         }
         __syncwarp();
+        // ---- phase B: test the leaf's surfaces, highest index first (rayhit) ----
+        {
+            int cnt = 0;
+            const int2* set = pool;
+            if (!done) {
+                set = pool + (-w - 2);
+                cnt = __ldg(&set[0]).x;
+                ws.leafents += cnt + 1;
+                ws.prims += cnt;
+            }
+            for (int k = cnt; k > 0; k--) {
+                int2 ent = __ldg(&set[k]);
+                const double* g = S.geom + ent.y;
+                int4 hd = __ldg(reinterpret_cast<const int4*>(g - 2));
+                if ((hd.x & 0xff) == PK_FACE) hit_face(S, ent.x, hd, g, org, dir, h, aft);
+                else hit_object(S, ent.x, org, dir, h, aft, errflag, errobj);
+            }
+        }
+        __syncwarp();
+        // ---- phase C: checkhit (raytrace.c:756-759): hit OK if in current cube ----
+        if (!done) {
+            need_adv = true;
+            if (h.robj >= 0) {
+                double lox = fma((double)ix, size, S.cuorg[0]);
+                double loy = fma((double)iy, size, S.cuorg[1]);
+                double loz = fma((double)iz, size, S.cuorg[2]);
+                double px = org[0] + h.rot * dir[0];
+                double py = org[1] + h.rot * dir[1];
+                double pz = org[2] + h.rot * dir[2];
+                if (!(lox > px || px >= lox + size || loy > py || py >= loy + size || loz > pz || pz >= loz + size)) {
+                    done = true; result = true;
+                }
+            }
+        }
     }
     return result;
 }

@@ -445,11 +445,28 @@ static void flatten_face(const Object& o, FlatScene& fs, int32_t hdr[4], std::st
     }
     if (nv > 65535) { hdr[0] = PK_UNSUPPORTED; warn = "too many vertices"; return; }
     int xi = (ax + 1) % 3, yi = (xi + 1) % 3;
-    size_t off = geom_alloc(fs, 4 + 2 * (size_t)nv);
+    // record: plane (4), 2-D bounding box xmin xmax ymin ymax (4), vertices (2 each)
+    size_t off = geom_alloc(fs, 8 + 2 * (size_t)nv);
     double* g = &fs.geom[off];
     g[0] = norm[0]; g[1] = norm[1]; g[2] = norm[2]; g[3] = offset;
-    for (int i = 0; i < nv; i++) { g[4 + 2 * i] = V(i)[xi]; g[5 + 2 * i] = V(i)[yi]; }
-    hdr[0] = PK_FACE | (ax << 10) | (nv << 16);
+    double bb[4] = {1e300, -1e300, 1e300, -1e300};
+    for (int i = 0; i < nv; i++) {
+        double x = V(i)[xi], y = V(i)[yi];
+        g[8 + 2 * i] = x; g[9 + 2 * i] = y;
+        bb[0] = std::min(bb[0], x); bb[1] = std::max(bb[1], x);
+        bb[2] = std::min(bb[2], y); bb[3] = std::max(bb[3], y);
+    }
+    for (int k = 0; k < 4; k++) g[4 + k] = bb[k];
+    // exact axis-aligned rectangle in the projection plane? (fast inside test)
+    int rect = 0;
+    if (nv == 4 && area != 0.0) {
+        auto X = [&](int i) { return V(i)[xi]; };
+        auto Y = [&](int i) { return V(i)[yi]; };
+        bool a = X(0) == X(1) && Y(1) == Y(2) && X(2) == X(3) && Y(3) == Y(0);
+        bool b = Y(0) == Y(1) && X(1) == X(2) && Y(2) == Y(3) && X(3) == X(0);
+        rect = (a || b) && bb[1] - bb[0] > 4 * FTINY && bb[3] - bb[2] > 4 * FTINY;
+    }
+    hdr[0] = PK_FACE | (ax << 10) | (rect << 12) | (nv << 16);
     hdr[3] = (int32_t)off;
 }
 

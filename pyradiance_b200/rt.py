@@ -1,0 +1,507 @@
+"""Drop-in replacements of pyradiance's process-boundary API for the hot path.
+
+``rtrace()`` and ``Rcontrib`` keep the signatures of the reference
+(src/pyradiance/rt.py:278-362 and :165-234).  Like the reference they first
+assemble the argv of the ``rtrace`` / ``rcontrib`` program; instead of spawning
+the CPU binary, the argv is interpreted here with the option grammar of
+rt/rtmain.c:119-349, rt/rcmain.c:207-320 and rt/renderopts.c:123-349 and the
+work is done by the CUDA library through the C ABI (include/rb200.h).  Input
+bytes and output bytes have the formats of rt/rtrace.c:504-539,907-1009 and
+rt/rc2.c:96-125,258-335.  Failures raise RuntimeError, as the reference's
+wrappers do for a non-zero exit (src/pyradiance/anci.py:13-30).  There is no
+CPU fallback.
+"""
+from __future__ import annotations
+
+import datetime
+import shlex
+from pathlib import Path
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import RBError
+
+VERSION_ID = "RADIANCE 6.0a (pyradiance_b200 CUDA sm_100a)"
+
+
+# --------------------------------------------------------------- helpers ----
+def _quote_args(argv):
+    """printargs() of common/header.c: words with spaces are quoted."""
+    out = []
+    for a in argv:
+        if a == "" or any(c.isspace() for c in a):
+            out.append('"' + a + '"' if '"' not in a else "'" + a + "'")
+        else:
+            out.append(a)
+    return " ".join(out)
+
+
+def _parse_rays(data: bytes, fmt: str) -> np.ndarray:
+    """Input vectors (rt/rtrace.c:504-539 getvec): ascii words, float or double
+    triples; origin then direction."""
+    if fmt == "a":
+        vals = np.array(data.split(), dtype=np.float64) if data.strip() else np.zeros(0)
+    elif fmt == "f":
+        n = len(data) // 4
+        vals = np.frombuffer(data, dtype=np.float32, count=n).astype(np.float64)
+    elif fmt == "d":
+        n = len(data) // 8
+        vals = np.frombuffer(data, dtype=np.float64, count=n)
+    else:
+        raise RBError(f"botched input format '{fmt}'")
+    n6 = (vals.size // 6) * 6
+    return np.ascontiguousarray(vals[:n6].reshape(-1, 6))
+
+
+def _set_format(spec: str, what: str):
+    """setformat(): -f[afd][afdc]"""
+    if not spec:
+        raise RBError(f"{what}: missing format")
+    inf = spec[0]
+    outf = spec[1] if len(spec) > 1 else spec[0]
+    if inf not in "afd" or outf not in "afdc":
+        raise RBError(f"{what}: unsupported i/o format '-f{spec}'")
+    return inf, outf
+
+
+def _header(ctx, prog_argv, ncomp, outfmt, extra=""):
+    now = datetime.datetime.now()
+    utc = datetime.datetime.now(datetime.timezone.utc)
+    lines = list(ctx.header_lines())
+    lines.append(_quote_args(prog_argv))
+    lines.append(f"SOFTWARE= {VERSION_ID}")
+    lines.append(now.strftime("CAPDATE= %Y:%m:%d %H:%M:%S"))
+    lines.append(utc.strftime("GMT= %Y:%m:%d %H:%M:%S"))
+    lines.append(f"NCOMP={ncomp}")
+    txt = "\n".join(lines) + "\n" + extra
+    if outfmt in "fd":
+        txt += "BigEndian=0\n"
+    fmt = {"a": "ascii", "f": "float", "d": "double", "c": "32-bit_rle_rgbe"}[outfmt]
+    txt += f"FORMAT={fmt}\n\n"
+    return txt.encode("latin-1")
+
+
+def _bool_opt(arg: str, pos: int, cur: bool) -> bool:
+    c = arg[pos:pos + 1]
+    if c == "":
+        return not cur
+    if c in "+1":
+        return True
+    if c in "-0":
+        return False
+    raise RBError(f"command line error at '{arg}'")
+
+
+# ---------------------------------------------------------------- rtrace ----
+_RT_UNSUPPORTED_SPEC = {"r": "mirrored contribution", "R": "mirrored distance", "x": "unmirrored contribution",
+                        "X": "unmirrored distance", "V": "contribution", "W": "coefficient", "l": "effective distance",
+                        "t": "ray-tree trace", "T": "source trace"}
+
+
+def rtrace_main(argv: Sequence[str], stdin: bytes, device: int = 0) -> bytes:
+    """Interpret an rtrace command line (argv[0] is the program name)."""
+    argv = [str(a) for a in argv]
+    if "-version" in argv[1:]:
+        return (VERSION_ID + "\n").encode()
+    ctx = _lib.Context(device, _lib.RB_PROGRAM_RTRACE)
+    try:
+        inform, outform = "a", "a"
+        outvals = "v"
+        header = True
+        imm_irrad = False
+        lim_dist = False
+        hres = vres = 0
+        i = 1
+        while i < len(argv):
+            a = argv[i]
+            if not a.startswith("-") or len(a) < 2:
+                break
+            rv = ctx.set_option(argv[i:])
+            if rv >= 0:
+                i += rv + 1
+                continue
+            c = a[1]
+            if c == "n":
+                i += 1          # number of processes: a hint, the GPU does the work
+            elif c == "x":
+                hres = int(argv[i + 1]); i += 1
+            elif c == "y":
+                vres = int(argv[i + 1]); i += 1
+            elif c == "w":
+                pass
+            elif c == "I":
+                imm_irrad = _bool_opt(a, 2, imm_irrad)
+            elif c == "f":
+                inform, outform = _set_format(a[2:], "rtrace")
+            elif c == "o":
+                outvals = a[2:]
+            elif c == "h":
+                header = _bool_opt(a, 2, header)
+            elif c == "l" and a[2:3] == "d":
+                lim_dist = _bool_opt(a, 3, lim_dist)
+            elif c == "t" and a[2:3] in ("e", "i", "E", "I"):
+                pass            # trace include/exclude lists only matter for -ot
+            elif c == "P" or c == "p":
+                raise RBError(f"unsupported rtrace option '{a}' (persist / primaries)")
+            else:
+                raise RBError(f"command line error at '{a}'")
+            i += 1
+        if i != len(argv) - 1:
+            raise RBError("missing octree argument" if i >= len(argv) else f"command line error at '{argv[i]}'")
+        octree = argv[i]
+        if not outvals:
+            raise RBError("empty output specification")
+        for ch in outvals:
+            if ch in _RT_UNSUPPORTED_SPEC:
+                raise RBError(f"unsupported output option '-o{ch}' ({_RT_UNSUPPORTED_SPEC[ch]}) in the CUDA path")
+            if ch not in "odvLpNnsmMwc~":
+                raise RBError(f"unrecognized output option '{ch}'")
+        if outform == "c":
+            raise RBError("color (RGBE) output format is not built")
+        want_values = "v" in outvals
+        p = ctx.get_params()
+        if (imm_irrad or p.do_irrad) and not want_values:
+            raise RBError("-I+ and -i+ options require some value output")
+        ctx.load_octree(octree)
+        rays = _parse_rays(stdin, inform)
+        flags = (_lib.RB_IRRAD_RTRACE if imm_irrad else _lib.RB_IRRAD_NONE) | (_lib.RB_FLAG_LIMDIST if lim_dist else 0)
+        n = rays.shape[0]
+        if vres > 0:
+            n = min(n, (hres if hres > 1 else 1) * vres) if hres > 0 or vres > 0 else n
+            rays = rays[:n]
+        values, res = ctx.rtrace(rays, flags=flags, want_values=want_values, want_results=True)
+        out = bytearray()
+        ncomp = 0
+        for ch in outvals:
+            ncomp += {"o": 3, "d": 3, "v": 3, "L": 1, "p": 3, "N": 3, "n": 3, "s": 1, "m": 1, "M": 1, "w": 1,
+                      "c": 2, "~": 0}[ch]
+        if header:
+            out += _header(ctx, ["rtrace"] + argv[1:-1], ncomp, outform)
+        if hres > 0 and vres > 0:
+            out += f"-Y {vres} +X {hres}\n".encode()
+        out += _format_rtrace(ctx, rays, values, res, outvals, outform)
+        return bytes(out)
+    finally:
+        ctx.close()
+
+
+def _names(ctx, idx, none="*", void="void"):
+    cache = {}
+    out = []
+    for i in idx:
+        i = int(i)
+        if i not in cache:
+            cache[i] = ctx.object_name(i) if i >= 0 else None
+        out.append(cache[i])
+    return out
+
+
+def _format_rtrace(ctx, rays, values, res, outvals, outform) -> bytes:
+    n = rays.shape[0]
+    dirn = rays[:, 3:6]
+    norm = np.linalg.norm(dirn, axis=1, keepdims=True)
+    bogus = (norm[:, 0] == 0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        dnorm = np.where(norm > 0, dirn / np.where(norm > 0, norm, 1), 0.0)
+    cols = []           # list of (kind, array/list)
+    hit = res["robj"] >= 0
+    for ch in outvals:
+        if ch == "o":
+            cols.append(("r", rays[:, 0:3]))
+        elif ch == "d":
+            cols.append(("r", dnorm))
+        elif ch == "v":
+            cols.append(("r", values))
+        elif ch == "L":
+            cols.append(("r", res["rot"].reshape(-1, 1)))
+        elif ch == "p":
+            cols.append(("r", res["rop"]))
+        elif ch in "Nn":
+            cols.append(("r", np.where(hit[:, None], res["ron"], 0.0)))
+        elif ch == "w":
+            cols.append(("r", res["rweight"].astype(np.float64).reshape(-1, 1)))
+        elif ch == "c":
+            cols.append(("r", np.zeros((n, 2))))
+        elif ch == "s":
+            cols.append(("s", [nm if nm is not None else "*" for nm in _names(ctx, res["robj"])]))
+        elif ch == "m":
+            names = []
+            for ro, om in zip(res["robj"], res["omod"]):
+                names.append("*" if ro < 0 else (ctx.object_name(int(om)) if om >= 0 else "void"))
+            cols.append(("s", names))
+        elif ch == "M":
+            raise RBError("unsupported output option '-oM' in the CUDA path")
+        elif ch == "~":
+            cols.append(("s", ["~"] * n))
+    if outform == "a":
+        lines = []
+        for i in range(n):
+            parts = []
+            for kind, c in cols:
+                if kind == "r":
+                    parts.append("".join("%e\t" % v for v in c[i]))
+                else:
+                    parts.append(c[i] + "\t")
+            lines.append("".join(parts))
+        return ("\n".join(lines) + ("\n" if lines else "")).encode("latin-1")
+    dt = np.float32 if outform == "f" else np.float64
+    if any(kind == "s" for kind, _ in cols):
+        out = bytearray()
+        for i in range(n):
+            for kind, c in cols:
+                out += np.asarray(c[i], dtype=dt).tobytes() if kind == "r" else (c[i] + "\t").encode()
+        return bytes(out)
+    if not cols:
+        return b""
+    return np.ascontiguousarray(np.concatenate([c for _, c in cols], axis=1), dtype=dt).tobytes()
+
+
+def rtrace(
+    rays: bytes,
+    octree,
+    header: bool = True,
+    inform: str = "a",
+    outform: str = "a",
+    irradiance: bool = False,
+    irradiance_lambertian: bool = False,
+    outspec: None | str = None,
+    trace_exclude: str = "",
+    trace_include: str = "",
+    trace_exclude_file=None,
+    trace_include_file=None,
+    uncorrelated: bool = False,
+    xres: None | int = None,
+    yres: None | int = None,
+    nproc: None | int = None,
+    params: None | Sequence[str] = None,
+    report: bool = False,
+    version: bool = False,
+) -> bytes:
+    """Run rtrace on the GPU.  Same arguments as pyradiance.rtrace
+    (src/pyradiance/rt.py:278-362)."""
+    cmd = ["rtrace"]
+    if version:
+        return rtrace_main(cmd + ["-version"], b"")
+    if not isinstance(rays, bytes):
+        raise TypeError("Rays must be bytes")
+    if not header:
+        cmd.append("-h")
+    if irradiance:
+        cmd.append("-I")
+    elif irradiance_lambertian:
+        cmd.append("-i")
+    cmd.append(f"-f{inform}{outform}")
+    if outspec:
+        cmd.append(f"-o{outspec}")
+    if trace_exclude:
+        cmd.append(f"-te{trace_exclude}")
+    elif trace_include:
+        cmd.append(f"-ti{trace_include}")
+    elif trace_exclude_file:
+        cmd.append(f"-tE{trace_exclude_file}")
+    elif trace_include_file:
+        cmd.append(f"-tI{trace_include_file}")
+    if uncorrelated:
+        cmd.append("-u+")
+    if xres is not None:
+        cmd.extend(["-x", str(xres)])
+    if yres is not None:
+        cmd.extend(["-y", str(yres)])
+    if nproc:
+        cmd.extend(["-n", str(nproc)])
+    if params is not None:
+        cmd.extend(params)
+    cmd.append(str(octree))
+    try:
+        return rtrace_main(cmd, rays)
+    except RBError as e:
+        raise RuntimeError(f"rtrace: {e}") from e
+
+
+# -------------------------------------------------------------- rcontrib ----
+def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_array: bool = False):
+    """Interpret an rcontrib command line (argv[0] is the program name).
+    Option order matters exactly as in rt/rcmain.c:207-320: -f/-e/-p act
+    immediately, -bn is evaluated when met, -b/-bn/-p/-o are sticky until -m."""
+    argv = [str(a) for a in argv]
+    if "-version" in argv[1:]:
+        return (VERSION_ID + "\n").encode()
+    ctx = _lib.Context(device, _lib.RB_PROGRAM_RCONTRIB)
+    try:
+        inform, outform = "a", "a"
+        header = True
+        imm_irrad = lim_dist = contrib = False
+        xres = yres = 0
+        accumulate = 1
+        curout = None
+        prms, binval, bincnt = "", None, 0
+        nmods = 0
+        i = 1
+        while i < len(argv):
+            a = argv[i]
+            if not a.startswith("-") or len(a) < 2:
+                break
+            rv = ctx.set_option(argv[i:])
+            if rv >= 0:
+                i += rv + 1
+                continue
+
+            def need(k=1):
+                if i + k >= len(argv):
+                    raise RBError(f"command line error at '{a}'")
+
+            c = a[1]
+            if c == "n":
+                need(); i += 1
+            elif c == "V":
+                contrib = _bool_opt(a, 2, contrib)
+            elif c == "x":
+                need(); xres = int(argv[i + 1]); i += 1
+            elif c == "y":
+                need(); yres = int(argv[i + 1]); i += 1
+            elif c == "w":
+                pass
+            elif c == "l" and a[2:3] == "d":
+                lim_dist = _bool_opt(a, 3, lim_dist)
+            elif c == "I":
+                imm_irrad = _bool_opt(a, 2, imm_irrad)
+            elif c == "f":
+                if a[2:3] == "o":
+                    pass
+                else:
+                    inform, outform = _set_format(a[2:], "rcontrib")
+            elif c == "o":
+                need(); curout = argv[i + 1]; i += 1
+            elif c == "r":
+                if _bool_opt(a, 2, False):
+                    raise RBError("unsupported option: -r (recover) is not built")
+            elif c == "h":
+                header = _bool_opt(a, 2, header)
+            elif c == "p":
+                need(); prms = argv[i + 1]; ctx.cal_set(prms); i += 1
+            elif c == "c":
+                need(); accumulate = int(argv[i + 1]); i += 1
+            elif c == "b":
+                need()
+                if a[2:3] == "n":
+                    bincnt = int(ctx.cal_eval(argv[i + 1]) + .5)
+                else:
+                    binval = argv[i + 1]
+                i += 1
+            elif c == "m":
+                need()
+                if curout is not None:
+                    raise RBError("unsupported option: -o file output is not built (matrix is returned)")
+                ctx.add_modifier(argv[i + 1], prms, binval if binval is not None else "0", bincnt)
+                nmods += 1
+                i += 1
+            elif c == "M":
+                need()
+                for name in Path(argv[i + 1]).read_text().split():
+                    ctx.add_modifier(name, prms, binval if binval is not None else "0", bincnt)
+                    nmods += 1
+                i += 1
+            elif c == "t":
+                need(); i += 1
+            else:
+                raise RBError(f"command line error at '{a}'")
+            i += 1
+        if nmods <= 0:
+            raise RBError("missing required modifier argument")
+        if i != len(argv) - 1:
+            raise RBError("missing octree argument" if i >= len(argv) else f"command line error at '{argv[i]}'")
+        if outform == "c":
+            raise RBError("color (RGBE) output format is not built")
+        ctx.load_octree(argv[i])
+        rays = _parse_rays(stdin, inform)
+        if accumulate > 0:
+            # zero-direction rays are flush requests that still produce a record
+            pass
+        flags = (_lib.RB_IRRAD_RCONTRIB if imm_irrad else 0) | (_lib.RB_FLAG_LIMDIST if lim_dist else 0) | \
+                (_lib.RB_FLAG_CONTRIB if contrib else 0)
+        dt = np.float32 if outform == "f" else np.float64
+        mat = ctx.rcontrib(rays, accum=accumulate, flags=flags, dtype=dt)
+        if return_array:
+            return mat
+        ncols = ctx.num_columns()
+        out = bytearray()
+        if header:
+            extra = ""
+            if yres > 0:
+                extra += f"NROWS={yres * (xres if xres else 1)}\n"
+            if xres <= 0 or ncols > 1:
+                extra += f"NCOLS={ncols}\n"
+            out += _header(ctx, ["rcontrib"] + argv[1:-1], 3, outform, extra)
+        if ncols == 1 and xres > 0 and yres > 0:
+            out += f"-Y {yres} +X {xres}\n".encode()
+        if outform == "a":
+            flat = mat.reshape(mat.shape[0], -1)
+            out += ("".join("".join("%.6e\t" % v for v in row) + "\n" for row in flat)).encode()
+        else:
+            out += mat.tobytes()
+        return bytes(out)
+    finally:
+        ctx.close()
+
+
+class Rcontrib:
+    """Same construction protocol as pyradiance.Rcontrib (src/pyradiance/rt.py:165-234)."""
+
+    def __init__(self, inp: bytes, octree, nproc: int = 1, yres=None, inform=None, outform=None, report: int = 0,
+                 params: None | Sequence[str] = None):
+        self.cmd = ["rcontrib"]
+        self.octree = octree
+        self.inp = inp
+        self.cmd.extend(["-n", str(nproc)])
+        if params is not None:
+            self.cmd.extend(params)
+        if None not in (inform, outform):
+            self.cmd.append(f"-f{inform}{outform}")
+        if yres is not None:
+            self.cmd.extend(["-y", str(yres)])
+        if report:
+            self.cmd.extend(["-t", str(report)])
+
+    def add_modifier(self, modifier=None, modifier_path=None, calfile=None, expression=None, nbins=None, binv=None,
+                     param=None, xres=None, yres=None, output=None):
+        arglist = []
+        if calfile is not None:
+            arglist.extend(["-f", str(calfile)])
+        if expression is not None:
+            arglist.extend(["-e", str(expression)])
+        if nbins is not None:
+            arglist.extend(["-bn", str(nbins)])
+        if binv is not None:
+            arglist.extend(["-b", str(binv)])
+        if param is not None:
+            arglist.extend(["-p", str(param)])
+        if xres is not None:
+            arglist.extend(["-x", str(xres)])
+        if yres is not None:
+            arglist.extend(["-y", str(yres)])
+        if output is not None:
+            arglist.extend(["-o", str(output)])
+        if modifier is not None:
+            arglist.extend(["-m", modifier])
+        elif modifier_path is not None:
+            arglist.extend(["-M", modifier_path])
+        else:
+            raise ValueError("Modifier or modifier path must be provided.")
+        self.cmd.extend(arglist)
+        return self
+
+    def __call__(self) -> bytes:
+        cmd = self.cmd + [str(self.octree)]
+        try:
+            return rcontrib_main(cmd, self.inp)
+        except RBError as e:
+            raise RuntimeError(f"rcontrib: {e}") from e
+
+    def as_array(self) -> np.ndarray:
+        """Extension: the matrix as float [nrecords, ncols, 3] without the byte round trip."""
+        try:
+            return rcontrib_main(self.cmd + [str(self.octree)], self.inp, return_array=True)
+        except RBError as e:
+            raise RuntimeError(f"rcontrib: {e}") from e
