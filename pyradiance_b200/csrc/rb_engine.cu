@@ -207,11 +207,14 @@ __global__ void __launch_bounds__(256) k_expand(const WaveArgs A, const ExpandAr
 }
 
 // rc2.c:293-335 put_contrib(): record value = accumulated sum / accumulate count
+// A partial final record is averaged over the rays it really got
+// (rcontrib.c:417-423 "partial accumulation in final record").
 template <class T>
-__global__ void k_finish(const double* __restrict__ acc, T* __restrict__ out, size_t n, double scale) {
+__global__ void k_finish(const double* __restrict__ acc, T* __restrict__ out, size_t n, double scale,
+                         size_t tail_start, double tail_scale) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) out[i] = (T)(acc[i] * scale);
+    for (; i < n; i += stride) out[i] = (T)(acc[i] * (i >= tail_start ? tail_scale : scale));
 }
 
 // ---------------------------------------------------------------- host -----
@@ -464,8 +467,16 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         }
         unsigned grid = (unsigned)std::min<size_t>((accn + 255) / 256, 148 * 16);
         CK(cudaEventRecord(ev0_, stream_));
-        if (job.cmat_double) k_finish<double><<<grid, 256, 0, stream_>>>(d_acc_, (double*)dst, accn, scale);
-        else k_finish<float><<<grid, 256, 0, stream_>>>(d_acc_, (float*)dst, accn, scale);
+        size_t tail_start = accn;
+        double tail_scale = scale;
+        if (accum > 1 && ray0 + nray == job.nrays && job.nrays % accum != 0) {
+            tail_start = (nrows - 1) * (size_t)ncols_ * 3;
+            tail_scale = 1.0 / (double)(job.nrays % accum);
+        }
+        if (job.cmat_double)
+            k_finish<double><<<grid, 256, 0, stream_>>>(d_acc_, (double*)dst, accn, scale, tail_start, tail_scale);
+        else
+            k_finish<float><<<grid, 256, 0, stream_>>>(d_acc_, (float*)dst, accn, scale, tail_start, tail_scale);
         CK(cudaEventRecord(ev1_, stream_));
         stats.launches++;
         if (!job.cmat_on_device)

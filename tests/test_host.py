@@ -1,0 +1,222 @@
+"""CPU-side tests of the product's host logic (no GPU needed): the C ABI loads
+and exports every declared symbol, the scene loader, the octree builder, the
+option parser / defaults, the calcomp stand-in and its explicit rejections,
+the Python boundary's input parsing, and the multi-GPU row plumbing (gloo)."""
+import json
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import has_gpu
+from oracle import port, refrun
+from pyradiance_b200 import _lib, dist, rt, scenegen
+import pyradiance_b200 as pr
+
+
+@pytest.fixture(scope="module")
+def G(golden):
+    return json.load(open(golden / "golden.json"))
+
+
+def test_abi_exports_every_declared_symbol(root):
+    hdr = (root / "include" / "rb200.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = _lib.load_library()
+    for name in declared:
+        assert hasattr(lib, name), f"librb200.so does not export {name}"
+    assert declared == {n for n, _, _ in _lib.SYMBOLS}, "ctypes table out of sync with include/rb200.h"
+    assert b"sm_100a" in lib.rb_version()
+
+
+def test_scene_loader_reads_reference_octree(golden):
+    c = _lib.Context(0)
+    err = c.parse_octree(golden / "trace.oct")
+    assert err is None or "no CUDA device" in err
+    assert c.num_objects() == 21
+    assert c.header_lines()[0] == "#?RADIANCE"
+    assert "oconv -f materials.mat" in c.header_lines()[1]
+    names = [(c.object_type(i), c.object_name(i)) for i in range(21)]
+    assert names[13] == ("polygon", "ceiling") and names[16] == ("source", "sun") and names[18] == ("glow", "skyglow")
+    assert c.object_modifier(13) == 0 and c.object_modifier(14) == 7 and c.object_modifier(0) == -1
+
+
+def test_loader_errors():
+    c = _lib.Context(0)
+    assert "cannot open octree" in c.parse_octree("/nonexistent/scene.oct")
+    assert "not an octree" in c.parse_octree(__file__)
+
+
+def test_native_bins_match_reference(G, golden):
+    dirs = np.load(golden / "bin_dirs.npy")[:, 3:6]
+    for name in [k for k in G if k.startswith("bins_")]:
+        args = G[name]["args"]
+        c = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+        i, params, binv, bn = 0, "", "0", "1"
+        while i < len(args):
+            a = args[i]
+            if a == "-f": c.cal_load(args[i + 1])
+            elif a == "-e": c.cal_set(args[i + 1])
+            elif a == "-p": params = args[i + 1]; c.cal_set(params)
+            elif a == "-bn": bn = args[i + 1]
+            elif a == "-b": binv = args[i + 1]
+            elif a == "-m": c.add_modifier(args[i + 1], params, binv, int(c.cal_eval(bn) + .5))
+            i += 2
+        assert c.num_columns() == G[name]["ncols"]
+        for d, b in zip(dirs, G[name]["bins"]):
+            v = c.bin_of_direction(0, d)
+            assert (-1 if v <= -.5 else int(v + .5)) == b, name
+
+
+def test_defaults_are_the_reference_defaults():
+    c = _lib.Context(0, _lib.RB_PROGRAM_RTRACE)
+    p = c.get_params()       # tests/test_api.py:168-236 pins these for rtrace
+    assert (p.shadthresh, p.shadcert, p.dstrsrc, p.directrelay, p.vspretest, p.srcsizerat) == (.03, .75, 0, 2, 512, .2)
+    assert (p.specthresh, p.specjitter, p.maxdepth, p.minweight) == (.15, 1, -10, 1e-4)
+    assert (p.ambacc, p.ambres, p.ambdiv, p.ambssamp, p.ambounce) == (.1, 256, 1024, 512, 0)
+    c = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+    p = c.get_params()       # rt/rcontrib.c:24-58
+    assert (p.ambounce, p.ambdiv, p.ambacc, p.minweight, p.dstrsrc, p.directrelay, p.specthresh) == (1, 350, 0, 2e-3, .9, 3, .02)
+
+
+def test_option_parser():
+    c = _lib.Context(0)
+    c.set_options(["-ab", "8", "-ad", "1024", "-u-", "-aa", ".1", "-lw", "1e-8", "-av", "1", "2", "3", "-bv", "-i+"])
+    p = c.get_params()
+    assert (p.ambounce, p.ambdiv, p.rand_samp, p.minweight, list(p.ambval), p.backvis, p.do_irrad) == \
+        (8, 1024, 0, 1e-8, [1, 2, 3], 0, 1)
+    assert c.set_option(["-zz"]) == -1 and c.set_option(["-ab"]) == -1 and c.set_option(["-ab", "x"]) == -1
+    with pytest.raises(_lib.RBError):
+        c.set_options(["-ab", "1", "-nonsense"])
+
+
+def test_module_level_param_api():
+    pr.set_ray_params(None)
+    pr.set_option(["-ab", "8", "-ad", "1024", "-u-", "-aa", ".1", "-lw", "1e-8", "-av", "1", "2", "3"])
+    rp = pr.get_ray_params()
+    assert (rp.ab, rp.ad, rp.u, rp.aa, rp.lw, rp.av) == (8, 1024, False, .1, 1e-8, (1.0, 2.0, 3.0))
+    rp.ab = 3
+    rp.as_ = 0
+    pr.set_ray_params(rp)
+    assert pr.get_ray_params().ab == 3
+    pr.set_ray_params(None)
+    assert pr.get_ray_params().ab == 0
+
+
+def test_cal_context_order_dependence_and_rejections():
+    c = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+    with pytest.raises(_lib.RBError, match="no Reinhart bin file"):
+        c.cal_eval("Nrbins")
+    c.cal_load("reinhartb.cal")
+    assert c.cal_eval("Nrbins") == 145          # MF defaults to 1 in reinhartb.cal
+    c.cal_set("MF=4")
+    assert c.cal_eval("Nrbins") == 2305         # -bn sees the MF in force when it is evaluated
+    assert c.cal_eval("2*Nrbins+1") == 4611
+    c.cal_load("reinhart.cal")
+    assert c.cal_eval("Nrbins") == 2306         # the later file's definition wins
+    with pytest.raises(_lib.RBError, match="unsupported function file"):
+        c.cal_load("perezlum.cal")
+    with pytest.raises(_lib.RBError, match="unsupported bin expression"):
+        c.add_modifier("m1", "", "floor(Dx*10)", 10)
+    with pytest.raises(_lib.RBError, match="illegal non-zero constant"):
+        c.add_modifier("m2", "", "3", 1)
+    with pytest.raises(_lib.RBError, match="duplicate modifier"):
+        c.add_modifier("m3", "", "0", 1)
+        c.add_modifier("m3", "", "0", 1)
+    with pytest.raises(_lib.RBError, match="needs -f klems_full.cal"):
+        c.add_modifier("m4", "", "kbin(0,0,-1,0,1,0)", 145)
+    c.cal_load("klems_full.cal")
+    assert c.add_modifier("m5", "RHS=-1", "kbinS", 145) >= 0
+
+
+def test_own_oconv_matches_reference_oconv(workdir):
+    rad = workdir / "o.rad"
+    scenegen.write_office(rad, npolys=3000, seed=3)
+    mine, ref = workdir / "mine.oct", workdir / "ref.oct"
+    scenegen.build_octree(rad, mine)
+    rays = scenegen.random_rays(5000, seed=2)
+    a = port.Scene(mine).rtrace(rays)
+    if refrun.available():
+        refrun.oconv([rad], ref)
+        b = port.Scene(ref).rtrace(rays)
+        assert np.array_equal(a["robj"], b["robj"])
+        assert np.array_equal(a["rot"], b["rot"])           # same hits, bit for bit, on either tree
+        out = refrun.rtrace(mine, rays[:200], ["-ab", "0", "-os"]).split()
+        s = port.Scene(mine)
+        assert out == [s.name(i) for i in a["robj"][:200]]  # the reference reads our octree
+    assert (a["robj"] >= 0).mean() > 0.9
+
+
+def test_ray_input_parsing():
+    r = rt._parse_rays(b"1 2 3 0 0 1\n4 5 6 0 1 0\n", "a")
+    assert r.shape == (2, 6) and r[1, 4] == 1
+    f = np.arange(12, dtype=np.float32)
+    assert np.array_equal(rt._parse_rays(f.tobytes(), "f"), f.astype(float).reshape(2, 6))
+    d = np.arange(12, dtype=np.float64)
+    assert np.array_equal(rt._parse_rays(d.tobytes(), "d"), d.reshape(2, 6))
+    assert rt._parse_rays(b"", "a").shape == (0, 6)
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu(golden):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pr.rtrace(b"0 0 0 0 0 1", golden / "trace.oct", params=["-ab", "0"])
+    rc = pr.Rcontrib(b"0 0 1 0 0 1", golden / "contrib.oct", params=["-ab", "0"]).add_modifier("skyglow")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rc()
+
+
+def test_shard_ranges_cover_all_rows():
+    for n in (0, 1, 7, 100, 1001):
+        for w in (1, 2, 3, 8):
+            rs = [dist.shard_range(n, r, w) for r in range(w)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+            assert max(b - a for a, b in rs) - min(b - a for a, b in rs) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys
+import numpy as np
+import torch.distributed as dist
+sys.path.insert(0, os.environ["RB_ROOT"])
+from pyradiance_b200 import dist as rbd
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["RB_PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+rank = dist.get_rank()
+n, ncols = 11, 5
+rays = np.arange(n * 6, dtype=np.float64).reshape(n, 6)
+mine, r0, r1 = rbd.local_rays(rays, 1, rank, 2)
+assert mine.shape[0] == r1 - r0
+# stand-in for the traced rows: a function of the GLOBAL record index only
+rows = np.stack([np.full((ncols, 3), float(g), dtype=np.float32) for g in range(r0, r1)])
+full = rbd.gather_rows(rows, n)
+if rank == 0:
+    assert full.shape == (n, ncols, 3)
+    assert np.array_equal(full[:, 0, 0], np.arange(n, dtype=np.float32))
+    print("GATHER_OK")
+else:
+    assert full is None
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_row_gather_world_size_2_gloo(root, workdir):
+    script = workdir / "gloo_worker.py"
+    script.write_text(_GLOO_WORKER)
+    import os
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port_ = s.getsockname()[1]; s.close()
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), RB_ROOT=str(root), RB_PORT=str(port_))
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE))
+    outs = [p.communicate(timeout=180) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert b"GATHER_OK" in outs[0][0]

@@ -1,0 +1,106 @@
+"""Pins the CPU oracle (oracle/rb_oracle.c) against the reference: the golden
+vectors of tests/golden/ (made by the unmodified reference binaries, see
+tests/golden/make_golden.py) and, when oracle/_ref is present, the reference
+rtrace / rcontrib run here on seeded inputs.  No GPU needed."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import port, refrun
+from pyradiance_b200 import scenegen
+
+BINCASES = [
+    ("bins_reinhartb_mf1", port.BIN_REINHARTB, 1, (0, 0, -1), (0, 1, 0)),
+    ("bins_reinhartb_mf4", port.BIN_REINHARTB, 4, (0, 0, -1), (0, 1, 0)),
+    ("bins_reinhart_mf2", port.BIN_REINHART, 2, (0, 0, 0), (0, 0, 0)),
+    ("bins_klems_full", port.BIN_KLEMS_FULL, 1, (0, 0, -1), (0, 1, 0)),
+    ("bins_klems_half", port.BIN_KLEMS_HALF, 1, (0, 0, -1), (0, 1, 0)),
+    ("bins_klems_quarter", port.BIN_KLEMS_QUARTER, 1, (0, 0, -1), (0, 1, 0)),
+    ("bins_hemi", port.BIN_HEMI, 1, (0, 0, -1), (0, 0, 0)),
+]
+
+
+@pytest.fixture(scope="module")
+def G(golden):
+    return json.load(open(golden / "golden.json"))
+
+
+@pytest.mark.parametrize("name,fn,mf,n,u", BINCASES)
+def test_oracle_bins_match_reference(G, golden, name, fn, mf, n, u):
+    dirs = np.load(golden / "bin_dirs.npy")[:, 3:]
+    want = G[name]["bins"]
+    for d, b in zip(dirs, want):
+        v = port.bin_of(fn, mf, n, u, 1.0, d)
+        got = -1 if v <= -.5 else int(v + .5)
+        assert got == b
+
+
+def test_oracle_known_answer_hits(G, golden):
+    k = G["trace_ovposmNL"]
+    s = port.Scene(golden / "trace.oct")
+    r = s.rtrace(np.array(k["rays"]))
+    for i, line in enumerate(k["out"].strip("\n").split("\n")):
+        f = line.split("\t")
+        assert s.name(r["robj"][i]) == f[9] and s.name(r["omod"][i]) == f[10]
+        np.testing.assert_allclose(r["rop"][i], [float(x) for x in f[3:6]], rtol=2e-7, atol=1e-12)
+        np.testing.assert_allclose(r["ron"][i], [float(x) for x in f[11:14]], atol=1e-9)
+        assert r["rot"][i] == pytest.approx(float(f[14]), rel=2e-7)
+
+
+def test_oracle_irradiance_ab0(G, golden):
+    k = G["trace_I_ab0"]
+    s = port.Scene(golden / "trace.oct", dstrsrc=0.0)
+    r = s.rtrace(np.array(k["rays"]), irrad=1)
+    want = np.array([[float(x) for x in ln.split()] for ln in k["out"].strip().split("\n")])
+    np.testing.assert_allclose(r["value"], want, rtol=1e-5, atol=1e-9)     # north_star: -ab 0 within 1e-5
+
+
+def test_oracle_config1_grid(G, golden):
+    gx, gy = np.meshgrid(np.linspace(1, 39, 100), np.linspace(2, 45, 100))
+    grid = np.stack([gx.ravel(), gy.ravel(), np.full(10000, 2.5), np.zeros(10000), np.zeros(10000), np.ones(10000)], 1)
+    s = port.Scene(golden / "trace.oct", dstrsrc=0.0)
+    v = s.rtrace(grid, irrad=1)["value"]
+    k = G["trace_grid_I_ab0"]
+    assert int((v[:, 0] > 0).sum()) == k["nonzero_rows"]
+    assert v.sum() == pytest.approx(k["sum"], rel=1e-6)
+
+
+@pytest.fixture(scope="module")
+def office2k(workdir):
+    rad, octf = workdir / "off2k.rad", workdir / "off2k.oct"
+    scenegen.write_office(rad, npolys=2000, seed=1)
+    scenegen.build_octree(rad, octf)            # own builder (CPU code of librb200.so)
+    return octf
+
+
+@pytest.mark.skipif(not refrun.available(), reason="oracle/_ref not built")
+def test_oracle_hits_equal_reference(office2k):
+    rays = scenegen.random_rays(20000, seed=11)
+    s = port.Scene(office2k)
+    r = s.rtrace(rays)
+    ref = refrun.rtrace(office2k, rays, ["-ab", "0", "-osmL"]).splitlines()
+    assert len(ref) == len(rays)
+    for i, line in enumerate(ref):
+        f = line.split("\t")
+        assert (s.name(r["robj"][i]), s.name(r["omod"][i])) == (f[0], f[1]), i     # bit-exact hit identity
+        assert r["rot"][i] == pytest.approx(float(f[2]), rel=1e-6)                # %e prints 7 digits
+
+
+@pytest.mark.skipif(not refrun.available(), reason="oracle/_ref not built")
+def test_oracle_stochastic_agrees_with_reference(golden):
+    """Row sums of a -ab 2 coefficient matrix: oracle vs reference, both Monte
+    Carlo.  Tolerance: 4 sigma of the difference, sigma from repeated runs."""
+    sens = np.array([[10, 10, 3, 0, 0, 1], [4, 5, 3, 0, 0, 1], [20, 20, 12, 0, 0, 1]], dtype=float)
+    args = ["-I", "-ab", "2", "-ad", "2048", "-lw", "1e-4", "-f", "reinhartb.cal", "-p",
+            "MF=1,rNx=0,rNy=0,rNz=-1,Ux=0,Uy=1,Uz=0,RHS=+1", "-bn", "Nrbins", "-b", "rbin", "-m", "skyglow"]
+    refs, mine = [], []
+    for k in range(6):
+        refs.append(refrun.rcontrib(golden / "contrib.oct", sens, args).reshape(3, -1, 3)[:, :, 0].sum(1))
+        s = port.Scene(golden / "contrib.oct", rcontrib=True, ambounce=2, ambdiv=2048, minweight=1e-4, seed=100 + k)
+        s.add_modifier("skyglow", port.BIN_REINHARTB, 1, (0, 0, -1), (0, 1, 0), 1.0, 145)
+        mine.append(s.rcontrib(sens, irrad=2)[:, :, 0].sum(1))
+    refs, mine = np.array(refs), np.array(mine)
+    sig = np.sqrt(refs.var(0, ddof=1) / 6 + mine.var(0, ddof=1) / 6) + 1e-6
+    assert np.all(np.abs(refs.mean(0) - mine.mean(0)) < 4 * sig + 2e-3 * refs.mean(0))
+    assert mine[:, 2] == pytest.approx(np.pi, rel=1e-6)        # unobstructed sensor sums to pi
