@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+Workload (config.workload): configs[1] = rcontrib daylight coefficients,
+Reinhart MF:1 (145 sky bins), -I+ -ab 3 -ad 4096 -lw 2.44e-4, 100 000 sensors,
+seeded synthetic 100k-polygon office (pyradiance_b200/scenegen.py, octree built
+by our own builder).  One STEP = the whole 100k-sensor matrix on one GPU.
+With N GPUs every rank owns its own 100k-sensor block of records (weak
+scaling; no data-path collective; RNG keyed by global record index).
+
+  value   traced rays/s, inputs and matrix resident in HBM (device pointers)
+  e2e     same metric through the host-buffer C-ABI call (rb_rcontrib with a
+          pinned host ray array in and a pinned host float32 matrix out)
+  roofline  the dominant kernel (k_trace: octree walk + intersection) against
+          the measured HBM copy bandwidth, on ALGORITHMIC bytes
+  cpu_baseline  the unmodified reference rcontrib -n <cores> (oracle/_ref) on a
+          bounded sample of the same workload
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+NSENS = int(os.environ.get("RB_BENCH_SENSORS", 100_000))
+NPOLY = int(os.environ.get("RB_BENCH_POLYS", 100_000))
+AB, AD = 3, 4096
+LW = 1.0 / AD
+OPTS = ["-ab", str(AB), "-ad", str(AD), "-lw", f"{LW:.4e}"]
+RB_P = "MF=1,rNx=0,rNy=0,rNz=-1,Ux=0,Uy=1,Uz=0,RHS=+1"
+RB_ARGS = ["-f", "reinhartb.cal", "-p", RB_P, "-bn", "Nrbins", "-b", "rbin", "-m", "skyglow"]
+WORKLOAD = (f"rcontrib -I+ -ab {AB} -ad {AD} -lw {LW:.3e} Reinhart MF:1 (145 bins), {NSENS} sensors, "
+            f"synthetic {NPOLY}-polygon office (BASELINE configs[1])")
+METRIC, UNIT = "traced_rays_per_sec", "rays/s"
+
+
+def scene_paths():
+    tmp = Path(os.environ.get("RB_TMP", "/tmp/rb200_bench"))
+    tmp.mkdir(parents=True, exist_ok=True)
+    return tmp / f"office{NPOLY}.rad", tmp / f"office{NPOLY}.oct"
+
+
+def ensure_scene():
+    from pyradiance_b200 import scenegen
+    rad, octf = scene_paths()
+    if not octf.exists():
+        tmp = octf.with_suffix(f".{os.getpid()}.tmp")
+        scenegen.write_office(rad.with_suffix(f".{os.getpid()}.rad"), npolys=NPOLY, seed=1234)
+        scenegen.build_octree(rad.with_suffix(f".{os.getpid()}.rad"), tmp)
+        os.replace(tmp, octf)
+    return octf
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_ = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self.stop_.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def reference_rcontrib_rate(octf, sens, cores, target_s=12.0):
+    """Time the unmodified reference rcontrib -n cores on a bounded sample.
+    Returns (sensors/s, sample description)."""
+    from oracle import refrun
+    n = 256
+    while True:
+        t = time.perf_counter()
+        refrun.rcontrib(octf, sens[:n], ["-I+"] + OPTS + ["-y", str(n)] + RB_ARGS, nproc=cores, outform="f")
+        dt = time.perf_counter() - t
+        if dt > 0.4 * target_s or n >= len(sens) or n >= 65536:
+            return n / dt, n, dt
+        n = int(min(len(sens), max(n * 2, n * target_s / max(dt, 1e-3) * 0.8)))
+
+
+def algorithmic_bytes_per_ray(octf, sens):
+    """bytes(ray) = 32 + 32 V + 4 E + 64 P + 16, with V/E/P counted
+    by the CPU restatement (oracle) on a sample of the same workload; plus 24
+    per contribution."""
+    from oracle import port
+    s = port.Scene(octf, rcontrib=True, ambounce=AB, ambdiv=AD, minweight=LW, seed=5)
+    s.add_modifier("skyglow", port.BIN_REINHARTB, 1, (0, 0, -1), (0, 1, 0), 1.0, 145)
+    idx = np.linspace(0, len(sens) - 1, 6).astype(int)
+    s.rcontrib(sens[idx], irrad=2)
+    c = s.counters()
+    nr = max(1, c["nrays"])
+    V, E, P, K = c["nodes"] / nr, c["leafents"] / nr, c["prims"] / nr, c["contribs"] / nr
+    return 32 + 32 * V + 4 * E + 64 * P + 16 + 24 * K, {"V": round(V, 2), "E": round(E, 2), "P": round(P, 2),
+                                                        "contribs_per_ray": round(K, 4)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import refrun
+    from pyradiance_b200 import scenegen
+    if not refrun.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        return 0
+    octf = ensure_scene()
+    sens = scenegen.office_sensors(NSENS)
+    cores = os.cpu_count() or 1
+    # rays per sensor of this workload, counted once by the oracle port (the reference does not print it)
+    from oracle import port
+    s = port.Scene(octf, rcontrib=True, ambounce=AB, ambdiv=AD, minweight=LW, seed=5)
+    s.add_modifier("skyglow", port.BIN_REINHARTB, 1, (0, 0, -1), (0, 1, 0), 1.0, 145)
+    idx = np.linspace(0, NSENS - 1, 6).astype(int)
+    s.rcontrib(sens[idx], irrad=2)
+    rays_per_sensor = s.counters()["nrays"] / len(idx)
+    rate, n0, dt0 = reference_rcontrib_rate(octf, sens, cores, target_s=6.0)
+    n = int(max(64, min(NSENS, rate * 6.0)))          # ~6 s per step
+    times = []
+    for it in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        refrun.rcontrib(octf, sens[:n], ["-I+"] + OPTS + ["-y", str(n)] + RB_ARGS, nproc=cores, outform="f")
+        dt = time.perf_counter() - t
+        if it >= args.warmup:
+            times.append(dt)
+    tot = sum(times)
+    val = n * args.steps * rays_per_sensor / tot
+    sample = (f"{n} of {NSENS} sensors per step, reference rcontrib -n {cores} (oracle/_ref, unmodified, "
+              f"-O3 -ffast-math), process start-up and scene load included; rays/sensor = {rays_per_sensor:.0f} "
+              f"counted by the oracle port on 6 sensors")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from pyradiance_b200 import _lib, scenegen
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: pyradiance_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if rank == 0:
+        octf = ensure_scene()
+    if world > 1:
+        dist.barrier()
+    octf = ensure_scene()
+
+    ctx = _lib.Context(local, _lib.RB_PROGRAM_RCONTRIB)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.load_octree(octf)
+    ctx.set_options(OPTS)
+    ctx.cal_load("reinhartb.cal")
+    ctx.cal_set(RB_P)
+    ctx.add_modifier("skyglow", RB_P, "rbin", int(ctx.cal_eval("Nrbins") + .5))
+    ncols = ctx.num_columns()
+    # weak scaling: rank r owns the records [r*NSENS, (r+1)*NSENS) of an N*NSENS-sensor job
+    sens = scenegen.office_sensors(NSENS, seed=42 + rank)
+    row_base = rank * NSENS
+    flags = _lib.RB_IRRAD_RCONTRIB
+    # HBM-resident buffers (torch owns the memory; the C ABI gets raw pointers)
+    d_rays = torch.from_numpy(sens).to("cuda")
+    d_out = torch.empty((NSENS, ncols, 3), dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > L2 (126 MB)
+
+    def step_device():
+        flush.fill_(1)                                                     # evict L2 between steps
+        ctx.rcontrib_device(d_rays.data_ptr(), NSENS, 1, flags, row_base, d_out.data_ptr(), d_out.numel())
+
+    h_rays = np.ascontiguousarray(sens)
+    h_out = np.empty((NSENS, ncols, 3), dtype=np.float32)
+    ctx.pin(h_rays)
+    ctx.pin(h_out)
+
+    def step_host():
+        flush.fill_(1)
+        ctx.rcontrib(h_rays, accum=1, flags=flags, row_base=row_base, out=h_out)
+        return float(h_out[0, 0, 0])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(args.warmup):
+        step_device()
+    ctx.reset_stats()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(step_device, args.steps)
+    st = ctx.stats()
+    ms_e2e = timed(step_host, args.steps)
+    sampler.stop_.set()
+    sampler.join(timeout=2)
+    assert np.isfinite(h_out).all() and h_out.sum() > 0
+    np.testing.assert_allclose(h_out.sum(), float(d_out.sum().item()), rtol=1e-3)   # same job, same seeds
+
+    rays_local = st["nrays"]
+    tot = torch.tensor([float(rays_local)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    rays_all = float(tot.item())
+    value = rays_all / (ms / 1e3)
+    e2e_value = rays_all / (ms_e2e / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        bpr, counts = algorithmic_bytes_per_ray(octf, sens)
+        launch_s = (st["wave_ms"] / 1e3) / max(1, st["wave_launches"])
+        rays_per_launch = rays_local / max(1, st["wave_launches"])
+        achieved = bpr * rays_per_launch / launch_s / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(ROOT / "profiles" / "r1_k_trace_dram.json")).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_sensors": NSENS, "rays_per_step_per_gpu": rays_local / args.steps,
+                       "dc_matrix_wall_ms": ms / args.steps, "sharding": f"records x{world}, scene replicated",
+                       "l2": "256 MiB flush buffer written before every step; ray queues (GBs per step) exceed L2; "
+                             "scene tables are L2-resident by design"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h_rays.nbytes), "d2h_bytes_per_step": int(h_out.nbytes)},
+            "gpu_launches": int(st["launches"]),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "k_trace", "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"
+                         if peaks else "fallback 6650 GB/s (of fallback)",
+                         "algorithmic_bytes_per_ray": bpr, "counts_per_ray": counts,
+                         "avg_launch_ms": launch_s * 1e3, "launches": int(st["wave_launches"]),
+                         "k_trace_share_of_kernel_time": st["wave_ms"] / max(1e-9, st["kernel_ms"])},
+        }
+        try:
+            from oracle import refrun
+            if refrun.available():
+                cores = os.cpu_count() or 1
+                rate, n, dt = reference_rcontrib_rate(octf, sens, cores)
+                rps = rays_local / args.steps / NSENS
+                line["cpu_baseline"] = {"value": rate * rps, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"{n} of {NSENS} sensors in {dt:.1f} s, unmodified reference rcontrib "
+                                                  f"-n {cores} (oracle/_ref), start-up included; rays/sensor taken "
+                                                  f"from the GPU run ({rps:.0f})"}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
+                                        "sample": "oracle/_ref not present on this box"}
+        except Exception as e:      # never lose the GPU numbers to a baseline hiccup
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

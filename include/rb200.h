@@ -172,6 +172,9 @@ int rb_device_free(rb_ctx* ctx, void* p);
 int rb_device_upload(rb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int rb_device_download(rb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int rb_device_sync(rb_ctx* ctx);
+/* page-lock / unlock a caller-owned host buffer (faster, truly asynchronous copies) */
+int rb_host_register(rb_ctx* ctx, void* p, size_t bytes);
+int rb_host_unregister(rb_ctx* ctx, void* p);
 
 /* own octree builder for synthetic scenes (next-row f3): text scene -> frozen .oct */
 int rb_oconv(const char* rad_path, const char* oct_path, int objlim, int maxres,

@@ -92,6 +92,8 @@ SYMBOLS = [
     ("rb_device_upload", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("rb_device_download", C.c_int, [_P, _P, _P, C.c_size_t]),
     ("rb_device_sync", C.c_int, [_P]),
+    ("rb_host_register", C.c_int, [_P, _P, C.c_size_t]),
+    ("rb_host_unregister", C.c_int, [_P, _P]),
     ("rb_oconv", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
 ]
 
@@ -302,6 +304,13 @@ class Context:
 
     def device_download(self, arr, dptr):
         self._ck(self.lib.rb_device_download(self.h, arr.ctypes.data, dptr, arr.nbytes))
+
+    def pin(self, arr):
+        """Page-lock a numpy array in place (cudaHostRegister)."""
+        self._ck(self.lib.rb_host_register(self.h, arr.ctypes.data, arr.nbytes))
+
+    def unpin(self, arr):
+        self.lib.rb_host_unregister(self.h, arr.ctypes.data)
 
     def sync(self):
         self._ck(self.lib.rb_device_sync(self.h))

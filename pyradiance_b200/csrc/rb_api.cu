@@ -611,6 +611,18 @@ int rb_device_download(rb_ctx* c, void* dst, const void* src, size_t bytes) {
     cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
     return e == cudaSuccess ? 0 : fail(c, cudaGetErrorString(e));
 }
+int rb_host_register(rb_ctx* c, void* p, size_t bytes) {
+    if (!c->cuda_ok) return fail(c, c->cuda_err);
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    return e == cudaSuccess ? 0 : fail(c, cudaGetErrorString(e));
+}
+int rb_host_unregister(rb_ctx* c, void* p) {
+    if (!c->cuda_ok) return fail(c, c->cuda_err);
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaHostUnregister(p);
+    return e == cudaSuccess ? 0 : fail(c, cudaGetErrorString(e));
+}
 int rb_device_sync(rb_ctx* c) {
     cudaSetDevice(c->device);
     cudaError_t e = cudaDeviceSynchronize();
