@@ -211,22 +211,32 @@ def test_stochastic_row_sums_vs_oracle_and_reference(golden):
 
 
 def test_stochastic_bins_office_vs_oracle(office2k):
-    """Per-bin agreement on a cluttered scene with glass: pooled over sensors,
-    bins with enough hits must agree within 4 sigma (binomial estimate) + 2 %."""
-    sens = scenegen.office_sensors(24, seed=5)
+    """Per-bin agreement on a cluttered scene with glass.  Sensors stand at the
+    south windows and look out, so each sees the sky through `glass` (two rays
+    per pane hit) and the room by reflection.  Tolerance: the matrix total and
+    every bin with >= 40 expected first-level hits must agree within 4 sigma,
+    sigma^2 = the Poisson variance of the hit count of both Monte-Carlo runs
+    (stratified sampling has less; two oracle runs with different seeds stay
+    below 0.15 of this tolerance), plus 1 %."""
+    n = 16
+    x = np.linspace(2.5, 37.5, n)
+    d = np.array([0.0, -1.0, 0.25]) / np.linalg.norm([0.0, -1.0, 0.25])
+    sens = np.stack([x, np.full(n, 1.5), np.full(n, 1.8)] + [np.full(n, v) for v in d], axis=1)
     opts = ["-ab", "2", "-ad", "1024", "-lw", "1e-3"]
     ctx = rc_ctx(office2k, opts)
     g = ctx.rcontrib(sens, flags=_lib.RB_IRRAD_RCONTRIB).astype(np.float64)[:, :, 0]
     s = port.Scene(office2k, rcontrib=True, ambounce=2, ambdiv=1024, minweight=1e-3, seed=3)
     s.add_modifier("skyglow", port.BIN_REINHARTB, 1, (0, 0, -1), (0, 1, 0), 1.0, 145)
     o = s.rcontrib(sens, irrad=2)[:, :, 0]
-    assert g.sum() == pytest.approx(o.sum(), rel=0.02)
-    pg, po = g.sum(0), o.sum(0)
     w = np.pi / 1024                      # weight of one first-level sample
-    nz = po > 40 * w                      # bins with >= ~40 expected hits
-    assert nz.sum() >= 10
-    sig = np.sqrt((pg + po) * w * 3)      # path weights vary: allow 3x the binomial variance
-    assert np.all(np.abs(pg[nz] - po[nz]) <= 4 * sig[nz] + 0.02 * po[nz])
+    assert o.sum() > 400 * w              # the test has signal
+    sig_tot = np.sqrt((g.sum() + o.sum()) * w)
+    assert abs(g.sum() - o.sum()) <= 4 * sig_tot + 0.01 * o.sum()
+    pg, po = g.sum(0), o.sum(0)
+    nz = po > 40 * w
+    assert nz.sum() >= 5
+    sig = np.sqrt((pg + po) * w)
+    assert np.all(np.abs(pg[nz] - po[nz]) <= 4 * sig[nz] + 0.01 * po[nz])
 
 
 # ------------------------------------------------------------- invariances --
