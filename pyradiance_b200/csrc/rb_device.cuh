@@ -128,7 +128,7 @@ struct DCounters {
     unsigned errflag;              // RB_ERR_* bits
     unsigned errobj;               // offending object
     unsigned badbin;               // bin >= nbins warnings
-    unsigned pad;
+    unsigned next_ray;             // k_trace's persistent-thread fetch counter
 };
 enum : unsigned { RB_ERR_UNSUP_MAT = 1, RB_ERR_UNSUP_PRIM = 2, RB_ERR_UNSUP_MOD = 4,
                   RB_ERR_LOCAL_SRC = 8, RB_ERR_DEPTH = 16 };

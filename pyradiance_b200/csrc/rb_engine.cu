@@ -35,7 +35,6 @@ namespace rb {
 
 // ------------------------------------------------------------- kernels -----
 __device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws, unsigned nr) {
-    if (!__any_sync(__activemask(), nr)) return;
     unsigned a = __reduce_add_sync(__activemask(), ws.nodes);
     unsigned b = __reduce_add_sync(__activemask(), ws.leafents);
     unsigned c = __reduce_add_sync(__activemask(), ws.prims);
@@ -50,35 +49,17 @@ __device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws, u
     }
 }
 
-// Trace: octree walk + intersection only (small code, few registers).
+// Trace: octree walk + intersection only (small code).  Persistent threads:
+// the grid is sized to fill the machine once and every warp pulls rays from
+// the queue until it is empty (rb_geom.cuh walk_rays).
 __global__ void __launch_bounds__(WAVE_THREADS) k_trace(const WaveArgs A) {
     __shared__ int stk[RB_STACK * WAVE_THREADS];
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < A.nin;
-    double org[3] = {0, 0, 0}, dir[3] = {0, 0, 0}, rmax = 0;
-    int rsrc = -1, crtype = 0;
-    if (active) {
-        const double2* q2 = reinterpret_cast<const double2*>(&A.qin[i]);
-        double2 a = __ldg(&q2[0]), b = __ldg(&q2[1]), c = __ldg(&q2[2]), d = __ldg(&q2[3]);
-        org[0] = a.x; org[1] = a.y; org[2] = b.x; dir[0] = b.y; dir[1] = c.x; dir[2] = c.y; rmax = d.x;
-        crtype = A.qin[i].info & 0x3ff; rsrc = A.qin[i].rsrc;
-    }
-    Hit h;
+    TraceIO io;
+    io.qin = A.qin; io.nin = A.nin; io.hits = A.hits; io.next = &A.C->next_ray;
     WalkStats ws = {0, 0, 0};
-    bool hit = localhit(A.S, active, org, dir, rmax, h, stk + threadIdx.x, WAVE_THREADS, ws,
-                        &A.C->errflag, &A.C->errobj);
-    flush_stats(A.C, ws, active ? 1u : 0u);
-    if (!active) return;
-    HitRec o;
-    o.rot = h.rot; o.rod = h.rod; o.robj = h.robj; o.local = 1;
-    if (!hit) {
-        o.rot = RB_FHUGE; o.rod = 1.0; o.robj = -1; o.local = 0;
-        if (!(rmax > RB_FTINY)) {                // aft-clipped rays never see sources
-            int sn = sourcehit(A.S, dir, rsrc, crtype);
-            if (sn >= 0) o.robj = A.S.srcs[sn].so;
-        }
-    }
-    A.hits[i] = o;
+    unsigned nretired = 0;
+    walk_rays(A.S, io, stk + threadIdx.x, WAVE_THREADS, ws, nretired, &A.C->errflag, &A.C->errobj);
+    flush_stats(A.C, ws, nretired);
 }
 
 // Shade: material evaluation, contribution accumulation, child-ray emission.
@@ -313,6 +294,12 @@ bool Engine::ensure_queues(std::string& err) {
     CK(cudaMalloc(&h_[0], hcap_ * sizeof(QHemi)));
     CK(cudaMalloc(&h_[1], hcap_ * sizeof(QHemi)));
     CK(cudaMalloc(&d_hits_, qcap_ * sizeof(HitRec)));
+    {   // persistent k_trace grid: every SM filled exactly once
+        int per_sm = 0, nsm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, WAVE_THREADS, 0));
+        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev_));
+        trace_blocks_ = std::max(1, per_sm) * std::max(1, nsm);
+    }
     return true;
 }
 
@@ -420,10 +407,12 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         if (nq == 0) break;
         // reset the out counters, keep the statistics
         CK(cudaMemsetAsync(&d_cnt_->nq_out, 0, 3 * sizeof(unsigned), stream_));
+        CK(cudaMemsetAsync(&d_cnt_->next_ray, 0, sizeof(unsigned), stream_));
         A.qin = q_[cur]; A.nin = nq; A.qout = q_[cur ^ 1]; A.hout = h_[cur ^ 1];
         unsigned grid = (nq + WAVE_THREADS - 1) / WAVE_THREADS;
+        unsigned tgrid = std::min<unsigned>(grid, (unsigned)trace_blocks_);
         CK(cudaEventRecord(ev0_, stream_));
-        k_trace<<<grid, WAVE_THREADS, 0, stream_>>>(A);
+        k_trace<<<tgrid, WAVE_THREADS, 0, stream_>>>(A);
         CK(cudaEventRecord(ev1_, stream_));
         CK(cudaEventRecord(ev2_, stream_));
         k_shade<<<grid, WAVE_THREADS, 0, stream_>>>(A);

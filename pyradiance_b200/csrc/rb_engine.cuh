@@ -73,6 +73,7 @@ private:
     RayResult* d_res_ = nullptr; size_t res_bytes_ = 0;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev2_ = nullptr, ev3_ = nullptr;
     HitRec* d_hits_ = nullptr;
+    int trace_blocks_ = 148;
     bool has_local_sources_ = false;
     std::string local_source_note_;
 };

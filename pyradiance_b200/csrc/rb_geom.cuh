@@ -291,63 +291,117 @@ __device__ __forceinline__ void hit_face(const DScene& S, int id, int4 hd, const
     h.robj = id; h.rot = t; h.rod = rdot;
 }
 
-// localhit(): returns true when a local surface was hit.  MUST be called by
-// all 32 lanes of a warp together (lanes without a ray pass active=false):
-// the walk is organised in warp-synchronous phases -- descend, test the leaf's
-// surfaces, step to the neighbour cube -- with a __syncwarp() after each, so
-// that lanes re-converge every phase instead of drifting apart for the whole
-// ray.  `stk` is this thread's column of the shared-memory node stack.
-__device__ __forceinline__ bool localhit(const DScene& S, bool active, const double org[3],
-                                         const double dir[3], double rmax, Hit& h, volatile int* stk,
-                                         int stride, WalkStats& ws, unsigned* errflag, unsigned* errobj) {
-    int dirf = 0;
-    double pos[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        pos[i] = org[i];
-        if (dir[i] > 1e-7) dirf |= 1 << i;
-        else if (dir[i] < -1e-7) dirf |= 0x10 << i;
-    }
-    h.robj = -1; h.rot = RB_FHUGE; h.rod = 1.0;
-    bool done = !active || !dirf;
-    bool result = false;
-    bool aft = false;
-    if (!done && rmax > RB_FTINY) { aft = true; h.rot = rmax; }
+// sourcehit() lives in rb_shade.cuh; declared here for the retire step
+__device__ __forceinline__ int sourcehit(const DScene& S, const double dir[3], int rsrc, int crtype);
+
+struct TraceIO {
+    const QRay* __restrict__ qin;
+    unsigned nin;
+    HitRec* __restrict__ hits;
+    unsigned* next;              // global fetch counter
+};
+#define RB_FETCH_MIN 6           // refill a warp when this many lanes are idle
+
+// walk_rays(): persistent-thread localhit().  Every warp keeps pulling rays
+// from the queue: a lane whose ray is finished retires it (writes its HitRec,
+// running sourcehit() for misses) and, as soon as RB_FETCH_MIN lanes of the
+// warp are idle, the warp reserves that many queue slots with one atomicAdd and
+// the idle lanes start new rays.  Ray lengths are heavy-tailed (most rays end
+// in nearby clutter, a few cross the whole room), so without the refill a warp
+// ran at < 5 live lanes on average (profiles/r1_notes.md).
+// The walk itself is organised in warp-synchronous phases -- walk to the next
+// full leaf / test the leaf's surfaces / accept-or-continue -- with a
+// __syncwarp() after each, so that lanes re-converge every phase.  `stk` is
+// this thread's column of the shared-memory node stack.  MUST be called by all
+// 32 lanes of a warp together.
+__device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, volatile int* stk, int stride,
+                                          WalkStats& ws, unsigned& nretired, unsigned* errflag,
+                                          unsigned* errobj) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
     const double cs = S.cusize;
-    // find global cube entrance point (raytrace.c:625-650)
-    if (!done) {
-        bool in = !(S.cuorg[0] > pos[0] || pos[0] >= S.cuorg[0] + cs ||
-                    S.cuorg[1] > pos[1] || pos[1] >= S.cuorg[1] + cs ||
-                    S.cuorg[2] > pos[2] || pos[2] >= S.cuorg[2] + cs);
-        if (!in) {
-            double t = 0.0;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-                double dt;
-                if (dirf & (1 << i)) dt = S.cuorg[i];
-                else if (dirf & (0x10 << i)) dt = S.cuorg[i] + cs;
-                else continue;
-                dt = (dt - org[i]) / dir[i];
-                if (dt > t) t = dt;
+    const int2* __restrict__ pool = reinterpret_cast<const int2*>(S.leafpool);
+    double org[3] = {0, 0, 0}, dir[3] = {0, 0, 1}, pos[3] = {0, 0, 0}, rmax = 0, size = cs;
+    Hit h; h.robj = -1; h.rot = RB_FHUGE; h.rod = 1.0;
+    int dirf = 0, w = -1, L = 0, rsrc = -1, crtype = 0;
+    unsigned ix = 0, iy = 0, iz = 0, ridx = 0;
+    bool aft = false, need_adv = false, done = true, result = false, have = false, exhausted = false;
+    for (;;) {
+        // ---- retire finished rays ----
+        if (have & done) {
+            HitRec o;
+            o.rot = h.rot; o.rod = h.rod; o.robj = h.robj; o.local = 1;
+            if (!result) {
+                o.rot = RB_FHUGE; o.rod = 1.0; o.robj = -1; o.local = 0;
+                if (!(rmax > RB_FTINY)) {            // aft-clipped rays never see sources
+                    int sn = sourcehit(S, dir, rsrc, crtype);
+                    if (sn >= 0) o.robj = S.srcs[sn].so;
+                }
             }
-            t += RB_FTINY;
-            if (t >= h.rot) done = true;
-            else {
+            io.hits[ridx] = o;
+            have = false;
+            nretired++;
+        }
+        // ---- refill idle lanes ----
+        unsigned idle = __ballot_sync(FULL, !have);
+        if (idle == FULL && exhausted) break;
+        if (!exhausted && (__popc(idle) >= RB_FETCH_MIN)) {
+            int n = __popc(idle);
+            int leader = __ffs(idle) - 1;
+            unsigned base = 0;
+            if ((int)lane == leader) base = atomicAdd(io.next, (unsigned)n);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + n >= io.nin) exhausted = true;
+            unsigned my = base + __popc(idle & ((1u << lane) - 1));
+            if (!have && my < io.nin) {
+                const double2* q2 = reinterpret_cast<const double2*>(&io.qin[my]);
+                double2 a = __ldg(&q2[0]), b = __ldg(&q2[1]), c = __ldg(&q2[2]), d = __ldg(&q2[3]);
+                org[0] = a.x; org[1] = a.y; org[2] = b.x; dir[0] = b.y; dir[1] = c.x; dir[2] = c.y; rmax = d.x;
+                crtype = io.qin[my].info & 0x3ff; rsrc = io.qin[my].rsrc;
+                ridx = my; have = true;
+                // ---- localhit() prologue (raytrace.c:604-651) ----
+                dirf = 0;
 #pragma unroll
-                for (int i = 0; i < 3; i++) pos[i] = pos[i] + dir[i] * t;
-                in = !(S.cuorg[0] > pos[0] || pos[0] >= S.cuorg[0] + cs ||
-                       S.cuorg[1] > pos[1] || pos[1] >= S.cuorg[1] + cs ||
-                       S.cuorg[2] > pos[2] || pos[2] >= S.cuorg[2] + cs);
-                if (!in) done = true;
+                for (int i = 0; i < 3; i++) {
+                    pos[i] = org[i];
+                    if (dir[i] > 1e-7) dirf |= 1 << i;
+                    else if (dir[i] < -1e-7) dirf |= 0x10 << i;
+                }
+                h.robj = -1; h.rot = RB_FHUGE; h.rod = 1.0;
+                done = !dirf; result = false; aft = false; need_adv = false;
+                if (!done && rmax > RB_FTINY) { aft = true; h.rot = rmax; }
+                if (!done) {
+                    bool in = !(S.cuorg[0] > pos[0] || pos[0] >= S.cuorg[0] + cs ||
+                                S.cuorg[1] > pos[1] || pos[1] >= S.cuorg[1] + cs ||
+                                S.cuorg[2] > pos[2] || pos[2] >= S.cuorg[2] + cs);
+                    if (!in) {                        // find global cube entrance point
+                        double t = 0.0;
+#pragma unroll
+                        for (int i = 0; i < 3; i++) {
+                            double dt;
+                            if (dirf & (1 << i)) dt = S.cuorg[i];
+                            else if (dirf & (0x10 << i)) dt = S.cuorg[i] + cs;
+                            else continue;
+                            dt = (dt - org[i]) / dir[i];
+                            if (dt > t) t = dt;
+                        }
+                        t += RB_FTINY;
+                        if (t >= h.rot) done = true;
+                        else {
+#pragma unroll
+                            for (int i = 0; i < 3; i++) pos[i] = pos[i] + dir[i] * t;
+                            in = !(S.cuorg[0] > pos[0] || pos[0] >= S.cuorg[0] + cs ||
+                                   S.cuorg[1] > pos[1] || pos[1] >= S.cuorg[1] + cs ||
+                                   S.cuorg[2] > pos[2] || pos[2] >= S.cuorg[2] + cs);
+                            if (!in) done = true;
+                        }
+                    }
+                }
+                w = S.root; L = 0; ix = iy = iz = 0; size = cs;
             }
         }
-    }
-    int w = S.root, L = 0;
-    unsigned ix = 0, iy = 0, iz = 0;
-    double size = cs;                   // size of the current cube (level L)
-    const int2* __restrict__ pool = reinterpret_cast<const int2*>(S.leafpool);
-    bool need_adv = false;              // current leaf is finished: step to the neighbour first
-    while (!__all_sync(0xffffffffu, done)) {
+        __syncwarp();
+
         // ---- phase A: walk (descend / skip empty cubes) until standing in a
         //      fresh full leaf.  One loop, two short bodies, so lanes re-join
         //      every iteration (raymove, raytrace.c:668-738) ----
@@ -455,7 +509,6 @@ __device__ __forceinline__ bool localhit(const DScene& S, bool active, const dou
             }
         }
     }
-    return result;
 }
 
 }  // namespace rb
