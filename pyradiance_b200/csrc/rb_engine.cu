@@ -22,7 +22,12 @@
 
 namespace rb {
 
+#ifndef WAVE_THREADS
 #define WAVE_THREADS 128
+#endif
+#ifndef RB_MINBLOCKS
+#define RB_MINBLOCKS 6
+#endif
 
 #define CK(call)                                                                     \
     do {                                                                             \
@@ -52,7 +57,7 @@ __device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws, u
 // Trace: octree walk + intersection only (small code).  Persistent threads:
 // the grid is sized to fill the machine once and every warp pulls rays from
 // the queue until it is empty (rb_geom.cuh walk_rays).
-__global__ void __launch_bounds__(WAVE_THREADS) k_trace(const WaveArgs A) {
+__global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const WaveArgs A) {
     __shared__ int stk[RB_STACK * WAVE_THREADS];
     TraceIO io;
     io.qin = A.qin; io.nin = A.nin; io.hits = A.hits; io.next = &A.C->next_ray;

@@ -300,7 +300,12 @@ struct TraceIO {
     HitRec* __restrict__ hits;
     unsigned* next;              // global fetch counter
 };
+#ifndef RB_MAILBOX
+#define RB_MAILBOX 0
+#endif
+#ifndef RB_FETCH_MIN
 #define RB_FETCH_MIN 6           // refill a warp when this many lanes are idle
+#endif
 
 // walk_rays(): persistent-thread localhit().  Every warp keeps pulling rays
 // from the queue: a lane whose ray is finished retires it (writes its HitRec,
@@ -326,6 +331,9 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, vol
     int dirf = 0, w = -1, L = 0, rsrc = -1, crtype = 0;
     unsigned ix = 0, iy = 0, iz = 0, ridx = 0;
     bool aft = false, need_adv = false, done = true, result = false, have = false, exhausted = false;
+#if RB_MAILBOX
+    int4 mb = make_int4(-1, -1, -1, -1);
+#endif
     for (;;) {
         // ---- retire finished rays ----
         if (have & done) {
@@ -398,6 +406,9 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, vol
                     }
                 }
                 w = S.root; L = 0; ix = iy = iz = 0; size = cs;
+#if RB_MAILBOX
+                mb = make_int4(-1, -1, -1, -1);
+#endif
             }
         }
         __syncwarp();
@@ -486,6 +497,12 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, vol
             }
             for (int k = cnt; k > 0; k--) {
                 int2 ent = __ldg(&set[k]);
+#if RB_MAILBOX
+                // mailbox: surfaces spanning several leaves were already tested for
+                // this ray; the re-test is a no-op (see header), so skip it
+                if ((ent.x == mb.x) | (ent.x == mb.y) | (ent.x == mb.z) | (ent.x == mb.w)) { ws.prims--; continue; }
+                mb.w = mb.z; mb.z = mb.y; mb.y = mb.x; mb.x = ent.x;
+#endif
                 const double* g = S.geom + ent.y;
                 int4 hd = __ldg(reinterpret_cast<const int4*>(g - 2));
                 if ((hd.x & 0xff) == PK_FACE) hit_face(S, ent.x, hd, g, org, dir, h, aft);
