@@ -26,7 +26,7 @@ namespace rb {
 #define WAVE_THREADS 128
 #endif
 #ifndef RB_MINBLOCKS
-#define RB_MINBLOCKS 6
+#define RB_MINBLOCKS 4
 #endif
 
 #define CK(call)                                                                     \
@@ -58,12 +58,12 @@ __device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws, u
 // the grid is sized to fill the machine once and every warp pulls rays from
 // the queue until it is empty (rb_geom.cuh walk_rays).
 __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const WaveArgs A) {
-    __shared__ int stk[RB_STACK * WAVE_THREADS];
+    __shared__ WalkSmem<WAVE_THREADS> sm;
     TraceIO io;
     io.qin = A.qin; io.nin = A.nin; io.hits = A.hits; io.next = &A.C->next_ray;
     WalkStats ws = {0, 0, 0};
     unsigned nretired = 0;
-    walk_rays(A.S, io, stk + threadIdx.x, WAVE_THREADS, ws, nretired, &A.C->errflag, &A.C->errobj);
+    walk_rays<WAVE_THREADS>(A.S, io, sm, ws, nretired, &A.C->errflag, &A.C->errobj);
     flush_stats(A.C, ws, nretired);
 }
 
@@ -82,9 +82,8 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_shade(const WaveArgs A) {
     r.nchild = 0;
     r.robj = hr.robj; r.rot = hr.rot; r.rod = hr.rod; r.flat = false;
     if (hr.local) {
-        Hit h; h.robj = hr.robj; h.rot = hr.rot; h.rod = hr.rod;
-        hit_frame(A.S, h, r.org, r.dir, r.rop, r.ron);
-        int kind = __ldg(&A.S.objhdr[h.robj]).x & 0xff;
+        hit_frame(A.S, hr.robj, hr.rot, r.org, r.dir, r.rop, r.ron, r.rod);
+        int kind = __ldg(&A.S.objhdr[hr.robj]).x & 0xff;
         r.flat = (kind == PK_FACE) | (kind == PK_RING);
     } else {
         for (int k = 0; k < 3; k++) { r.rop[k] = r.org[k]; r.ron[k] = -r.dir[k]; }

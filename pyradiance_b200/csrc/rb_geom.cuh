@@ -1,13 +1,15 @@
 // rb_geom.cuh -- octree walk and surface intersection on the device.
 //
-// Restates, as an iterative integer-coordinate walk with a shared-memory node
-// stack, the reference's recursive octant DDA and its intersectors:
+// Restates the reference's recursive octant DDA and its intersectors:
 //   localhit/raymove/checkhit   src/radiance/rt/raytrace.c:595-760
 //   rayhit + rayreject          src/radiance/rt/raytrace.c:535-591
 //   incube                      src/radiance/common/octree.c:115-126
 //   o_face + inface             src/radiance/rt/o_face.c:16-62, common/face.c:121-162
 //   o_sphere                    src/radiance/rt/sphere.c:16-83
 //   o_cone + quadratic          src/radiance/rt/o_cone.c:17-146, common/zeroes.c:19-54
+// as a persistent-thread, WARP-COOPERATIVE kernel body with shared-memory ray
+// staging (walk_rays below).
+//
 // All geometry is IEEE double (RREAL); this translation unit is compiled with
 // -fmad=false so that products and sums round exactly like the reference's
 // non-fused x86-64 code.  Differences from the reference, by design:
@@ -16,48 +18,28 @@
 //   * objects already tested in an earlier leaf are tested again instead of
 //     being filtered through a per-ray checked set: rayreject() makes the
 //     re-test a no-op (o == r->ro, or t > rot + FTINY, or the same pairwise
-//     tie decision).
+//     tie decision);
+//   * every surface of a leaf first yields at most one CANDIDATE (t, facing,
+//     inside) that does not depend on the ray's current best hit -- computed by
+//     whichever lane of the warp is free -- and the ray's own lane then applies
+//     rayreject() to the candidates in the reference's order (descending object
+//     index).  Since inface()/the end-cap and radius checks do not depend on
+//     the current hit, this gives exactly the sequential result.
 #pragma once
 #include "rb_device.cuh"
 
 namespace rb {
 
-struct Hit {
-    int robj;           // -1 none
-    double rot, rod;
-};
+#ifndef RB_OPR
+#define RB_OPR 6                 // surfaces per ray per round handed to the warp
+#endif
+#ifndef RB_FETCH_MIN
+#define RB_FETCH_MIN 6           // refill a warp when this many lanes are idle
+#endif
+#define RB_PAIRS (32 * RB_OPR)
 
 __device__ __forceinline__ double dot3(const double a[3], const double b[3]) {
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
-}
-
-// raytrace.c:535-575 -- returns true if candidate (t, rod) on object `id`
-// must be rejected in favour of the current hit.
-__device__ __forceinline__ bool rayreject(const DScene& S, int id, int4 hnew, const Hit& h,
-                                          bool aft, double t, double rod) {
-    if ((t <= RB_FTINY) | (t > h.rot + RB_FTINY)) return true;
-    if (t < h.rot - RB_FTINY) return false;
-    // coincident point, so decide...
-    if (id == h.robj) return true;
-    if (h.robj < 0) return aft ? true /* Aftplane has no material: see below */ : false;
-    int4 hold = __ldg(&S.objhdr[h.robj]);
-    int fnew = hnew.x >> 8, fold = hold.x >> 8;
-    bool mnew = fnew & PF_HASMAT, mray = fold & PF_HASMAT;
-    if (!mnew) {
-        if (mray) return true;
-    } else if (!mray) {
-        return false;
-    } else if (fnew & PF_TRANSP) {
-        if (!(fold & PF_TRANSP)) return true;
-    } else if (fold & PF_TRANSP) {
-        return false;
-    }
-    if (rod <= 0) {
-        if (h.rod > 0) return true;
-    } else if (h.rod <= 0) {
-        return false;
-    }
-    return hold.y >= hnew.y;     // later modifier definition wins tie
 }
 
 // common/face.c:121-162 inface() on the pre-projected 2-D vertices
@@ -102,54 +84,53 @@ __device__ __forceinline__ int quadratic(double r[2], double a, double b, double
     return 2;
 }
 
-// Test one object; on acceptance updates h and returns true.
-__device__ __noinline__ bool hit_object(const DScene& S, int id, const double org[3],
-                                        const double dir[3], Hit& h, bool aft,
-                                        unsigned* errflag, unsigned* errobj) {
-    int4 hd = __ldg(&S.objhdr[id]);
-    int kind = hd.x & 0xff;
-    const double* g = S.geom + hd.w;
-    if (kind == PK_FACE) {
-        const double2* g2 = reinterpret_cast<const double2*>(g);
-        double2 n01 = __ldg(&g2[0]), n2o = __ldg(&g2[1]);
-        double rdot = -(dir[0] * n01.x + dir[1] * n01.y + dir[2] * n2o.x);
-        if ((rdot <= RB_FTINY) & (rdot >= -RB_FTINY)) return false;
-        double t = ((org[0] * n01.x + org[1] * n01.y + org[2] * n2o.x) - n2o.y) / rdot;
-        if (rayreject(S, id, hd, h, aft, t, rdot)) return false;
-        int ax = (hd.x >> 10) & 3;
-        int xi = ax + 1; if (xi >= 3) xi -= 3;
-        int yi = xi + 1; if (yi >= 3) yi -= 3;
-        double p[3] = {org[0] + t * dir[0], org[1] + t * dir[1], org[2] + t * dir[2]};
-        double x = xi == 0 ? p[0] : xi == 1 ? p[1] : p[2];
-        double y = yi == 0 ? p[0] : yi == 1 ? p[1] : p[2];
-        if (!inface2d(g + 8, (hd.x >> 16) & 0xffff, x, y)) return false;
-        h.robj = id; h.rot = t; h.rod = rdot;
-        return true;
-    }
+// Candidate of a polygon: o_face() up to, but not including, rayreject().
+// `tmax` is a conservative upper bound (current rot + a few FTINY).
+__device__ __forceinline__ bool cand_face(int4 hd, const double* __restrict__ g, const double org[3],
+                                          const double dir[3], double tmax, double& t, bool& front) {
+    const double2* g2 = reinterpret_cast<const double2*>(g);
+    double2 n01 = __ldg(&g2[0]), n2o = __ldg(&g2[1]);
+    double rdot = -(dir[0] * n01.x + dir[1] * n01.y + dir[2] * n2o.x);
+    if ((rdot <= RB_FTINY) & (rdot >= -RB_FTINY)) return false;
+    t = ((org[0] * n01.x + org[1] * n01.y + org[2] * n2o.x) - n2o.y) / rdot;
+    if ((t <= RB_FTINY) | (t > tmax)) return false;
+    front = rdot > 0;
+    int ax = (hd.x >> 10) & 3;
+    double p0 = org[0] + t * dir[0], p1 = org[1] + t * dir[1], p2 = org[2] + t * dir[2];
+    double x = ax == 0 ? p1 : ax == 1 ? p2 : p0;      // xi = (ax+1)%3
+    double y = ax == 0 ? p2 : ax == 1 ? p0 : p1;      // yi = (ax+2)%3
+    // 2-D bounding box first: outside by more than FTINY can never be "in"
+    // (no edge straddles y / all straddling edges on one side, and none of
+    // inface()'s three FABSEQ cases can fire); well inside an exact axis-aligned
+    // rectangle is always "in".  Only the FTINY border zone runs the edge loop.
+    double2 bx = __ldg(&g2[2]), by = __ldg(&g2[3]);
+    if ((x < bx.x - RB_FTINY) | (x > bx.y + RB_FTINY) | (y < by.x - RB_FTINY) | (y > by.y + RB_FTINY)) return false;
+    bool in = ((hd.x >> 12) & 1) && (x > bx.x + RB_FTINY) & (x < bx.y - RB_FTINY) & (y > by.x + RB_FTINY) &
+                                        (y < by.y - RB_FTINY);
+    return in || inface2d(g + 8, (hd.x >> 16) & 0xffff, x, y);
+}
+
+// Candidate of a sphere / cone-family surface (rare kinds, kept out of line).
+// Returns the single root the reference could accept: the first root > FTINY
+// (sphere.c:60-66) / the first root > FTINY within the end caps (o_cone.c:98-110)
+// / the ring's plane hit within its radii (o_cone.c:71-83).
+__device__ __noinline__ bool cand_other(int kind, const double* __restrict__ g, const double org[3],
+                                        const double dir[3], double tmax, double& t, bool& front) {
     if (kind == PK_SPHERE || kind == PK_BUBBLE) {
         double a = 0, b = 0, c = 0, root[2];
         for (int i = 0; i < 3; i++) {
             a += dir[i] * dir[i];
-            double t = org[i] - g[i];
-            b += 2.0 * dir[i] * t;
-            c += t * t;
+            double d = org[i] - g[i];
+            b += 2.0 * dir[i] * d;
+            c += d * d;
         }
         c -= g[3] * g[3];
         int nroots = quadratic(root, a, b, c);
-        int i; double t = 0;
+        int i;
         for (i = 0; i < nroots; i++)
             if ((t = root[i]) > RB_FTINY) break;
-        if (i >= nroots) return false;
-        double rodc = 1 - 2 * ((i > 0) ^ (kind == PK_BUBBLE));
-        if (rayreject(S, id, hd, h, aft, t, rodc)) return false;
-        // rod proper = -dir . ron (sphere.c:78)
-        double ar = g[3] * (1 - 2 * (kind == PK_BUBBLE));
-        double rod = 0;
-        for (int k = 0; k < 3; k++) {
-            double rp = org[k] + dir[k] * t;
-            rod += dir[k] * ((rp - g[k]) / ar);
-        }
-        h.robj = id; h.rot = t; h.rod = -rod;
+        if (i >= nroots || t > tmax) return false;
+        front = (1 - 2 * ((i > 0) ^ (kind == PK_BUBBLE))) > 0;
         return true;
     }
     if (kind >= PK_CONE && kind <= PK_RING) {
@@ -174,73 +155,61 @@ __device__ __noinline__ bool hit_object(const DScene& S, int id, const double or
             c = rox[0] * rox[0] + rox[1] * rox[1] - r0 * r0;
         } else {  // ring
             if ((rdx[2] <= RB_FTINY) & (rdx[2] >= -RB_FTINY)) return false;
-            root[0] = -rox[2] / rdx[2];
-            if (rayreject(S, id, hd, h, aft, root[0], -rdx[2])) return false;
-            b = root[0] * rdx[0] + rox[0];
-            c = root[0] * rdx[1] + rox[1];
+            t = -rox[2] / rdx[2];
+            if ((t <= RB_FTINY) | (t > tmax)) return false;
+            b = t * rdx[0] + rox[0];
+            c = t * rdx[1] + rox[1];
             a = b * b + c * c;
             if (a > r1 * r1 || a < r0 * r0) return false;
-            h.robj = id; h.rot = root[0]; h.rod = -rdx[2];
+            front = -rdx[2] > 0;
             return true;
         }
         int nroots = quadratic(root, a, b, c);
         for (int rn = 0; rn < nroots; rn++) {
             if (root[rn] <= RB_FTINY) continue;
-            if (root[rn] > h.rot + RB_FTINY) break;
-            double px[3], dx[3];
-            for (int k = 0; k < 3; k++) { px[k] = org[k] + root[rn] * dir[k]; dx[k] = px[k] - p0[k]; }
+            if (root[rn] > tmax) break;
+            double dx[3];
+            for (int k = 0; k < 3; k++) dx[k] = (org[k] + root[rn] * dir[k]) - p0[k];
             b = dot3(dx, ad);
             if (b < 0.0) continue;
             if (b > al) continue;
-            double rodc = 1 - 2 * ((rn > 0) ^ ((kind == PK_CUP) | (kind == PK_TUBE)));
-            if (rayreject(S, id, hd, h, aft, root[rn], rodc)) break;
-            // normal (o_cone.c:114-137) only to get rod
-            double sl = g[7], ron[3];
-            if (kind == PK_CYL) a = r0;
-            else if (kind == PK_TUBE) a = -r0;
-            else {
-                c = r1 - r0;
-                a = r0 + b * c / al;
-                if (kind == PK_CUP) { c = -c; a = -a; }
-            }
-            for (int k = 0; k < 3; k++) ron[k] = (dx[k] - b * ad[k]) / a;
-            if ((kind == PK_CONE) | (kind == PK_CUP))
-                for (int k = 0; k < 3; k++) ron[k] = (al * ron[k] - c * ad[k]) / sl;
-            a = dot3(ron, ron);
-            if ((a > 1. + RB_FTINY) | (a < 1. - RB_FTINY)) {
-                c = 1. / (.5 + .5 * a);
-                ron[0] *= c; ron[1] *= c; ron[2] *= c;
-            }
-            h.robj = id; h.rot = root[rn]; h.rod = -dot3(dir, ron);
+            t = root[rn];
+            front = (1 - 2 * ((rn > 0) ^ ((kind == PK_CUP) | (kind == PK_TUBE)))) > 0;
             return true;
         }
-        return false;
-    }
-    if (kind == PK_UNSUPPORTED) {
-        atomicOr(errflag, RB_ERR_UNSUP_PRIM);
-        *errobj = (unsigned)id;
     }
     return false;
 }
 
-// Surface normal and hit point of an accepted hit (recomputed once per ray
-// instead of being carried through the walk).
-__device__ __noinline__ void hit_frame(const DScene& S, const Hit& h, const double org[3],
-                                       const double dir[3], double rop[3], double ron[3]) {
-    for (int k = 0; k < 3; k++) rop[k] = org[k] + h.rot * dir[k];
-    int4 hd = __ldg(&S.objhdr[h.robj]);
+// Hit point, surface normal and rod = -rdir.ron of an accepted hit, computed
+// once per ray by the shading kernel with the reference's expressions
+// (o_face.c:52-56, sphere.c:72-78, o_cone.c:84-138).
+__device__ __noinline__ void hit_frame(const DScene& S, int robj, double rot, const double org[3],
+                                       const double dir[3], double rop[3], double ron[3], double& rod) {
+    for (int k = 0; k < 3; k++) rop[k] = org[k] + rot * dir[k];
+    int4 hd = __ldg(&S.objhdr[robj]);
     int kind = hd.x & 0xff;
     const double* g = S.geom + hd.w;
-    if (kind == PK_FACE) { ron[0] = g[0]; ron[1] = g[1]; ron[2] = g[2]; return; }
+    if (kind == PK_FACE) {
+        ron[0] = g[0]; ron[1] = g[1]; ron[2] = g[2];
+        rod = -(dir[0] * ron[0] + dir[1] * ron[1] + dir[2] * ron[2]);
+        return;
+    }
     if (kind == PK_SPHERE || kind == PK_BUBBLE) {
         double ar = g[3] * (1 - 2 * (kind == PK_BUBBLE));
         for (int k = 0; k < 3; k++) {
-            rop[k] = org[k] + dir[k] * h.rot;
+            rop[k] = org[k] + dir[k] * rot;
             ron[k] = (rop[k] - g[k]) / ar;
         }
+        rod = -dot3(dir, ron);
         return;
     }
-    if (kind == PK_RING) { ron[0] = g[0]; ron[1] = g[1]; ron[2] = g[2]; return; }
+    if (kind == PK_RING) {
+        const double* tm = g + 12;
+        ron[0] = g[0]; ron[1] = g[1]; ron[2] = g[2];
+        rod = -(dir[0] * tm[2] + dir[1] * tm[5] + dir[2] * tm[8]);      // -rdx[2]
+        return;
+    }
     const double* ad = g; double al = g[3];
     const double* p0 = g + 4;
     double r0 = g[8], r1 = g[9], sl = g[7];
@@ -262,34 +231,10 @@ __device__ __noinline__ void hit_frame(const DScene& S, const Hit& h, const doub
         c = 1. / (.5 + .5 * a);
         ron[0] *= c; ron[1] *= c; ron[2] *= c;
     }
+    rod = -dot3(dir, ron);
 }
 
 struct WalkStats { unsigned nodes, leafents, prims; };
-
-// The polygon test of o_face(), inlined in the walk (it is >95 % of all tests).
-__device__ __forceinline__ void hit_face(const DScene& S, int id, int4 hd, const double* __restrict__ g,
-                                         const double org[3], const double dir[3], Hit& h, bool aft) {
-    const double2* g2 = reinterpret_cast<const double2*>(g);
-    double2 n01 = __ldg(&g2[0]), n2o = __ldg(&g2[1]);
-    double rdot = -(dir[0] * n01.x + dir[1] * n01.y + dir[2] * n2o.x);
-    if ((rdot <= RB_FTINY) & (rdot >= -RB_FTINY)) return;
-    double t = ((org[0] * n01.x + org[1] * n01.y + org[2] * n2o.x) - n2o.y) / rdot;
-    if (rayreject(S, id, hd, h, aft, t, rdot)) return;
-    int ax = (hd.x >> 10) & 3;
-    double p0 = org[0] + t * dir[0], p1 = org[1] + t * dir[1], p2 = org[2] + t * dir[2];
-    double x = ax == 0 ? p1 : ax == 1 ? p2 : p0;      // xi = (ax+1)%3
-    double y = ax == 0 ? p2 : ax == 1 ? p0 : p1;      // yi = (ax+2)%3
-    // 2-D bounding box first: outside by more than FTINY can never be "in"
-    // (no edge straddles y / all straddling edges on one side, and none of
-    // inface()'s three FABSEQ cases can fire); well inside an exact axis-aligned
-    // rectangle is always "in".  Only the FTINY border zone runs the edge loop.
-    double2 bx = __ldg(&g2[2]), by = __ldg(&g2[3]);
-    if ((x < bx.x - RB_FTINY) | (x > bx.y + RB_FTINY) | (y < by.x - RB_FTINY) | (y > by.y + RB_FTINY)) return;
-    bool in = ((hd.x >> 12) & 1) && (x > bx.x + RB_FTINY) & (x < bx.y - RB_FTINY) & (y > by.x + RB_FTINY) &
-                                        (y < by.y - RB_FTINY);
-    if (!in && !inface2d(g + 8, (hd.x >> 16) & 0xffff, x, y)) return;
-    h.robj = id; h.rot = t; h.rod = rdot;
-}
 
 // sourcehit() lives in rb_shade.cuh; declared here for the retire step
 __device__ __forceinline__ int sourcehit(const DScene& S, const double dir[3], int rsrc, int crtype);
@@ -300,49 +245,64 @@ struct TraceIO {
     HitRec* __restrict__ hits;
     unsigned* next;              // global fetch counter
 };
-#ifndef RB_MAILBOX
-#define RB_MAILBOX 0
-#endif
-#ifndef RB_FETCH_MIN
-#define RB_FETCH_MIN 6           // refill a warp when this many lanes are idle
-#endif
 
-// walk_rays(): persistent-thread localhit().  Every warp keeps pulling rays
-// from the queue: a lane whose ray is finished retires it (writes its HitRec,
-// running sourcehit() for misses) and, as soon as RB_FETCH_MIN lanes of the
-// warp are idle, the warp reserves that many queue slots with one atomicAdd and
-// the idle lanes start new rays.  Ray lengths are heavy-tailed (most rays end
-// in nearby clutter, a few cross the whole room), so without the refill a warp
-// ran at < 5 live lanes on average (profiles/r1_notes.md).
-// The walk itself is organised in warp-synchronous phases -- walk to the next
-// full leaf / test the leaf's surfaces / accept-or-continue -- with a
-// __syncwarp() after each, so that lanes re-converge every phase.  `stk` is
-// this thread's column of the shared-memory node stack.  MUST be called by all
-// 32 lanes of a warp together.
-__device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, volatile int* stk, int stride,
-                                          WalkStats& ws, unsigned& nretired, unsigned* errflag,
-                                          unsigned* errobj) {
-    const unsigned lane = threadIdx.x & 31;
+// Shared memory of one CTA of k_trace (per-thread columns, SoA).
+template <int NT>
+struct WalkSmem {
+    int stk[RB_STACK][NT];       // ancestors of the current cube
+    double ray[6][NT];           // staged ray: origin, direction
+    double rot[NT];              // current best distance
+    int set[NT];                 // leaf-set offset of the surfaces to test this round
+    int kst[NT];                 // index of the first of them (descending)
+    int excl[NT];                // exclusive prefix of the per-lane surface counts
+    int ndef[NT / 32];           // deferred (non-polygon) pairs of this round
+    int defer[NT / 32][RB_PAIRS];
+    double ct[NT / 32][RB_PAIRS];   // candidate distance per (ray, surface) pair
+    int cid[NT / 32][RB_PAIRS];     // candidate: object id << 1 | front, or -1
+};
+
+// walk_rays(): persistent-thread, warp-cooperative localhit().
+//  * Every warp keeps pulling rays from the queue: a lane whose ray is finished
+//    retires it (HitRec; sourcehit() for misses) and, when RB_FETCH_MIN lanes
+//    are idle, the warp reserves that many queue slots with one atomicAdd.
+//    Ray lengths are heavy-tailed, so without the refill a warp ran at < 5 live
+//    lanes on average (profiles/r1_notes.md).
+//  * Phase A (per lane): descend to the leaf that holds the ray's position
+//    (raymove, raytrace.c:668-687); 1-3 cheap iterations.
+//  * Phase B (whole warp): the surfaces waiting in the lanes' leaves form
+//    (ray, surface) pairs; the 32 lanes take pairs round-robin, read the ray
+//    from shared memory and compute the pair's candidate.  Leaves hold 0..6
+//    surfaces and only ~1 lane in 6 stands in a full leaf at a time, so testing
+//    them lane-by-lane left ~10 of 32 lanes busy; pairs keep all lanes busy.
+//    The owner then applies rayreject() to its candidates in descending index
+//    order.  Spheres / cones (rare) are deferred to a second cooperative pass.
+//  * Phase C (per lane, all lanes together): checkhit()'s "hit point in this
+//    cube" test (raytrace.c:756-759), else the step to the neighbour cube
+//    (raytrace.c:688-738).  Every live lane does exactly one step per round,
+//    so the expensive step code (3 divisions) runs with the warp nearly full;
+//    in the first version it ran with ~5 of 32 lanes.
+// MUST be called by all threads of the CTA.
+template <int NT>
+__device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, WalkSmem<NT>& sm, WalkStats& ws,
+                                          unsigned& nretired, unsigned* errflag, unsigned* errobj) {
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     const double cs = S.cusize;
     const int2* __restrict__ pool = reinterpret_cast<const int2*>(S.leafpool);
-    double org[3] = {0, 0, 0}, dir[3] = {0, 0, 1}, pos[3] = {0, 0, 0}, rmax = 0, size = cs;
-    Hit h; h.robj = -1; h.rot = RB_FHUGE; h.rod = 1.0;
-    int dirf = 0, w = -1, L = 0, rsrc = -1, crtype = 0;
+    double dir[3] = {0, 0, 1}, pos[3] = {0, 0, 0}, size = cs, rot = RB_FHUGE;
+    int robj = -1, dirf = 0, w = -1, L = 0;
     unsigned ix = 0, iy = 0, iz = 0, ridx = 0;
-    bool aft = false, need_adv = false, done = true, result = false, have = false, exhausted = false;
-#if RB_MAILBOX
-    int4 mb = make_int4(-1, -1, -1, -1);
-#endif
+    bool front = true, aft = false, done = true, result = false, have = false, exhausted = false;
     for (;;) {
         // ---- retire finished rays ----
         if (have & done) {
             HitRec o;
-            o.rot = h.rot; o.rod = h.rod; o.robj = h.robj; o.local = 1;
+            o.rot = rot; o.rod = front ? 1.0 : -1.0; o.robj = robj; o.local = 1;
             if (!result) {
                 o.rot = RB_FHUGE; o.rod = 1.0; o.robj = -1; o.local = 0;
-                if (!(rmax > RB_FTINY)) {            // aft-clipped rays never see sources
-                    int sn = sourcehit(S, dir, rsrc, crtype);
+                const QRay& q = io.qin[ridx];
+                if (!(q.rmax > RB_FTINY)) {          // aft-clipped rays never see sources
+                    int sn = sourcehit(S, dir, q.rsrc, q.info & 0x3ff);
                     if (sn >= 0) o.robj = S.srcs[sn].so;
                 }
             }
@@ -364,8 +324,11 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, vol
             if (!have && my < io.nin) {
                 const double2* q2 = reinterpret_cast<const double2*>(&io.qin[my]);
                 double2 a = __ldg(&q2[0]), b = __ldg(&q2[1]), c = __ldg(&q2[2]), d = __ldg(&q2[3]);
-                org[0] = a.x; org[1] = a.y; org[2] = b.x; dir[0] = b.y; dir[1] = c.x; dir[2] = c.y; rmax = d.x;
-                crtype = io.qin[my].info & 0x3ff; rsrc = io.qin[my].rsrc;
+                double org[3] = {a.x, a.y, b.x};
+                dir[0] = b.y; dir[1] = c.x; dir[2] = c.y;
+                double rmax = d.x;
+                sm.ray[0][tid] = org[0]; sm.ray[1][tid] = org[1]; sm.ray[2][tid] = org[2];
+                sm.ray[3][tid] = dir[0]; sm.ray[4][tid] = dir[1]; sm.ray[5][tid] = dir[2];
                 ridx = my; have = true;
                 // ---- localhit() prologue (raytrace.c:604-651) ----
                 dirf = 0;
@@ -375,9 +338,9 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, vol
                     if (dir[i] > 1e-7) dirf |= 1 << i;
                     else if (dir[i] < -1e-7) dirf |= 0x10 << i;
                 }
-                h.robj = -1; h.rot = RB_FHUGE; h.rod = 1.0;
-                done = !dirf; result = false; aft = false; need_adv = false;
-                if (!done && rmax > RB_FTINY) { aft = true; h.rot = rmax; }
+                robj = -1; rot = RB_FHUGE; front = true;
+                done = !dirf; result = false; aft = false;
+                if (!done && rmax > RB_FTINY) { aft = true; rot = rmax; }
                 if (!done) {
                     bool in = !(S.cuorg[0] > pos[0] || pos[0] >= S.cuorg[0] + cs ||
                                 S.cuorg[1] > pos[1] || pos[1] >= S.cuorg[1] + cs ||
@@ -394,7 +357,7 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, vol
                             if (dt > t) t = dt;
                         }
                         t += RB_FTINY;
-                        if (t >= h.rot) done = true;
+                        if (t >= rot) done = true;
                         else {
 #pragma unroll
                             for (int i = 0; i < 3; i++) pos[i] = pos[i] + dir[i] * t;
@@ -406,48 +369,153 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, vol
                     }
                 }
                 w = S.root; L = 0; ix = iy = iz = 0; size = cs;
-#if RB_MAILBOX
-                mb = make_int4(-1, -1, -1, -1);
-#endif
             }
         }
         __syncwarp();
-
-        // ---- phase A: walk (descend / skip empty cubes) until standing in a
-        //      fresh full leaf.  One loop, two short bodies, so lanes re-join
-        //      every iteration (raymove, raytrace.c:668-738) ----
-        if (!done) {
-            for (;;) {
-                if (w >= 0) {                         // descend one level
-                    stk[L * stride] = w;
-                    double half = size * 0.5;
-                    double lox = fma((double)ix, size, S.cuorg[0]);
-                    double loy = fma((double)iy, size, S.cuorg[1]);
-                    double loz = fma((double)iz, size, S.cuorg[2]);
-                    int br = 0;
-                    ix <<= 1; iy <<= 1; iz <<= 1;
-                    if (pos[0] >= lox + half) { br |= 1; ix |= 1; }
-                    if (pos[1] >= loy + half) { br |= 2; iy |= 1; }
-                    if (pos[2] >= loz + half) { br |= 4; iz |= 1; }
-                    w = __ldg(&S.nodes[(size_t)w * 8 + br]);
-                    ws.nodes++;
-                    size = half; L++;
-                    continue;
-                }
-                if ((w < -1) & !need_adv) break;      // arrived at a full leaf
+        bool act = have & !done;
+        // ---- phase A: descend to a leaf (raymove, raytrace.c:668-687) ----
+        for (;;) {
+            const bool d = act & (w >= 0);
+            if (!__any_sync(FULL, d)) break;
+            if (d) {
+                sm.stk[L][tid] = w;
+                double half = size * 0.5;
                 double lox = fma((double)ix, size, S.cuorg[0]);
                 double loy = fma((double)iy, size, S.cuorg[1]);
                 double loz = fma((double)iz, size, S.cuorg[2]);
-                double hix = lox + size, hiy = loy + size, hiz = loz + size;
-                if ((w == -1) & aft & (h.robj < 0)) { // aft-plane point in an empty leaf (:709-710)
-                    double px = org[0] + h.rot * dir[0];
-                    double py = org[1] + h.rot * dir[1];
-                    double pz = org[2] + h.rot * dir[2];
-                    if (!(lox > px || px >= hix || loy > py || py >= hiy || loz > pz || pz >= hiz)) {
-                        done = true; result = false;
-                        break;
+                int br = 0;
+                ix <<= 1; iy <<= 1; iz <<= 1;
+                if (pos[0] >= lox + half) { br |= 1; ix |= 1; }
+                if (pos[1] >= loy + half) { br |= 2; iy |= 1; }
+                if (pos[2] >= loz + half) { br |= 4; iz |= 1; }
+                w = __ldg(&S.nodes[(size_t)w * 8 + br]);
+                ws.nodes++;
+                size = half; L++;
+            }
+        }
+        const bool full = act & (w < -1);
+        int kleft = 0, setoff = 0;
+        if (full) {
+            setoff = -w - 2;
+            kleft = __ldg(&pool[setoff]).x;
+            ws.leafents += kleft + 1;
+            ws.prims += kleft;
+        }
+        // ---- phase B: the warp tests the leaves' surfaces as (ray, surface) pairs ----
+        for (;;) {
+            const int m = min(kleft, RB_OPR);
+            int incl = m;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int v = __shfl_up_sync(FULL, incl, d);
+                if ((int)lane >= d) incl += v;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            if (total == 0) break;
+            const unsigned wbase = wid * 32;
+            sm.excl[tid] = incl - m;
+            sm.set[tid] = setoff;
+            sm.kst[tid] = kleft;
+            sm.rot[tid] = rot;
+            if (lane == 0) sm.ndef[wid] = 0;
+            __syncwarp();
+            for (int p = lane; p < total; p += 32) {
+                // owner = last lane whose exclusive prefix is <= p
+                int lo = 0;
+#pragma unroll
+                for (int s2 = 16; s2 > 0; s2 >>= 1)
+                    if (sm.excl[wbase + lo + s2] <= p) lo += s2;
+                const unsigned own = wbase + lo;
+                const int k = sm.kst[own] - (p - sm.excl[own]);          // descending index
+                const int2 ent = __ldg(&pool[sm.set[own] + k]);
+                const double* g = S.geom + ent.y;
+                const int4 hd = __ldg(reinterpret_cast<const int4*>(g - 2));
+                const int kind = hd.x & 0xff;
+                if (kind == PK_FACE) {
+                    const double org[3] = {sm.ray[0][own], sm.ray[1][own], sm.ray[2][own]};
+                    const double rd[3] = {sm.ray[3][own], sm.ray[4][own], sm.ray[5][own]};
+                    const double tmax = sm.rot[own] + 8 * RB_FTINY;      // ties may raise rot by < FTINY each
+                    double t = 0;
+                    bool fr = true;
+                    const bool ok = cand_face(hd, g, org, rd, tmax, t, fr);
+                    sm.ct[wid][p] = t;
+                    sm.cid[wid][p] = ok ? ((ent.x << 1) | (int)fr) : -1;
+                } else {                         // rare kinds: second pass, again with all lanes
+                    sm.cid[wid][p] = -1;
+                    if (kind == PK_UNSUPPORTED) { atomicOr(errflag, RB_ERR_UNSUP_PRIM); *errobj = (unsigned)ent.x; }
+                    else if (kind != PK_NONE) sm.defer[wid][atomicAdd(&sm.ndef[wid], 1)] = p | (own << 16);
+                }
+            }
+            __syncwarp();
+            const int ndef = sm.ndef[wid];
+            for (int q = lane; q < ndef; q += 32) {
+                const int pq = sm.defer[wid][q];
+                const int p = pq & 0xffff;
+                const unsigned own = (unsigned)pq >> 16;
+                const int k = sm.kst[own] - (p - sm.excl[own]);
+                const int2 ent = __ldg(&pool[sm.set[own] + k]);
+                const double* g = S.geom + ent.y;
+                const int kind = __ldg(reinterpret_cast<const int4*>(g - 2)).x & 0xff;
+                const double org[3] = {sm.ray[0][own], sm.ray[1][own], sm.ray[2][own]};
+                const double rd[3] = {sm.ray[3][own], sm.ray[4][own], sm.ray[5][own]};
+                double t = 0;
+                bool fr = true;
+                if (cand_other(kind, g, org, rd, sm.rot[own] + 8 * RB_FTINY, t, fr)) {
+                    sm.ct[wid][p] = t;
+                    sm.cid[wid][p] = (ent.x << 1) | (int)fr;
+                }
+            }
+            __syncwarp();
+            // owners apply rayreject() in the reference's order (raytrace.c:535-575)
+            const int e0 = incl - m;
+            for (int j = 0; j < m; j++) {
+                const int c = sm.cid[wid][e0 + j];
+                if (c < 0) continue;
+                const double t = sm.ct[wid][e0 + j];
+                const int id = c >> 1;
+                const bool fr = c & 1;
+                if ((t <= RB_FTINY) | (t > rot + RB_FTINY)) continue;
+                if (!(t < rot - RB_FTINY)) {              // coincident point, so decide...
+                    if (id == robj) continue;
+                    if (robj < 0) { if (aft) continue; }
+                    else {
+                        const int4 hnew = __ldg(&S.objhdr[id]), hold = __ldg(&S.objhdr[robj]);
+                        const int fnew = hnew.x >> 8, fold = hold.x >> 8;
+                        const bool mnew = fnew & PF_HASMAT, mray = fold & PF_HASMAT;
+                        bool rej = false, dec = false;
+                        if (!mnew) { if (mray) { rej = true; dec = true; } }
+                        else if (!mray) { dec = true; }
+                        else if (fnew & PF_TRANSP) { if (!(fold & PF_TRANSP)) { rej = true; dec = true; } }
+                        else if (fold & PF_TRANSP) { dec = true; }
+                        if (!dec) {
+                            if (!fr) { if (front) { rej = true; dec = true; } }
+                            else if (!front) { dec = true; }
+                        }
+                        if (!dec) rej = hold.y >= hnew.y;  // later modifier definition wins tie
+                        if (rej) continue;
                     }
                 }
+                robj = id; rot = t; front = fr;
+            }
+            kleft -= m;
+            __syncwarp();
+        }
+        // ---- phase C: accept (checkhit / aft plane), else step to the neighbour cube ----
+        if (act) {
+            const double lox = fma((double)ix, size, S.cuorg[0]);
+            const double loy = fma((double)iy, size, S.cuorg[1]);
+            const double loz = fma((double)iz, size, S.cuorg[2]);
+            const double hix = lox + size, hiy = loy + size, hiz = loz + size;
+            if (full ? (robj >= 0) : (aft & (robj < 0))) {
+                // checkhit (raytrace.c:756-759) / aft-plane point in an empty leaf (:709-710)
+                const double px = sm.ray[0][tid] + rot * dir[0];
+                const double py = sm.ray[1][tid] + rot * dir[1];
+                const double pz = sm.ray[2][tid] + rot * dir[2];
+                if (!(lox > px || px >= hix || loy > py || py >= hiy || loz > pz || pz >= hiz)) {
+                    done = true; result = full;
+                }
+            }
+            if (!done) {
                 // advance to next cube (raytrace.c:712-738)
                 int ax = 0;
                 double t;
@@ -470,58 +538,18 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, vol
                 for (int i = 0; i < 3; i++) pos[i] = pos[i] + dir[i] * t;
                 // step to the neighbour, ascending on overflow (raytrace.c:688-706):
                 // climb while the cell coordinate along ax cannot move that way
-                bool positive = dirf & (1 << ax);
-                unsigned ia = ax == 0 ? ix : ax == 1 ? iy : iz;
-                unsigned blocked = positive ? ia : ~ia;            // trailing ones = levels to climb
-                int up = (~blocked) ? __ffs(~blocked) - 1 : 32;    // number of trailing one bits
-                if (up >= L) { done = true; result = (h.robj >= 0); break; }   // left the scene cube
-                ix >>= up; iy >>= up; iz >>= up; L -= up;
-                size = ldexp(size, up);
-                if (ax == 0) ix ^= 1; else if (ax == 1) iy ^= 1; else iz ^= 1;
-                int br = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
-                w = __ldg(&S.nodes[(size_t)stk[(L - 1) * stride] * 8 + br]);
-                ws.nodes++;
-                need_adv = false;
-            }
-        }
-        __syncwarp();
-        // ---- phase B: test the leaf's surfaces, highest index first (rayhit) ----
-        {
-            int cnt = 0;
-            const int2* set = pool;
-            if (!done) {
-                set = pool + (-w - 2);
-                cnt = __ldg(&set[0]).x;
-                ws.leafents += cnt + 1;
-                ws.prims += cnt;
-            }
-            for (int k = cnt; k > 0; k--) {
-                int2 ent = __ldg(&set[k]);
-#if RB_MAILBOX
-                // mailbox: surfaces spanning several leaves were already tested for
-                // this ray; the re-test is a no-op (see header), so skip it
-                if ((ent.x == mb.x) | (ent.x == mb.y) | (ent.x == mb.z) | (ent.x == mb.w)) { ws.prims--; continue; }
-                mb.w = mb.z; mb.z = mb.y; mb.y = mb.x; mb.x = ent.x;
-#endif
-                const double* g = S.geom + ent.y;
-                int4 hd = __ldg(reinterpret_cast<const int4*>(g - 2));
-                if ((hd.x & 0xff) == PK_FACE) hit_face(S, ent.x, hd, g, org, dir, h, aft);
-                else hit_object(S, ent.x, org, dir, h, aft, errflag, errobj);
-            }
-        }
-        __syncwarp();
-        // ---- phase C: checkhit (raytrace.c:756-759): hit OK if in current cube ----
-        if (!done) {
-            need_adv = true;
-            if (h.robj >= 0) {
-                double lox = fma((double)ix, size, S.cuorg[0]);
-                double loy = fma((double)iy, size, S.cuorg[1]);
-                double loz = fma((double)iz, size, S.cuorg[2]);
-                double px = org[0] + h.rot * dir[0];
-                double py = org[1] + h.rot * dir[1];
-                double pz = org[2] + h.rot * dir[2];
-                if (!(lox > px || px >= lox + size || loy > py || py >= loy + size || loz > pz || pz >= loz + size)) {
-                    done = true; result = true;
+                const bool positive = dirf & (1 << ax);
+                const unsigned ia = ax == 0 ? ix : ax == 1 ? iy : iz;
+                const unsigned blocked = positive ? ia : ~ia;          // trailing ones = levels to climb
+                const int up = (~blocked) ? __ffs(~blocked) - 1 : 32;  // number of trailing one bits
+                if (up >= L) { done = true; result = (robj >= 0); }    // left the scene cube
+                else {
+                    ix >>= up; iy >>= up; iz >>= up; L -= up;
+                    size = ldexp(size, up);
+                    if (ax == 0) ix ^= 1; else if (ax == 1) iy ^= 1; else iz ^= 1;
+                    const int br = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
+                    w = __ldg(&S.nodes[(size_t)sm.stk[L - 1][tid] * 8 + br]);
+                    ws.nodes++;
                 }
             }
         }
