@@ -68,7 +68,13 @@ __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const Wave
 }
 
 // Shade: material evaluation, contribution accumulation, child-ray emission.
-__global__ void __launch_bounds__(WAVE_THREADS) k_shade(const WaveArgs A) {
+#ifndef RB_SHADE_MINBLOCKS
+#define RB_SHADE_MINBLOCKS 6
+#endif
+#ifndef RB_SHADE_THREADS
+#define RB_SHADE_THREADS 128
+#endif
+__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(const WaveArgs A) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.nin) return;
     const QRay q = A.qin[i];
@@ -419,7 +425,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         k_trace<<<tgrid, WAVE_THREADS, 0, stream_>>>(A);
         CK(cudaEventRecord(ev1_, stream_));
         CK(cudaEventRecord(ev2_, stream_));
-        k_shade<<<grid, WAVE_THREADS, 0, stream_>>>(A);
+        k_shade<<<(nq + RB_SHADE_THREADS - 1) / RB_SHADE_THREADS, RB_SHADE_THREADS, 0, stream_>>>(A);
         CK(cudaEventRecord(ev3_, stream_));
         stats.launches += 2; stats.wave_launches++; stats.waves++;
         CK(cudaGetLastError());

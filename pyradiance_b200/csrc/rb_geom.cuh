@@ -33,6 +33,9 @@ namespace rb {
 #ifndef RB_OPR
 #define RB_OPR 6                 // surfaces per ray per round handed to the warp
 #endif
+#ifndef RB_DITERS
+#define RB_DITERS 32             // descend steps per round
+#endif
 #ifndef RB_FETCH_MIN
 #define RB_FETCH_MIN 6           // refill a warp when this many lanes are idle
 #endif
@@ -373,8 +376,11 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
         }
         __syncwarp();
         bool act = have & !done;
-        // ---- phase A: descend to a leaf (raymove, raytrace.c:668-687) ----
-        for (;;) {
+        // ---- phase A: descend towards a leaf (raymove, raytrace.c:668-687); at most
+        //      RB_DITERS levels per round -- a freshly fetched ray needs ~8 levels and
+        //      would otherwise hold the other 31 lanes; it just sits out this round ----
+#pragma unroll 1
+        for (int it = 0; it < RB_DITERS; it++) {
             const bool d = act & (w >= 0);
             if (!__any_sync(FULL, d)) break;
             if (d) {
@@ -393,6 +399,7 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 size = half; L++;
             }
         }
+        act &= (w < 0);                          // still inside the tree: continue next round
         const bool full = act & (w < -1);
         int kleft = 0, setoff = 0;
         if (full) {

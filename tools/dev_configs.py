@@ -1,0 +1,60 @@
+"""Developer check of BASELINE configs 3 and 4 at reduced size against the reference binaries."""
+import os, sys, time
+from pathlib import Path
+import numpy as np
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from pyradiance_b200 import _lib, scenegen
+from oracle import refrun
+TMP = Path(os.environ.get("RB_TMP", "/tmp/rbt")); TMP.mkdir(parents=True, exist_ok=True)
+
+def c3(npoly=1_000_000, floors=10, nsens=2000, nref=24):
+    rad, octf = TMP / "bld.rad", TMP / "bld.oct"
+    t = time.time(); scenegen.write_office(rad, npolys=npoly, floors=floors, seed=77); t1 = time.time()
+    scenegen.build_octree(rad, octf); print(f"C3 scene: gen {t1-t:.1f}s oconv {time.time()-t1:.1f}s {octf.stat().st_size/1e6:.0f} MB")
+    sens = scenegen.office_sensors(nsens, floors=floors, seed=3)
+    opts = ["-ab", "5", "-ad", "10000", "-lw", "1e-4"]
+    P = "MF=4,rNx=0,rNy=0,rNz=-1,Ux=0,Uy=1,Uz=0,RHS=+1"
+    ctx = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB); t = time.time(); ctx.load_octree(octf); print(f"  load {time.time()-t:.2f}s")
+    ctx.set_options(opts); ctx.cal_load("reinhartb.cal"); ctx.cal_set(P); ctx.add_modifier("skyglow", P, "rbin", int(ctx.cal_eval("Nrbins")+.5))
+    t = time.time(); m = ctx.rcontrib(sens, flags=_lib.RB_IRRAD_RCONTRIB); dt = time.time()-t; st = ctx.stats()
+    print(f"  GPU: {nsens} sensors x 2305 bins in {dt:.2f}s, {st['nrays']/1e6:.0f} Mrays, {st['nrays']/dt/1e6:.0f} Mrays/s wall, k_trace {st['nrays']/st['wave_ms']/1e3:.0f} Mrays/s, batches {st['batches']} retries {st['retries']}; nodes/ray {st['nodes']/st['nrays']:.1f} prims/ray {st['prims']/st['nrays']:.1f}")
+    idx = np.linspace(0, nsens-1, nref).astype(int)
+    t = time.time()
+    ref = refrun.rcontrib(octf, sens[idx], ["-I+"] + opts + ["-f", "reinhartb.cal", "-p", P, "-bn", "Nrbins", "-b", "rbin", "-m", "skyglow"], nproc=os.cpu_count()).reshape(nref, -1, 3)
+    print(f"  ref: {nref} sensors in {time.time()-t:.1f}s")
+    a = m[idx, :, 0].sum(1); b = ref[:, :, 0].sum(1)
+    print("  row sums gpu", np.round(a[:8], 4), "\n  row sums ref", np.round(b[:8], 4), "\n  total gpu %.4f ref %.4f" % (a.sum(), b.sum()))
+
+def c4(nrays=200000, nref=2000):
+    # S-view-like: 8 window groups, each window its own glow modifier, Klems full bins
+    rad, octf = TMP / "view.rad", TMP / "view.oct"
+    import io
+    rng = np.random.default_rng(5); out = io.StringIO(); out.write(scenegen.MATERIALS)
+    for i in range(8):
+        out.write(f"void glow wg{i}\n0\n0\n4 1 1 1 0\n\n")
+    # office with windows replaced by glow polygons wg_i (facing inward)
+    buf = io.StringIO(); scenegen.office_floor(buf, rng, 0.0, 1500, tag="f0")
+    txt = buf.getvalue()
+    for i in range(8):
+        txt = txt.replace(f"win_glass polygon f0.win{i}\n", f"wg{i} polygon f0.win{i}\n")
+    out.write(txt); rad.write_text(out.getvalue()); scenegen.build_octree(rad, octf)
+    rays = scenegen.random_rays(nrays, seed=9, lo=(5, 5, 0.5), hi=(35, 20, 2.5))
+    opts = ["-ab", "3", "-ad", "1024", "-lw", "1e-4"]
+    ctx = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB); ctx.load_octree(octf); ctx.set_options(opts)
+    ctx.cal_load("klems_full.cal"); ctx.cal_set("RHS=+1")
+    args = ["-f", "klems_full.cal", "-p", "RHS=+1", "-bn", "Nkbins", "-b", "kbin(0,-1,0,0,0,1)"]
+    for i in range(8):
+        ctx.add_modifier(f"wg{i}", "RHS=+1", "kbin(0,-1,0,0,0,1)", int(ctx.cal_eval("Nkbins")+.5)); args += ["-m", f"wg{i}"]
+    t = time.time(); m = ctx.rcontrib(rays); dt = time.time()-t; st = ctx.stats()
+    print(f"C4-mini GPU: {nrays} view rays x {ctx.num_columns()} cols in {dt:.2f}s, {st['nrays']/1e6:.0f} Mrays, {st['nrays']/dt/1e6:.0f} Mrays/s wall")
+    t = time.time(); ref = refrun.rcontrib(octf, rays[:nref], opts + args, nproc=os.cpu_count()).reshape(nref, -1, 3); print(f"  ref {nref} rays {time.time()-t:.1f}s")
+    g = m[:nref, :, 0].astype(float); r = ref[:, :, 0]
+    per_mod_g = g.reshape(nref, 8, 145).sum((0, 2)); per_mod_r = r.reshape(nref, 8, 145).sum((0, 2))
+    print("  per-window-group totals gpu", np.round(per_mod_g, 2), "\n  per-window-group totals ref", np.round(per_mod_r, 2))
+    print("  total gpu %.3f ref %.3f" % (g.sum(), r.sum()))
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c3", "c4"]
+    if "c4" in which: c4()
+    if "c3" in which: c3()

@@ -20,4 +20,4 @@ for r in range(reps):
     ctx.reset_stats(); t = time.time()
     m = ctx.rcontrib(sens, flags=_lib.RB_IRRAD_RCONTRIB); dt = time.time() - t
     st = ctx.stats()
-    print(f"rep {r}: {nsens} sensors {dt:.3f}s rays {st['nrays']} {st['nrays']/dt/1e6:.1f} Mrays/s wall; k_wave {st['wave_ms']:.1f} ms -> {st['nrays']/st['wave_ms']/1e3:.1f} Mrays/s; nodes/ray {st['nodes']/st['nrays']:.1f} leafents/ray {st['leafents']/st['nrays']:.1f} prims/ray {st['prims']/st['nrays']:.1f} sum {m.sum():.3f}")
+    print(f"rep {r}: {nsens} sensors {dt:.3f}s rays {st['nrays']} {st['nrays']/dt/1e6:.1f} Mrays/s wall; k_trace {st["wave_ms"]:.1f} ms shade {st["shade_ms"]:.1f} ms -> {st['nrays']/st['wave_ms']/1e3:.1f} Mrays/s; nodes/ray {st['nodes']/st['nrays']:.1f} leafents/ray {st['leafents']/st['nrays']:.1f} prims/ray {st['prims']/st['nrays']:.1f} sum {m.sum():.3f}")
