@@ -321,6 +321,34 @@ def rtrace(
 
 
 # -------------------------------------------------------------- rcontrib ----
+def _ofname(ospec: str, mname: str, bn: int):
+    """rc2.c:40-92 ofname(): expand %s (modifier) and %d (bin) in an output spec.
+    Returns (file name, has_modifier, has_bin)."""
+    order = []
+    i = 0
+    while i < len(ospec):
+        if ospec[i] == "%":
+            i += 1
+            while i < len(ospec) and ospec[i].isdigit():
+                i += 1
+            c = ospec[i:i + 1]
+            if c == "%":
+                pass
+            elif c == "s":
+                if "s" in order:
+                    raise RBError(f"bad output format '{ospec}'")
+                order.append("s")
+            elif c and c in "dioxX":
+                if "d" in order:
+                    raise RBError(f"bad output format '{ospec}'")
+                order.append("d")
+            else:
+                raise RBError(f"bad output format '{ospec}'")
+        i += 1
+    args = tuple(mname if o == "s" else bn for o in order)
+    return (ospec % args) if args else ospec.replace("%%", "%"), "s" in order, "d" in order
+
+
 def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_array: bool = False):
     """Interpret an rcontrib command line (argv[0] is the program name).
     Option order matters exactly as in rt/rcmain.c:207-320: -f/-e/-p act
@@ -332,12 +360,12 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
     try:
         inform, outform = "a", "a"
         header = True
-        imm_irrad = lim_dist = contrib = False
+        imm_irrad = lim_dist = contrib = force_open = False
         xres = yres = 0
         accumulate = 1
         curout = None
         prms, binval, bincnt = "", None, 0
-        nmods = 0
+        mods = []                   # (name, outspec, col0, nbins)
         i = 1
         while i < len(argv):
             a = argv[i]
@@ -351,6 +379,10 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
             def need(k=1):
                 if i + k >= len(argv):
                     raise RBError(f"command line error at '{a}'")
+
+            def addmod(name):
+                col0 = ctx.add_modifier(name, prms, binval if binval is not None else "0", bincnt)
+                mods.append((name, curout, col0, ctx.num_columns() - col0))
 
             c = a[1]
             if c == "n":
@@ -369,7 +401,7 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
                 imm_irrad = _bool_opt(a, 2, imm_irrad)
             elif c == "f":
                 if a[2:3] == "o":
-                    pass
+                    force_open = _bool_opt(a, 3, force_open)
                 else:
                     inform, outform = _set_format(a[2:], "rcontrib")
             elif c == "o":
@@ -391,24 +423,18 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
                     binval = argv[i + 1]
                 i += 1
             elif c == "m":
-                need()
-                if curout is not None:
-                    raise RBError("unsupported option: -o file output is not built (matrix is returned)")
-                ctx.add_modifier(argv[i + 1], prms, binval if binval is not None else "0", bincnt)
-                nmods += 1
-                i += 1
+                need(); addmod(argv[i + 1]); i += 1
             elif c == "M":
                 need()
                 for name in Path(argv[i + 1]).read_text().split():
-                    ctx.add_modifier(name, prms, binval if binval is not None else "0", bincnt)
-                    nmods += 1
+                    addmod(name)
                 i += 1
             elif c == "t":
                 need(); i += 1
             else:
                 raise RBError(f"command line error at '{a}'")
             i += 1
-        if nmods <= 0:
+        if not mods:
             raise RBError("missing required modifier argument")
         if i != len(argv) - 1:
             raise RBError("missing octree argument" if i >= len(argv) else f"command line error at '{argv[i]}'")
@@ -416,32 +442,69 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
             raise RBError("color (RGBE) output format is not built")
         ctx.load_octree(argv[i])
         rays = _parse_rays(stdin, inform)
-        if accumulate > 0:
-            # zero-direction rays are flush requests that still produce a record
-            pass
         flags = (_lib.RB_IRRAD_RCONTRIB if imm_irrad else 0) | (_lib.RB_FLAG_LIMDIST if lim_dist else 0) | \
                 (_lib.RB_FLAG_CONTRIB if contrib else 0)
         dt = np.float32 if outform == "f" else np.float64
-        mat = ctx.rcontrib(rays, accum=accumulate, flags=flags, dtype=dt)
+        if accumulate > 0:
+            mat = ctx.rcontrib(rays, accum=accumulate, flags=flags, dtype=dt)
+        else:
+            # -c 0: one record holding the SUM over all rays (rc2.c:301-302 sf = 1);
+            # dummy (zero-direction) rays are ignored (rcontrib.c:392-398)
+            live = rays[np.any(rays[:, 3:6] != 0, axis=1)]
+            tot = np.zeros((1, ctx.num_columns(), 3), dtype=np.float64)
+            chunk = 4096
+            for k in range(0, live.shape[0], chunk):
+                part = live[k:k + chunk]
+                tot += ctx.rcontrib(part, accum=part.shape[0], flags=flags, row_base=k, dtype=np.float64) * part.shape[0]
+            mat = tot.astype(dt)
         if return_array:
             return mat
-        ncols = ctx.num_columns()
-        out = bytearray()
-        if header:
-            extra = ""
-            if yres > 0:
-                extra += f"NROWS={yres * (xres if xres else 1)}\n"
-            if xres <= 0 or ncols > 1:
-                extra += f"NCOLS={ncols}\n"
-            out += _header(ctx, ["rcontrib"] + argv[1:-1], 3, outform, extra)
-        if ncols == 1 and xres > 0 and yres > 0:
-            out += f"-Y {yres} +X {xres}\n".encode()
-        if outform == "a":
-            flat = mat.reshape(mat.shape[0], -1)
-            out += ("".join("".join("%.6e\t" % v for v in row) + "\n" for row in flat)).encode()
-        else:
-            out += mat.tobytes()
-        return bytes(out)
+        # ---- output streams (rc2.c:150-254 getostream, :339-356 mod_output) ----
+        streams = {}                # name (None = stdout) -> dict(cols=[...], info=str)
+        for name, ospec, col0, nb in mods:
+            for j in range(nb):
+                if ospec is None:
+                    key, hm, hb = None, False, False
+                else:
+                    key, hm, hb = _ofname(ospec, name, j)
+                st = streams.setdefault(key, {"cols": [], "mod": None, "bin": None})
+                if not st["cols"]:
+                    st["mod"] = name if hm else None
+                    st["bin"] = j if hb else None
+                st["cols"].append(col0 + j)
+        stdout = bytearray()
+        prog_argv = ["rcontrib"] + argv[1:-1]
+        for key, st in streams.items():
+            reclen = len(st["cols"])
+            out = bytearray()
+            if header:
+                extra = ""
+                if key is not None and (st["mod"] is not None or reclen == 1):
+                    extra += f"MODIFIER={st['mod'] if st['mod'] is not None else [m for m in mods if m[2] <= st['cols'][0] < m[2] + m[3]][0][0]}\n"
+                if key is not None and st["bin"] is not None:
+                    extra += f"BIN={st['bin']}\n"
+                if yres > 0:
+                    extra += f"NROWS={yres * (xres if xres else 1)}\n"
+                if xres <= 0 or reclen > 1:
+                    extra += f"NCOLS={reclen}\n"
+                out += _header(ctx, prog_argv, 3, outform, extra)
+            if reclen == 1 and xres > 0 and yres > 0:
+                out += f"-Y {yres} +X {xres}\n".encode()
+            sub = mat[:, st["cols"], :]
+            if outform == "a":
+                flat = sub.reshape(sub.shape[0], -1)
+                out += ("".join("".join("%.6e\t" % v for v in row) + "\n" for row in flat)).encode()
+            else:
+                out += np.ascontiguousarray(sub).tobytes()
+            if key is None:
+                stdout += out
+            elif key.startswith("!"):
+                raise RBError("unsupported output spec: pipes to commands ('!cmd') are not built")
+            else:
+                if Path(key).exists() and not force_open:
+                    raise RBError(f"cannot open '{key}' for writing")       # file exists (rc2.c:197-201)
+                Path(key).write_bytes(bytes(out))
+        return bytes(stdout)
     finally:
         ctx.close()
 

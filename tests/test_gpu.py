@@ -379,3 +379,104 @@ def test_rtrace_simul_manager_like_reference_test(golden):
     assert mgr.enqueue_bundle(rays) == 2
     mgr.flush_queue()
     mgr.cleanup(True)
+
+
+# ---------------------------------------------- more of the rcontrib boundary --
+def test_output_files_and_accumulate_zero(golden, workdir):
+    """-o spec with %s / %d (rc2.c:40-92,150-254), -fo, and -c 0 (sum of all rays)."""
+    import os
+    up = np.load(golden / "bin_dirs.npy")[:50]
+    rays = up.tobytes()
+    cwd = os.getcwd()
+    os.chdir(workdir)
+    try:
+        rc = pr.Rcontrib(rays, golden / "contrib.oct", inform="d", outform="d", params=["-ab", "0"])
+        rc.add_modifier("skyglow", calfile="klems_quarter.cal", nbins="Nkqbins", binv="kqbin(0,0,-1,0,1,0)",
+                        output="q_%s.dat")
+        rc.add_modifier("groundglow", binv="0", output="g_%s_%d.dat")
+        assert rc() == b""                                   # everything went to files
+        q = (workdir / "q_skyglow.dat").read_bytes()
+        head, body = q.split(b"\n\n", 1)
+        assert b"MODIFIER=skyglow" in head and b"NCOLS=41" in head and b"FORMAT=double" in head
+        m = np.frombuffer(body, dtype=np.float64).reshape(50, 41, 3)
+        assert np.all(m.sum(axis=1) == 1.0)
+        gfile = (workdir / "g_groundglow_0.dat").read_bytes()
+        assert b"MODIFIER=groundglow" in gfile and b"BIN=0" in gfile
+        with pytest.raises(RuntimeError, match="cannot open 'q_skyglow.dat' for writing"):
+            rc()                                             # refuses to overwrite ...
+        rc.cmd.insert(1, "-fo")
+        rc()                                                 # ... unless -fo
+    finally:
+        os.chdir(cwd)
+    rc0 = pr.Rcontrib(rays, golden / "contrib.oct", inform="d", outform="d", params=["-ab", "0", "-c", "0", "-h"])
+    rc0.add_modifier("skyglow", calfile="klems_quarter.cal", nbins="Nkqbins", binv="kqbin(0,0,-1,0,1,0)")
+    tot = np.frombuffer(rc0(), dtype=np.float64).reshape(1, 41, 3)
+    np.testing.assert_allclose(tot[0], m.sum(axis=0), rtol=1e-12)
+    if refrun.available():
+        ref = refrun.rcontrib(golden / "contrib.oct", up, ["-ab", "0", "-c", "0", "-f", "klems_quarter.cal", "-bn", "Nkqbins",
+                                                           "-b", "kqbin(0,0,-1,0,1,0)", "-m", "skyglow"]).reshape(1, 41, 3)
+        np.testing.assert_allclose(tot, ref, rtol=1e-12)
+
+
+def test_view_matrix_klems_window_groups(workdir):
+    """BASELINE config 4 in miniature: Klems full bins per window group, 8 glow
+    window modifiers tracked at once, view rays from inside the room; per-group
+    totals against the reference / oracle within Monte-Carlo tolerance."""
+    import io
+    rng = np.random.default_rng(5)
+    out = io.StringIO()
+    out.write(scenegen.MATERIALS)
+    for i in range(8):
+        out.write(f"void glow wg{i}\n0\n0\n4 1 1 1 0\n\n")
+    buf = io.StringIO()
+    scenegen.office_floor(buf, rng, 0.0, 300, tag="f0")
+    txt = buf.getvalue()
+    for i in range(8):
+        txt = txt.replace(f"win_glass polygon f0.win{i}\n", f"wg{i} polygon f0.win{i}\n")
+    out.write(txt)
+    rad, octf = workdir / "view.rad", workdir / "view.oct"
+    rad.write_text(out.getvalue())
+    scenegen.build_octree(rad, octf)
+    rays = scenegen.random_rays(4000, seed=9, lo=(5, 3, 0.9), hi=(35, 12, 2.5))
+    rays[:, 4] = -np.abs(rays[:, 4]) - 0.3                   # look towards the south facade
+    rays[:, 3:6] /= np.linalg.norm(rays[:, 3:6], axis=1, keepdims=True)
+    opts = ["-ab", "2", "-ad", "512", "-lw", "2e-3"]
+    ctx = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+    ctx.load_octree(octf)
+    ctx.set_options(opts)
+    ctx.cal_load("klems_full.cal")
+    s = port.Scene(octf, rcontrib=True, ambounce=2, ambdiv=512, minweight=2e-3, seed=11)
+    args = ["-f", "klems_full.cal", "-p", "RHS=+1", "-bn", "Nkbins", "-b", "kbinS"]
+    for i in range(8):
+        ctx.add_modifier(f"wg{i}", "RHS=+1", "kbinS", int(ctx.cal_eval("Nkbins") + .5))
+        s.add_modifier(f"wg{i}", port.BIN_KLEMS_FULL, 1, (0, 1, 0), (0, 0, 1), 1.0, 145)
+        args += ["-m", f"wg{i}"]
+    assert ctx.num_columns() == 8 * 145
+    g = ctx.rcontrib(rays).astype(np.float64)[:, :, 0].reshape(-1, 8, 145)
+    o = s.rcontrib(rays)[:, :, 0].reshape(-1, 8, 145)
+    # deterministic part: primary rays that see a window directly land coefficient 1 in one bin
+    direct_g = (g == 1.0).sum()
+    assert direct_g > 100 and direct_g == (o == 1.0).sum()
+    assert np.array_equal(np.argwhere(g == 1.0), np.argwhere(o == 1.0))
+    tg, to = g.sum((0, 2)), o.sum((0, 2))
+    assert np.all(np.abs(tg - to) <= 0.03 * to + 0.5)       # per window group, Monte-Carlo part included
+    if refrun.available():
+        r = refrun.rcontrib(octf, rays, opts + args, nproc=4).reshape(-1, 8, 145, 3)[..., 0]
+        assert np.array_equal(np.argwhere(r == 1.0), np.argwhere(g == 1.0))
+        assert np.all(np.abs(tg - r.sum((0, 2))) <= 0.03 * to + 0.5)
+
+
+def test_full_size_properties(office100k):
+    """BASELINE config 2 at full scene size on a slice of the sensors:
+    size-independent properties of a daylight-coefficient matrix."""
+    sens = scenegen.office_sensors(100_000)[::50]            # 2000 of the 100k sensors
+    ctx = rc_ctx(office100k, ["-ab", "3", "-ad", "4096", "-lw", f"{1 / 4096:.4e}"])
+    m = ctx.rcontrib(sens, flags=_lib.RB_IRRAD_RCONTRIB, dtype=np.float64)
+    st = ctx.stats()
+    assert m.shape == (2000, 145, 3) and np.isfinite(m).all() and (m >= 0).all()
+    assert m[..., 0].sum(1).max() <= np.pi * (1 + 1e-9)      # a sensor cannot see more than the whole sky
+    assert m.sum() > 0 and np.array_equal(m[..., 0], m[..., 1])     # grey scene: channels identical
+    assert 1.0e4 < st["nrays"] / 2000 < 1.6e4                 # ~12.6k rays per sensor (SURVEY 3.2: 12 100)
+    # records are independent: a permuted / re-based run of a subset reproduces the same rows
+    sub = ctx.rcontrib(sens[500:600], flags=_lib.RB_IRRAD_RCONTRIB, row_base=500, dtype=np.float64)
+    np.testing.assert_allclose(sub, m[500:600], rtol=1e-12, atol=1e-15)
