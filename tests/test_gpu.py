@@ -475,7 +475,8 @@ def test_full_size_properties(office100k):
     st = ctx.stats()
     assert m.shape == (2000, 145, 3) and np.isfinite(m).all() and (m >= 0).all()
     assert m[..., 0].sum(1).max() <= np.pi * (1 + 1e-9)      # a sensor cannot see more than the whole sky
-    assert m.sum() > 0 and np.array_equal(m[..., 0], m[..., 1])     # grey scene: channels identical
+    # every material of the scene has R >= G >= B, so every coefficient product has too
+    assert m.sum() > 0 and (m[..., 0] >= m[..., 1] - 1e-12).all() and (m[..., 1] >= m[..., 2] - 1e-12).all()
     assert 1.0e4 < st["nrays"] / 2000 < 1.6e4                 # ~12.6k rays per sensor (12 100)
     # records are independent: a permuted / re-based run of a subset reproduces the same rows
     sub = ctx.rcontrib(sens[500:600], flags=_lib.RB_IRRAD_RCONTRIB, row_base=500, dtype=np.float64)
