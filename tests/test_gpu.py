@@ -182,18 +182,21 @@ def test_unobstructed_sensor_sums_to_pi(golden):
 
 
 def _stat_compare(a, b, reps_a, reps_b, what):
-    """|mean_a - mean_b| <= 4 sigma of the difference (sigma from the repeated
-    runs) + 0.3 % of the value, for every row sum."""
+    """|mean_a - mean_b| <= 5 sigma of the difference (sigma estimated from the
+    repeated runs, 16 each, so the estimate itself is good to ~20 %) + 0.3 % of
+    the value, for every row sum.  The reference seeds from time(0), so this
+    test sees different reference samples every run; 5 sigma keeps the
+    false-alarm rate below 1e-4."""
     ma, mb = a.mean(0), b.mean(0)
     sig = np.sqrt(a.var(0, ddof=1) / reps_a + b.var(0, ddof=1) / reps_b)
-    bad = np.abs(ma - mb) > 4 * sig + 3e-3 * np.abs(mb) + 1e-6
+    bad = np.abs(ma - mb) > 5 * sig + 3e-3 * np.abs(mb) + 1e-6
     assert not bad.any(), (what, ma[bad], mb[bad], sig[bad])
 
 
 def test_stochastic_row_sums_vs_oracle_and_reference(golden):
     sens = np.array([[10, 10, 3, 0, 0, 1], [4, 5, 3, 0, 0, 1], [30, 40, 5, 0, 0, 1]], dtype=float)
     opts = ["-ab", "3", "-ad", "2048", "-lw", "1e-4"]
-    reps = 8
+    reps = 16
     gpu, orc, ref = [], [], []
     for k in range(reps):
         ctx = rc_ctx(golden / "contrib.oct", opts)
