@@ -125,6 +125,8 @@ int rb_set_params(rb_ctx* ctx, const rb_params* in);
 int rb_set_option(rb_ctx* ctx, int argc, const char* const* argv);
 
 int rb_load_octree(rb_ctx* ctx, const char* path);
+/* write the loaded (instance-expanded) scene as a frozen octree any Radiance program reads */
+int rb_save_octree(rb_ctx* ctx, const char* path);
 /* scene queries */
 int rb_num_objects(rb_ctx* ctx);
 const char* rb_object_name(rb_ctx* ctx, int obj);

@@ -66,6 +66,7 @@ SYMBOLS = [
     ("rb_set_params", C.c_int, [_P, C.POINTER(rb_params)]),
     ("rb_set_option", C.c_int, [_P, C.c_int, C.POINTER(C.c_char_p)]),
     ("rb_load_octree", C.c_int, [_P, C.c_char_p]),
+    ("rb_save_octree", C.c_int, [_P, C.c_char_p]),
     ("rb_num_objects", C.c_int, [_P]),
     ("rb_object_name", C.c_char_p, [_P, C.c_int]),
     ("rb_object_type", C.c_char_p, [_P, C.c_int]),
@@ -193,6 +194,10 @@ class Context:
         if rv < 0:
             return self.lib.rb_last_error(self.h).decode()
         return None
+
+    def save_octree(self, path):
+        """Write the loaded scene (instances expanded) as a frozen octree."""
+        self._ck(self.lib.rb_save_octree(self.h, os.fspath(path).encode()))
 
     def num_objects(self):
         return self.lib.rb_num_objects(self.h)

@@ -475,6 +475,13 @@ int rb_load_octree(rb_ctx* c, const char* path) {
     return 0;
 }
 
+int rb_save_octree(rb_ctx* c, const char* path) {
+    if (c->scene.objs.empty()) return fail(c, "no octree loaded");
+    std::string err;
+    if (!rb::build_octree_file(c->scene, "rb_save_octree", path, 6, 16384, err)) return fail(c, err);
+    return 0;
+}
+
 int rb_num_objects(rb_ctx* c) { return (int)c->scene.objs.size(); }
 const char* rb_object_name(rb_ctx* c, int i) { return (i >= 0 && i < (int)c->scene.objs.size()) ? c->scene.objs[i].name.c_str() : ""; }
 const char* rb_object_type(rb_ctx* c, int i) { return (i >= 0 && i < (int)c->scene.objs.size()) ? c->scene.objs[i].tname.c_str() : ""; }

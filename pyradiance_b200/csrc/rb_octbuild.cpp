@@ -153,9 +153,11 @@ void puttree(Out& o, const Builder& B, int w) {
 
 }  // namespace
 
-bool build_octree_file(const Scene& sc, const std::string& cmdline, const std::string& oct_path, int objlim,
-                       int maxres, std::string& err) {
-    Builder B;
+// Collect the surfaces of `sc` and build the tree.  With keep_cube the scene's
+// own cube is kept (re-build after instance / mesh expansion), else the cube of
+// ot/oconv.c:122-139 is computed.  Result in B; cube in cuorg/cusize.
+static bool build_tree(const Scene& sc, Builder& B, int objlim, int maxres, bool keep_cube, double cuorg[3],
+                       double& cusize, char sbuf[4][64], int& root, std::string& err) {
     B.objlim = objlim > 0 ? objlim : 6;
     double bbmin[3] = {1e10, 1e10, 1e10}, bbmax[3] = {-1e10, -1e10, -1e10};
     for (int i = 0; i < (int)sc.objs.size(); i++) {
@@ -208,23 +210,69 @@ bool build_octree_file(const Scene& sc, const std::string& cmdline, const std::s
         for (int k = 0; k < 3; k++) { bbmin[k] = std::min(bbmin[k], p.lo[k]); bbmax[k] = std::max(bbmax[k], p.hi[k]); }
         B.prims.push_back(p);
     }
-    // ot/oconv.c:122-139: cube centred on the bounding box, with margin
     const double OMARGIN = 10 * FTINY;
-    double cuorg[3] = {0, 0, 0}, cusize = 0;
-    if (!B.prims.empty()) {
-        for (int k = 0; k < 3; k++) { bbmin[k] -= OMARGIN; bbmax[k] += OMARGIN; }
-        for (int k = 0; k < 3; k++) cusize = std::max(cusize, bbmax[k] - bbmin[k]);
-        for (int k = 0; k < 3; k++) cuorg[k] = (bbmax[k] + bbmin[k] - cusize) * .5;
+    if (keep_cube) {
+        for (int k = 0; k < 3; k++) cuorg[k] = sc.cuorg[k];
+        cusize = sc.cusize;
+        for (int k = 0; k < 3 && !B.prims.empty(); k++)
+            if (bbmin[k] < cuorg[k] - OMARGIN || bbmax[k] > cuorg[k] + cusize + OMARGIN) {
+                err = "boundary does not encompass scene (instance or mesh sticks out of the parent octree's cube)";
+                return false;
+            }
+    } else {
+        // ot/oconv.c:122-139: cube centred on the bounding box, with margin
+        cuorg[0] = cuorg[1] = cuorg[2] = 0; cusize = 0;
+        if (!B.prims.empty()) {
+            for (int k = 0; k < 3; k++) { bbmin[k] -= OMARGIN; bbmax[k] += OMARGIN; }
+            for (int k = 0; k < 3; k++) cusize = std::max(cusize, bbmax[k] - bbmin[k]);
+            for (int k = 0; k < 3; k++) cuorg[k] = (bbmax[k] + bbmin[k] - cusize) * .5;
+        }
+        // the reader parses the "%.12g" strings: build with exactly those values
+        for (int k = 0; k < 3; k++) { snprintf(sbuf[k], 64, "%.12g", cuorg[k]); cuorg[k] = atof(sbuf[k]); }
+        snprintf(sbuf[3], 64, "%.12g", cusize); cusize = atof(sbuf[3]);
     }
-    // the reader parses the "%.12g" strings: build with exactly those values
-    char sbuf[4][64];
-    for (int k = 0; k < 3; k++) { snprintf(sbuf[k], 64, "%.12g", cuorg[k]); cuorg[k] = atof(sbuf[k]); }
-    snprintf(sbuf[3], 64, "%.12g", cusize); cusize = atof(sbuf[3]);
     B.mincusize = cusize / (maxres > 0 ? maxres : 16384) - FTINY;
     std::vector<int> all(B.prims.size());
     for (size_t i = 0; i < all.size(); i++) all[i] = (int)i;
-    int root = B.build(all, cuorg, cusize, 0);
+    root = B.build(all, cuorg, cusize, 0);
     if (!B.err.empty()) { err = B.err; return false; }
+    return true;
+}
+
+// Re-build sc's octree in memory over its current surface list (used after
+// instances / meshes have been expanded into world-space surfaces).
+bool rebuild_octree(Scene& sc, int objlim, int maxres, std::string& err) {
+    Builder B;
+    double cuorg[3], cusize; char sbuf[4][64]; int root;
+    if (!build_tree(sc, B, objlim, maxres, true, cuorg, cusize, sbuf, root, err)) return false;
+    sc.nodes = B.nodes;
+    sc.leafpool.clear();
+    std::vector<int> off(B.sets.size());
+    for (size_t i = 0; i < B.sets.size(); i++) {
+        off[i] = (int)sc.leafpool.size();
+        sc.leafpool.push_back((int)B.sets[i].size());
+        for (int id : B.sets[i]) sc.leafpool.push_back(id);
+    }
+    auto remap = [&](int w) { return w < -1 ? -off[-w - 2] - 2 : w; };
+    for (auto& w : sc.nodes) w = remap(w);
+    sc.root = remap(root);
+    // depth of the new tree
+    sc.maxdepth = 0;
+    std::vector<std::pair<int, int>> st;
+    if (sc.root >= 0) st.push_back({sc.root, 1});
+    while (!st.empty()) {
+        auto [nd, d] = st.back(); st.pop_back();
+        sc.maxdepth = std::max(sc.maxdepth, d);
+        for (int k = 0; k < 8; k++) { int w = sc.nodes[(size_t)nd * 8 + k]; if (w >= 0) st.push_back({w, d + 1}); }
+    }
+    return true;
+}
+
+bool build_octree_file(const Scene& sc, const std::string& cmdline, const std::string& oct_path, int objlim,
+                       int maxres, std::string& err) {
+    Builder B;
+    double cuorg[3], cusize; char sbuf[4][64]; int root;
+    if (!build_tree(sc, B, objlim, maxres, false, cuorg, cusize, sbuf, root, err)) return false;
 
     Out o;
     std::string hdr = "#?RADIANCE\n" + cmdline + "\nFORMAT=Radiance_octree\n\n";
@@ -267,6 +315,12 @@ extern "C" int rb_oconv(const char* rad_path, const char* oct_path, int objlim, 
     std::string err;
     bool ok = sc.read_rad_text(rad_path);
     if (!ok) err = sc.error;
+    for (size_t i = 0; ok && i < sc.objs.size(); i++)
+        if (rb::ot_is_volume(sc.objs[i].otype)) {
+            ok = false;
+            err = "rb_oconv: " + sc.objs[i].tname + " \"" + sc.objs[i].name +
+                  "\" cannot be placed by this builder (use the reference oconv for scenes with instances / meshes)";
+        }
     if (ok) {
         std::string cmd = std::string("rb_oconv -f ") + rad_path;
         ok = rb::build_octree_file(sc, cmd, oct_path, objlim, maxres, err);

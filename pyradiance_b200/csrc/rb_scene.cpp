@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <fstream>
 #include <functional>
+#include <memory>
 #include <sstream>
 
 namespace rb {
@@ -122,6 +123,36 @@ struct Rd {
 }  // namespace
 
 // --------------------------------------------------------------- loader ----
+// sceneio.c:90-109 readscene() + :20-87 getobj(): type-name table then objects
+static bool read_frozen_scene(Rd& rd, int objsize, std::vector<Object>& objs, std::string& err) {
+    std::string s;
+    std::vector<int> tmap; std::vector<std::string> tnames;
+    for (;;) {
+        if (!rd.getstr(s)) { err = "truncated scene"; return false; }
+        if (s.empty()) break;
+        tnames.push_back(s);
+        tmap.push_back(ot_from_name(s));
+    }
+    for (;;) {
+        long ti = rd.getint(1);
+        if (rd.bad) { err = "unexpected EOF in scene"; return false; }
+        if (ti == -1) break;
+        if (ti < 0 || ti >= (long)tmap.size()) { err = "reference to unknown type"; return false; }
+        Object o;
+        o.otype = tmap[ti]; o.tname = tnames[ti];
+        o.omod = (int)rd.getint(objsize);
+        rd.getstr(o.name);
+        long ns = rd.getint(2);
+        for (long i = 0; i < ns; i++) { rd.getstr(s); o.sargs.push_back(s); }
+        long nf = rd.getint(2);
+        o.fargs.resize(nf > 0 ? nf : 0);
+        for (long i = 0; i < nf; i++) o.fargs[i] = rd.getflt();
+        if (rd.bad) { err = "unexpected EOF in scene"; return false; }
+        objs.push_back(std::move(o));
+    }
+    return true;
+}
+
 static int read_tree(Rd& rd, Scene& sc, int objsize, int depth, std::string& err) {
     if (depth > sc.maxdepth) sc.maxdepth = depth;
     int c = rd.getc_();
@@ -206,31 +237,8 @@ bool Scene::load_octree(const std::string& path) {
     if (!terr.empty()) { error = "(" + path + "): " + terr; return false; }
     objs.clear();
     if (frozen) {
-        // sceneio.c:90-109 readscene(): type-name table then objects
-        std::vector<int> tmap; std::vector<std::string> tnames;
-        for (;;) {
-            if (!rd.getstr(s)) { error = "(" + path + "): truncated octree"; return false; }
-            if (s.empty()) break;
-            tnames.push_back(s);
-            tmap.push_back(ot_from_name(s));
-        }
-        for (;;) {  // sceneio.c:20-87 getobj()
-            long ti = rd.getint(1);
-            if (rd.bad) { error = "(" + path + "): unexpected EOF in scene"; return false; }
-            if (ti == -1) break;
-            if (ti < 0 || ti >= (long)tmap.size()) { error = "(" + path + "): reference to unknown type"; return false; }
-            Object o;
-            o.otype = tmap[ti]; o.tname = tnames[ti];
-            o.omod = (int)rd.getint(objsize);
-            rd.getstr(o.name);
-            long ns = rd.getint(2);
-            for (long i = 0; i < ns; i++) { rd.getstr(s); o.sargs.push_back(s); }
-            long nf = rd.getint(2);
-            o.fargs.resize(nf > 0 ? nf : 0);
-            for (long i = 0; i < nf; i++) o.fargs[i] = rd.getflt();
-            if (rd.bad) { error = "(" + path + "): unexpected EOF in scene"; return false; }
-            objs.push_back(std::move(o));
-        }
+        std::string rerr;
+        if (!read_frozen_scene(rd, objsize, objs, rerr)) { error = "(" + path + "): " + rerr; return false; }
         if ((long)objs.size() != nobj) {
             error = "(" + path + "): bad object count in frozen octree"; return false;
         }
@@ -251,6 +259,314 @@ bool Scene::load_octree(const std::string& path) {
         }
     }
     index_modifiers();
+    {
+        std::string dir;
+        size_t sl = path.rfind('/');
+        if (sl != std::string::npos) dir = path.substr(0, sl + 1);
+        if (!expand_volumes(dir)) return false;
+    }
+    return true;
+}
+
+// getpath(fname, getrlibpath(), R_OK) (common/getpath.c): absolute or explicitly
+// relative names as they are, else the RAYPATH directories; as a last resort the
+// directory of the referring octree.
+std::string find_radiance_file(const std::string& name, const std::string& basedir) {
+    auto readable = [](const std::string& p) { std::ifstream f(p); return (bool)f; };
+    if (name.empty()) return "";
+    if (name[0] == '/' || name[0] == '.') return readable(name) ? name : (readable(basedir + name) ? basedir + name : "");
+    const char* rp = getenv("RAYPATH");
+    std::string path = rp ? rp : ".:/usr/local/lib/ray";
+    size_t i = 0;
+    while (i <= path.size()) {
+        size_t j = path.find(':', i);
+        if (j == std::string::npos) j = path.size();
+        std::string d = path.substr(i, j - i);
+        if (d.empty()) d = ".";
+        if (readable(d + "/" + name)) return d + "/" + name;
+        i = j + 1;
+    }
+    if (readable(basedir + name)) return basedir + name;
+    return "";
+}
+
+namespace {
+struct Xf { double m[4][4]; double sca; };
+static void xf_ident(double m[4][4]) { for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) m[i][j] = (i == j); }
+static void xf_mul(double a[4][4], double b[4][4], double c[4][4]) {
+    double t[4][4];
+    for (int i = 4; i--;) for (int j = 4; j--;)
+        t[i][j] = b[i][0] * c[0][j] + b[i][1] * c[1][j] + b[i][2] * c[2][j] + b[i][3] * c[3][j];
+    memcpy(a, t, sizeof(t));
+}
+// common/xf.c:38-139 xf(): -t -rx -ry -rz -s -mx -my -mz -i
+static bool parse_xf(const std::vector<std::string>& av, size_t i0, Xf& ret, std::string& err) {
+    const double D2R = 3.14159265358979323846 / 180.;
+    xf_ident(ret.m); ret.sca = 1.0;
+    double xfmat[4][4], m4[4][4], xfsca = 1.0;
+    int icnt = 1;
+    xf_ident(xfmat);
+    size_t i = i0;
+    auto num = [&](size_t k, double& v) { if (k >= av.size()) return false; char* e; v = strtod(av[k].c_str(), &e); return e != av[k].c_str() && !*e; };
+    for (; i < av.size() && av[i][0] == '-'; i++) {
+        xf_ident(m4);
+        const std::string& a = av[i];
+        double v[3];
+        if (a == "-t") { if (!num(i + 1, v[0]) || !num(i + 2, v[1]) || !num(i + 3, v[2])) break; m4[3][0] = v[0]; m4[3][1] = v[1]; m4[3][2] = v[2]; i += 3; }
+        else if (a == "-rx") { if (!num(i + 1, v[0])) break; double d = D2R * v[0]; m4[1][1] = m4[2][2] = cos(d); m4[2][1] = -(m4[1][2] = sin(d)); i++; }
+        else if (a == "-ry") { if (!num(i + 1, v[0])) break; double d = D2R * v[0]; m4[0][0] = m4[2][2] = cos(d); m4[0][2] = -(m4[2][0] = sin(d)); i++; }
+        else if (a == "-rz") { if (!num(i + 1, v[0])) break; double d = D2R * v[0]; m4[0][0] = m4[1][1] = cos(d); m4[1][0] = -(m4[0][1] = sin(d)); i++; }
+        else if (a == "-s") { if (!num(i + 1, v[0]) || v[0] == 0.0) break; xfsca *= m4[0][0] = m4[1][1] = m4[2][2] = v[0]; i++; }
+        else if (a == "-mx") { xfsca *= m4[0][0] = -1.0; }
+        else if (a == "-my") { xfsca *= m4[1][1] = -1.0; }
+        else if (a == "-mz") { xfsca *= m4[2][2] = -1.0; }
+        else if (a == "-i") {
+            if (!num(i + 1, v[0])) break;
+            while (icnt-- > 0) { xf_mul(ret.m, ret.m, xfmat); ret.sca *= xfsca; }
+            icnt = (int)v[0]; xf_ident(xfmat); xfsca = 1.0; i++;
+            continue;
+        } else break;
+        xf_mul(xfmat, xfmat, m4);
+    }
+    while (icnt-- > 0) { xf_mul(ret.m, ret.m, xfmat); ret.sca *= xfsca; }
+    if (i != av.size()) { err = "bad transform"; return false; }
+    return true;
+}
+static void xf_point(double r[3], const double p[3], const Xf& x) {
+    double t[3];
+    for (int j = 0; j < 3; j++) t[j] = p[0] * x.m[0][j] + p[1] * x.m[1][j] + p[2] * x.m[2][j] + x.m[3][j];
+    r[0] = t[0]; r[1] = t[1]; r[2] = t[2];
+}
+static void xf_vector(double r[3], const double p[3], const Xf& x) {
+    double t[3];
+    for (int j = 0; j < 3; j++) t[j] = p[0] * x.m[0][j] + p[1] * x.m[1][j] + p[2] * x.m[2][j];
+    r[0] = t[0]; r[1] = t[1]; r[2] = t[2];
+}
+}  // namespace
+
+
+namespace {
+// A compiled triangle mesh (.rtm): common/readmesh.c:124-305, common/mesh.h.
+struct MeshFile {
+    std::vector<Object> mats;                 // mesh-local materials (frozen scene)
+    struct Tri { double v[3][3]; int mat; };  // mesh-space vertices, local material index (-1 void)
+    std::vector<Tri> tris;
+    bool has_normals = false;
+};
+
+static bool load_rtm(const std::string& path, MeshFile& mf, std::string& err) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) { err = "cannot open mesh file \"" + path + "\""; return false; }
+    std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    const unsigned char* b = (const unsigned char*)data.data();
+    const unsigned char* e = b + data.size();
+    const unsigned char* p = b;
+    bool gotfmt = false;
+    for (;;) {
+        const unsigned char* nl = (const unsigned char*)memchr(p, '\n', e - p);
+        if (!nl) { err = "(" + path + "): not a mesh"; return false; }
+        std::string line((const char*)p, nl - p);
+        p = nl + 1;
+        if (line.empty()) break;
+        if (line.compare(0, 7, "FORMAT=") == 0) gotfmt = line.find("Radiance_tmesh") != std::string::npos;
+    }
+    if (!gotfmt) { err = "(" + path + "): not a mesh"; return false; }
+    Rd rd{p, e};
+    const int MESHMAGIC = 1 * 8 + 311;
+    int objsize = (int)rd.getint(2) - MESHMAGIC;
+    if (objsize <= 0 || objsize > 8) { err = "(" + path + "): incompatible mesh format"; return false; }
+    double cuorg[3], cusize;
+    std::string s;
+    for (int i = 0; i < 3; i++) { rd.getstr(s); cuorg[i] = atof(s.c_str()); }
+    rd.getstr(s); cusize = atof(s.c_str());
+    for (int i = 0; i < 4; i++) rd.getflt();                       // uv limits
+    Scene dummy; std::string terr;
+    read_tree(rd, dummy, objsize, 0, terr);                         // the mesh's own octree is not needed
+    if (!terr.empty()) { err = "(" + path + "): " + terr; return false; }
+    if (!read_frozen_scene(rd, objsize, mf.mats, err)) { err = "(" + path + "): " + err; return false; }
+    long npatches = rd.getint(4);
+    if (rd.bad || npatches < 0) { err = "(" + path + "): truncated mesh"; return false; }
+    struct Patch { std::vector<uint32_t> xyz; int nverts; };
+    std::vector<Patch> patches(npatches);
+    struct RawTri { long v[3]; int mat; };
+    std::vector<RawTri> raw;
+    for (long pn = 0; pn < npatches; pn++) {                       // readmesh.c:124-230 getpatch()
+        int flags = (int)rd.getint(1);
+        if (!(flags & 1) || (flags & ~7)) { err = "(" + path + "): bad patch flags"; return false; }
+        int nv = (int)rd.getint(2);
+        if (nv <= 0 || nv > 256) { err = "(" + path + "): bad number of patch vertices"; return false; }
+        patches[pn].nverts = nv;
+        patches[pn].xyz.resize((size_t)nv * 3);
+        for (int i = 0; i < nv * 3; i++) patches[pn].xyz[i] = (uint32_t)rd.getint(4);
+        if (flags & 2) { mf.has_normals = true; for (int i = 0; i < nv; i++) rd.getint(4); }
+        if (flags & 4) for (int i = 0; i < nv * 2; i++) rd.getint(4);
+        int nt = (int)rd.getint(2);
+        if (nt < 0 || nt > 512) { err = "(" + path + "): bad number of local triangles"; return false; }
+        size_t t0 = raw.size();
+        for (int i = 0; i < nt; i++) {
+            RawTri t;
+            t.v[0] = pn << 8 | rd.getint(1) & 0xff; t.v[1] = pn << 8 | rd.getint(1) & 0xff; t.v[2] = pn << 8 | rd.getint(1) & 0xff;
+            t.mat = -1;
+            raw.push_back(t);
+        }
+        if (rd.getint(2) > 1) for (int i = 0; i < nt; i++) raw[t0 + i].mat = (short)rd.getint(2);
+        else { int sole = (short)rd.getint(2); for (int i = 0; i < nt; i++) raw[t0 + i].mat = sole; }
+        int nj1 = (int)rd.getint(2);
+        if (nj1 < 0 || nj1 > 256) { err = "(" + path + "): bad number of joiner triangles"; return false; }
+        for (int i = 0; i < nj1; i++) {
+            RawTri t;
+            t.v[0] = rd.getint(4); t.v[1] = pn << 8 | rd.getint(1) & 0xff; t.v[2] = pn << 8 | rd.getint(1) & 0xff;
+            t.mat = (short)rd.getint(2);
+            raw.push_back(t);
+        }
+        int nj2 = (int)rd.getint(2);
+        if (nj2 < 0 || nj2 > 256) { err = "(" + path + "): bad number of double joiner triangles"; return false; }
+        for (int i = 0; i < nj2; i++) {
+            RawTri t;
+            t.v[0] = rd.getint(4); t.v[1] = rd.getint(4); t.v[2] = pn << 8 | rd.getint(1) & 0xff;
+            t.mat = (short)rd.getint(2);
+            raw.push_back(t);
+        }
+        if (rd.bad) { err = "(" + path + "): truncated mesh"; return false; }
+    }
+    // common/mesh.c:233-262 getmeshvert(): cuorg + (q + .5) * cusize / 2^32
+    const double vres = (1. / 4294967296.) * cusize;
+    mf.tris.reserve(raw.size());
+    for (const RawTri& t : raw) {
+        MeshFile::Tri o;
+        o.mat = t.mat;
+        for (int k = 0; k < 3; k++) {
+            long pn = t.v[k] >> 8; int vid = (int)(t.v[k] & 0xff);
+            if (pn < 0 || pn >= npatches || vid >= patches[pn].nverts) { err = "(" + path + "): bad mesh vertex reference"; return false; }
+            for (int i = 0; i < 3; i++) o.v[k][i] = cuorg[i] + (patches[pn].xyz[(size_t)vid * 3 + i] + .5) * vres;
+        }
+        mf.tris.push_back(o);
+    }
+    return true;
+}
+}  // namespace
+
+// Instances (rt/o_instance.c:16-71, common/instance.c:24-101) are FLATTENED at
+// load: every surface of the instanced octree becomes a world-space copy in the
+// parent's object table (named and modified as the reference would report the
+// hit: the instance's own name/modifier when it has a modifier, else the inner
+// surface's), and the parent's octree is re-built over the flat list.  The walk
+// then needs no nested traversal.  Differences: distances are computed on
+// transformed geometry instead of a transformed ray (last-bit differences), and
+// coincident inner/outer surfaces are arbitrated by rayreject() instead of
+// "first found wins".
+bool Scene::expand_volumes(const std::string& basedir, int depth) {
+    const size_t n0 = objs.size();
+    bool any = false;
+    for (size_t i = 0; i < n0; i++) if (ot_is_volume(objs[i].otype)) any = true;
+    if (!any) return true;
+    if (depth > 8) { error = "instances nested too deeply"; return false; }
+    struct Nested { std::shared_ptr<Scene> sc; std::vector<int> remap; };
+    struct MeshNested { std::shared_ptr<MeshFile> mf; std::vector<int> remap; };
+    std::unordered_map<std::string, MeshNested> meshes;
+    std::unordered_map<std::string, Nested> cache;
+    for (size_t i = 0; i < n0; i++) {
+        if (objs[i].otype == OT_MESH) {
+            // rt/o_mesh.c:146-217: triangles become world-space polygons; a hit reports the
+            // pseudo object "M-Tri" with the mesh-local material, or the mesh object itself
+            // when it has its own modifier (or the triangle has none)
+            const Object msh = objs[i];
+            if (msh.sargs.empty()) { error = "bad # of arguments for mesh \"" + msh.name + "\""; return false; }
+            Xf x; std::string xe;
+            if (!parse_xf(msh.sargs, 1, x, xe)) { error = xe + " for mesh \"" + msh.name + "\""; return false; }
+            auto mit = meshes.find(msh.sargs[0]);
+            if (mit == meshes.end()) {
+                std::string path = find_radiance_file(msh.sargs[0], basedir);
+                if (path.empty()) { error = "cannot find mesh file \"" + msh.sargs[0] + "\""; return false; }
+                MeshNested mn;
+                mn.mf = std::make_shared<MeshFile>();
+                if (!load_rtm(path, *mn.mf, error)) return false;
+                if (mn.mf->has_normals) {
+                    error = "unsupported mesh \"" + msh.sargs[0] + "\": vertex normals (smooth shading) are not built";
+                    return false;
+                }
+                mn.remap.assign(mn.mf->mats.size(), -1);
+                for (size_t j = 0; j < mn.mf->mats.size(); j++) {
+                    Object c = mn.mf->mats[j];
+                    c.omod = c.omod >= 0 ? mn.remap[c.omod] : -1;
+                    mn.remap[j] = (int)objs.size();
+                    objs.push_back(std::move(c));
+                }
+                mit = meshes.emplace(msh.sargs[0], std::move(mn)).first;
+            }
+            const MeshFile& mf = *mit->second.mf;
+            const bool mirrored = x.sca < 0;
+            for (const auto& t : mf.tris) {
+                Object c;
+                c.otype = OT_POLYGON; c.tname = "polygon";
+                if (msh.omod < 0 && t.mat >= 0 && t.mat < (int)mit->second.remap.size()) { c.name = "M-Tri"; c.omod = mit->second.remap[t.mat]; }
+                else { c.name = msh.name; c.omod = msh.omod; }
+                c.fargs.resize(9);
+                for (int k = 0; k < 3; k++) xf_point(&c.fargs[3 * (mirrored ? 2 - k : k)], t.v[k], x);
+                objs.push_back(std::move(c));
+            }
+            objs[i].expanded = true;
+            nexpanded++;
+            continue;
+        }
+        if (objs[i].otype != OT_INSTANCE) continue;
+        const Object inst = objs[i];           // copy: objs grows below
+        if (inst.sargs.empty()) { error = "bad # of arguments for instance \"" + inst.name + "\""; return false; }
+        Xf x;
+        std::string xe;
+        if (!parse_xf(inst.sargs, 1, x, xe)) { error = xe + " for instance \"" + inst.name + "\""; return false; }
+        const bool mirrored = x.sca < 0;
+        const double sca = fabs(x.sca);
+        auto it = cache.find(inst.sargs[0]);
+        if (it == cache.end()) {
+            std::string path = find_radiance_file(inst.sargs[0], basedir);
+            if (path.empty()) { error = "cannot find octree file \"" + inst.sargs[0] + "\""; return false; }
+            Nested nn;
+            nn.sc = std::make_shared<Scene>();
+            if (!nn.sc->load_octree(path)) { error = nn.sc->error; return false; }
+            // the nested scene's modifiers join our object table once per file
+            nn.remap.assign(nn.sc->objs.size(), -1);
+            for (size_t j = 0; j < nn.sc->objs.size(); j++) {
+                const Object& o = nn.sc->objs[j];
+                if (o.expanded || !ot_is_modifier(o.otype)) continue;
+                Object c = o;
+                c.omod = o.omod >= 0 ? nn.remap[o.omod] : -1;
+                nn.remap[j] = (int)objs.size();
+                objs.push_back(std::move(c));
+            }
+            it = cache.emplace(inst.sargs[0], std::move(nn)).first;
+        }
+        const Scene& ns = *it->second.sc;
+        const std::vector<int>& remap = it->second.remap;
+        for (size_t j = 0; j < ns.objs.size(); j++) {
+            const Object& o = ns.objs[j];
+            if (o.expanded) continue;
+            if (!ot_is_surface(o.otype) || o.otype == OT_SOURCE) continue;
+            Object c = o;
+            if (inst.omod >= 0) { c.name = inst.name; c.omod = inst.omod; }      // o_instance.c:41-43
+            else c.omod = o.omod >= 0 ? remap[o.omod] : -1;
+            std::vector<double>& a = c.fargs;
+            if (o.otype == OT_POLYGON) {
+                int nv = (int)a.size() / 3;
+                for (int v = 0; v < nv; v++) xf_point(&a[3 * v], &a[3 * v], x);
+                if (mirrored)                       // keep the normal = M n (xform reverses vertex order too)
+                    for (int v = 0; v < nv / 2; v++)
+                        for (int k = 0; k < 3; k++) std::swap(a[3 * v + k], a[3 * (nv - 1 - v) + k]);
+            } else if (o.otype == OT_SPHERE || o.otype == OT_BUBBLE) {
+                if (a.size() == 4) { xf_point(&a[0], &a[0], x); a[3] *= sca; }
+            } else if (o.otype == OT_RING) {
+                if (a.size() == 8) { xf_point(&a[0], &a[0], x); xf_vector(&a[3], &a[3], x); a[6] *= sca; a[7] *= sca; }
+            } else {
+                if (a.size() >= 7) { xf_point(&a[0], &a[0], x); xf_point(&a[3], &a[3], x); a[6] *= sca; if (a.size() == 8) a[7] *= sca; }
+            }
+            objs.push_back(std::move(c));
+        }
+        objs[i].expanded = true;
+        nexpanded++;
+    }
+    index_modifiers();
+    std::string err;
+    if (!rebuild_octree(*this, 6, 16384, err)) { error = err; return false; }
     return true;
 }
 
@@ -649,6 +965,7 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
         const Object& o = sc.objs[i];
         int32_t* hdr = &fs.objhdr[(size_t)i * 4];
         hdr[0] = PK_NONE; hdr[1] = o.omod; hdr[2] = -1; hdr[3] = 0;
+        if (ot_is_volume(o.otype) && o.expanded) continue;
         if (ot_is_volume(o.otype)) {
             hdr[0] = PK_UNSUPPORTED;
             hdr[3] = (int32_t)geom_alloc(fs, 0);

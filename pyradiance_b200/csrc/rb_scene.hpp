@@ -47,6 +47,7 @@ struct Object {
     std::string name;
     std::vector<std::string> sargs;
     std::vector<double> fargs;
+    bool expanded = false;      // instance / mesh replaced by world-space surfaces at load
 };
 
 struct Scene {
@@ -72,6 +73,10 @@ struct Scene {
     std::unordered_map<std::string, int> modtab;   // name -> last modifier idx
     void index_modifiers();
     bool read_rad_text(const std::string& path);
+    // replace instances (and meshes) by transformed copies of their surfaces and
+    // re-build the octree over the flat surface list
+    bool expand_volumes(const std::string& basedir, int depth = 0);
+    int nexpanded = 0;
 };
 
 // ---- flattened (device-ready) tables -------------------------------------
@@ -130,5 +135,9 @@ struct FlatScene {
 };
 
 bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err);
+bool rebuild_octree(Scene& sc, int objlim, int maxres, std::string& err);
+bool build_octree_file(const Scene& sc, const std::string& cmdline, const std::string& oct_path, int objlim,
+                       int maxres, std::string& err);
+std::string find_radiance_file(const std::string& name, const std::string& basedir);
 
 }  // namespace rb

@@ -65,6 +65,32 @@ def main():
         m = m.reshape(3000, -1, 3)
         bins = np.where(m[:, :, 0].sum(axis=1) > 0, m[:, :, 0].argmax(axis=1), -1)
         g["bins_" + name] = {"args": args, "ncols": int(m.shape[1]), "bins": bins.astype(int).tolist()}
+    # instances and meshes: fixtures built by the reference oconv / obj2mesh from
+    # the small text scenes in tests/golden/volumes/, known answers by the reference rtrace
+    import os
+    import subprocess
+    V = HERE / "volumes"
+    env = dict(os.environ, RAYPATH=f".:{refrun.LIB}")
+    def sh(cmd, out=None):
+        r = subprocess.run(cmd, cwd=V, env=env, capture_output=True)
+        assert r.returncode == 0, r.stderr
+        if out:
+            (V / out).write_bytes(r.stdout)
+    sh([str(refrun.BIN / "oconv"), "-f", "louvre.rad"], "louvre.oct")
+    sh([str(refrun.BIN / "obj2mesh"), "-a", "meshmats.rad", "bump.obj", "bump.rtm"])
+    sh([str(refrun.BIN / "oconv"), "-f", "room.rad"], "room.oct")
+    sh([str(refrun.BIN / "oconv"), "-f", "meshroom.rad"], "meshroom.oct")
+    rng = np.random.default_rng(6)
+    o = rng.uniform((-4.5, -4.5, -0.9), (4.5, 4.5, 3.5), size=(4000, 3))
+    d = rng.normal(size=(4000, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    vr = np.concatenate([o, d], axis=1)
+    np.save(HERE / "volume_rays.npy", vr)
+    for name in ("room", "meshroom"):
+        r = subprocess.run([str(refrun.BIN / "rtrace"), "-h", "-fda", "-ab", "0", "-osmLN", f"{name}.oct"], cwd=V, env=env,
+                           input=vr.tobytes(), capture_output=True)
+        assert r.returncode == 0, r.stderr
+        g["volumes_" + name] = r.stdout.decode()
     (HERE / "golden.json").write_text(json.dumps(g, indent=0))
     print("wrote", HERE / "golden.json")
 

@@ -484,3 +484,28 @@ def test_full_size_properties(office100k):
     # records are independent: a permuted / re-based run of a subset reproduces the same rows
     sub = ctx.rcontrib(sens[500:600], flags=_lib.RB_IRRAD_RCONTRIB, row_base=500, dtype=np.float64)
     np.testing.assert_allclose(sub, m[500:600], rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", ["room", "meshroom"])
+def test_instances_and_meshes_vs_reference_golden(G, golden, name):
+    """Config-5 ingredients: octree instances and triangle meshes, against the
+    reference rtrace's answers for the same rays (tests/golden/make_golden.py)."""
+    ctx = _lib.Context(0)
+    ctx.load_octree(golden / "volumes" / f"{name}.oct")
+    ctx.set_options(["-ab", "0"])
+    rays = np.load(golden / "volume_rays.npy")
+    _, res = ctx.rtrace(rays, want_values=False)
+    s, m = names(ctx, res["robj"]), names(ctx, res["omod"])
+    for i, line in enumerate(G["volumes_" + name].splitlines()):
+        f = line.split("\t")
+        assert (s[i], m[i] if res["robj"][i] >= 0 else "*") == (f[0], f[1]), (i, f)
+        if f[0] != "*":
+            assert res["rot"][i] == pytest.approx(float(f[2]), rel=2e-6)
+            np.testing.assert_allclose(res["ron"][i], [float(x) for x in f[3:6]], atol=2e-5)
+    # and a daylight-coefficient run over it works end to end
+    rc = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+    rc.load_octree(golden / "volumes" / f"{name}.oct")
+    rc.set_options(["-ab", "1", "-ad", "256", "-lw", "1e-3"])
+    rc.add_modifier("wall", "", "0", 1)
+    m1 = rc.rcontrib(np.array([[0, 0, 3.0, 0, 0, -1.0]]))
+    assert m1.shape == (1, 1, 3) and m1[0, 0, 0] > 0

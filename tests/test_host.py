@@ -220,3 +220,39 @@ def test_row_gather_world_size_2_gloo(root, workdir):
     outs = [p.communicate(timeout=180) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert b"GATHER_OK" in outs[0][0]
+
+
+@pytest.mark.parametrize("name", ["room", "meshroom"])
+def test_instances_and_meshes_flatten_like_reference(G, golden, workdir, name):
+    """instances (nested, mirrored, scaled, with modifier override)
+    and meshes are expanded into world-space surfaces at load.  The expanded
+    scene, saved as a frozen octree and traced by the CPU oracle, must report
+    the surfaces / modifiers / normals the reference reported for the original
+    scene with real instances (golden vectors by the reference rtrace)."""
+    c = _lib.Context(0)
+    err = c.parse_octree(golden / "volumes" / f"{name}.oct")
+    assert err is None or "no CUDA device" in err
+    flat = workdir / f"{name}_flat.oct"
+    c.save_octree(flat)
+    rays = np.load(golden / "volume_rays.npy")
+    s = port.Scene(flat)
+    r = s.rtrace(rays)
+    ref = G["volumes_" + name].splitlines()
+    assert len(ref) == len(rays)
+    seen = set()
+    for i, line in enumerate(ref):
+        f = line.split("\t")
+        assert (s.name(r["robj"][i]), s.name(r["omod"][i]) if r["robj"][i] >= 0 else "*") == (f[0], f[1]), (i, f)
+        seen.add(f[0])
+        if f[0] != "*":
+            assert r["rot"][i] == pytest.approx(float(f[2]), rel=2e-6)
+            np.testing.assert_allclose(r["ron"][i], [float(x) for x in f[3:6]], atol=2e-5)
+    assert ({"slat1", "lv_c", "post"} <= seen) if name == "room" else ({"M-Tri", "bump_c", "slat1"} <= seen)
+
+
+def test_volume_rejections(workdir):
+    (workdir / "noinst.rad").write_text("void instance gone\n1 no_such_file.oct\n0\n0\n")
+    c = _lib.Context(0)
+    # our own builder refuses volumes; the loader reports a missing nested octree by name
+    with pytest.raises(_lib.RBError):
+        scenegen.build_octree(workdir / "noinst.rad", workdir / "noinst.oct")
