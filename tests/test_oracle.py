@@ -90,20 +90,23 @@ def test_oracle_hits_equal_reference(office2k):
 @pytest.mark.skipif(not refrun.available(), reason="oracle/_ref not built")
 def test_oracle_stochastic_agrees_with_reference(golden):
     """Row sums of a -ab 2 coefficient matrix: oracle vs reference, both Monte
-    Carlo (the reference seeds from time(0): different samples every run).
-    Tolerance: 6 sigma of the difference of the means, sigma estimated from 12
-    repetitions each, plus 0.5 % -- false-alarm rate far below 1e-5."""
+    Carlo.  The reference seeds from time(0), so separate runs inside one second
+    repeat the same sample; instead ONE reference run carries 16 copies of each
+    sensor (consecutive records continue the random sequence -> independent).
+    Tolerance: 6 sigma of the difference of the means, sigma estimated from the
+    16 repetitions of each arm, plus 0.5 % -- false-alarm rate far below 1e-5."""
     sens = np.array([[10, 10, 3, 0, 0, 1], [4, 5, 3, 0, 0, 1], [20, 20, 12, 0, 0, 1]], dtype=float)
     args = ["-I", "-ab", "2", "-ad", "2048", "-lw", "1e-4", "-f", "reinhartb.cal", "-p",
             "MF=1,rNx=0,rNy=0,rNz=-1,Ux=0,Uy=1,Uz=0,RHS=+1", "-bn", "Nrbins", "-b", "rbin", "-m", "skyglow"]
-    refs, mine = [], []
-    reps = 12
+    reps = 16
+    refs = refrun.rcontrib(golden / "contrib.oct", np.tile(sens, (reps, 1)), args)
+    refs = refs.reshape(reps, 3, -1, 3)[:, :, :, 0].sum(2)
+    mine = []
     for k in range(reps):
-        refs.append(refrun.rcontrib(golden / "contrib.oct", sens, args).reshape(3, -1, 3)[:, :, 0].sum(1))
         s = port.Scene(golden / "contrib.oct", rcontrib=True, ambounce=2, ambdiv=2048, minweight=1e-4, seed=100 + k)
         s.add_modifier("skyglow", port.BIN_REINHARTB, 1, (0, 0, -1), (0, 1, 0), 1.0, 145)
         mine.append(s.rcontrib(sens, irrad=2)[:, :, 0].sum(1))
-    refs, mine = np.array(refs), np.array(mine)
+    mine = np.array(mine)
     sig = np.sqrt(refs.var(0, ddof=1) / reps + mine.var(0, ddof=1) / reps) + 1e-6
     assert np.all(np.abs(refs.mean(0) - mine.mean(0)) < 6 * sig + 5e-3 * refs.mean(0))
     assert mine[:, 2] == pytest.approx(np.pi, rel=1e-6)        # unobstructed sensor sums to pi
