@@ -173,6 +173,33 @@ def office_floor(out, rng, z0, nboxes, tag="f0", W=40.0, D=25.0, H=3.0, nwin=8,
     return n
 
 
+
+_TNAZ = (30, 30, 24, 24, 18, 12, 6)
+
+
+def reinhart_suns(mf=1):
+    """Unit vectors to the centres of the Reinhart MF:n sky patches in the bin
+    order of reinhart.cal's rbin (sky bins 1..144*mf*mf+1; bin 0 is the ground):
+    the sun positions of a 5-phase direct-sun matrix (BASELINE config 5)."""
+    alpha = 90.0 / (7 * mf + 0.5)
+    dirs = []
+    for row in range(7 * mf):
+        n = mf * _TNAZ[row // mf]
+        alt = np.radians((row + 0.5) * alpha)
+        for k in range(n):
+            azi = np.radians(k * 360.0 / n)
+            dirs.append((np.sin(azi) * np.cos(alt), np.cos(azi) * np.cos(alt), np.sin(alt)))
+    dirs.append((0.0, 0.0, 1.0))
+    return np.array(dirs)
+
+
+def write_suns(out, mf=1, modifier="solar", radiance=1e6, angle=0.533):
+    """`light` material + one `source` per Reinhart patch centre, all sharing one
+    modifier (the form rcontrib's sun-coefficient runs use)."""
+    out.write(f"void light {modifier}\n0\n0\n3 {radiance:g} {radiance:g} {radiance:g}\n\n")
+    for i, d in enumerate(reinhart_suns(mf)):
+        out.write(f"{modifier} source sun{i}\n0\n0\n4 {d[0]:.8f} {d[1]:.8f} {d[2]:.8f} {angle:g}\n\n")
+
 def write_office(path, npolys=100_000, floors=1, seed=1234, sun=False):
     """Write the S-office (floors=1) / S-building (floors=10) scene; returns
     the surface count."""

@@ -91,6 +91,25 @@ def main():
                            input=vr.tobytes(), capture_output=True)
         assert r.returncode == 0, r.stderr
         g["volumes_" + name] = r.stdout.decode()
+    # 5-phase direct-sun matrix in miniature (BASELINE config 5): 145 `light` suns at the Reinhart MF:1
+    # patch centres sharing modifier `solar`, louvre instances + meshes shading a floor of sensors
+    import io
+    from pyradiance_b200 import scenegen
+    buf = io.StringIO()
+    buf.write((V / "sunroom_base.rad").read_text())
+    scenegen.write_suns(buf, mf=1)
+    (V / "sunroom.rad").write_text(buf.getvalue())
+    sh([str(refrun.BIN / "oconv"), "-f", "sunroom.rad"], "sunroom.oct")
+    sx, sy = np.meshgrid(np.linspace(-4, 4, 8), np.linspace(-4, 4, 6))
+    ss = np.stack([sx.ravel(), sy.ravel(), np.full(48, 0.01), np.zeros(48), np.zeros(48), np.ones(48)], axis=1)
+    np.save(HERE / "sunroom_sensors.npy", ss)
+    sun_args = ["-I+", "-ab", "0", "-dc", "1", "-dt", "0", "-dj", "0", "-e", "MF:1", "-f", "reinhart.cal",
+                "-b", "rbin", "-bn", "Nrbins", "-m", "solar"]
+    r = subprocess.run([str(refrun.BIN / "rcontrib"), "-h", "-fdd"] + sun_args + ["sunroom.oct"], cwd=V, env=env,
+                       input=ss.tobytes(), capture_output=True)
+    assert r.returncode == 0, r.stderr
+    np.save(HERE / "sunroom_ab0.npy", np.frombuffer(r.stdout, dtype=np.float64).reshape(48, 146, 3))
+    g["sunroom_args"] = sun_args
     (HERE / "golden.json").write_text(json.dumps(g, indent=0))
     print("wrote", HERE / "golden.json")
 

@@ -250,6 +250,26 @@ def test_instances_and_meshes_flatten_like_reference(G, golden, workdir, name):
     assert ({"slat1", "lv_c", "post"} <= seen) if name == "room" else ({"M-Tri", "bump_c", "slat1"} <= seen)
 
 
+def test_sun_matrix_flattened_scene_oracle_vs_reference_golden(golden, workdir):
+    """BASELINE config 5 in miniature: 145 `light` suns (one modifier, reinhart.cal
+    rbin, -e MF:1) over louvre instances, meshes and a glass skylight.  The
+    loader's flattened scene, traced by the CPU oracle, reproduces the
+    reference rcontrib's deterministic -ab 0 sun coefficients (golden)."""
+    c = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+    err = c.parse_octree(golden / "volumes" / "sunroom.oct")
+    assert err is None or "no CUDA device" in err
+    flat = workdir / "sunroom_flat.oct"
+    c.save_octree(flat)
+    sens = np.load(golden / "sunroom_sensors.npy")
+    ref = np.load(golden / "sunroom_ab0.npy")
+    s = port.Scene(flat, rcontrib=True, ambounce=0, dstrsrc=0.0)
+    s.add_modifier("solar", port.BIN_REINHART, 1, (0, 0, -1), (0, 1, 0), 1.0, 146)
+    m = s.rcontrib(sens, irrad=2)
+    assert np.array_equal(m != 0, ref != 0)
+    np.testing.assert_allclose(m, ref, rtol=1e-5, atol=0)
+    assert (ref[:, 0] == 0).all() and 1000 < (ref[:, :, 0] > 0).sum() < 48 * 145   # shaded and lit both present
+
+
 def test_volume_rejections(workdir):
     (workdir / "noinst.rad").write_text("void instance gone\n1 no_such_file.oct\n0\n0\n")
     c = _lib.Context(0)
