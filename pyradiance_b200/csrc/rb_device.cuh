@@ -129,6 +129,7 @@ struct DCounters {
     unsigned errobj;               // offending object
     unsigned badbin;               // bin >= nbins warnings
     unsigned next_ray;             // k_trace's persistent-thread fetch counter
+    unsigned nd_out;               // parked direct() jobs (keep right after next_ray: reset together)
 };
 enum : unsigned { RB_ERR_UNSUP_MAT = 1, RB_ERR_UNSUP_PRIM = 2, RB_ERR_UNSUP_MOD = 4,
                   RB_ERR_LOCAL_SRC = 8, RB_ERR_DEPTH = 16 };

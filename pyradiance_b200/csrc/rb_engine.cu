@@ -76,33 +76,33 @@ __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const Wave
 #endif
 __global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(const WaveArgs A) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.nin) return;
-    const QRay q = A.qin[i];
-    const HitRec hr = A.hits[i];
-    RayCtx r;
-    for (int k = 0; k < 3; k++) { r.org[k] = q.org[k]; r.dir[k] = q.dir[k]; r.coef[k] = q.coef[k]; }
-    r.rmax = q.rmax; r.rweight = q.rweight; r.row = q.row;
-    r.crtype = q.info & 0x3ff; r.rlvl = (q.info >> 10) & 0x3f; r.rdepth = (q.info >> 16) & 0x3f;
-    r.rsrc = q.rsrc;
-    r.key = ((unsigned long long)q.key_hi << 32) | q.key_lo;
-    r.nchild = 0;
-    r.robj = hr.robj; r.rot = hr.rot; r.rod = hr.rod; r.flat = false;
-    if (hr.local) {
-        hit_frame(A.S, hr.robj, hr.rot, r.org, r.dir, r.rop, r.ron, r.rod);
-        int kind = __ldg(&A.S.objhdr[hr.robj]).x & 0xff;
-        r.flat = (kind == PK_FACE) | (kind == PK_RING);
-    } else {
-        for (int k = 0; k < 3; k++) { r.rop[k] = r.org[k]; r.ron[k] = -r.dir[k]; }
+    if (i < A.nin) {
+        const QRay q = A.qin[i];
+        const HitRec hr = A.hits[i];
+        RayCtx r;
+        for (int k = 0; k < 3; k++) { r.org[k] = q.org[k]; r.dir[k] = q.dir[k]; r.coef[k] = q.coef[k]; }
+        r.rmax = q.rmax; r.rweight = q.rweight; r.row = q.row;
+        r.crtype = q.info & 0x3ff; r.rlvl = (q.info >> 10) & 0x3f; r.rdepth = (q.info >> 16) & 0x3f;
+        r.rsrc = q.rsrc;
+        r.key = ((unsigned long long)q.key_hi << 32) | q.key_lo;
+        r.nchild = 0;
+        r.robj = hr.robj; r.rot = hr.rot; r.rod = hr.rod; r.flat = false;
+        if (hr.local) {
+            hit_frame(A.S, hr.robj, hr.rot, r.org, r.dir, r.rop, r.ron, r.rod);
+            int kind = __ldg(&A.S.objhdr[hr.robj]).x & 0xff;
+            r.flat = (kind == PK_FACE) | (kind == PK_RING);
+        } else {
+            for (int k = 0; k < 3; k++) { r.rop[k] = r.org[k]; r.ron[k] = -r.dir[k]; }
+        }
+        if (A.res && r.crtype == RT_PRIMARY) {
+            RayResult& o = A.res[r.row - A.row0];
+            for (int k = 0; k < 3; k++) { o.rop[k] = r.rop[k]; o.ron[k] = r.ron[k]; }
+            o.rot = r.rot; o.rod = r.rod; o.robj = r.robj;
+            o.omod = r.robj >= 0 ? __ldg(&A.S.objhdr[r.robj]).y : -1;
+            o.rweight = r.rweight; o.pad = 0;
+        }
+        if (r.robj >= 0) shade_ray(A, r);
     }
-    if (A.res && r.crtype == RT_PRIMARY) {
-        RayResult& o = A.res[r.row - A.row0];
-        for (int k = 0; k < 3; k++) { o.rop[k] = r.rop[k]; o.ron[k] = r.ron[k]; }
-        o.rot = r.rot; o.rod = r.rod; o.robj = r.robj;
-        o.omod = r.robj >= 0 ? __ldg(&A.S.objhdr[r.robj]).y : -1;
-        o.rweight = r.rweight; o.pad = 0;
-    }
-    if (r.robj < 0) return;
-    shade_ray(A, r);
 }
 
 struct InitArgs {
@@ -114,9 +114,7 @@ struct InitArgs {
     int lim_dist;
 };
 
-__global__ void __launch_bounds__(WAVE_THREADS) k_init(const WaveArgs A, const InitArgs I) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= I.nrays) return;
+__device__ void init_ray(const WaveArgs& A, const InitArgs& I, unsigned i) {
     const double* v = I.rays + (size_t)i * 6;
     double org[3] = {v[0], v[1], v[2]}, dir[3] = {v[3], v[4], v[5]};
     unsigned row = I.accum > 0 ? (unsigned)((I.ray0 + i) / I.accum - I.ray0 / I.accum) + A.row0 : A.row0;
@@ -165,6 +163,34 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_init(const WaveArgs A, const I
     }
     const float lamb[5] = {(float)RB_PI, (float)RB_PI, (float)RB_PI, 0.f, 0.f};
     m_normal(A, r, MK_PLASTIC, lamb);
+}
+
+__global__ void __launch_bounds__(WAVE_THREADS) k_init(const WaveArgs A, const InitArgs I) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < I.nrays) init_ray(A, I, i);
+}
+
+// direct() for scenes with many sources: one CTA per parked shading point, one
+// source per thread and pass (source.c:398-556 with every source tested).
+struct DirectArgs {
+    const DirectJob* din;
+    unsigned nd;
+};
+
+__global__ void __launch_bounds__(256) k_direct(const WaveArgs A, const DirectArgs D) {
+    __shared__ DirectJob sj;
+    const int ns = A.S.nsrcs;
+    for (unsigned job = blockIdx.x; job < D.nd; job += gridDim.x) {
+        __syncthreads();
+        {   // cooperative copy of the job record
+            const unsigned* src = reinterpret_cast<const unsigned*>(D.din + job);
+            unsigned* dst = reinterpret_cast<unsigned*>(&sj);
+            for (unsigned w = threadIdx.x; w < sizeof(DirectJob) / 4; w += blockDim.x) dst[w] = src[w];
+        }
+        __syncthreads();
+        const unsigned base = sj.r.nchild;
+        for (int sn = threadIdx.x; sn < ns; sn += blockDim.x) direct_one(A, sj.r, sj.nd, sn, base);
+    }
 }
 
 struct ExpandArgs {
@@ -224,7 +250,7 @@ Engine::~Engine() {
     cudaSetDevice(dev_);
     cudaDeviceSynchronize();
     void* ptrs[] = {d_nodes_, d_leaf_, d_hdr_, d_geom_, d_mats_, d_srcs_, d_otrack_, d_bins_, q_[0], q_[1],
-                    h_[0], h_[1], d_hits_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_};
+                    h_[0], h_[1], d_hits_, dq_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_cnt_) cudaFreeHost(h_cnt_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -259,6 +285,8 @@ bool Engine::upload_scene(const FlatScene& fs, const Scene& sc, std::string& err
     for (int k = 0; k < 3; k++) S_.cuorg[k] = sc.cuorg[k];
     S_.cusize = sc.cusize;
     S_.root = fs.root; S_.nobjs = (int)sc.objs.size(); S_.nsrcs = (int)fs.srcs.size();
+    nsrc_active_ = 0;
+    for (const SrcRec& sr : fs.srcs) nsrc_active_ += ((sr.flags & SF_DISTANT) && !(sr.flags & SF_SKIP)) ? 1 : 0;
     S_.maxdepth = sc.maxdepth;
     S_.nodes = (const int*)d_nodes_; S_.leafpool = (const int*)d_leaf_;
     S_.objhdr = (const int4*)d_hdr_; S_.geom = (const double*)d_geom_;
@@ -290,6 +318,9 @@ bool Engine::set_bins(const std::vector<DBinSpec>& bins, const std::vector<int>&
 }
 
 bool Engine::ensure_queues(std::string& err) {
+    if (nsrc_active_ >= RB_COOP_SRC_MIN && !dq_ && q_[0]) {   // a many-source scene loaded after the queues were made
+        CK(cudaMalloc(&dq_, dcap_ * sizeof(DirectJob)));
+    }
     if (q_[0]) return true;
     size_t freeb = 0, totalb = 0;
     CK(cudaMemGetInfo(&freeb, &totalb));
@@ -304,6 +335,10 @@ bool Engine::ensure_queues(std::string& err) {
     CK(cudaMalloc(&h_[0], hcap_ * sizeof(QHemi)));
     CK(cudaMalloc(&h_[1], hcap_ * sizeof(QHemi)));
     CK(cudaMalloc(&d_hits_, qcap_ * sizeof(HitRec)));
+    dcap_ = std::max<size_t>(qcap_ / 32, 4096);
+    if (nsrc_active_ >= RB_COOP_SRC_MIN) {      // many sources: direct() runs as its own kernel from a job queue
+        CK(cudaMalloc(&dq_, dcap_ * sizeof(DirectJob)));
+    }
     {   // persistent k_trace grid: every SM filled exactly once
         int per_sm = 0, nsm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, WAVE_THREADS, 0));
@@ -367,6 +402,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
     A.inline_hemi_max = 16;
     A.qcap = (unsigned)qcap_; A.hcap = (unsigned)hcap_;
     A.hits = d_hits_;
+    A.dout = nsrc_active_ >= RB_COOP_SRC_MIN ? dq_ : nullptr; A.dcap = (unsigned)dcap_;
 
     auto sync_counters = [&](std::string& err) -> bool {
         CK(cudaMemcpyAsync(h_cnt_, d_cnt_, sizeof(DCounters), cudaMemcpyDeviceToHost, stream_));
@@ -397,7 +433,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         CK(cudaGetLastError());
         if (!sync_counters(err) || !timed(stats.kernel_ms, err)) return false;
     }
-    unsigned nq = h_cnt_->nq_out, nh = h_cnt_->nh_out;
+    unsigned nq = h_cnt_->nq_out, nh = h_cnt_->nh_out, nd = h_cnt_->nd_out;
     for (int wave = 0; wave < 4096; wave++) {
         if (h_cnt_->overflow || (size_t)nq + h_cnt_->hemi_rays > qcap_) { overflow = true; return true; }
         if (h_cnt_->errflag) break;
@@ -414,10 +450,23 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
             if (h_cnt_->overflow) { overflow = true; return true; }
             nq = h_cnt_->nq_out;
         }
+        if (nd > 0) {                         // parked direct() calculations: shadow rays into the current queue
+            DirectArgs D; D.din = dq_; D.nd = nd;
+            A.qout = q_[cur];
+            unsigned grid = std::min<unsigned>(nd, 148u * 8u);
+            CK(cudaEventRecord(ev0_, stream_));
+            k_direct<<<grid, 256, 0, stream_>>>(A, D);
+            CK(cudaEventRecord(ev1_, stream_));
+            stats.launches++;
+            CK(cudaGetLastError());
+            if (!sync_counters(err) || !timed(stats.kernel_ms, err)) return false;
+            if (h_cnt_->overflow) { overflow = true; return true; }
+            nq = h_cnt_->nq_out;
+        }
         if (nq == 0) break;
         // reset the out counters, keep the statistics
         CK(cudaMemsetAsync(&d_cnt_->nq_out, 0, 3 * sizeof(unsigned), stream_));
-        CK(cudaMemsetAsync(&d_cnt_->next_ray, 0, sizeof(unsigned), stream_));
+        CK(cudaMemsetAsync(&d_cnt_->next_ray, 0, 2 * sizeof(unsigned), stream_));    // next_ray, nd_out
         A.qin = q_[cur]; A.nin = nq; A.qout = q_[cur ^ 1]; A.hout = h_[cur ^ 1];
         unsigned grid = (nq + WAVE_THREADS - 1) / WAVE_THREADS;
         unsigned tgrid = std::min<unsigned>(grid, (unsigned)trace_blocks_);
@@ -440,7 +489,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
                         h_cnt_->nq_out, h_cnt_->nh_out);
         }
         cur ^= 1;
-        nq = h_cnt_->nq_out; nh = h_cnt_->nh_out;
+        nq = h_cnt_->nq_out; nh = h_cnt_->nh_out; nd = h_cnt_->nd_out;
     }
     if (h_cnt_->errflag) {
         unsigned f = h_cnt_->errflag;
@@ -514,7 +563,9 @@ bool Engine::run(const TraceJob& job, const DParams& P, std::string& err) {
         if (n < 1) n = 1;
         per_rec = (double)n * n;
     }
-    per_rec += S_.nsrcs;
+    // every shading point also sends one shadow ray per active source; the
+    // widest wave is the first-bounce one (about half the sources face a surface)
+    per_rec = per_rec * (1.0 + 0.6 * nsrc_active_) + nsrc_active_;
     per_rec *= (accum > 0 ? accum : 1);
     size_t batch = (size_t)std::max(1.0, (double)qcap_ * 0.45 / per_rec);
     if (accum <= 0) batch = 1;

@@ -5,6 +5,8 @@
 #include "rb_device.cuh"
 
 namespace rb {
+struct DirectJob;
+
 
 struct EngineStats {
     unsigned long long nrays = 0, nodes = 0, leafents = 0, prims = 0, contribs = 0;
@@ -63,6 +65,8 @@ private:
     int nbins_ = 0, ncols_ = 0;
     QRay* q_[2] = {nullptr, nullptr};
     QHemi* h_[2] = {nullptr, nullptr};
+    DirectJob* dq_ = nullptr;   // parked direct() calculations (only when the scene has many sources)
+    size_t dcap_ = 0;
     size_t qcap_ = 0, hcap_ = 0, qcap_req_ = 0;
     DCounters* d_cnt_ = nullptr;
     DCounters* h_cnt_ = nullptr;          // pinned
@@ -75,6 +79,7 @@ private:
     HitRec* d_hits_ = nullptr;
     int trace_blocks_ = 148;
     bool has_local_sources_ = false;
+    int nsrc_active_ = 0;       // distant sources direct() samples (not glow skies)
     std::string local_source_note_;
 };
 

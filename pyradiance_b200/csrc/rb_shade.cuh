@@ -46,6 +46,7 @@ __device__ __forceinline__ unsigned long long child_key(unsigned long long key, 
 }
 
 // ------------------------------------------------------------- context -----
+struct DirectJob;
 struct WaveArgs {
     DScene S;
     DParams P;
@@ -62,6 +63,7 @@ struct WaveArgs {
     RayResult* res;         // per-row primary-hit report (or null)
     DCounters* C;
     int inline_hemi_max;    // hemispheres with n*n <= this are expanded in-thread
+    DirectJob* dout; unsigned dcap;   // parked direct() calculations (null: sources are walked in-thread)
 };
 
 struct RayCtx {             // the ray being shaded (a subset of RAY, rt/ray.h:48-83)
@@ -284,6 +286,7 @@ struct NormDat {           // normal.c:53-67 NORMDAT
     double alpha2, rdiff, rspec, trans, tdiff, tspec;
     double pnorm[3], pdot;
 };
+struct DirectJob { RayCtx r; NormDat nd; };
 enum : int { SP_REFL = 01, SP_TRAN = 02, SP_PURE = 04, SP_FLAT = 010, SP_RBLT = 020, SP_TBLT = 040 };
 
 // normal.c:71-173
@@ -330,45 +333,75 @@ __device__ void dirnorm(float scval[3], const NormDat& np, const RayCtx& r, cons
 }
 
 // source.c:398-556 direct(), with every source tested (the reference's -dt 0
-// behaviour, which rcontrib forces: rcmain.c:164-171).
-__device__ void direct(const WaveArgs& A, RayCtx& r, const NormDat& nd) {
-    const DScene& S = A.S;
-    for (int sn = 0; sn < S.nsrcs; sn++) {
-        const SrcRec& s = S.srcs[sn];
-        if (s.flags & SF_SKIP) continue;                 // srcskip()
-        if (!(s.flags & SF_DISTANT)) continue;
-        // srcray(): rayorigin(sr, SHADOW, r, NULL) never fails for weight > 0
-        unsigned long long key = child_key(r.key, r.nchild++);
-        double vpos[3] = {0, 0, 0};
-        if (A.P.dstrsrc > RB_FTINY) {                    // srcsamp.c:67-79 jitter
-            for (int k = 0; k < 3; k++) vpos[k] = A.P.dstrsrc * (1. - 2. * rnd01(key, 20 + k));
-        }
-        if ((s.flags & SF_CIRC) && (A.P.dstrsrc > 0.7)) {   // srcsamp.c:83-107
-            double d = 1.12837917;
-            double t0 = d * sqrt(1.0 - 0.5 * vpos[1] * vpos[1]);
-            double t1 = d * sqrt(1.0 - 0.5 * vpos[0] * vpos[0]);
-            vpos[0] *= t0; vpos[1] *= t1; vpos[2] *= 0.0;
-        }
-        double ldir[3];
-        for (int k = 0; k < 3; k++)
-            ldir[k] = s.sloc[k] + vpos[0] * s.ss[0][k] + vpos[1] * s.ss[1][k] + vpos[2] * s.ss[2][k];
-        if (normalize3(ldir) == 0.0) continue;
-        double dom = s.ss2;                              // nopart: whole source
-        float scval[3];
-        dirnorm(scval, nd, r, ldir, dom, A.P.dstrsrc);
-        if (!(max3(scval) > 0.f)) continue;
-        // shadow test ray: TSHADOW if through the surface (ray.h:87 thrudir)
-        bool thru = (r.rod > 0) ^ (dot3(r.ron, ldir) > 0);
-        int rt = thru ? RT_TSHADOW : RT_RSHADOW;
-        QRay q;
-        RayCtx par = r; par.key = key; par.nchild = 0;
-        float rc[3];
-        if (!rayorigin(A.P, par, rt, rc, false, q)) continue;
-        q.coef[0] = r.coef[0] * scval[0]; q.coef[1] = r.coef[1] * scval[1]; q.coef[2] = r.coef[2] * scval[2];
-        q.dir[0] = ldir[0]; q.dir[1] = ldir[1]; q.dir[2] = ldir[2];
-        q.rsrc = sn;
-        push_ray(A, q);
+// behaviour, which rcontrib forces: rcmain.c:164-171).  One source -> one
+// shadow ray; its random key is child (nchild0 + sn) of the shaded ray, so the
+// serial and the warp-cooperative forms below emit identical rays.
+__device__ __forceinline__ void direct_one(const WaveArgs& A, const RayCtx& r, const NormDat& nd, int sn,
+                                           unsigned nchild0) {
+    const SrcRec& s = A.S.srcs[sn];
+    if (s.flags & SF_SKIP) return;                   // srcskip()
+    if (!(s.flags & SF_DISTANT)) return;
+    // srcray(): rayorigin(sr, SHADOW, r, NULL) never fails for weight > 0
+    unsigned long long key = child_key(r.key, nchild0 + (unsigned)sn);
+    double vpos[3] = {0, 0, 0};
+    if (A.P.dstrsrc > RB_FTINY) {                    // srcsamp.c:67-79 jitter
+        for (int k = 0; k < 3; k++) vpos[k] = A.P.dstrsrc * (1. - 2. * rnd01(key, 20 + k));
     }
+    if ((s.flags & SF_CIRC) && (A.P.dstrsrc > 0.7)) {   // srcsamp.c:83-107
+        double d = 1.12837917;
+        double t0 = d * sqrt(1.0 - 0.5 * vpos[1] * vpos[1]);
+        double t1 = d * sqrt(1.0 - 0.5 * vpos[0] * vpos[0]);
+        vpos[0] *= t0; vpos[1] *= t1; vpos[2] *= 0.0;
+    }
+    double ldir[3];
+    for (int k = 0; k < 3; k++)
+        ldir[k] = s.sloc[k] + vpos[0] * s.ss[0][k] + vpos[1] * s.ss[1][k] + vpos[2] * s.ss[2][k];
+    if (normalize3(ldir) == 0.0) return;
+    double dom = s.ss2;                              // nopart: whole source
+    float scval[3];
+    dirnorm(scval, nd, r, ldir, dom, A.P.dstrsrc);
+    if (!(max3(scval) > 0.f)) return;
+    // shadow test ray: TSHADOW if through the surface (ray.h:87 thrudir)
+    bool thru = (r.rod > 0) ^ (dot3(r.ron, ldir) > 0);
+    int rt = thru ? RT_TSHADOW : RT_RSHADOW;
+    if (r.rot >= RB_FHUGE * .99 || !(r.rweight > 0.f)) return;      // rayorigin() refusals
+    QRay q;
+    q.org[0] = r.rop[0]; q.org[1] = r.rop[1]; q.org[2] = r.rop[2];
+    q.dir[0] = ldir[0]; q.dir[1] = ldir[1]; q.dir[2] = ldir[2];
+    const bool refl = (rt & RT_RAYREFL) != 0;        // RSHADOW starts a new path segment, TSHADOW continues
+    q.rmax = refl ? 0.0 : (r.rmax > RB_FTINY) * (r.rmax - r.rot);
+    q.coef[0] = r.coef[0] * scval[0]; q.coef[1] = r.coef[1] * scval[1]; q.coef[2] = r.coef[2] * scval[2];
+    q.rweight = r.rweight;
+    q.row = r.row;
+    q.info = pack_info(r.crtype | rt, r.rlvl + (refl ? 1 : 0), r.rdepth);
+    q.rsrc = sn;
+    q.key_lo = (unsigned)key; q.key_hi = (unsigned)(key >> 32);
+    q.pad = 0;
+    push_ray(A, q);
+}
+
+__device__ void direct(const WaveArgs& A, RayCtx& r, const NormDat& nd) {
+    const int ns = A.S.nsrcs;
+    for (int sn = 0; sn < ns; sn++) direct_one(A, r, nd, sn, r.nchild);
+    r.nchild += (unsigned)ns;
+}
+
+// Scenes with many sources (a 5-phase sun matrix has thousands): the shading
+// thread parks its state in a job queue and k_direct walks the source list
+// with one CTA per job, writing its shadow rays to consecutive queue slots.
+#ifndef RB_COOP_SRC_MIN
+#define RB_COOP_SRC_MIN 64
+#endif
+
+__device__ __forceinline__ void direct_or_park(const WaveArgs& A, RayCtx& r, const NormDat& nd) {
+    if (A.dout) {
+        unsigned slot = reserve_slot(&A.C->nd_out);
+        if (slot >= A.dcap) { A.C->overflow = 1; return; }
+        A.dout[slot].r = r;
+        A.dout[slot].nd = nd;
+        return;
+    }
+    direct(A, r, nd);
 }
 
 // ambient.c:229-297 (aa = 0 branch) + ambcomp.c:350-422
@@ -562,7 +595,7 @@ __device__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind, const float* a
         double bn[3] = {-nd.pnorm[0], -nd.pnorm[1], -nd.pnorm[2]};
         multambient(A, r, sct, bn);
     }
-    direct(A, r, nd);
+    direct_or_park(A, r, nd);
 }
 
 // glass.c:46-165

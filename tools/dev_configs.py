@@ -54,7 +54,31 @@ def c4(nrays=200000, nref=2000):
     print("  per-window-group totals gpu", np.round(per_mod_g, 2), "\n  per-window-group totals ref", np.round(per_mod_r, 2))
     print("  total gpu %.3f ref %.3f" % (g.sum(), r.sum()))
 
+def c5(npoly=100_000, nsens=1000, nref=8, mf=6):
+    # S-sun-like: MF:6 light suns sharing modifier solar, -ab 1 (instances/meshes are covered by the golden tests)
+    import io
+    rad, octf = TMP / "sun.rad", TMP / "sun.oct"
+    out = io.StringIO(); out.write(scenegen.MATERIALS); scenegen.write_suns(out, mf=mf)
+    rng = np.random.default_rng(11); scenegen.office_floor(out, rng, 0.0, (npoly - 24) // 6, tag="f0")
+    rad.write_text(out.getvalue()); scenegen.build_octree(rad, octf)
+    sens = scenegen.office_sensors(nsens, seed=4)
+    opts = ["-ab", "1", "-ad", "256", "-lw", "1e-3", "-dc", "1", "-dt", "0", "-dj", "0"]
+    nb = 144 * mf * mf + 2
+    ctx = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB); ctx.load_octree(octf); ctx.set_options(opts)
+    ctx.cal_load("reinhart.cal"); ctx.cal_set(f"MF={mf}"); ctx.add_modifier("solar", "", "rbin", nb)
+    for rep in range(2):
+        ctx.reset_stats(); t = time.time(); m = ctx.rcontrib(sens, flags=_lib.RB_IRRAD_RCONTRIB); dt = time.time() - t; st = ctx.stats()
+        print(f"C5-mini GPU: {nsens} sensors x {nb} bins in {dt:.2f}s, {st['nrays']/1e6:.0f} Mrays, {st['nrays']/dt/1e6:.0f} Mrays/s wall, k_trace {st['nrays']/max(st['wave_ms'],1e-9)/1e3:.0f} Mrays/s, shade_ms {st['shade_ms']:.0f} wave_ms {st['wave_ms']:.0f} batches {st['batches']} retries {st['retries']} waves {st['waves']}")
+    idx = np.linspace(0, nsens - 1, nref).astype(int)
+    t = time.time()
+    ref = refrun.rcontrib(octf, sens[idx], ["-I+"] + opts + ["-e", f"MF:{mf}", "-f", "reinhart.cal", "-b", "rbin", "-bn", "Nrbins", "-m", "solar"], nproc=os.cpu_count()).reshape(nref, -1, 3)
+    print(f"  ref: {nref} sensors in {time.time()-t:.1f}s")
+    a = m[idx, :, 0].sum(1); b = ref[:, :, 0].sum(1)
+    print("  row sums gpu", np.round(a, 5), "\n  row sums ref", np.round(b, 5), "\n  total gpu %.5f ref %.5f" % (a.sum(), b.sum()))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c3", "c4"]
     if "c4" in which: c4()
     if "c3" in which: c3()
+    if "c5" in which: c5()
