@@ -26,7 +26,7 @@ namespace rb {
 #define WAVE_THREADS 128
 #endif
 #ifndef RB_MINBLOCKS
-#define RB_MINBLOCKS 4
+#define RB_MINBLOCKS 5
 #endif
 
 #define CK(call)                                                                     \
@@ -59,11 +59,12 @@ __device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws, u
 // the queue until it is empty (rb_geom.cuh walk_rays).
 __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const WaveArgs A) {
     __shared__ WalkSmem<WAVE_THREADS> sm;
+    extern __shared__ int stk_dyn[];         // [maxdepth + 1][WAVE_THREADS]
     TraceIO io;
     io.qin = A.qin; io.nin = A.nin; io.hits = A.hits; io.next = &A.C->next_ray;
     WalkStats ws = {0, 0, 0};
     unsigned nretired = 0;
-    walk_rays<WAVE_THREADS>(A.S, io, sm, ws, nretired, &A.C->errflag, &A.C->errobj);
+    walk_rays<WAVE_THREADS>(A.S, io, sm, stk_dyn, ws, nretired, &A.C->errflag, &A.C->errobj);
     flush_stats(A.C, ws, nretired);
 }
 
@@ -339,12 +340,18 @@ bool Engine::ensure_queues(std::string& err) {
     if (nsrc_active_ >= RB_COOP_SRC_MIN) {      // many sources: direct() runs as its own kernel from a job queue
         CK(cudaMalloc(&dq_, dcap_ * sizeof(DirectJob)));
     }
-    {   // persistent k_trace grid: every SM filled exactly once
-        int per_sm = 0, nsm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, WAVE_THREADS, 0));
-        CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev_));
-        trace_blocks_ = std::max(1, per_sm) * std::max(1, nsm);
-    }
+    return size_trace_grid(err);
+}
+
+// Persistent k_trace grid: every SM filled exactly once.  Depends on the octree
+// depth through the dynamic shared memory of the ancestor stack.
+bool Engine::size_trace_grid(std::string& err) {
+    int per_sm = 0, nsm = 0;
+    trace_smem_ = (size_t)(S_.maxdepth + 1) * WAVE_THREADS * sizeof(int);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, WAVE_THREADS, trace_smem_));
+    CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev_));
+    if (const char* e = getenv("RB_TRACE_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));   // developer knob
+    trace_blocks_ = std::max(1, per_sm) * std::max(1, nsm);
     return true;
 }
 
@@ -471,7 +478,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         unsigned grid = (nq + WAVE_THREADS - 1) / WAVE_THREADS;
         unsigned tgrid = std::min<unsigned>(grid, (unsigned)trace_blocks_);
         CK(cudaEventRecord(ev0_, stream_));
-        k_trace<<<tgrid, WAVE_THREADS, 0, stream_>>>(A);
+        k_trace<<<tgrid, WAVE_THREADS, trace_smem_, stream_>>>(A);
         CK(cudaEventRecord(ev1_, stream_));
         CK(cudaEventRecord(ev2_, stream_));
         k_shade<<<(nq + RB_SHADE_THREADS - 1) / RB_SHADE_THREADS, RB_SHADE_THREADS, 0, stream_>>>(A);
@@ -550,7 +557,7 @@ bool Engine::run(const TraceJob& job, const DParams& P, std::string& err) {
         err = "unsupported scene: " + local_source_note_;
         return false;
     }
-    if (!ensure_queues(err)) return false;
+    if (!ensure_queues(err) || !size_trace_grid(err)) return false;
     if (job.nrays == 0) return true;
     const int accum = job.accum;
     const size_t nrec_total = accum > 0 ? (job.nrays + accum - 1) / accum : 1;

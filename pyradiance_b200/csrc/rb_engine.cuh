@@ -55,6 +55,7 @@ public:
 
 private:
     bool ensure_queues(std::string& err);
+    bool size_trace_grid(std::string& err);
     bool run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_t nrec, std::string& err, bool& overflow);
     int dev_;
     cudaStream_t stream_ = nullptr;
@@ -78,6 +79,7 @@ private:
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev2_ = nullptr, ev3_ = nullptr;
     HitRec* d_hits_ = nullptr;
     int trace_blocks_ = 148;
+    size_t trace_smem_ = 0;      // dynamic shared memory of k_trace (ancestor stack)
     bool has_local_sources_ = false;
     int nsrc_active_ = 0;       // distant sources direct() samples (not glow skies)
     std::string local_source_note_;

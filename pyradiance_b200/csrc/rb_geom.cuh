@@ -39,7 +39,18 @@ namespace rb {
 #ifndef RB_FETCH_MIN
 #define RB_FETCH_MIN 6           // refill a warp when this many lanes are idle
 #endif
+#ifndef RB_WALK_STATS
+#define RB_WALK_STATS 0          // count node / leaf-entry / surface-test visits (developer builds)
+#endif
+#if RB_WALK_STATS
+#define RB_STAT(x) x
+#else
+#define RB_STAT(x)
+#endif
 #define RB_PAIRS (32 * RB_OPR)
+#ifndef RB_PAIR_ILP
+#define RB_PAIR_ILP 1            // (ray, surface) pairs a lane has in flight in the pair loop
+#endif
 
 __device__ __forceinline__ double dot3(const double a[3], const double b[3]) {
     return a[0] * b[0] + a[1] * b[1] + a[2] * b[2];
@@ -89,10 +100,9 @@ __device__ __forceinline__ int quadratic(double r[2], double a, double b, double
 
 // Candidate of a polygon: o_face() up to, but not including, rayreject().
 // `tmax` is a conservative upper bound (current rot + a few FTINY).
-__device__ __forceinline__ bool cand_face(int4 hd, const double* __restrict__ g, const double org[3],
+__device__ __forceinline__ bool cand_face(int4 hd, const double* __restrict__ g, double2 n01, double2 n2o,
+                                          double2 bx, double2 by, const double org[3],
                                           const double dir[3], double tmax, double& t, bool& front) {
-    const double2* g2 = reinterpret_cast<const double2*>(g);
-    double2 n01 = __ldg(&g2[0]), n2o = __ldg(&g2[1]);
     double rdot = -(dir[0] * n01.x + dir[1] * n01.y + dir[2] * n2o.x);
     if ((rdot <= RB_FTINY) & (rdot >= -RB_FTINY)) return false;
     t = ((org[0] * n01.x + org[1] * n01.y + org[2] * n2o.x) - n2o.y) / rdot;
@@ -106,7 +116,6 @@ __device__ __forceinline__ bool cand_face(int4 hd, const double* __restrict__ g,
     // (no edge straddles y / all straddling edges on one side, and none of
     // inface()'s three FABSEQ cases can fire); well inside an exact axis-aligned
     // rectangle is always "in".  Only the FTINY border zone runs the edge loop.
-    double2 bx = __ldg(&g2[2]), by = __ldg(&g2[3]);
     if ((x < bx.x - RB_FTINY) | (x > bx.y + RB_FTINY) | (y < by.x - RB_FTINY) | (y > by.y + RB_FTINY)) return false;
     bool in = ((hd.x >> 12) & 1) && (x > bx.x + RB_FTINY) & (x < bx.y - RB_FTINY) & (y > by.x + RB_FTINY) &
                                         (y < by.y - RB_FTINY);
@@ -249,20 +258,53 @@ struct TraceIO {
     unsigned* next;              // global fetch counter
 };
 
-// Shared memory of one CTA of k_trace (per-thread columns, SoA).
+// Shared memory of one CTA of k_trace (per-thread columns, SoA).  Everything a
+// ray owns between rounds lives here, not in registers: the kernel is bound by
+// dependent-load latency, throughput scales with the warps resident per SM
+// (profiles/r2_notes.md), and registers are what limits them.  The ancestor
+// stack [depth + 1][NT] is dynamic shared memory sized by the octree's depth.
 template <int NT>
 struct WalkSmem {
-    int stk[RB_STACK][NT];       // ancestors of the current cube
     double ray[6][NT];           // staged ray: origin, direction
+    double pos[3][NT];           // current position along the ray (raymove's pos)
     double rot[NT];              // current best distance
-    int set[NT];                 // leaf-set offset of the surfaces to test this round
-    int kst[NT];                 // index of the first of them (descending)
-    int excl[NT];                // exclusive prefix of the per-lane surface counts
+    unsigned cell[3][NT];        // integer coordinates of the current cube at its level
+    int robj[NT];                // current best object << 1 | front-facing, or -1
+    unsigned ridx[NT];           // queue slot of the ray
+    unsigned pair[NT / 32][RB_PAIRS];   // (ray, surface) pairs of this round: leaf-set entry << 5 | owner lane
     int ndef[NT / 32];           // deferred (non-polygon) pairs of this round
-    int defer[NT / 32][RB_PAIRS];
+    unsigned short defer[NT / 32][RB_PAIRS];   // their pair indices
     double ct[NT / 32][RB_PAIRS];   // candidate distance per (ray, surface) pair
     int cid[NT / 32][RB_PAIRS];     // candidate: object id << 1 | front, or -1
 };
+
+// One (ray, surface) pair: polygon candidates are computed here, the rare
+// other kinds are queued for the warp's second pass.
+template <int NT>
+__device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, unsigned wid, int p, unsigned own,
+                                          int2 ent, const double* __restrict__ g, int4 hd, double2 n01, double2 n2o,
+                                          double2 bx, double2 by, unsigned* errflag, unsigned* errobj) {
+    const int kind = hd.x & 0xff;
+    if (kind == PK_FACE) {
+        const double org[3] = {sm.ray[0][own], sm.ray[1][own], sm.ray[2][own]};
+        const double rd[3] = {sm.ray[3][own], sm.ray[4][own], sm.ray[5][own]};
+        const double tmax = sm.rot[own] + 8 * RB_FTINY;      // ties may raise rot by < FTINY each
+        double t = 0;
+        bool fr = true;
+        const bool ok = cand_face(hd, g, n01, n2o, bx, by, org, rd, tmax, t, fr);
+        sm.ct[wid][p] = t;
+        sm.cid[wid][p] = ok ? ((ent.x << 1) | (int)fr) : -1;
+    } else {                         // rare kinds: second pass, again with all lanes
+        sm.cid[wid][p] = -1;
+        if (kind == PK_UNSUPPORTED) { atomicOr(errflag, RB_ERR_UNSUP_PRIM); *errobj = (unsigned)ent.x; }
+        else if (kind != PK_NONE) sm.defer[wid][atomicAdd(&sm.ndef[wid], 1)] = (unsigned short)p;
+    }
+}
+
+// cusize * 2^-L, exactly what L halvings of the root cube size give
+__device__ __forceinline__ double cube_size(double cs, int L) {
+    return cs * __hiloint2double((1023 - L) << 20, 0);
+}
 
 // walk_rays(): persistent-thread, warp-cooperative localhit().
 //  * Every warp keeps pulling rays from the queue: a lane whose ray is finished
@@ -284,66 +326,76 @@ struct WalkSmem {
 //    (raytrace.c:688-738).  Every live lane does exactly one step per round,
 //    so the expensive step code (3 divisions) runs with the warp nearly full;
 //    in the first version it ran with ~5 of 32 lanes.
+// Registers carry only what a phase is working on: between phases a lane's
+// state is {flags, node word, level} plus the shared-memory columns above.
 // MUST be called by all threads of the CTA.
+enum : unsigned { WF_HAVE = 1, WF_DONE = 2, WF_RESULT = 4, WF_AFT = 8 };
+
 template <int NT>
-__device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, WalkSmem<NT>& sm, WalkStats& ws,
+__device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, WalkSmem<NT>& sm, int* __restrict__ stk,
+                                          WalkStats& ws,
                                           unsigned& nretired, unsigned* errflag, unsigned* errobj) {
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     const double cs = S.cusize;
     const int2* __restrict__ pool = reinterpret_cast<const int2*>(S.leafpool);
-    double dir[3] = {0, 0, 1}, pos[3] = {0, 0, 0}, size = cs, rot = RB_FHUGE;
-    int robj = -1, dirf = 0, w = -1, L = 0;
-    unsigned ix = 0, iy = 0, iz = 0, ridx = 0;
-    bool front = true, aft = false, done = true, result = false, have = false, exhausted = false;
+    unsigned fl = WF_DONE;       // WF_* flags of this lane's ray
+    int w = -1;                  // node word of the current cube
+    int Ld = 0;                  // level of the current cube | direction flags << 8
+    bool exhausted = false;
     for (;;) {
         // ---- retire finished rays ----
-        if (have & done) {
+        if ((fl & (WF_HAVE | WF_DONE)) == (WF_HAVE | WF_DONE)) {
+            const unsigned ridx = sm.ridx[tid];
+            const int ro = sm.robj[tid];
             HitRec o;
-            o.rot = rot; o.rod = front ? 1.0 : -1.0; o.robj = robj; o.local = 1;
-            if (!result) {
+            o.rot = sm.rot[tid]; o.rod = (ro & 1) ? 1.0 : -1.0; o.robj = ro >> 1; o.local = 1;
+            if (!(fl & WF_RESULT)) {
                 o.rot = RB_FHUGE; o.rod = 1.0; o.robj = -1; o.local = 0;
                 const QRay& q = io.qin[ridx];
                 if (!(q.rmax > RB_FTINY)) {          // aft-clipped rays never see sources
+                    const double dir[3] = {sm.ray[3][tid], sm.ray[4][tid], sm.ray[5][tid]};
                     int sn = sourcehit(S, dir, q.rsrc, q.info & 0x3ff);
                     if (sn >= 0) o.robj = S.srcs[sn].so;
                 }
             }
             io.hits[ridx] = o;
-            have = false;
+            fl &= ~WF_HAVE;
             nretired++;
         }
         // ---- refill idle lanes ----
-        unsigned idle = __ballot_sync(FULL, !have);
+        const unsigned idle = __ballot_sync(FULL, !(fl & WF_HAVE));
         if (idle == FULL && exhausted) break;
         if (!exhausted && (__popc(idle) >= RB_FETCH_MIN)) {
-            int n = __popc(idle);
-            int leader = __ffs(idle) - 1;
+            const int n = __popc(idle);
+            const int leader = __ffs(idle) - 1;
             unsigned base = 0;
             if ((int)lane == leader) base = atomicAdd(io.next, (unsigned)n);
             base = __shfl_sync(FULL, base, leader);
             if (base + n >= io.nin) exhausted = true;
-            unsigned my = base + __popc(idle & ((1u << lane) - 1));
-            if (!have && my < io.nin) {
+            const unsigned my = base + __popc(idle & ((1u << lane) - 1));
+            if (!(fl & WF_HAVE) && my < io.nin) {
                 const double2* q2 = reinterpret_cast<const double2*>(&io.qin[my]);
-                double2 a = __ldg(&q2[0]), b = __ldg(&q2[1]), c = __ldg(&q2[2]), d = __ldg(&q2[3]);
-                double org[3] = {a.x, a.y, b.x};
-                dir[0] = b.y; dir[1] = c.x; dir[2] = c.y;
-                double rmax = d.x;
+                const double2 a = __ldg(&q2[0]), b = __ldg(&q2[1]), c = __ldg(&q2[2]), d = __ldg(&q2[3]);
+                const double org[3] = {a.x, a.y, b.x};
+                const double dir[3] = {b.y, c.x, c.y};
+                const double rmax = d.x;
                 sm.ray[0][tid] = org[0]; sm.ray[1][tid] = org[1]; sm.ray[2][tid] = org[2];
                 sm.ray[3][tid] = dir[0]; sm.ray[4][tid] = dir[1]; sm.ray[5][tid] = dir[2];
-                ridx = my; have = true;
+                sm.ridx[tid] = my;
                 // ---- localhit() prologue (raytrace.c:604-651) ----
-                dirf = 0;
+                int dirf = 0;
+                double pos[3];
 #pragma unroll
                 for (int i = 0; i < 3; i++) {
                     pos[i] = org[i];
                     if (dir[i] > 1e-7) dirf |= 1 << i;
                     else if (dir[i] < -1e-7) dirf |= 0x10 << i;
                 }
-                robj = -1; rot = RB_FHUGE; front = true;
-                done = !dirf; result = false; aft = false;
-                if (!done && rmax > RB_FTINY) { aft = true; rot = rmax; }
+                double rot = RB_FHUGE;
+                bool done = !dirf;
+                fl = WF_HAVE;
+                if (!done && rmax > RB_FTINY) { fl |= WF_AFT; rot = rmax; }
                 if (!done) {
                     bool in = !(S.cuorg[0] > pos[0] || pos[0] >= S.cuorg[0] + cs ||
                                 S.cuorg[1] > pos[1] || pos[1] >= S.cuorg[1] + cs ||
@@ -371,42 +423,55 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                         }
                     }
                 }
-                w = S.root; L = 0; ix = iy = iz = 0; size = cs;
+                if (done) fl |= WF_DONE;
+                sm.pos[0][tid] = pos[0]; sm.pos[1][tid] = pos[1]; sm.pos[2][tid] = pos[2];
+                sm.rot[tid] = rot;
+                sm.robj[tid] = -1;
+                sm.cell[0][tid] = 0; sm.cell[1][tid] = 0; sm.cell[2][tid] = 0;
+                w = S.root; Ld = dirf << 8;
             }
         }
         __syncwarp();
-        bool act = have & !done;
+        bool act = (fl & (WF_HAVE | WF_DONE)) == WF_HAVE;
         // ---- phase A: descend towards a leaf (raymove, raytrace.c:668-687); at most
-        //      RB_DITERS levels per round -- a freshly fetched ray needs ~8 levels and
-        //      would otherwise hold the other 31 lanes; it just sits out this round ----
+        //      RB_DITERS levels per round ----
+        if (__any_sync(FULL, act & (w >= 0))) {
+            unsigned ix = sm.cell[0][tid], iy = sm.cell[1][tid], iz = sm.cell[2][tid];
+            const double px = sm.pos[0][tid], py = sm.pos[1][tid], pz = sm.pos[2][tid];
+            int L = Ld & 0xff;
+            double size = cube_size(cs, L);
 #pragma unroll 1
-        for (int it = 0; it < RB_DITERS; it++) {
-            const bool d = act & (w >= 0);
-            if (!__any_sync(FULL, d)) break;
-            if (d) {
-                sm.stk[L][tid] = w;
-                double half = size * 0.5;
-                double lox = fma((double)ix, size, S.cuorg[0]);
-                double loy = fma((double)iy, size, S.cuorg[1]);
-                double loz = fma((double)iz, size, S.cuorg[2]);
-                int br = 0;
-                ix <<= 1; iy <<= 1; iz <<= 1;
-                if (pos[0] >= lox + half) { br |= 1; ix |= 1; }
-                if (pos[1] >= loy + half) { br |= 2; iy |= 1; }
-                if (pos[2] >= loz + half) { br |= 4; iz |= 1; }
-                w = __ldg(&S.nodes[(size_t)w * 8 + br]);
-                ws.nodes++;
-                size = half; L++;
+            for (int it = 0; it < RB_DITERS; it++) {
+                const bool d = act & (w >= 0);
+                if (!__any_sync(FULL, d)) break;
+                if (d) {
+                    stk[L * NT + tid] = w;
+                    const double half = size * 0.5;
+                    const double lox = fma((double)ix, size, S.cuorg[0]);
+                    const double loy = fma((double)iy, size, S.cuorg[1]);
+                    const double loz = fma((double)iz, size, S.cuorg[2]);
+                    int br = 0;
+                    ix <<= 1; iy <<= 1; iz <<= 1;
+                    if (px >= lox + half) { br |= 1; ix |= 1; }
+                    if (py >= loy + half) { br |= 2; iy |= 1; }
+                    if (pz >= loz + half) { br |= 4; iz |= 1; }
+                    w = __ldg(&S.nodes[(size_t)w * 8 + br]);
+                    RB_STAT(ws.nodes++;)
+                    size = half; L++;
+                }
             }
+            sm.cell[0][tid] = ix; sm.cell[1][tid] = iy; sm.cell[2][tid] = iz;
+            Ld = (Ld & ~0xff) | L;
         }
         act &= (w < 0);                          // still inside the tree: continue next round
         const bool full = act & (w < -1);
         int kleft = 0, setoff = 0;
         if (full) {
-            setoff = -w - 2;
-            kleft = __ldg(&pool[setoff]).x;
-            ws.leafents += kleft + 1;
-            ws.prims += kleft;
+            const unsigned u = (unsigned)(-w - 2);       // set offset << 3 | min(count, 7)
+            setoff = (int)(u >> 3);
+            kleft = (int)(u & 7);
+            if (kleft == 7) kleft = __ldg(&pool[setoff]).x;
+            RB_STAT(ws.leafents += kleft + 1; ws.prims += kleft;)
         }
         // ---- phase B: the warp tests the leaves' surfaces as (ray, surface) pairs ----
         for (;;) {
@@ -420,47 +485,51 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
             const int total = __shfl_sync(FULL, incl, 31);
             if (total == 0) break;
             const unsigned wbase = wid * 32;
-            sm.excl[tid] = incl - m;
-            sm.set[tid] = setoff;
-            sm.kst[tid] = kleft;
-            sm.rot[tid] = rot;
+            const int e0 = incl - m;
+            for (int j = 0; j < m; j++)               // owners publish their pairs, descending set index
+                sm.pair[wid][e0 + j] = ((unsigned)(setoff + kleft - j) << 5) | lane;
             if (lane == 0) sm.ndef[wid] = 0;
             __syncwarp();
-            for (int p = lane; p < total; p += 32) {
-                // owner = last lane whose exclusive prefix is <= p
-                int lo = 0;
-#pragma unroll
-                for (int s2 = 16; s2 > 0; s2 >>= 1)
-                    if (sm.excl[wbase + lo + s2] <= p) lo += s2;
-                const unsigned own = wbase + lo;
-                const int k = sm.kst[own] - (p - sm.excl[own]);          // descending index
-                const int2 ent = __ldg(&pool[sm.set[own] + k]);
-                const double* g = S.geom + ent.y;
-                const int4 hd = __ldg(reinterpret_cast<const int4*>(g - 2));
-                const int kind = hd.x & 0xff;
-                if (kind == PK_FACE) {
-                    const double org[3] = {sm.ray[0][own], sm.ray[1][own], sm.ray[2][own]};
-                    const double rd[3] = {sm.ray[3][own], sm.ray[4][own], sm.ray[5][own]};
-                    const double tmax = sm.rot[own] + 8 * RB_FTINY;      // ties may raise rot by < FTINY each
-                    double t = 0;
-                    bool fr = true;
-                    const bool ok = cand_face(hd, g, org, rd, tmax, t, fr);
-                    sm.ct[wid][p] = t;
-                    sm.cid[wid][p] = ok ? ((ent.x << 1) | (int)fr) : -1;
-                } else {                         // rare kinds: second pass, again with all lanes
-                    sm.cid[wid][p] = -1;
-                    if (kind == PK_UNSUPPORTED) { atomicOr(errflag, RB_ERR_UNSUP_PRIM); *errobj = (unsigned)ent.x; }
-                    else if (kind != PK_NONE) sm.defer[wid][atomicAdd(&sm.ndef[wid], 1)] = p | (own << 16);
-                }
+#if RB_PAIR_ILP == 2
+            // two pairs per lane and pass: both records are in flight together
+            for (int p = lane; p < total; p += 64) {
+                const int pb = p + 32;
+                const bool two = pb < total;
+                const unsigned prA = sm.pair[wid][p], prB = sm.pair[wid][two ? pb : p];
+                const unsigned ownA = wbase + (prA & 31), ownB = wbase + (prB & 31);
+                const int2 entA = __ldg(&pool[prA >> 5]);
+                const int2 entB = __ldg(&pool[prB >> 5]);
+                const double* gA = S.geom + entA.y;
+                const double* gB = S.geom + entB.y;
+                const double2* gA2 = reinterpret_cast<const double2*>(gA);
+                const double2* gB2 = reinterpret_cast<const double2*>(gB);
+                const int4 hdA = __ldg(reinterpret_cast<const int4*>(gA - 2));
+                const double2 a0 = __ldg(&gA2[0]), a1 = __ldg(&gA2[1]), a2 = __ldg(&gA2[2]), a3 = __ldg(&gA2[3]);
+                const int4 hdB = __ldg(reinterpret_cast<const int4*>(gB - 2));
+                const double2 b0 = __ldg(&gB2[0]), b1 = __ldg(&gB2[1]), b2 = __ldg(&gB2[2]), b3 = __ldg(&gB2[3]);
+                pair_test(S, sm, wid, p, ownA, entA, gA, hdA, a0, a1, a2, a3, errflag, errobj);
+                if (two) pair_test(S, sm, wid, pb, ownB, entB, gB, hdB, b0, b1, b2, b3, errflag, errobj);
             }
+#else
+            for (int p = lane; p < total; p += 32) {
+                const unsigned pr = sm.pair[wid][p];
+                const unsigned own = wbase + (pr & 31);
+                const int2 ent = __ldg(&pool[pr >> 5]);
+                const double* g = S.geom + ent.y;
+                // header, plane and 2-D box of the record in one go (one latency, not three)
+                const double2* g2 = reinterpret_cast<const double2*>(g);
+                const int4 hd = __ldg(reinterpret_cast<const int4*>(g - 2));
+                const double2 n01 = __ldg(&g2[0]), n2o = __ldg(&g2[1]), bx = __ldg(&g2[2]), by = __ldg(&g2[3]);
+                pair_test(S, sm, wid, p, own, ent, g, hd, n01, n2o, bx, by, errflag, errobj);
+            }
+#endif
             __syncwarp();
             const int ndef = sm.ndef[wid];
             for (int q = lane; q < ndef; q += 32) {
-                const int pq = sm.defer[wid][q];
-                const int p = pq & 0xffff;
-                const unsigned own = (unsigned)pq >> 16;
-                const int k = sm.kst[own] - (p - sm.excl[own]);
-                const int2 ent = __ldg(&pool[sm.set[own] + k]);
+                const int p = sm.defer[wid][q];
+                const unsigned pr = sm.pair[wid][p];
+                const unsigned own = wbase + (pr & 31);
+                const int2 ent = __ldg(&pool[pr >> 5]);
                 const double* g = S.geom + ent.y;
                 const int kind = __ldg(reinterpret_cast<const int4*>(g - 2)).x & 0xff;
                 const double org[3] = {sm.ray[0][own], sm.ray[1][own], sm.ray[2][own]};
@@ -474,56 +543,71 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
             }
             __syncwarp();
             // owners apply rayreject() in the reference's order (raytrace.c:535-575)
-            const int e0 = incl - m;
-            for (int j = 0; j < m; j++) {
-                const int c = sm.cid[wid][e0 + j];
-                if (c < 0) continue;
-                const double t = sm.ct[wid][e0 + j];
-                const int id = c >> 1;
-                const bool fr = c & 1;
-                if ((t <= RB_FTINY) | (t > rot + RB_FTINY)) continue;
-                if (!(t < rot - RB_FTINY)) {              // coincident point, so decide...
-                    if (id == robj) continue;
-                    if (robj < 0) { if (aft) continue; }
-                    else {
-                        const int4 hnew = __ldg(&S.objhdr[id]), hold = __ldg(&S.objhdr[robj]);
-                        const int fnew = hnew.x >> 8, fold = hold.x >> 8;
-                        const bool mnew = fnew & PF_HASMAT, mray = fold & PF_HASMAT;
-                        bool rej = false, dec = false;
-                        if (!mnew) { if (mray) { rej = true; dec = true; } }
-                        else if (!mray) { dec = true; }
-                        else if (fnew & PF_TRANSP) { if (!(fold & PF_TRANSP)) { rej = true; dec = true; } }
-                        else if (fold & PF_TRANSP) { dec = true; }
-                        if (!dec) {
-                            if (!fr) { if (front) { rej = true; dec = true; } }
-                            else if (!front) { dec = true; }
+            if (m > 0) {
+                double rot = sm.rot[tid];
+                int ro = sm.robj[tid];
+                for (int j = 0; j < m; j++) {
+                    const int c = sm.cid[wid][e0 + j];
+                    if (c < 0) continue;
+                    const double t = sm.ct[wid][e0 + j];
+                    if ((t <= RB_FTINY) | (t > rot + RB_FTINY)) continue;
+                    if (!(t < rot - RB_FTINY)) {              // coincident point, so decide...
+                        const int id = c >> 1, robj = ro >> 1;
+                        if (id == robj) continue;
+                        if (ro < 0) { if (fl & WF_AFT) continue; }
+                        else {
+                            const bool fr = c & 1, front = ro & 1;
+                            const int4 hnew = __ldg(&S.objhdr[id]), hold = __ldg(&S.objhdr[robj]);
+                            const int fnew = hnew.x >> 8, fold = hold.x >> 8;
+                            const bool mnew = fnew & PF_HASMAT, mray = fold & PF_HASMAT;
+                            bool rej = false, dec = false;
+                            if (!mnew) { if (mray) { rej = true; dec = true; } }
+                            else if (!mray) { dec = true; }
+                            else if (fnew & PF_TRANSP) { if (!(fold & PF_TRANSP)) { rej = true; dec = true; } }
+                            else if (fold & PF_TRANSP) { dec = true; }
+                            if (!dec) {
+                                if (!fr) { if (front) { rej = true; dec = true; } }
+                                else if (!front) { dec = true; }
+                            }
+                            if (!dec) rej = hold.y >= hnew.y;  // later modifier definition wins tie
+                            if (rej) continue;
                         }
-                        if (!dec) rej = hold.y >= hnew.y;  // later modifier definition wins tie
-                        if (rej) continue;
                     }
+                    ro = c; rot = t;
                 }
-                robj = id; rot = t; front = fr;
+                sm.rot[tid] = rot;
+                sm.robj[tid] = ro;
             }
             kleft -= m;
             __syncwarp();
         }
         // ---- phase C: accept (checkhit / aft plane), else step to the neighbour cube ----
         if (act) {
+            unsigned ix = sm.cell[0][tid], iy = sm.cell[1][tid], iz = sm.cell[2][tid];
+            int L = Ld & 0xff;
+            const int dirf = Ld >> 8;
+            const double size = cube_size(cs, L);
             const double lox = fma((double)ix, size, S.cuorg[0]);
             const double loy = fma((double)iy, size, S.cuorg[1]);
             const double loz = fma((double)iz, size, S.cuorg[2]);
             const double hix = lox + size, hiy = loy + size, hiz = loz + size;
-            if (full ? (robj >= 0) : (aft & (robj < 0))) {
+            const double dir[3] = {sm.ray[3][tid], sm.ray[4][tid], sm.ray[5][tid]};
+            const int ro = sm.robj[tid];
+            bool done = false;
+            if (full ? (ro >= 0) : ((fl & WF_AFT) && ro < 0)) {
                 // checkhit (raytrace.c:756-759) / aft-plane point in an empty leaf (:709-710)
+                const double rot = sm.rot[tid];
                 const double px = sm.ray[0][tid] + rot * dir[0];
                 const double py = sm.ray[1][tid] + rot * dir[1];
                 const double pz = sm.ray[2][tid] + rot * dir[2];
                 if (!(lox > px || px >= hix || loy > py || py >= hiy || loz > pz || pz >= hiz)) {
-                    done = true; result = full;
+                    done = true;
+                    if (full) fl |= WF_RESULT;
                 }
             }
             if (!done) {
                 // advance to next cube (raytrace.c:712-738)
+                const double pos[3] = {sm.pos[0][tid], sm.pos[1][tid], sm.pos[2][tid]};
                 int ax = 0;
                 double t;
                 if (dirf & 0x11) {
@@ -542,23 +626,25 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                     if (dt < t) { t = dt; ax = 2; }
                 }
 #pragma unroll
-                for (int i = 0; i < 3; i++) pos[i] = pos[i] + dir[i] * t;
+                for (int i = 0; i < 3; i++) sm.pos[i][tid] = pos[i] + dir[i] * t;
                 // step to the neighbour, ascending on overflow (raytrace.c:688-706):
                 // climb while the cell coordinate along ax cannot move that way
                 const bool positive = dirf & (1 << ax);
                 const unsigned ia = ax == 0 ? ix : ax == 1 ? iy : iz;
                 const unsigned blocked = positive ? ia : ~ia;          // trailing ones = levels to climb
                 const int up = (~blocked) ? __ffs(~blocked) - 1 : 32;  // number of trailing one bits
-                if (up >= L) { done = true; result = (robj >= 0); }    // left the scene cube
+                if (up >= L) { done = true; if (ro >= 0) fl |= WF_RESULT; }    // left the scene cube
                 else {
                     ix >>= up; iy >>= up; iz >>= up; L -= up;
-                    size = ldexp(size, up);
                     if (ax == 0) ix ^= 1; else if (ax == 1) iy ^= 1; else iz ^= 1;
                     const int br = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
-                    w = __ldg(&S.nodes[(size_t)sm.stk[L - 1][tid] * 8 + br]);
-                    ws.nodes++;
+                    w = __ldg(&S.nodes[(size_t)stk[(L - 1) * NT + tid] * 8 + br]);
+                    RB_STAT(ws.nodes++;)
+                    sm.cell[0][tid] = ix; sm.cell[1][tid] = iy; sm.cell[2][tid] = iz;
+                    Ld = (Ld & ~0xff) | L;
                 }
             }
+            if (done) fl |= WF_DONE;
         }
     }
 }

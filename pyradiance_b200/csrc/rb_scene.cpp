@@ -1029,8 +1029,17 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
             }
             p += cnt + 1;
         }
-        for (auto& w : fs.nodes) if (w < -1) w = -newoff[-w - 2] - 2;
-        fs.root = sc.root < -1 ? -newoff[-sc.root - 2] - 2 : sc.root;
+        // full-leaf word = -(set offset << 3 | min(count, 7)) - 2: the walker knows how many
+        // surfaces wait in a leaf without a dependent read of the set's count word
+        if (fs.leaf2.size() / 2 >= ((size_t)1 << 27)) { err = "octree has too many leaf-set entries for this engine"; return false; }
+        auto leafword = [&](int w) {
+            const size_t p = (size_t)(-w - 2);
+            const int cnt = sc.leafpool[p];
+            return -((newoff[p] << 3) | std::min(cnt, 7)) - 2;
+        };
+        for (auto& w : fs.nodes) if (w < -1) w = leafword(w);
+        fs.root = sc.root < -1 ? leafword(sc.root) : sc.root;
+        for (int k = 0; k < 8; k++) fs.geom.push_back(0.0);       // records are read 80 bytes at a time
     }
 
     // ---- sources: rt/source.c:46-142 marksources(), srcsupp.c:155-179 ----
