@@ -39,20 +39,20 @@ namespace rb {
     } while (0)
 
 // ------------------------------------------------------------- kernels -----
-__device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws, unsigned nr) {
+#if RB_WALK_STATS
+__device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws) {
     unsigned a = __reduce_add_sync(__activemask(), ws.nodes);
     unsigned b = __reduce_add_sync(__activemask(), ws.leafents);
     unsigned c = __reduce_add_sync(__activemask(), ws.prims);
-    unsigned d = __reduce_add_sync(__activemask(), nr);
     unsigned lane = threadIdx.x & 31;
     unsigned leader = __ffs(__activemask()) - 1;
     if (lane == leader) {
         atomicAdd(&C->nodes, (unsigned long long)a);
         atomicAdd(&C->leafents, (unsigned long long)b);
         atomicAdd(&C->prims, (unsigned long long)c);
-        atomicAdd(&C->nrays, (unsigned long long)d);
     }
 }
+#endif
 
 // Trace: octree walk + intersection only (small code).  Persistent threads:
 // the grid is sized to fill the machine once and every warp pulls rays from
@@ -63,9 +63,10 @@ __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const Wave
     TraceIO io;
     io.qin = A.qin; io.nin = A.nin; io.hits = A.hits; io.next = &A.C->next_ray;
     WalkStats ws = {0, 0, 0};
-    unsigned nretired = 0;
-    walk_rays<WAVE_THREADS>(A.S, io, sm, stk_dyn, ws, nretired, &A.C->errflag, &A.C->errobj);
-    flush_stats(A.C, ws, nretired);
+    walk_rays<WAVE_THREADS>(A.S, io, sm, stk_dyn, ws, &A.C->errflag, &A.C->errobj);
+#if RB_WALK_STATS
+    flush_stats(A.C, ws);
+#endif
 }
 
 // Shade: material evaluation, contribution accumulation, child-ray emission.
@@ -424,6 +425,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
     };
 
     int cur = 0;
+    unsigned long long batch_rays = 0;
     // ---- k_init ----
     {
         InitArgs I;
@@ -484,6 +486,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         k_shade<<<(nq + RB_SHADE_THREADS - 1) / RB_SHADE_THREADS, RB_SHADE_THREADS, 0, stream_>>>(A);
         CK(cudaEventRecord(ev3_, stream_));
         stats.launches += 2; stats.wave_launches++; stats.waves++;
+        batch_rays += nq;                       // every queued ray is traced exactly once
         CK(cudaGetLastError());
         if (!sync_counters(err)) return false;
         {
@@ -507,7 +510,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         else err = "unsupported modifier on " + what + " reached by a ray (patterns/textures/mixtures are not built)";
         return false;
     }
-    stats.nrays += h_cnt_->nrays; stats.nodes += h_cnt_->nodes; stats.leafents += h_cnt_->leafents;
+    stats.nrays += batch_rays; stats.nodes += h_cnt_->nodes; stats.leafents += h_cnt_->leafents;
     stats.prims += h_cnt_->prims; stats.contribs += h_cnt_->contribs; stats.badbin += h_cnt_->badbin;
     // ---- outputs ----
     if (want_c) {

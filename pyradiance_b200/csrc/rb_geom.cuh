@@ -82,54 +82,71 @@ __device__ __forceinline__ bool inface2d(const double* __restrict__ vp, int nv, 
 }
 
 // common/zeroes.c:19-54
-__device__ __forceinline__ int quadratic(double r[2], double a, double b, double c) {
+__device__ __forceinline__ int quadratic(double& r0, double& r1, double a, double b, double c) {
     int first;
+    r0 = r1 = 0.0;
     if (a < -RB_FTINY) first = 1;
     else if (a > RB_FTINY) first = 0;
-    else if (fabs(b) > RB_FTINY) { r[0] = -c / b; return 1; }
+    else if (fabs(b) > RB_FTINY) { r0 = -c / b; return 1; }
     else return 0;
     b *= 0.5;
     double disc = b * b - a * c;
     if (disc < -RB_FTINY * RB_FTINY) return 0;
-    if (disc <= RB_FTINY * RB_FTINY) { r[0] = -b / a; return 1; }
+    if (disc <= RB_FTINY * RB_FTINY) { r0 = -b / a; return 1; }
     disc = sqrt(disc);
-    r[first] = (-b - disc) / a;
-    r[1 - first] = (-b + disc) / a;
+    const double lo = (-b - disc) / a, hi = (-b + disc) / a;
+    if (first) { r1 = lo; r0 = hi; } else { r0 = lo; r1 = hi; }
     return 2;
 }
 
 // Candidate of a polygon: o_face() up to, but not including, rayreject().
-// `tmax` is a conservative upper bound (current rot + a few FTINY).
-__device__ __forceinline__ bool cand_face(int4 hd, const double* __restrict__ g, double2 n01, double2 n2o,
-                                          double2 bx, double2 by, const double org[3],
-                                          const double dir[3], double tmax, double& t, bool& front) {
+// `tmax` is a conservative upper bound (current rot + a few FTINY).  `hot` =
+// kind | projection axis << 4 | exact-rectangle flag << 6 (from the leaf entry);
+// n01/n2o = the plane, box = the polygon's 2-D bounds as floats rounded outward.
+__device__ __forceinline__ bool cand_face(int hot, const double* __restrict__ g, double2 n01, double2 n2o, float4 box,
+                                          const double org[3], const double dir[3], double tmax, double& t,
+                                          bool& front) {
     double rdot = -(dir[0] * n01.x + dir[1] * n01.y + dir[2] * n2o.x);
     if ((rdot <= RB_FTINY) & (rdot >= -RB_FTINY)) return false;
     t = ((org[0] * n01.x + org[1] * n01.y + org[2] * n2o.x) - n2o.y) / rdot;
     if ((t <= RB_FTINY) | (t > tmax)) return false;
     front = rdot > 0;
-    int ax = (hd.x >> 10) & 3;
+    int ax = (hot >> 4) & 3;
     double p0 = org[0] + t * dir[0], p1 = org[1] + t * dir[1], p2 = org[2] + t * dir[2];
     double x = ax == 0 ? p1 : ax == 1 ? p2 : p0;      // xi = (ax+1)%3
     double y = ax == 0 ? p2 : ax == 1 ? p0 : p1;      // yi = (ax+2)%3
-    // 2-D bounding box first: outside by more than FTINY can never be "in"
-    // (no edge straddles y / all straddling edges on one side, and none of
-    // inface()'s three FABSEQ cases can fire); well inside an exact axis-aligned
-    // rectangle is always "in".  Only the FTINY border zone runs the edge loop.
-    if ((x < bx.x - RB_FTINY) | (x > bx.y + RB_FTINY) | (y < by.x - RB_FTINY) | (y > by.y + RB_FTINY)) return false;
-    bool in = ((hd.x >> 12) & 1) && (x > bx.x + RB_FTINY) & (x < bx.y - RB_FTINY) & (y > by.x + RB_FTINY) &
-                                        (y < by.y - RB_FTINY);
-    return in || inface2d(g + 8, (hd.x >> 16) & 0xffff, x, y);
+    // 2-D bounding box first: outside the (outward-rounded, hence larger) box by
+    // more than FTINY can never be "in" (no edge straddles y / all straddling
+    // edges on one side, and none of inface()'s three FABSEQ cases can fire).
+    const double lx = box.x, hx = box.y, ly = box.z, hy = box.w;
+    if ((x < lx - RB_FTINY) | (x > hx + RB_FTINY) | (y < ly - RB_FTINY) | (y > hy + RB_FTINY)) return false;
+    // Well inside an exact axis-aligned rectangle is always "in".  The float
+    // bounds are within one float ulp (<= 1.2e-7 |v|) of the exact ones, so the
+    // margin below implies "inside the exact rectangle by more than FTINY".
+    // Only the border zone runs the edge loop.
+    if (hot & 0x40) {
+        const double ulp = 1.2e-7;
+        if ((x > lx + (RB_FTINY + 1e-30 + ulp * fabs(lx))) & (x < hx - (RB_FTINY + 1e-30 + ulp * fabs(hx))) &
+            (y > ly + (RB_FTINY + 1e-30 + ulp * fabs(ly))) & (y < hy - (RB_FTINY + 1e-30 + ulp * fabs(hy))))
+            return true;
+    }
+    const int nv = (__ldg(reinterpret_cast<const int*>(g - 2)) >> 16) & 0xffff;
+    return inface2d(g + 6, nv, x, y);
 }
 
 // Candidate of a sphere / cone-family surface (rare kinds, kept out of line).
 // Returns the single root the reference could accept: the first root > FTINY
 // (sphere.c:60-66) / the first root > FTINY within the end caps (o_cone.c:98-110)
-// / the ring's plane hit within its radii (o_cone.c:71-83).
-__device__ __noinline__ bool cand_other(int kind, const double* __restrict__ g, const double org[3],
-                                        const double dir[3], double tmax, double& t, bool& front) {
+// / the ring's plane hit within its radii (o_cone.c:71-83); as +t for a
+// front-facing candidate, -t for a back-facing one, 0 for none.  Everything
+// travels by value: reference arguments of a __noinline__ function live in
+// local memory, which showed up as 200 M L1 sectors per launch.
+__device__ __noinline__ double cand_other(int kind, const double* __restrict__ g, double ox, double oy, double oz,
+                                          double dx, double dy, double dz, double tmax) {
+    const double org[3] = {ox, oy, oz}, dir[3] = {dx, dy, dz};
     if (kind == PK_SPHERE || kind == PK_BUBBLE) {
-        double a = 0, b = 0, c = 0, root[2];
+        double a = 0, b = 0, c = 0;
+#pragma unroll
         for (int i = 0; i < 3; i++) {
             a += dir[i] * dir[i];
             double d = org[i] - g[i];
@@ -137,13 +154,15 @@ __device__ __noinline__ bool cand_other(int kind, const double* __restrict__ g, 
             c += d * d;
         }
         c -= g[3] * g[3];
-        int nroots = quadratic(root, a, b, c);
-        int i;
-        for (i = 0; i < nroots; i++)
-            if ((t = root[i]) > RB_FTINY) break;
-        if (i >= nroots || t > tmax) return false;
-        front = (1 - 2 * ((i > 0) ^ (kind == PK_BUBBLE))) > 0;
-        return true;
+        double r0, r1;
+        const int nroots = quadratic(r0, r1, a, b, c);
+        double t; int i;
+        if (nroots >= 1 && r0 > RB_FTINY) { t = r0; i = 0; }
+        else if (nroots >= 2 && r1 > RB_FTINY) { t = r1; i = 1; }
+        else return 0.0;
+        if (t > tmax) return 0.0;
+        const bool front = (1 - 2 * ((i > 0) ^ (kind == PK_BUBBLE))) > 0;
+        return front ? t : -t;
     }
     if (kind >= PK_CONE && kind <= PK_RING) {
         const double* ad = g; double al = g[3];
@@ -151,12 +170,13 @@ __device__ __noinline__ bool cand_other(int kind, const double* __restrict__ g, 
         double r0 = g[8], r1 = g[9];
         const double* tm = g + 12;       // tm[i][j] at tm[i*3+j], i = 0..3
         double rox[3], rdx[3];
+#pragma unroll
         for (int j = 0; j < 3; j++) {
             rdx[j] = dir[0] * tm[0 + j] + dir[1] * tm[3 + j] + dir[2] * tm[6 + j];
             rox[j] = org[0] * tm[0 + j] + org[1] * tm[3 + j] + org[2] * tm[6 + j];
             rox[j] += tm[9 + j];
         }
-        double a, b, c, root[2];
+        double a, b, c;
         if (kind == PK_CONE || kind == PK_CUP) {
             a = rdx[0] * rdx[0] + rdx[1] * rdx[1] - rdx[2] * rdx[2];
             b = 2.0 * (rdx[0] * rox[0] + rdx[1] * rox[1] - rdx[2] * rox[2]);
@@ -166,31 +186,34 @@ __device__ __noinline__ bool cand_other(int kind, const double* __restrict__ g, 
             b = 2.0 * (rdx[0] * rox[0] + rdx[1] * rox[1]);
             c = rox[0] * rox[0] + rox[1] * rox[1] - r0 * r0;
         } else {  // ring
-            if ((rdx[2] <= RB_FTINY) & (rdx[2] >= -RB_FTINY)) return false;
-            t = -rox[2] / rdx[2];
-            if ((t <= RB_FTINY) | (t > tmax)) return false;
+            if ((rdx[2] <= RB_FTINY) & (rdx[2] >= -RB_FTINY)) return 0.0;
+            const double t = -rox[2] / rdx[2];
+            if ((t <= RB_FTINY) | (t > tmax)) return 0.0;
             b = t * rdx[0] + rox[0];
             c = t * rdx[1] + rox[1];
             a = b * b + c * c;
-            if (a > r1 * r1 || a < r0 * r0) return false;
-            front = -rdx[2] > 0;
-            return true;
+            if (a > r1 * r1 || a < r0 * r0) return 0.0;
+            return (-rdx[2] > 0) ? t : -t;
         }
-        int nroots = quadratic(root, a, b, c);
-        for (int rn = 0; rn < nroots; rn++) {
-            if (root[rn] <= RB_FTINY) continue;
-            if (root[rn] > tmax) break;
-            double dx[3];
-            for (int k = 0; k < 3; k++) dx[k] = (org[k] + root[rn] * dir[k]) - p0[k];
-            b = dot3(dx, ad);
+        double q0, q1;
+        const int nroots = quadratic(q0, q1, a, b, c);
+#pragma unroll
+        for (int rn = 0; rn < 2; rn++) {
+            if (rn >= nroots) break;
+            const double root = rn ? q1 : q0;
+            if (root <= RB_FTINY) continue;
+            if (root > tmax) break;
+            double dx3[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) dx3[k] = (org[k] + root * dir[k]) - p0[k];
+            b = dot3(dx3, ad);
             if (b < 0.0) continue;
             if (b > al) continue;
-            t = root[rn];
-            front = (1 - 2 * ((rn > 0) ^ ((kind == PK_CUP) | (kind == PK_TUBE)))) > 0;
-            return true;
+            const bool front = (1 - 2 * ((rn > 0) ^ ((kind == PK_CUP) | (kind == PK_TUBE)))) > 0;
+            return front ? root : -root;
         }
     }
-    return false;
+    return 0.0;
 }
 
 // Hit point, surface normal and rod = -rdir.ron of an accepted hit, computed
@@ -271,6 +294,7 @@ struct WalkSmem {
     unsigned cell[3][NT];        // integer coordinates of the current cube at its level
     int robj[NT];                // current best object << 1 | front-facing, or -1
     unsigned ridx[NT];           // queue slot of the ray
+    int lvl[NT];                 // level of the current cube | direction flags << 8
     unsigned pair[NT / 32][RB_PAIRS];   // (ray, surface) pairs of this round: leaf-set entry << 5 | owner lane
     int ndef[NT / 32];           // deferred (non-polygon) pairs of this round
     unsigned short defer[NT / 32][RB_PAIRS];   // their pair indices
@@ -280,23 +304,26 @@ struct WalkSmem {
 
 // One (ray, surface) pair: polygon candidates are computed here, the rare
 // other kinds are queued for the warp's second pass.
+#define RB_ENT_ID(e) ((e) & 0x1ffffff)
+#define RB_ENT_HOT(e) ((int)((unsigned)(e) >> 25))
 template <int NT>
 __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, unsigned wid, int p, unsigned own,
-                                          int2 ent, const double* __restrict__ g, int4 hd, double2 n01, double2 n2o,
-                                          double2 bx, double2 by, unsigned* errflag, unsigned* errobj) {
-    const int kind = hd.x & 0xff;
+                                          int2 ent, const double* __restrict__ g, double2 n01, double2 n2o,
+                                          float4 box, unsigned* errflag, unsigned* errobj) {
+    const int hot = RB_ENT_HOT(ent.x);
+    const int kind = hot & 0xf;
     if (kind == PK_FACE) {
         const double org[3] = {sm.ray[0][own], sm.ray[1][own], sm.ray[2][own]};
         const double rd[3] = {sm.ray[3][own], sm.ray[4][own], sm.ray[5][own]};
         const double tmax = sm.rot[own] + 8 * RB_FTINY;      // ties may raise rot by < FTINY each
         double t = 0;
         bool fr = true;
-        const bool ok = cand_face(hd, g, n01, n2o, bx, by, org, rd, tmax, t, fr);
+        const bool ok = cand_face(hot, g, n01, n2o, box, org, rd, tmax, t, fr);
         sm.ct[wid][p] = t;
-        sm.cid[wid][p] = ok ? ((ent.x << 1) | (int)fr) : -1;
+        sm.cid[wid][p] = ok ? ((RB_ENT_ID(ent.x) << 1) | (int)fr) : -1;
     } else {                         // rare kinds: second pass, again with all lanes
         sm.cid[wid][p] = -1;
-        if (kind == PK_UNSUPPORTED) { atomicOr(errflag, RB_ERR_UNSUP_PRIM); *errobj = (unsigned)ent.x; }
+        if (kind == PK_UNSUPPORTED) { atomicOr(errflag, RB_ERR_UNSUP_PRIM); *errobj = (unsigned)RB_ENT_ID(ent.x); }
         else if (kind != PK_NONE) sm.defer[wid][atomicAdd(&sm.ndef[wid], 1)] = (unsigned short)p;
     }
 }
@@ -329,20 +356,21 @@ __device__ __forceinline__ double cube_size(double cs, int L) {
 // Registers carry only what a phase is working on: between phases a lane's
 // state is {flags, node word, level} plus the shared-memory columns above.
 // MUST be called by all threads of the CTA.
-enum : unsigned { WF_HAVE = 1, WF_DONE = 2, WF_RESULT = 4, WF_AFT = 8 };
+enum : unsigned { WF_HAVE = 1, WF_DONE = 2, WF_RESULT = 4, WF_AFT = 8, WF_EXHAUSTED = 16 };
 
 template <int NT>
 __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, WalkSmem<NT>& sm, int* __restrict__ stk,
-                                          WalkStats& ws,
-                                          unsigned& nretired, unsigned* errflag, unsigned* errobj) {
+                                          WalkStats& ws, unsigned* errflag, unsigned* errobj) {
     const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     const double cs = S.cusize;
     const int2* __restrict__ pool = reinterpret_cast<const int2*>(S.leafpool);
     unsigned fl = WF_DONE;       // WF_* flags of this lane's ray
-    int w = -1;                  // node word of the current cube
-    int Ld = 0;                  // level of the current cube | direction flags << 8
-    bool exhausted = false;
+    // cube the ray stands in: set by the refill or by phase C, consumed by phase A
+    // (registers only between those two; parked in shared memory across phase B)
+    unsigned ix = 0, iy = 0, iz = 0;
+    int w = -1, Ld = 0;          // node word; level | direction flags << 8
+    double px = 0, py = 0, pz = 0;
     for (;;) {
         // ---- retire finished rays ----
         if ((fl & (WF_HAVE | WF_DONE)) == (WF_HAVE | WF_DONE)) {
@@ -361,18 +389,17 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
             }
             io.hits[ridx] = o;
             fl &= ~WF_HAVE;
-            nretired++;
         }
         // ---- refill idle lanes ----
         const unsigned idle = __ballot_sync(FULL, !(fl & WF_HAVE));
-        if (idle == FULL && exhausted) break;
-        if (!exhausted && (__popc(idle) >= RB_FETCH_MIN)) {
+        if (idle == FULL && (fl & WF_EXHAUSTED)) break;
+        if (!(fl & WF_EXHAUSTED) && (__popc(idle) >= RB_FETCH_MIN)) {
             const int n = __popc(idle);
             const int leader = __ffs(idle) - 1;
             unsigned base = 0;
             if ((int)lane == leader) base = atomicAdd(io.next, (unsigned)n);
             base = __shfl_sync(FULL, base, leader);
-            if (base + n >= io.nin) exhausted = true;
+            const bool last = base + n >= io.nin;
             const unsigned my = base + __popc(idle & ((1u << lane) - 1));
             if (!(fl & WF_HAVE) && my < io.nin) {
                 const double2* q2 = reinterpret_cast<const double2*>(&io.qin[my]);
@@ -394,7 +421,7 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 }
                 double rot = RB_FHUGE;
                 bool done = !dirf;
-                fl = WF_HAVE;
+                fl = WF_HAVE;          // (queue-exhausted bit is set again below)
                 if (!done && rmax > RB_FTINY) { fl |= WF_AFT; rot = rmax; }
                 if (!done) {
                     bool in = !(S.cuorg[0] > pos[0] || pos[0] >= S.cuorg[0] + cs ||
@@ -424,20 +451,20 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                     }
                 }
                 if (done) fl |= WF_DONE;
-                sm.pos[0][tid] = pos[0]; sm.pos[1][tid] = pos[1]; sm.pos[2][tid] = pos[2];
+                px = pos[0]; py = pos[1]; pz = pos[2];
+                sm.pos[0][tid] = px; sm.pos[1][tid] = py; sm.pos[2][tid] = pz;
                 sm.rot[tid] = rot;
                 sm.robj[tid] = -1;
-                sm.cell[0][tid] = 0; sm.cell[1][tid] = 0; sm.cell[2][tid] = 0;
+                ix = iy = iz = 0;
                 w = S.root; Ld = dirf << 8;
             }
+            if (last) fl |= WF_EXHAUSTED;
         }
         __syncwarp();
         bool act = (fl & (WF_HAVE | WF_DONE)) == WF_HAVE;
         // ---- phase A: descend towards a leaf (raymove, raytrace.c:668-687); at most
         //      RB_DITERS levels per round ----
-        if (__any_sync(FULL, act & (w >= 0))) {
-            unsigned ix = sm.cell[0][tid], iy = sm.cell[1][tid], iz = sm.cell[2][tid];
-            const double px = sm.pos[0][tid], py = sm.pos[1][tid], pz = sm.pos[2][tid];
+        {
             int L = Ld & 0xff;
             double size = cube_size(cs, L);
 #pragma unroll 1
@@ -460,8 +487,9 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                     size = half; L++;
                 }
             }
-            sm.cell[0][tid] = ix; sm.cell[1][tid] = iy; sm.cell[2][tid] = iz;
             Ld = (Ld & ~0xff) | L;
+            sm.cell[0][tid] = ix; sm.cell[1][tid] = iy; sm.cell[2][tid] = iz;
+            sm.lvl[tid] = Ld;
         }
         act &= (w < 0);                          // still inside the tree: continue next round
         const bool full = act & (w < -1);
@@ -503,12 +531,12 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 const double* gB = S.geom + entB.y;
                 const double2* gA2 = reinterpret_cast<const double2*>(gA);
                 const double2* gB2 = reinterpret_cast<const double2*>(gB);
-                const int4 hdA = __ldg(reinterpret_cast<const int4*>(gA - 2));
-                const double2 a0 = __ldg(&gA2[0]), a1 = __ldg(&gA2[1]), a2 = __ldg(&gA2[2]), a3 = __ldg(&gA2[3]);
-                const int4 hdB = __ldg(reinterpret_cast<const int4*>(gB - 2));
-                const double2 b0 = __ldg(&gB2[0]), b1 = __ldg(&gB2[1]), b2 = __ldg(&gB2[2]), b3 = __ldg(&gB2[3]);
-                pair_test(S, sm, wid, p, ownA, entA, gA, hdA, a0, a1, a2, a3, errflag, errobj);
-                if (two) pair_test(S, sm, wid, pb, ownB, entB, gB, hdB, b0, b1, b2, b3, errflag, errobj);
+                const double2 a0 = __ldg(&gA2[0]), a1 = __ldg(&gA2[1]);
+                const float4 a2 = __ldg(reinterpret_cast<const float4*>(gA + 4));
+                const double2 b0 = __ldg(&gB2[0]), b1 = __ldg(&gB2[1]);
+                const float4 b2 = __ldg(reinterpret_cast<const float4*>(gB + 4));
+                pair_test(S, sm, wid, p, ownA, entA, gA, a0, a1, a2, errflag, errobj);
+                if (two) pair_test(S, sm, wid, pb, ownB, entB, gB, b0, b1, b2, errflag, errobj);
             }
 #else
             for (int p = lane; p < total; p += 32) {
@@ -516,11 +544,11 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 const unsigned own = wbase + (pr & 31);
                 const int2 ent = __ldg(&pool[pr >> 5]);
                 const double* g = S.geom + ent.y;
-                // header, plane and 2-D box of the record in one go (one latency, not three)
+                // plane and 2-D box of the record in one go (one latency): 48 contiguous bytes
                 const double2* g2 = reinterpret_cast<const double2*>(g);
-                const int4 hd = __ldg(reinterpret_cast<const int4*>(g - 2));
-                const double2 n01 = __ldg(&g2[0]), n2o = __ldg(&g2[1]), bx = __ldg(&g2[2]), by = __ldg(&g2[3]);
-                pair_test(S, sm, wid, p, own, ent, g, hd, n01, n2o, bx, by, errflag, errobj);
+                const double2 n01 = __ldg(&g2[0]), n2o = __ldg(&g2[1]);
+                const float4 box = __ldg(reinterpret_cast<const float4*>(g + 4));
+                pair_test(S, sm, wid, p, own, ent, g, n01, n2o, box, errflag, errobj);
             }
 #endif
             __syncwarp();
@@ -531,14 +559,12 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 const unsigned own = wbase + (pr & 31);
                 const int2 ent = __ldg(&pool[pr >> 5]);
                 const double* g = S.geom + ent.y;
-                const int kind = __ldg(reinterpret_cast<const int4*>(g - 2)).x & 0xff;
-                const double org[3] = {sm.ray[0][own], sm.ray[1][own], sm.ray[2][own]};
-                const double rd[3] = {sm.ray[3][own], sm.ray[4][own], sm.ray[5][own]};
-                double t = 0;
-                bool fr = true;
-                if (cand_other(kind, g, org, rd, sm.rot[own] + 8 * RB_FTINY, t, fr)) {
-                    sm.ct[wid][p] = t;
-                    sm.cid[wid][p] = (ent.x << 1) | (int)fr;
+                const int kind = RB_ENT_HOT(ent.x) & 0xf;
+                const double t = cand_other(kind, g, sm.ray[0][own], sm.ray[1][own], sm.ray[2][own], sm.ray[3][own],
+                                            sm.ray[4][own], sm.ray[5][own], sm.rot[own] + 8 * RB_FTINY);
+                if (t != 0.0) {
+                    sm.ct[wid][p] = fabs(t);
+                    sm.cid[wid][p] = (RB_ENT_ID(ent.x) << 1) | (int)(t > 0.0);
                 }
             }
             __syncwarp();
@@ -583,7 +609,8 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
         }
         // ---- phase C: accept (checkhit / aft plane), else step to the neighbour cube ----
         if (act) {
-            unsigned ix = sm.cell[0][tid], iy = sm.cell[1][tid], iz = sm.cell[2][tid];
+            ix = sm.cell[0][tid]; iy = sm.cell[1][tid]; iz = sm.cell[2][tid];
+            Ld = sm.lvl[tid];
             int L = Ld & 0xff;
             const int dirf = Ld >> 8;
             const double size = cube_size(cs, L);
@@ -625,8 +652,8 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                     dt = (dt - pos[2]) / dir[2];
                     if (dt < t) { t = dt; ax = 2; }
                 }
-#pragma unroll
-                for (int i = 0; i < 3; i++) sm.pos[i][tid] = pos[i] + dir[i] * t;
+                px = pos[0] + dir[0] * t; py = pos[1] + dir[1] * t; pz = pos[2] + dir[2] * t;
+                sm.pos[0][tid] = px; sm.pos[1][tid] = py; sm.pos[2][tid] = pz;
                 // step to the neighbour, ascending on overflow (raytrace.c:688-706):
                 // climb while the cell coordinate along ax cannot move that way
                 const bool positive = dirf & (1 << ax);
@@ -640,7 +667,6 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                     const int br = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
                     w = __ldg(&S.nodes[(size_t)stk[(L - 1) * NT + tid] * 8 + br]);
                     RB_STAT(ws.nodes++;)
-                    sm.cell[0][tid] = ix; sm.cell[1][tid] = iy; sm.cell[2][tid] = iz;
                     Ld = (Ld & ~0xff) | L;
                 }
             }

@@ -761,18 +761,28 @@ static void flatten_face(const Object& o, FlatScene& fs, int32_t hdr[4], std::st
     }
     if (nv > 65535) { hdr[0] = PK_UNSUPPORTED; warn = "too many vertices"; return; }
     int xi = (ax + 1) % 3, yi = (xi + 1) % 3;
-    // record: plane (4), 2-D bounding box xmin xmax ymin ymax (4), vertices (2 each)
-    size_t off = geom_alloc(fs, 8 + 2 * (size_t)nv);
+    // record: plane (4 doubles), 2-D bounding box xmin xmax ymin ymax as 4 floats rounded
+    // OUTWARD (2 doubles' worth; a conservative reject only), vertices (2 doubles each)
+    size_t off = geom_alloc(fs, 6 + 2 * (size_t)nv);
     double* g = &fs.geom[off];
     g[0] = norm[0]; g[1] = norm[1]; g[2] = norm[2]; g[3] = offset;
     double bb[4] = {1e300, -1e300, 1e300, -1e300};
     for (int i = 0; i < nv; i++) {
         double x = V(i)[xi], y = V(i)[yi];
-        g[8 + 2 * i] = x; g[9 + 2 * i] = y;
+        g[6 + 2 * i] = x; g[7 + 2 * i] = y;
         bb[0] = std::min(bb[0], x); bb[1] = std::max(bb[1], x);
         bb[2] = std::min(bb[2], y); bb[3] = std::max(bb[3], y);
     }
-    for (int k = 0; k < 4; k++) g[4 + k] = bb[k];
+    {
+        float fb[4];
+        for (int k = 0; k < 4; k++) {
+            float f = (float)bb[k];
+            if (!(k & 1) && (double)f > bb[k]) f = nextafterf(f, -INFINITY);      // lower bounds round down
+            if ((k & 1) && (double)f < bb[k]) f = nextafterf(f, INFINITY);        // upper bounds round up
+            fb[k] = f;
+        }
+        memcpy(&g[4], fb, 16);
+    }
     // exact axis-aligned rectangle in the projection plane? (fast inside test)
     int rect = 0;
     if (nv == 4 && area != 0.0) {
@@ -1024,13 +1034,18 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
             for (int k = 1; k <= cnt; k++) {
                 int id = sc.leafpool[p + k];
                 if (id < 0 || id >= n) { err = "octree refers to object " + std::to_string(id) + " outside the scene"; return false; }
-                fs.leaf2.push_back(id);
+                // entry = object id | hot bits << 25 (kind, projection axis, rectangle flag), record offset:
+                // what the walker needs to pick the test without touching the object header
+                const int h0 = fs.objhdr[(size_t)id * 4];
+                const int hot = (h0 & 0xf) | (((h0 >> 10) & 3) << 4) | (((h0 >> 12) & 1) << 6);
+                fs.leaf2.push_back(id | (hot << 25));
                 fs.leaf2.push_back(fs.objhdr[(size_t)id * 4 + 3]);
             }
             p += cnt + 1;
         }
         // full-leaf word = -(set offset << 3 | min(count, 7)) - 2: the walker knows how many
         // surfaces wait in a leaf without a dependent read of the set's count word
+        if (n >= (1 << 25)) { err = "scene has too many objects for this engine (2^25)"; return false; }
         if (fs.leaf2.size() / 2 >= ((size_t)1 << 27)) { err = "octree has too many leaf-set entries for this engine"; return false; }
         auto leafword = [&](int w) {
             const size_t p = (size_t)(-w - 2);
