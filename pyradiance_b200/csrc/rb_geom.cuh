@@ -219,7 +219,7 @@ __device__ __noinline__ double cand_other(int kind, const double* __restrict__ g
 // Hit point, surface normal and rod = -rdir.ron of an accepted hit, computed
 // once per ray by the shading kernel with the reference's expressions
 // (o_face.c:52-56, sphere.c:72-78, o_cone.c:84-138).
-__device__ __noinline__ void hit_frame(const DScene& S, int robj, double rot, const double org[3],
+__device__ __forceinline__ void hit_frame(const DScene& S, int robj, double rot, const double org[3],
                                        const double dir[3], double rop[3], double ron[3], double& rod) {
     for (int k = 0; k < 3; k++) rop[k] = org[k] + rot * dir[k];
     int4 hd = __ldg(&S.objhdr[robj]);

@@ -96,7 +96,7 @@ __device__ __forceinline__ unsigned reserve_slot(unsigned* ctr) {
 
 // raytrace.c:39-135.  `rc` is the child's coefficient w.r.t. the parent (may be
 // rescaled by Russian roulette); has_rc=false stands for rc==NULL.
-__device__ bool rayorigin(const DParams& P, RayCtx& par, int rt, float rc[3], bool has_rc, QRay& q) {
+__device__ __forceinline__ bool rayorigin(const DParams& P, RayCtx& par, int rt, float rc[3], bool has_rc, QRay& q) {
     float rw = 1.0f;
     if (has_rc) { rw = max3(rc); if (rw > 1.0f) rw = 1.0f; }
     else rc[0] = rc[1] = rc[2] = 1.0f;
@@ -290,7 +290,7 @@ struct DirectJob { RayCtx r; NormDat nd; };
 enum : int { SP_REFL = 01, SP_TRAN = 02, SP_PURE = 04, SP_FLAT = 010, SP_RBLT = 020, SP_TBLT = 040 };
 
 // normal.c:71-173
-__device__ void dirnorm(float scval[3], const NormDat& np, const RayCtx& r, const double ldir[3],
+__device__ __forceinline__ void dirnorm(float scval[3], const NormDat& np, const RayCtx& r, const double ldir[3],
                         double omega, double dstrsrc) {
     scval[0] = scval[1] = scval[2] = 0.f;
     double ldot = dot3(np.pnorm, ldir);
@@ -380,7 +380,7 @@ __device__ __forceinline__ void direct_one(const WaveArgs& A, const RayCtx& r, c
     push_ray(A, q);
 }
 
-__device__ void direct(const WaveArgs& A, RayCtx& r, const NormDat& nd) {
+__device__ __forceinline__ void direct(const WaveArgs& A, RayCtx& r, const NormDat& nd) {
     const int ns = A.S.nsrcs;
     for (int sn = 0; sn < ns; sn++) direct_one(A, r, nd, sn, r.nchild);
     r.nchild += (unsigned)ns;
@@ -405,7 +405,7 @@ __device__ __forceinline__ void direct_or_park(const WaveArgs& A, RayCtx& r, con
 }
 
 // ambient.c:229-297 (aa = 0 branch) + ambcomp.c:350-422
-__device__ void multambient(const WaveArgs& A, RayCtx& r, const float aval[3], const double nrm[3]) {
+__device__ __forceinline__ void multambient(const WaveArgs& A, RayCtx& r, const float aval[3], const double nrm[3]) {
     const DParams& P = A.P;
     bool dumb = (P.ambdiv <= 0) | (r.rdepth >= P.ambounce);
     float d = max3(aval);
@@ -461,7 +461,7 @@ __device__ void multambient(const WaveArgs& A, RayCtx& r, const float aval[3], c
 }
 
 // raytrace.c:196-207 raytrans(): continue the ray unchanged
-__device__ void raytrans(const WaveArgs& A, RayCtx& r) {
+__device__ __forceinline__ void raytrans(const WaveArgs& A, RayCtx& r) {
     QRay q; float rc[3];
     if (!rayorigin(A.P, r, RT_TRANS, rc, false, q)) return;
     q.dir[0] = r.dir[0]; q.dir[1] = r.dir[1]; q.dir[2] = r.dir[2];
@@ -469,7 +469,7 @@ __device__ void raytrans(const WaveArgs& A, RayCtx& r) {
 }
 
 // normal.c:176-360.  a[] = material reals; mkind = MK_PLASTIC / MK_METAL / MK_TRANS.
-__device__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind, const float* a) {
+__device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind, const float* a) {
     const DParams& P = A.P;
     if ((r.crtype & RT_SHADOW) && mkind != MK_TRANS) return;      // easy shadow test
     if (r.rod < 0.0) {
@@ -599,7 +599,7 @@ __device__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind, const float* a
 }
 
 // glass.c:46-165
-__device__ void m_glass(const WaveArgs& A, RayCtx& r, const float* a, int nargs) {
+__device__ __forceinline__ void m_glass(const WaveArgs& A, RayCtx& r, const float* a, int nargs) {
     const DParams& P = A.P;
     double rindex = (nargs == 4) ? (double)a[3] : 1.52;
     if (!P.backvis && r.rod <= 0.0) { raytrans(A, r); return; }
@@ -647,7 +647,7 @@ __device__ void m_glass(const WaveArgs& A, RayCtx& r, const float* a, int nargs)
 
 // source.c:749-793 m_light.  Returns 1 and sets rcol when the ray sees the
 // emitter, 0 when its coefficient is zeroed / it is passed on.
-__device__ int m_light(const WaveArgs& A, RayCtx& r, const MatRec& m, float rcol[3], bool& zeroed) {
+__device__ __forceinline__ int m_light(const WaveArgs& A, RayCtx& r, const MatRec& m, float rcol[3], bool& zeroed) {
     const DScene& S = A.S;
     zeroed = false;
     bool isglow = (m.kind == MK_GLOW);
@@ -682,7 +682,7 @@ __device__ int m_light(const WaveArgs& A, RayCtx& r, const MatRec& m, float rcol
 }
 
 // rayshade() + trace callback for one traced ray (raytrace.c:162-179,210-256)
-__device__ void shade_ray(const WaveArgs& A, RayCtx& r) {
+__device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
     const DScene& S = A.S;
     int4 hd = __ldg(&S.objhdr[r.robj]);
     int ms = hd.z;
@@ -695,7 +695,8 @@ __device__ void shade_ray(const WaveArgs& A, RayCtx& r) {
     }
     const MatRec* m = &S.mats[ms];
     bool tst_irrad = A.P.do_irrad && !(r.crtype & ~(RT_PRIMARY | RT_TRANS));
-    const float lamb[5] = {(float)RB_PI, (float)RB_PI, (float)RB_PI, 0.f, 0.f};
+    int nk = -1;                        // m_normal() material kind and reals, when that is what shades the ray
+    float na[7];
     for (int guard = 0; guard < 8; guard++) {
         int k = m->kind;
         if (k == MK_UNSUPPORTED || ((m->flags & 1) && !(k >= MK_LIGHT && k <= MK_SPOT)) || (m->flags & 2)) {
@@ -705,9 +706,9 @@ __device__ void shade_ray(const WaveArgs& A, RayCtx& r) {
         }
         if (tst_irrad) {                // raytirrad(), raytrace.c:210-228
             if (k == MK_TRANS || k == MK_GLASS) { raytrans(A, r); break; }
-            if (!(k >= MK_LIGHT && k <= MK_SPOT)) { m_normal(A, r, MK_PLASTIC, lamb); break; }
+            if (!(k >= MK_LIGHT && k <= MK_SPOT)) { nk = MK_PLASTIC; for (int j = 0; j < 7; j++) na[j] = j < 3 ? (float)RB_PI : 0.f; break; }
         }
-        if (k == MK_PLASTIC || k == MK_METAL || k == MK_TRANS) { m_normal(A, r, k, m->a); break; }
+        if (k == MK_PLASTIC || k == MK_METAL || k == MK_TRANS) { nk = k; for (int j = 0; j < 7; j++) na[j] = m->a[j]; break; }
         if (k == MK_GLASS) { m_glass(A, r, m->a, m->nargs); break; }
         int rv = m_light(A, r, *m, rcol, zeroed);
         if (rv == 1) {
@@ -719,6 +720,7 @@ __device__ void shade_ray(const WaveArgs& A, RayCtx& r) {
         }
         break;
     }
+    if (nk >= 0) m_normal(A, r, nk, na);
     trace_contrib(A, r, zeroed, rcol, have_rcol);
 }
 
