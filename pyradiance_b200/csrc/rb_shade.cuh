@@ -229,6 +229,26 @@ __device__ __forceinline__ void add_value(const WaveArgs& A, unsigned row, const
     atomicAdd(v + 2, (double)(c[2] * b));
 }
 
+// Bin function + accumulation of one contribution.  Out of line on purpose: one
+// ray in a hundred gets here, and the bin functions (asin/acos/atan2 in double)
+// are 30 % of k_shade's SASS -- kept out of the hot path's instruction stream.
+// (Scalars by value: reference arguments of a real call live in local memory.
+// Moving m_glass / gaussamp / raytrans out of line the same way made k_shade 70 %
+// SLOWER -- they take the whole RayCtx by reference.)
+__device__ __noinline__ void add_contrib(const DBinSpec* b, double* row, DCounters* C, double dx, double dy,
+                                         double dz, float c0, float c1, float c2) {
+    const double D[3] = {dx, dy, dz};
+    double bval = rb_eval_bin(*b, D);
+    if (bval <= -.5) return;
+    int bn = (int)(bval + .5);
+    if (bn >= b->nbins) { atomicAdd(&C->badbin, 1u); return; }
+    double* d = row + (size_t)(b->col0 + bn) * 3;
+    atomicAdd(d + 0, (double)c0);
+    atomicAdd(d + 1, (double)c1);
+    atomicAdd(d + 2, (double)c2);
+    atomicAdd(&C->contribs, 1ULL);
+}
+
 // rcontrib.c:272-317.  `rcoef_ok`: the ray's own coefficient was not zeroed by
 // its material; rcol = the ray's returned radiance (emitters only).
 __device__ __forceinline__ void trace_contrib(const WaveArgs& A, const RayCtx& r, bool rcoef_zeroed,
@@ -247,16 +267,8 @@ __device__ __forceinline__ void trace_contrib(const WaveArgs& A, const RayCtx& r
         // reference tests rcoef*rcol of the ray itself; the chain product has the same zero set
         if (!(c[0] > 0.f || c[1] > 0.f || c[2] > 0.f)) return;
     }
-    const DBinSpec& b = A.bins[slot];
-    double bval = rb_eval_bin(b, r.dir);
-    if (bval <= -.5) return;
-    int bn = (int)(bval + .5);
-    if (bn >= b.nbins) { atomicAdd(&A.C->badbin, 1u); return; }
-    double* d = A.acc + ((size_t)(r.row - A.row0) * A.ncols + b.col0 + bn) * 3;
-    atomicAdd(d + 0, (double)c[0]);
-    atomicAdd(d + 1, (double)c[1]);
-    atomicAdd(d + 2, (double)c[2]);
-    atomicAdd(&A.C->contribs, 1ULL);
+    add_contrib(A.bins + slot, A.acc + (size_t)(r.row - A.row0) * A.ncols * 3, A.C, r.dir[0], r.dir[1], r.dir[2],
+                c[0], c[1], c[2]);
 }
 
 // ----------------------------------------------------------- sources -------
