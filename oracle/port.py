@@ -19,7 +19,7 @@ class orc_params(C.Structure):
     _fields_ = [("ambounce", C.c_int), ("ambdiv", C.c_int), ("maxdepth", C.c_int), ("backvis", C.c_int),
                 ("directvis", C.c_int), ("do_irrad", C.c_int), ("minweight", C.c_double), ("dstrsrc", C.c_double),
                 ("specthresh", C.c_double), ("specjitter", C.c_double), ("ambval", C.c_double * 3),
-                ("contrib", C.c_int), ("seed", C.c_uint64)]
+                ("contrib", C.c_int), ("seed", C.c_uint64), ("srcsizerat", C.c_double)]
 
 
 RESULT_DTYPE = np.dtype([("rop", "<f8", 3), ("ron", "<f8", 3), ("rot", "<f8"), ("rod", "<f8"),

@@ -68,7 +68,11 @@ typedef struct {
     int bad;                 /* unsupported / malformed */
 } OBJ;
 
-typedef struct { double sloc[3], ss2, ss[3][3]; int so, skip, distant; } SRC;
+typedef struct {
+    double sloc[3], ss2, ss[3][3], srad;      /* ss[2] doubles as snorm for flat sources (source.h:88) */
+    int so, skip, distant, flat, cyl, cir, prox_on, spot_on;
+    double prox, spot_siz, spot_aim[3], spot_flen;
+} SRC;
 
 typedef struct { char* name; int fn, mf, nbins, col0; double n[3], u[3], rhs; } MOD;
 
@@ -303,6 +307,15 @@ static int getperp0(double* vp, const double* v) {      /* getperpendicular(rand
     return normalize(vp) > 0.0;
 }
 
+static int inface(const double* p, const OBJ* f);
+/* fvect.c dist2line(): squared distance from p to the line through ep1, ep2 */
+static double dist2line(const double* p, const double* ep1, const double* ep2) {
+    double d, d1, d2; int k;
+    d = d1 = d2 = 0;
+    for (k = 0; k < 3; k++) { d += (ep1[k] - ep2[k]) * (ep1[k] - ep2[k]); d1 += (ep1[k] - p[k]) * (ep1[k] - p[k]); d2 += (ep2[k] - p[k]) * (ep2[k] - p[k]); }
+    return d1 - 0.25 * (d + d1 - d2) * (d + d1 - d2) / d;
+}
+
 static void mark_sources(orc_scene* s) {
     int i, k;
     for (i = 0; i < s->nobjs; i++) {
@@ -331,12 +344,85 @@ static void mark_sources(orc_scene* s) {
             mult = .5 * sqrt(src.ss2);
             for (k = 0; k < 3; k++) src.ss[0][k] *= mult;
             cross(src.ss[1], snorm, src.ss[0]);
+        } else if (o->otype == T_POLYGON) {      /* fsetsrc(), srcsupp.c:91-152 */
+            int nv = o->nv, j; double d; const double* va = o->fargs;
+            if (o->bad || o->area == 0.) { fail(s, "zero source area:", o->name); continue; }
+            for (j = 0; j < 3; j++) { src.sloc[j] = 0.0; for (k = 0; k < nv; k++) src.sloc[j] += va[3 * k + j]; src.sloc[j] /= (double)nv; }
+            if (!inface(src.sloc, o)) { fail(s, "cannot hit source center:", o->name); continue; }
+            src.flat = 1;
+            for (j = 0; j < 3; j++) src.ss[2][j] = o->norm[j];
+            src.ss2 = o->area;
+            src.srad = 0.;
+            for (k = 0; k < nv; k++) { d = 0; for (j = 0; j < 3; j++) d += (va[3 * k + j] - src.sloc[j]) * (va[3 * k + j] - src.sloc[j]); if (d > src.srad) src.srad = d; }
+            src.srad = (float)sqrt(src.srad);
+            if (nv == 4) {
+                for (j = 0; j < 3; j++) { src.ss[0][j] = .5 * (va[3 + j] - va[j]); src.ss[1][j] = .5 * (va[9 + j] - va[j]); }
+            } else if (nv == 3) {
+                int near0 = 2, i2; double dmin = dist2line(src.sloc, va + 6, va);
+                for (k = 0; k < 2; k++) { double d2 = dist2line(src.sloc, va + 3 * k, va + 3 * (k + 1)); if (d2 >= dmin) continue; near0 = k; dmin = d2; }
+                i2 = (near0 + 1) % 3;
+                for (j = 0; j < 3; j++) src.ss[0][j] = va[3 * i2 + j] - va[3 * near0 + j];
+                normalize(src.ss[0]);
+                dmin = sqrt(dmin);
+                for (j = 0; j < 3; j++) src.ss[0][j] *= dmin;
+                cross(src.ss[1], o->norm, src.ss[0]);
+            } else {                              /* setflatss() with -u- */
+                double mult;
+                getperp0(src.ss[0], src.ss[2]);
+                mult = .5 * sqrt(src.ss2);
+                for (j = 0; j < 3; j++) src.ss[0][j] *= mult;
+                cross(src.ss[1], src.ss[2], src.ss[0]);
+            }
+        } else if (o->otype == T_SPHERE) {        /* sphsetsrc(), srcsupp.c:182-203 */
+            if (o->nfargs != 4 || o->fargs[3] <= FTINY) { fail(s, "illegal source radius:", o->name); continue; }
+            src.cir = 1;
+            for (k = 0; k < 3; k++) src.sloc[k] = o->fargs[k];
+            src.srad = (float)o->fargs[3];
+            src.ss2 = (float)(PI * src.srad * src.srad);
+            for (k = 0; k < 3; k++) src.ss[k][k] = 0.7236 * o->fargs[3];
+        } else if (o->otype == T_RING) {          /* rsetsrc(), srcsupp.c:206-232 */
+            double mult;
+            if (o->bad || o->ctype != T_RING) { fail(s, "illegal source:", o->name); continue; }
+            if (o->r1 <= FTINY) { fail(s, "illegal source radius:", o->name); continue; }
+            if (o->r0 > 0.0) { fail(s, "cannot hit source center:", o->name); continue; }
+            for (k = 0; k < 3; k++) { src.sloc[k] = o->p0[k]; src.ss[2][k] = o->ad[k]; }
+            src.flat = src.cir = 1;
+            src.srad = (float)o->r1;
+            src.ss2 = (float)(PI * src.srad * src.srad);
+            getperp0(src.ss[0], src.ss[2]);
+            mult = .5 * sqrt(src.ss2);
+            for (k = 0; k < 3; k++) src.ss[0][k] *= mult;
+            cross(src.ss[1], src.ss[2], src.ss[0]);
+        } else if (o->otype == T_CYLINDER) {      /* cylsetsrc(), srcsupp.c:235-268 */
+            if (o->bad || o->ctype != T_CYLINDER) { fail(s, "illegal source:", o->name); continue; }
+            if (o->r0 <= FTINY) { fail(s, "illegal source radius:", o->name); continue; }
+            src.cyl = 1;
+            for (k = 0; k < 3; k++) src.sloc[k] = .5 * (o->fargs[3 + k] + o->fargs[k]);
+            src.srad = (float)(.5 * o->al);
+            src.ss2 = (float)(2. * o->r0 * o->al);
+            for (k = 0; k < 3; k++) src.ss[0][k] = .5 * o->al * o->ad[k];
+            getperp0(src.ss[2], o->ad);
+            for (k = 0; k < 3; k++) src.ss[2][k] *= .8559 * o->r0;
+            cross(src.ss[1], src.ss[2], o->ad);
         } else {
-            fail(s, "local light source not supported by the oracle:", o->name);
+            fail(s, "illegal material (this surface type cannot be a light source):", o->name);
             continue;
         }
-        if (m->otype == T_GLOW && src.distant) src.skip = 1;
-        if (m->otype == T_SPOT) { fail(s, "spotlight not supported by the oracle:", m->name); continue; }
+        src.ss2 = (float)src.ss2;                 /* SRCREC.ss2 and .srad are floats (source.h:60-61) */
+        if (m->otype == T_GLOW) {
+            src.prox_on = 1; src.prox = (float)m->fargs[3];
+            if (src.distant) src.skip = 1;
+        } else if (m->otype == T_SPOT) {          /* makespot(), srcsupp.c:271-291 */
+            if (m->fargs[3] <= FTINY) { fail(s, "zero angle for spotlight", m->name); continue; }
+            src.spot_on = 1;
+            src.spot_siz = (float)(2.0 * PI * (1.0 - cos(PI / 180.0 / 2.0 * m->fargs[3])));
+            for (k = 0; k < 3; k++) src.spot_aim[k] = m->fargs[4 + k];
+            if ((src.spot_flen = (float)normalize(src.spot_aim)) == 0.0) { fail(s, "zero focus vector for spotlight", m->name); continue; }
+            if (src.flat) {                       /* checkspot(), srcsupp.c:443-459 */
+                double d = dot(src.spot_aim, src.ss[2]);
+                if (!(d > FTINY)) { double d1 = 1. - src.spot_siz / (2. * PI); if (!(1. - FTINY - d * d < d1 * d1)) src.skip = 1; }
+            }
+        }
         s->srcs = (SRC*)realloc(s->srcs, sizeof(SRC) * (s->nsrcs + 1));
         s->srcs[s->nsrcs++] = src;
     }
@@ -439,6 +525,7 @@ void orc_default_params(orc_params* p, int rcontrib) {
     if (rcontrib) { p->ambounce = 1; p->ambdiv = 350; p->minweight = 2e-3; p->dstrsrc = 0.9; p->specthresh = .02; }
     else { p->ambounce = 0; p->ambdiv = 1024; p->minweight = 1e-4; p->dstrsrc = 0.0; p->specthresh = .15; }
     p->seed = 1;
+    p->srcsizerat = .2;
 }
 void orc_set_params(orc_scene* s, const orc_params* p) {
     s->P = *p;
@@ -871,29 +958,193 @@ static void dirnorm(orc_scene* s, float* scval, NORMDAT* np, const double* ldir,
     }
 }
 
-static void direct(orc_scene* s, RAY* r, NORMDAT* nd) {
-    int sn, k;
-    for (sn = 0; sn < s->nsrcs; sn++) {
-        SRC* src = &s->srcs[sn]; double vpos[3] = {0, 0, 0}, ldir[3]; float coef[3]; RAY sr; int thru;
-        if (src->skip || !src->distant) continue;
-        if (s->P.dstrsrc > FTINY) for (k = 0; k < 3; k++) vpos[k] = s->P.dstrsrc * (1. - 2. * frandom(s));
-        if (s->P.dstrsrc > 0.7) {
-            double d = 1.12837917, t0 = d * sqrt(1.0 - 0.5 * vpos[1] * vpos[1]), t1 = d * sqrt(1.0 - 0.5 * vpos[0] * vpos[0]);
-            vpos[0] *= t0; vpos[1] *= t1; vpos[2] = 0;
+/* ---- source partitioning and sampling: srcsamp.c:36-376 ---- */
+#define MAXSPART 64
+enum { SU = 0, SV = 1, SW = 2, S0 = 3 };
+typedef struct { double dom; int sn, np, sp; unsigned char spt[MAXSPART / 2]; } SRCINDEX;
+#define clrpart(pt) memset((pt), 0, MAXSPART / 2)
+#define setpart(pt, i, v) ((pt)[(i) >> 2] |= (v) << (((i) & 3) << 1))
+#define spart(pt, pi) ((pt)[(pi) >> 2] >> (((pi) & 3) << 1) & 3)
+static double dist2(const double* a, const double* b) {
+    return (a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]);
+}
+static int skipparts(int* ct, int* sz, int* pp, unsigned char* pt) {     /* srcsamp.c:147-180 */
+    int p = spart(pt, pp[0]);
+    pp[0]++;
+    if (p == S0) { if (pp[1]) { pp[1]--; return 0; } return 1; }
+    sz[p] >>= 1; ct[p] -= sz[p];
+    if (skipparts(ct, sz, pp, pt)) return 1;
+    ct[p] += sz[p] << 1;
+    if (skipparts(ct, sz, pp, pt)) return 1;
+    ct[p] -= sz[p]; sz[p] <<= 1;
+    return 0;
+}
+static int cyl_partit(const double* ro, unsigned char* pt, int* pi, int mp, const double* cent, const double* axis, double d2) {
+    double newct[3], newax[3]; int npl, npu, k;
+    if (mp < 2 || dist2(ro, cent) >= d2) { setpart(pt, *pi, S0); (*pi)++; return 1; }
+    setpart(pt, *pi, SU); (*pi)++;
+    for (k = 0; k < 3; k++) newax[k] = .5 * axis[k];
+    d2 *= 0.25;
+    for (k = 0; k < 3; k++) newct[k] = cent[k] - newax[k];
+    npl = cyl_partit(ro, pt, pi, mp / 2, newct, newax, d2);
+    for (k = 0; k < 3; k++) newct[k] = cent[k] + newax[k];
+    npu = cyl_partit(ro, pt, pi, mp / 2, newct, newax, d2);
+    return npl + npu;
+}
+static int flt_partit(const double* ro, unsigned char* pt, int* pi, int mp, const double* cent, const double* u, const double* v, double du2, double dv2) {
+    double d2, newct[3], newax[3]; int npl, npu, k;
+    if (mp < 2 || ((d2 = dist2(ro, cent)) >= du2 && d2 >= dv2)) { setpart(pt, *pi, S0); (*pi)++; return 1; }
+    if (du2 > dv2) { setpart(pt, *pi, SU); (*pi)++; for (k = 0; k < 3; k++) newax[k] = .5 * u[k]; u = newax; du2 *= 0.25; }
+    else { setpart(pt, *pi, SV); (*pi)++; for (k = 0; k < 3; k++) newax[k] = .5 * v[k]; v = newax; dv2 *= 0.25; }
+    for (k = 0; k < 3; k++) newct[k] = cent[k] - newax[k];
+    npl = flt_partit(ro, pt, pi, mp / 2, newct, u, v, du2, dv2);
+    for (k = 0; k < 3; k++) newct[k] = cent[k] + newax[k];
+    npu = flt_partit(ro, pt, pi, mp / 2, newct, u, v, du2, dv2);
+    return npl + npu;
+}
+/* partition source si->sn as seen from ray origin `ro` with weight `rw`: nopart / flatpart / cylpart */
+static void partition_source(orc_scene* s, SRCINDEX* si, const double* ro, double rw) {
+    const SRC* sp = &s->srcs[si->sn]; int otype = s->objs[sp->so].otype, pi = 0, k;
+    clrpart(si->spt);
+    if (s->P.srcsizerat <= FTINY || otype == T_SOURCE || otype == T_SPHERE) { setpart(si->spt, 0, S0); si->np = 1; return; }
+    if (otype == T_CYLINDER) {                    /* cylpart(), srcsamp.c:229-264 */
+        double d2, safedist2, dist2cent, rad2, v[3];
+        rad2 = 1.365 * dot(sp->ss[SV], sp->ss[SV]);
+        for (k = 0; k < 3; k++) v[k] = ro[k] - sp->sloc[k];
+        d2 = dot(v, sp->ss[SU]);
+        safedist2 = dot(sp->ss[SU], sp->ss[SU]);
+        d2 *= d2 / safedist2;
+        dist2cent = dot(v, v);
+        d2 = dist2cent - d2;
+        if (d2 <= rad2) { si->np = 0; return; }
+        safedist2 *= 4. * rw * rw / (s->P.srcsizerat * s->P.srcsizerat);
+        if (d2 <= 4. * rad2 || dist2cent >= safedist2) { setpart(si->spt, 0, S0); si->np = 1; return; }
+        si->np = cyl_partit(ro, si->spt, &pi, MAXSPART, sp->sloc, sp->ss[SU], safedist2);
+        return;
+    }
+    {                                             /* flatpart(), srcsamp.c:322-352 */
+        double v[3], du2, dv2;
+        for (k = 0; k < 3; k++) v[k] = ro[k] - sp->sloc[k];
+        if (dot(v, sp->ss[SW]) <= 0.) { si->np = 0; return; }
+        dv2 = 2. * rw / s->P.srcsizerat; dv2 *= dv2;
+        du2 = dv2 * dot(sp->ss[SU], sp->ss[SU]);
+        dv2 *= dot(sp->ss[SV], sp->ss[SV]);
+        si->np = flt_partit(ro, si->spt, &pi, MAXSPART, sp->sloc, sp->ss[SU], sp->ss[SV], du2, dv2);
+    }
+}
+static int srcskip(orc_scene* s, int sn, const double* ro) {          /* srcsamp.c:19-33 */
+    const SRC* sp = &s->srcs[sn];
+    if (sp->skip) return 1;
+    if (sp->prox_on && !sp->distant) return dist2(ro, sp->sloc) > (sp->prox + sp->srad) * (sp->prox + sp->srad);
+    return 0;
+}
+static int spotout(const SRC* sp, const RAY* r) {                     /* srcsupp.c:294-322 */
+    if (!sp->spot_on) return 0;
+    if (sp->spot_flen < -FTINY) {
+        double vd[3], d; int k;
+        for (k = 0; k < 3; k++) vd[k] = sp->spot_aim[k] - r->rorg[k];
+        d = dot(r->rdir, vd);
+        d = dot(vd, vd) - d * d;
+        return PI * d > sp->spot_siz;
+    }
+    return sp->spot_siz < 2.0 * PI * (1.0 + dot(sp->spot_aim, r->rdir));
+}
+/* nextssamp() + srcray(): next usable sample of the source list for shadow ray sr (origin set);
+   returns 0 when the sources are exhausted, else 1 with sr->rdir, sr->rsrc and si->dom set */
+static int srcray_next(orc_scene* s, RAY* sr, SRCINDEX* si, double rw) {
+    for (;;) {
+        int cent[3], size[3], parr[2], i; const SRC* srcp; double vpos[3], d;
+        while (++si->sp >= si->np) {
+            if (++si->sn >= s->nsrcs) return 0;
+            if (srcskip(s, si->sn, sr->rorg)) si->np = 0;
+            else partition_source(s, si, sr->rorg, rw);
+            si->sp = -1;
         }
-        for (k = 0; k < 3; k++) ldir[k] = src->sloc[k] + vpos[0] * src->ss[0][k] + vpos[1] * src->ss[1][k] + vpos[2] * src->ss[2][k];
-        if (normalize(ldir) == 0.0) continue;
-        dirnorm(s, coef, nd, ldir, src->ss2);
+        cent[0] = cent[1] = cent[2] = 0;
+        size[0] = size[1] = size[2] = MAXSPART;
+        parr[0] = 0; parr[1] = si->sp;
+        if (!skipparts(cent, size, parr, si->spt)) { fail(s, "bad source partition", ""); return 0; }
+        srcp = &s->srcs[si->sn];
+        if (s->P.dstrsrc > FTINY) {
+            if (srcp->flat) { vpos[0] = frandom(s); vpos[1] = frandom(s); vpos[2] = 0.5; }
+            else { vpos[0] = frandom(s); vpos[1] = frandom(s); vpos[2] = frandom(s); }
+            for (i = 0; i < 3; i++) vpos[i] = s->P.dstrsrc * (1. - 2. * vpos[i]) * (double)size[i] * (1.0 / MAXSPART);
+        } else vpos[0] = vpos[1] = vpos[2] = 0.0;
+        for (i = 0; i < 3; i++) vpos[i] += cent[i] * (1.0 / MAXSPART);
+        if (srcp->cir && ((si->np > 1) | (s->P.dstrsrc > 0.7))) {
+            double trim[3];
+            if (srcp->flat | srcp->distant) {
+                d = 1.12837917;
+                trim[SU] = d * sqrt(1.0 - 0.5 * vpos[SV] * vpos[SV]);
+                trim[SV] = d * sqrt(1.0 - 0.5 * vpos[SU] * vpos[SU]);
+                trim[SW] = 0.0;
+            } else {
+                trim[SW] = trim[SU] = vpos[SU] * vpos[SU];
+                d = vpos[SV] * vpos[SV];
+                if (d > trim[SW]) trim[SW] = d;
+                trim[SU] += d;
+                d = vpos[SW] * vpos[SW];
+                if (d > trim[SW]) trim[SW] = d;
+                trim[SU] += d;
+                if (trim[SU] > FTINY * FTINY) { d = 1.0 / 0.7236; trim[SW] = trim[SV] = trim[SU] = d * sqrt(trim[SW] / trim[SU]); }
+                else trim[SW] = trim[SV] = trim[SU] = 0.0;
+            }
+            for (i = 0; i < 3; i++) vpos[i] *= trim[i];
+        }
+        for (i = 0; i < 3; i++)
+            sr->rdir[i] = srcp->sloc[i] + vpos[SU] * srcp->ss[SU][i] + vpos[SV] * srcp->ss[SV][i] + vpos[SW] * srcp->ss[SW][i];
+        if (!srcp->distant) for (i = 0; i < 3; i++) sr->rdir[i] -= sr->rorg[i];
+        if ((d = normalize(sr->rdir)) == 0.0) continue;
+        if (srcp->flat) { si->dom = -dot(srcp->ss[SW], sr->rdir); si->dom *= size[SU] * size[SV] * (1.0 / MAXSPART / MAXSPART); }
+        else if (srcp->cyl) {
+            double dd = dot(sr->rdir, srcp->ss[SU]);
+            dd *= dd / dot(srcp->ss[SU], srcp->ss[SU]);
+            si->dom = sqrt(1. - dd) * size[SU] * (1.0 / MAXSPART);
+        } else si->dom = size[SU] * size[SV] * (double)size[SW] * (1.0 / MAXSPART / MAXSPART / MAXSPART);
+        sr->rsrc = si->sn;
+        if (srcp->distant) {
+            si->dom *= srcp->ss2;
+            if (srcp->spot_on && spotout(srcp, sr)) continue;
+            return 1;
+        }
+        if (si->dom <= 1e-4) continue;            /* behind source? */
+        si->dom *= srcp->ss2 / (d * d);
+        if (srcp->prox_on && d > srcp->prox) continue;
+        if (srcp->spot_on) {
+            if (spotout(srcp, sr)) continue;
+            si->dom *= d * d; d += srcp->spot_flen; si->dom /= d * d;
+        }
+        return 1;
+    }
+}
+
+/* source.c:398-556 direct(), every source sample tested (= -dt 0) */
+static void direct(orc_scene* s, RAY* r, NORMDAT* nd) {
+    SRCINDEX si; RAY sr0; int k;
+    si.sn = si.sp = -1; si.np = 0;
+    if (rayorigin(s, &sr0, SHADOW, r, NULL) < 0) return;
+    while (srcray_next(s, &sr0, &si, r->rweight)) {
+        const SRC* src = &s->srcs[si.sn]; float coef[3]; RAY sr; int thru; double ldir[3];
+        for (k = 0; k < 3; k++) ldir[k] = sr0.rdir[k];
+        dirnorm(s, coef, nd, ldir, si.dom);
         if (max3f(coef) <= 0.0) continue;
+        if (!src->distant) {                      /* srcvalue(): potential contribution, aiming test included */
+            RAY pr = sr0;
+            pr.rot = FHUGE; pr.ro = -1; pr.rsrc = si.sn;
+            if (!hit_obj(s, src->so, &pr)) continue;
+            pr.rcol[0] = pr.rcol[1] = pr.rcol[2] = 0;
+            if (!rayshade(s, &pr, s->objs[pr.ro].omod)) continue;
+            if (!(pr.rcol[0] * coef[0] > 0 || pr.rcol[1] * coef[1] > 0 || pr.rcol[2] * coef[2] > 0)) continue;
+        }
         thru = (r->rod > 0) ^ (dot(r->ron, ldir) > 0);
         if (rayorigin(s, &sr, thru ? TSHADOW : RSHADOW, r, NULL) < 0) continue;
         for (k = 0; k < 3; k++) { sr.rcoef[k] = coef[k]; sr.rdir[k] = ldir[k]; }
-        sr.rsrc = sn;
+        sr.rsrc = si.sn;
         if (localhit(s, &sr)) {      /* SFOLLOW: follow entire path */
             if (!rayshade(s, &sr, s->objs[sr.ro].omod)) raytrans(s, &sr);
             trace_contrib(s, &sr);
             if ((sr.rcol[0] + sr.rcol[1] + sr.rcol[2]) / 3. <= FTINY) continue;
-        } else if (sourcehit(s, &sr) && rayshade(s, &sr, s->objs[sr.ro].omod)) trace_contrib(s, &sr);
+        } else if (src->distant && sourcehit(s, &sr) && rayshade(s, &sr, s->objs[sr.ro].omod)) trace_contrib(s, &sr);
         else continue;
         for (k = 0; k < 3; k++) r->rcol[k] += sr.rcol[k] * coef[k];
     }
@@ -1124,6 +1375,14 @@ static int m_light(orc_scene* s, const OBJ* m, RAY* r) {
     }
     if (!(s->P.directvis || (r->crtype & SHADOW) || distglow(r->rot))) { r->rcoef[0] = r->rcoef[1] = r->rcoef[2] = 0; return 1; }
     if (r->rod < 0.0) { if (!s->P.backvis) raytrans(s, r); return 1; }
+    if (m->otype == T_SPOT) {                     /* check for outside spot (source.c:778-779) */
+        SRC sp; memset(&sp, 0, sizeof(sp));
+        sp.spot_on = 1;
+        sp.spot_siz = (float)(2.0 * PI * (1.0 - cos(PI / 180.0 / 2.0 * m->fargs[3])));
+        for (k = 0; k < 3; k++) sp.spot_aim[k] = m->fargs[4 + k];
+        sp.spot_flen = (float)normalize(sp.spot_aim);
+        if (spotout(&sp, r)) return 1;
+    }
     /* a pattern under an emitter (e.g. brightfunc sky) is ignored: the value is the plain
        material RGB; coefficients (-V-) do not depend on it.  Tests compare geometry only there. */
     for (k = 0; k < 3; k++) r->rcol[k] = (float)m->fargs[k];
@@ -1146,7 +1405,7 @@ static int rayshade(orc_scene* s, RAY* r, int mod) {
         case T_PLASTIC: case T_METAL: if (m->nfargs != 5) { fail(s, "bad arguments for", m->name); return 1; } return m_normal(s, t, m->fargs, r, flat);
         case T_TRANS: if (m->nfargs != 7) { fail(s, "bad arguments for", m->name); return 1; } return m_normal(s, t, m->fargs, r, flat);
         case T_GLASS: return m_glass(s, m, r);
-        case T_GLOW: case T_LIGHT: case T_ILLUM: return m_light(s, m, r);
+        case T_GLOW: case T_LIGHT: case T_ILLUM: case T_SPOT: return m_light(s, m, r);
         default: fail(s, "unsupported modifier reached by the oracle:", m->name); return 1;
         }
     }

@@ -23,6 +23,7 @@ typedef struct orc_params {
     double ambval[3];
     int contrib;            /* -V+ */
     uint64_t seed;
+    double srcsizerat;      /* -ds */
 } orc_params;
 
 /* bin function ids (same meaning as the .cal files, see rb_oracle.c) */
