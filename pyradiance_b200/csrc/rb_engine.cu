@@ -191,7 +191,10 @@ __global__ void __launch_bounds__(256) k_direct(const WaveArgs A, const DirectAr
         }
         __syncthreads();
         const unsigned base = sj.r.nchild;
-        for (int sn = threadIdx.x; sn < ns; sn += blockDim.x) direct_one(A, sj.r, sj.nd, sn, base);
+        for (int sn = threadIdx.x; sn < ns; sn += blockDim.x) {
+            if (A.S.srcs[sn].flags & SF_DISTANT) direct_one(A, sj.r, sj.nd, sn, base);
+            else direct_local(A, sj.r, sj.nd, sn, base);
+        }
     }
 }
 
@@ -288,15 +291,16 @@ bool Engine::upload_scene(const FlatScene& fs, const Scene& sc, std::string& err
     S_.cusize = sc.cusize;
     S_.root = fs.root; S_.nobjs = (int)sc.objs.size(); S_.nsrcs = (int)fs.srcs.size();
     nsrc_active_ = 0;
-    for (const SrcRec& sr : fs.srcs) nsrc_active_ += ((sr.flags & SF_DISTANT) && !(sr.flags & SF_SKIP)) ? 1 : 0;
+    for (const SrcRec& sr : fs.srcs)              // local sources: a few partitions each on average
+        nsrc_active_ += (sr.flags & SF_SKIP) ? 0 : (sr.flags & SF_DISTANT) ? 1 : 4;
     S_.maxdepth = sc.maxdepth;
     S_.nodes = (const int*)d_nodes_; S_.leafpool = (const int*)d_leaf_;
     S_.objhdr = (const int4*)d_hdr_; S_.geom = (const double*)d_geom_;
     S_.mats = (const MatRec*)d_mats_; S_.srcs = (const SrcRec*)d_srcs_;
     S_.otrack = (const int*)d_otrack_;
-    has_local_sources_ = false;
+    has_local_sources_ = false;                  // local emitters: direct() always runs in k_direct
     for (const auto& s : fs.srcs)
-        if (!(s.flags & SF_DISTANT)) { has_local_sources_ = true; local_source_note_ = fs.unsupported_note; }
+        if (!(s.flags & SF_DISTANT) && !(s.flags & SF_SKIP)) has_local_sources_ = true;
     objdesc.clear();
     for (const auto& o : sc.objs) objdesc.push_back(o.tname + " \"" + o.name + "\"");
     nbins_ = 0; ncols_ = 0;
@@ -320,7 +324,7 @@ bool Engine::set_bins(const std::vector<DBinSpec>& bins, const std::vector<int>&
 }
 
 bool Engine::ensure_queues(std::string& err) {
-    if (nsrc_active_ >= RB_COOP_SRC_MIN && !dq_ && q_[0]) {   // a many-source scene loaded after the queues were made
+    if (park_direct() && !dq_ && q_[0]) {   // a many-source scene loaded after the queues were made
         CK(cudaMalloc(&dq_, dcap_ * sizeof(DirectJob)));
     }
     if (q_[0]) return true;
@@ -338,7 +342,7 @@ bool Engine::ensure_queues(std::string& err) {
     CK(cudaMalloc(&h_[1], hcap_ * sizeof(QHemi)));
     CK(cudaMalloc(&d_hits_, qcap_ * sizeof(HitRec)));
     dcap_ = std::max<size_t>(qcap_ / 32, 4096);
-    if (nsrc_active_ >= RB_COOP_SRC_MIN) {      // many sources: direct() runs as its own kernel from a job queue
+    if (park_direct()) {      // many or local sources: direct() runs as its own kernel from a job queue
         CK(cudaMalloc(&dq_, dcap_ * sizeof(DirectJob)));
     }
     return size_trace_grid(err);
@@ -410,7 +414,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
     A.inline_hemi_max = 16;
     A.qcap = (unsigned)qcap_; A.hcap = (unsigned)hcap_;
     A.hits = d_hits_;
-    A.dout = nsrc_active_ >= RB_COOP_SRC_MIN ? dq_ : nullptr; A.dcap = (unsigned)dcap_;
+    A.dout = park_direct() ? dq_ : nullptr; A.dcap = (unsigned)dcap_;
 
     auto sync_counters = [&](std::string& err) -> bool {
         CK(cudaMemcpyAsync(h_cnt_, d_cnt_, sizeof(DCounters), cudaMemcpyDeviceToHost, stream_));
@@ -556,10 +560,6 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
 bool Engine::run(const TraceJob& job, const DParams& P, std::string& err) {
     CK(cudaSetDevice(dev_));
     if (!d_nodes_) { err = "no octree loaded"; return false; }
-    if (has_local_sources_) {
-        err = "unsupported scene: " + local_source_note_;
-        return false;
-    }
     if (!ensure_queues(err) || !size_trace_grid(err)) return false;
     if (job.nrays == 0) return true;
     const int accum = job.accum;

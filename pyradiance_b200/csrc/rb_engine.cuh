@@ -81,6 +81,7 @@ private:
     int trace_blocks_ = 148;
     size_t trace_smem_ = 0;      // dynamic shared memory of k_trace (ancestor stack)
     bool has_local_sources_ = false;
+    bool park_direct() const { return has_local_sources_ || nsrc_active_ >= 64; }   // 64 = RB_COOP_SRC_MIN
     int nsrc_active_ = 0;       // distant sources direct() samples (not glow skies)
     std::string local_source_note_;
 };

@@ -695,6 +695,24 @@ static void vcross(double r[3], const double a[3], const double b[3]) {
 static double vdot(const double a[3], const double b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
 // deterministic getperpendicular (fvect.c:159-196 with randomize=0)
+// "cannot hit source center" (srcsupp.c:109-110): is the vertex centroid inside the
+// polygon?  Load-time input validation only, so the winding number of the centroid
+// in the projection plane is enough (the reference uses inface(), face.c:121-162).
+static bool inface_host(const double p[3], int hdr0, const double* g, int nv) {
+    const int ax = (hdr0 >> 10) & 3;
+    const int xi = (ax + 1) % 3, yi = (xi + 1) % 3;
+    const double x = p[xi], y = p[yi];
+    const double* vp = g + 6;
+    double wn = 0.0;
+    for (int n = 0; n < nv; n++) {
+        const int n1 = (n + 1) % nv;
+        const double ax0 = vp[2 * n] - x, ay0 = vp[2 * n + 1] - y;
+        const double ax1 = vp[2 * n1] - x, ay1 = vp[2 * n1 + 1] - y;
+        wn += atan2(ax0 * ay1 - ay0 * ax1, ax0 * ax1 + ay0 * ay1);
+    }
+    return fabs(wn) > PI;
+}
+
 static bool getperp(double vp[3], const double v[3]) {
     double v1[3] = {0, 0, 0};
     int i;
@@ -1091,22 +1109,128 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
             vcross(s.ss[1], snorm, s.ss[0]);
             s.ss[2][0] = s.ss[2][1] = s.ss[2][2] = 0.0;
         } else {
-            // local emitters need fsetsrc/sphsetsrc/rsetsrc/cylsetsrc + source
-            // partitioning; not built yet -> explicit rejection when used.
-            s.flags |= SF_SKIP;
-            s.mat = slot_of(mi);
-            fs.mats[s.mat].flags |= 2;       // "local source not supported"
-            note_unsupported("local light source \"" + o.name + "\" (" + m.tname + " on " + o.tname +
-                             ") is not supported yet; only distant sources are");
+            // local emitters: srcsupp.c fsetsrc / sphsetsrc / rsetsrc / cylsetsrc.  The
+            // perpendiculars are the deterministic ones (-u-); with -u+ the reference
+            // only randomises the orientation of the partition / jitter frame.
+            const int32_t* hdr = &fs.objhdr[(size_t)i * 4];
+            const int kind = hdr[0] & 0xff;
+            const double* g = &fs.geom[hdr[3]];
+            auto bad = [&](const char* what) { err = std::string(what) + " \"" + o.name + "\""; return false; };
+            if (kind == PK_FACE) {                                   // fsetsrc(), srcsupp.c:91-152
+                int nv = (hdr[0] >> 16) & 0xffff;
+                const double* va = o.fargs.data();
+                double norm[3] = {g[0], g[1], g[2]};
+                double area = 0.0;
+                {   // getface(): area = |sum of fan cross products| / 2 (face.c:66-82)
+                    double nsum[3] = {0, 0, 0}, v1[3], v2[3], v3[3];
+                    for (int k = 0; k < 3; k++) v1[k] = va[3 + k] - va[k];
+                    for (int q = 2; q < nv; q++) {
+                        for (int k = 0; k < 3; k++) v2[k] = va[3 * q + k] - va[k];
+                        vcross(v3, v1, v2);
+                        for (int k = 0; k < 3; k++) { nsum[k] += v3[k]; v1[k] = v2[k]; }
+                    }
+                    area = 0.5 * vnormalize(nsum);
+                }
+                if (area == 0.0) return bad("zero source area for");
+                for (int j = 0; j < 3; j++) {
+                    s.sloc[j] = 0.0;
+                    for (int q = 0; q < nv; q++) s.sloc[j] += va[3 * q + j];
+                    s.sloc[j] /= (double)nv;
+                }
+                if (!inface_host(s.sloc, hdr[0], g, nv)) return bad("cannot hit source center of");
+                s.flags |= SF_FLAT;
+                for (int j = 0; j < 3; j++) s.ss[2][j] = norm[j];
+                s.ss2 = area;
+                double r2 = 0.0;
+                for (int q = 0; q < nv; q++) {
+                    double d = 0; for (int j = 0; j < 3; j++) d += (va[3 * q + j] - s.sloc[j]) * (va[3 * q + j] - s.sloc[j]);
+                    if (d > r2) r2 = d;
+                }
+                s.srad = sqrt(r2);
+                if (nv == 4) {                                       // parallelogram case
+                    for (int j = 0; j < 3; j++) { s.ss[0][j] = .5 * (va[3 + j] - va[j]); s.ss[1][j] = .5 * (va[9 + j] - va[j]); }
+                } else if (nv == 3) {                                // triangle case
+                    auto d2line = [&](const double* pp, const double* e1, const double* e2) {
+                        double d = 0, d1 = 0, dd = 0;
+                        for (int k = 0; k < 3; k++) { d += (e1[k] - e2[k]) * (e1[k] - e2[k]); d1 += (e1[k] - pp[k]) * (e1[k] - pp[k]); dd += (e2[k] - pp[k]) * (e2[k] - pp[k]); }
+                        double d2 = d + d1 - dd;
+                        return d1 - 0.25 * d2 * d2 / d;
+                    };
+                    int near0 = 2;
+                    double dmin = d2line(s.sloc, va + 6, va);
+                    for (int q = 0; q < 2; q++) {
+                        double d2 = d2line(s.sloc, va + 3 * q, va + 3 * (q + 1));
+                        if (d2 >= dmin) continue;
+                        near0 = q; dmin = d2;
+                    }
+                    int i2 = (near0 + 1) % 3;
+                    for (int j = 0; j < 3; j++) s.ss[0][j] = va[3 * i2 + j] - va[3 * near0 + j];
+                    vnormalize(s.ss[0]);
+                    dmin = sqrt(dmin);
+                    for (int j = 0; j < 3; j++) s.ss[0][j] *= dmin;
+                    vcross(s.ss[1], norm, s.ss[0]);
+                } else {                                             // setflatss(): hope for convex
+                    getperp(s.ss[0], s.ss[2]);
+                    double mult = .5 * sqrt(s.ss2);
+                    for (int k = 0; k < 3; k++) s.ss[0][k] *= mult;
+                    vcross(s.ss[1], s.ss[2], s.ss[0]);
+                }
+            } else if (kind == PK_SPHERE) {                          // sphsetsrc(), srcsupp.c:182-203
+                if (o.fargs[3] <= FTINY) return bad("illegal source radius for");
+                s.flags |= SF_CIRC;
+                for (int k = 0; k < 3; k++) s.sloc[k] = o.fargs[k];
+                s.srad = (float)o.fargs[3];
+                s.ss2 = PI * s.srad * s.srad;
+                for (int k = 0; k < 3; k++) s.ss[k][k] = 0.7236 * o.fargs[3];
+            } else if (kind == PK_RING) {                            // rsetsrc(), srcsupp.c:206-232
+                if (g[9] <= FTINY) return bad("illegal source radius for");
+                if (g[8] > 0.0) return bad("cannot hit source center of");
+                for (int k = 0; k < 3; k++) { s.sloc[k] = g[4 + k]; s.ss[2][k] = g[k]; }
+                s.flags |= SF_FLAT | SF_CIRC;
+                s.srad = (float)g[9];
+                s.ss2 = PI * s.srad * s.srad;
+                getperp(s.ss[0], s.ss[2]);
+                double mult = .5 * sqrt((double)(float)s.ss2);
+                for (int k = 0; k < 3; k++) s.ss[0][k] *= mult;
+                vcross(s.ss[1], s.ss[2], s.ss[0]);
+            } else if (kind == PK_CYL) {                             // cylsetsrc(), srcsupp.c:235-268
+                const double al = g[3], r0 = g[8];
+                const double ad[3] = {g[0], g[1], g[2]};
+                if (r0 <= FTINY) return bad("illegal source radius for");
+                s.flags |= SF_CYL;
+                for (int k = 0; k < 3; k++) s.sloc[k] = .5 * (o.fargs[3 + k] + o.fargs[k]);
+                s.srad = (float)(.5 * al);
+                s.ss2 = 2. * r0 * al;
+                for (int k = 0; k < 3; k++) s.ss[0][k] = .5 * al * ad[k];
+                getperp(s.ss[2], ad);
+                for (int k = 0; k < 3; k++) s.ss[2][k] *= .8559 * r0;
+                vcross(s.ss[1], s.ss[2], ad);
+            } else
+                return bad("illegal material (this surface type cannot be a light source) on");
+            s.srad = (double)(float)s.srad;
         }
+        s.ss2 = (double)(float)s.ss2;            // SRCREC.ss2 / .srad are floats (source.h:60-61)
         if (m.otype == OT_GLOW) {
             s.flags |= SF_PROX;
-            s.prox = m.fargs[3];
+            s.prox = (double)(float)m.fargs[3];
             if (s.flags & SF_DISTANT) s.flags |= SF_SKIP;
-        } else if (m.otype == OT_SPOTLIGHT) {
+        } else if (m.otype == OT_SPOTLIGHT) {    // makespot(), srcsupp.c:271-291
+            if (m.fargs[3] <= FTINY) { err = "zero angle for spotlight \"" + m.name + "\""; return false; }
             s.flags |= SF_SPOT;
-            note_unsupported("spotlight \"" + m.name + "\" is not supported");
-            fs.mats[s.mat].flags |= 1;
+            s.spot_siz = (float)(2.0 * PI * (1.0 - cos(PI / 180.0 / 2.0 * m.fargs[3])));
+            for (int k = 0; k < 3; k++) s.spot_aim[k] = m.fargs[4 + k];
+            s.spot_flen = (float)vnormalize(s.spot_aim);
+            if (s.spot_flen == 0.0f) { err = "zero focus vector for spotlight \"" + m.name + "\""; return false; }
+            if (s.flags & SF_FLAT) {             // checkspot(), srcsupp.c:443-459
+                double d = vdot(s.spot_aim, s.ss[2]);
+                if (!(d > FTINY)) {
+                    double d1 = 1. - s.spot_siz / (2. * PI);
+                    if (!(1. - FTINY - d * d < d1 * d1)) {
+                        s.flags |= SF_SKIP;
+                        fs.warnings.push_back("invalid spotlight direction for \"" + o.name + "\"");
+                    }
+                }
+            }
         }
         fs.srcs.push_back(s);
     }

@@ -116,6 +116,9 @@ struct SrcRec {          // distant & local sources (source.h SRCREC subset)
     int    flags;        // SF_*
     int    mat;          // material slot
     int    pad;
+    double spot_aim[3];  // spotlight: unit aim vector (srcsupp.c makespot)
+    float  spot_siz;     // spotlight: solid angle of the cone
+    float  spot_flen;    // spotlight: focal length (length of the aim vector as given)
 };
 enum : int { SF_DISTANT = 1, SF_SKIP = 2, SF_PROX = 4, SF_SPOT = 8, SF_FLAT = 16,
              SF_CIRC = 32, SF_CYL = 64, SF_FOLLOW = 128 };

@@ -398,6 +398,198 @@ __device__ __forceinline__ void direct(const WaveArgs& A, RayCtx& r, const NormD
     r.nchild += (unsigned)ns;
 }
 
+// ---- local light sources: srcsamp.c source partitioning + srcray() + srcvalue() ----
+// srcsupp.c:294-322 spotout() for the shadow ray (org, dir)
+__device__ __forceinline__ bool spotout(const SrcRec& s, const double org[3], const double dir[3]) {
+    if (s.spot_flen < -(float)RB_FTINY) {            // distant-type spot
+        double vd[3] = {s.spot_aim[0] - org[0], s.spot_aim[1] - org[1], s.spot_aim[2] - org[2]};
+        double d = dot3(dir, vd);
+        d = dot3(vd, vd) - d * d;
+        return RB_PI * d > (double)s.spot_siz;
+    }
+    return (double)s.spot_siz < 2.0 * RB_PI * (1.0 + dot3(s.spot_aim, dir));
+}
+
+// One partition of a local source (integer centre ct / size sz in 1/64 units, srcsamp.c:57-144):
+// sample -> solid angle -> proximity / spot tests -> coefficient -> aiming test against the
+// source surface itself (srcvalue(), source.c:260-300) -> shadow ray.
+__device__ __noinline__ void local_sample(const WaveArgs& A, const RayCtx& r, const NormDat& nd, int sn,
+                                          unsigned long long key, int ctU, int ctV, int szU, int szV, bool many) {
+    const SrcRec& s = A.S.srcs[sn];
+    const double dj = A.P.dstrsrc;
+    const double inv = 1.0 / 64.0;
+    double vpos[3] = {0, 0, 0};
+    const int sz[3] = {szU, szV, 64};
+    if (dj > RB_FTINY) {
+        vpos[0] = rnd01(key, 20); vpos[1] = rnd01(key, 21);
+        vpos[2] = (s.flags & SF_FLAT) ? 0.5 : rnd01(key, 22);
+        for (int i = 0; i < 3; i++) vpos[i] = dj * (1. - 2. * vpos[i]) * (double)sz[i] * inv;
+    }
+    vpos[0] += ctU * inv; vpos[1] += ctV * inv;
+    if ((s.flags & SF_CIRC) && (many | (dj > 0.7))) {
+        double trim[3];
+        if (s.flags & (SF_FLAT | SF_DISTANT)) {
+            const double d = 1.12837917;
+            trim[0] = d * sqrt(1.0 - 0.5 * vpos[1] * vpos[1]);
+            trim[1] = d * sqrt(1.0 - 0.5 * vpos[0] * vpos[0]);
+            trim[2] = 0.0;
+        } else {
+            trim[2] = trim[0] = vpos[0] * vpos[0];
+            double d = vpos[1] * vpos[1];
+            if (d > trim[2]) trim[2] = d;
+            trim[0] += d;
+            d = vpos[2] * vpos[2];
+            if (d > trim[2]) trim[2] = d;
+            trim[0] += d;
+            if (trim[0] > RB_FTINY * RB_FTINY) { d = 1.0 / 0.7236; trim[2] = trim[1] = trim[0] = d * sqrt(trim[2] / trim[0]); }
+            else trim[2] = trim[1] = trim[0] = 0.0;
+        }
+        for (int i = 0; i < 3; i++) vpos[i] *= trim[i];
+    }
+    double ldir[3];
+    for (int i = 0; i < 3; i++)
+        ldir[i] = (s.sloc[i] + vpos[0] * s.ss[0][i] + vpos[1] * s.ss[1][i] + vpos[2] * s.ss[2][i]) - r.rop[i];
+    double d = normalize3(ldir);
+    if (d == 0.0) return;                                // at source!
+    double dom;
+    if (s.flags & SF_FLAT) dom = -dot3(s.ss[2], ldir) * (szU * szV * (inv * inv));
+    else if (s.flags & SF_CYL) {
+        double dd = dot3(ldir, s.ss[0]);
+        dd *= dd / dot3(s.ss[0], s.ss[0]);
+        dom = sqrt(1. - dd) * (szU * inv);
+    } else dom = szU * szV * 64.0 * (inv * inv * inv);
+    if (dom <= 1e-4) return;                             // behind source?
+    dom *= s.ss2 / (d * d);
+    if ((s.flags & SF_PROX) && d > s.prox) return;
+    if (s.flags & SF_SPOT) {
+        if (spotout(s, r.rop, ldir)) return;
+        dom *= d * d; d += (double)s.spot_flen; dom /= d * d;
+    }
+    float scval[3];
+    dirnorm(scval, nd, r, ldir, dom, dj);
+    if (!(max3(scval) > 0.f)) return;
+    // srcvalue(): the sample must hit the source surface, on its emitting side
+    {
+        const int4 hd = __ldg(&A.S.objhdr[s.so]);
+        const int kind = hd.x & 0xff;
+        const double* g = A.S.geom + hd.w;
+        bool front = false, hit;
+        if (kind == PK_FACE) {
+            const double2* g2 = reinterpret_cast<const double2*>(g);
+            const int hot = kind | (((hd.x >> 10) & 3) << 4) | (((hd.x >> 12) & 1) << 6);
+            double t;
+            hit = cand_face(hot, g, __ldg(&g2[0]), __ldg(&g2[1]), __ldg(reinterpret_cast<const float4*>(g + 4)),
+                            r.rop, ldir, RB_FHUGE, t, front);
+        } else {
+            const double t = cand_other(kind, g, r.rop[0], r.rop[1], r.rop[2], ldir[0], ldir[1], ldir[2], RB_FHUGE);
+            hit = t != 0.0; front = t > 0.0;
+        }
+        if (!(hit && front)) return;
+    }
+    if (r.rot >= RB_FHUGE * .99 || !(r.rweight > 0.f)) return;      // rayorigin() refusals
+    const bool thru = (r.rod > 0) ^ (dot3(r.ron, ldir) > 0);
+    const int rt = thru ? RT_TSHADOW : RT_RSHADOW;
+    const bool refl = (rt & RT_RAYREFL) != 0;
+    QRay q;
+    q.org[0] = r.rop[0]; q.org[1] = r.rop[1]; q.org[2] = r.rop[2];
+    q.dir[0] = ldir[0]; q.dir[1] = ldir[1]; q.dir[2] = ldir[2];
+    q.rmax = refl ? 0.0 : (r.rmax > RB_FTINY) * (r.rmax - r.rot);
+    q.coef[0] = r.coef[0] * scval[0]; q.coef[1] = r.coef[1] * scval[1]; q.coef[2] = r.coef[2] * scval[2];
+    q.rweight = r.rweight;
+    q.row = r.row;
+    q.info = pack_info(r.crtype | rt, r.rlvl + (refl ? 1 : 0), r.rdepth);
+    q.rsrc = sn;
+    q.key_lo = (unsigned)key; q.key_hi = (unsigned)(key >> 32);
+    q.pad = 0;
+    push_ray(A, q);
+}
+
+// direct() for one LOCAL source: srcskip(), then nopart / flatpart / cylpart as an explicit-stack
+// pre-order walk (lower half first, like flt_partit / cyl_partit), one sample per leaf.
+__device__ void direct_local(const WaveArgs& A, const RayCtx& r, const NormDat& nd, int sn, unsigned nchild0) {
+    const SrcRec& s = A.S.srcs[sn];
+    if (s.flags & SF_SKIP) return;
+    const double* ro = r.rop;
+    auto dist2 = [](const double* a, const double* b) {
+        return (a[0] - b[0]) * (a[0] - b[0]) + (a[1] - b[1]) * (a[1] - b[1]) + (a[2] - b[2]) * (a[2] - b[2]);
+    };
+    if (s.flags & SF_PROX) {                             // srcsamp.c:28-31
+        const double lim = s.prox + s.srad;
+        if (dist2(ro, s.sloc) > lim * lim) return;
+    }
+    const unsigned long long base = (unsigned long long)nchild0 + (unsigned)A.S.nsrcs + (unsigned long long)sn * 64u;
+    const double ds = A.P.srcsizerat;
+    const bool flat = (s.flags & SF_FLAT) != 0, cyl = (s.flags & SF_CYL) != 0;
+    if (ds <= RB_FTINY || !(flat | cyl)) {               // nopart()
+        local_sample(A, r, nd, sn, child_key(r.key, base), 0, 0, 64, 64, false);
+        return;
+    }
+    double du2, dv2 = 0.0;
+    if (cyl) {                                           // cylpart(), srcsamp.c:229-264
+        const double rad2 = 1.365 * dot3(s.ss[1], s.ss[1]);
+        const double v[3] = {ro[0] - s.sloc[0], ro[1] - s.sloc[1], ro[2] - s.sloc[2]};
+        double d2 = dot3(v, s.ss[0]);
+        double safedist2 = dot3(s.ss[0], s.ss[0]);
+        d2 *= d2 / safedist2;
+        const double dist2cent = dot3(v, v);
+        d2 = dist2cent - d2;
+        if (d2 <= rad2) return;                          // point inside extended cylinder
+        safedist2 *= 4. * (double)r.rweight * (double)r.rweight / (ds * ds);
+        if (d2 <= 4. * rad2 || dist2cent >= safedist2) {
+            local_sample(A, r, nd, sn, child_key(r.key, base), 0, 0, 64, 64, false);
+            return;
+        }
+        du2 = safedist2;
+    } else {                                             // flatpart(), srcsamp.c:322-352
+        const double v[3] = {ro[0] - s.sloc[0], ro[1] - s.sloc[1], ro[2] - s.sloc[2]};
+        if (dot3(v, s.ss[2]) <= 0.) return;              // behind source
+        dv2 = 2. * (double)r.rweight / ds;
+        dv2 *= dv2;
+        du2 = dv2 * dot3(s.ss[0], s.ss[0]);
+        dv2 *= dot3(s.ss[1], s.ss[1]);
+    }
+    // explicit stack: centre point, integer centre/size, remaining budget mp, halvings of U and V
+    double scx[8], scy[8], scz[8];
+    short sct[8][2], ssz[8][2];
+    unsigned char smp[8], sa[8], sb[8];
+    int top = 0, leaf = 0;
+    scx[0] = s.sloc[0]; scy[0] = s.sloc[1]; scz[0] = s.sloc[2];
+    sct[0][0] = sct[0][1] = 0; ssz[0][0] = ssz[0][1] = 64; smp[0] = 64; sa[0] = sb[0] = 0;
+    bool many = false;
+    while (top >= 0) {
+        const double c[3] = {scx[top], scy[top], scz[top]};
+        const int ctU = sct[top][0], ctV = sct[top][1], szU = ssz[top][0], szV = ssz[top][1];
+        const int mp = smp[top], a = sa[top], b = sb[top];
+        top--;
+        const double lu2 = du2 * __hiloint2double((1023 - 2 * a) << 20, 0);      // du2 * 0.25^a, exact
+        const double lv2 = dv2 * __hiloint2double((1023 - 2 * b) << 20, 0);
+        const double d2 = dist2(ro, c);
+        const bool isleaf = cyl ? (mp < 2 || d2 >= lu2) : (mp < 2 || (d2 >= lu2 && d2 >= lv2));
+        if (isleaf) {
+            local_sample(A, r, nd, sn, child_key(r.key, base + (unsigned)leaf), ctU, ctV, szU, szV, many);
+            leaf++;
+            continue;
+        }
+        many = true;                                     // (the root split: np > 1 for every leaf)
+        const bool inU = cyl || (lu2 > lv2);
+        const double h = __hiloint2double((1023 - ((inU ? a : b) + 1)) << 20, 0);   // 0.5^(n+1), exact
+        const double* ax = inU ? s.ss[0] : s.ss[1];
+        const double nx = h * ax[0], ny = h * ax[1], nz = h * ax[2];
+        const int hs = (inU ? szU : szV) >> 1;
+        // push upper first so that the lower half is walked first
+        for (int up = 1; up >= 0; up--) {
+            top++;
+            const double sg = up ? 1.0 : -1.0;
+            scx[top] = c[0] + sg * nx; scy[top] = c[1] + sg * ny; scz[top] = c[2] + sg * nz;
+            sct[top][0] = (short)(inU ? ctU + (up ? hs : -hs) : ctU);
+            sct[top][1] = (short)(inU ? ctV : ctV + (up ? hs : -hs));
+            ssz[top][0] = (short)(inU ? hs : szU); ssz[top][1] = (short)(inU ? szV : hs);
+            smp[top] = (unsigned char)(mp / 2);
+            sa[top] = (unsigned char)(inU ? a + 1 : a); sb[top] = (unsigned char)(inU ? b : b + 1);
+        }
+    }
+}
+
 // Scenes with many sources (a 5-phase sun matrix has thousands): the shading
 // thread parks its state in a job queue and k_direct walks the source list
 // with one CTA per job, writing its shadow rays to consecutive queue slots.
@@ -685,7 +877,17 @@ __device__ __forceinline__ int m_light(const WaveArgs& A, RayCtx& r, const MatRe
         if (!A.P.backvis) raytrans(A, r);
         return 0;
     }
-    if (m.kind == MK_SPOT) { atomicOr(&A.C->errflag, RB_ERR_UNSUP_MAT); A.C->errobj = (unsigned)m.obj; return 0; }
+    if (m.kind == MK_SPOT) {                      // check for outside spot (source.c:778-779)
+        if (r.rsrc >= 0 && (S.srcs[r.rsrc].flags & SF_SPOT)) {
+            if (spotout(S.srcs[r.rsrc], r.org, r.dir)) return 0;
+        } else {                                  // seen directly: makespot() from the material's reals
+            SrcRec sp;
+            sp.spot_siz = (float)(2.0 * RB_PI * (1.0 - cos(RB_PI / 180.0 / 2.0 * (double)m.a[3])));
+            sp.spot_aim[0] = m.a[4]; sp.spot_aim[1] = m.a[5]; sp.spot_aim[2] = m.a[6];
+            sp.spot_flen = (float)normalize3(sp.spot_aim);
+            if (spotout(sp, r.org, r.dir)) return 0;
+        }
+    }
     if ((m.flags & 1) && A.P.need_values) {       // pattern under an emitter only matters for values
         atomicOr(&A.C->errflag, RB_ERR_UNSUP_MOD); A.C->errobj = (unsigned)m.obj;
     }

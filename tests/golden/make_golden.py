@@ -110,6 +110,36 @@ def main():
     assert r.returncode == 0, r.stderr
     np.save(HERE / "sunroom_ab0.npy", np.frombuffer(r.stdout, dtype=np.float64).reshape(48, 146, 3))
     g["sunroom_args"] = sun_args
+    # local light sources: polygon / triangle / pentagon / sphere / ring / cylinder
+    # emitters, an illum, a glow with a radius, a spotlight, occluders and a glass screen.  Deterministic
+    # reference runs (-u- -dj 0 -dt 0 -dc 1): irradiance at 500 sensors for three -ds settings, values seen
+    # by 500 view rays, and rcontrib coefficients per source modifier.
+    L = HERE / "lights"
+    r = subprocess.run([str(refrun.BIN / "oconv"), "-f", "lights.rad"], cwd=L, env=env, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    (L / "lights.oct").write_bytes(r.stdout)
+    rng = np.random.default_rng(3)
+    n = 400
+    pts = np.stack([rng.uniform(0.2, 7.8, n), rng.uniform(0.2, 5.8, n), np.full(n, 0.02)], 1)
+    sens = np.concatenate([pts, np.tile([0, 0, 1.], (n, 1))], 1)
+    pw = np.stack([np.full(100, 7.98), rng.uniform(0.2, 5.8, 100), rng.uniform(0.2, 2.8, 100)], 1)
+    sens = np.concatenate([sens, np.concatenate([pw, np.tile([-1., 0, 0], (100, 1))], 1)])
+    o = rng.uniform((0.5, 0.5, 0.3), (7.5, 5.5, 2.5), size=(500, 3))
+    d = rng.normal(size=(500, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([o, d], 1)
+    out = {"sensors": sens, "rays": rays}
+    det = ["-u-", "-ab", "0", "-dt", "0", "-dj", "0", "-dc", "1"]
+    for ds in ("0.2", "0", "0.05"):
+        out["irrad_ds" + ds] = refrun.rtrace(L / "lights.oct", sens, ["-I"] + det + ["-ds", ds], outform="d").reshape(-1, 3)
+    out["view_ds0.2"] = refrun.rtrace(L / "lights.oct", rays, det + ["-ds", ".2"], outform="d").reshape(-1, 3)
+    mods = ["lum", "lum2", "spot", "glw", "ill"]
+    margs = ["-u-", "-I", "-ab", "0", "-dj", "0", "-ds", ".2"]
+    for m in mods:
+        margs += ["-m", m]
+    out["rcontrib_ab0"] = refrun.rcontrib(L / "lights.oct", sens, margs).reshape(len(sens), -1, 3)
+    np.savez_compressed(HERE / "lights.npz", **out)
+    g["lights_mods"] = mods
     (HERE / "golden.json").write_text(json.dumps(g, indent=0))
     print("wrote", HERE / "golden.json")
 

@@ -305,14 +305,21 @@ def test_explicit_rejections(workdir, golden):
         ctx3.rtrace(np.array([[4, 5, 6, 0, 1, 0.0]]))         # value of a brightfunc sky is not built
     rad2 = workdir / "lamp.rad"
     rad2.write_text(scenegen.MATERIALS + "void light lamp\n0\n0\n3 10 10 10\n\n"
-                    "lamp polygon fixture\n0\n0\n12 0 0 3  1 0 3  1 1 3  0 1 3\n\n"
+                    "lamp polygon fixture\n0\n0\n12 0 0 3  0 1 3  1 1 3  1 0 3\n\n"
                     "floor_mat polygon fl\n0\n0\n12 0 0 0  4 0 0  4 4 0  0 4 0\n\n")
     oct2 = workdir / "lamp.oct"
     scenegen.build_octree(rad2, oct2)
     ctx4 = _lib.Context(0)
-    ctx4.load_octree(oct2)
-    with pytest.raises(_lib.RBError, match="local light source"):
-        ctx4.rtrace(np.array([[2, 2, 1, 0, 0, -1.0]]))
+    ctx4.load_octree(oct2)                                    # local emitters are built (test_local_light_sources)
+    ctx4.set_options(["-ab", "0"])
+    v, _ = ctx4.rtrace(np.array([[2, 2, 1, 0, 0, -1.0]]))
+    assert v[0, 0] > 0
+    rad3 = workdir / "conelamp.rad"
+    rad3.write_text("void light lamp\n0\n0\n3 10 10 10\n\nlamp cone shade\n0\n0\n8 0 0 3  0 0 2.5  .1 .4\n\n")
+    oct3 = workdir / "conelamp.oct"
+    scenegen.build_octree(rad3, oct3)
+    with pytest.raises(_lib.RBError, match="cannot be a light source"):
+        _lib.Context(0).load_octree(oct3)                     # the reference: "illegal material"
 
 
 # ------------------------------------------------------ Python boundaries ---
@@ -550,4 +557,43 @@ def test_sun_matrix_config5_miniature(G, golden, workdir):
     # direct part unchanged by the bounce in both
     lit = ref[:, :, 0] > 0
     assert np.all(g[:, :, 0][lit] >= ref[:, :, 0][lit] * (1 - 1e-5))
+
+
+def test_local_light_sources_vs_reference_golden(golden):
+    """local emitters through k_direct -- source partitioning (-ds),
+    srcray()'s proximity / spot tests, the aiming test against the source surface,
+    shadow rays through glass, m_light on the source.  Deterministic settings
+    (-dj 0, every source tested): values within 1e-5 of the reference rtrace /
+    rcontrib, identical zero pattern of the coefficient matrix."""
+    G = np.load(golden / "lights.npz")
+    octf = golden / "lights" / "lights.oct"
+    det = ["-ab", "0", "-dt", "0", "-dj", "0", "-dc", "1"]
+    for ds in ("0.2", "0", "0.05"):
+        ctx = _lib.Context(0)
+        ctx.load_octree(octf)
+        ctx.set_options(det + ["-ds", ds])
+        v, _ = ctx.rtrace(G["sensors"], flags=_lib.RB_IRRAD_RTRACE)
+        np.testing.assert_allclose(v, G["irrad_ds" + ds], rtol=1e-5, atol=1e-9)
+    ctx = _lib.Context(0)
+    ctx.load_octree(octf)
+    ctx.set_options(det + ["-ds", ".2"])
+    v, _ = ctx.rtrace(G["rays"])
+    np.testing.assert_allclose(v, G["view_ds0.2"], rtol=1e-5, atol=1e-9)
+    rc = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+    rc.load_octree(octf)
+    rc.set_options(["-ab", "0", "-dj", "0", "-ds", ".2"])
+    for m in ("lum", "lum2", "spot", "glw", "ill"):
+        rc.add_modifier(m, "", "0", 1)
+    m = rc.rcontrib(G["sensors"], flags=_lib.RB_IRRAD_RCONTRIB, dtype=np.float64)
+    assert np.array_equal(m > 0, G["rcontrib_ab0"] > 0)
+    np.testing.assert_allclose(m, G["rcontrib_ab0"], rtol=1e-5, atol=1e-12)
+    # jittered, one bounce: totals per emitter against the oracle (8 repetitions pooled, 4 % + noise floor)
+    big = np.tile(G["sensors"][:100], (8, 1))
+    rc.set_options(["-ab", "1", "-ad", "512", "-lw", "1e-3", "-dj", "0.9", "-ds", ".2"])
+    g = rc.rcontrib(big, flags=_lib.RB_IRRAD_RCONTRIB, dtype=np.float64)[:, :, 0].sum(0) / 8
+    s = port.Scene(octf, rcontrib=True, ambounce=1, ambdiv=512, minweight=1e-3, srcsizerat=0.2, seed=3)
+    for mm in ("lum", "lum2", "spot", "glw", "ill"):
+        s.add_modifier(mm)
+    o = s.rcontrib(big, irrad=2)[:, :, 0].sum(0) / 8
+    assert np.all(np.abs(g - o) <= 0.04 * o + 0.01)
 

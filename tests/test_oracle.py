@@ -110,3 +110,26 @@ def test_oracle_stochastic_agrees_with_reference(golden):
     sig = np.sqrt(refs.var(0, ddof=1) / reps + mine.var(0, ddof=1) / reps) + 1e-6
     assert np.all(np.abs(refs.mean(0) - mine.mean(0)) < 6 * sig + 5e-3 * refs.mean(0))
     assert mine[:, 2] == pytest.approx(np.pi, rel=1e-6)        # unobstructed sensor sums to pi
+
+
+def test_oracle_local_light_sources_vs_reference_golden(golden):
+    """local emitters (polygon, triangle, pentagon, sphere, ring,
+    cylinder; light / illum / glow-with-radius / spotlight), source partitioning
+    (-ds), the aiming test and shadow rays.  Deterministic settings: the oracle
+    reproduces the reference's values to float-output precision."""
+    G = np.load(golden / "lights.npz")
+    octf = golden / "lights" / "lights.oct"
+    for ds in ("0.2", "0", "0.05"):
+        s = port.Scene(octf, ambounce=0, dstrsrc=0.0, srcsizerat=float(ds))
+        v = s.rtrace(G["sensors"], irrad=1)["value"]
+        np.testing.assert_allclose(v, G["irrad_ds" + ds], rtol=1e-5, atol=1e-9)
+    s = port.Scene(octf, ambounce=0, dstrsrc=0.0, srcsizerat=0.2)
+    np.testing.assert_allclose(s.rtrace(G["rays"])["value"], G["view_ds0.2"], rtol=1e-5, atol=1e-9)
+    s = port.Scene(octf, rcontrib=True, ambounce=0, dstrsrc=0.0, srcsizerat=0.2)
+    for m in ("lum", "lum2", "spot", "glw", "ill"):
+        s.add_modifier(m)
+    m = s.rcontrib(G["sensors"], irrad=2)
+    assert np.array_equal(m > 0, G["rcontrib_ab0"] > 0)
+    np.testing.assert_allclose(m, G["rcontrib_ab0"], rtol=1e-5, atol=1e-12)
+    assert (G["rcontrib_ab0"][:, :, 0].sum(0) > 0).all()          # every kind of emitter contributes somewhere
+
