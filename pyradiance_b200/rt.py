@@ -158,8 +158,8 @@ def rtrace_main(argv: Sequence[str], stdin: bytes, device: int = 0) -> bytes:
                 raise RBError(f"unsupported output option '-o{ch}' ({_RT_UNSUPPORTED_SPEC[ch]}) in the CUDA path")
             if ch not in "odvLpNnsmMwc~":
                 raise RBError(f"unrecognized output option '{ch}'")
-        if outform == "c":
-            raise RBError("color (RGBE) output format is not built")
+        if outform == "c" and outvals != "v":
+            raise RBError("color format only with -ov" + (" (-or, -ox are not built)" if outvals[:1] in "rx" else ""))
         want_values = "v" in outvals
         p = ctx.get_params()
         if (imm_irrad or p.do_irrad) and not want_values:
@@ -196,6 +196,26 @@ def _names(ctx, idx, none="*", void="void"):
             cache[i] = ctx.object_name(i) if i >= 0 else None
         out.append(cache[i])
     return out
+
+
+def _rgbe(rgb: np.ndarray, single: bool = False) -> bytes:
+    """Radiance 4-byte RGBE encoding of [n, 3] values.  single=False restates
+    setcolr() (common/color.c:797-823, arithmetic in double: what rtrace's -f?c
+    does); single=True restates scolor2scolr() (color.c:299-320, the scale factor
+    and the products are COLORV = float: what rcontrib's -f?c does)."""
+    v = np.ascontiguousarray(rgb, dtype=np.float32 if single else np.float64).reshape(-1, 3)
+    d = v.max(axis=1)
+    out = np.zeros((v.shape[0], 4), dtype=np.uint8)
+    ok = d > 1e-32
+    if ok.any():
+        m, e = np.frexp(d[ok].astype(np.float64))
+        scale = m * 256.0 / d[ok].astype(np.float64)
+        if single:
+            scale = scale.astype(np.float32)
+        prod = v[ok] * scale[:, None]                      # float32 * float32 stays float32
+        out[ok, :3] = np.where(v[ok] > 0, prod.astype(np.int64), 0).astype(np.uint8)
+        out[ok, 3] = (e + 128).astype(np.uint8)
+    return out.tobytes()
 
 
 def _format_rtrace(ctx, rays, values, res, outvals, outform) -> bytes:
@@ -235,6 +255,8 @@ def _format_rtrace(ctx, rays, values, res, outvals, outform) -> bytes:
             raise RBError("unsupported output option '-oM' in the CUDA path")
         elif ch == "~":
             cols.append(("s", ["~"] * n))
+    if outform == "c":                 # rtrace.c:999-1002: the float radiance through setcolr()
+        return _rgbe(values.astype(np.float32).astype(np.float64))
     if outform == "a":
         lines = []
         for i in range(n):
@@ -438,13 +460,11 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
             raise RBError("missing required modifier argument")
         if i != len(argv) - 1:
             raise RBError("missing octree argument" if i >= len(argv) else f"command line error at '{argv[i]}'")
-        if outform == "c":
-            raise RBError("color (RGBE) output format is not built")
         ctx.load_octree(argv[i])
         rays = _parse_rays(stdin, inform)
         flags = (_lib.RB_IRRAD_RCONTRIB if imm_irrad else 0) | (_lib.RB_FLAG_LIMDIST if lim_dist else 0) | \
                 (_lib.RB_FLAG_CONTRIB if contrib else 0)
-        dt = np.float32 if outform == "f" else np.float64
+        dt = np.float32 if outform in "fc" else np.float64
         if accumulate > 0:
             mat = ctx.rcontrib(rays, accum=accumulate, flags=flags, dtype=dt)
         else:
@@ -491,7 +511,9 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
             if reclen == 1 and xres > 0 and yres > 0:
                 out += f"-Y {yres} +X {xres}\n".encode()
             sub = mat[:, st["cols"], :]
-            if outform == "a":
+            if outform == "c":         # rc2.c:324-331: float coefficients through scolor_scolr()
+                out += _rgbe(sub.reshape(-1, 3), single=True)
+            elif outform == "a":
                 flat = sub.reshape(sub.shape[0], -1)
                 out += ("".join("".join("%.6e\t" % v for v in row) + "\n" for row in flat)).encode()
             else:

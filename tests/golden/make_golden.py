@@ -138,6 +138,15 @@ def main():
     for m in mods:
         margs += ["-m", m]
     out["rcontrib_ab0"] = refrun.rcontrib(L / "lights.oct", sens, margs).reshape(len(sens), -1, 3)
+    # the same two runs in the 4-byte RGBE output format (-f?c)
+    r = subprocess.run([str(refrun.BIN / "rtrace"), "-h", "-fdc", "-ov"] + det + ["-ds", ".2", "lights.oct"], cwd=L, env=env,
+                       input=rays.tobytes(), capture_output=True)
+    assert r.returncode == 0, r.stderr
+    out["view_rgbe"] = np.frombuffer(r.stdout, dtype=np.uint8).reshape(-1, 4)
+    r = subprocess.run([str(refrun.BIN / "rcontrib"), "-h", "-fdc"] + margs + ["lights.oct"], cwd=L, env=env,
+                       input=sens.tobytes(), capture_output=True)
+    assert r.returncode == 0, r.stderr
+    out["rcontrib_rgbe"] = np.frombuffer(r.stdout, dtype=np.uint8).reshape(-1, 4)
     np.savez_compressed(HERE / "lights.npz", **out)
     g["lights_mods"] = mods
     (HERE / "golden.json").write_text(json.dumps(g, indent=0))

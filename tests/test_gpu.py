@@ -597,3 +597,28 @@ def test_local_light_sources_vs_reference_golden(golden):
     o = s.rcontrib(big, irrad=2)[:, :, 0].sum(0) / 8
     assert np.all(np.abs(g - o) <= 0.04 * o + 0.01)
 
+
+def test_rgbe_output_format(golden):
+    """rtrace -fdc -ov and rcontrib -fdc through the Python boundary: the 4-byte
+    RGBE stream of the reference, allowing the last mantissa bit to differ where
+    a value sits on a rounding boundary (values agree to 1e-6, not bit for bit)."""
+    G = np.load(golden / "lights.npz")
+    octf = golden / "lights" / "lights.oct"
+    out = pr.rtrace(G["rays"].tobytes(), octf, header=False, inform="d", outform="c", outspec="v",
+                    params=["-ab", "0", "-dt", "0", "-dj", "0", "-dc", "1", "-ds", ".2"])
+    mine = np.frombuffer(out, dtype=np.uint8).reshape(-1, 4).astype(int)
+    ref = G["view_rgbe"].astype(int)
+    assert mine.shape == ref.shape
+    assert np.array_equal(mine[:, 3], ref[:, 3]) and np.abs(mine - ref).max() <= 1 and (mine != ref).mean() < 0.01
+    rc = pr.Rcontrib(G["sensors"].tobytes(), octf, inform="d", outform="c", params=["-I", "-ab", "0", "-dj", "0", "-ds", ".2", "-h"])
+    for m in G_mods(golden):
+        rc.add_modifier(m)
+    mine = np.frombuffer(rc(), dtype=np.uint8).reshape(-1, 4).astype(int)
+    ref = G["rcontrib_rgbe"].astype(int)
+    assert mine.shape == ref.shape
+    assert np.abs(mine - ref).max() <= 1 and (mine != ref).mean() < 0.01
+
+
+def G_mods(golden):
+    return json.load(open(golden / "golden.json"))["lights_mods"]
+

@@ -276,3 +276,17 @@ def test_volume_rejections(workdir):
     # our own builder refuses volumes; the loader reports a missing nested octree by name
     with pytest.raises(_lib.RBError):
         scenegen.build_octree(workdir / "noinst.rad", workdir / "noinst.oct")
+
+
+def test_rgbe_encoder_matches_reference_bytes(golden):
+    """-f?c output: setcolr() for rtrace values, scolor2scolr()
+    for rcontrib coefficients -- byte-identical to the reference's output when
+    fed the reference's own double-format values."""
+    from pyradiance_b200 import rt
+    G = np.load(golden / "lights.npz")
+    mine = np.frombuffer(rt._rgbe(G["view_ds0.2"].astype(np.float32).astype(np.float64)), dtype=np.uint8).reshape(-1, 4)
+    assert np.array_equal(mine, G["view_rgbe"])
+    mine = np.frombuffer(rt._rgbe(G["rcontrib_ab0"].astype(np.float32).reshape(-1, 3), single=True), dtype=np.uint8)
+    assert np.array_equal(mine.reshape(-1, 4), G["rcontrib_rgbe"])
+    assert rt._rgbe(np.zeros((2, 3))) == bytes(8)
+
