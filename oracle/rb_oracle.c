@@ -53,7 +53,7 @@ enum { PRIMARY = 01, RSHADOW = 02, REFLECTED = 04, REFRACTED = 010, TRANS = 020,
 
 enum { T_OTHER = 0, T_POLYGON, T_CONE, T_SPHERE, T_RING, T_CYLINDER, T_CUP, T_BUBBLE, T_TUBE, T_SOURCE, T_INSTANCE,
        T_MESH, T_ALIAS, T_PLASTIC, T_METAL, T_GLASS, T_TRANS, T_GLOW, T_LIGHT, T_ILLUM, T_SPOT, T_TRANSP_MAT,
-       T_OTHER_MAT, T_PATTERN };
+       T_OTHER_MAT, T_PATTERN, T_BRIGHTFUNC };
 
 typedef struct {
     int omod, otype;
@@ -156,7 +156,7 @@ static int type_of(const char* n) {
         {"metfunc", T_OTHER_MAT}, {"mirror", T_OTHER_MAT}, {"transfunc", T_OTHER_MAT}, {"BRTDfunc", T_OTHER_MAT},
         {"BSDF", T_OTHER_MAT}, {"WGMDfunc", T_OTHER_MAT}, {"plasdata", T_OTHER_MAT}, {"metdata", T_OTHER_MAT},
         {"transdata", T_OTHER_MAT}, {"antimatter", T_OTHER_MAT}, {"prism1", T_OTHER_MAT}, {"prism2", T_OTHER_MAT},
-        {"ashik2", T_OTHER_MAT}, {NULL, 0}};
+        {"ashik2", T_OTHER_MAT}, {"brightfunc", T_BRIGHTFUNC}, {NULL, 0}};
     int i;
     for (i = 0; tab[i].n; i++) if (!strcmp(n, tab[i].n)) return tab[i].t;
     return T_PATTERN;     /* patterns, textures, mixtures: anything else is a non-material modifier */
@@ -1360,6 +1360,38 @@ static int m_glass(orc_scene* s, const OBJ* m, RAY* r) {
     return 1;
 }
 
+/* gen/skybright.cal:21-44 and gen/perezlum.cal:18-39 (rayinit.cal: Acos(x) = acos(bound(-1,x,1)),
+   if(a,b,c) = a > 0 ? b : c, select(N,...) picks argument int(N+.5)) */
+static double cal_Acos(double x) { return acos(x < -1 ? -1 : x > 1 ? 1 : x); }
+static int sky_brightfunc(const OBJ* p, const double* D, double* bval) {
+    const double* A = p->fargs - 1;      /* A[1]..A[n] */
+    const char* file; const char* var;
+    if (p->otype != T_BRIGHTFUNC || p->nsargs != 2) return 0;       /* extra sargs = a transform: not restated */
+    var = p->sargs[0]; file = p->sargs[1];
+    if (!strcmp(file, "skybright.cal") && !strcmp(var, "skybr") && p->nfargs >= 7) {
+        double cosgamma = D[0] * A[5] + D[1] * A[6] + D[2] * A[7];
+        double gamma = cal_Acos(cosgamma), zt = cal_Acos(A[7]), eta = cal_Acos(D[2]), sky;
+        int sel = (int)(A[1] + .5);
+        if (sel == 1) sky = A[2] * (.91 + 10 * exp(-3 * gamma) + .45 * cosgamma * cosgamma) * (D[2] - .01 > 0 ? 1.0 - exp(-.32 / D[2]) : 1.0) / A[4];
+        else if (sel == 2) sky = A[2] * (1 + 2 * D[2]) / 3;
+        else if (sel == 3) sky = A[2];
+        else if (sel == 4) sky = A[2] * ((1.35 * sin(5.631 - 3.59 * eta) + 3.12) * sin(4.396 - 2.6 * zt) + 6.37 - eta) / 2.326 *
+                                 exp(gamma * -.563 * ((2.629 - eta) * (1.562 - zt) + .812)) / A[4];
+        else return 0;
+        { double a = pow(D[2] + 1.01, 10), b = pow(D[2] + 1.01, -10); *bval = (a * sky + b * A[3]) / (a + b); }
+        return 1;
+    }
+    if (!strcmp(file, "perezlum.cal") && !strcmp(var, "skybright") && p->nfargs >= 10) {
+        double cosgamma = D[0] * A[8] + D[1] * A[9] + D[2] * A[10];
+        double gamma = cal_Acos(cosgamma), sky;
+        double dz = (D[2] - 0.01 > 0) ? D[2] : 0.01;
+        sky = A[1] * (1 + A[3] * exp(A[4] / dz)) * (1 + A[5] * exp(A[6] * gamma) + A[7] * cosgamma * cosgamma);
+        { double a = pow(D[2] + 1.01, 10), b = pow(D[2] + 1.01, -10); *bval = (a * sky + b * A[2]) / (a + b); }
+        return 1;
+    }
+    return 0;
+}
+
 static int m_light(orc_scene* s, const OBJ* m, RAY* r) {
     int isglow = m->otype == T_GLOW, k;
 #define distglow(d) (isglow && m->fargs[3] >= -FTINY && (d) > m->fargs[3])
@@ -1383,9 +1415,18 @@ static int m_light(orc_scene* s, const OBJ* m, RAY* r) {
         sp.spot_flen = (float)normalize(sp.spot_aim);
         if (spotout(&sp, r)) return 1;
     }
-    /* a pattern under an emitter (e.g. brightfunc sky) is ignored: the value is the plain
-       material RGB; coefficients (-V-) do not depend on it.  Tests compare geometry only there. */
-    for (k = 0; k < 3; k++) r->rcol[k] = (float)m->fargs[k];
+    /* raytexture(r, m->omod): the patterns under the emitter scale r->pcol (p_func.c:49-69).
+       Built: brightfunc with gen/skybright.cal `skybr` (gensky) or gen/perezlum.cal `skybright`
+       (gendaylight), no transform.  Anything else is ignored here (the value is then the plain
+       material RGB; coefficients (-V-) do not depend on it) -- tests compare geometry only there. */
+    {
+        float pcol = 1.f; int pm;
+        for (pm = m->omod; pm >= 0; pm = s->objs[pm].omod) {
+            double b;
+            if (sky_brightfunc(&s->objs[pm], r->rdir, &b)) pcol *= (float)b;
+        }
+        for (k = 0; k < 3; k++) r->rcol[k] = (float)m->fargs[k] * pcol;
+    }
     return 1;
 #undef distglow
 }

@@ -41,6 +41,7 @@ struct DScene {
     const double* __restrict__ geom;
     const MatRec* __restrict__ mats;
     const SrcRec* __restrict__ srcs;
+    const PatRec* __restrict__ pats;
     const int* __restrict__ otrack;
 };
 

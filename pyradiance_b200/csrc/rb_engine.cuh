@@ -62,7 +62,7 @@ private:
     bool user_stream_ = false;
     DScene S_{};
     void *d_nodes_ = nullptr, *d_leaf_ = nullptr, *d_hdr_ = nullptr, *d_geom_ = nullptr,
-         *d_mats_ = nullptr, *d_srcs_ = nullptr, *d_otrack_ = nullptr, *d_bins_ = nullptr;
+         *d_mats_ = nullptr, *d_srcs_ = nullptr, *d_pats_ = nullptr, *d_otrack_ = nullptr, *d_bins_ = nullptr;
     int nbins_ = 0, ncols_ = 0;
     QRay* q_[2] = {nullptr, nullptr};
     QHemi* h_[2] = {nullptr, nullptr};

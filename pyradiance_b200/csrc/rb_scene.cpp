@@ -965,13 +965,48 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
             r.kind = MK_UNSUPPORTED;
             note_unsupported("unsupported material type " + m.tname + " \"" + m.name + "\"");
         }
-        // any pattern/texture/mixture under the material poisons it (raytexture)
+        // patterns under the material (raytexture(r, m->omod)): the two sky brightness
+        // functions are built as native code, anything else poisons the material
+        r.pat = -1;
+        int lastpat = -1;
         for (int q = m.omod, g = 0; q >= 0 && g < 10000; q = sc.objs[q].omod, g++) {
-            int t = sc.objs[q].otype;
-            if (t == OT_ALIAS && sc.objs[q].sargs.empty()) continue;
-            r.flags |= 1;
-            note_unsupported("unsupported modifier type " + sc.objs[q].tname + " \"" + sc.objs[q].name +
-                             "\" (under " + m.tname + " \"" + m.name + "\")");
+            const Object& po = sc.objs[q];
+            int t = po.otype;
+            if (t == OT_ALIAS && po.sargs.empty()) continue;
+            PatRec pr; memset(&pr, 0, sizeof(pr));
+            pr.next = -1;
+            if (po.tname == "brightfunc" && po.sargs.size() >= 2) {
+                if (po.sargs[1] == "skybright.cal" && po.sargs[0] == "skybr" && po.fargs.size() >= 7) pr.kind = PAT_SKYBRIGHT;
+                else if (po.sargs[1] == "perezlum.cal" && po.sargs[0] == "skybright" && po.fargs.size() >= 10) pr.kind = PAT_PEREZLUM;
+            }
+            Xf x; std::string xe;
+            if (pr.kind && !parse_xf(po.sargs, 2, x, xe)) pr.kind = 0;
+            if (pr.kind) {
+                for (size_t k = 0; k < 10 && k < po.fargs.size(); k++) pr.a[k] = po.fargs[k];
+                // backward transform = inverse of the forward 3x3, divided by the backward scale (= 1 / forward scale)
+                const double (*f)[4] = x.m;
+                double det = f[0][0] * (f[1][1] * f[2][2] - f[1][2] * f[2][1]) - f[0][1] * (f[1][0] * f[2][2] - f[1][2] * f[2][0]) +
+                             f[0][2] * (f[1][0] * f[2][1] - f[1][1] * f[2][0]);
+                if (det == 0.0) pr.kind = 0;
+                else {
+                    double inv[3][3];
+                    inv[0][0] = (f[1][1] * f[2][2] - f[1][2] * f[2][1]) / det; inv[0][1] = (f[0][2] * f[2][1] - f[0][1] * f[2][2]) / det; inv[0][2] = (f[0][1] * f[1][2] - f[0][2] * f[1][1]) / det;
+                    inv[1][0] = (f[1][2] * f[2][0] - f[1][0] * f[2][2]) / det; inv[1][1] = (f[0][0] * f[2][2] - f[0][2] * f[2][0]) / det; inv[1][2] = (f[0][2] * f[1][0] - f[0][0] * f[1][2]) / det;
+                    inv[2][0] = (f[1][0] * f[2][1] - f[1][1] * f[2][0]) / det; inv[2][1] = (f[0][1] * f[2][0] - f[0][0] * f[2][1]) / det; inv[2][2] = (f[0][0] * f[1][1] - f[0][1] * f[1][0]) / det;
+                    const double bsca = 1.0 / fabs(x.sca);
+                    for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) pr.xb[a * 3 + b] = inv[a][b] / bsca;
+                }
+            }
+            if (!pr.kind) {
+                r.flags |= 1;
+                note_unsupported("unsupported modifier type " + po.tname + " \"" + po.name +
+                                 "\" (under " + m.tname + " \"" + m.name + "\")");
+                continue;
+            }
+            int pi = (int)fs.pats.size();
+            fs.pats.push_back(pr);
+            if (lastpat < 0) r.pat = pi; else fs.pats[lastpat].next = pi;
+            lastpat = pi;
         }
         int slot = (int)fs.mats.size();
         matslot[mi] = slot;

@@ -102,8 +102,21 @@ struct MatRec {          // 64 bytes
     int nargs;
     float a[8];          // real args (as given)
     int alt;             // illum: alternate material slot (-1 = void/none)
-    int pad[3];
+    int pat;             // first pattern record under the material (-1 = none)
+    int pad[2];
 };
+
+// A pattern under a material that is built as native code: brightfunc with
+// gen/skybright.cal `skybr` (gensky) or gen/perezlum.cal `skybright` (gendaylight).
+struct PatRec {
+    int kind;            // PAT_SKYBRIGHT / PAT_PEREZLUM
+    int next;            // next pattern of the same material's chain, -1 = end
+    int pad[2];
+    double a[10];        // A1..A10
+    double xb[9];        // backward transform of the function's coordinates, already divided by its scale:
+                         // D' = D . xb (func.c:455-458)
+};
+enum : int { PAT_SKYBRIGHT = 1, PAT_PEREZLUM = 2 };
 
 struct SrcRec {          // distant & local sources (source.h SRCREC subset)
     double sloc[3];      // direction (distant) or position
@@ -128,6 +141,7 @@ struct FlatScene {
     std::vector<double>  geom;       // packed geometry records
     std::vector<MatRec>  mats;
     std::vector<SrcRec>  srcs;
+    std::vector<PatRec>  pats;
     std::vector<int>     nodes;      // same encoding as Scene
     std::vector<int>     leafpool;
     std::vector<int>     leaf2;      // (count,0),(id, geom offset)... pairs; nodes[] index these

@@ -149,6 +149,22 @@ def main():
     out["rcontrib_rgbe"] = np.frombuffer(r.stdout, dtype=np.uint8).reshape(-1, 4)
     np.savez_compressed(HERE / "lights.npz", **out)
     g["lights_mods"] = mods
+    # sky brightness patterns under glow emitters (brightfunc skybright.cal `skybr`, perezlum.cal
+    # `skybright`): values seen by 2000 rays in all directions, for the reference's own
+    # trace.oct (perezlum), a rotated sunny sky and an overcast / intermediate pair
+    S = HERE / "sky"
+    rng = np.random.default_rng(1)
+    d = rng.normal(size=(2000, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    skyrays = np.concatenate([np.tile([20., 20., 20.], (2000, 1)), d], 1)
+    sky = {"rays": skyrays}
+    sky["trace"] = refrun.rtrace(HERE / "trace.oct", skyrays, ["-ab", "0"], outform="d").reshape(-1, 3)
+    for name in ("skies", "overcast"):
+        r = subprocess.run([str(refrun.BIN / "oconv"), "-f", f"{name}.rad"], cwd=S, env=env, capture_output=True)
+        assert r.returncode == 0, r.stderr
+        (S / f"{name}.oct").write_bytes(r.stdout)
+        sky[name] = refrun.rtrace(S / f"{name}.oct", skyrays, ["-ab", "0"], outform="d").reshape(-1, 3)
+    np.savez_compressed(HERE / "sky.npz", **sky)
     (HERE / "golden.json").write_text(json.dumps(g, indent=0))
     print("wrote", HERE / "golden.json")
 

@@ -133,3 +133,14 @@ def test_oracle_local_light_sources_vs_reference_golden(golden):
     np.testing.assert_allclose(m, G["rcontrib_ab0"], rtol=1e-5, atol=1e-12)
     assert (G["rcontrib_ab0"][:, :, 0].sum(0) > 0).all()          # every kind of emitter contributes somewhere
 
+
+def test_oracle_sky_brightness_patterns_vs_reference_golden(golden):
+    """brightfunc skies under glow emitters: gen/perezlum.cal (the reference's own
+    trace.oct) and gen/skybright.cal overcast + intermediate branches, restated as
+    closed forms -- the values the reference rtrace reports for 2000 directions."""
+    G = np.load(golden / "sky.npz")
+    for name, octf in (("trace", golden / "trace.oct"), ("overcast", golden / "sky" / "overcast.oct")):
+        v = port.Scene(octf, ambounce=0).rtrace(G["rays"])["value"]
+        np.testing.assert_allclose(v, G[name], rtol=2e-6, atol=1e-9)
+    assert G["trace"].min() > 1 and G["overcast"].max() > 10
+
