@@ -85,9 +85,9 @@ typedef struct rb_ray_result {
 /* counters of the last compute call (device-side, summed over launches) */
 typedef struct rb_stats {
     uint64_t nrays;        /* rays walked through the octree (localhit calls) */
-    uint64_t nodes;        /* octree child words read */
-    uint64_t leafents;     /* leaf-set entries read */
-    uint64_t prims;        /* primitive intersection tests */
+    uint64_t nodes;        /* octree child words read   } counted only by developer builds   */
+    uint64_t leafents;     /* leaf-set entries read     } (-DRB_WALK_STATS=1); 0 otherwise:  */
+    uint64_t prims;        /* primitive intersection tests } the walker keeps no statistics registers */
     uint64_t contribs;     /* contributions accumulated */
     uint64_t launches;     /* kernels launched */
     uint64_t wave_launches;/* launches of the dominant (trace) kernel */
