@@ -244,6 +244,45 @@ def test_stochastic_bins_office_vs_oracle(office2k):
     assert np.all(np.abs(pg[nz] - po[nz]) <= 4 * sig[nz] + 0.01 * po[nz])
 
 
+def test_stochastic_per_bin_vs_high_sample_reference(office2k):
+    """SURVEY 8(d) parity protocol, literally: the reference run with 32x the
+    samples (`-c 32` accumulation of the same sensors) is the truth c*; every
+    bin of the GPU matrix with >= 30 expected first-level hits must satisfy
+    |c_gpu - c*| <= 4 sqrt(sigma_gpu^2 + sigma_ref^2) for >= 99.9 % of such
+    bins (sigma^2 from the Poisson variance of the hit count: stratified
+    sampling has less), row sums within 1 %; and the same statistic between
+    two halves of the reference's own repetitions sets the scale: the GPU's
+    normalised chi^2 may not exceed theirs by more than 50 %."""
+    if not refrun.available():
+        pytest.skip("oracle/_ref (the unmodified reference binaries) is not on this box")
+    n, acc = 8, 32
+    x = np.linspace(4, 36, n)
+    d = np.array([0.0, -1.0, 0.3]) / np.linalg.norm([0.0, -1.0, 0.3])
+    sens = np.stack([x, np.full(n, 1.5), np.full(n, 1.8)] + [np.full(n, v) for v in d], axis=1)
+    opts = ["-ab", "2", "-ad", "2048", "-lw", "5e-4"]
+    w = np.pi / 2048                                   # weight of one first-level sample
+    rep = np.repeat(sens, acc, axis=0)                 # acc consecutive copies of each sensor
+    ref_all = refrun.rcontrib(office2k, rep, ["-I"] + opts + RB_ARGS, nproc=8).reshape(n, acc, 145, 3)[..., 0]
+    cstar = ref_all.mean(1)                            # 32x samples
+    ctx = rc_ctx(office2k, opts)
+    g = ctx.rcontrib(rep, flags=_lib.RB_IRRAD_RCONTRIB, accum=acc).astype(np.float64)[:, :, 0]     # same job on the GPU (also 32x)
+    g1 = ctx.rcontrib(sens, flags=_lib.RB_IRRAD_RCONTRIB).astype(np.float64)[:, :, 0]              # and a single-sample run
+    big = cstar * acc >= 30 * w                        # >= 30 expected hits in a 32x run
+    assert big.sum() >= 40
+    for name, c, k in (("32x", g, acc), ("1x", g1, 1)):
+        sel = cstar * k >= 30 * w                      # >= 30 expected hits in THIS run
+        sig = np.sqrt(cstar * w / k + cstar * w / acc)
+        z = np.abs(c - cstar)[sel] / sig[sel]
+        assert sel.sum() == 0 or (z <= 4).mean() >= 0.999, (name, z.max())
+        assert np.all(np.abs(c.sum(1) - cstar.sum(1)) <= 0.01 * cstar.sum(1) + 4 * np.sqrt(cstar.sum(1) * w * (1 / k + 1 / acc))), name
+    # reference vs reference: two halves of its own repetitions give the chi^2 scale
+    ha, hb = ref_all[:, :acc // 2].mean(1), ref_all[:, acc // 2:].mean(1)
+    chi_ref = (((ha - hb) ** 2)[big] / (2 * cstar[big] * w / (acc // 2))).mean()
+    gh = ctx.rcontrib(np.repeat(sens, acc // 2, axis=0), flags=_lib.RB_IRRAD_RCONTRIB, accum=acc // 2, row_base=10_000).astype(np.float64)[:, :, 0]
+    chi_gpu = (((gh - ha) ** 2)[big] / (2 * cstar[big] * w / (acc // 2))).mean()
+    assert chi_gpu <= 1.5 * chi_ref + 0.1, (chi_gpu, chi_ref)
+
+
 # ------------------------------------------------------------- invariances --
 def test_result_independent_of_batching_and_sharding(office2k):
     sens = scenegen.office_sensors(64, seed=9)
