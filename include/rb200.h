@@ -181,6 +181,10 @@ int rb_host_unregister(rb_ctx* ctx, void* p);
 /* own octree builder for synthetic scenes (next-row f3): text scene -> frozen .oct */
 int rb_oconv(const char* rad_path, const char* oct_path, int objlim, int maxres,
              char* errbuf, size_t errlen);
+/* oconv -f [-i include_octree] rad_paths...: what rfluxmtx runs to put its receivers into the scene
+ * (util/rfluxmtx.c:139-187 oconv_command); include_octree may be NULL */
+int rb_oconv_files(const char* const* rad_paths, int npaths, const char* include_octree, const char* oct_path,
+                   int objlim, int maxres, char* errbuf, size_t errlen);
 
 #ifdef __cplusplus
 }

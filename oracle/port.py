@@ -25,7 +25,7 @@ class orc_params(C.Structure):
 RESULT_DTYPE = np.dtype([("rop", "<f8", 3), ("ron", "<f8", 3), ("rot", "<f8"), ("rod", "<f8"),
                          ("robj", "<i4"), ("omod", "<i4"), ("value", "<f8", 3)])
 
-BIN_CONST, BIN_REINHARTB, BIN_REINHART, BIN_KLEMS_FULL, BIN_HEMI, BIN_KLEMS_HALF, BIN_KLEMS_QUARTER = range(7)
+BIN_CONST, BIN_REINHARTB, BIN_REINHART, BIN_KLEMS_FULL, BIN_HEMI, BIN_KLEMS_HALF, BIN_KLEMS_QUARTER, BIN_SHIRCHIU = range(8)
 
 _lib = None
 

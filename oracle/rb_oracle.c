@@ -596,6 +596,19 @@ double orc_bin(int fn, int mf, const double N[3], const double U[3], double rhs,
         double alt = deg_asin(D[2]), azi = deg_atan2(D[0], D[1]);
         return -alt > 0 ? 0 : reinhart_patch(alt, azi, mf) + 1;
     }
+    case ORC_BIN_SHIRCHIU: {       /* util/disk2square.cal: scbin with SCdim = mf */
+        double dz = -D[0] * N[0] - D[1] * N[1] - D[2] * N[2];
+        double rx = -rhs * (D[0] * (U[1] * N[2] - U[2] * N[1]) + D[1] * (U[2] * N[0] - U[0] * N[2]) + D[2] * (U[0] * N[1] - U[1] * N[0]));
+        double ry = D[0] * U[0] + D[1] * U[1] + D[2] * U[2] + dz * (N[0] * U[0] + N[1] * U[1] + N[2] * U[2]);
+        double den2 = rx * rx + ry * ry, radf = cal_if(den2 - 1e-7, sqrt((1 - dz * dz) / den2), 0);
+        double dx = rx * radf, dy = -ry * radf, r = sqrt(dx * dx + dy * dy), phi = atan2(dy, dx), a, b;
+        int rgn;
+        phi = cal_if(-phi - PI / 4, phi + 2 * PI, phi);
+        rgn = (int)(floor((phi + PI / 4) / (PI / 2)) + 1 + .5);
+        a = rgn == 1 ? r : rgn == 2 ? (PI / 2 - phi) * r / (PI / 4) : rgn == 3 ? -r : rgn == 4 ? (phi - 3 * PI / 2) * r / (PI / 4) : r;
+        b = rgn == 1 ? phi * r / (PI / 4) : rgn == 2 ? r : rgn == 3 ? (PI - phi) * r / (PI / 4) : -r;
+        return cal_if(dz, floor((a + 1) / 2 * mf) * mf + floor((b + 1) / 2 * mf), -1);
+    }
     default: {
         double pol = deg_acos(-D[0] * N[0] - D[1] * N[1] - D[2] * N[2]);
         double y = -D[0] * U[0] - D[1] * U[1] - D[2] * U[2] + (N[0] * D[0] + N[1] * D[1] + N[2] * D[2]) * (N[0] * U[0] + N[1] * U[1] + N[2] * U[2]);

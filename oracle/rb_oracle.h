@@ -28,7 +28,7 @@ typedef struct orc_params {
 
 /* bin function ids (same meaning as the .cal files, see rb_oracle.c) */
 enum { ORC_BIN_CONST = 0, ORC_BIN_REINHARTB = 1, ORC_BIN_REINHART = 2, ORC_BIN_KLEMS_FULL = 3, ORC_BIN_HEMI = 4,
-       ORC_BIN_KLEMS_HALF = 5, ORC_BIN_KLEMS_QUARTER = 6 };
+       ORC_BIN_KLEMS_HALF = 5, ORC_BIN_KLEMS_QUARTER = 6, ORC_BIN_SHIRCHIU = 7 };
 
 typedef struct orc_result {
     double rop[3], ron[3], rot, rod;

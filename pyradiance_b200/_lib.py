@@ -96,6 +96,8 @@ SYMBOLS = [
     ("rb_host_register", C.c_int, [_P, _P, C.c_size_t]),
     ("rb_host_unregister", C.c_int, [_P, _P]),
     ("rb_oconv", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
+    ("rb_oconv_files", C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p,
+                                 C.c_size_t]),
 ]
 
 _lib = None
@@ -319,6 +321,17 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.rb_device_sync(self.h))
+
+
+def oconv_files(rad_paths, oct_path, include_octree=None, objlim=6, maxres=16384):
+    """Own octree builder, `oconv -f [-i include_octree] rad_paths...` (C ABI rb_oconv_files)."""
+    lib = load_library()
+    buf = C.create_string_buffer(1024)
+    arr = (C.c_char_p * len(rad_paths))(*[os.fspath(p).encode() for p in rad_paths])
+    rv = lib.rb_oconv_files(arr, len(rad_paths), os.fspath(include_octree).encode() if include_octree else None,
+                            os.fspath(oct_path).encode(), objlim, maxres, buf, 1024)
+    if rv < 0:
+        raise RBError(buf.value.decode())
 
 
 def oconv_file(rad_path, oct_path, objlim=6, maxres=16384):

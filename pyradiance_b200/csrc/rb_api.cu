@@ -259,6 +259,14 @@ static bool make_binspec(rb_ctx* c, const std::string& params, const std::string
         if (b.mf < 1) { err = "illegal MF"; return false; }
         return true;
     }
+    if (e == "scbin") {               // Shirley-Chiu square bins (util/disk2square.cal), rfluxmtx h=scN
+        if (!c->cal.has("disk2square.cal")) { err = "bin expression 'scbin' needs -f disk2square.cal"; return false; }
+        b.fn = BIN_SHIRCHIU; b.mf = (int)var("SCdim", 0);
+        if (b.mf < 1) { err = "scbin needs SCdim to be set (-p SCdim=n,...)"; return false; }
+        b.n[0] = var("rNx", 0); b.n[1] = var("rNy", 0); b.n[2] = var("rNz", -1);
+        b.u[0] = var("Ux", 0); b.u[1] = var("Uy", 1); b.u[2] = var("Uz", 0);
+        return true;
+    }
     struct KForm { const char* pre; const char* file; int fn; };
     const KForm kf[3] = {{"kbin", "klems_full.cal", BIN_KLEMS_FULL}, {"khbin", "klems_half.cal", BIN_KLEMS_HALF},
                          {"kqbin", "klems_quarter.cal", BIN_KLEMS_QUARTER}};
@@ -310,7 +318,7 @@ static bool make_binspec(rb_ctx* c, const std::string& params, const std::string
         }
     }
     err = "unsupported bin expression '" + binexpr_in +
-          "': only rbin (reinhartb.cal / reinhart.cal), kbin/khbin/kqbin (klems_*.cal), "
+          "': only rbin (reinhartb.cal / reinhart.cal), kbin/khbin/kqbin (klems_*.cal), scbin (disk2square.cal), "
           "if(-Dx*nx-Dy*ny-Dz*nz,0,-1) and constant 0 are built as native code (no .cal interpreter)";
     return false;
 }
@@ -495,11 +503,11 @@ int rb_cal_load(rb_ctx* c, const char* calfile) {
     size_t sl = f.rfind('/');
     if (sl != std::string::npos) f = f.substr(sl + 1);
     static const char* known[] = {"reinhartb.cal", "reinhart.cal", "klems_full.cal", "klems_half.cal",
-                                  "klems_quarter.cal", "rayinit.cal"};
+                                  "klems_quarter.cal", "disk2square.cal", "rayinit.cal"};
     for (const char* k : known)
         if (f == k) { c->cal.files.push_back(f); return 0; }
     return fail(c, "unsupported function file \"" + std::string(calfile) +
-                       "\": only reinhartb.cal, reinhart.cal and klems_{full,half,quarter}.cal are built as native bin functions (no .cal interpreter, no CPU fallback)");
+                       "\": only reinhartb.cal, reinhart.cal, klems_{full,half,quarter}.cal and disk2square.cal are built as native bin functions (no .cal interpreter, no CPU fallback)");
 }
 
 int rb_cal_set(rb_ctx* c, const char* assignments) {

@@ -131,6 +131,32 @@ RB_HD inline double rb_eval_bin(const DBinSpec& b, const double D[3]) {
                              D[2] * (U[0] * N[1] - U[1] * N[0]));
         return (double)rb_klems(pol, rb_Atan2_deg(y, x), b.fn);
     }
+    case BIN_SHIRCHIU: {          // util/disk2square.cal:62-76 scbin, :43-60 disk -> square (SCdim in b.mf)
+        const double* N = b.n; const double* U = b.u;
+        const double PI_ = 3.14159265358979323846;
+        double dz = -D[0] * N[0] - D[1] * N[1] - D[2] * N[2];
+        double rx = -b.rhs * (D[0] * (U[1] * N[2] - U[2] * N[1]) + D[1] * (U[2] * N[0] - U[0] * N[2]) +
+                              D[2] * (U[0] * N[1] - U[1] * N[0]));
+        double ry = D[0] * U[0] + D[1] * U[1] + D[2] * U[2] + dz * (N[0] * U[0] + N[1] * U[1] + N[2] * U[2]);
+        double den2 = rx * rx + ry * ry;
+        double radf = (den2 - 1e-7 > 0) ? sqrt((1 - dz * dz) / den2) : 0.;
+        double dx = rx * radf, dy = -ry * radf;
+        double r = sqrt(dx * dx + dy * dy);
+        double phi = atan2(dy, dx);
+        if (-phi - PI_ / 4 > 0) phi += 2 * PI_;                    // norm_radians
+        int rgn = (int)floor((phi + PI_ / 4) / (PI_ / 2)) + 1;     // select() index 1..5
+        double a, bb;
+        switch (rgn) {
+        case 1: a = r; bb = phi * r / (PI_ / 4); break;
+        case 2: a = (PI_ / 2 - phi) * r / (PI_ / 4); bb = r; break;
+        case 3: a = -r; bb = (PI_ - phi) * r / (PI_ / 4); break;
+        case 4: a = (phi - 3 * PI_ / 2) * r / (PI_ / 4); bb = -r; break;
+        default: a = r; bb = -r; break;
+        }
+        double sx = (a + 1) / 2, sy = (bb + 1) / 2;
+        if (!(dz > 0)) return -1.;
+        return floor(sx * b.mf) * b.mf + floor(sy * b.mf);
+    }
     }
     return -1.;
 }

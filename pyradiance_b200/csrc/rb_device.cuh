@@ -58,7 +58,7 @@ struct DParams {
 
 // one tracked modifier (rt/rcontrib.h:62-74 MODCONT, bins as native code)
 enum : int { BIN_CONST = 0, BIN_REINHARTB, BIN_REINHART, BIN_KLEMS_FULL, BIN_HEMI,
-             BIN_KLEMS_HALF, BIN_KLEMS_QUARTER };
+             BIN_KLEMS_HALF, BIN_KLEMS_QUARTER, BIN_SHIRCHIU };
 struct DBinSpec {
     int fn, nbins, col0, mf;
     double n[3], u[3], rhs;

@@ -309,22 +309,35 @@ bool build_octree_file(const Scene& sc, const std::string& cmdline, const std::s
 
 }  // namespace rb
 
-extern "C" int rb_oconv(const char* rad_path, const char* oct_path, int objlim, int maxres, char* errbuf,
-                        size_t errlen) {
+// oconv -f [-i octree] file ...: text scenes (and optionally the objects of an existing octree,
+// instances and meshes already expanded by the loader) into ONE frozen octree (ot/oconv.c:215-320).
+extern "C" int rb_oconv_files(const char* const* rad_paths, int npaths, const char* include_octree, const char* oct_path,
+                              int objlim, int maxres, char* errbuf, size_t errlen) {
     rb::Scene sc;
-    std::string err;
-    bool ok = sc.read_rad_text(rad_path);
-    if (!ok) err = sc.error;
+    std::string err, cmd = "rb_oconv -f";
+    bool ok = true;
+    if (include_octree && *include_octree) {
+        ok = sc.load_octree(include_octree);
+        if (!ok) err = sc.error;
+        cmd += std::string(" -i ") + include_octree;
+    }
+    for (int k = 0; ok && k < npaths; k++) {
+        ok = sc.read_rad_text(rad_paths[k]);
+        if (!ok) err = sc.error;
+        cmd += std::string(" ") + rad_paths[k];
+    }
     for (size_t i = 0; ok && i < sc.objs.size(); i++)
-        if (rb::ot_is_volume(sc.objs[i].otype)) {
+        if (rb::ot_is_volume(sc.objs[i].otype) && !sc.objs[i].expanded) {
             ok = false;
             err = "rb_oconv: " + sc.objs[i].tname + " \"" + sc.objs[i].name +
                   "\" cannot be placed by this builder (use the reference oconv for scenes with instances / meshes)";
         }
-    if (ok) {
-        std::string cmd = std::string("rb_oconv -f ") + rad_path;
-        ok = rb::build_octree_file(sc, cmd, oct_path, objlim, maxres, err);
-    }
+    if (ok) ok = rb::build_octree_file(sc, cmd, oct_path, objlim, maxres, err);
     if (!ok && errbuf && errlen) { strncpy(errbuf, err.c_str(), errlen - 1); errbuf[errlen - 1] = 0; }
     return ok ? 0 : -1;
+}
+
+extern "C" int rb_oconv(const char* rad_path, const char* oct_path, int objlim, int maxres, char* errbuf,
+                        size_t errlen) {
+    return rb_oconv_files(&rad_path, 1, nullptr, oct_path, objlim, maxres, errbuf, errlen);
 }

@@ -58,6 +58,8 @@ def main():
         "klems_half": ["-f", "klems_half.cal", "-bn", "Nkhbins", "-b", "khbin(0,0,-1,0,1,0)", "-m", "skyglow"],
         "klems_quarter": ["-f", "klems_quarter.cal", "-bn", "Nkqbins", "-b", "kqbin(0,0,-1,0,1,0)", "-m", "skyglow"],
         "hemi": ["-b", "if(-Dx*0-Dy*0-Dz*-1,0,-1)", "-bn", "1", "-m", "skyglow"],
+        "shirchiu": ["-f", "disk2square.cal", "-p", "SCdim=6,rNx=0,rNy=0,rNz=-1,Ux=0,Uy=1,Uz=0,RHS=+1", "-bn", "SCdim*SCdim",
+                     "-b", "scbin", "-m", "skyglow"],
     }
     np.save(HERE / "bin_dirs.npy", up)
     for name, args in cases.items():

@@ -99,7 +99,7 @@ def test_config1_grid_matches_oracle(G, golden):
 
 
 @pytest.mark.parametrize("name", ["bins_reinhartb_mf1", "bins_reinhartb_mf4", "bins_reinhart_mf2", "bins_klems_full",
-                                  "bins_klems_half", "bins_klems_quarter", "bins_hemi"])
+                                  "bins_klems_half", "bins_klems_quarter", "bins_hemi", "bins_shirchiu"])
 def test_bins_on_device(G, golden, name):
     """-ab 0 from above the scene: each ray lands coefficient 1 in exactly one column."""
     up = np.load(golden / "bin_dirs.npy")

@@ -18,6 +18,7 @@ BINCASES = [
     ("bins_klems_half", port.BIN_KLEMS_HALF, 1, (0, 0, -1), (0, 1, 0)),
     ("bins_klems_quarter", port.BIN_KLEMS_QUARTER, 1, (0, 0, -1), (0, 1, 0)),
     ("bins_hemi", port.BIN_HEMI, 1, (0, 0, -1), (0, 0, 0)),
+    ("bins_shirchiu", port.BIN_SHIRCHIU, 6, (0, 0, -1), (0, 1, 0)),
 ]
 
 
