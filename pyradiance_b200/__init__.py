@@ -17,5 +17,6 @@ from .manager import (RCCONTEXT, RCcontrib, RTdoFIFO, RTimmIrrad, RTlimDist, RTm
                       calcontext, eval, get_ray_params, initfunc, loadfunc, ray_done, set_eparams, set_option,
                       set_ray_params, setspectrsamp)
 from .rt import Rcontrib, rcontrib_main, rtrace, rtrace_main  # noqa: F401
+from .fluxmtx import rfluxmtx, rfluxmtx_main  # noqa: F401
 
 __version__ = "0.1.0"

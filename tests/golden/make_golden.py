@@ -167,6 +167,37 @@ def main():
         (S / f"{name}.oct").write_bytes(r.stdout)
         sky[name] = refrun.rtrace(S / f"{name}.oct", skyrays, ["-ab", "0"], outform="d").reshape(-1, 3)
     np.savez_compressed(HERE / "sky.npz", **sky)
+    # rfluxmtx front-end: the rcontrib command lines the reference synthesises (-v), a
+    # deterministic pass-through matrix (view rays -> Klems window) and a sender-sampled daylight matrix
+    # (Klems window -> Reinhart MF:2 sky, 5000 samples per sender bin) as the statistical truth
+    import shlex
+    F = HERE / "flux"
+    fenv = dict(env, PATH=f"{refrun.BIN}:{os.environ['PATH']}")
+    specs = ["- window_kf.rad room.rad", "-ab 1 -ad 64 -lw 1e-2 -I+ -y 3 - window_multi.rad room.rad",
+             "-w -ab 2 -c 4 - sky_r2.rad room.rad window_kf.rad", "-ffd -ab 0 -c 50 sender_window.rad sky_r2.rad room.rad",
+             "-bj .7 -fdf -c 3 -ab 1 - window_kf.rad -i x.oct room.rad"]
+    cmds = []
+    for sp in specs:
+        r = subprocess.run([str(refrun.BIN / "rfluxmtx"), "-v"] + sp.split(), cwd=F, env=fenv, input=b"", capture_output=True)
+        line = [ln for ln in r.stderr.decode().splitlines() if "rcontrib -fo+" in ln][0]
+        cmds.append({"spec": sp, "rcontrib": shlex.split(line[line.index("rcontrib -fo+"):])[:-1]})
+    g["rfluxmtx_commands"] = cmds
+    rng = np.random.default_rng(8)
+    o = rng.uniform((0.5, 1.0, 0.5), (3.5, 4.5, 2.5), size=(300, 3))
+    d = rng.normal(size=(300, 3))
+    d[:, 1] = -np.abs(d[:, 1]) - 0.5                       # towards the south wall with the window
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    frays = np.concatenate([o, d], 1)
+    flux = {"rays": frays}
+    r = subprocess.run([str(refrun.BIN / "rfluxmtx"), "-h", "-fdd", "-ab", "0", "-", "window_kf.rad", "room.rad"], cwd=F,
+                       env=fenv, input=frays.tobytes(), capture_output=True)
+    assert r.returncode == 0, r.stderr
+    flux["pass_kf"] = np.frombuffer(r.stdout, dtype=np.float64).reshape(300, 145, 3)
+    r = subprocess.run([str(refrun.BIN / "rfluxmtx"), "-h", "-ffd", "-ab", "0", "-c", "5000", "sender_window.rad", "sky_r2.rad",
+                        "room.rad"], cwd=F, env=fenv, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    flux["dmx_kf_r2"] = np.frombuffer(r.stdout, dtype=np.float64).reshape(145, 578, 3)[:, :, 0].astype(np.float32)
+    np.savez_compressed(HERE / "flux.npz", **flux)
     (HERE / "golden.json").write_text(json.dumps(g, indent=0))
     print("wrote", HERE / "golden.json")
 

@@ -694,3 +694,36 @@ def test_sky_brightness_patterns(golden):
     np.testing.assert_allclose(g, o, rtol=0.015)
     assert o[2, 0] > 5 and o[0, 0] > 300          # under the ceiling: sky light only through the open sides
 
+
+def test_rfluxmtx_front_end(golden):
+    """rfluxmtx on the CUDA path.  (1) pass-through mode (view rays -> Klems-full window,
+    -ab 0) is deterministic: the reference's matrix exactly; (2) sampling mode (Klems window sender ->
+    uniform ground + Reinhart MF:2 sky, -ab 0): every sender row sums to 1 and each entry agrees with the
+    reference's 5000-sample matrix within 5 sigma of the two binomial estimates (+ 0.003);
+    (3) the call of the reference's own test (tests/test_api.py:351-361) in miniature."""
+    import os
+    F = golden / "flux"
+    G = np.load(golden / "flux.npz")
+    cwd = os.getcwd()
+    os.chdir(F)
+    try:
+        out = pr.rfluxmtx_main(["rfluxmtx", "-h", "-fdd", "-ab", "0", "-", "window_kf.rad", "room.rad"], G["rays"].tobytes())
+        m = np.frombuffer(out, dtype=np.float64).reshape(300, 145, 3)
+        assert np.array_equal(m, G["pass_kf"]) and (m[:, :, 0].sum(1) > 0).sum() >= 20
+        n = 2000
+        out = pr.rfluxmtx_main(["rfluxmtx", "-h", "-ffd", "-ab", "0", "-c", str(n), "sender_window.rad", "sky_r2.rad", "room.rad"],
+                               seed=5)
+        d = np.frombuffer(out, dtype=np.float64).reshape(145, 578, 3)[:, :, 0]
+        ref = G["dmx_kf_r2"].astype(np.float64)
+        np.testing.assert_allclose(d.sum(1), 1.0, atol=1e-6)
+        pm = 0.5 * (d + ref)
+        sig = np.sqrt(pm * (1 - pm) * (1.0 / n + 1.0 / 5000))
+        assert np.all(np.abs(d - ref) <= 5 * sig + 0.003)
+        assert abs(d[:, 0].sum() - ref[:, 0].sum()) < 1.0          # the ground column as a whole (of 145 rows)
+        res = pr.rfluxmtx(F / "sky_r2.rad", rays=b"2 2 1 0 0 1", params=["-ab", "1", "-ad", "64"], scene=[F / "room.rad"])
+        assert b"NCOLS=578" in res and b"FORMAT=ascii" in res and len(res.split(b"\n\n", 1)[1].split()) == 578 * 3
+        with pytest.raises(RuntimeError, match="-bj"):
+            pr.rfluxmtx_main(["rfluxmtx", "-bj", ".5", "-", "window_kf.rad", "room.rad"], b"2 2 1 0 -1 0")
+    finally:
+        os.chdir(cwd)
+

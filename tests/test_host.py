@@ -290,3 +290,58 @@ def test_rgbe_encoder_matches_reference_bytes(golden):
     assert np.array_equal(mine.reshape(-1, 4), G["rcontrib_rgbe"])
     assert rt._rgbe(np.zeros((2, 3))) == bytes(8)
 
+
+def test_rfluxmtx_command_lines_match_reference(G, golden):
+    """receiver directives (#@rfluxmtx h= u= o=) -> the rcontrib command line, argument for
+    argument what the reference rfluxmtx -v prints (uniform / Klems full+quarter / Reinhart / Shirley-Chiu
+    receivers, pass-through and sampling mode, -bj, -i octree, left-handed Klems)."""
+    import os
+    from pyradiance_b200 import fluxmtx
+    cwd = os.getcwd()
+    os.chdir(golden / "flux")
+    try:
+        for case in G["rfluxmtx_commands"]:
+            rc, sendfn, inputs, sampcnt, verbose = fluxmtx.rcontrib_command(["rfluxmtx", "-v"] + case["spec"].split())
+            if sendfn is not None:
+                p = fluxmtx._load_sender(sendfn)
+                rc = rc + ["-y", str(fluxmtx._prepare_sampler(p)[1])]
+            assert rc == case["rcontrib"], case["spec"]
+    finally:
+        os.chdir(cwd)
+    with pytest.raises(_lib.RBError, match="hemisphere sampling"):
+        fluxmtx.rcontrib_command(["rfluxmtx", "-", str(golden / "flux" / "room.rad"), str(golden / "flux" / "room.rad")])
+
+
+def test_rfluxmtx_sender_sampling_geometry(golden):
+    """Sender rays (sample_klems / _reinhart / _shirchiu / _uniform + sample_origin): every ray starts on the
+    sender polygon, leaves against its normal, and falls into the sender bin it was drawn for -- checked with
+    the library's own native bin functions on the reversed direction."""
+    from pyradiance_b200 import fluxmtx
+    rng = np.random.default_rng(2)
+    for hemis, fn, calf, binv, nb in (("kf", None, "klems_full.cal", "kbin(0,1,0,0,0,1)", 145),
+                                      ("kq", None, "klems_quarter.cal", "kqbin(0,1,0,0,0,1)", 41),
+                                      ("r2", None, "reinhartb.cal", "rbin", 577), ("sc5", None, "disk2square.cal", "scbin", 25),
+                                      ("u", None, None, None, 1)):
+        p = fluxmtx._load_sender(golden / "flux" / "sender_window.rad")
+        p.hemis = hemis
+        p.hsiz = int("".join(ch for ch in hemis if ch.isdigit()) or 1)
+        kind, nbins = fluxmtx._prepare_sampler(p)
+        assert nbins == nb
+        rays = fluxmtx._sample_sender(p, kind, nbins, 40, rng)
+        assert rays.shape == (nbins * 40, 6)
+        o, d = rays[:, :3], rays[:, 3:]
+        assert np.allclose(np.linalg.norm(d, axis=1), 1.0)
+        assert np.all(d[:, 1] < 0) and np.allclose(o[:, 1], 0.0)                       # against the +Y normal
+        assert o[:, 0].min() >= 1 and o[:, 0].max() <= 3 and o[:, 2].min() >= 1 and o[:, 2].max() <= 2.5
+        assert abs(o[:, 0].mean() - 2.0) < 0.05 and abs(o[:, 2].mean() - 1.75) < 0.05   # uniform over the pane
+        if calf is None:
+            continue
+        c = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+        c.cal_load(calf)
+        prm = f"MF=2,SCdim=5,rNx=0,rNy=1,rNz=0,Ux=0,Uy=0,Uz=1,RHS=+1"
+        c.cal_set(prm)
+        c.add_modifier("m", prm, binv, nbins)
+        # the bin functions take the direction of a ray ARRIVING at the front of the surface: D.N < 0, like d
+        got = np.array([int(np.floor(c.bin_of_direction(0, dd) + .5)) for dd in d])
+        assert np.array_equal(got, np.repeat(np.arange(nbins), 40)), hemis
+
