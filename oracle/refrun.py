@@ -25,7 +25,8 @@ def available() -> bool:
 
 def _env():
     env = dict(os.environ)
-    env["RAYPATH"] = f".:{LIB}"
+    extra = os.environ.get("RB_RAYPATH_EXTRA", "")       # e.g. the directory of nested octrees / meshes
+    env["RAYPATH"] = f".:{LIB}" + (f":{extra}" if extra else "")
     return env
 
 

@@ -323,14 +323,23 @@ bool Engine::set_bins(const std::vector<DBinSpec>& bins, const std::vector<int>&
     return true;
 }
 
-bool Engine::ensure_queues(std::string& err) {
+// `hint` = rays per queue that would let a batch hold a few hundred records of the coming job
+// (0: none).  Queues only ever grow: 2 x 48 M rays by default, more when a job's records are
+// wide (thousands of suns per shading point) and HBM is there -- 180 GB per B200.
+bool Engine::ensure_queues(std::string& err, size_t hint) {
     if (park_direct() && !dq_ && q_[0]) {   // a many-source scene loaded after the queues were made
         CK(cudaMalloc(&dq_, dcap_ * sizeof(DirectJob)));
     }
-    if (q_[0]) return true;
+    size_t want = qcap_req_ ? qcap_req_ : std::max<size_t>((size_t)48 << 20, hint);     // rays per queue
+    if (q_[0] && want <= qcap_) return true;
+    if (q_[0]) {                            // grow: drop the old queues first
+        CK(cudaStreamSynchronize(stream_));
+        void* old[] = {q_[0], q_[1], h_[0], h_[1], d_hits_, dq_};
+        for (void* p : old) if (p) cudaFree(p);
+        q_[0] = q_[1] = nullptr; h_[0] = h_[1] = nullptr; d_hits_ = nullptr; dq_ = nullptr;
+    }
     size_t freeb = 0, totalb = 0;
     CK(cudaMemGetInfo(&freeb, &totalb));
-    size_t want = qcap_req_ ? qcap_req_ : (size_t)48 << 20;     // rays per queue
     size_t maxq = (freeb / 3) / (2 * sizeof(QRay));              // at most a third of free HBM
     if (want > maxq) want = maxq;
     if (want < 4096) { err = "not enough device memory for ray queues"; return false; }
@@ -560,7 +569,6 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
 bool Engine::run(const TraceJob& job, const DParams& P, std::string& err) {
     CK(cudaSetDevice(dev_));
     if (!d_nodes_) { err = "no octree loaded"; return false; }
-    if (!ensure_queues(err) || !size_trace_grid(err)) return false;
     if (job.nrays == 0) return true;
     const int accum = job.accum;
     const size_t nrec_total = accum > 0 ? (job.nrays + accum - 1) / accum : 1;
@@ -577,6 +585,10 @@ bool Engine::run(const TraceJob& job, const DParams& P, std::string& err) {
     // widest wave is the first-bounce one (about half the sources face a surface)
     per_rec = per_rec * (1.0 + 0.6 * nsrc_active_) + nsrc_active_;
     per_rec *= (accum > 0 ? accum : 1);
+    {   // queues wide enough for ~256 records per batch (or the whole job), memory permitting
+        const double want_rec = (double)std::min<size_t>(nrec_total, 256);
+        if (!ensure_queues(err, (size_t)(per_rec * want_rec / 0.45)) || !size_trace_grid(err)) return false;
+    }
     size_t batch = (size_t)std::max(1.0, (double)qcap_ * 0.45 / per_rec);
     if (accum <= 0) batch = 1;
     size_t rec = 0;

@@ -54,7 +54,7 @@ public:
     std::vector<std::string> objdesc;      // "type \"name\"" per object, for messages
 
 private:
-    bool ensure_queues(std::string& err);
+    bool ensure_queues(std::string& err, size_t hint = 0);
     bool size_trace_grid(std::string& err);
     bool run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_t nrec, std::string& err, bool& overflow);
     int dev_;

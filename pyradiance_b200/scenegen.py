@@ -255,7 +255,8 @@ def build_octree(rad_path, oct_path, use_reference_oconv=None):
     if use_reference_oconv:
         import subprocess
         with open(oct_path, "wb") as f:
-            subprocess.run([use_reference_oconv, "-f", os.fspath(rad_path)], check=True, stdout=f)
+            subprocess.run([use_reference_oconv, "-f", os.path.basename(os.fspath(rad_path))], check=True, stdout=f,
+                           cwd=os.path.dirname(os.path.abspath(os.fspath(rad_path))))      # nested .oct / .rtm are relative
         return
     from ._lib import oconv_file
     oconv_file(rad_path, oct_path)

@@ -54,13 +54,26 @@ def c4(nrays=200000, nref=2000):
     print("  per-window-group totals gpu", np.round(per_mod_g, 2), "\n  per-window-group totals ref", np.round(per_mod_r, 2))
     print("  total gpu %.3f ref %.3f" % (g.sum(), r.sum()))
 
-def c5(npoly=100_000, nsens=1000, nref=8, mf=6):
-    # S-sun-like: MF:6 light suns sharing modifier solar, -ab 1 (instances/meshes are covered by the golden tests)
-    import io
+def c5(npoly=100_000, nsens=int(os.environ.get("C5_SENSORS", 1000)), nref=8, mf=6):
+    # S-sun: MF:6 light suns sharing modifier solar, -ab 1, facade louvres as octree instances + two meshes
+    # (needs the reference oconv for the instances; without it the plain scene is used)
+    import io, shutil
     rad, octf = TMP / "sun.rad", TMP / "sun.oct"
     out = io.StringIO(); out.write(scenegen.MATERIALS); scenegen.write_suns(out, mf=mf)
     rng = np.random.default_rng(11); scenegen.office_floor(out, rng, 0.0, (npoly - 24) // 6, tag="f0")
-    rad.write_text(out.getvalue()); scenegen.build_octree(rad, octf)
+    vol = ROOT / "tests" / "golden" / "volumes"
+    os.environ["RB_RAYPATH_EXTRA"] = str(TMP)
+    if refrun.available():
+        for f in ("louvre.oct", "bump.rtm"):
+            shutil.copyfile(vol / f, TMP / f)
+        for i in range(64):              # louvres outside the south windows, 8 per window
+            x, z = 1.0 + 38.0 * (i + 0.5) / 64, 1.0 + 0.25 * (i % 8)
+            out.write(f"void instance lv{i}\n7 louvre.oct -s 0.6 -t {x:.3f} -0.45 {z:.3f}\n0\n0\n\n")
+        out.write("void mesh bumpA\n7 bump.rtm -s 1.5 -t 10 12 0.75\n0\n0\n\nvoid mesh bumpB\n9 bump.rtm -rz 40 -s 2 -t 28 9 0.75\n0\n0\n\n")
+        rad.write_text(out.getvalue())
+        scenegen.build_octree(rad, octf, use_reference_oconv=str(refrun.BIN / "oconv"))
+    else:
+        rad.write_text(out.getvalue()); scenegen.build_octree(rad, octf)
     sens = scenegen.office_sensors(nsens, seed=4)
     opts = ["-ab", "1", "-ad", "256", "-lw", "1e-3", "-dc", "1", "-dt", "0", "-dj", "0"]
     nb = 144 * mf * mf + 2
