@@ -186,6 +186,10 @@ int rb_oconv(const char* rad_path, const char* oct_path, int objlim, int maxres,
 int rb_oconv_files(const char* const* rad_paths, int npaths, const char* include_octree, const char* oct_path,
                    int objlim, int maxres, char* errbuf, size_t errlen);
 
+/* ASCII output of a value matrix at C speed: "%e\t" per value, "\n" per row (rc2.c:304-312 put_contrib,
+ * rtrace.c:907-918 puta).  Returns the text length; the text is written when outlen is large enough. */
+size_t rb_format_ascii(const void* values, int is_double, size_t nrows, size_t per_row, char* out, size_t outlen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,7 @@ SYMBOLS = [
     ("rb_host_register", C.c_int, [_P, _P, C.c_size_t]),
     ("rb_host_unregister", C.c_int, [_P, _P]),
     ("rb_oconv", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
+    ("rb_format_ascii", C.c_size_t, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]),
     ("rb_oconv_files", C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p,
                                  C.c_size_t]),
 ]
@@ -321,6 +322,24 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.rb_device_sync(self.h))
+
+
+def format_ascii(values: np.ndarray) -> bytes:
+    """[nrows, ...] float32/float64 -> the "%e\\t" ... "\\n" text rtrace / rcontrib write (C ABI rb_format_ascii)."""
+    v = np.ascontiguousarray(values)
+    if v.dtype not in (np.float32, np.float64):
+        v = v.astype(np.float64)
+    nrows = v.shape[0] if v.ndim > 0 else 0
+    if nrows == 0:
+        return b""
+    per_row = v.size // nrows
+    lib = load_library()
+    buf = bytearray(v.size * 16 + nrows)
+    cbuf = (C.c_char * len(buf)).from_buffer(buf)
+    n = lib.rb_format_ascii(v.ctypes.data, int(v.dtype == np.float64), nrows, per_row, C.addressof(cbuf), len(buf))
+    assert n <= len(buf)
+    del cbuf
+    return bytes(buf[:n])
 
 
 def oconv_files(rad_paths, oct_path, include_octree=None, objlim=6, maxres=16384):

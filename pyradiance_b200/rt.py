@@ -257,6 +257,8 @@ def _format_rtrace(ctx, rays, values, res, outvals, outform) -> bytes:
             cols.append(("s", ["~"] * n))
     if outform == "c":                 # rtrace.c:999-1002: the float radiance through setcolr()
         return _rgbe(values.astype(np.float32).astype(np.float64))
+    if outform == "a" and cols and all(kind == "r" for kind, _ in cols):
+        return _lib.format_ascii(np.concatenate([np.asarray(c, dtype=np.float64).reshape(n, -1) for _, c in cols], axis=1))
     if outform == "a":
         lines = []
         for i in range(n):
@@ -514,8 +516,7 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
             if outform == "c":         # rc2.c:324-331: float coefficients through scolor_scolr()
                 out += _rgbe(sub.reshape(-1, 3), single=True)
             elif outform == "a":
-                flat = sub.reshape(sub.shape[0], -1)
-                out += ("".join("".join("%.6e\t" % v for v in row) + "\n" for row in flat)).encode()
+                out += _lib.format_ascii(sub.reshape(sub.shape[0], -1))
             else:
                 out += np.ascontiguousarray(sub).tobytes()
             if key is None:
