@@ -198,6 +198,24 @@ def main():
     assert r.returncode == 0, r.stderr
     flux["dmx_kf_r2"] = np.frombuffer(r.stdout, dtype=np.float64).reshape(145, 578, 3)[:, :, 0].astype(np.float32)
     np.savez_compressed(HERE / "flux.npz", **flux)
+    # vwrays: rays of every view type from the reference binary, -fd, plus -d dimensions
+    vcases = {
+        "persp": ["-vtv", "-vp", "2", "3", "1.5", "-vd", "0.3", "1", "-0.1", "-vu", "0", "0", "1", "-vh", "60", "-vv", "40"],
+        "persp_shift_clip": ["-vtv", "-vp", "2", "3", "1.5", "-vd", "1", "0.2", "0", "-vu", "0", "0", "1", "-vh", "50", "-vv", "50",
+                             "-vs", "0.2", "-vl", "-0.1", "-vo", "0.5", "-va", "10"],
+        "parallel": ["-vtl", "-vp", "0", "0", "10", "-vd", "0", "0", "-1", "-vu", "0", "1", "0", "-vh", "8", "-vv", "6"],
+        "fisheye_h": ["-vth", "-vp", "2", "2", "1", "-vd", "0", "-1", "0", "-vu", "0", "0", "1", "-vh", "180", "-vv", "180"],
+        "fisheye_a": ["-vta", "-vp", "2", "2", "1", "-vd", "0", "0", "1", "-vu", "0", "1", "0", "-vh", "180", "-vv", "180"],
+        "cyl": ["-vtc", "-vp", "2", "2", "1", "-vd", "1", "0", "0", "-vu", "0", "0", "1", "-vh", "300", "-vv", "60"],
+        "plan": ["-vts", "-vp", "2", "2", "1", "-vd", "0", "0", "1", "-vu", "0", "1", "0", "-vh", "200", "-vv", "200"],
+    }
+    vw = {}
+    g["vwrays"] = {}
+    for name, va in vcases.items():
+        vw[name] = np.frombuffer(refrun.run("vwrays", ["-fd", "-x", "24", "-y", "18"] + va), dtype=np.float64).reshape(-1, 6)
+        g["vwrays"][name] = {"view": va, "dim": refrun.run("vwrays", ["-d", "-x", "24", "-y", "18"] + va).decode(),
+                             "ascii_5x4": refrun.run("vwrays", ["-x", "5", "-y", "4"] + va).decode()}
+    np.savez_compressed(HERE / "vwrays.npz", **vw)
     (HERE / "golden.json").write_text(json.dumps(g, indent=0))
     print("wrote", HERE / "golden.json")
 

@@ -345,3 +345,25 @@ def test_rfluxmtx_sender_sampling_geometry(golden):
         got = np.array([int(np.floor(c.bin_of_direction(0, dd) + .5)) for dd in d])
         assert np.array_equal(got, np.repeat(np.arange(nbins), 40)), hemis
 
+
+def test_vwrays_matches_reference(G, golden):
+    """view rays of all six view types (perspective with shift / lift / clipping, parallel,
+    hemispherical and angular fisheye, cylinder, planisphere): the reference vwrays' doubles to 1e-14, its
+    -d dimension line and its ASCII text exactly."""
+    import pyradiance_b200 as pr
+    V = np.load(golden / "vwrays.npz")
+    for name, case in G["vwrays"].items():
+        out = pr.vwrays_main(["vwrays", "-fd", "-x", "24", "-y", "18"] + case["view"])
+        mine = np.frombuffer(out, dtype=np.float64).reshape(-1, 6)
+        assert mine.shape == V[name].shape, name
+        np.testing.assert_allclose(mine, V[name], rtol=0, atol=1e-14, err_msg=name)
+        assert pr.vwrays_main(["vwrays", "-d", "-x", "24", "-y", "18"] + case["view"]).decode() == case["dim"]
+        assert pr.vwrays_main(["vwrays", "-x", "5", "-y", "4"] + case["view"]).decode() == case["ascii_5x4"]
+    # the Python signature of pyradiance.vwrays; float output; pixel positions from stdin
+    f = pr.vwrays(outform="f", xres=8, yres=8, view=G["vwrays"]["fisheye_h"]["view"])
+    assert len(f) == 8 * 8 * 6 * 4
+    one = pr.vwrays(pixpos=b"3 4\n", outform="d", xres=8, yres=8, view=G["vwrays"]["persp"]["view"])
+    assert np.frombuffer(one, dtype=np.float64).shape == (6,)
+    with pytest.raises(_lib.RBError, match="illegal horizontal view size"):
+        pr.vwrays(view=["-vtv", "-vh", "190"])
+
