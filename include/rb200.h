@@ -186,9 +186,21 @@ int rb_oconv(const char* rad_path, const char* oct_path, int objlim, int maxres,
 int rb_oconv_files(const char* const* rad_paths, int npaths, const char* include_octree, const char* oct_path,
                    int objlim, int maxres, char* errbuf, size_t errlen);
 
-/* ASCII output of a value matrix at C speed: "%e\t" per value, "\n" per row (rc2.c:304-312 put_contrib,
- * rtrace.c:907-918 puta).  Returns the text length; the text is written when outlen is large enough. */
-size_t rb_format_ascii(const void* values, int is_double, size_t nrows, size_t per_row, char* out, size_t outlen);
+/* The matrix consumer right after the path: out[nrows][ncols][3] = a[nrows][ninner][3] x b[ninner][ncols][3],
+ * colour channel by colour channel -- util/cmatrix.c:420-475 cm_multiply() as dctimestep / rmtxop use it on a
+ * daylight-coefficient matrix and a sky matrix.  fp32 with two-level accumulation (within 1e-5 of the reference's
+ * double accumulation).  Buffers are host memory unless flagged; kernel_ms (may be NULL) gets the device time. */
+#define RB_MTX_A_ON_DEVICE 1u
+#define RB_MTX_B_ON_DEVICE 2u
+#define RB_MTX_OUT_ON_DEVICE 4u
+int rb_mtx_multiply(rb_ctx* ctx, const float* a, size_t nrows, size_t ninner, const float* b, size_t ncols, float* out,
+                    unsigned flags, double* kernel_ms);
+
+/* ASCII output of a value matrix at C speed.  style 0: "%e\t" per value, "\n" per row (rc2.c:304-312
+ * put_contrib, rtrace.c:907-918 puta); style 1: "%e %e %e" triplets separated by tabs, "\n" at the end of a row
+ * (util/cmatrix.c:492-498 cm_write).  Returns the text length; the text is written when outlen is large enough. */
+size_t rb_format_ascii(const void* values, int is_double, size_t nrows, size_t per_row, int style, char* out,
+                       size_t outlen);
 
 #ifdef __cplusplus
 }

@@ -96,7 +96,9 @@ SYMBOLS = [
     ("rb_host_register", C.c_int, [_P, _P, C.c_size_t]),
     ("rb_host_unregister", C.c_int, [_P, _P]),
     ("rb_oconv", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
-    ("rb_format_ascii", C.c_size_t, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t]),
+    ("rb_mtx_multiply", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint,
+                                  C.POINTER(C.c_double)]),
+    ("rb_format_ascii", C.c_size_t, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]),
     ("rb_oconv_files", C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p,
                                  C.c_size_t]),
 ]
@@ -264,6 +266,18 @@ class Context:
                                       out.ctypes.data, out.size))
         return out
 
+    def mtx_multiply(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        """[nr, ni, 3] x [ni, nc, 3] -> [nr, nc, 3] float32, per colour channel (C ABI rb_mtx_multiply)."""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        b = np.ascontiguousarray(b, dtype=np.float32)
+        assert a.ndim == 3 and b.ndim == 3 and a.shape[2] == 3 and b.shape[2] == 3 and a.shape[1] == b.shape[0]
+        out = np.empty((a.shape[0], b.shape[1], 3), dtype=np.float32)
+        ms = C.c_double(0)
+        self._ck(self.lib.rb_mtx_multiply(self.h, a.ctypes.data, a.shape[0], a.shape[1], b.ctypes.data, b.shape[1],
+                                          out.ctypes.data, 0, C.byref(ms)))
+        self.last_mtx_ms = ms.value
+        return out
+
     def rcontrib_device(self, d_rays, nrays, accum, flags, row_base, d_out, out_floats):
         """Both buffers already in HBM (raw device pointers)."""
         self._ck(self.lib.rb_rcontrib(self.h, d_rays, int(nrays), int(accum),
@@ -324,7 +338,7 @@ class Context:
         self._ck(self.lib.rb_device_sync(self.h))
 
 
-def format_ascii(values: np.ndarray) -> bytes:
+def format_ascii(values: np.ndarray, triplets: bool = False) -> bytes:
     """[nrows, ...] float32/float64 -> the "%e\\t" ... "\\n" text rtrace / rcontrib write (C ABI rb_format_ascii)."""
     v = np.ascontiguousarray(values)
     if v.dtype not in (np.float32, np.float64):
@@ -336,7 +350,8 @@ def format_ascii(values: np.ndarray) -> bytes:
     lib = load_library()
     buf = bytearray(v.size * 16 + nrows)
     cbuf = (C.c_char * len(buf)).from_buffer(buf)
-    n = lib.rb_format_ascii(v.ctypes.data, int(v.dtype == np.float64), nrows, per_row, C.addressof(cbuf), len(buf))
+    n = lib.rb_format_ascii(v.ctypes.data, int(v.dtype == np.float64), nrows, per_row, int(triplets), C.addressof(cbuf),
+                            len(buf))
     assert n <= len(buf)
     del cbuf
     return bytes(buf[:n])

@@ -626,6 +626,17 @@ int rb_device_download(rb_ctx* c, void* dst, const void* src, size_t bytes) {
     cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
     return e == cudaSuccess ? 0 : fail(c, cudaGetErrorString(e));
 }
+int rb_mtx_multiply(rb_ctx* c, const float* a, size_t nrows, size_t ninner, const float* b, size_t ncols, float* out,
+                    unsigned flags, double* kernel_ms) {
+    if (!c->cuda_ok) return fail(c, c->cuda_err);
+    std::string err;
+    cudaStream_t st = c->user_stream ? (cudaStream_t)c->user_stream : (cudaStream_t)0;
+    if (!rb::mtx_multiply(c->device, st, a, nrows, ninner, b, ncols, out, (flags & RB_MTX_A_ON_DEVICE) != 0,
+                          (flags & RB_MTX_B_ON_DEVICE) != 0, (flags & RB_MTX_OUT_ON_DEVICE) != 0, kernel_ms, err))
+        return fail(c, err);
+    return 0;
+}
+
 int rb_host_register(rb_ctx* c, void* p, size_t bytes) {
     if (!c->cuda_ok) return fail(c, c->cuda_err);
     cudaSetDevice(c->device);

@@ -86,4 +86,8 @@ private:
     std::string local_source_note_;
 };
 
+// rb_mtx.cu: C[nr][nc][3] = A[nr][ni][3] x B[ni][nc][3] per colour channel (dctimestep's cm_multiply)
+bool mtx_multiply(int device, cudaStream_t stream, const float* A, size_t nr, size_t ni, const float* B, size_t nc,
+                  float* C, bool a_dev, bool b_dev, bool c_dev, double* kernel_ms, std::string& err);
+
 }  // namespace rb

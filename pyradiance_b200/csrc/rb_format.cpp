@@ -14,8 +14,9 @@
 #include "../../include/rb200.h"
 
 namespace {
+// style 0: "v\tv\t...v\t\n" (rcontrib / rtrace); style 1: "r g b\tr g b\t...r g b\n" (cm_write, cmatrix.c:492-498)
 template <class T>
-void format_rows(const T* v, size_t r0, size_t r1, size_t per_row, std::string& out) {
+void format_rows(const T* v, size_t r0, size_t r1, size_t per_row, int style, std::string& out) {
     out.reserve((r1 - r0) * (per_row * 15 + 1));
     char buf[64];
     for (size_t r = r0; r < r1; r++) {
@@ -23,16 +24,17 @@ void format_rows(const T* v, size_t r0, size_t r1, size_t per_row, std::string& 
         for (size_t k = 0; k < per_row; k++) {
             // std::to_chars(scientific, 6) == printf("%e"): correctly rounded, two-digit exponent at least
             auto res = std::to_chars(buf, buf + sizeof(buf) - 1, (double)p[k], std::chars_format::scientific, 6);
-            *res.ptr++ = '\t';
+            if (style == 0) *res.ptr++ = '\t';
+            else *res.ptr++ = (k % 3 != 2) ? ' ' : (k + 1 == per_row ? '\n' : '\t');
             out.append(buf, (size_t)(res.ptr - buf));
         }
-        out.push_back('\n');
+        if (style == 0) out.push_back('\n');
     }
 }
 }  // namespace
 
 // Returns the number of bytes the text takes; writes it when `out` is large enough (outlen >= result).
-extern "C" size_t rb_format_ascii(const void* values, int is_double, size_t nrows, size_t per_row, char* out,
+extern "C" size_t rb_format_ascii(const void* values, int is_double, size_t nrows, size_t per_row, int style, char* out,
                                   size_t outlen) {
     if (nrows == 0) return 0;
     unsigned hw = std::thread::hardware_concurrency();
@@ -42,8 +44,8 @@ extern "C" size_t rb_format_ascii(const void* values, int is_double, size_t nrow
     for (size_t t = 0; t < nt; t++) {
         size_t r0 = nrows * t / nt, r1 = nrows * (t + 1) / nt;
         th.emplace_back([=, &parts]() {
-            if (is_double) format_rows((const double*)values, r0, r1, per_row, parts[t]);
-            else format_rows((const float*)values, r0, r1, per_row, parts[t]);
+            if (is_double) format_rows((const double*)values, r0, r1, per_row, style, parts[t]);
+            else format_rows((const float*)values, r0, r1, per_row, style, parts[t]);
         });
     }
     for (auto& x : th) x.join();

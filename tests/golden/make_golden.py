@@ -216,6 +216,49 @@ def main():
         g["vwrays"][name] = {"view": va, "dim": refrun.run("vwrays", ["-d", "-x", "24", "-y", "18"] + va).decode(),
                              "ascii_5x4": refrun.run("vwrays", ["-x", "5", "-y", "4"] + va).decode()}
     np.savez_compressed(HERE / "vwrays.npz", **vw)
+    # dctimestep: small matrix files (ascii DC with header, float sky with header, headerless
+    # ascii sky for -n) and the reference's products, ascii text and float bytes; plus a V.T.D.s chain
+    D = HERE / "dct"
+    D.mkdir(exist_ok=True)
+    rng = np.random.default_rng(12)
+
+    def write_mtx(path, m, fmt):
+        hdr = f"#?RADIANCE\nNROWS={m.shape[0]}\nNCOLS={m.shape[1]}\nNCOMP=3\n"
+        if fmt == "a":
+            body = "".join("\t".join("%.6e %.6e %.6e" % tuple(c) for c in row) + "\n" for row in m).encode()
+            path.write_bytes((hdr + "FORMAT=ascii\n\n").encode() + body)
+        else:
+            dt = np.float32 if fmt == "f" else np.float64
+            path.write_bytes((hdr + "BigEndian=0\nFORMAT=" + ("float" if fmt == "f" else "double") + "\n\n").encode()
+                             + np.ascontiguousarray(m, dtype=dt).tobytes())
+    dc = (rng.random((37, 146, 3)) ** 6 * 0.05).astype(np.float32)          # coefficients over several decades
+    sky = (rng.random((146, 29, 3)) ** 3 * 2e4).astype(np.float32)
+    sky[:, 5] = 0                                                           # a night-time step
+    write_mtx(D / "dc.mtx", dc, "a")
+    write_mtx(D / "sky_f.smx", sky, "f")
+    write_mtx(D / "sky_d.smx", sky, "d")
+    (D / "sky_n.txt").write_text("".join("%.6e %.6e %.6e\n" % tuple(c) for row in sky for c in row))
+    vm = (rng.random((11, 20, 3)) * 0.2).astype(np.float32)
+    tm = (rng.random((20, 20, 3)) * 0.1).astype(np.float32)
+    dm = (rng.random((20, 146, 3)) * 0.01).astype(np.float32)
+    write_mtx(D / "v.mtx", vm, "f"); write_mtx(D / "t.mtx", tm, "a"); write_mtx(D / "d.mtx", dm, "d")
+    dct = {}
+
+    def body(b):
+        return b[b.index(b"\n\n") + 2:]
+    r = subprocess.run([str(refrun.BIN / "dctimestep"), "dc.mtx", "sky_f.smx"], cwd=D, env=env, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    g["dctimestep_ascii"] = body(r.stdout).decode()
+    g["dctimestep_header"] = r.stdout[:r.stdout.index(b"\n\n")].decode()
+    r = subprocess.run([str(refrun.BIN / "dctimestep"), "-of", "dc.mtx", "sky_d.smx"], cwd=D, env=env, capture_output=True)
+    dct["dc_sky"] = np.frombuffer(body(r.stdout), dtype=np.float32).reshape(37, 29, 3)
+    r = subprocess.run([str(refrun.BIN / "dctimestep"), "-h", "-of", "-n", "29", "dc.mtx", "sky_n.txt"], cwd=D, env=env, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    dct["dc_sky_n"] = np.frombuffer(r.stdout, dtype=np.float32).reshape(37, 29, 3)
+    r = subprocess.run([str(refrun.BIN / "dctimestep"), "-h", "-of", "v.mtx", "t.mtx", "d.mtx", "sky_f.smx"], cwd=D, env=env, capture_output=True)
+    assert r.returncode == 0, r.stderr
+    dct["vtds"] = np.frombuffer(r.stdout, dtype=np.float32).reshape(11, 29, 3)
+    np.savez_compressed(HERE / "dct.npz", **dct)
     (HERE / "golden.json").write_text(json.dumps(g, indent=0))
     print("wrote", HERE / "golden.json")
 

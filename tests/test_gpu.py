@@ -727,3 +727,43 @@ def test_rfluxmtx_front_end(golden):
     finally:
         os.chdir(cwd)
 
+
+def test_dctimestep_matrix_consumer(G, golden):
+    """the matrix product after the path (rb_mtx_multiply / dctimestep).  Against the reference
+    dctimestep on the same files: ascii and float outputs, the -n headerless sky, the V.T.D.s chain -- all
+    within 1e-5 (the reference accumulates in double, the kernel in two-level fp32); header lines identical
+    except dates; then a large ragged product (K = 2305 like MF:4) against numpy float64."""
+    import os
+    D = golden / "dct"
+    R = np.load(golden / "dct.npz")
+    cwd = os.getcwd()
+    os.chdir(D)
+    try:
+        out = pr.dctimestep_main(["dctimestep", "dc.mtx", "sky_f.smx"])
+        hdr, body = out.split(b"\n\n", 1)
+        ref_hdr = [ln for ln in G["dctimestep_header"].split("\n") if not ln.startswith(("CAPDATE", "GMT"))]
+        assert [ln for ln in hdr.decode().split("\n") if not ln.startswith(("CAPDATE", "GMT"))] == ref_hdr
+        mine = np.array(body.split(), dtype=np.float64)
+        ref = np.array(G["dctimestep_ascii"].split(), dtype=np.float64)
+        np.testing.assert_allclose(mine, ref, rtol=1e-5, atol=1e-30)
+        assert body.count(b"\n") == 37 and body.split(b"\n")[0].count(b"\t") == 28
+        f = np.frombuffer(pr.dctimestep("dc.mtx", "sky_d.smx", header=False, outform="f"), dtype=np.float32).reshape(37, 29, 3)
+        np.testing.assert_allclose(f, R["dc_sky"], rtol=1e-5, atol=1e-30)
+        assert np.all(f[:, 5] == 0)
+        f = np.frombuffer(pr.dctimestep("dc.mtx", (D / "sky_n.txt").read_bytes(), nstep=29, header=False, outform="f"),
+                          dtype=np.float32).reshape(37, 29, 3)
+        np.testing.assert_allclose(f, R["dc_sky_n"], rtol=1e-5, atol=1e-30)
+        f = np.frombuffer(pr.dctimestep("v.mtx", "t.mtx", "d.mtx", "sky_f.smx", header=False, outform="f"),
+                          dtype=np.float32).reshape(11, 29, 3)
+        np.testing.assert_allclose(f, R["vtds"], rtol=2e-5, atol=1e-30)
+    finally:
+        os.chdir(cwd)
+    rng = np.random.default_rng(4)
+    a = (rng.random((1003, 2305, 3)) ** 5).astype(np.float32)
+    b = (rng.random((2305, 517, 3)) ** 2 * 1e4).astype(np.float32)
+    ctx = _lib.Context(0)
+    c = ctx.mtx_multiply(a, b)
+    ref = np.einsum("rik,ick->rck", a.astype(np.float64), b.astype(np.float64))
+    np.testing.assert_allclose(c, ref, rtol=1e-5)
+    assert ctx.last_mtx_ms > 0
+

@@ -367,3 +367,25 @@ def test_vwrays_matches_reference(G, golden):
     with pytest.raises(_lib.RBError, match="illegal horizontal view size"):
         pr.vwrays(view=["-vtv", "-vh", "190"])
 
+
+def test_matrix_file_reader_and_ascii_styles(G, golden):
+    """SURVEY 8f f2, host side: cm_load() for ascii / float / double matrix files with headers and a
+    headerless ascii sky (-n), and cm_write()'s ascii layout from the C formatter."""
+    from pyradiance_b200 import mtx
+    D = golden / "dct"
+    dc = mtx.load_matrix(D / "dc.mtx")
+    assert dc.shape == (37, 146, 3) and dc.dtype == np.float32
+    sf, sd = mtx.load_matrix(D / "sky_f.smx"), mtx.load_matrix(D / "sky_d.smx")
+    sn = mtx.load_matrix((D / "sky_n.txt").read_bytes(), 0, 29, "a")
+    assert sf.shape == (146, 29, 3) and np.array_equal(sf, sd)
+    np.testing.assert_allclose(sn, sf, rtol=1e-6)
+    assert np.all(sf[:, 5] == 0)
+    txt = _lib.format_ascii(sf[:2, :3], triplets=True).decode()
+    rows = txt.split("\n")
+    assert rows[-1] == "" and len(rows) == 3 and all(len(r.split("\t")) == 3 for r in rows[:2])
+    assert rows[0].split("\t")[1] == "%.6e %.6e %.6e" % tuple(sf[0, 1])
+    with pytest.raises(_lib.RBError, match="XML"):
+        mtx.load_matrix("klems.xml")
+    with pytest.raises(_lib.RBError, match="components"):
+        mtx.parse_matrix(b"#?RADIANCE\nNCOMP=1\nNROWS=1\nNCOLS=1\nFORMAT=ascii\n\n1\n")
+
