@@ -48,6 +48,9 @@ namespace rb {
 #define RB_STAT(x)
 #endif
 #define RB_PAIRS (32 * RB_OPR)
+#ifndef RB_SLOW_MIN
+#define RB_SLOW_MIN 0            // lanes in curved-surface leaves that gather before their round runs (0: off; measured slower)
+#endif
 #ifndef RB_PAIR_ILP
 #define RB_PAIR_ILP 1            // (ray, surface) pairs a lane has in flight in the pair loop
 #endif
@@ -366,6 +369,7 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
     const double cs = S.cusize;
     const int2* __restrict__ pool = reinterpret_cast<const int2*>(S.leafpool);
     unsigned fl = WF_DONE;       // WF_* flags of this lane's ray
+    unsigned round = 0;
     // cube the ray stands in: set by the refill or by phase C, consumed by phase A
     // (registers only between those two; parked in shared memory across phase B)
     unsigned ix = 0, iy = 0, iz = 0;
@@ -494,13 +498,27 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
         act &= (w < 0);                          // still inside the tree: continue next round
         const bool full = act & (w < -1);
         int kleft = 0, setoff = 0;
+        bool slow = false;
         if (full) {
-            const unsigned u = (unsigned)(-w - 2);       // set offset << 3 | min(count, 7)
-            setoff = (int)(u >> 3);
+            const unsigned u = (unsigned)(-w - 2);       // set offset << 4 | curved << 3 | min(count, 7)
+            setoff = (int)(u >> 4);
+            slow = (u >> 3) & 1;
             kleft = (int)(u & 7);
             if (kleft == 7) kleft = __ldg(&pool[setoff]).x;
-            RB_STAT(ws.leafents += kleft + 1; ws.prims += kleft;)
         }
+#if RB_SLOW_MIN > 0
+        // Leaves holding a sphere / cone need the second (out-of-line, ~400 instruction) pass, which ran
+        // with 3-4 live lanes when every round paid for it.  Such lanes now wait in their leaf until
+        // RB_SLOW_MIN of them have gathered (or nothing else is runnable, or every 8th round), so the
+        // pass runs less often and fuller.  Only the schedule changes, not what any ray computes.
+        {
+            const unsigned mslow = __ballot_sync(FULL, slow);
+            const unsigned mfast = __ballot_sync(FULL, act & !slow);
+            const bool go = (__popc(mslow) >= RB_SLOW_MIN) | (mfast == 0) | ((++round & 7) == 0);
+            if (slow & !go) { act = false; kleft = 0; }
+        }
+#endif
+        RB_STAT(if (act & full) { ws.leafents += kleft + 1; ws.prims += kleft; })
         // ---- phase B: the warp tests the leaves' surfaces as (ray, surface) pairs ----
         for (;;) {
             const int m = min(kleft, RB_OPR);

@@ -1096,14 +1096,20 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
             }
             p += cnt + 1;
         }
-        // full-leaf word = -(set offset << 3 | min(count, 7)) - 2: the walker knows how many
-        // surfaces wait in a leaf without a dependent read of the set's count word
+        // the walker knows how many surfaces wait in a leaf (and whether any needs the slow sphere / cone
+        // test) without a dependent read of the set's count word
         if (n >= (1 << 25)) { err = "scene has too many objects for this engine (2^25)"; return false; }
-        if (fs.leaf2.size() / 2 >= ((size_t)1 << 27)) { err = "octree has too many leaf-set entries for this engine"; return false; }
+        if (fs.leaf2.size() / 2 >= ((size_t)1 << 26)) { err = "octree has too many leaf-set entries for this engine"; return false; }
+        // full-leaf word = -(set offset << 4 | has-curved-surface << 3 | min(count, 7)) - 2
         auto leafword = [&](int w) {
             const size_t p = (size_t)(-w - 2);
             const int cnt = sc.leafpool[p];
-            return -((newoff[p] << 3) | std::min(cnt, 7)) - 2;
+            int curved = 0;
+            for (int k = 1; k <= cnt; k++) {
+                const int kind = fs.objhdr[(size_t)sc.leafpool[p + k] * 4] & 0xff;
+                if (kind != PK_FACE && kind != PK_NONE) curved = 1;
+            }
+            return -((newoff[p] << 4) | (curved << 3) | std::min(cnt, 7)) - 2;
         };
         for (auto& w : fs.nodes) if (w < -1) w = leafword(w);
         fs.root = sc.root < -1 ? leafword(sc.root) : sc.root;

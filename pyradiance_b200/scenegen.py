@@ -200,7 +200,7 @@ def write_suns(out, mf=1, modifier="solar", radiance=1e6, angle=0.533):
     for i, d in enumerate(reinhart_suns(mf)):
         out.write(f"{modifier} source sun{i}\n0\n0\n4 {d[0]:.8f} {d[1]:.8f} {d[2]:.8f} {angle:g}\n\n")
 
-def write_office(path, npolys=100_000, floors=1, seed=1234, sun=False):
+def write_office(path, npolys=100_000, floors=1, seed=1234, sun=False, curved=True):
     """Write the S-office (floors=1) / S-building (floors=10) scene; returns
     the surface count."""
     rng = np.random.default_rng(seed)
@@ -215,7 +215,7 @@ def write_office(path, npolys=100_000, floors=1, seed=1234, sun=False):
     nboxes = max(0, (per_floor - shell) // 6)
     n = 0
     for f in range(floors):
-        n += office_floor(out, rng, 3.3 * f, nboxes, tag=f"f{f}")
+        n += office_floor(out, rng, 3.3 * f, nboxes, tag=f"f{f}", **({} if curved else {"frac_sphere": 0.0, "frac_cyl": 0.0}))
     Path(path).write_text(out.getvalue())
     return n
 

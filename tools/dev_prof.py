@@ -8,9 +8,10 @@ from pyradiance_b200 import _lib, scenegen
 TMP = Path(os.environ.get("RB_TMP", "/tmp/rbt")); TMP.mkdir(parents=True, exist_ok=True)
 npolys = int(os.environ.get("NPOLY", 100000)); nsens = int(os.environ.get("NSENS", 512))
 ab = int(os.environ.get("AB", 3)); ad = int(os.environ.get("AD", 4096)); reps = int(os.environ.get("REPS", 1))
-rad = TMP / f"off{npolys}.rad"; octf = TMP / f"off{npolys}.oct"
+curved = os.environ.get("CURVED", "1") != "0"
+rad = TMP / f"off{npolys}{"" if curved else "p"}.rad"; octf = TMP / f"off{npolys}{"" if curved else "p"}.oct"
 if not octf.exists():
-    scenegen.write_office(rad, npolys=npolys, seed=1234); scenegen.build_octree(rad, octf)
+    scenegen.write_office(rad, npolys=npolys, seed=1234, curved=curved); scenegen.build_octree(rad, octf)
 sens = scenegen.office_sensors(nsens)
 ctx = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB); ctx.load_octree(octf)
 ctx.set_options(["-ab", str(ab), "-ad", str(ad), "-lw", f"{1.0/ad:.3e}"])
