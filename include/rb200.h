@@ -116,6 +116,8 @@ rb_ctx* rb_create(int cuda_device);
 void rb_destroy(rb_ctx* ctx);
 const char* rb_last_error(rb_ctx* ctx);
 const char* rb_version(void);
+/* CUDA devices visible to this process (0 without a usable driver): what `-n N` can spread records over */
+int rb_device_count(void);
 
 int rb_set_defaults(rb_ctx* ctx, int program);
 int rb_get_params(rb_ctx* ctx, rb_params* out);

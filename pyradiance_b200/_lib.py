@@ -61,6 +61,7 @@ SYMBOLS = [
     ("rb_destroy", None, [_P]),
     ("rb_last_error", C.c_char_p, [_P]),
     ("rb_version", C.c_char_p, []),
+    ("rb_device_count", C.c_int, []),
     ("rb_set_defaults", C.c_int, [_P, C.c_int]),
     ("rb_get_params", C.c_int, [_P, C.POINTER(rb_params)]),
     ("rb_set_params", C.c_int, [_P, C.POINTER(rb_params)]),
@@ -336,6 +337,11 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.rb_device_sync(self.h))
+
+
+def device_count() -> int:
+    """CUDA devices visible to this process (C ABI rb_device_count)."""
+    return int(load_library().rb_device_count())
 
 
 def format_ascii(values: np.ndarray, triplets: bool = False) -> bytes:

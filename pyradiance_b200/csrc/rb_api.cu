@@ -370,6 +370,11 @@ static int check_params(rb_ctx* c) {
 extern "C" {
 
 const char* rb_version(void) { return "pyradiance_b200 0.1 (sm_100a)"; }
+int rb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 rb_ctx* rb_create(int cuda_device) {
     rb_ctx* c = new rb_ctx();

@@ -373,7 +373,11 @@ def _ofname(ospec: str, mname: str, bn: int):
     return (ospec % args) if args else ospec.replace("%%", "%"), "s" in order, "d" in order
 
 
-def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_array: bool = False):
+MULTI_GPU_MIN_RECORDS = 2048        # below this a second GPU costs more (octree load) than it saves
+
+
+def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_array: bool = False, _row_base: int = 0,
+                  _single: bool = False):
     """Interpret an rcontrib command line (argv[0] is the program name).
     Option order matters exactly as in rt/rcmain.c:207-320: -f/-e/-p act
     immediately, -bn is evaluated when met, -b/-bn/-p/-o are sticky until -m."""
@@ -387,6 +391,7 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
         imm_irrad = lim_dist = contrib = force_open = False
         xres = yres = 0
         accumulate = 1
+        nproc = 1
         curout = None
         prms, binval, bincnt = "", None, 0
         mods = []                   # (name, outspec, col0, nbins)
@@ -410,7 +415,7 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
 
             c = a[1]
             if c == "n":
-                need(); i += 1
+                need(); nproc = max(1, int(argv[i + 1])); i += 1
             elif c == "V":
                 contrib = _bool_opt(a, 2, contrib)
             elif c == "x":
@@ -467,8 +472,39 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
         flags = (_lib.RB_IRRAD_RCONTRIB if imm_irrad else 0) | (_lib.RB_FLAG_LIMDIST if lim_dist else 0) | \
                 (_lib.RB_FLAG_CONTRIB if contrib else 0)
         dt = np.float32 if outform in "fc" else np.float64
-        if accumulate > 0:
-            mat = ctx.rcontrib(rays, accum=accumulate, flags=flags, dtype=dt)
+        nrec = (rays.shape[0] + accumulate - 1) // accumulate if accumulate > 0 else 1
+        ngpu = min(nproc, _lib.device_count()) if (nproc > 1 and not _single and accumulate > 0) else 1
+        if ngpu > 1 and nrec >= MULTI_GPU_MIN_RECORDS * ngpu:
+            # -n N: the reference forks N processes over the records (rc3.c:598-622); here the records go to
+            # min(N, visible GPUs) devices, one host thread + context each, rows written straight into
+            # disjoint slices of the result.  RNG streams are keyed by the global record index (row_base),
+            # so the matrix is the one a single GPU computes.
+            import threading
+            mat = np.empty((nrec, ctx.num_columns(), 3), dtype=dt)
+            bounds = [nrec * k // ngpu for k in range(ngpu + 1)]
+            errors = []
+
+            def work(k):
+                try:
+                    r0, r1 = bounds[k], bounds[k + 1]
+                    part = rays[r0 * accumulate:r1 * accumulate]
+                    if k == 0:
+                        mat[r0:r1] = ctx.rcontrib(part, accum=accumulate, flags=flags, row_base=_row_base + r0, dtype=dt)
+                    else:
+                        wargv = argv[:-1] + ["-fd" + outform, argv[-1]]
+                        mat[r0:r1] = rcontrib_main(wargv, np.ascontiguousarray(part).tobytes(), device=(device + k) % _lib.device_count(),
+                                                   return_array=True, _row_base=_row_base + r0, _single=True)
+                except Exception as e:          # noqa: BLE001 - re-raised in the caller's thread
+                    errors.append(e)
+            threads = [threading.Thread(target=work, args=(k,)) for k in range(ngpu)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            if errors:
+                raise errors[0]
+        elif accumulate > 0:
+            mat = ctx.rcontrib(rays, accum=accumulate, flags=flags, row_base=_row_base, dtype=dt)
         else:
             # -c 0: one record holding the SUM over all rays (rc2.c:301-302 sf = 1);
             # dummy (zero-direction) rays are ignored (rcontrib.c:392-398)

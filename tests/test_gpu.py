@@ -767,3 +767,18 @@ def test_dctimestep_matrix_consumer(G, golden):
     np.testing.assert_allclose(c, ref, rtol=1e-5)
     assert ctx.last_mtx_ms > 0
 
+
+def test_nproc_spreads_records_over_gpus(office2k):
+    """`-n N` (Rcontrib(nproc=N)): records go to min(N, visible GPUs) devices inside one process; the
+    matrix must be the single-GPU matrix bit for bit (RNG streams are keyed by the global record index)."""
+    if _lib.device_count() < 2:
+        pytest.skip("needs two visible GPUs (the driver's multi-GPU step / gpurun --gpus 2)")
+    sens = scenegen.office_sensors(6000, seed=21)
+    args = ["-I+", "-ab", "1", "-ad", "64", "-lw", "1e-2", "-fdf", "-h"] + RB_ARGS
+    one = pr.rcontrib_main(["rcontrib", "-n", "1"] + args + [str(office2k)], sens.tobytes())
+    two = pr.rcontrib_main(["rcontrib", "-n", "2"] + args + [str(office2k)], sens.tobytes())
+    assert len(one) == 6000 * 145 * 3 * 4 and one == two
+    eight = pr.rcontrib_main(["rcontrib", "-n", "8", "-c", "3"] + args + [str(office2k)], sens.tobytes())
+    one_c = pr.rcontrib_main(["rcontrib", "-c", "3"] + args + [str(office2k)], sens.tobytes())
+    assert len(eight) == 2000 * 145 * 3 * 4 and eight == one_c           # 2000 records < threshold x GPUs: single path
+
