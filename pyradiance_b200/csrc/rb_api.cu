@@ -363,6 +363,8 @@ static int check_params(rb_ctx* c) {
         return fail(c, "unsupported option: ambient super-sampling (-as) is not built");
     if (p.maxdepth <= 0 && p.minweight <= 0)
         return fail(c, "zero ray weight in Russian roulette");
+    if (p.specjitter > 1.5)
+        return fail(c, "unsupported option: -ss > 1.5 (several specular samples per hit, normal.c:374-386) is not built");
     return 0;
 }
 

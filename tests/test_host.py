@@ -389,3 +389,13 @@ def test_matrix_file_reader_and_ascii_styles(G, golden):
     with pytest.raises(_lib.RBError, match="components"):
         mtx.parse_matrix(b"#?RADIANCE\nNCOMP=1\nNROWS=1\nNCOLS=1\nFORMAT=ascii\n\n1\n")
 
+
+def test_option_rejections_are_explicit():
+    """Options whose behaviour is not built fail by name instead of being accepted and ignored."""
+    c = _lib.Context(0)
+    for bad in (["-ae", "wall"], ["-ai", "wall"], ["-cs", "9"], ["-ap", "f.pm", "50"], ["-pc", "1"]):
+        with pytest.raises(_lib.RBError, match="unsupported option"):
+            c.set_options(bad)
+    c.set_options(["-ss", "4"])                  # parsed like the reference; refused when a run would need it
+    assert c.get_params().specjitter == 4.0
+
