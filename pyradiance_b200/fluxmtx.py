@@ -169,7 +169,6 @@ def _scan_scene(path):
             yield ("params", t[1])
             i += 1
             continue
-        words = []
         # an object: mod type name, then three counted argument lists
         def nxt():
             nonlocal i
@@ -190,7 +189,6 @@ def _scan_scene(path):
             nxt()
         nf = int(nxt()); fargs = [float(nxt()) for _ in range(nf)]
         yield ("object", mod, typ, name, sargs, fargs)
-        del words
 
 
 def _make_surface(st, name, farg) -> _Surf | None:
@@ -722,7 +720,7 @@ def rfluxmtx_main(argv: Sequence[str], stdin: bytes | None = None, device: int =
     """The rfluxmtx command: argv[0] is the program name."""
     from .rt import rcontrib_main
     rc, sendfn, inputs, sampcnt, verbose = rcontrib_command(argv)
-    if any(a.startswith("-p") is False and ",JTR=" in a for a in rc):
+    if any(",JTR=" in a for a in rc):
         raise RBError("rfluxmtx: bin jitter (-bj) is not built (the bin functions are native code, not .cal files)")
     with tempfile.TemporaryDirectory(prefix="rb200_rfluxmtx_") as td:
         octf = _build_octree(inputs, Path(td))
