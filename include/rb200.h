@@ -163,6 +163,9 @@ int rb_rcontrib(rb_ctx* ctx, const double* rays, size_t nrays, int accum,
 /* values: [nrays][3] doubles (may be NULL), results: [nrays] (may be NULL) */
 int rb_rtrace(rb_ctx* ctx, const double* rays, size_t nrays, unsigned flags,
               double* values, rb_ray_result* results);
+/* rb_rtrace over a SHARD of a larger ray set: the global index of the shard's first ray, so that the random
+ * streams (keyed by global ray index) do not depend on how the rays were split over calls or GPUs */
+int rb_set_row_base(rb_ctx* ctx, uint64_t first_ray);
 
 int rb_get_stats(rb_ctx* ctx, rb_stats* out);
 int rb_reset_stats(rb_ctx* ctx);

@@ -62,6 +62,7 @@ SYMBOLS = [
     ("rb_last_error", C.c_char_p, [_P]),
     ("rb_version", C.c_char_p, []),
     ("rb_device_count", C.c_int, []),
+    ("rb_set_row_base", C.c_int, [C.c_void_p, C.c_uint64]),
     ("rb_set_defaults", C.c_int, [_P, C.c_int]),
     ("rb_get_params", C.c_int, [_P, C.POINTER(rb_params)]),
     ("rb_set_params", C.c_int, [_P, C.POINTER(rb_params)]),
@@ -285,8 +286,9 @@ class Context:
                                       int(flags) | RB_FLAG_RAYS_ON_DEVICE | RB_FLAG_OUT_ON_DEVICE,
                                       int(row_base), d_out, int(out_floats)))
 
-    def rtrace(self, rays, flags=RB_IRRAD_NONE, want_values=True, want_results=True):
+    def rtrace(self, rays, flags=RB_IRRAD_NONE, want_values=True, want_results=True, row_base=0):
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        self._ck(self.lib.rb_set_row_base(self.h, int(row_base)))
         n = rays.shape[0]
         values = np.zeros((n, 3), dtype=np.float64) if want_values else None
         results = np.zeros(n, dtype=RAY_RESULT_DTYPE) if want_results else None

@@ -61,6 +61,7 @@ struct rb_ctx {
     bool bins_dirty = true;
     uint64_t seed = 0x5eed5eedULL;
     size_t qcap = 0;
+    uint64_t rtrace_row_base = 0;     // global index of the first ray of the next rb_rtrace call (RNG keys)
     void* user_stream = nullptr;
     std::string tmp;
 };
@@ -591,11 +592,14 @@ int rb_rtrace(rb_ctx* c, const double* rays, size_t nrays, unsigned flags, doubl
     job.rays_on_device = flags & RB_FLAG_RAYS_ON_DEVICE;
     job.values = values; job.results = (RayResult*)results;
     job.irrad = flags & RB_FLAG_IRRAD_MASK; job.lim_dist = flags & RB_FLAG_LIMDIST;
+    job.row_base = c->rtrace_row_base;
     DParams P = device_params(c, false, values != nullptr);
     std::string err;
     if (!c->eng->run(job, P, err)) return fail(c, err);
     return 0;
 }
+
+int rb_set_row_base(rb_ctx* c, uint64_t first_ray) { c->rtrace_row_base = first_ray; return 0; }
 
 int rb_get_stats(rb_ctx* c, rb_stats* o) {
     memset(o, 0, sizeof(*o));

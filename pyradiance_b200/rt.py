@@ -100,7 +100,7 @@ _RT_UNSUPPORTED_SPEC = {"r": "mirrored contribution", "R": "mirrored distance", 
                         "t": "ray-tree trace", "T": "source trace"}
 
 
-def rtrace_main(argv: Sequence[str], stdin: bytes, device: int = 0) -> bytes:
+def rtrace_main(argv: Sequence[str], stdin: bytes, device: int = 0, _shard=None):
     """Interpret an rtrace command line (argv[0] is the program name)."""
     argv = [str(a) for a in argv]
     if "-version" in argv[1:]:
@@ -113,6 +113,7 @@ def rtrace_main(argv: Sequence[str], stdin: bytes, device: int = 0) -> bytes:
         imm_irrad = False
         lim_dist = False
         hres = vres = 0
+        nproc = 1
         i = 1
         while i < len(argv):
             a = argv[i]
@@ -124,7 +125,7 @@ def rtrace_main(argv: Sequence[str], stdin: bytes, device: int = 0) -> bytes:
                 continue
             c = a[1]
             if c == "n":
-                i += 1          # number of processes: a hint, the GPU does the work
+                nproc = max(1, int(argv[i + 1])); i += 1     # number of processes -> number of GPUs
             elif c == "x":
                 hres = int(argv[i + 1]); i += 1
             elif c == "y":
@@ -171,7 +172,36 @@ def rtrace_main(argv: Sequence[str], stdin: bytes, device: int = 0) -> bytes:
         if vres > 0:
             n = min(n, (hres if hres > 1 else 1) * vres) if hres > 0 or vres > 0 else n
             rays = rays[:n]
-        values, res = ctx.rtrace(rays, flags=flags, want_values=want_values, want_results=True)
+        if _shard is not None:                      # a worker of the multi-GPU split below: rays arrive as an array
+            return ctx.rtrace(_shard[0], flags=flags, want_values=want_values, want_results=True, row_base=_shard[1])
+        ngpu = min(nproc, _lib.device_count()) if nproc > 1 else 1
+        if ngpu > 1 and n >= MULTI_GPU_MIN_RAYS * ngpu:
+            # -n N: rays go to min(N, visible GPUs) devices, one host thread + context each; the random streams
+            # are keyed by the global ray index, so the output is the single-GPU output
+            import threading
+            bounds = [n * k // ngpu for k in range(ngpu + 1)]
+            parts, errors = [None] * ngpu, []
+
+            def work(k):
+                try:
+                    sl = rays[bounds[k]:bounds[k + 1]]
+                    if k == 0:
+                        parts[k] = ctx.rtrace(sl, flags=flags, want_values=want_values, want_results=True, row_base=0)
+                    else:
+                        parts[k] = rtrace_main(argv, b"", device=(device + k) % _lib.device_count(), _shard=(sl, bounds[k]))
+                except Exception as e:          # noqa: BLE001 - re-raised in the caller's thread
+                    errors.append(e)
+            threads = [threading.Thread(target=work, args=(k,)) for k in range(ngpu)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            if errors:
+                raise errors[0]
+            values = np.concatenate([p[0] for p in parts]) if want_values else None
+            res = np.concatenate([p[1] for p in parts])
+        else:
+            values, res = ctx.rtrace(rays, flags=flags, want_values=want_values, want_results=True)
         out = bytearray()
         ncomp = 0
         for ch in outvals:
@@ -374,6 +404,7 @@ def _ofname(ospec: str, mname: str, bn: int):
 
 
 MULTI_GPU_MIN_RECORDS = 2048        # below this a second GPU costs more (octree load) than it saves
+MULTI_GPU_MIN_RAYS = 65536           # same for rtrace rays
 
 
 def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_array: bool = False, _row_base: int = 0,

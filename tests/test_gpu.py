@@ -781,4 +781,10 @@ def test_nproc_spreads_records_over_gpus(office2k):
     eight = pr.rcontrib_main(["rcontrib", "-n", "8", "-c", "3"] + args + [str(office2k)], sens.tobytes())
     one_c = pr.rcontrib_main(["rcontrib", "-c", "3"] + args + [str(office2k)], sens.tobytes())
     assert len(eight) == 2000 * 145 * 3 * 4 and eight == one_c           # 2000 records < threshold x GPUs: single path
+    # rtrace -n N: rays split over the GPUs, random streams keyed by the global ray index
+    rays = scenegen.random_rays(140_000, seed=3)
+    targs = ["-h", "-fdd", "-ab", "1", "-aa", "0", "-ad", "16", "-lw", "5e-2", "-ovL"]
+    t1 = pr.rtrace_main(["rtrace", "-n", "1"] + targs + [str(office2k)], rays.tobytes())
+    t2 = pr.rtrace_main(["rtrace", "-n", "2"] + targs + [str(office2k)], rays.tobytes())
+    assert len(t1) == 140_000 * 4 * 8 and t1 == t2
 
