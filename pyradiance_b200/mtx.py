@@ -6,12 +6,14 @@ Radiance matrix files with an information header (NROWS= NCOLS= NCOMP=3 [BigEndi
 double), RGB triplets.  The products run in `rb_mtx_multiply` (csrc/rb_mtx.cu).
 
 Same Python signature as `pyradiance.dctimestep` (src/pyradiance/util.py:140-195).  Not built:
-picture inputs (`%03d.hdr` view components) and RGBE output, BSDF XML files as the transmission
-matrix, `!command` inputs, per-step output files (`-o spec`).
+picture inputs (`%03d.hdr` view components) and RGBE output, `!command` inputs, per-step output files
+(`-o spec`).  The transmission matrix may be a Klems-matrix BSDF XML file (`load_btdf`, util/cmbsdf.c);
+tensor-tree and colour (CIE-X/Z) BSDF files are rejected.
 """
 from __future__ import annotations
 
 import datetime
+import math
 import os
 import re
 from pathlib import Path
@@ -87,7 +89,7 @@ def load_matrix(spec, nrows: int = 0, ncols: int = 0, dtype: str | None = None) 
     if spec.startswith("!"):
         raise RBError(f"dctimestep: input from command '{spec}' is not supported (commands are not executed)")
     if spec.lower().endswith(".xml"):
-        raise RBError("dctimestep: BSDF XML files as the transmission matrix are not built")
+        raise RBError("dctimestep: a BSDF XML file is only read as the transmission matrix (Vspec Tbsdf Dmat [sky])")
     if re.search(r"%[0-9]*[dioxX]", spec):
         raise RBError("dctimestep: picture view components (a %d file specification) are not built")
     try:
@@ -95,6 +97,205 @@ def load_matrix(spec, nrows: int = 0, ncols: int = 0, dtype: str | None = None) 
     except OSError:
         raise RBError(f"dctimestep: cannot open file '{spec}'")
     return parse_matrix(data, nrows, ncols, dtype, what=spec)
+
+
+# ---- Klems-matrix BSDF XML as the transmission matrix (util/cmbsdf.c:168-203 cm_loadBTDF) -------------
+_ABASES = {                                        # common/bsdf_m.c:31-66 abase_list (tmin per latitude, nphis)
+    "lbnl/klems full": ([0., 5., 15., 25., 35., 45., 55., 65., 75., 90.], [1, 8, 16, 20, 24, 24, 24, 16, 12]),
+    "lbnl/klems half": ([0., 6.5, 19.5, 32.5, 45.5, 58.5, 71.5, 90.], [1, 8, 12, 16, 20, 12, 8]),
+    "lbnl/klems quarter": ([0., 9., 27., 45., 63., 90.], [1, 8, 12, 12, 8]),
+}
+_MAXLATS, _MAXABASES = 46, 7                       # common/bsdf_m.h
+
+
+def _strip_ns(root):
+    for el in root.iter():
+        if isinstance(el.tag, str) and "}" in el.tag:
+            el.tag = el.tag.split("}", 1)[1]
+    return root
+
+
+def _txt(el, *path) -> str:
+    """ezxml_txt(ezxml_child(...)): text of the first child along `path`, "" when absent."""
+    for name in path:
+        el = el.find(name) if el is not None else None
+    return (el.text or "").strip() if el is not None else ""
+
+
+def _basis_ohm(tmin, nphis) -> np.ndarray:
+    """Projected solid angle of every patch (common/bsdf_m.c:192-213 io_getohm)."""
+    out = []
+    for li, n in enumerate(nphis):
+        th, th1 = math.pi / 180. * tmin[li], math.pi / 180. * tmin[li + 1]
+        out += [math.pi * (math.cos(th) ** 2 - math.cos(th1) ** 2) / float(n)] * n
+    return np.array(out, dtype=np.float64)
+
+
+def _basis_rot180(nphis) -> np.ndarray:
+    """Patch index after turning the direction half-way round the normal: what cmbsdf.c:58-81
+    (recip_out_from_in / recip_in_from_out: centre vector, flip z, look up on the other side) amounts to."""
+    out, base = [], 0
+    for n in nphis:
+        out += [base + int((k + 0.5 * n) % n + .5) % n if n > 1 else base for k in range(n)]
+        base += n
+    return np.array(out, dtype=np.int64)
+
+
+def _ee_white(y: float) -> np.ndarray:
+    """ccy2rgb(&c_dfcolor, y) (common/ccyrgb.c:12-28): equal-energy white of luminance y through the
+    float chromaticity (1/3, 1/3) and xyz2rgbmat (common/spec_rgb.c:203-213, nominal CRT primaries)."""
+    xr, yr, xg, yg, xb, yb, xw, yw = 0.640, 0.330, 0.290, 0.600, 0.150, 0.060, 1. / 3., 1. / 3.
+    crd = (1. / yw) * (xw * (yg - yb) - yw * (xg - xb) + xg * yb - xb * yg)
+    cgd = (1. / yw) * (xw * (yb - yr) - yw * (xb - xr) - xr * yb + xb * yr)
+    cbd = (1. / yw) * (xw * (yr - yg) - yw * (xr - xg) + xr * yg - xg * yr)
+    mat = [[(yg - yb - xb * yg + yb * xg) / crd, (xb - xg - xb * yg + xg * yb) / crd, (xg * yb - xb * yg) / crd],
+           [(yb - yr - yb * xr + yr * xb) / cgd, (xr - xb - xr * yb + xb * yr) / cgd, (xb * yr - xr * yb) / cgd],
+           [(yr - yg - yr * xg + yg * xr) / cbd, (xg - xr - xg * yr + xr * yg) / cbd, (xr * yg - xg * yr) / cbd]]
+    cx = cy = float(np.float32(1. / 3.))
+    d = cx / cy
+    xyz = np.array([d * y, y, (1. / cy - d - 1.) * y]).astype(np.float32)
+    mat = np.array(mat).astype(np.float32)                                    # COLORMAT is float: float arithmetic
+    return np.array([m[0] * xyz[0] + m[1] * xyz[1] + m[2] * xyz[2] for m in mat], dtype=np.float32)
+
+
+def load_btdf(path) -> np.ndarray:
+    """cm_loadBTDF (util/cmbsdf.c:168-203): the visible transmission block of a Klems-matrix BSDF XML file as
+    a coefficient matrix [nout, ninc, 3]: T[o][i] = BTDF(o, i) x projected solid angle of incident patch i.
+    The "Transmission Front" block is used when present (XML front/back are swapped on loading, common/
+    bsdf_m.c:418-440), otherwise "Transmission Back" through reciprocity.  The loader's minimum-value (diffuse)
+    separation (bsdf_m.c:594-640 subtract_min, with its position-dependent 6e-4 perturbation, bsdf_m.c:283-303)
+    is followed in float so the sums round like the reference's."""
+    import xml.etree.ElementTree as ET
+    path = os.fspath(path)
+    try:
+        data = Path(path).read_bytes()
+        root = _strip_ns(ET.fromstring(data[max(data.find(b"<"), 0):]))       # ezxml skips anything before the first tag
+    except OSError:
+        raise RBError(f"dctimestep: Cannot open BSDF \"{path}\"")
+    except ET.ParseError as e:
+        raise RBError(f"dctimestep: BSDF \"{path}\" {e}")
+    if root.tag != "WindowElement":
+        raise RBError(f"dctimestep: BSDF \"{path}\": top level node not 'WindowElement'")
+    ft = root.find("FileType")
+    if ft is not None and (ft.text or "").strip() != "BSDF":
+        raise RBError(f"dctimestep: XML \"{path}\": wrong FileType (must be 'BSDF')")
+    wtl = root.find("Optical")
+    wtl = wtl.find("Layer") if wtl is not None else None
+    if wtl is None:
+        raise RBError(f"dctimestep: BSDF \"{path}\": no optical layers")
+    dd = wtl.find("DataDefinition")
+    ids = _txt(wtl, "DataDefinition", "IncidentDataStructure")
+    if ids.lower().startswith("tensortree"):       # common/bsdf_t.c SDloadTre is the other loader
+        raise RBError(f"dctimestep: unsupported BSDF '{path}'")
+    if not ids:
+        raise RBError(f"dctimestep: BSDF \"{path}\": missing IncidentDataStructure")
+    if ids.lower() not in ("rows", "columns"):
+        raise RBError(f"dctimestep: BSDF \"{path}\": unsupported IncidentDataStructure")
+    row_in = ids.lower() == "rows"
+    bases = dict(_ABASES)
+    for wab in (dd.findall("AngleBasis") if dd is not None else []):          # bsdf_m.c:306-368 load_angle_basis
+        name = _txt(wab, "AngleBasisName")
+        if not name or name.lower() in bases:
+            continue
+        if len(bases) >= _MAXABASES:
+            raise RBError(f"dctimestep: Out of angle bases reading '{name}'")
+        tmin, nphis = [0.], []
+        for i, wbb in enumerate(wab.findall("AngleBasisBlock")):
+            if i >= _MAXLATS:
+                raise RBError(f"dctimestep: Too many latitudes for '{name}'")
+            lo = float(_txt(wbb, "ThetaBounds", "LowerTheta") or 0)
+            if i and abs((lo / tmin[i] - 1.) if tmin[i] != 0 else lo) > 1e-6:
+                raise RBError(f"dctimestep: Theta values disagree in '{name}'")
+            tmin.append(float(_txt(wbb, "ThetaBounds", "UpperTheta") or 0))
+            n = int(float(_txt(wbb, "nPhis") or 0))
+            if n <= 0 or (n == 1 and tmin[i] > 1e-6):
+                raise RBError(f"dctimestep: Illegal phi count in '{name}'")
+            nphis.append(n)
+        bases[name.lower()] = (tmin, nphis)
+    blocks = {}                                    # XML direction -> (values[o][i] float32, inc basis, out basis)
+    for wld in wtl.findall("WavelengthData"):
+        wl = _txt(wld, "Wavelength")
+        if wl.lower() in ("cie-x", "cie-z"):
+            raise RBError(f"dctimestep: colour (CIE-X/CIE-Z) BSDF blocks in '{path}' are not built; use the Visible-only file")
+        if wl.lower() != "visible":
+            continue
+        for wdb in wld.findall("WavelengthDataBlock"):
+            direction = _txt(wdb, "WavelengthDataDirection").lower()
+            if direction not in ("transmission front", "transmission back", "reflection front", "reflection back"):
+                continue
+            cb, rb = _txt(wdb, "ColumnAngleBasis"), _txt(wdb, "RowAngleBasis")
+            if not cb:
+                raise RBError(f"dctimestep: Missing column basis for BSDF '{path}'")
+            if cb.lower() not in bases:
+                raise RBError(f"dctimestep: Undefined ColumnAngleBasis '{cb}'")
+            if not rb:
+                raise RBError(f"dctimestep: Missing row basis for BSDF '{path}'")
+            if rb.lower() not in bases:
+                raise RBError(f"dctimestep: Undefined RowAngleBasis '{rb}'")
+            if not direction.startswith("transmission"):
+                continue
+            inb, outb = bases[cb.lower()], bases[rb.lower()]
+            ninc, nout = sum(inb[1]), sum(outb[1])
+            sdata = _txt(wdb, "ScatteringData")
+            if not sdata:
+                raise RBError(f"dctimestep: Missing BSDF ScatteringData in '{path}'")
+            try:
+                vals = np.array(sdata.replace(",", " ").split(), dtype=np.float64)
+            except ValueError:
+                raise RBError(f"dctimestep: Bad/missing BSDF ScatteringData in '{path}'")
+            if vals.size < ninc * nout:
+                raise RBError(f"dctimestep: Bad/missing BSDF ScatteringData in '{path}'")
+            vals = np.maximum(vals[:ninc * nout], 0.).astype(np.float32)      # negative values are not allowed
+            m = vals.reshape(ninc, nout).T if row_in else vals.reshape(nout, ninc)
+            blocks[direction] = (np.ascontiguousarray(m), inb, outb)
+
+    def separated(blk):
+        """extract_diffuse for a Y-only block: -> (values with the minimum taken off, the minimum, maxHemi)."""
+        m, inb, outb = blk
+        nout, ninc = m.shape
+        oo, ii = np.meshgrid(np.arange(nout, dtype=np.float64), np.arange(ninc, dtype=np.float64), indexing="ij")
+        d = 2 * ninc / (ii + .22545) + 4 * nout / (oo + .70281)
+        d -= np.floor(d)
+        ymin = np.float32((m.astype(np.float64) * (1. + 6e-4 * (d - .5))).astype(np.float32).min())
+        hemi = float((_basis_ohm(*outb)[:, None] * m.astype(np.float64)).sum(0).max())
+        if float(ymin) <= .01 / math.pi:
+            return m, np.float32(0), hemi
+        return (m - ymin).astype(np.float32), ymin, hemi - math.pi * float(ymin)
+
+    tb = separated(blocks["transmission front"]) + blocks["transmission front"][1:] if "transmission front" in blocks else None
+    tf = separated(blocks["transmission back"]) + blocks["transmission back"][1:] if "transmission back" in blocks else None
+    lamb_f = tf[1] if tf else np.float32(0)
+    lamb_b = tb[1] if tb else np.float32(0)
+    if tb is not None and tf is None:              # bsdf_m.c:711-717
+        lamb_f = lamb_b
+    elif tb is None and tf is not None:
+        lamb_b = lamb_f
+    if tf is not None and tf[2] <= .001:           # common/bsdf.c:230-241 insignificant components
+        tf = None
+    if tb is not None and tb[2] <= .001:
+        tb = None
+    recip = tb is None
+    # tLamb*.cieY = M_PI*ymin (double); diffBTDF = ccy2rgb(white, cieY/PI)
+    ymin = lamb_f if recip else lamb_b
+    diff = _ee_white(math.pi * float(ymin) / math.pi) if float(ymin) > 0 else np.zeros(3, np.float32)
+    tdf = tf if recip else tb
+    if tdf is None:                                # cm_bsdf_Lamb: "this is a hack" -- always Klems full
+        ohm = _basis_ohm(*_ABASES["lbnl/klems full"])
+        return np.ascontiguousarray((diff[None, None, :] * np.ones((145, 1, 1), np.float32)
+                                     * ohm[None, :, None]).astype(np.float32))
+    m, _, _, inb, outb = tdf
+    if recip:                                      # cm_bsdf_recip: T[r][c] = f(ro(c), ri(r)) * outohm(ro(c))
+        ro, ri = _basis_rot180(inb[1]), _basis_rot180(outb[1])
+        if max(ro) >= m.shape[0] or max(ri) >= m.shape[1]:
+            raise RBError(f"dctimestep: BSDF '{path}': reciprocity needs matching incident and exiting bases")
+        f = m[np.ix_(ro, ri)].T
+        dom = _basis_ohm(*outb)[ro]
+    else:                                          # cm_bsdf: T[r][c] = f(r, c) * incohm(c)
+        f = m
+        dom = _basis_ohm(*inb)
+    f = np.where(f > 0, f, np.float32(0)).astype(np.float32)
+    t = (f[:, :, None] + diff[None, None, :]).astype(np.float32)              # addcolor in float
+    return np.ascontiguousarray((t * dom[None, :, None]).astype(np.float32))  # scalecolor: float *= double
 
 
 def multiply(a: np.ndarray, b: np.ndarray, device: int = 0, ctx: _lib.Context | None = None) -> np.ndarray:
@@ -171,7 +372,8 @@ def dctimestep_main(argv: Sequence[str], stdin: bytes | None = None, device: int
     try:
         if len(files) > 2:                       # V T D [s]
             smtx = sky(files[3] if len(files) > 3 else None)
-            tmat = load_matrix(files[1])
+            t_is_xml = not files[1].startswith("!") and "." in files[1][1:] and files[1].rsplit(".", 1)[1].lower() == "xml"
+            tmat = load_btdf(files[1]) if t_is_xml else load_matrix(files[1])
             dmat = load_matrix(files[2], tmat.shape[1], smtx.shape[0])
             cmtx = multiply(tmat, multiply(dmat, smtx, ctx=ctx), ctx=ctx)
         else:

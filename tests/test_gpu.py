@@ -756,6 +756,14 @@ def test_dctimestep_matrix_consumer(G, golden):
         f = np.frombuffer(pr.dctimestep("v.mtx", "t.mtx", "d.mtx", "sky_f.smx", header=False, outform="f"),
                           dtype=np.float32).reshape(11, 29, 3)
         np.testing.assert_allclose(f, R["vtds"], rtol=2e-5, atol=1e-30)
+        # three-phase form with a Klems BSDF XML as the transmission matrix (util/cmbsdf.c cm_loadBTDF)
+        B = np.load(golden / "bsdf.npz")
+        f = np.frombuffer(pr.dctimestep("v41.mtx", "bsdf_both.xml", "d41.mtx", "sky_f.smx", header=False, outform="f"),
+                          dtype=np.float32).reshape(9, 29, 3)
+        np.testing.assert_allclose(f, B["vtds_xml"], rtol=2e-5, atol=1e-30)
+        f = np.frombuffer(pr.dctimestep("ident41.mtx", "bsdf_back.xml", "ident41.mtx", "ident41.mtx", header=False, outform="f"),
+                          dtype=np.float32).reshape(41, 41, 3)
+        assert np.array_equal(f, B["bsdf_back"])                               # identity products are exact
     finally:
         os.chdir(cwd)
     rng = np.random.default_rng(4)

@@ -390,6 +390,35 @@ def test_matrix_file_reader_and_ascii_styles(G, golden):
         mtx.parse_matrix(b"#?RADIANCE\nNCOMP=1\nNROWS=1\nNCOLS=1\nFORMAT=ascii\n\n1\n")
 
 
+def test_bsdf_xml_transmission_matrix(golden, tmp_path):
+    """cm_loadBTDF (util/cmbsdf.c:168-203).  Klems-matrix BSDF XML -> the transmission matrix
+    the reference dctimestep derives from the same file (picked out with identity V, D and sky), bit for
+    bit: both transmission blocks with a separated diffuse floor, "Transmission Back" only (reciprocity,
+    incident in rows, zeros, a negative entry, junk ahead of the declaration), a basis defined by the file,
+    and purely Lambertian transmission (145x145 fallback)."""
+    from pyradiance_b200 import mtx
+    R = np.load(golden / "bsdf.npz")
+    for name in ("bsdf_both", "bsdf_back", "bsdf_custom", "bsdf_lamb"):
+        t = mtx.load_btdf(golden / "dct" / f"{name}.xml")
+        assert t.dtype == np.float32 and t.shape == R[name].shape, name
+        assert np.array_equal(t, R[name]), name
+    assert np.any(R["bsdf_both"][..., 0] != R["bsdf_both"][..., 1])        # the white conversion is not exactly grey
+    assert np.array_equal(mtx._basis_rot180([1, 8, 12]), [0, 5, 6, 7, 8, 1, 2, 3, 4, 15, 16, 17, 18, 19, 20, 9, 10, 11, 12, 13, 14])
+    tt = tmp_path / "tree.xml"
+    tt.write_text("<WindowElement><Optical><Layer><DataDefinition><IncidentDataStructure>TensorTree4"
+                  "</IncidentDataStructure></DataDefinition></Layer></Optical></WindowElement>")
+    with pytest.raises(_lib.RBError, match="unsupported BSDF"):
+        mtx.load_btdf(tt)
+    tt.write_text((golden / "dct" / "bsdf_custom.xml").read_text().replace(">Visible<", ">CIE-X<"))
+    with pytest.raises(_lib.RBError, match="CIE-X"):
+        mtx.load_btdf(tt)
+    tt.write_text("<Window><Optical/></Window>")
+    with pytest.raises(_lib.RBError, match="top level node"):
+        mtx.load_btdf(tt)
+    with pytest.raises(_lib.RBError, match="Cannot open"):
+        mtx.load_btdf(tmp_path / "missing.xml")
+
+
 def test_option_rejections_are_explicit():
     """Options whose behaviour is not built fail by name instead of being accepted and ignored."""
     c = _lib.Context(0)
