@@ -3,9 +3,12 @@ and exports every declared symbol, the scene loader, the octree builder, the
 option parser / defaults, the calcomp stand-in and its explicit rejections,
 the Python boundary's input parsing, and the multi-GPU row plumbing (gloo)."""
 import json
+import os
 import re
 import subprocess
 import sys
+
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -149,6 +152,47 @@ def test_own_oconv_matches_reference_oconv(workdir):
         s = port.Scene(mine)
         assert out == [s.name(i) for i in a["robj"][:200]]  # the reference reads our octree
     assert (a["robj"] >= 0).mean() > 0.9
+
+
+def test_own_oconv_writes_the_reference_octree_byte_for_byte(workdir, golden):
+    """the builder restates the reference's cube/surface tests (ot/o_face.c, ot/sphere.c,
+    ot/o_cone.c), its bounding cube (ot/bbox.c) and its subdivision rule, so everything after the header's
+    command line equals `oconv -f`'s output: seeded offices (polygons, spheres, cylinders; one and two
+    floors), the text fixtures (rings, spheres, sources), and non-default -n / -r.  Digests come from
+    the unmodified reference oconv (tests/golden/make_golden_oct.py)."""
+    import hashlib
+    import json
+    G = json.loads((golden / "octree_sha.json").read_text())
+
+    def sha(path):
+        d = path.read_bytes()
+        return hashlib.sha256(d[d.index(b"\n\n") + 2:]).hexdigest()
+    for name, case in G["scenes"].items():
+        rad = workdir / f"{name}.rad"
+        scenegen.write_office(rad, **case["args"])
+        _lib.oconv_files([rad], workdir / f"{name}.oct")
+        assert sha(workdir / f"{name}.oct") == case["sha256"], name
+    _lib.oconv_files([workdir / "office_3k.rad"], workdir / "opt.oct", objlim=3, maxres=2048)
+    assert sha(workdir / "opt.oct") == G["options"]["office_3k -n 3 -r 2048"]
+    cwd = os.getcwd()
+    for f, want in G["files"].items():
+        os.chdir((golden / f).parent)
+        try:
+            _lib.oconv_files([Path(f).name], workdir / "f.oct")
+        finally:
+            os.chdir(cwd)
+        assert sha(workdir / "f.oct") == want, f
+    # text parser corner cases: comments, a command line, a bad real
+    bad = workdir / "bad.rad"
+    bad.write_text("# comment\nvoid plastic p # trailing comment\n0\n0\n5 .5 .5 .5 0 0\n\n!genbox p b 1 1 1\n")
+    with pytest.raises(_lib.RBError, match="command"):
+        _lib.oconv_files([bad], workdir / "bad.oct")
+    bad.write_text("void plastic p\n0\n0\n5 .5 .5 x 0 0\n")
+    with pytest.raises(_lib.RBError, match="bad real argument"):
+        _lib.oconv_files([bad], workdir / "bad.oct")
+    bad.write_text("void plastic p\n0\n0\n5 +.5 5e-1 .5 0 0\np polygon t\n0\n0\n9 0 0 0  1 0 0  0 1 0\n")
+    _lib.oconv_files([bad], workdir / "ok.oct")
+    assert port.Scene(workdir / "ok.oct").name(1) == "t"
 
 
 def test_ray_input_parsing():
