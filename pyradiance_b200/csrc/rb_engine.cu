@@ -362,6 +362,8 @@ bool Engine::ensure_queues(std::string& err, size_t hint) {
 bool Engine::size_trace_grid(std::string& err) {
     int per_sm = 0, nsm = 0;
     trace_smem_ = (size_t)(S_.maxdepth + 1) * WAVE_THREADS * sizeof(int);
+    if (const char* e = getenv("RB_TRACE_CARVEOUT"))      // developer knob: shared-memory share of the SM's 256 KB, percent
+        CK(cudaFuncSetAttribute(k_trace, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, WAVE_THREADS, trace_smem_));
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev_));
     if (const char* e = getenv("RB_TRACE_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));   // developer knob

@@ -39,6 +39,15 @@ namespace rb {
 #ifndef RB_FETCH_MIN
 #define RB_FETCH_MIN 6           // refill a warp when this many lanes are idle
 #endif
+#ifndef RB_CSTEPS
+#define RB_CSTEPS 1              // cubes a lane may step through per round while it lands in empty leaves
+#endif
+#ifndef RB_STEP_BRANCHLESS
+#define RB_STEP_BRANCHLESS 1
+#endif
+#ifndef RB_SPHERE_INLINE
+#define RB_SPHERE_INLINE 1
+#endif
 #ifndef RB_WALK_STATS
 #define RB_WALK_STATS 0          // count node / leaf-entry / surface-test visits (developer builds)
 #endif
@@ -47,7 +56,10 @@ namespace rb {
 #else
 #define RB_STAT(x)
 #endif
-#define RB_PAIRS (32 * RB_OPR)
+#ifndef RB_PAIR_CAP
+#define RB_PAIR_CAP 192          // (ray, surface) pairs a warp takes per pass; what does not fit waits for the next pass
+#endif
+#define RB_PAIRS (32 * RB_OPR < RB_PAIR_CAP ? 32 * RB_OPR : RB_PAIR_CAP)
 #ifndef RB_SLOW_MIN
 #define RB_SLOW_MIN 0            // lanes in curved-surface leaves that gather before their round runs (0: off; measured slower)
 #endif
@@ -324,6 +336,32 @@ __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, uns
         const bool ok = cand_face(hot, g, n01, n2o, box, org, rd, tmax, t, fr);
         sm.ct[wid][p] = t;
         sm.cid[wid][p] = ok ? ((RB_ENT_ID(ent.x) << 1) | (int)fr) : -1;
+#if RB_SPHERE_INLINE
+    } else if ((kind == PK_SPHERE) | (kind == PK_BUBBLE)) {
+        // o_sphere (sphere.c:16-83) on the record words the pair loop already holds (centre, radius):
+        // short enough to stay in line, which keeps the out-of-line second pass for the cone family
+        const double org[3] = {sm.ray[0][own], sm.ray[1][own], sm.ray[2][own]};
+        const double rd[3] = {sm.ray[3][own], sm.ray[4][own], sm.ray[5][own]};
+        const double ctr[3] = {n01.x, n01.y, n2o.x};
+        double a = 0, b = 0, c = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            a += rd[i] * rd[i];
+            const double d = org[i] - ctr[i];
+            b += 2.0 * rd[i] * d;
+            c += d * d;
+        }
+        c -= n2o.y * n2o.y;
+        double r0, r1;
+        const int nroots = quadratic(r0, r1, a, b, c);
+        double t = 0.0; int i = 0;
+        if (nroots >= 1 && r0 > RB_FTINY) { t = r0; i = 0; }
+        else if (nroots >= 2 && r1 > RB_FTINY) { t = r1; i = 1; }
+        const bool ok = (t > 0.0) & (t <= sm.rot[own] + 8 * RB_FTINY);
+        const bool fr = !((i > 0) ^ (kind == PK_BUBBLE));
+        sm.ct[wid][p] = t;
+        sm.cid[wid][p] = ok ? ((RB_ENT_ID(ent.x) << 1) | (int)fr) : -1;
+#endif
     } else {                         // rare kinds: second pass, again with all lanes
         sm.cid[wid][p] = -1;
         if (kind == PK_UNSUPPORTED) { atomicOr(errflag, RB_ERR_UNSUP_PRIM); *errobj = (unsigned)RB_ENT_ID(ent.x); }
@@ -521,17 +559,19 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
         RB_STAT(if (act & full) { ws.leafents += kleft + 1; ws.prims += kleft; })
         // ---- phase B: the warp tests the leaves' surfaces as (ray, surface) pairs ----
         for (;;) {
-            const int m = min(kleft, RB_OPR);
-            int incl = m;
+            if (!__any_sync(FULL, kleft > 0)) break;
+            const int m0 = min(kleft, RB_OPR);
+            int incl = m0;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 int v = __shfl_up_sync(FULL, incl, d);
                 if ((int)lane >= d) incl += v;
             }
-            const int total = __shfl_sync(FULL, incl, 31);
+            const int total = min(__shfl_sync(FULL, incl, 31), RB_PAIRS);
             if (total == 0) break;
             const unsigned wbase = wid * 32;
-            const int e0 = incl - m;
+            const int e0 = incl - m0;
+            const int m = min(m0, max(0, RB_PAIRS - e0));     // the pair table holds RB_PAIRS per pass
             for (int j = 0; j < m; j++)               // owners publish their pairs, descending set index
                 sm.pair[wid][e0 + j] = ((unsigned)(setoff + kleft - j) << 5) | lane;
             if (lane == 0) sm.ndef[wid] = 0;
@@ -625,34 +665,49 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
             kleft -= m;
             __syncwarp();
         }
-        // ---- phase C: accept (checkhit / aft plane), else step to the neighbour cube ----
+        // ---- phase C: accept (checkhit / aft plane), else step to the neighbour cube; a lane
+        //      that lands in an EMPTY leaf has nothing to do in phases A and B, so it keeps
+        //      stepping (up to RB_CSTEPS cubes per round) instead of idling through a round ----
         if (act) {
             ix = sm.cell[0][tid]; iy = sm.cell[1][tid]; iz = sm.cell[2][tid];
             Ld = sm.lvl[tid];
             int L = Ld & 0xff;
             const int dirf = Ld >> 8;
-            const double size = cube_size(cs, L);
-            const double lox = fma((double)ix, size, S.cuorg[0]);
-            const double loy = fma((double)iy, size, S.cuorg[1]);
-            const double loz = fma((double)iz, size, S.cuorg[2]);
-            const double hix = lox + size, hiy = loy + size, hiz = loz + size;
             const double dir[3] = {sm.ray[3][tid], sm.ray[4][tid], sm.ray[5][tid]};
             const int ro = sm.robj[tid];
-            bool done = false;
-            if (full ? (ro >= 0) : ((fl & WF_AFT) && ro < 0)) {
-                // checkhit (raytrace.c:756-759) / aft-plane point in an empty leaf (:709-710)
-                const double rot = sm.rot[tid];
-                const double px = sm.ray[0][tid] + rot * dir[0];
-                const double py = sm.ray[1][tid] + rot * dir[1];
-                const double pz = sm.ray[2][tid] + rot * dir[2];
-                if (!(lox > px || px >= hix || loy > py || py >= hiy || loz > pz || pz >= hiz)) {
-                    done = true;
-                    if (full) fl |= WF_RESULT;
+            double pos[3] = {sm.pos[0][tid], sm.pos[1][tid], sm.pos[2][tid]};
+            bool done = false, fullc = full;
+#pragma unroll 1
+            for (int cstep = 0;; cstep++) {
+                const double size = cube_size(cs, L);
+                const double lox = fma((double)ix, size, S.cuorg[0]);
+                const double loy = fma((double)iy, size, S.cuorg[1]);
+                const double loz = fma((double)iz, size, S.cuorg[2]);
+                const double hix = lox + size, hiy = loy + size, hiz = loz + size;
+                if (fullc ? (ro >= 0) : ((fl & WF_AFT) && ro < 0)) {
+                    // checkhit (raytrace.c:756-759) / aft-plane point in an empty leaf (:709-710)
+                    const double rot = sm.rot[tid];
+                    const double hx = sm.ray[0][tid] + rot * dir[0];
+                    const double hy = sm.ray[1][tid] + rot * dir[1];
+                    const double hz = sm.ray[2][tid] + rot * dir[2];
+                    if (!(lox > hx || hx >= hix || loy > hy || hy >= hiy || loz > hz || hz >= hiz)) {
+                        done = true;
+                        if (fullc) fl |= WF_RESULT;
+                        break;
+                    }
                 }
-            }
-            if (!done) {
                 // advance to next cube (raytrace.c:712-738)
-                const double pos[3] = {sm.pos[0][tid], sm.pos[1][tid], sm.pos[2][tid]};
+#if RB_STEP_BRANCHLESS
+                // the three plane distances are independent: computed unconditionally (with a harmless
+                // denominator on an axis the ray does not move along) so their division sequences interleave
+                const double tx = (((dirf & 1) ? hix : lox) - pos[0]) / ((dirf & 0x11) ? dir[0] : 1.0);
+                const double ty = (((dirf & 2) ? hiy : loy) - pos[1]) / ((dirf & 0x22) ? dir[1] : 1.0);
+                const double tz = (((dirf & 4) ? hiz : loz) - pos[2]) / ((dirf & 0x44) ? dir[2] : 1.0);
+                int ax = 0;
+                double t = (dirf & 0x11) ? tx : RB_FHUGE;
+                if ((dirf & 0x22) && ty < t) { t = ty; ax = 1; }
+                if ((dirf & 0x44) && tz < t) { t = tz; ax = 2; }
+#else
                 int ax = 0;
                 double t;
                 if (dirf & 0x11) {
@@ -670,24 +725,26 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                     dt = (dt - pos[2]) / dir[2];
                     if (dt < t) { t = dt; ax = 2; }
                 }
-                px = pos[0] + dir[0] * t; py = pos[1] + dir[1] * t; pz = pos[2] + dir[2] * t;
-                sm.pos[0][tid] = px; sm.pos[1][tid] = py; sm.pos[2][tid] = pz;
+#endif
+                pos[0] = pos[0] + dir[0] * t; pos[1] = pos[1] + dir[1] * t; pos[2] = pos[2] + dir[2] * t;
                 // step to the neighbour, ascending on overflow (raytrace.c:688-706):
                 // climb while the cell coordinate along ax cannot move that way
                 const bool positive = dirf & (1 << ax);
                 const unsigned ia = ax == 0 ? ix : ax == 1 ? iy : iz;
                 const unsigned blocked = positive ? ia : ~ia;          // trailing ones = levels to climb
                 const int up = (~blocked) ? __ffs(~blocked) - 1 : 32;  // number of trailing one bits
-                if (up >= L) { done = true; if (ro >= 0) fl |= WF_RESULT; }    // left the scene cube
-                else {
-                    ix >>= up; iy >>= up; iz >>= up; L -= up;
-                    if (ax == 0) ix ^= 1; else if (ax == 1) iy ^= 1; else iz ^= 1;
-                    const int br = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
-                    w = __ldg(&S.nodes[(size_t)stk[(L - 1) * NT + tid] * 8 + br]);
-                    RB_STAT(ws.nodes++;)
-                    Ld = (Ld & ~0xff) | L;
-                }
+                if (up >= L) { done = true; if (ro >= 0) fl |= WF_RESULT; break; }    // left the scene cube
+                ix >>= up; iy >>= up; iz >>= up; L -= up;
+                if (ax == 0) ix ^= 1; else if (ax == 1) iy ^= 1; else iz ^= 1;
+                const int br = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
+                w = __ldg(&S.nodes[(size_t)stk[(L - 1) * NT + tid] * 8 + br]);
+                RB_STAT(ws.nodes++;)
+                if ((w != -1) | (cstep + 1 >= RB_CSTEPS)) break;
+                fullc = false;
             }
+            px = pos[0]; py = pos[1]; pz = pos[2];
+            sm.pos[0][tid] = px; sm.pos[1][tid] = py; sm.pos[2][tid] = pz;
+            Ld = (Ld & ~0xff) | L;
             if (done) fl |= WF_DONE;
         }
     }
