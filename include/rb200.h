@@ -73,13 +73,14 @@ typedef struct rb_params {
 /* per-ray report of rb_rtrace (the fields rtrace's -o spec can print) */
 typedef struct rb_ray_result {
     double rop[3];         /* -op intersection point */
-    double ron[3];         /* -on unperturbed normal */
+    double ron[3];         /* -oN unperturbed normal, as intersected */
     double rot;            /* -oL distance (1e10 = none) */
     double rod;
     int32_t robj;          /* -os surface object index, -1 none */
     int32_t omod;          /* -om modifier object index, -1 none */
     float rweight;         /* -ow */
-    int32_t pad;
+    int32_t pad;           /* 1: the material reversed the surface (hit from behind; flipsurface), so -on = -(...) */
+    double pert[3];        /* normal perturbation (smooth mesh triangles; 0 otherwise): -on = raynormal(ron + pert) */
 } rb_ray_result;
 
 /* counters of the last compute call (device-side, summed over launches) */

@@ -43,7 +43,7 @@ class rb_stats(C.Structure):
 
 RAY_RESULT_DTYPE = np.dtype([
     ("rop", "<f8", 3), ("ron", "<f8", 3), ("rot", "<f8"), ("rod", "<f8"),
-    ("robj", "<i4"), ("omod", "<i4"), ("rweight", "<f4"), ("pad", "<i4"),
+    ("robj", "<i4"), ("omod", "<i4"), ("rweight", "<f4"), ("pad", "<i4"), ("pert", "<f8", (3,)),
 ])
 
 RB_IRRAD_NONE, RB_IRRAD_RTRACE, RB_IRRAD_RCONTRIB, RB_IRRAD_MANAGER = 0, 1, 2, 3

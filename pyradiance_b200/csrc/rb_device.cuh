@@ -114,6 +114,7 @@ struct RayResult {
     int omod;               // its modifier object index or -1
     float rweight;
     int pad;
+    double pert[3];         // RAY.pert of the primary hit (o_mesh.c:201-209)
 };
 
 struct DCounters {

@@ -88,11 +88,13 @@ __global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(
         r.rsrc = q.rsrc;
         r.key = ((unsigned long long)q.key_hi << 32) | q.key_lo;
         r.nchild = 0;
-        r.robj = hr.robj; r.rot = hr.rot; r.rod = hr.rod; r.flat = false;
+        r.robj = hr.robj; r.rot = hr.rot; r.rod = hr.rod; r.flat = false; r.xfl = 0;
         if (hr.local) {
             hit_frame(A.S, hr.robj, hr.rot, r.org, r.dir, r.rop, r.ron, r.rod);
-            int kind = __ldg(&A.S.objhdr[hr.robj]).x & 0xff;
-            r.flat = (kind == PK_FACE) | (kind == PK_RING);
+            const int hx = __ldg(&A.S.objhdr[hr.robj]).x;
+            const int kind = hx & 0xff;
+            r.flat = ((kind == PK_FACE) | (kind == PK_RING)) & !(hx & PX_NOTFLAT);
+            r.xfl = (unsigned char)((hx >> 13) & 3);          // PX_SMOOTH, PX_PHONG
         } else {
             for (int k = 0; k < 3; k++) { r.rop[k] = r.org[k]; r.ron[k] = -r.dir[k]; }
         }
@@ -102,8 +104,15 @@ __global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(
             o.rot = r.rot; o.rod = r.rod; o.robj = r.robj;
             o.omod = r.robj >= 0 ? __ldg(&A.S.objhdr[r.robj]).y : -1;
             o.rweight = r.rweight; o.pad = 0;
+            o.pert[0] = o.pert[1] = o.pert[2] = 0.0;
+            if (r.xfl & 1) smooth_pert(A.S, r.robj, r.rop, r.ron, false, o.pert);
         }
-        if (r.robj >= 0) shade_ray(A, r);
+        if (r.robj >= 0) {
+            const bool front = r.rod > 0.0;
+            shade_ray(A, r);
+            // the material reversed a surface hit from behind (flipsurface): rtrace -on reports it that way
+            if (A.res && r.crtype == RT_PRIMARY && front != (r.rod > 0.0)) A.res[r.row - A.row0].pad = 1;
+        }
     }
 }
 
@@ -144,7 +153,7 @@ __device__ void init_ray(const WaveArgs& A, const InitArgs& I, unsigned i) {
     r.coef[0] = r.coef[1] = r.coef[2] = 1.f;
     r.rweight = 1.f; r.row = A.res ? A.row0 + i : row;
     r.crtype = RT_PRIMARY; r.rlvl = 0; r.rdepth = 0; r.rsrc = -1;
-    r.robj = -1; r.flat = false; r.key = key; r.nchild = 0; r.rmax = 0.0;
+    r.robj = -1; r.flat = false; r.xfl = 0; r.key = key; r.nchild = 0; r.rmax = 0.0;
     r.rod = 1.0;
     for (int k = 0; k < 3; k++) { r.ron[k] = dir[k]; r.dir[k] = -dir[k]; }
     if (I.irrad == IRR_RTRACE) {                     // rtrace.c:443-448,415-432
@@ -162,6 +171,7 @@ __device__ void init_ray(const WaveArgs& A, const InitArgs& I, unsigned i) {
         RayResult& o = A.res[i];
         for (int k = 0; k < 3; k++) { o.rop[k] = r.rop[k]; o.ron[k] = r.ron[k]; }
         o.rot = r.rot; o.rod = r.rod; o.robj = -1; o.omod = -1; o.rweight = 1.f; o.pad = 0;
+        o.pert[0] = o.pert[1] = o.pert[2] = 0.0;
     }
     const float lamb[5] = {(float)RB_PI, (float)RB_PI, (float)RB_PI, 0.f, 0.f};
     m_normal(A, r, MK_PLASTIC, lamb);

@@ -350,10 +350,29 @@ namespace {
 // A compiled triangle mesh (.rtm): common/readmesh.c:124-305, common/mesh.h.
 struct MeshFile {
     std::vector<Object> mats;                 // mesh-local materials (frozen scene)
-    struct Tri { double v[3][3]; int mat; };  // mesh-space vertices, local material index (-1 void)
-    std::vector<Tri> tris;
-    bool has_normals = false;
+    struct Tri { double v[3][3]; int mat; bool smooth; double n[3][3]; };  // mesh-space vertices, local material
+    std::vector<Tri> tris;                    // index (-1 void), vertex normals when all three vertices carry one
 };
+
+// common/dircode.c:56-79 decodedir(): the 4-byte direction code of a vertex normal
+static void decode_dir(double dv[3], int32_t dc) {
+    const double DCSCALE = 11584.5;
+    enum { FXNEG = 01, FYNEG = 02, FZNEG = 04, F1X = 010, F2Z = 020, F1SFT = 5, F2SFT = 18, FMASK = 0x1fff };
+    if (!dc) { dv[0] = dv[1] = dv[2] = 0.; return; }
+    const double d1 = (dc >> F1SFT & FMASK) * (1. / DCSCALE);
+    const double d2 = (dc >> F2SFT & FMASK) * (1. / DCSCALE);
+    const double der = sqrt(1. - d1 * d1 - d2 * d2);
+    if (dc & F1X) {
+        dv[0] = d1;
+        if (dc & F2Z) { dv[1] = der; dv[2] = d2; } else { dv[1] = d2; dv[2] = der; }
+    } else {
+        dv[1] = d1;
+        if (dc & F2Z) { dv[0] = der; dv[2] = d2; } else { dv[0] = d2; dv[2] = der; }
+    }
+    if (dc & FXNEG) dv[0] = -dv[0];
+    if (dc & FYNEG) dv[1] = -dv[1];
+    if (dc & FZNEG) dv[2] = -dv[2];
+}
 
 static bool load_rtm(const std::string& path, MeshFile& mf, std::string& err) {
     std::ifstream f(path, std::ios::binary);
@@ -387,7 +406,7 @@ static bool load_rtm(const std::string& path, MeshFile& mf, std::string& err) {
     if (!read_frozen_scene(rd, objsize, mf.mats, err)) { err = "(" + path + "): " + err; return false; }
     long npatches = rd.getint(4);
     if (rd.bad || npatches < 0) { err = "(" + path + "): truncated mesh"; return false; }
-    struct Patch { std::vector<uint32_t> xyz; int nverts; };
+    struct Patch { std::vector<uint32_t> xyz; std::vector<int32_t> norm; int nverts; };
     std::vector<Patch> patches(npatches);
     struct RawTri { long v[3]; int mat; };
     std::vector<RawTri> raw;
@@ -399,7 +418,7 @@ static bool load_rtm(const std::string& path, MeshFile& mf, std::string& err) {
         patches[pn].nverts = nv;
         patches[pn].xyz.resize((size_t)nv * 3);
         for (int i = 0; i < nv * 3; i++) patches[pn].xyz[i] = (uint32_t)rd.getint(4);
-        if (flags & 2) { mf.has_normals = true; for (int i = 0; i < nv; i++) rd.getint(4); }
+        if (flags & 2) { patches[pn].norm.resize(nv); for (int i = 0; i < nv; i++) patches[pn].norm[i] = (int32_t)rd.getint(4); }
         if (flags & 4) for (int i = 0; i < nv * 2; i++) rd.getint(4);
         int nt = (int)rd.getint(2);
         if (nt < 0 || nt > 512) { err = "(" + path + "): bad number of local triangles"; return false; }
@@ -436,10 +455,14 @@ static bool load_rtm(const std::string& path, MeshFile& mf, std::string& err) {
     for (const RawTri& t : raw) {
         MeshFile::Tri o;
         o.mat = t.mat;
+        o.smooth = true;                          // mesh.c:316: flags of the three vertices ANDed
         for (int k = 0; k < 3; k++) {
             long pn = t.v[k] >> 8; int vid = (int)(t.v[k] & 0xff);
             if (pn < 0 || pn >= npatches || vid >= patches[pn].nverts) { err = "(" + path + "): bad mesh vertex reference"; return false; }
             for (int i = 0; i < 3; i++) o.v[k][i] = cuorg[i] + (patches[pn].xyz[(size_t)vid * 3 + i] + .5) * vres;
+            const int32_t dc = patches[pn].norm.empty() ? 0 : patches[pn].norm[vid];      // mesh.c:258-261
+            if (dc) decode_dir(o.n[k], dc);
+            else { o.smooth = false; o.n[k][0] = o.n[k][1] = o.n[k][2] = 0.; }
         }
         mf.tris.push_back(o);
     }
@@ -482,10 +505,6 @@ bool Scene::expand_volumes(const std::string& basedir, int depth) {
                 MeshNested mn;
                 mn.mf = std::make_shared<MeshFile>();
                 if (!load_rtm(path, *mn.mf, error)) return false;
-                if (mn.mf->has_normals) {
-                    error = "unsupported mesh \"" + msh.sargs[0] + "\": vertex normals (smooth shading) are not built";
-                    return false;
-                }
                 mn.remap.assign(mn.mf->mats.size(), -1);
                 for (size_t j = 0; j < mn.mf->mats.size(); j++) {
                     Object c = mn.mf->mats[j];
@@ -501,9 +520,13 @@ bool Scene::expand_volumes(const std::string& basedir, int depth) {
                 Object c;
                 c.otype = OT_POLYGON; c.tname = "polygon";
                 if (msh.omod < 0 && t.mat >= 0 && t.mat < (int)mit->second.remap.size()) { c.name = "M-Tri"; c.omod = mit->second.remap[t.mat]; }
-                else { c.name = msh.name; c.omod = msh.omod; }
+                else { c.name = msh.name; c.omod = msh.omod; c.volume_obj = true; }
                 c.fargs.resize(9);
                 for (int k = 0; k < 3; k++) xf_point(&c.fargs[3 * (mirrored ? 2 - k : k)], t.v[k], x);
+                if (t.smooth) {              // o_mesh.c:201-209: the interpolated normal goes through the forward
+                    c.vnorm.resize(9);       // matrix (multv3) and is normalised after that, so the vertex normals may
+                    for (int k = 0; k < 3; k++) xf_vector(&c.vnorm[3 * (mirrored ? 2 - k : k)], t.n[k], x);   // be moved first
+                }
                 objs.push_back(std::move(c));
             }
             objs[i].expanded = true;
@@ -544,7 +567,7 @@ bool Scene::expand_volumes(const std::string& basedir, int depth) {
             if (o.expanded) continue;
             if (!ot_is_surface(o.otype) || o.otype == OT_SOURCE) continue;
             Object c = o;
-            if (inst.omod >= 0) { c.name = inst.name; c.omod = inst.omod; }      // o_instance.c:41-43
+            if (inst.omod >= 0) { c.name = inst.name; c.omod = inst.omod; c.volume_obj = true; }      // o_instance.c:41-43
             else c.omod = o.omod >= 0 ? remap[o.omod] : -1;
             std::vector<double>& a = c.fargs;
             if (o.otype == OT_POLYGON) {
@@ -777,6 +800,34 @@ static size_t geom_alloc(FlatScene& fs, size_t n) {
     return off;
 }
 
+// common/tmesh.c:45-93 comp_baryc(): out = {axis, tm[0][0..2], tm[1][0..2]}; false for a degenerate triangle
+static bool comp_baryc(double out[7], const double* v1, const double* v2, const double* v3) {
+    double va[3], vab[3], vcb[3];
+    for (int k = 0; k < 3; k++) { vab[k] = v1[k] - v2[k]; vcb[k] = v3[k] - v2[k]; }
+    vcross(va, vab, vcb);
+    int ax = (va[1] * va[1] > va[0] * va[0]);
+    if (va[2] * va[2] > va[ax] * va[ax]) ax = 2;
+    const int ax0 = (ax + 1) % 3, ax1 = (ax + 2) % 3;
+    out[0] = ax;
+    for (int i = 0; i < 2; i++) {
+        vab[0] = v1[ax0] - v2[ax0]; vcb[0] = v3[ax0] - v2[ax0];
+        vab[1] = v1[ax1] - v2[ax1]; vcb[1] = v3[ax1] - v2[ax1];
+        double d = vcb[0] * vcb[0] + vcb[1] * vcb[1];
+        if (d <= FTINY * FTINY) return false;
+        d = (vcb[0] * vab[0] + vcb[1] * vab[1]) / d;
+        va[0] = vab[0] - vcb[0] * d;
+        va[1] = vab[1] - vcb[1] * d;
+        d = va[0] * va[0] + va[1] * va[1];
+        if (d <= FTINY * FTINY) return false;
+        d = 1.0 / d;
+        out[1 + 3 * i] = va[0] *= d;
+        out[2 + 3 * i] = va[1] *= d;
+        out[3 + 3 * i] = -(v2[ax0] * va[0] + v2[ax1] * va[1]);
+        const double* vt = v1; v1 = v2; v2 = v3; v3 = vt;
+    }
+    return true;
+}
+
 // common/face.c:35-106 getface() -> plane + 2-D projected vertices
 static void flatten_face(const Object& o, FlatScene& fs, int32_t hdr[4], std::string& warn) {
     int nf = (int)o.fargs.size();
@@ -814,9 +865,17 @@ static void flatten_face(const Object& o, FlatScene& fs, int32_t hdr[4], std::st
     int xi = (ax + 1) % 3, yi = (xi + 1) % 3;
     // record: plane (4 doubles), 2-D bounding box xmin xmax ymin ymax as 4 floats rounded
     // OUTWARD (2 doubles' worth; a conservative reject only), vertices (2 doubles each)
-    size_t off = geom_alloc(fs, 6 + 2 * (size_t)nv);
+    // a mesh triangle with vertex normals (o_mesh.c:193-209) also carries, after its vertices, the barycentric
+    // coordinate matrix of common/tmesh.c:45-93 comp_baryc() (axis, tm[2][3]) and its three normals: 16 doubles
+    double bary[7];
+    const bool smooth = o.vnorm.size() == 9 && nv == 3 && area != 0.0 && comp_baryc(bary, V(0), V(1), V(2));
+    size_t off = geom_alloc(fs, 6 + 2 * (size_t)nv + (smooth ? 16 : 0));
     double* g = &fs.geom[off];
     g[0] = norm[0]; g[1] = norm[1]; g[2] = norm[2]; g[3] = offset;
+    if (smooth) {
+        for (int k = 0; k < 7; k++) g[12 + k] = bary[k];
+        for (int k = 0; k < 9; k++) g[19 + k] = o.vnorm[k];
+    }
     double bb[4] = {1e300, -1e300, 1e300, -1e300};
     for (int i = 0; i < nv; i++) {
         double x = V(i)[xi], y = V(i)[yi];
@@ -843,7 +902,7 @@ static void flatten_face(const Object& o, FlatScene& fs, int32_t hdr[4], std::st
         bool b = Y(0) == Y(1) && X(1) == X(2) && Y(2) == Y(3) && X(3) == X(0);
         rect = (a || b) && bb[1] - bb[0] > 4 * FTINY && bb[3] - bb[2] > 4 * FTINY;
     }
-    hdr[0] = PK_FACE | (ax << 10) | (rect << 12) | (nv << 16);
+    hdr[0] = PK_FACE | (ax << 10) | (rect << 12) | (smooth ? PX_SMOOTH : 0) | (nv << 16);
     hdr[3] = (int32_t)off;
 }
 
@@ -1082,6 +1141,8 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
         if (!warn.empty()) fs.warnings.push_back(warn);
         if ((hdr[0] & 0xff) == PK_UNSUPPORTED) { fs.nsurf_unsupported++; note_unsupported(warn); }
         int flags = 0;
+        if (o.omod >= 0 && sc.objs[o.omod].name == "Phong") hdr[0] |= PX_PHONG;
+        if (o.volume_obj) hdr[0] |= PX_NOTFLAT;
         if (o.omod >= 0) {
             int mi = sc.findmaterial(i);
             if (mi >= 0) {

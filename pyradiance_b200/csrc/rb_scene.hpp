@@ -48,6 +48,8 @@ struct Object {
     std::vector<std::string> sargs;
     std::vector<double> fargs;
     bool expanded = false;      // instance / mesh replaced by world-space surfaces at load
+    bool volume_obj = false;    // hits report the enclosing instance / mesh object (modifier override)
+    std::vector<double> vnorm;  // mesh triangle with vertex normals: 3 world-space (unnormalised) normals
 };
 
 struct Scene {
@@ -84,6 +86,11 @@ struct Scene {
 // per-object header, 16 bytes: x = type | flags<<8 | nv<<16 ; y = omod ;
 // z = material slot (-1 none) ; w = offset into geom[] (doubles)
 enum : int { PF_TRANSP = 1, PF_HASMAT = 2 };
+// x bits above the flags: 10-11 projection axis, 12 exact rectangle, 13 smooth triangle (vertex normals after the
+// vertices), 14 the surface's modifier is named "Phong" (rt/rtotypes.h:13 usesPhongSmoothing)
+// 15 the reference reports the enclosing instance / mesh object for a hit on this surface (o_instance.c:41-43,
+// o_mesh.c:183-190: modifier override), which is not isflat() whatever the surface inside is
+enum : int { PX_SMOOTH = 1 << 13, PX_PHONG = 1 << 14, PX_NOTFLAT = 1 << 15 };
 enum : int {            // device primitive kinds (x & 0xff)
     PK_NONE = 0, PK_FACE, PK_SPHERE, PK_BUBBLE, PK_CONE, PK_CUP, PK_CYL,
     PK_TUBE, PK_RING, PK_UNSUPPORTED

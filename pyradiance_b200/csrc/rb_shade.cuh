@@ -75,6 +75,7 @@ struct RayCtx {             // the ray being shaded (a subset of RAY, rt/ray.h:4
     int crtype, rlvl, rdepth, rsrc;
     int robj;               // object hit (-1: none / fake irradiance hit)
     bool flat;              // isflat(ro->otype)
+    unsigned char xfl;      // 1: smooth mesh triangle (vertex normals), 2: its modifier is named "Phong"
     unsigned long long key;
     unsigned nchild;        // children spawned so far (for key derivation)
 };
@@ -673,12 +674,58 @@ __device__ __forceinline__ void raytrans(const WaveArgs& A, RayCtx& r) {
 }
 
 // normal.c:176-360.  a[] = material reals; mkind = MK_PLASTIC / MK_METAL / MK_TRANS.
+// RAY.pert of a smooth mesh triangle (o_mesh.c:193-209): barycentric weights of the hit point
+// (tmesh.c:96-112 eval_baryc on the matrix the loader stored behind the vertices), interpolated vertex normal,
+// normalised, minus the face normal.  Computed where a material needs it instead of being carried by every ray;
+// `flipped` says flipsurface() (raytrace.c) has already reversed r.ron, in which case it reverses pert too.
+__device__ __noinline__ bool smooth_pert(const DScene& S, int robj, const double rop[3], const double ron[3], bool flipped,
+                                         double pert[3]) {
+    const double* g = S.geom + __ldg(&S.objhdr[robj]).w;
+    int i = (int)g[12] + 1;
+    if (i >= 3) i -= 3;
+    const double u = rop[i];
+    if (++i >= 3) i -= 3;
+    const double v = rop[i];
+    double wt[3];
+    wt[0] = u * g[13] + v * g[14] + g[15];
+    wt[1] = u * g[16] + v * g[17] + g[18];
+    wt[2] = 1. - wt[1] - wt[0];
+    for (int k = 0; k < 3; k++) pert[k] = wt[0] * g[19 + k] + wt[1] * g[22 + k] + wt[2] * g[25 + k];
+    const double sgn = flipped ? -1.0 : 1.0;
+    if (normalize3(pert) != 0.0)
+        for (int k = 0; k < 3; k++) pert[k] = pert[k] - sgn * ron[k];
+    if (flipped)
+        for (int k = 0; k < 3; k++) pert[k] = -pert[k];
+    return dot3(pert, pert) > RB_FTINY * RB_FTINY;
+}
+__device__ __forceinline__ bool ray_pert(const DScene& S, const RayCtx& r, bool flipped, double pert[3]) {
+    if (!(r.xfl & 1) || r.robj < 0) return false;
+    return smooth_pert(S, r.robj, r.rop, r.ron, flipped, pert);
+}
+
+// raytrace.c:445-478 raynormal()
+__device__ __forceinline__ double raynormal(double norm[3], const RayCtx& r, const double pert[3]) {
+    for (int i = 0; i < 3; i++) norm[i] = r.ron[i] + pert[i];
+    if (normalize3(norm) == 0.0) {
+        for (int i = 0; i < 3; i++) norm[i] = r.ron[i];
+        return r.rod;
+    }
+    double newdot = -dot3(norm, r.dir);
+    if ((newdot > 0.0) ^ (r.rod > 0.0)) {
+        for (int i = 0; i < 3; i++) norm[i] += 2.0 * newdot * r.dir[i];
+        newdot = -newdot;
+    }
+    return newdot;
+}
+
 __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind, const float* a) {
     const DParams& P = A.P;
     if ((r.crtype & RT_SHADOW) && mkind != MK_TRANS) return;      // easy shadow test
+    bool flipped = false;
     if (r.rod < 0.0) {
         if (!P.backvis) { raytrans(A, r); return; }
         r.rod = -r.rod; r.ron[0] = -r.ron[0]; r.ron[1] = -r.ron[1]; r.ron[2] = -r.ron[2];   // flipsurface
+        flipped = true;
     }
     NormDat nd;
     nd.mcolor[0] = a[0]; nd.mcolor[1] = a[1]; nd.mcolor[2] = a[2];
@@ -687,7 +734,10 @@ __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind
     if ((nd.alpha2 *= nd.alpha2) <= RB_FTINY) nd.specfl |= SP_PURE;
     nd.pnorm[0] = r.ron[0]; nd.pnorm[1] = r.ron[1]; nd.pnorm[2] = r.ron[2];
     nd.pdot = r.rod;
-    if (r.robj >= 0 && r.flat) nd.specfl |= SP_FLAT;
+    double pert[3];
+    const bool hastexture = ray_pert(A.S, r, flipped, pert);       // normal.c:221-226
+    if (hastexture) nd.pdot = raynormal(nd.pnorm, r, pert);
+    if (!hastexture && r.robj >= 0 && r.flat) nd.specfl |= SP_FLAT;
     if (nd.pdot < .001) nd.pdot = .001;
     nd.rspec = a[3];
     double fest = 0.;
@@ -703,6 +753,13 @@ __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind
             nd.specfl |= SP_TRAN;
             if (!(nd.specfl & SP_PURE) && P.specthresh >= nd.tspec - RB_FTINY) nd.specfl |= SP_TBLT;
             nd.prdir[0] = r.dir[0]; nd.prdir[1] = r.dir[1]; nd.prdir[2] = r.dir[2];
+            if (hastexture && !(r.crtype & (RT_SHADOW | RT_AMBIENT)) && !(r.xfl & 2)) {      // normal.c:251-262
+                double pd[3] = {r.dir[0] - pert[0], r.dir[1] - pert[1], r.dir[2] - pert[2]};
+                if (dot3(pd, r.ron) < -RB_FTINY) {
+                    normalize3(pd);
+                    nd.prdir[0] = pd[0]; nd.prdir[1] = pd[1]; nd.prdir[2] = pd[2];
+                }
+            }
         }
     } else
         nd.tdiff = nd.tspec = nd.trans = 0.0;
@@ -734,6 +791,8 @@ __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind
         QRay q;
         if (rayorigin(P, r, RT_REFLECTED, rc, true, q)) {
             for (int k = 0; k < 3; k++) q.dir[k] = r.dir[k] + nd.pnorm[k] * (2. * nd.pdot);
+            if (hastexture && dot3(q.dir, r.ron) <= RB_FTINY)          // penetration? (normal.c:314-316)
+                for (int k = 0; k < 3; k++) q.dir[k] = r.dir[k] + r.ron[k] * (2. * r.rod);
             normalize3(q.dir);
             push_ray(A, q);
         }
@@ -811,8 +870,12 @@ __device__ __forceinline__ void m_glass(const WaveArgs& A, RayCtx& r, const floa
     bool hastrans = max3(mcolor) > 1e-15f;
     if (hastrans) { for (int k = 0; k < 3; k++) if (mcolor[k] < 1e-15f) mcolor[k] = 1e-15f; }
     else if (r.crtype & RT_SHADOW) return;
-    if (r.rod < 0.0) { r.rod = -r.rod; r.ron[0] = -r.ron[0]; r.ron[1] = -r.ron[1]; r.ron[2] = -r.ron[2]; }
+    bool flipped = false;
+    if (r.rod < 0.0) { r.rod = -r.rod; r.ron[0] = -r.ron[0]; r.ron[1] = -r.ron[1]; r.ron[2] = -r.ron[2]; flipped = true; }
     double pdot = r.rod;
+    double pnorm[3] = {r.ron[0], r.ron[1], r.ron[2]}, pert[3];
+    const bool hastexture = ray_pert(A.S, r, flipped, pert);       // glass.c:91-98
+    if (hastexture) pdot = raynormal(pnorm, r, pert);
     double cos2 = sqrt((1.0 - 1.0 / (rindex * rindex)) + pdot * pdot / (rindex * rindex));
     if (hastrans)
         for (int k = 0; k < 3; k++) mcolor[k] = (float)pow((double)mcolor[k], 1.0 / cos2);
@@ -830,6 +893,11 @@ __device__ __forceinline__ void m_glass(const WaveArgs& A, RayCtx& r, const floa
         QRay q;
         if (rayorigin(P, r, RT_TRANS, rc, true, q)) {
             q.dir[0] = r.dir[0]; q.dir[1] = r.dir[1]; q.dir[2] = r.dir[2];
+            if (hastexture && !(r.crtype & (RT_SHADOW | RT_AMBIENT)) && !(r.xfl & 2)) {      // glass.c:124-130
+                double pd[3];
+                for (int k = 0; k < 3; k++) pd[k] = r.dir[k] + pert[k] * (2. * (1. - rindex));
+                if (normalize3(pd) != 0.0) { q.dir[0] = pd[0]; q.dir[1] = pd[1]; q.dir[2] = pd[2]; }
+            }
             push_ray(A, q);
         }
     }
@@ -843,7 +911,7 @@ __device__ __forceinline__ void m_glass(const WaveArgs& A, RayCtx& r, const floa
     }
     QRay q;
     if (rayorigin(P, r, RT_REFLECTED, rc, true, q)) {
-        for (int k = 0; k < 3; k++) q.dir[k] = r.dir[k] + r.ron[k] * (2. * pdot);
+        for (int k = 0; k < 3; k++) q.dir[k] = r.dir[k] + pnorm[k] * (2. * pdot);
         normalize3(q.dir);
         push_ray(A, q);
     }

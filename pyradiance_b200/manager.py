@@ -189,10 +189,13 @@ class Ray:
         self.rorg = tuple(rorg)
         self.rdir = tuple(rdir)
         self.rop = tuple(res["rop"])
-        self.ron = tuple(res["ron"])
-        self.pert = (0.0, 0.0, 0.0)
+        # the callback sees the RAY as shading left it: m_normal / m_glass reverse a surface that was
+        # hit from behind (flipsurface, raytrace.c), which `pad` = 1 in the result records
+        sgn = -1.0 if int(res["pad"]) == 1 else 1.0
+        self.ron = tuple(sgn * x for x in res["ron"])
+        self.pert = tuple(sgn * x for x in res["pert"])
         self.rmax = 0.0
-        self.rod = float(res["rod"])
+        self.rod = sgn * float(res["rod"])
         self.rot = float(res["rot"])
         self.rweight = float(res["rweight"])
         self.rno = rno

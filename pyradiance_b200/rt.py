@@ -217,6 +217,28 @@ def rtrace_main(argv: Sequence[str], stdin: bytes, device: int = 0, _shard=None)
         ctx.close()
 
 
+def _raynormal(res, rdir):
+    """rtrace -on: ron + pert normalised, turned back to the ray's side of the surface when the perturbation
+    tipped it over (raytrace.c:445-478), on the ray as the material left it -- m_normal / m_glass reverse a
+    surface hit from behind (flipsurface; `pad` = 1 in the result).  pert is zero except on smooth mesh
+    triangles (o_mesh.c:201-209)."""
+    sgn = np.where(res["pad"] == 1, -1.0, 1.0)
+    ron, pert, rod = res["ron"] * sgn[:, None], res["pert"] * sgn[:, None], res["rod"] * sgn
+    out = ron.copy()
+    sm = (pert * pert).sum(1) > 0
+    if sm.any():
+        nrm = ron[sm] + pert[sm]
+        ln = np.linalg.norm(nrm, axis=1)
+        ok = ln > 0
+        nrm[ok] /= ln[ok, None]
+        nd = -(nrm * rdir[sm]).sum(1)
+        fix = ok & ((nd > 0) ^ (rod[sm] > 0))
+        nrm[fix] += 2.0 * nd[fix, None] * rdir[sm][fix]
+        nrm[~ok] = ron[sm][~ok]
+        out[sm] = nrm
+    return out
+
+
 def _names(ctx, idx, none="*", void="void"):
     cache = {}
     out = []
@@ -268,8 +290,10 @@ def _format_rtrace(ctx, rays, values, res, outvals, outform) -> bytes:
             cols.append(("r", res["rot"].reshape(-1, 1)))
         elif ch == "p":
             cols.append(("r", res["rop"]))
-        elif ch in "Nn":
+        elif ch == "N":                # rtrace.c:787-804 oputN: unperturbed normal, flips undone
             cols.append(("r", np.where(hit[:, None], res["ron"], 0.0)))
+        elif ch == "n":                # rtrace.c:807-820 oputn: raynormal() of the ray as shading left it
+            cols.append(("r", np.where(hit[:, None], _raynormal(res, dnorm), 0.0)))
         elif ch == "w":
             cols.append(("r", res["rweight"].astype(np.float64).reshape(-1, 1)))
         elif ch == "c":

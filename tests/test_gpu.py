@@ -796,3 +796,36 @@ def test_nproc_spreads_records_over_gpus(office2k):
     t2 = pr.rtrace_main(["rtrace", "-n", "2"] + targs + [str(office2k)], rays.tobytes())
     assert len(t1) == 140_000 * 4 * 8 and t1 == t2
 
+
+
+def test_smooth_mesh_vertex_normals_vs_reference_golden(golden):
+    """mesh triangles with vertex normals (o_mesh.c:193-209 -> RAY.pert ->
+    raynormal() in m_normal / m_glass), against the reference rtrace on the same rays
+    (tests/golden/make_golden_smooth.py): surface and modifier names, distance, the unperturbed
+    (-oN) and perturbed (-on) normals, and the deterministic -ab 0 value, which sees the
+    perturbed normal through the sun's cosine and highlight, the mirror direction of the
+    metal, and the bent transmission through glass and trans (but not through "Phong")."""
+    g = np.load(golden / "smooth.npz")
+    rays = g["rays"]
+    out = pr.rtrace(rays.tobytes(), str(golden / "smooth" / "smoothroom.oct"), header=False, inform="d", outform="a",
+                    outspec="vNnLsm", params=[str(a) for a in g["args"]]).decode()
+    rows = [ln.split("\t") for ln in out.splitlines()]
+    assert len(rows) == len(rays)
+    surf = np.array([r[10] for r in rows]); mod = np.array([r[11] for r in rows])
+    assert (surf == g["surf"]).all() and (mod == g["mod"]).all()
+    val = np.array([[float(x) for x in r[0:3]] for r in rows])
+    fn = np.array([[float(x) for x in r[3:6]] for r in rows])
+    pn = np.array([[float(x) for x in r[6:9]] for r in rows])
+    dist = np.array([float(r[9]) for r in rows])
+    np.testing.assert_allclose(dist, g["dist"], rtol=2e-6)
+    np.testing.assert_allclose(fn, g["fnorm"], atol=2e-6)
+    np.testing.assert_allclose(pn, g["pnorm"], atol=2e-6)
+    smooth = np.abs(np.abs(g["pnorm"]) - np.abs(g["fnorm"])).max(1) > 1e-6
+    assert smooth.sum() > 1500
+    # values: a ray that grazes a triangle edge or a shadow boundary may fall on the other side in the last
+    # digits of a distance (the mesh is flattened into world space here), so allow a handful of outliers
+    bad = ~np.isclose(val, g["value"], rtol=2e-5, atol=1e-7).all(1)
+    assert bad.sum() <= 2, (bad.sum(), np.flatnonzero(bad)[:10], val[bad][:5], g["value"][bad][:5])
+    for m in ("sm_plastic", "sm_metal", "sm_glass", "sm_trans", "Phong", "green"):
+        k = (mod == m) & smooth
+        assert k.sum() > 30 and (~bad[k]).mean() > 0.97, m

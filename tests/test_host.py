@@ -294,6 +294,29 @@ def test_instances_and_meshes_flatten_like_reference(G, golden, workdir, name):
     assert ({"slat1", "lv_c", "post"} <= seen) if name == "room" else ({"M-Tri", "bump_c", "slat1"} <= seen)
 
 
+def test_smooth_mesh_loads_and_flattens(golden, workdir):
+    """A mesh with vertex normals (and a strip of faces without) is accepted by the loader; the
+    flattened scene, traced by the CPU oracle, reports the reference's surfaces, modifiers,
+    distances and unperturbed normals (tests/golden/make_golden_smooth.py; the perturbed normal
+    and the values it shades are checked on the GPU)."""
+    c = _lib.Context(0)
+    err = c.parse_octree(golden / "smooth" / "smoothroom.oct")
+    assert err is None or "no CUDA device" in err
+    flat = workdir / "smooth_flat.oct"
+    c.save_octree(flat)
+    g = np.load(golden / "smooth.npz")
+    s = port.Scene(flat)
+    r = s.rtrace(g["rays"])
+    hit = r["robj"] >= 0
+    names = np.array([s.name(o) if o >= 0 else "*" for o in r["robj"]])
+    mods = np.array([s.name(m) if o >= 0 else "*" for o, m in zip(r["robj"], r["omod"])])
+    local = g["dist"] < 1e9                      # the oracle reports distant sources (sky) as misses
+    assert (names[local] == g["surf"][local]).all() and (mods[local] == g["mod"][local]).all()
+    np.testing.assert_allclose(r["rot"][local], g["dist"][local], rtol=2e-6)
+    np.testing.assert_allclose(r["ron"][local], g["fnorm"][local], atol=2e-6)
+    assert hit[local].all() and (names == "M-Tri").sum() > 1000
+
+
 def test_sun_matrix_flattened_scene_oracle_vs_reference_golden(golden, workdir):
     """BASELINE config 5 in miniature: 145 `light` suns (one modifier, reinhart.cal
     rbin, -e MF:1) over louvre instances, meshes and a glass skylight.  The
