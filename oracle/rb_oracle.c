@@ -53,7 +53,7 @@ enum { PRIMARY = 01, RSHADOW = 02, REFLECTED = 04, REFRACTED = 010, TRANS = 020,
 
 enum { T_OTHER = 0, T_POLYGON, T_CONE, T_SPHERE, T_RING, T_CYLINDER, T_CUP, T_BUBBLE, T_TUBE, T_SOURCE, T_INSTANCE,
        T_MESH, T_ALIAS, T_PLASTIC, T_METAL, T_GLASS, T_TRANS, T_GLOW, T_LIGHT, T_ILLUM, T_SPOT, T_TRANSP_MAT,
-       T_OTHER_MAT, T_PATTERN, T_BRIGHTFUNC };
+       T_OTHER_MAT, T_PATTERN, T_BRIGHTFUNC, T_PLASTIC2, T_METAL2, T_TRANS2 };
 
 typedef struct {
     int omod, otype;
@@ -151,8 +151,8 @@ static int type_of(const char* n) {
         {"cup", T_CUP}, {"bubble", T_BUBBLE}, {"tube", T_TUBE}, {"source", T_SOURCE}, {"instance", T_INSTANCE},
         {"mesh", T_MESH}, {"alias", T_ALIAS}, {"plastic", T_PLASTIC}, {"metal", T_METAL}, {"glass", T_GLASS},
         {"trans", T_TRANS}, {"glow", T_GLOW}, {"light", T_LIGHT}, {"illum", T_ILLUM}, {"spotlight", T_SPOT},
-        {"dielectric", T_TRANSP_MAT}, {"interface", T_TRANSP_MAT}, {"mist", T_TRANSP_MAT}, {"trans2", T_TRANSP_MAT},
-        {"aBSDF", T_TRANSP_MAT}, {"plastic2", T_OTHER_MAT}, {"metal2", T_OTHER_MAT}, {"plasfunc", T_OTHER_MAT},
+        {"dielectric", T_TRANSP_MAT}, {"interface", T_TRANSP_MAT}, {"mist", T_TRANSP_MAT}, {"trans2", T_TRANS2},
+        {"aBSDF", T_TRANSP_MAT}, {"plastic2", T_PLASTIC2}, {"metal2", T_METAL2}, {"plasfunc", T_OTHER_MAT},
         {"metfunc", T_OTHER_MAT}, {"mirror", T_OTHER_MAT}, {"transfunc", T_OTHER_MAT}, {"BRTDfunc", T_OTHER_MAT},
         {"BSDF", T_OTHER_MAT}, {"WGMDfunc", T_OTHER_MAT}, {"plasdata", T_OTHER_MAT}, {"metdata", T_OTHER_MAT},
         {"transdata", T_OTHER_MAT}, {"antimatter", T_OTHER_MAT}, {"prism1", T_OTHER_MAT}, {"prism2", T_OTHER_MAT},
@@ -162,10 +162,10 @@ static int type_of(const char* n) {
     return T_PATTERN;     /* patterns, textures, mixtures: anything else is a non-material modifier */
 }
 static int is_surface(int t) { return t >= T_POLYGON && t <= T_SOURCE; }
-static int is_material(int t) { return (t >= T_PLASTIC && t <= T_SPOT) || t == T_TRANSP_MAT || t == T_OTHER_MAT; }
+static int is_material(int t) { return (t >= T_PLASTIC && t <= T_SPOT) || t == T_TRANSP_MAT || t == T_OTHER_MAT || (t >= T_PLASTIC2 && t <= T_TRANS2); }
 static int is_modifier(int t) { return !(t >= T_POLYGON && t <= T_MESH); }
 static int is_light(int t) { return t >= T_GLOW && t <= T_SPOT; }
-static int is_transp(int t) { return t == T_TRANS || t == T_GLASS || t == T_TRANSP_MAT; }
+static int is_transp(int t) { return t == T_TRANS || t == T_GLASS || t == T_TRANSP_MAT || t == T_TRANS2; }
 
 static int lastmod(const orc_scene* s, int before, const char* name) {
     int i;
@@ -942,13 +942,16 @@ static void rayvalue(orc_scene* s, RAY* r) { raytrace(s, r); }
 
 typedef struct {
     RAY* rp; int specfl; float mcolor[3], scolor[3]; double prdir[3], alpha2, rdiff, rspec, trans, tdiff, tspec, pnorm[3], pdot;
+    int aniso; double u[3], v[3], u_alpha, v_alpha;      /* plastic2 / metal2 / trans2 (aniso.c ANISODAT) */
 } NORMDAT;
 enum { SP_REFL = 01, SP_TRAN = 02, SP_PURE = 04, SP_FLAT = 010, SP_RBLT = 020, SP_TBLT = 040 };
 #define FRESNE(ci) (exp(-5.85 * (ci)) - 0.00202943064)
 #define FRESTHRESH 0.017999
 
+static void diraniso(orc_scene* s, float* scval, NORMDAT* np, const double* ldir, double omega);
 static void dirnorm(orc_scene* s, float* scval, NORMDAT* np, const double* ldir, double omega) {
     double ldot, lrdiff, ltdiff, dtmp, d2, d3, d4, vtmp[3]; int k;
+    if (np->aniso) { diraniso(s, scval, np, ldir, omega); return; }
     scval[0] = scval[1] = scval[2] = 0;
     ldot = dot(np->pnorm, ldir);
     if (ldot < 0.0 ? np->trans <= FTINY : np->trans >= 1.0 - FTINY) return;
@@ -1232,7 +1235,7 @@ static int m_normal(orc_scene* s, int mtype, const double* a, RAY* r, int ro_fla
         r->rod = -r->rod; for (k = 0; k < 3; k++) r->ron[k] = -r->ron[k];
         r->rflips++;
     }
-    nd.rp = r;
+    nd.rp = r; nd.aniso = 0;
     for (k = 0; k < 3; k++) nd.mcolor[k] = (float)a[k];
     nd.specfl = 0; nd.alpha2 = a[4];
     if ((nd.alpha2 *= nd.alpha2) <= FTINY) nd.specfl |= SP_PURE;
@@ -1313,6 +1316,143 @@ static int m_normal(orc_scene* s, int mtype, const double* a, RAY* r, int ro_fla
                     for (k = 0; k < 3; k++) r->rcol[k] += sr.rcol[k] * sr.rcoef[k];
                     break;
                 }
+            }
+        }
+    }
+    if (nd.rdiff > FTINY) {
+        for (k = 0; k < 3; k++) sctmp[k] = (float)(nd.mcolor[k] * nd.rdiff);
+        if (nd.specfl & SP_RBLT) for (k = 0; k < 3; k++) sctmp[k] += nd.scolor[k];
+        multambient(s, sctmp, r, nd.pnorm);
+        for (k = 0; k < 3; k++) r->rcol[k] += sctmp[k];
+    }
+    if (nd.tdiff > FTINY) {
+        double bnorm[3];
+        for (k = 0; k < 3; k++) { sctmp[k] = (float)(nd.mcolor[k] * ((nd.specfl & SP_TBLT) ? nd.trans : nd.tdiff)); bnorm[k] = -nd.pnorm[k]; }
+        multambient(s, sctmp, r, bnorm);
+        for (k = 0; k < 3; k++) r->rcol[k] += sctmp[k];
+    }
+    direct(s, r, &nd);
+    return 1;
+}
+
+/* ---- anisotropic Gaussian materials: plastic2, metal2, trans2 (rt/aniso.c) ----
+ * The orientation vector (string arguments 1-3) must be numeric constants here and
+ * the function file "." without a transform; anything else fails by name. */
+/* aniso.c:64-182 diraniso(): coefficient of one source sample */
+static void diraniso(orc_scene* s, float* scval, NORMDAT* np, const double* ldir, double omega) {
+    const double ua2 = np->u_alpha * np->u_alpha, va2 = np->v_alpha * np->v_alpha;
+    double ldot = dot(np->pnorm, ldir), w, h[3], au2, av2, e1, e2, nh; int k;
+    scval[0] = scval[1] = scval[2] = 0;
+    if (ldot < 0.0 ? np->trans <= FTINY : np->trans >= 1.0 - FTINY) return;      /* wrong side */
+    if ((ldot > FTINY) & (np->rdiff > FTINY)) {                                  /* diffuse reflection */
+        w = ldot * omega * np->rdiff * (1.0 / PI);
+        for (k = 0; k < 3; k++) scval[k] += (float)(np->mcolor[k] * w);
+    }
+    if ((ldot < -FTINY) & (np->tdiff > FTINY)) {                                 /* diffuse transmission */
+        w = -ldot * omega * np->tdiff * (1.0 / PI);
+        for (k = 0; k < 3; k++) scval[k] += (float)(np->mcolor[k] * w);
+    }
+    if (ldot > FTINY && np->specfl & SP_REFL) {                                  /* W-G-M-D highlight */
+        au2 = av2 = (np->specfl & SP_FLAT) ? (1. - s->P.dstrsrc) * omega * (0.25 / PI) : 0.0;
+        au2 += ua2; av2 += va2;
+        for (k = 0; k < 3; k++) h[k] = ldir[k] - np->rp->rdir[k];
+        e1 = dot(np->u, h); e1 *= e1 / au2;
+        e2 = dot(np->v, h); e2 *= e2 / av2;
+        nh = dot(np->pnorm, h); nh *= nh;
+        e1 = (e1 + e2) / nh;
+        w = exp(-e1) * dot(h, h) / (PI * nh * nh * sqrt(au2 * av2));
+        if (w > FTINY) { w *= ldot * omega; for (k = 0; k < 3; k++) scval[k] += (float)(np->scolor[k] * w); }
+    }
+    if (ldot < -FTINY && np->specfl & SP_TRAN) {                                 /* transmitted highlight */
+        au2 = av2 = omega * (1.0 / PI);
+        au2 += ua2; av2 += va2;
+        for (k = 0; k < 3; k++) h[k] = ldir[k] - np->prdir[k];
+        w = dot(h, h);
+        if (w > FTINY * FTINY) { e1 = dot(h, np->pnorm); w = 1.0 - e1 * e1 / w; }
+        if (w > FTINY * FTINY) {
+            e1 = dot(h, np->u); e1 *= e1 / au2;
+            e2 = dot(h, np->v); e2 *= e2 / av2;
+            w = exp(-((e1 + e2) / w));
+        } else w = 1.0;
+        w *= (1.0 / PI) * sqrt(-ldot / (np->pdot * au2 * av2));
+        if (w > FTINY) { w *= np->tspec * omega; for (k = 0; k < 3; k++) scval[k] += (float)(np->mcolor[k] * w); }
+    }
+}
+
+/* one direction of agaussamp()'s elliptical Gaussian (aniso.c:351-363 / 427-441): offset in the (u, v) plane */
+static double aniso_offset(orc_scene* s, const NORMDAT* np, double* cosp, double* sinp) {
+    double rv0 = frandom(s), rv1 = frandom(s), d;
+    *cosp = cos(2.0 * PI * rv0) * np->u_alpha; *sinp = sin(2.0 * PI * rv0) * np->v_alpha;
+    d = 1. / sqrt(*cosp * *cosp + *sinp * *sinp);
+    *cosp *= d; *sinp *= d;
+    if ((0. <= s->P.specjitter) & (s->P.specjitter < 1.)) rv1 = 1.0 - s->P.specjitter * rv1;
+    return (rv1 <= FTINY) ? 1.0 : sqrt(-log(rv1) / (*cosp * *cosp / (np->u_alpha * np->u_alpha) + *sinp * *sinp / (np->v_alpha * np->v_alpha)));
+}
+
+/* aniso.c:185-297 m_aniso() + :299-326 getacoords() + :329-470 agaussamp() (single-sample form) */
+static int m_aniso(orc_scene* s, const OBJ* m, RAY* r, int ro_flat) {
+    NORMDAT nd; const double* a = m->fargs; const int t = m->otype; float sctmp[3]; int k, ntr; double d, cosp, sinp, h[3]; char* end;
+    if (r->crtype & SHADOW) return 1;
+    if (m->nfargs != (t == T_TRANS2 ? 8 : 6)) { fail(s, "bad number of real arguments for", m->name); return 1; }
+    if (m->nsargs != 4 || strcmp(m->sargs[3], ".")) { fail(s, "oracle: function file / transform not built for", m->name); return 1; }
+    for (k = 0; k < 3; k++) {
+        nd.u[k] = strtod(m->sargs[k], &end);
+        if (end == m->sargs[k] || *end) { fail(s, "oracle: orientation is not a numeric constant in", m->name); return 1; }
+    }
+    if (r->rod < 0.0) {
+        if (!s->P.backvis) { raytrans(s, r); return 1; }
+        r->rod = -r->rod; for (k = 0; k < 3; k++) r->ron[k] = -r->ron[k];
+        r->rflips++;
+    }
+    nd.rp = r; nd.aniso = 1; nd.alpha2 = 0; nd.specfl = 0;
+    for (k = 0; k < 3; k++) { nd.mcolor[k] = (float)a[k]; nd.scolor[k] = 0; nd.pnorm[k] = r->ron[k]; nd.prdir[k] = r->rdir[k]; }
+    nd.u_alpha = a[4]; nd.v_alpha = a[5];
+    if ((nd.u_alpha <= FTINY) | (nd.v_alpha <= FTINY)) { fail(s, "roughness too small for", m->name); return 1; }
+    nd.pdot = r->rod;
+    if (nd.pdot < .001) nd.pdot = .001;
+    if ((nd.rspec = a[3]) > FTINY) {
+        nd.specfl |= SP_REFL;
+        for (k = 0; k < 3; k++) nd.scolor[k] = (float)((t == T_METAL2 ? nd.mcolor[k] : 1.0f) * nd.rspec);
+        if (s->P.specthresh >= nd.rspec - FTINY) nd.specfl |= SP_RBLT;
+    }
+    if (t == T_TRANS2) {
+        nd.trans = a[6] * (1.0 - nd.rspec); nd.tspec = nd.trans * a[7]; nd.tdiff = nd.trans - nd.tspec;
+        if (nd.tspec > FTINY) { nd.specfl |= SP_TRAN; if (s->P.specthresh >= nd.tspec - FTINY) nd.specfl |= SP_TBLT; }
+    } else nd.tdiff = nd.tspec = nd.trans = 0.0;
+    nd.rdiff = 1.0 - nd.trans - nd.rspec;
+    if (ro_flat) nd.specfl |= SP_FLAT;
+    /* getacoords(): v = n x u, u = v x n; a degenerate orientation falls back to an isotropic lobe */
+    cross(nd.v, nd.pnorm, nd.u);
+    if (normalize(nd.v) == 0.0) {
+        getperp0(nd.u, nd.pnorm);
+        cross(nd.v, nd.pnorm, nd.u);
+        nd.u_alpha = nd.v_alpha = sqrt(0.5 * (nd.u_alpha * nd.u_alpha + nd.v_alpha * nd.v_alpha));
+    } else cross(nd.u, nd.v, nd.pnorm);
+    if (nd.specfl & (SP_REFL | SP_TRAN)) {
+        RAY sr;
+        if ((nd.specfl & (SP_REFL | SP_RBLT)) == SP_REFL && rayorigin(s, &sr, RSPECULAR, r, nd.scolor) == 0) {
+            for (ntr = 0; ntr < 10; ntr++) {
+                d = aniso_offset(s, &nd, &cosp, &sinp);
+                for (k = 0; k < 3; k++) h[k] = nd.pnorm[k] + d * (cosp * nd.u[k] + sinp * nd.v[k]);
+                d = -2.0 * dot(h, r->rdir) / (1.0 + d * d);
+                for (k = 0; k < 3; k++) sr.rdir[k] = r->rdir[k] + h[k] * d;
+                if (dot(sr.rdir, r->ron) <= FTINY) continue;
+                normalize(sr.rdir);                              /* checknorm() */
+                rayvalue(s, &sr);
+                for (k = 0; k < 3; k++) r->rcol[k] += sr.rcol[k] * sr.rcoef[k];
+                break;
+            }
+        }
+        for (k = 0; k < 3; k++) sr.rcoef[k] = (float)(nd.mcolor[k] * nd.tspec);
+        if ((nd.specfl & (SP_TRAN | SP_TBLT)) == SP_TRAN && rayorigin(s, &sr, TSPECULAR, r, sr.rcoef) == 0) {
+            for (ntr = 0; ntr < 10; ntr++) {
+                d = aniso_offset(s, &nd, &cosp, &sinp);
+                for (k = 0; k < 3; k++) sr.rdir[k] = nd.prdir[k] + d * (cosp * nd.u[k] + sinp * nd.v[k]);
+                if (dot(sr.rdir, r->ron) >= -FTINY) continue;
+                normalize(sr.rdir);
+                rayvalue(s, &sr);
+                for (k = 0; k < 3; k++) r->rcol[k] += sr.rcol[k] * sr.rcoef[k];
+                break;
             }
         }
     }
@@ -1458,6 +1598,7 @@ static int rayshade(orc_scene* s, RAY* r, int mod) {
         switch (t) {
         case T_PLASTIC: case T_METAL: if (m->nfargs != 5) { fail(s, "bad arguments for", m->name); return 1; } return m_normal(s, t, m->fargs, r, flat);
         case T_TRANS: if (m->nfargs != 7) { fail(s, "bad arguments for", m->name); return 1; } return m_normal(s, t, m->fargs, r, flat);
+        case T_PLASTIC2: case T_METAL2: case T_TRANS2: return m_aniso(s, m, r, flat);
         case T_GLASS: return m_glass(s, m, r);
         case T_GLOW: case T_LIGHT: case T_ILLUM: case T_SPOT: return m_light(s, m, r);
         default: fail(s, "unsupported modifier reached by the oracle:", m->name); return 1;

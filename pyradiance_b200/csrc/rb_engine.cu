@@ -57,7 +57,11 @@ __device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws) {
 // Trace: octree walk + intersection only (small code).  Persistent threads:
 // the grid is sized to fill the machine once and every warp pulls rays from
 // the queue until it is empty (rb_geom.cuh walk_rays).
+#ifdef RB_TRACE_MAXNREG        // developer knob: cap the registers directly (CTA sizes whose warps do not divide evenly)
+__global__ void __maxnreg__(RB_TRACE_MAXNREG) k_trace(const WaveArgs A) {
+#else
 __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const WaveArgs A) {
+#endif
     __shared__ WalkSmem<WAVE_THREADS> sm;
     extern __shared__ int stk_dyn[];         // [maxdepth + 1][WAVE_THREADS]
     TraceIO io;
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const Wave
 #ifndef RB_SHADE_THREADS
 #define RB_SHADE_THREADS 128
 #endif
-__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(const WaveArgs A) {
+__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(const __grid_constant__ WaveArgs A) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < A.nin) {
         const QRay q = A.qin[i];
@@ -189,7 +193,7 @@ struct DirectArgs {
     unsigned nd;
 };
 
-__global__ void __launch_bounds__(256) k_direct(const WaveArgs A, const DirectArgs D) {
+__global__ void __launch_bounds__(256) k_direct(const __grid_constant__ WaveArgs A, const DirectArgs D) {
     __shared__ DirectJob sj;
     const int ns = A.S.nsrcs;
     for (unsigned job = blockIdx.x; job < D.nd; job += gridDim.x) {
@@ -378,6 +382,7 @@ bool Engine::size_trace_grid(std::string& err) {
     CK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev_));
     if (const char* e = getenv("RB_TRACE_CTAS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));   // developer knob
     trace_blocks_ = std::max(1, per_sm) * std::max(1, nsm);
+    if (getenv("RB_DEBUG_GRID")) fprintf(stderr, "[rb] k_trace: %d CTAs/SM x %d threads, %zu B dynamic smem\n", per_sm, WAVE_THREADS, trace_smem_);
     return true;
 }
 

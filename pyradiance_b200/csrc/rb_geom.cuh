@@ -63,6 +63,9 @@ namespace rb {
 #ifndef RB_SLOW_MIN
 #define RB_SLOW_MIN 0            // lanes in curved-surface leaves that gather before their round runs (0: off; measured slower)
 #endif
+#ifndef RB_STEP_RCP
+#define RB_STEP_RCP 0            // 1: the step to the next cube multiplies by 1/dir (kept per ray) instead of dividing
+#endif
 #ifndef RB_PAIR_ILP
 #define RB_PAIR_ILP 1            // (ray, surface) pairs a lane has in flight in the pair loop
 #endif
@@ -304,6 +307,9 @@ struct TraceIO {
 template <int NT>
 struct WalkSmem {
     double ray[6][NT];           // staged ray: origin, direction
+#if RB_STEP_RCP
+    double inv[3][NT];           // 1 / direction (1 where the ray does not move along the axis)
+#endif
     double pos[3][NT];           // current position along the ray (raymove's pos)
     double rot[NT];              // current best distance
     unsigned cell[3][NT];        // integer coordinates of the current cube at its level
@@ -451,6 +457,10 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 const double rmax = d.x;
                 sm.ray[0][tid] = org[0]; sm.ray[1][tid] = org[1]; sm.ray[2][tid] = org[2];
                 sm.ray[3][tid] = dir[0]; sm.ray[4][tid] = dir[1]; sm.ray[5][tid] = dir[2];
+#if RB_STEP_RCP
+#pragma unroll
+                for (int i = 0; i < 3; i++) sm.inv[i][tid] = (fabs(dir[i]) > 1e-7) ? 1.0 / dir[i] : 1.0;
+#endif
                 sm.ridx[tid] = my;
                 // ---- localhit() prologue (raytrace.c:604-651) ----
                 int dirf = 0;
@@ -697,7 +707,19 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                     }
                 }
                 // advance to next cube (raytrace.c:712-738)
-#if RB_STEP_BRANCHLESS
+#if RB_STEP_RCP
+                // raymove() walks the ray with t = (plane - pos) / dir; here the quotient is a product with the
+                // ray's reciprocal direction.  pos may differ from the reference's in the last bit, which only
+                // decides the cube when pos already sits within an ulp of a cube face; hit distances do not
+                // come from pos (they are computed from the ray's origin), so results stay what they were.
+                const double tx = (((dirf & 1) ? hix : lox) - pos[0]) * sm.inv[0][tid];
+                const double ty = (((dirf & 2) ? hiy : loy) - pos[1]) * sm.inv[1][tid];
+                const double tz = (((dirf & 4) ? hiz : loz) - pos[2]) * sm.inv[2][tid];
+                int ax = 0;
+                double t = (dirf & 0x11) ? tx : RB_FHUGE;
+                if ((dirf & 0x22) && ty < t) { t = ty; ax = 1; }
+                if ((dirf & 0x44) && tz < t) { t = tz; ax = 2; }
+#elif RB_STEP_BRANCHLESS
                 // the three plane distances are independent: computed unconditionally (with a harmless
                 // denominator on an axis the ray does not move along) so their division sequences interleave
                 const double tx = (((dirf & 1) ? hix : lox) - pos[0]) / ((dirf & 0x11) ? dir[0] : 1.0);

@@ -32,7 +32,7 @@ static const TypeInfo kTypes[] = {
     {"mist", OT_MIST}, {"aBSDF", OT_ABSDF}, {"trans2", OT_TRANS2},
     {"antimatter", OT_ANTIMATTER},
     // other materials (src/radiance/common/otypes.h:127-186, T_M entries)
-    {"plastic2", OT_OTHER_MATERIAL}, {"metal2", OT_OTHER_MATERIAL},
+    {"plastic2", OT_PLASTIC2}, {"metal2", OT_METAL2},
     {"plasfunc", OT_OTHER_MATERIAL}, {"metfunc", OT_OTHER_MATERIAL},
     {"mirror", OT_OTHER_MATERIAL}, {"transfunc", OT_OTHER_MATERIAL},
     {"BRTDfunc", OT_OTHER_MATERIAL}, {"BSDF", OT_OTHER_MATERIAL},
@@ -69,7 +69,7 @@ bool ot_is_material(int t) {
     case OT_PLASTIC: case OT_METAL: case OT_GLASS: case OT_TRANS: case OT_GLOW:
     case OT_LIGHT: case OT_ILLUM: case OT_SPOTLIGHT: case OT_DIELECTRIC:
     case OT_INTERFACE: case OT_MIST: case OT_ABSDF: case OT_TRANS2:
-    case OT_ANTIMATTER: case OT_OTHER_MATERIAL:
+    case OT_ANTIMATTER: case OT_OTHER_MATERIAL: case OT_PLASTIC2: case OT_METAL2:
         return true;
     }
     return false;
@@ -1049,6 +1049,39 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
                 r.kind = MK_UNSUPPORTED; note_unsupported("bad arguments for glass \"" + m.name + "\"");
             }
             break;
+        case OT_PLASTIC2: case OT_METAL2: case OT_TRANS2: {
+            // aniso.c:185-326.  The orientation vector's three expressions must be numeric constants (they
+            // usually are); the function file's transform is applied here (getacoords(), multv3 by fxp->xfm).
+            r.kind = m.otype == OT_PLASTIC2 ? MK_PLASTIC2 : m.otype == OT_METAL2 ? MK_METAL2 : MK_TRANS2;
+            if (!need(m.otype == OT_TRANS2 ? 8 : 6)) break;
+            if (m.sargs.size() < 4) {
+                r.kind = MK_UNSUPPORTED; note_unsupported("bad arguments for " + m.tname + " \"" + m.name + "\"");
+                break;
+            }
+            if (!(m.fargs[4] > 1e-6) || !(m.fargs[5] > 1e-6)) {
+                r.kind = MK_UNSUPPORTED; note_unsupported("roughness too small for " + m.tname + " \"" + m.name + "\"");
+                break;
+            }
+            double u[3];
+            bool konst = true;
+            for (int k = 0; k < 3; k++) {
+                const char* b = m.sargs[k].c_str(); char* e = nullptr;
+                u[k] = strtod(b, &e);
+                if (e == b || *e) konst = false;
+            }
+            if (!konst) {
+                r.kind = MK_UNSUPPORTED;
+                note_unsupported("orientation vector of " + m.tname + " \"" + m.name + "\" is not a numeric constant (.cal expressions are not built)");
+                break;
+            }
+            Xf x; std::string xe;
+            if (!parse_xf(m.sargs, 4, x, xe)) {
+                r.kind = MK_UNSUPPORTED; note_unsupported(xe + " for " + m.tname + " \"" + m.name + "\"");
+                break;
+            }
+            for (int k = 0; k < 3; k++) r.u[k] = u[0] * x.m[0][k] + u[1] * x.m[1][k] + u[2] * x.m[2][k];   // multv3
+            break;
+        }
         case OT_LIGHT: r.kind = MK_LIGHT; need(3); break;
         case OT_GLOW:  r.kind = MK_GLOW; need(4); break;
         case OT_ILLUM: r.kind = MK_ILLUM; need(3); break;

@@ -30,6 +30,7 @@ enum OType : int {
     // known but unsupported material / pattern families (for messages + flags)
     OT_DIELECTRIC, OT_INTERFACE, OT_MIST, OT_ABSDF, OT_TRANS2, OT_ANTIMATTER,
     OT_OTHER_MATERIAL, OT_PATTERN, OT_TEXTURE, OT_MIXTURE,
+    OT_PLASTIC2, OT_METAL2,      // anisotropic (rt/aniso.c), with OT_TRANS2 above
     OT_NTYPES
 };
 
@@ -99,10 +100,10 @@ enum : int {            // device primitive kinds (x & 0xff)
 // material kinds on device
 enum : int {
     MK_NONE = 0, MK_PLASTIC, MK_METAL, MK_TRANS, MK_GLASS, MK_LIGHT, MK_GLOW,
-    MK_ILLUM, MK_SPOT, MK_UNSUPPORTED
+    MK_ILLUM, MK_SPOT, MK_UNSUPPORTED, MK_PLASTIC2, MK_METAL2, MK_TRANS2
 };
 
-struct MatRec {          // 64 bytes
+struct MatRec {          // 96 bytes
     int kind;
     int flags;           // bit0: chain has unsupported pattern/texture
     int obj;             // object index of the material
@@ -111,7 +112,10 @@ struct MatRec {          // 64 bytes
     int alt;             // illum: alternate material slot (-1 = void/none)
     int pat;             // first pattern record under the material (-1 = none)
     int pad[2];
+    double u[3];         // plastic2 / metal2 / trans2: orientation vector, function transform applied (aniso.c:305-313)
+    double pad2;
 };
+static_assert(sizeof(MatRec) == 96, "MatRec must be 96 bytes");
 
 // A pattern under a material that is built as native code: brightfunc with
 // gen/skybright.cal `skybr` (gensky) or gen/perezlum.cal `skybright` (gendaylight).

@@ -298,13 +298,66 @@ struct NormDat {           // normal.c:53-67 NORMDAT
     double prdir[3];
     double alpha2, rdiff, rspec, trans, tdiff, tspec;
     double pnorm[3], pdot;
+    // plastic2 / metal2 / trans2 only (aniso.c:46-62 ANISODAT), valid when specfl & SP_ANISO
+    double u[3], v[3], u_alpha, v_alpha;
 };
 struct DirectJob { RayCtx r; NormDat nd; };
-enum : int { SP_REFL = 01, SP_TRAN = 02, SP_PURE = 04, SP_FLAT = 010, SP_RBLT = 020, SP_TBLT = 040 };
+enum : int { SP_REFL = 01, SP_TRAN = 02, SP_PURE = 04, SP_FLAT = 010, SP_RBLT = 020, SP_TBLT = 040, SP_ANISO = 0100 };
+
+// aniso.c:64-182 diraniso(): source coefficient of the anisotropic Gaussian (Ward / Geisler-Moroder-Duer)
+__device__ __forceinline__ void diraniso(float scval[3], const NormDat& np, const RayCtx& r, const double ldir[3],
+                                         double omega, double dstrsrc) {
+    scval[0] = scval[1] = scval[2] = 0.f;
+    const double ldot = dot3(np.pnorm, ldir);
+    if (ldot < 0.0 ? np.trans <= RB_FTINY : np.trans >= 1.0 - RB_FTINY) return;      // wrong side
+    if ((ldot > RB_FTINY) & (np.rdiff > RB_FTINY)) {
+        const double w = ldot * omega * np.rdiff * (1.0 / RB_PI);
+        for (int k = 0; k < 3; k++) scval[k] += (float)(np.mcolor[k] * w);
+    }
+    if ((ldot < -RB_FTINY) & (np.tdiff > RB_FTINY)) {
+        const double w = -ldot * omega * np.tdiff * (1.0 / RB_PI);
+        for (int k = 0; k < 3; k++) scval[k] += (float)(np.mcolor[k] * w);
+    }
+    const double ua2 = np.u_alpha * np.u_alpha, va2 = np.v_alpha * np.v_alpha;
+    if ((ldot > RB_FTINY) && (np.specfl & SP_REFL)) {
+        double au2 = (np.specfl & SP_FLAT) ? (1. - dstrsrc) * omega * (0.25 / RB_PI) : 0.0;   // source width if flat
+        double av2 = au2;
+        au2 += ua2; av2 += va2;
+        const double h[3] = {ldir[0] - r.dir[0], ldir[1] - r.dir[1], ldir[2] - r.dir[2]};     // half vector
+        double e1 = dot3(np.u, h); e1 *= e1 / au2;
+        double e2 = dot3(np.v, h); e2 *= e2 / av2;
+        double nh = dot3(np.pnorm, h); nh *= nh;
+        e1 = (e1 + e2) / nh;
+        double w = exp(-e1) * dot3(h, h) / (RB_PI * nh * nh * sqrt(au2 * av2));
+        if (w > RB_FTINY) {
+            w *= ldot * omega;
+            for (int k = 0; k < 3; k++) scval[k] += (float)(np.scolor[k] * w);
+        }
+    }
+    if ((ldot < -RB_FTINY) && (np.specfl & SP_TRAN)) {
+        double au2 = omega * (1.0 / RB_PI), av2 = au2;
+        au2 += ua2; av2 += va2;
+        const double h[3] = {ldir[0] - np.prdir[0], ldir[1] - np.prdir[1], ldir[2] - np.prdir[2]};
+        double w = dot3(h, h);
+        if (w > RB_FTINY * RB_FTINY) { const double e = dot3(h, np.pnorm); w = 1.0 - e * e / w; }
+        if (w > RB_FTINY * RB_FTINY) {
+            double e1 = dot3(h, np.u); e1 *= e1 / au2;
+            double e2 = dot3(h, np.v); e2 *= e2 / av2;
+            w = exp(-((e1 + e2) / w));
+        } else
+            w = 1.0;
+        w *= (1.0 / RB_PI) * sqrt(-ldot / (np.pdot * au2 * av2));
+        if (w > RB_FTINY) {
+            w *= np.tspec * omega;
+            for (int k = 0; k < 3; k++) scval[k] += (float)(np.mcolor[k] * w);
+        }
+    }
+}
 
 // normal.c:71-173
 __device__ __forceinline__ void dirnorm(float scval[3], const NormDat& np, const RayCtx& r, const double ldir[3],
                         double omega, double dstrsrc) {
+    if (np.specfl & SP_ANISO) { diraniso(scval, np, r, ldir, omega, dstrsrc); return; }
     scval[0] = scval[1] = scval[2] = 0.f;
     double ldot = dot3(np.pnorm, ldir);
     if (ldot < 0.0 ? np.trans <= RB_FTINY : np.trans >= 1.0 - RB_FTINY) return;
@@ -861,6 +914,132 @@ __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind
     direct_or_park(A, r, nd);
 }
 
+// fvect.c:159-196 getperpendicular() with randomize = 0
+__device__ __forceinline__ bool getperpendicular0(double vp[3], const double v[3]) {
+    int i;
+    for (i = 3; i--;)
+        if ((-0.6 < v[i]) & (v[i] < 0.6)) break;
+    if (i < 0) return false;
+    const double v1[3] = {i == 0 ? 1.0 : 0.0, i == 1 ? 1.0 : 0.0, i == 2 ? 1.0 : 0.0};
+    vp[0] = v1[1] * v[2] - v1[2] * v[1];
+    vp[1] = v1[2] * v[0] - v1[0] * v[2];
+    vp[2] = v1[0] * v[1] - v1[1] * v[0];
+    return normalize3(vp) > 0.0;
+}
+
+// aniso.c:185-297 m_aniso(), :299-326 getacoords(), :329-470 agaussamp() in its single-sample form (-ss <= 1.5).
+// a[] = material reals (6, or 8 for trans2), uvec = orientation vector with the function transform applied by the
+// loader.  Out of line: these materials are rare, and the isotropic path's code stays what it was.
+__device__ __noinline__ void m_aniso(const WaveArgs& A, RayCtx& r, int mkind, const float* a, const double* uvec) {
+    const DParams& P = A.P;
+    if (r.crtype & RT_SHADOW) return;                    // easy shadow test (trans2 included)
+    bool flipped = false;
+    if (r.rod < 0.0) {
+        if (!P.backvis) { raytrans(A, r); return; }
+        r.rod = -r.rod; r.ron[0] = -r.ron[0]; r.ron[1] = -r.ron[1]; r.ron[2] = -r.ron[2];   // flipsurface
+        flipped = true;
+    }
+    NormDat nd;
+    nd.specfl = SP_ANISO;
+    nd.alpha2 = 0.0;
+    for (int k = 0; k < 3; k++) { nd.mcolor[k] = a[k]; nd.scolor[k] = 0.f; nd.pnorm[k] = r.ron[k]; nd.prdir[k] = r.dir[k]; nd.u[k] = uvec[k]; }
+    nd.u_alpha = a[4]; nd.v_alpha = a[5];
+    nd.pdot = r.rod;
+    double pert[3];
+    const bool hastexture = ray_pert(A.S, r, flipped, pert);
+    if (hastexture) nd.pdot = raynormal(nd.pnorm, r, pert);
+    if (nd.pdot < .001) nd.pdot = .001;
+    if ((nd.rspec = a[3]) > RB_FTINY) {
+        nd.specfl |= SP_REFL;
+        for (int k = 0; k < 3; k++) nd.scolor[k] = (float)((mkind == MK_METAL2 ? nd.mcolor[k] : 1.f) * nd.rspec);
+        if (P.specthresh >= nd.rspec - RB_FTINY) nd.specfl |= SP_RBLT;
+    }
+    if (mkind == MK_TRANS2) {
+        nd.trans = a[6] * (1.0 - nd.rspec);
+        nd.tspec = nd.trans * a[7];
+        nd.tdiff = nd.trans - nd.tspec;
+        if (nd.tspec > RB_FTINY) {
+            nd.specfl |= SP_TRAN;
+            if (P.specthresh >= nd.tspec - RB_FTINY) nd.specfl |= SP_TBLT;
+            if (hastexture && !(r.xfl & 2)) {            // aniso.c:241-252: bent transmission, not under "Phong"
+                double pd[3] = {r.dir[0] - pert[0], r.dir[1] - pert[1], r.dir[2] - pert[2]};
+                if (dot3(pd, r.ron) < -RB_FTINY) {
+                    normalize3(pd);
+                    nd.prdir[0] = pd[0]; nd.prdir[1] = pd[1]; nd.prdir[2] = pd[2];
+                }
+            }
+        }
+    } else
+        nd.tdiff = nd.tspec = nd.trans = 0.0;
+    nd.rdiff = 1.0 - nd.trans - nd.rspec;
+    if (!hastexture && r.robj >= 0 && r.flat) nd.specfl |= SP_FLAT;
+    // getacoords(): v = n x u, u = v x n; an orientation along the normal falls back to an isotropic lobe
+    nd.v[0] = nd.pnorm[1] * nd.u[2] - nd.pnorm[2] * nd.u[1];
+    nd.v[1] = nd.pnorm[2] * nd.u[0] - nd.pnorm[0] * nd.u[2];
+    nd.v[2] = nd.pnorm[0] * nd.u[1] - nd.pnorm[1] * nd.u[0];
+    if (normalize3(nd.v) == 0.0) {
+        getperpendicular0(nd.u, nd.pnorm);
+        nd.v[0] = nd.pnorm[1] * nd.u[2] - nd.pnorm[2] * nd.u[1];
+        nd.v[1] = nd.pnorm[2] * nd.u[0] - nd.pnorm[0] * nd.u[2];
+        nd.v[2] = nd.pnorm[0] * nd.u[1] - nd.pnorm[1] * nd.u[0];
+        nd.u_alpha = nd.v_alpha = sqrt(0.5 * (nd.u_alpha * nd.u_alpha + nd.v_alpha * nd.v_alpha));
+    } else {
+        const double ux = nd.v[1] * nd.pnorm[2] - nd.v[2] * nd.pnorm[1];
+        const double uy = nd.v[2] * nd.pnorm[0] - nd.v[0] * nd.pnorm[2];
+        const double uz = nd.v[0] * nd.pnorm[1] - nd.v[1] * nd.pnorm[0];
+        nd.u[0] = ux; nd.u[1] = uy; nd.u[2] = uz;
+    }
+    if (nd.specfl & (SP_REFL | SP_TRAN)) {
+        const unsigned long long gkey = child_key(r.key, r.nchild++);
+        const double ua2 = nd.u_alpha * nd.u_alpha, va2 = nd.v_alpha * nd.v_alpha;
+        for (int side = 0; side < 2; side++) {           // 0: reflected lobe, 1: transmitted lobe
+            if (side == 0 ? (nd.specfl & (SP_REFL | SP_RBLT)) != SP_REFL : (nd.specfl & (SP_TRAN | SP_TBLT)) != SP_TRAN) continue;
+            float rc[3];
+            for (int k = 0; k < 3; k++) rc[k] = side == 0 ? nd.scolor[k] : (float)(nd.mcolor[k] * nd.tspec);
+            QRay q;
+            if (!rayorigin(P, r, side == 0 ? RT_RSPECULAR : RT_TSPECULAR, rc, true, q)) continue;
+            for (int ntr = 0; ntr < 10; ntr++) {
+                const unsigned dim = (side == 0 ? 30 : 60) + 2 * ntr;
+                double rv1 = rnd01(gkey, dim + 1);
+                double sinp, cosp;
+                sincos(2.0 * RB_PI * rnd01(gkey, dim), &sinp, &cosp);
+                cosp *= nd.u_alpha; sinp *= nd.v_alpha;
+                double d = 1. / sqrt(cosp * cosp + sinp * sinp);
+                cosp *= d; sinp *= d;
+                if ((0. <= P.specjitter) & (P.specjitter < 1.)) rv1 = 1.0 - P.specjitter * rv1;
+                d = (rv1 <= RB_FTINY) ? 1.0 : sqrt(-log(rv1) / (cosp * cosp / ua2 + sinp * sinp / va2));
+                if (side == 0) {
+                    double h[3];
+                    for (int k = 0; k < 3; k++) h[k] = nd.pnorm[k] + d * (cosp * nd.u[k] + sinp * nd.v[k]);
+                    d = -2.0 * dot3(h, r.dir) / (1.0 + d * d);
+                    for (int k = 0; k < 3; k++) q.dir[k] = r.dir[k] + h[k] * d;
+                    if (dot3(q.dir, r.ron) <= RB_FTINY) continue;      // sample rejection test
+                } else {
+                    for (int k = 0; k < 3; k++) q.dir[k] = nd.prdir[k] + d * (cosp * nd.u[k] + sinp * nd.v[k]);
+                    if (dot3(q.dir, r.ron) >= -RB_FTINY) continue;
+                }
+                normalize3(q.dir);
+                push_ray(A, q);
+                break;
+            }
+        }
+    }
+    if (nd.rdiff > RB_FTINY) {
+        float sct[3];
+        for (int k = 0; k < 3; k++) sct[k] = (float)(nd.mcolor[k] * nd.rdiff);
+        if (nd.specfl & SP_RBLT) for (int k = 0; k < 3; k++) sct[k] += nd.scolor[k];
+        multambient(A, r, sct, nd.pnorm);
+    }
+    if (nd.tdiff > RB_FTINY) {
+        float sct[3];
+        const double f = (nd.specfl & SP_TBLT) ? nd.trans : nd.tdiff;
+        for (int k = 0; k < 3; k++) sct[k] = (float)(nd.mcolor[k] * f);
+        const double bn[3] = {-nd.pnorm[0], -nd.pnorm[1], -nd.pnorm[2]};
+        multambient(A, r, sct, bn);
+    }
+    direct_or_park(A, r, nd);
+}
+
 // glass.c:46-165
 __device__ __forceinline__ void m_glass(const WaveArgs& A, RayCtx& r, const float* a, int nargs) {
     const DParams& P = A.P;
@@ -1025,11 +1204,12 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
             return;
         }
         if (tst_irrad) {                // raytirrad(), raytrace.c:210-228
-            if (k == MK_TRANS || k == MK_GLASS) { raytrans(A, r); break; }
+            if (k == MK_TRANS || k == MK_GLASS || k == MK_TRANS2) { raytrans(A, r); break; }
             if (!(k >= MK_LIGHT && k <= MK_SPOT)) { nk = MK_PLASTIC; for (int j = 0; j < 7; j++) na[j] = j < 3 ? (float)RB_PI : 0.f; break; }
         }
         if (k == MK_PLASTIC || k == MK_METAL || k == MK_TRANS) { nk = k; for (int j = 0; j < 7; j++) na[j] = m->a[j]; break; }
         if (k == MK_GLASS) { m_glass(A, r, m->a, m->nargs); break; }
+        if (k >= MK_PLASTIC2 && k <= MK_TRANS2) { m_aniso(A, r, k, m->a, m->u); break; }
         int rv = m_light(A, r, *m, rcol, zeroed);
         if (rv == 1) {
             have_rcol = true;

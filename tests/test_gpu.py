@@ -333,6 +333,16 @@ def test_explicit_rejections(workdir, golden):
     with pytest.raises(_lib.RBError, match="unsupported material.*dielectric"):
         ctx.rtrace(np.array([[2, 2, 0, 0, 0, 1.0]]))
     ctx.rtrace(np.array([[9, 9, 0, 0, 0, 1.0]]))              # a ray that never meets it is fine
+    rad6 = workdir / "brushed.rad"                            # plastic2 orientation given as a .cal expression
+    rad6.write_text(scenegen.MATERIALS + scenegen.SKY + "void plastic2 brushed\n4 Ny -Nx 0 .\n0\n6 .5 .5 .5 .1 .1 .3\n\n"
+                    "brushed polygon plate\n0\n0\n12 0 0 1  4 0 1  4 4 1  0 4 1\n\n")
+    oct6 = workdir / "brushed.oct"
+    scenegen.build_octree(rad6, oct6)
+    ctx6 = _lib.Context(0)
+    ctx6.load_octree(oct6)
+    ctx6.set_options(["-ab", "0"])
+    with pytest.raises(_lib.RBError, match="unsupported material.*plastic2"):
+        ctx6.rtrace(np.array([[2, 2, 3, 0, 0, -1.0]]))
     ctx2 = _lib.Context(0)
     ctx2.load_octree(golden / "trace.oct")
     ctx2.set_options(["-ab", "2"])                            # rtrace default -aa .1
@@ -829,3 +839,47 @@ def test_smooth_mesh_vertex_normals_vs_reference_golden(golden):
     for m in ("sm_plastic", "sm_metal", "sm_glass", "sm_trans", "Phong", "green"):
         k = (mod == m) & smooth
         assert k.sum() > 30 and (~bad[k]).mean() > 0.97, m
+
+
+def test_anisotropic_materials_vs_reference_golden(golden):
+    """plastic2 / metal2 / trans2 (rt/aniso.c: diraniso, getacoords, agaussamp)
+    on the device, against the unmodified reference (tests/golden/make_golden_aniso.py).
+    (1) deterministic (-st 1 -dj 0): surface, modifier, distance and value of 2400 view rays
+    from above and below the panels, with and without a function transform on the
+    orientation vector, and -I values through the trans2 panels: 1e-5 relative;
+    (2) highlights sampled (-st 0): per-ray means over 1500 repetitions within 5 combined
+    standard errors of the reference's; (3) rcontrib -ab 1 coefficients per tracked emitter:
+    means over 200 repetitions within 5 combined standard errors + 2 %."""
+    g = np.load(golden / "aniso.npz")
+    rays = g["rays"]
+    for tag, octf in (("", "aniso.oct"), ("xf_", "anisoxf.oct")):
+        out = pr.rtrace(rays.tobytes(), str(golden / "aniso" / octf), header=False, inform="d", outform="a",
+                        outspec="vLsm", params=[str(a) for a in g["args"]]).decode()
+        rows = [ln.split("\t") for ln in out.splitlines()]
+        assert len(rows) == len(rays)
+        assert [r[4] for r in rows] == list(g[tag + "surf"]) and [r[5] for r in rows] == list(g[tag + "mod"])
+        np.testing.assert_allclose([float(r[3]) for r in rows], g[tag + "dist"], rtol=2e-6)
+        val = np.array([[float(x) for x in r[0:3]] for r in rows])
+        np.testing.assert_allclose(val, g[tag + "value"], rtol=1e-5, atol=1e-9)
+    assert np.abs(g["xf_value"] - g["value"]).max() > 1e-2       # the transform does change the highlights
+    ctx = _lib.Context(0)
+    ctx.load_octree(golden / "aniso" / "aniso.oct")
+    ctx.set_options([str(a) for a in g["args"]])
+    v, _ = ctx.rtrace(g["sensors"], flags=_lib.RB_IRRAD_RTRACE)
+    np.testing.assert_allclose(v, g["irrad"], rtol=1e-5, atol=1e-9)
+    # (2) sampled highlights
+    pick, reps = g["st_pick"], 1500
+    ctx.set_options([str(a) for a in g["st_args"]])
+    v, _ = ctx.rtrace(np.tile(rays[pick], (reps, 1)))
+    v = v.reshape(reps, len(pick), 3)
+    sem = np.sqrt(v.var(0, ddof=1) / reps + g["st_sem"] ** 2)
+    assert (np.abs(v.mean(0) - g["st_mean"]) <= 5 * sem + 1e-5 * g["st_mean"]).all()
+    # (3) coefficients per emitter through one diffuse bounce
+    rc = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+    rc.load_octree(golden / "aniso" / "aniso.oct")
+    rc.set_options([str(a) for a in g["rc_args"]])
+    for m in ("skyg", "lampl", "lowl"):
+        rc.add_modifier(m, "", "0", 1)
+    m = rc.rcontrib(np.tile(rays[pick[:60]], (200, 1)), dtype=np.float64).reshape(200, 60, 3, 3)
+    sem = np.sqrt(m.var(0, ddof=1) / 200 + g["rc_sem"] ** 2)
+    assert (np.abs(m.mean(0) - g["rc_mean"]) <= 5 * sem + 0.02 * g["rc_mean"] + 1e-9).all()
