@@ -63,6 +63,9 @@ namespace rb {
 #ifndef RB_SLOW_MIN
 #define RB_SLOW_MIN 0            // lanes in curved-surface leaves that gather before their round runs (0: off; measured slower)
 #endif
+#ifndef RB_PREFETCH
+#define RB_PREFETCH 0            // bit 0: prefetch the next leaf's set entries at the end of the step; bit 1: the next node's words
+#endif
 #ifndef RB_STEP_RCP
 #define RB_STEP_RCP 0            // 1: the step to the next cube multiplies by 1/dir (kept per ray) instead of dividing
 #endif
@@ -514,6 +517,16 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
         }
         __syncwarp();
         bool act = (fl & (WF_HAVE | WF_DONE)) == WF_HAVE;
+#if RB_PREFETCH & 4
+        // second level: the set entries asked for at the end of the last step name the records the pair
+        // loop will read; ask for those too (the entries themselves are L1 hits by now)
+        if (act && w < -1) {
+            const unsigned u = (unsigned)(-w - 2);
+            const int so = (int)(u >> 4), k = min((int)(u & 7), 6);
+            for (int j = 1; j <= k; j++)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(S.geom + __ldg(&pool[so + j]).y));
+        }
+#endif
         // ---- phase A: descend towards a leaf (raymove, raytrace.c:668-687); at most
         //      RB_DITERS levels per round ----
         {
@@ -764,6 +777,16 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 if ((w != -1) | (cstep + 1 >= RB_CSTEPS)) break;
                 fullc = false;
             }
+#if RB_PREFETCH
+            // the word just read names what the next round will read first: say so now, a round's worth of
+            // work ahead of the dependent load
+            if (!done) {
+                if ((RB_PREFETCH & 1) && w < -1)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pool + ((unsigned)(-w - 2) >> 4)));
+                if ((RB_PREFETCH & 2) && w >= 0)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(S.nodes + (size_t)w * 8));
+            }
+#endif
             px = pos[0]; py = pos[1]; pz = pos[2];
             sm.pos[0][tid] = px; sm.pos[1][tid] = py; sm.pos[2][tid] = pz;
             Ld = (Ld & ~0xff) | L;

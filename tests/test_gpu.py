@@ -123,7 +123,7 @@ def test_bins_on_device(G, golden, name):
     assert np.array_equal(m[:, :, 0].argmax(axis=1), np.array(G[name]["bins"]))
 
 
-@pytest.mark.parametrize("fixture,nrays", [("office2k", 100_000), ("office100k", 300_000)])
+@pytest.mark.parametrize("fixture,nrays", [("office2k", 100_000), ("office100k", 1_000_000)])
 def test_hits_bit_exact_vs_oracle(fixture, nrays, request):
     octf = request.getfixturevalue(fixture)
     rays = scenegen.random_rays(nrays, seed=21)
