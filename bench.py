@@ -274,7 +274,7 @@ def run_ours(args):
         achieved = bpr * rays_per_launch / launch_s / 1e9
         traffic = None
         try:
-            prof = json.load(open(ROOT / "profiles" / "r2_k_trace_dram.json"))
+            prof = json.load(open(ROOT / "profiles" / "r3_k_trace_dram.json"))
             # one ncu --set full capture: dram bytes of a k_trace launch / rays in that launch, scaled to
             # the mean launch of this run
             traffic = prof["dram_bytes_per_launch"] / prof["rays_in_launch"] * rays_per_launch

@@ -20,6 +20,8 @@
  *   rayorigin/rayclear/raytrace/raycont/raytrans/rayshade/raycontrib   rt/raytrace.c:39-442
  *   marksources/ssetsrc/sourcehit/direct/srcray/nextssamp   rt/source.c, rt/srcsupp.c:155-179, rt/srcsamp.c:36-144
  *   m_light, m_normal+dirnorm+gaussamp, m_glass   rt/source.c:749-793, rt/normal.c, rt/glass.c
+ *   m_aniso+diraniso+getacoords+agaussamp (plastic2/metal2/trans2)   rt/aniso.c
+ *   m_dielectric (dielectric/interface, no DISPERSE), rayparticipate (albedo 0)   rt/dielectric.c, rt/raytrace.c:259-295
  *   multambient(aa=0)/doambient/samp_hemi/ambsample   rt/ambient.c:229-297, rt/ambcomp.c:177-248,350-422
  *   trace_contrib, eval_irrad     rt/rcontrib.c:272-339
  *   rbin/kbin bin functions       util/reinhartb.cal, cal/cal/reinhart.cal, util/klems_*.cal
@@ -53,7 +55,7 @@ enum { PRIMARY = 01, RSHADOW = 02, REFLECTED = 04, REFRACTED = 010, TRANS = 020,
 
 enum { T_OTHER = 0, T_POLYGON, T_CONE, T_SPHERE, T_RING, T_CYLINDER, T_CUP, T_BUBBLE, T_TUBE, T_SOURCE, T_INSTANCE,
        T_MESH, T_ALIAS, T_PLASTIC, T_METAL, T_GLASS, T_TRANS, T_GLOW, T_LIGHT, T_ILLUM, T_SPOT, T_TRANSP_MAT,
-       T_OTHER_MAT, T_PATTERN, T_BRIGHTFUNC, T_PLASTIC2, T_METAL2, T_TRANS2 };
+       T_OTHER_MAT, T_PATTERN, T_BRIGHTFUNC, T_PLASTIC2, T_METAL2, T_TRANS2, T_DIELECTRIC, T_INTERFACE };
 
 typedef struct {
     int omod, otype;
@@ -96,6 +98,7 @@ typedef struct ray {
     int ro, robj, rsrc, rlvl, rtype, crtype, aft, rflips;
     double rweight;
     float rcoef[3], rcol[3];
+    float cext[3];            /* extinction coefficient of the medium the ray travels in (ray.h cext) */
     int rdepth;               /* ambient recursion depth (static rdepth in ambient.c:236) */
 } RAY;
 
@@ -151,7 +154,7 @@ static int type_of(const char* n) {
         {"cup", T_CUP}, {"bubble", T_BUBBLE}, {"tube", T_TUBE}, {"source", T_SOURCE}, {"instance", T_INSTANCE},
         {"mesh", T_MESH}, {"alias", T_ALIAS}, {"plastic", T_PLASTIC}, {"metal", T_METAL}, {"glass", T_GLASS},
         {"trans", T_TRANS}, {"glow", T_GLOW}, {"light", T_LIGHT}, {"illum", T_ILLUM}, {"spotlight", T_SPOT},
-        {"dielectric", T_TRANSP_MAT}, {"interface", T_TRANSP_MAT}, {"mist", T_TRANSP_MAT}, {"trans2", T_TRANS2},
+        {"dielectric", T_DIELECTRIC}, {"interface", T_INTERFACE}, {"mist", T_TRANSP_MAT}, {"trans2", T_TRANS2},
         {"aBSDF", T_TRANSP_MAT}, {"plastic2", T_PLASTIC2}, {"metal2", T_METAL2}, {"plasfunc", T_OTHER_MAT},
         {"metfunc", T_OTHER_MAT}, {"mirror", T_OTHER_MAT}, {"transfunc", T_OTHER_MAT}, {"BRTDfunc", T_OTHER_MAT},
         {"BSDF", T_OTHER_MAT}, {"WGMDfunc", T_OTHER_MAT}, {"plasdata", T_OTHER_MAT}, {"metdata", T_OTHER_MAT},
@@ -162,10 +165,10 @@ static int type_of(const char* n) {
     return T_PATTERN;     /* patterns, textures, mixtures: anything else is a non-material modifier */
 }
 static int is_surface(int t) { return t >= T_POLYGON && t <= T_SOURCE; }
-static int is_material(int t) { return (t >= T_PLASTIC && t <= T_SPOT) || t == T_TRANSP_MAT || t == T_OTHER_MAT || (t >= T_PLASTIC2 && t <= T_TRANS2); }
+static int is_material(int t) { return (t >= T_PLASTIC && t <= T_SPOT) || t == T_TRANSP_MAT || t == T_OTHER_MAT || (t >= T_PLASTIC2 && t <= T_INTERFACE); }
 static int is_modifier(int t) { return !(t >= T_POLYGON && t <= T_MESH); }
 static int is_light(int t) { return t >= T_GLOW && t <= T_SPOT; }
-static int is_transp(int t) { return t == T_TRANS || t == T_GLASS || t == T_TRANSP_MAT || t == T_TRANS2; }
+static int is_transp(int t) { return t == T_TRANS || t == T_GLASS || t == T_TRANSP_MAT || t == T_TRANS2 || t == T_DIELECTRIC || t == T_INTERFACE; }
 
 static int lastmod(const orc_scene* s, int before, const char* name) {
     int i;
@@ -859,14 +862,21 @@ static int rayorigin(orc_scene* s, RAY* r, int rt, const RAY* ro, const float* r
     else { rw = max3f(rc); if (rw > 1.0) rw = 1.0; if (rc != r->rcoef) for (i = 0; i < 3; i++) r->rcoef[i] = rc[i]; }
     if ((r->parent = ro) == NULL) {
         r->rlvl = 0; r->rweight = rw; r->crtype = r->rtype = rt; r->rsrc = -1; r->rdepth = 0;
+        r->cext[0] = r->cext[1] = r->cext[2] = 0;      /* global -me is not built: air */
     } else {
         if (ro->rot >= FHUGE * .99) { memset(r, 0, sizeof(RAY)); return -1; }
         r->rlvl = ro->rlvl; r->rsrc = ro->rsrc; r->rdepth = ro->rdepth;
         if (rt & RAYREFL) { r->rlvl++; if (r->rsrc >= 0) r->rsrc = -1; r->rmax = 0.0; }
         else r->rmax = (ro->rmax > FTINY) * (ro->rmax - ro->rot);
         r->crtype = ro->crtype | (r->rtype = rt);
-        for (i = 0; i < 3; i++) r->rorg[i] = ro->rop[i];
+        for (i = 0; i < 3; i++) { r->rorg[i] = ro->rop[i]; r->cext[i] = ro->cext[i]; }
         r->rweight = (float)(ro->rweight * rw);
+        {   /* estimate extinction (raytrace.c:96-107): the weight, not the coefficient */
+            double re = ro->cext[0] < ro->cext[1] ? ro->cext[0] : ro->cext[1];
+            if (ro->cext[2] < re) re = ro->cext[2];
+            re *= ro->rot;
+            if (re > 0.1) r->rweight = re > 92. ? 0.f : (float)(r->rweight * exp(-re));
+        }
     }
     rayclear(r);
     if (r->rweight <= 0.0) return -1;
@@ -932,11 +942,20 @@ static void raytrans(orc_scene* s, RAY* r) {
     for (i = 0; i < 3; i++) r->rcol[i] = tr.rcol[i];
 }
 
+/* rayparticipate(), raytrace.c:259-295, for a non-scattering medium (albedo 0): path extinction */
+static void participate(RAY* r) {
+    int k;
+    if ((r->cext[0] > r->cext[1] ? (r->cext[0] > r->cext[2] ? r->cext[0] : r->cext[2])
+                                 : (r->cext[1] > r->cext[2] ? r->cext[1] : r->cext[2])) <= 1. / FHUGE) return;
+    for (k = 0; k < 3; k++) { double e = r->rot * r->cext[k]; r->rcol[k] *= (float)(e <= FTINY ? 1. : e > 92. ? 0. : exp(-e)); }
+}
+
 static void raytrace(orc_scene* s, RAY* r) {
     if (localhit(s, r)) { if (!rayshade(s, r, s->objs[r->ro].omod)) raytrans(s, r); }
     else if (r->aft) { r->ro = -1; r->rot = FHUGE; }
     else if (sourcehit(s, r)) rayshade(s, r, s->objs[r->ro].omod);
     trace_contrib(s, r);
+    participate(r);
 }
 static void rayvalue(orc_scene* s, RAY* r) { raytrace(s, r); }
 
@@ -1150,7 +1169,13 @@ static void direct(orc_scene* s, RAY* r, NORMDAT* nd) {
             if (!hit_obj(s, src->so, &pr)) continue;
             pr.rcol[0] = pr.rcol[1] = pr.rcol[2] = 0;
             if (!rayshade(s, &pr, s->objs[pr.ro].omod)) continue;
+            participate(&pr);
             if (!(pr.rcol[0] * coef[0] > 0 || pr.rcol[1] * coef[1] > 0 || pr.rcol[2] * coef[2] > 0)) continue;
+        } else {                                  /* srcvalue() of a distant source through an absorbing medium: nothing left */
+            RAY pr = sr0;
+            pr.rot = FHUGE; pr.rcol[0] = pr.rcol[1] = pr.rcol[2] = 1.f;
+            participate(&pr);
+            if (!(pr.rcol[0] > 0 || pr.rcol[1] > 0 || pr.rcol[2] > 0)) continue;
         }
         thru = (r->rod > 0) ^ (dot(r->ron, ldir) > 0);
         if (rayorigin(s, &sr, thru ? TSHADOW : RSHADOW, r, NULL) < 0) continue;
@@ -1160,7 +1185,8 @@ static void direct(orc_scene* s, RAY* r, NORMDAT* nd) {
             if (!rayshade(s, &sr, s->objs[sr.ro].omod)) raytrans(s, &sr);
             trace_contrib(s, &sr);
             if ((sr.rcol[0] + sr.rcol[1] + sr.rcol[2]) / 3. <= FTINY) continue;
-        } else if (src->distant && sourcehit(s, &sr) && rayshade(s, &sr, s->objs[sr.ro].omod)) trace_contrib(s, &sr);
+            participate(&sr);
+        } else if (src->distant && sourcehit(s, &sr) && rayshade(s, &sr, s->objs[sr.ro].omod)) { trace_contrib(s, &sr); participate(&sr); }
         else continue;
         for (k = 0; k < 3; k++) r->rcol[k] += sr.rcol[k] * coef[k];
     }
@@ -1472,6 +1498,52 @@ static int m_aniso(orc_scene* s, const OBJ* m, RAY* r, int ro_flat) {
     return 1;
 }
 
+/* ---- dielectric / interface (rt/dielectric.c, built without DISPERSE like the reference) ---- */
+static double mylog(double x) { return x < 1e-40 ? -100. : x >= 1. ? 0. : log(x); }
+
+static int m_dielectric(orc_scene* s, const OBJ* m, RAY* r) {
+    const double* a = m->fargs; const int iface = m->otype == T_INTERFACE;
+    double cos1 = r->rod, nratio, d1, d2, cos2, refl, trans, dnorm[3]; float ctrans[3]; RAY p; int i;
+    if (m->nfargs != (iface ? 8 : 5)) { fail(s, "bad arguments for", m->name); return 1; }
+    for (i = 0; i < 3; i++) dnorm[i] = r->ron[i];
+    nratio = iface ? a[3] / a[7] : a[3] + a[4] / 500.;            /* Hartmann, mean lambda 500 */
+    if (cos1 < 0.0) {                                            /* ray arrives from inside */
+        cos1 = -cos1;
+        for (i = 0; i < 3; i++) { dnorm[i] = -dnorm[i]; r->cext[i] = (float)-mylog(a[i]); }
+        for (i = 0; i < 3; i++) ctrans[i] = iface ? (float)-mylog(a[4 + i]) : 0.f;     /* else the global medium */
+    } else {
+        nratio = 1.0 / nratio;
+        for (i = 0; i < 3; i++) ctrans[i] = (float)-mylog(a[i]);
+        if (iface) for (i = 0; i < 3; i++) r->cext[i] = (float)-mylog(a[4 + i]);
+    }
+    d2 = 1.0 - nratio * nratio * (1.0 - cos1 * cos1);
+    if (d2 < FTINY) refl = 1.0;                                  /* total reflection */
+    else {
+        cos2 = sqrt(d2);
+        d1 = cos1; d2 = nratio * cos2; d1 = (d1 - d2) / (d1 + d2); refl = d1 * d1;
+        d1 = 1.0 / cos1; d2 = nratio / cos2; d1 = (d1 - d2) / (d1 + d2); refl += d1 * d1;
+        refl *= 0.5;
+        trans = (1.0 - refl) * nratio * nratio;                  /* solid angle ratio */
+        p.rcoef[0] = p.rcoef[1] = p.rcoef[2] = (float)trans;
+        if (rayorigin(s, &p, REFRACTED, r, p.rcoef) == 0) {
+            d1 = nratio * cos1 - cos2;
+            for (i = 0; i < 3; i++) p.rdir[i] = nratio * r->rdir[i] + d1 * dnorm[i];
+            normalize(p.rdir);                                   /* checknorm() of a -ffast-math build */
+            for (i = 0; i < 3; i++) p.cext[i] = ctrans[i];
+            rayvalue(s, &p);
+            for (i = 0; i < 3; i++) r->rcol[i] += p.rcol[i] * p.rcoef[i];
+        }
+    }
+    p.rcoef[0] = p.rcoef[1] = p.rcoef[2] = (float)refl;
+    if (!(r->crtype & SHADOW) && rayorigin(s, &p, REFLECTED, r, p.rcoef) == 0) {
+        for (i = 0; i < 3; i++) p.rdir[i] = r->rdir[i] + dnorm[i] * (2. * cos1);
+        normalize(p.rdir);
+        rayvalue(s, &p);
+        for (i = 0; i < 3; i++) r->rcol[i] += p.rcol[i] * p.rcoef[i];
+    }
+    return 1;
+}
+
 static int m_glass(orc_scene* s, const OBJ* m, RAY* r) {
     double mcolor[3], ctemp[3], pdot, rindex, cos2, d, r1e, r1m; float scoef[3]; int hastrans, i; RAY p;
     if (m->nfargs == 3) rindex = 1.52; else if (m->nfargs == 4) rindex = m->fargs[3]; else { fail(s, "bad arguments for glass", m->name); return 1; }
@@ -1599,6 +1671,7 @@ static int rayshade(orc_scene* s, RAY* r, int mod) {
         case T_PLASTIC: case T_METAL: if (m->nfargs != 5) { fail(s, "bad arguments for", m->name); return 1; } return m_normal(s, t, m->fargs, r, flat);
         case T_TRANS: if (m->nfargs != 7) { fail(s, "bad arguments for", m->name); return 1; } return m_normal(s, t, m->fargs, r, flat);
         case T_PLASTIC2: case T_METAL2: case T_TRANS2: return m_aniso(s, m, r, flat);
+        case T_DIELECTRIC: case T_INTERFACE: return m_dielectric(s, m, r);
         case T_GLASS: return m_glass(s, m, r);
         case T_GLOW: case T_LIGHT: case T_ILLUM: case T_SPOT: return m_light(s, m, r);
         default: fail(s, "unsupported modifier reached by the oracle:", m->name); return 1;

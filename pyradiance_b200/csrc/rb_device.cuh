@@ -77,7 +77,7 @@ struct __align__(16) QRay {
     unsigned info;          // crtype (10 bits) | rlvl<<10 (6) | rdepth<<16 (6) | spare
     int rsrc;
     unsigned key_lo, key_hi;  // RNG path key
-    unsigned pad;
+    unsigned med;           // medium the ray travels in: 0 = none, else (material slot + 1) << 1 | side (rb_shade.cuh medium_cext)
 };
 static_assert(sizeof(QRay) == 96, "QRay must be 96 bytes");
 
@@ -92,7 +92,7 @@ struct __align__(16) QHemi {
     int n;
     unsigned row, info;     // parent's crtype / rlvl / rdepth
     unsigned key_lo, key_hi;
-    int atype;              // RT_RAMBIENT or RT_TAMBIENT
+    int atype;              // RT_RAMBIENT or RT_TAMBIENT | medium of the parent ray << 10
     int rsrc;
 };
 static_assert(sizeof(QHemi) == 112, "QHemi must be 112 bytes");

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(
         r.rsrc = q.rsrc;
         r.key = ((unsigned long long)q.key_hi << 32) | q.key_lo;
         r.nchild = 0;
+        r.med = q.med; r.re = 0.f;
         r.robj = hr.robj; r.rot = hr.rot; r.rod = hr.rod; r.flat = false; r.xfl = 0;
         if (hr.local) {
             hit_frame(A.S, hr.robj, hr.rot, r.org, r.dir, r.rop, r.ron, r.rod);
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(
         }
         if (r.robj >= 0) {
             const bool front = r.rod > 0.0;
+            if (r.med) ray_medium(A, r, -1);          // path extinction of an absorbing medium (rayparticipate)
             shade_ray(A, r);
             // the material reversed a surface hit from behind (flipsurface): rtrace -on reports it that way
             if (A.res && r.crtype == RT_PRIMARY && front != (r.rod > 0.0)) A.res[r.row - A.row0].pad = 1;
@@ -149,7 +151,7 @@ __device__ void init_ray(const WaveArgs& A, const InitArgs& I, unsigned i) {
         q.row = A.res ? A.row0 + i : row;           // rtrace reports per ray
         q.info = pack_info(RT_PRIMARY, 0, 0);
         q.rsrc = -1;
-        q.key_lo = (unsigned)key; q.key_hi = (unsigned)(key >> 32); q.pad = 0;
+        q.key_lo = (unsigned)key; q.key_hi = (unsigned)(key >> 32); q.med = 0;
         A.qout[slot] = q;
         return;
     }
@@ -158,6 +160,7 @@ __device__ void init_ray(const WaveArgs& A, const InitArgs& I, unsigned i) {
     r.rweight = 1.f; r.row = A.res ? A.row0 + i : row;
     r.crtype = RT_PRIMARY; r.rlvl = 0; r.rdepth = 0; r.rsrc = -1;
     r.robj = -1; r.flat = false; r.xfl = 0; r.key = key; r.nchild = 0; r.rmax = 0.0;
+    r.med = 0; r.re = 0.f;
     r.rod = 1.0;
     for (int k = 0; k < 3; k++) { r.ron[k] = dir[k]; r.dir[k] = -dir[k]; }
     if (I.irrad == IRR_RTRACE) {                     // rtrace.c:443-448,415-432
@@ -232,12 +235,14 @@ __global__ void __launch_bounds__(256) k_expand(const WaveArgs A, const ExpandAr
         par.rweight = h.rweight; par.row = h.row;
         par.crtype = h.info & 0x3ff; par.rlvl = (h.info >> 10) & 0x3f; par.rdepth = (h.info >> 16) & 0x3f;
         par.rsrc = h.rsrc; par.robj = -1; par.flat = false; par.key = hkey;
+        par.med = (unsigned)h.atype >> 10; par.re = 0.f;      // (the weight estimate is already in h.rweight)
+        const int atype = h.atype & 0x3ff;
         const float acoef[3] = {h.acoef[0], h.acoef[1], h.acoef[2]};
         const int n = h.n, nn = n * n;
         for (int idx = threadIdx.x; idx < nn; idx += blockDim.x) {
             par.nchild = (unsigned)idx;
             QRay q;
-            if (ambsample(A.P, par, h.atype, acoef, onrm, ux, uy, n, idx / n, idx % n, q)) push_ray(A, q);
+            if (ambsample(A.P, par, atype, acoef, onrm, ux, uy, n, idx / n, idx % n, q)) push_ray(A, q);
         }
     }
 }

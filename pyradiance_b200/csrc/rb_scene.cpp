@@ -1082,6 +1082,8 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
             for (int k = 0; k < 3; k++) r.u[k] = u[0] * x.m[0][k] + u[1] * x.m[1][k] + u[2] * x.m[2][k];   // multv3
             break;
         }
+        case OT_DIELECTRIC: r.kind = MK_DIELECTRIC; need(5); break;      // dielectric.c (built without DISPERSE)
+        case OT_INTERFACE: r.kind = MK_INTERFACE; need(8); break;
         case OT_LIGHT: r.kind = MK_LIGHT; need(3); break;
         case OT_GLOW:  r.kind = MK_GLOW; need(4); break;
         case OT_ILLUM: r.kind = MK_ILLUM; need(3); break;

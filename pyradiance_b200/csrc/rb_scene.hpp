@@ -100,7 +100,7 @@ enum : int {            // device primitive kinds (x & 0xff)
 // material kinds on device
 enum : int {
     MK_NONE = 0, MK_PLASTIC, MK_METAL, MK_TRANS, MK_GLASS, MK_LIGHT, MK_GLOW,
-    MK_ILLUM, MK_SPOT, MK_UNSUPPORTED, MK_PLASTIC2, MK_METAL2, MK_TRANS2
+    MK_ILLUM, MK_SPOT, MK_UNSUPPORTED, MK_PLASTIC2, MK_METAL2, MK_TRANS2, MK_DIELECTRIC, MK_INTERFACE
 };
 
 struct MatRec {          // 96 bytes

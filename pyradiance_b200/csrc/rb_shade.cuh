@@ -78,6 +78,8 @@ struct RayCtx {             // the ray being shaded (a subset of RAY, rt/ray.h:4
     unsigned char xfl;      // 1: smooth mesh triangle (vertex normals), 2: its modifier is named "Phong"
     unsigned long long key;
     unsigned nchild;        // children spawned so far (for key derivation)
+    unsigned med;           // medium the ray travelled in (QRay.med), possibly replaced by the dielectric it hit from inside
+    float re;               // min(cext) * rot of that medium: rayorigin()'s extinction estimate for the children
 };
 
 __device__ __forceinline__ float max3(const float c[3]) { return fmaxf(c[0], fmaxf(c[1], c[2])); }
@@ -93,6 +95,50 @@ __device__ __forceinline__ unsigned reserve_slot(unsigned* ctr) {
     if (g.thread_rank() == 0) base = atomicAdd(ctr, g.size());
     base = g.shfl(base, 0);
     return base + g.thread_rank();
+}
+
+// rayorigin()'s extinction estimate of a child's weight (raytrace.c:96-107), out of line: rays in an absorbing
+// medium are rare and k_shade is instruction-fetch sensitive (call sites test re > 0.1 first)
+__device__ __noinline__ float ext_weight(float rweight, float re) {
+    return re > 92.f ? 0.f : (float)((double)rweight * exp(-(double)re));
+}
+
+// ---- absorbing media (dielectric.c sets RAY.cext; raytrace.c:259-295 rayparticipate applies it) ----
+// A ray names its medium by QRay.med / RayCtx.med: 0 = none (the global -me medium is not built and is
+// rejected), else (material slot + 1) << 1 | side, side 0 = reals 0..2 of that dielectric / interface
+// (its inside), side 1 = reals 4..6 of an interface (its outside).  Extinction per unit length is
+// -mylog(transmission per unit length), dielectric.c:55-66.
+__device__ __forceinline__ float mylogf(float x) { return x < 1e-40f ? -100.f : x >= 1.f ? 0.f : (float)log((double)x); }
+__device__ __forceinline__ unsigned medium_id(int slot, int side) { return ((unsigned)(slot + 1) << 1) | (unsigned)side; }
+__device__ __noinline__ void medium_cext(const DScene& S, unsigned med, float cext[3]) {
+    const MatRec& m = S.mats[(med >> 1) - 1];
+    const int o = (med & 1) ? 4 : 0;
+    for (int k = 0; k < 3; k++) cext[k] = -mylogf(m.a[o + k]);
+}
+// rayparticipate() of a non-scattering medium for the ray being shaded, in the forward form: everything the
+// ray and its descendants will add is worth exp(-cext * rot) of it, so its cumulative coefficient is scaled
+// before anything is spawned.  Not for rcontrib: its coefficients are products of rcoef alone
+// (rcontrib.c:272-317 runs before rayparticipate).  `over` >= 0: the medium is replaced first, the way
+// m_dielectric() writes r->cext of a ray that arrives from inside (or at an interface from outside).
+// Also leaves min(cext) * rot for rayorigin()'s weight estimate (raytrace.c:96-107).
+__device__ __noinline__ void ray_medium(const WaveArgs& A, RayCtx& r, int over) {
+    if (over >= 0) r.med = (unsigned)over;
+    else if (r.robj >= 0) {               // about to be replaced by the dielectric this ray hits? then leave it to m_dielectric
+        const int ms = __ldg(&A.S.objhdr[r.robj]).z;
+        if (ms >= 0) {
+            const int k = A.S.mats[ms].kind;
+            if ((k == MK_DIELECTRIC && r.rod < 0.0) || k == MK_INTERFACE) return;
+        }
+    }
+    if (!r.med) { r.re = 0.f; return; }
+    float cext[3];
+    medium_cext(A.S, r.med, cext);
+    r.re = (float)((double)fminf(cext[0], fminf(cext[1], cext[2])) * r.rot);
+    if (fmaxf(cext[0], fmaxf(cext[1], cext[2])) <= (float)(1. / RB_FHUGE) || A.acc) return;
+    for (int k = 0; k < 3; k++) {
+        const double e = r.rot * (double)cext[k];
+        r.coef[k] *= (float)(e <= RB_FTINY ? 1. : e > 92. ? 0. : exp(-e));
+    }
 }
 
 // raytrace.c:39-135.  `rc` is the child's coefficient w.r.t. the parent (may be
@@ -112,6 +158,7 @@ __device__ __forceinline__ bool rayorigin(const DParams& P, RayCtx& par, int rt,
         rmax = (par.rmax > RB_FTINY) * (par.rmax - par.rot);
     int crtype = par.crtype | rt;
     float rweight = par.rweight * rw;
+    if (par.re > 0.1f) rweight = ext_weight(rweight, par.re);   // estimate extinction
     unsigned long long key = child_key(par.key, par.nchild++);
     if (rweight <= 0.0f) return false;
     if (!(crtype & RT_SHADOW)) {
@@ -134,7 +181,7 @@ __device__ __forceinline__ bool rayorigin(const DParams& P, RayCtx& par, int rt,
     q.info = pack_info(crtype, rlvl, par.rdepth);
     q.rsrc = rsrc;
     q.key_lo = (unsigned)key; q.key_hi = (unsigned)(key >> 32);
-    q.pad = 0;
+    q.med = par.med;
     return true;
 }
 
@@ -407,6 +454,11 @@ __device__ __forceinline__ void direct_one(const WaveArgs& A, const RayCtx& r, c
     const SrcRec& s = A.S.srcs[sn];
     if (s.flags & SF_SKIP) return;                   // srcskip()
     if (!(s.flags & SF_DISTANT)) return;
+    if (r.med) {                                     // srcvalue() -> rayparticipate() over FHUGE: nothing is left of a
+        float cext[3];                               // distant source in an absorbing medium, so it is never tested
+        medium_cext(A.S, r.med, cext);
+        if (fminf(cext[0], fminf(cext[1], cext[2])) * RB_FHUGE > 92.) return;
+    }
     // srcray(): rayorigin(sr, SHADOW, r, NULL) never fails for weight > 0
     unsigned long long key = child_key(r.key, nchild0 + (unsigned)sn);
     double vpos[3] = {0, 0, 0};
@@ -437,12 +489,12 @@ __device__ __forceinline__ void direct_one(const WaveArgs& A, const RayCtx& r, c
     const bool refl = (rt & RT_RAYREFL) != 0;        // RSHADOW starts a new path segment, TSHADOW continues
     q.rmax = refl ? 0.0 : (r.rmax > RB_FTINY) * (r.rmax - r.rot);
     q.coef[0] = r.coef[0] * scval[0]; q.coef[1] = r.coef[1] * scval[1]; q.coef[2] = r.coef[2] * scval[2];
-    q.rweight = r.rweight;
+    q.rweight = r.re > 0.1f ? ext_weight(r.rweight, r.re) : r.rweight;
     q.row = r.row;
     q.info = pack_info(r.crtype | rt, r.rlvl + (refl ? 1 : 0), r.rdepth);
     q.rsrc = sn;
     q.key_lo = (unsigned)key; q.key_hi = (unsigned)(key >> 32);
-    q.pad = 0;
+    q.med = r.med;
     push_ray(A, q);
 }
 
@@ -549,12 +601,12 @@ __device__ __noinline__ void local_sample(const WaveArgs& A, const RayCtx& r, co
     q.dir[0] = ldir[0]; q.dir[1] = ldir[1]; q.dir[2] = ldir[2];
     q.rmax = refl ? 0.0 : (r.rmax > RB_FTINY) * (r.rmax - r.rot);
     q.coef[0] = r.coef[0] * scval[0]; q.coef[1] = r.coef[1] * scval[1]; q.coef[2] = r.coef[2] * scval[2];
-    q.rweight = r.rweight;
+    q.rweight = r.re > 0.1f ? ext_weight(r.rweight, r.re) : r.rweight;
     q.row = r.row;
     q.info = pack_info(r.crtype | rt, r.rlvl + (refl ? 1 : 0), r.rdepth);
     q.rsrc = sn;
     q.key_lo = (unsigned)key; q.key_hi = (unsigned)(key >> 32);
-    q.pad = 0;
+    q.med = r.med;
     push_ray(A, q);
 }
 
@@ -697,10 +749,11 @@ __device__ __forceinline__ void multambient(const WaveArgs& A, RayCtx& r, const 
         atomicAdd(&A.C->hemi_rays, (unsigned)(n * n));
         QHemi h;
         for (int k = 0; k < 3; k++) { h.rop[k] = r.rop[k]; h.onrm[k] = onrm[k]; h.acoef[k] = acoef[k]; h.ccoef[k] = r.coef[k]; }
-        h.rweight = r.rweight; h.n = n; h.row = r.row;
+        h.rweight = r.re > 0.1f ? ext_weight(r.rweight, r.re) : r.rweight;
+        h.n = n; h.row = r.row;
         h.info = pack_info(r.crtype, r.rlvl, r.rdepth);
         h.key_lo = (unsigned)hkey; h.key_hi = (unsigned)(hkey >> 32);
-        h.atype = atyp; h.rsrc = r.rsrc;
+        h.atype = atyp | (int)(r.med << 10); h.rsrc = r.rsrc;
         h.rmax_rem = (r.rmax > RB_FTINY) * (r.rmax - r.rot);
         A.hout[slot] = h;
         return;
@@ -1040,6 +1093,72 @@ __device__ __noinline__ void m_aniso(const WaveArgs& A, RayCtx& r, int mkind, co
     direct_or_park(A, r, nd);
 }
 
+// dielectric.c:69-251 m_dielectric() (built without DISPERSE, like the reference): Fresnel reflection and
+// refraction at a dielectric / interface, a[] = reals (5 / 8).  The refracted ray leaves in the medium on
+// the other side; the ray itself is charged with the medium it came through (ray_medium).
+__device__ __noinline__ void m_dielectric(const WaveArgs& A, RayCtx& r, int mkind, int slot, const float* a) {
+    const DParams& P = A.P;
+    const bool iface = mkind == MK_INTERFACE;
+    double dnorm[3] = {r.ron[0], r.ron[1], r.ron[2]};
+    double cos1 = r.rod;
+    double pert[3];
+    int hastexture = ray_pert(A.S, r, false, pert) ? 1 : 0;
+    if (hastexture) cos1 = raynormal(dnorm, r, pert);
+    double nratio = iface ? (double)a[3] / (double)a[7] : (double)a[3] + (double)a[4] / 500.;   // Hartmann, mean lambda
+    unsigned mtrans;                                 // medium of the refracted ray
+    if (cos1 < 0.0) {                                // inside
+        hastexture = -hastexture;
+        cos1 = -cos1;
+        dnorm[0] = -dnorm[0]; dnorm[1] = -dnorm[1]; dnorm[2] = -dnorm[2];
+        ray_medium(A, r, (int)medium_id(slot, 0));
+        mtrans = iface ? medium_id(slot, 1) : 0u;
+    } else {                                         // outside
+        nratio = 1.0 / nratio;
+        mtrans = medium_id(slot, 0);
+        if (iface) ray_medium(A, r, (int)medium_id(slot, 1));     // (a plain dielectric hit from outside: k_shade has charged r.med)
+    }
+    double d2 = 1.0 - nratio * nratio * (1.0 - cos1 * cos1);       // cos theta2 squared
+    double refl;
+    if (d2 < RB_FTINY) refl = 1.0;                   // total reflection
+    else {
+        const double cos2 = sqrt(d2);
+        double d1 = cos1;
+        d2 = nratio * cos2;
+        d1 = (d1 - d2) / (d1 + d2);
+        refl = d1 * d1;
+        d1 = 1.0 / cos1;
+        d2 = nratio / cos2;
+        d1 = (d1 - d2) / (d1 + d2);
+        refl += d1 * d1;
+        refl *= 0.5;
+        const double trans = (1.0 - refl) * nratio * nratio;       // solid angle ratio
+        float rc[3] = {(float)trans, (float)trans, (float)trans};
+        QRay q;
+        if (rayorigin(P, r, RT_REFRACTED, rc, true, q)) {
+            d1 = nratio * cos1 - cos2;
+            for (int k = 0; k < 3; k++) q.dir[k] = nratio * r.dir[k] + d1 * dnorm[k];
+            if (hastexture && dot3(q.dir, r.ron) * hastexture >= -RB_FTINY) {     // accidental reflection: ignore texture
+                d1 *= (double)hastexture;
+                for (int k = 0; k < 3; k++) q.dir[k] = nratio * r.dir[k] + d1 * r.ron[k];
+            }
+            normalize3(q.dir);
+            q.med = mtrans;
+            push_ray(A, q);
+        }
+    }
+    if (!(r.crtype & RT_SHADOW)) {
+        float rc[3] = {(float)refl, (float)refl, (float)refl};
+        QRay q;
+        if (rayorigin(P, r, RT_REFLECTED, rc, true, q)) {
+            for (int k = 0; k < 3; k++) q.dir[k] = r.dir[k] + dnorm[k] * (2. * cos1);
+            if (hastexture && dot3(q.dir, r.ron) * hastexture <= RB_FTINY)        // accidental penetration
+                for (int k = 0; k < 3; k++) q.dir[k] = r.dir[k] + r.ron[k] * (2. * r.rod);
+            normalize3(q.dir);
+            push_ray(A, q);
+        }
+    }
+}
+
 // glass.c:46-165
 __device__ __forceinline__ void m_glass(const WaveArgs& A, RayCtx& r, const float* a, int nargs) {
     const DParams& P = A.P;
@@ -1204,12 +1323,13 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
             return;
         }
         if (tst_irrad) {                // raytirrad(), raytrace.c:210-228
-            if (k == MK_TRANS || k == MK_GLASS || k == MK_TRANS2) { raytrans(A, r); break; }
+            if (k == MK_TRANS || k == MK_GLASS || k == MK_TRANS2 || k == MK_DIELECTRIC || k == MK_INTERFACE) { raytrans(A, r); break; }
             if (!(k >= MK_LIGHT && k <= MK_SPOT)) { nk = MK_PLASTIC; for (int j = 0; j < 7; j++) na[j] = j < 3 ? (float)RB_PI : 0.f; break; }
         }
         if (k == MK_PLASTIC || k == MK_METAL || k == MK_TRANS) { nk = k; for (int j = 0; j < 7; j++) na[j] = m->a[j]; break; }
         if (k == MK_GLASS) { m_glass(A, r, m->a, m->nargs); break; }
         if (k >= MK_PLASTIC2 && k <= MK_TRANS2) { m_aniso(A, r, k, m->a, m->u); break; }
+        if (k == MK_DIELECTRIC || k == MK_INTERFACE) { m_dielectric(A, r, k, (int)(m - S.mats), m->a); break; }
         int rv = m_light(A, r, *m, rcol, zeroed);
         if (rv == 1) {
             have_rcol = true;

@@ -434,3 +434,381 @@ def dctimestep(*mtx, nstep: int | None = None, header: bool = True, xres: int | 
         mtx = mtx[:-1]
     cmd.extend(os.fspath(m) for m in mtx)
     return dctimestep_main(cmd, stdin)
+
+
+# =====================================================================================================
+# rmtxop (second half): general component-matrix operations around the GPU product.
+# Restates util/rmtxop.c (:503-716 main, :310-380 loadop, :383-470 binaryop, :168-300 checksymbolic for
+# 3-component RGB input) and the matrix I/O of util/rmatrix.c (:286-316 header, :471-481 ascii rows,
+# :542-596 output header).  Same call as pyradiance.rmtxop / pyradiance.Rmtxop (src/pyradiance/util.py:874-966).
+# The matrix product `.` runs in rb_mtx_multiply on the GPU (fp32, two-level accumulation); the
+# element-wise operations (+ * /, -s, -c, -t) are streaming passes done with numpy on the host next to
+# the file parsing.  Not built (rejected by name): picture (RGBE / XYZE) and spectral (NCOMP > 3) data,
+# -fc output, BSDF XML inputs with -rf / -rb, `!command` inputs, the symbolic transforms S M s m.
+# =====================================================================================================
+_DT_ORDER = {"f": 4, "a": 5, "d": 6}                # util/cmatrix.h:19-26: rmx_newtype() keeps the smaller
+_WHTEFFICACY = 179.0
+
+
+def _colormats():
+    """common/spec_rgb.c:203-221 (float COLORMAT from the CIE (x,y) of the nominal CRT primaries, EE white)."""
+    xr, yr, xg, yg, xb, yb, xw, yw = 0.640, 0.330, 0.290, 0.600, 0.150, 0.060, 1. / 3., 1. / 3.
+    D = xr * (yg - yb) + xg * (yb - yr) + xb * (yr - yg)
+    CrD = (1. / yw) * (xw * (yg - yb) - yw * (xg - xb) + xg * yb - xb * yg)
+    CgD = (1. / yw) * (xw * (yb - yr) - yw * (xb - xr) - xr * yb + xb * yr)
+    CbD = (1. / yw) * (xw * (yr - yg) - yw * (xr - xg) + xr * yg - xg * yr)
+    xyz2rgb = [[(yg - yb - xb * yg + yb * xg) / CrD, (xb - xg - xb * yg + xg * yb) / CrD, (xg * yb - xb * yg) / CrD],
+               [(yb - yr - yb * xr + yr * xb) / CgD, (xr - xb - xr * yb + xb * yr) / CgD, (xb * yr - xr * yb) / CgD],
+               [(yr - yg - yr * xg + yg * xr) / CbD, (xg - xr - xg * yr + xr * yg) / CbD, (xr * yg - xg * yr) / CbD]]
+    rgb2xyz = [[xr * CrD / D, xg * CgD / D, xb * CbD / D], [yr * CrD / D, yg * CgD / D, yb * CbD / D],
+               [(1. - xr - yr) * CrD / D, (1. - xg - yg) * CgD / D, (1. - xb - yb) * CbD / D]]
+    return (np.array(rgb2xyz, dtype=np.float32).astype(np.float64), np.array(xyz2rgb, dtype=np.float32).astype(np.float64))
+
+
+class _Rmx:
+    def __init__(self, m: np.ndarray, dtype: str):
+        self.m, self.dtype = m, dtype                # float64 [nrows, ncols, ncomp]; 'a' / 'f' / 'd'
+
+
+def _rmx_parse(data: bytes, what: str) -> _Rmx:
+    """rmx_load(): header (NROWS NCOLS NCOMP BigEndian EXPOSURE FORMAT) + data."""
+    end = data.find(b"\n\n")
+    if not data.startswith(b"#?") or end < 0:
+        raise RBError(f"rmtxop: Bad header in: {what}")
+    nrows = ncols = 0
+    ncomp, dtype, swap, expo = 3, "a", False, 1.0
+    for line in data[:end].decode("latin-1").split("\n")[1:]:
+        if line.startswith("NCOMP="):
+            ncomp = int(line[6:])
+        elif line.startswith("NROWS="):
+            nrows = int(line[6:])
+        elif line.startswith("NCOLS="):
+            ncols = int(line[6:])
+        elif line.startswith("BigEndian="):
+            swap = line[10:].strip()[:1] in ("1", "+", "y", "Y", "t", "T")
+        elif line.startswith("EXPOSURE="):
+            expo *= float(line[9:])
+        elif line.startswith("FORMAT="):
+            fmt = line[7:].strip()
+            if fmt not in _FMT:
+                raise RBError(f"rmtxop: {what}: {fmt} data is not built (only ascii / float / double matrices)")
+            dtype = _FMT[fmt]
+    if ncomp > 3 or ncomp < 1:
+        raise RBError(f"rmtxop: {what}: spectral data (NCOMP={ncomp}) is not built")
+    if ncols <= 0:
+        raise RBError(f"rmtxop: Bad header in: {what}")
+    body = data[end + 2:]
+    if dtype == "a":
+        vals = np.array(body.split(), dtype=np.float64)
+    else:
+        dt = np.dtype(np.float32 if dtype == "f" else np.float64)
+        if swap:
+            dt = dt.newbyteorder(">")
+        vals = np.frombuffer(body, dtype=dt, count=len(body) // dt.itemsize).astype(np.float64)
+    per_row = ncols * ncomp
+    if nrows <= 0:
+        nrows = vals.size // per_row
+    if nrows <= 0 or vals.size < nrows * per_row:
+        raise RBError(f"rmtxop: Error loading data from: {what}")
+    m = vals[:nrows * per_row].reshape(nrows, ncols, ncomp)
+    if expo != 1.0:
+        m = m * (1.0 / expo)
+    return _Rmx(np.ascontiguousarray(m), dtype)
+
+
+class _Op:
+    def __init__(self):
+        self.inspec = None; self.data = None; self.cmat = None; self.csym = None
+        self.sca = None; self.transpose = False; self.binop = None; self.rmp = None
+
+
+def _symbolic(csym: str, nc: int, what: str) -> np.ndarray:
+    """checksymbolic() for 3-component RGB data: one output component per letter."""
+    if "." in csym:
+        raise RBError(f"rmtxop: -c {csym}: a reference file for the component transform is not built")
+    if nc < 3:
+        raise RBError(f"{what}: -c '{csym}' requires at least 3 components")
+    rgb2xyz, _ = _colormats()
+    rows = []
+    cf = 1.0                                          # (sticky across letters, as in the reference)
+    for ch in csym:
+        row = np.zeros(nc)
+        if ch in "RGBrgb":
+            row["RGB".index(ch.upper())] = 1.0
+        elif ch in "XYZxyz":
+            if ch <= "Z":
+                cf = _WHTEFFICACY
+            row[:] = rgb2xyz["XYZ".index(ch.upper())]
+            if cf != 1:
+                row *= cf
+        elif ch in "Aa":
+            row[:] = 1.0 / nc
+        else:
+            raise RBError(f"{what}: -c '{ch}' unsupported" + (" (scotopic / melanopic transforms are not built)" if ch in "SsMm" else ""))
+        rows.append(row)
+    return np.array(rows)
+
+
+def _loadop(op: _Op, stdin: bytes | None, mres: _Rmx | None = None) -> _Rmx:
+    """loadop(): load (or take the running result) and apply -c, -s, -t in the reference's order."""
+    if mres is None:
+        if op.rmp:
+            raise RBError("rmtxop: BSDF reflection inputs (-rf / -rb) are not built")
+        if op.inspec == "-":
+            if stdin is None:
+                raise RBError("rmtxop: no standard input given")
+            rm = _rmx_parse(stdin, "<stdin>")
+        else:
+            spec = os.fspath(op.inspec)
+            if spec.startswith("!"):
+                raise RBError(f"rmtxop: input from command '{spec}' is not supported (commands are not executed)")
+            if spec.lower().endswith(".xml"):
+                raise RBError("rmtxop: BSDF XML inputs are not built (dctimestep reads them as the transmission matrix)")
+            try:
+                rm = _rmx_parse(Path(spec).read_bytes(), spec)
+            except OSError:
+                raise RBError(f"Cannot open for reading: {spec}")
+    else:
+        rm = mres
+    what = op.inspec or "trailing_ops"
+    nc = rm.m.shape[2]
+    cmat = op.cmat
+    if op.csym:
+        cmat = _symbolic(op.csym, nc, what).ravel()
+    sca = None if op.sca is None else np.array(op.sca, dtype=np.float64)
+    if cmat is not None and len(cmat):
+        cmat = np.array(cmat, dtype=np.float64)
+        if cmat.size % nc:
+            raise RBError(f"{what}: -c must have N x {nc} coefficients")
+        cmat = cmat.reshape(-1, nc).copy()
+        if sca is not None:                           # scale transform, first
+            if sca.size == 1:
+                cmat *= sca[0]
+            elif sca.size * nc != cmat.size:
+                raise RBError(f"{what}: -s must have one or {cmat.size // nc} factors")
+            else:
+                cmat *= sca[:, None]
+            sca = None
+        rm = _Rmx(np.einsum("rci,ji->rcj", rm.m, cmat), rm.dtype)      # rmx_transform()
+        nc = rm.m.shape[2]
+    if sca is not None:
+        if sca.size == 1:
+            sca = np.full(nc, sca[0])
+        elif sca.size != nc:
+            raise RBError(f"{what}: -s must have one or {nc} factors")
+        rm = _Rmx(rm.m * sca[None, None, :], rm.dtype)
+    if op.transpose:
+        rm = _Rmx(np.ascontiguousarray(rm.m.transpose(1, 0, 2)), rm.dtype)
+    return rm
+
+
+def _newtype(a: str, b: str) -> str:
+    return a if _DT_ORDER[a] < _DT_ORDER[b] else b
+
+
+def _binaryop(inspec, left: _Rmx, op: str, right: _Rmx, device: int) -> _Rmx:
+    a, b = left.m, right.m
+    dt = _newtype(left.dtype, right.dtype)
+    if op == ".":
+        if a.shape[2] != b.shape[2]:
+            raise RBError(f"{inspec}: # components do not match")
+        if a.shape[1] != b.shape[0]:
+            raise RBError(f"{inspec}: mismatched dimensions")
+        nc = a.shape[2]
+        a3 = np.ascontiguousarray(np.broadcast_to(a, a.shape[:2] + (3,)) if nc == 1 else a[:, :, :3], dtype=np.float32)
+        b3 = np.ascontiguousarray(np.broadcast_to(b, b.shape[:2] + (3,)) if nc == 1 else b[:, :, :3], dtype=np.float32)
+        if nc == 2:
+            raise RBError(f"{inspec}: 2-component concatenation is not built")
+        r = multiply(a3, b3, device=device).astype(np.float64)
+        return _Rmx(np.ascontiguousarray(r[:, :, :nc]), dt)
+    if a.shape[:2] != b.shape[:2]:
+        raise RBError(f"{inspec}: " + ("matrix sum failed" if op == "+" else
+                                       f"element-wise {'division' if op == '/' else 'multiplication'} failed"))
+    if op == "+":
+        if a.shape[2] != b.shape[2]:
+            raise RBError(f"{inspec}: matrix sum failed")
+        return _Rmx(a + b, dt)
+    if b.shape[2] > 1 and b.shape[2] != a.shape[2]:
+        raise RBError(f"{inspec}: element-wise {'division' if op == '/' else 'multiplication'} failed")
+    if op == "*":
+        return _Rmx(a * b, dt)
+    with np.errstate(divide="ignore", invalid="ignore"):                # zero divides give 0 (rmx_elemult)
+        return _Rmx(np.where(b == 0, 0.0, a / np.where(b == 0, 1.0, b)), dt)
+
+
+def _isflt(s: str) -> bool:
+    return re.fullmatch(r"[+-]?(\d+\.?\d*|\.\d+)([eE][+-]?\d+)?", s) is not None
+
+
+def rmtxop_main(argv: Sequence[str], stdin: bytes | None = None, device: int = 0) -> bytes:
+    """The rmtxop command (argv[0] = program name):
+    rmtxop [-v][-f{adf}][-t][-s sf .. | -c ce ..] m1 [.+*/] .. > mres"""
+    argv = [str(a) for a in argv]
+    usage = RBError(f"Usage: {argv[0]} [-v][-f{{adfc}}][-t][-s sf .. | -c ce ..][-rf|-rb] m1 [.+*/] .. > mres")
+    outfmt = None
+    def_csym = None
+    mop = [_Op()]
+    stdin_used = False
+    i = 1
+    while i < len(argv):
+        a = argv[i]
+        cur = mop[-1]
+        if len(a) == 1 and a in ".+*/":
+            if len(mop) < 2 or mop[-2].binop:
+                raise RBError(f"{argv[0]}: missing matrix argument before '{a}' operation")
+            mop[-2].binop = a
+        elif not a.startswith("-") or len(a) == 1:
+            if a == "-":
+                if stdin_used:
+                    raise RBError(f"{argv[0]}: standard input used for more than one matrix")
+                stdin_used = True
+            cur.inspec = a
+            if cur.csym is None and cur.cmat is None:
+                cur.csym = def_csym
+            if len(mop) > 1 and not mop[-2].binop:
+                mop[-2].binop = "."
+            mop.append(_Op())
+        else:
+            n = len(argv) - 1 - i
+            c = a[1]
+            if c == "v":
+                pass
+            elif c == "f":
+                if a[2:3] == "c":
+                    raise RBError("rmtxop: -fc (picture) output is not built")
+                if a[2:3] not in ("a", "f", "d"):
+                    raise usage
+                outfmt = a[2]
+            elif c == "t":
+                cur.transpose = True
+            elif c == "s":
+                k = 0
+                while k < n and _isflt(argv[i + 1 + k]):
+                    k += 1
+                if k <= 0:
+                    raise RBError(f"{argv[0]}: -s missing arguments")
+                cur.sca = [float(x) for x in argv[i + 1:i + 1 + k]]
+                i += k
+            elif c == "C":
+                if not n or _isflt(argv[i + 1]):
+                    raise usage
+                i += 1
+                def_csym = cur.csym = argv[i]
+                cur.cmat = None
+            elif c == "c":
+                if n and not _isflt(argv[i + 1]):
+                    i += 1
+                    cur.csym = argv[i]
+                    cur.cmat = None
+                else:
+                    k = 0
+                    while k < n and _isflt(argv[i + 1 + k]):
+                        k += 1
+                    if k <= 0:
+                        raise RBError(f"{argv[0]}: -c missing arguments")
+                    cur.cmat = [float(x) for x in argv[i + 1:i + 1 + k]]
+                    cur.csym = None
+                    i += k
+            elif c == "r":
+                if a[2:3] not in ("f", "b"):
+                    raise usage
+                cur.rmp = a[2]
+            else:
+                raise RBError(f"{argv[0]}: unknown operation '{a}'")
+        i += 1
+    trailing = mop.pop()
+    if not mop:
+        raise usage
+    if mop[-1].binop:
+        raise RBError(f"{argv[0]}: missing matrix argument after '{mop[-1].binop}' operation")
+    # left to right (the reference may go right to left for a chain of products: same result up to rounding)
+    res = _loadop(mop[0], stdin)
+    for k in range(len(mop) - 1):
+        res = _binaryop(mop[k + 1].inspec, res, mop[k].binop, _loadop(mop[k + 1], stdin), device)
+    trailing.inspec = None
+    res = _loadop(trailing, stdin, res)
+    fmt = outfmt or res.dtype
+    nr, ncol, nc = res.m.shape
+    from .rt import _quote_args
+    hdr = "#?RADIANCE\n" + _quote_args(argv) + "\n" + f"NROWS={nr}\nNCOLS={ncol}\nNCOMP={nc}\n"
+    if fmt in "fd":
+        hdr += "BigEndian=0\n"
+    hdr += "FORMAT=" + {"a": "ascii", "f": "float", "d": "double"}[fmt] + "\n\n"
+    if fmt == "a":                                     # rmx_write_ascii(): " %.7e" per component, tab per element
+        rows = []
+        for r in res.m:
+            rows.append("".join("".join(" %.7e" % v for v in el) + "\t" for el in r) + "\n")
+        body = "".join(rows).encode()
+    else:
+        body = res.m.astype("<f4" if fmt == "f" else "<f8").tobytes()
+    return hdr.encode("latin-1") + body
+
+
+def rmtxop(inp, outform: str = "a", transpose: bool = False, scale=None, transform=None, reflectance=None,
+           device: int = 0) -> bytes:
+    """Same call as pyradiance.rmtxop (src/pyradiance/util.py:874-910)."""
+    cmd = ["rmtxop"]
+    stdin = None
+    if transpose:
+        cmd.append("-t")
+    cmd.append(f"-f{outform}")
+    if scale is not None:
+        cmd.extend(["-s", str(scale)])
+    if transform is not None:
+        cmd.extend(["-c", *[str(c) for c in transform]])
+    if reflectance is not None:
+        cmd.append(f"r{reflectance}")
+    if isinstance(inp, bytes):
+        stdin = inp
+        cmd.append("-")
+    else:
+        cmd.append(str(inp))
+    return rmtxop_main(cmd, stdin, device)
+
+
+class Rmtxop:
+    """Same interface as pyradiance.Rmtxop (src/pyradiance/util.py:913-966)."""
+
+    def __init__(self, outform: str = "a", color: str | None = None, device: int = 0):
+        self.cmd = ["rmtxop", f"-f{outform}"]
+        self.stdin = None
+        self.device = device
+        if color is not None:
+            self.cmd.extend(["-C", color])
+        self.nparts = 0
+
+    def add_input(self, input_data, op: str = ".", scale=None, transform=None, transpose: bool = False,
+                  refl_side: str | None = None, color: str | None = None):
+        if self.nparts >= 1:
+            self.cmd.append(op)
+        if scale is not None:
+            self.cmd.append("-s")
+            if isinstance(scale, (int, float)):
+                self.cmd.append(str(scale))
+            else:
+                self.cmd.extend(map(str, scale))
+        if refl_side is not None:
+            self.cmd.append(f"r{refl_side[0]}")
+        if transpose:
+            self.cmd.append("-t")
+        if transform is not None:
+            self.cmd.append("-c")
+            if isinstance(transform, str):
+                self.cmd.append(transform)
+            else:
+                self.cmd.extend(map(str, transform))
+        elif color is not None:
+            self.cmd.extend(["-C", color])
+        if isinstance(input_data, bytes):
+            if self.stdin is None:
+                self.stdin = input_data
+                self.cmd.append("-")
+            else:
+                raise ValueError("stdin is already taken")
+        else:
+            self.cmd.append(str(input_data))
+        self.nparts += 1
+        return self
+
+    def __call__(self) -> bytes:
+        return rmtxop_main(self.cmd, self.stdin, self.device)

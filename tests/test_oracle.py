@@ -167,3 +167,26 @@ def test_oracle_anisotropic_materials_vs_reference_golden(golden):
     v = s.rtrace(np.tile(g["rays"][pick], (reps, 1)))["value"].reshape(reps, len(pick), 3)
     sem = np.sqrt(v.var(0, ddof=1) / reps + g["st_sem"] ** 2)
     assert (np.abs(v.mean(0) - g["st_mean"]) <= 5 * sem + 1e-5 * g["st_mean"]).all()
+
+
+def test_oracle_dielectric_interface_vs_reference_golden(golden):
+    """dielectric / interface (rt/dielectric.c, no DISPERSE) and the path
+    extinction they switch on (rayparticipate, the weight estimate of rayorigin, the distant
+    source that an absorbing medium wipes out).  Deterministic settings (-lr 8: no roulette):
+    3000 view rays through a tinted slab, a lens and an interface tank, and -I sensors under
+    them, equal the reference to 1e-5; with Russian roulette (-lr -10 -lw 2e-2) the per-ray
+    means over 300 repetitions agree within 5 combined standard errors."""
+    g = np.load(golden / "dielectric.npz")
+    octf = golden / "dielectric" / "diel.oct"
+    s = port.Scene(octf, ambounce=0, dstrsrc=0.0, specthresh=1.0, ambval=(.05, .05, .05), maxdepth=8, minweight=1e-3)
+    r = s.rtrace(g["rays"])
+    assert [s.name(i) for i in r["robj"]] == list(g["surf"])
+    np.testing.assert_allclose(r["value"], g["value"], rtol=1e-5, atol=1e-9)
+    for m in ("tinted", "clear", "water_in_glass"):
+        assert (g["mod"] == m).sum() > 500
+    np.testing.assert_allclose(s.rtrace(g["sensors"], irrad=1)["value"], g["irrad"], rtol=1e-5, atol=1e-9)
+    s = port.Scene(octf, ambounce=0, dstrsrc=0.0, specthresh=1.0, ambval=(.05, .05, .05), maxdepth=-10, minweight=2e-2, seed=9)
+    pick, reps = g["rr_pick"], 300
+    v = s.rtrace(np.tile(g["rays"][pick], (reps, 1)))["value"].reshape(reps, len(pick), 3)
+    sem = np.sqrt(v.var(0, ddof=1) / reps + g["rr_sem"] ** 2)
+    assert (np.abs(v.mean(0) - g["rr_mean"]) <= 5 * sem + 1e-5 * g["rr_mean"]).all()
