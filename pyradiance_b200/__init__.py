@@ -19,6 +19,6 @@ from .manager import (RCCONTEXT, RCcontrib, RTdoFIFO, RTimmIrrad, RTlimDist, RTm
 from .rt import Rcontrib, rcontrib_main, rtrace, rtrace_main  # noqa: F401
 from .fluxmtx import rfluxmtx, rfluxmtx_main  # noqa: F401
 from .views import vwrays, vwrays_main  # noqa: F401
-from .mtx import dctimestep, dctimestep_main  # noqa: F401
+from .mtx import Rmtxop, dctimestep, dctimestep_main, rmtxop, rmtxop_main  # noqa: F401
 
 __version__ = "0.1.0"

@@ -467,7 +467,7 @@ def _colormats():
 
 class _Rmx:
     def __init__(self, m: np.ndarray, dtype: str):
-        self.m, self.dtype = m, dtype                # float64 [nrows, ncols, ncomp]; 'a' / 'f' / 'd'
+        self.m, self.dtype = np.ascontiguousarray(m, dtype=np.float32), dtype    # rmx_dtype is float (util/rmatrix.h:24-27); 'a' / 'f' / 'd'
 
 
 def _rmx_parse(data: bytes, what: str) -> _Rmx:
@@ -510,10 +510,10 @@ def _rmx_parse(data: bytes, what: str) -> _Rmx:
         nrows = vals.size // per_row
     if nrows <= 0 or vals.size < nrows * per_row:
         raise RBError(f"rmtxop: Error loading data from: {what}")
-    m = vals[:nrows * per_row].reshape(nrows, ncols, ncomp)
+    m = vals[:nrows * per_row].reshape(nrows, ncols, ncomp).astype(np.float32)
     if expo != 1.0:
-        m = m * (1.0 / expo)
-    return _Rmx(np.ascontiguousarray(m), dtype)
+        m = m * np.float32(1.0 / np.float32(expo))
+    return _Rmx(m, dtype)
 
 
 class _Op:
@@ -589,14 +589,18 @@ def _loadop(op: _Op, stdin: bytes | None, mres: _Rmx | None = None) -> _Rmx:
             else:
                 cmat *= sca[:, None]
             sca = None
-        rm = _Rmx(np.einsum("rci,ji->rcj", rm.m, cmat), rm.dtype)      # rmx_transform()
+        src = rm.m.astype(np.float64)                 # rmx_transform(): double sums in the reference's order, float result
+        dst = np.zeros(src.shape[:2] + (cmat.shape[0],))
+        for ks in range(nc - 1, -1, -1):
+            dst += cmat[None, None, :, ks] * src[:, :, ks:ks + 1]
+        rm = _Rmx(dst, rm.dtype)
         nc = rm.m.shape[2]
     if sca is not None:
         if sca.size == 1:
             sca = np.full(nc, sca[0])
         elif sca.size != nc:
             raise RBError(f"{what}: -s must have one or {nc} factors")
-        rm = _Rmx(rm.m * sca[None, None, :], rm.dtype)
+        rm = _Rmx(rm.m * sca.astype(np.float32)[None, None, :], rm.dtype)           # rmx_scale(): float *= (float)sf
     if op.transpose:
         rm = _Rmx(np.ascontiguousarray(rm.m.transpose(1, 0, 2)), rm.dtype)
     return rm
@@ -619,7 +623,7 @@ def _binaryop(inspec, left: _Rmx, op: str, right: _Rmx, device: int) -> _Rmx:
         b3 = np.ascontiguousarray(np.broadcast_to(b, b.shape[:2] + (3,)) if nc == 1 else b[:, :, :3], dtype=np.float32)
         if nc == 2:
             raise RBError(f"{inspec}: 2-component concatenation is not built")
-        r = multiply(a3, b3, device=device).astype(np.float64)
+        r = multiply(a3, b3, device=device)
         return _Rmx(np.ascontiguousarray(r[:, :, :nc]), dt)
     if a.shape[:2] != b.shape[:2]:
         raise RBError(f"{inspec}: " + ("matrix sum failed" if op == "+" else
@@ -632,8 +636,12 @@ def _binaryop(inspec, left: _Rmx, op: str, right: _Rmx, device: int) -> _Rmx:
         raise RBError(f"{inspec}: element-wise {'division' if op == '/' else 'multiplication'} failed")
     if op == "*":
         return _Rmx(a * b, dt)
-    with np.errstate(divide="ignore", invalid="ignore"):                # zero divides give 0 (rmx_elemult)
-        return _Rmx(np.where(b == 0, 0.0, a / np.where(b == 0, 1.0, b)), dt)
+    safe = np.where(b == 0, np.float32(1), b)                           # zero divides give 0 (rmx_elemult)
+    if b.shape[2] == 1:                                                 # d = 1./d kept as float, then float products
+        q = a * (1.0 / safe.astype(np.float64)).astype(np.float32)
+    else:
+        q = a / safe
+    return _Rmx(np.where(b == 0, np.float32(0), q), dt)
 
 
 def _isflt(s: str) -> bool:

@@ -917,3 +917,37 @@ def test_dielectric_interface_vs_reference_golden(golden):
     v = v.reshape(reps, len(pick), 3)
     sem = np.sqrt(v.var(0, ddof=1) / reps + g["rr_sem"] ** 2)
     assert (np.abs(v.mean(0) - g["rr_mean"]) <= 5 * sem + 1e-5 * g["rr_mean"]).all()
+
+
+def test_rmtxop_products_vs_reference(golden, monkeypatch):
+    """rmtxop's matrix product `.` on the GPU (rb_mtx_multiply, fp32 with two-level
+    accumulation) inside the mirror of the command -- chains, transposes, scalars, component
+    transforms before and after -- against the unmodified reference rmtxop (double accumulation,
+    float storage): 1e-5 relative to the largest entry of each result, same header and dimensions;
+    plus the pyradiance.rmtxop / Rmtxop call forms."""
+    from pyradiance_b200 import mtx
+    g = np.load(golden / "rmtxop.npz")
+    monkeypatch.chdir(golden / "rmtxop")
+    n = 0
+    for i, c in enumerate(g["cases"]):
+        argv = c.split("\x1f")
+        ops = [a for a in argv if a in (".", "+", "*", "/")]
+        nmat = sum(a.endswith(".mtx") for a in argv)
+        if not ("." in ops or nmat - 1 > len(ops)):
+            continue
+        want = g[f"out{i}"].tobytes()
+        got = mtx.rmtxop_main(["rmtxop"] + argv)
+        assert got.split(b"\n\n")[0] == want.split(b"\n\n")[0], argv
+        a, b = mtx._rmx_parse(got, "got"), mtx._rmx_parse(want, "want")
+        assert a.m.shape == b.m.shape and a.dtype == b.dtype
+        assert np.abs(a.m - b.m).max() <= 1e-5 * np.abs(b.m).max(), argv
+        n += 1
+    assert n >= 7
+    v = (golden / "rmtxop" / "V.mtx").read_bytes()
+    one = mtx.rmtxop(v, outform="f", scale=2.0, transform=[0.265, 0.670, 0.065])
+    m = mtx._rmx_parse(one, "one").m
+    ref = mtx._rmx_parse(v, "v").m.astype(np.float64) @ np.array([0.265, 0.670, 0.065]) * 2.0
+    np.testing.assert_allclose(m[:, :, 0], ref, rtol=1e-6)
+    chain = mtx.Rmtxop(outform="d").add_input("V.mtx", transform="Y").add_input("S.mtx", transform="Y")()
+    w = mtx._rmx_parse(chain, "chain").m
+    assert w.shape == (40, 24, 1)

@@ -495,3 +495,38 @@ def test_option_rejections_are_explicit():
     c.set_options(["-ss", "4"])                  # parsed like the reference; refused when a run would need it
     assert c.get_params().specjitter == 4.0
 
+
+
+def _rmtxop_cases(golden):
+    g = np.load(golden / "rmtxop.npz")
+    return [(c.split("\x1f"), g[f"out{i}"].tobytes()) for i, c in enumerate(g["cases"])]
+
+
+def test_rmtxop_host_operations_match_reference_bytes(golden, monkeypatch):
+    """the rmtxop mirror's load / -c / -s / -t / + * / and output formatting against the
+    unmodified reference rmtxop (tests/golden/make_golden_rmtxop.py).  Everything that does not need the
+    GPU product is byte-identical, header included; element-wise division within one float ulp (the
+    reference's -ffast-math build divides through a reciprocal approximation)."""
+    from pyradiance_b200 import mtx
+    monkeypatch.chdir(golden / "rmtxop")
+    n = 0
+    for argv, want in _rmtxop_cases(golden):
+        ops = [a for a in argv if a in (".", "+", "*", "/")]
+        nmat = sum(a.endswith(".mtx") for a in argv)
+        if "." in ops or nmat - 1 > len(ops):          # an explicit or implied product: GPU test
+            continue
+        got = mtx.rmtxop_main(["rmtxop"] + argv)
+        if "/" in ops:
+            a, b = mtx._rmx_parse(got, "got"), mtx._rmx_parse(want, "want")
+            assert got.split(b"\n\n")[0] == want.split(b"\n\n")[0]
+            np.testing.assert_allclose(a.m, b.m, rtol=2.5e-7)
+        else:
+            assert got == want, argv
+        n += 1
+    assert n >= 20
+    with pytest.raises(_lib.RBError, match="not built"):
+        mtx.rmtxop_main(["rmtxop", "-fc", "A.mtx"])
+    with pytest.raises(_lib.RBError, match="mismatched|sum failed"):
+        mtx.rmtxop_main(["rmtxop", "A.mtx", "+", "B.mtx"])
+    with pytest.raises(_lib.RBError, match="missing matrix argument"):
+        mtx.rmtxop_main(["rmtxop", "A.mtx", "+"])
