@@ -66,6 +66,9 @@ namespace rb {
 #ifndef RB_PREFETCH
 #define RB_PREFETCH 0            // bit 0: prefetch the next leaf's set entries at the end of the step; bit 1: the next node's words
 #endif
+#ifndef RB_CONE_BSPHERE
+#define RB_CONE_BSPHERE 1        // cone-family pairs are first tested against the surface's bounding sphere (inline, cheap)
+#endif
 #ifndef RB_STEP_RCP
 #define RB_STEP_RCP 0            // 1: the step to the next cube multiplies by 1/dir (kept per ray) instead of dividing
 #endif
@@ -374,7 +377,21 @@ __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, uns
     } else {                         // rare kinds: second pass, again with all lanes
         sm.cid[wid][p] = -1;
         if (kind == PK_UNSUPPORTED) { atomicOr(errflag, RB_ERR_UNSUP_PRIM); *errobj = (unsigned)RB_ENT_ID(ent.x); }
-        else if (kind != PK_NONE) sm.defer[wid][atomicAdd(&sm.ndef[wid], 1)] = (unsigned short)p;
+        else if (kind != PK_NONE) {
+#if RB_CONE_BSPHERE
+            // the loader left a bounding sphere (4 floats, rounded outward) in the record's spare words: a ray
+            // that passes it by, points away from it, or ends before it cannot have a candidate there
+            const float4 bs = __ldg(reinterpret_cast<const float4*>(g + 10));
+            const double ox = (double)bs.x - sm.ray[0][own], oy = (double)bs.y - sm.ray[1][own], oz = (double)bs.z - sm.ray[2][own];
+            const double dx = sm.ray[3][own], dy = sm.ray[4][own], dz = sm.ray[5][own];
+            const double R = (double)bs.w, oo = ox * ox + oy * oy + oz * oz, b = ox * dx + oy * dy + oz * dz;
+            const double dd = dx * dx + dy * dy + dz * dz;
+            const bool miss = (oo - b * b / dd > R * R * (1.0 + 1e-9)) | ((b < 0.0) & (oo > R * R)) |
+                              (b - R * 1.000001 > (sm.rot[own] + 8 * RB_FTINY) * 1.000001);
+            if (!miss)
+#endif
+            sm.defer[wid][atomicAdd(&sm.ndef[wid], 1)] = (unsigned short)p;
+        }
     }
 }
 

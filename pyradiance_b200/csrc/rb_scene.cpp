@@ -985,7 +985,17 @@ static void flatten_cone(const Object& o, FlatScene& fs, int32_t hdr[4], std::st
         double* g = &fs.geom[off];
         g[0] = ad[0]; g[1] = ad[1]; g[2] = ad[2]; g[3] = al;
         g[4] = ca[p0]; g[5] = ca[p0 + 1]; g[6] = ca[p0 + 2]; g[7] = sl;
-        g[8] = ca[r0]; g[9] = ca[r1]; g[10] = 0; g[11] = 0;
+        g[8] = ca[r0]; g[9] = ca[r1];
+        {   // bounding sphere of the surface as 4 floats in the two spare words (centre, radius rounded up):
+            // the pair loop drops rays that cannot touch it before the out-of-line cone test
+            const double hl = 0.5 * al, rm = std::max(fabs(ca[r0]), fabs(ca[r1]));
+            float bs[4];
+            double cmax = 0;
+            for (int k = 0; k < 3; k++) { const double c = ca[p0 + k] + ad[k] * hl; bs[k] = (float)c; cmax = std::max(cmax, fabs(c)); }
+            const double R = sqrt(hl * hl + rm * rm);
+            bs[3] = (float)((R + 2e-7 * cmax + 1e-5) * (1.0 + 2e-7) + 1e-5);      // float rounding of centre and radius, FTINY slack
+            memcpy(&g[10], bs, sizeof(bs));
+        }
         for (int i = 0; i < 4; i++) for (int j = 0; j < 3; j++) g[12 + i * 3 + j] = tm[i][j];
         int kind = ot == OT_CONE ? PK_CONE : ot == OT_CUP ? PK_CUP : ot == OT_CYLINDER ? PK_CYL
                  : ot == OT_TUBE ? PK_TUBE : PK_RING;
