@@ -67,7 +67,7 @@ namespace rb {
 #define RB_PREFETCH 0            // bit 0: prefetch the next leaf's set entries at the end of the step; bit 1: the next node's words
 #endif
 #ifndef RB_CONE_BSPHERE
-#define RB_CONE_BSPHERE 1        // cone-family pairs are first tested against the surface's bounding sphere (inline, cheap)
+#define RB_CONE_BSPHERE 0        // 1: cone-family pairs are first tested against the bounding sphere the loader left in the record (measured: no gain)
 #endif
 #ifndef RB_STEP_RCP
 #define RB_STEP_RCP 0            // 1: the step to the next cube multiplies by 1/dir (kept per ray) instead of dividing
