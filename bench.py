@@ -280,6 +280,17 @@ def run_ours(args):
             traffic = prof["dram_bytes_per_launch"] / prof["rays_in_launch"] * rays_per_launch
         except Exception:
             pass
+        # north_star: rays/s per SM (live: k_trace rate / SM count) and warp execution efficiency (from the committed
+        # ncu --set full capture of k_trace: live lanes per warp instruction / 32)
+        extra = {}
+        try:
+            nsm = torch.cuda.get_device_properties(local).multi_processor_count
+            extra["k_trace_rays_per_s_per_sm"] = rays_per_launch / launch_s / nsm
+            summ = json.load(open(ROOT / "profiles" / "r3_ncu_summaries.json"))["r3_trace"]
+            extra["warp_execution_efficiency_ncu"] = float(summ["smsp__thread_inst_executed_per_inst_executed.ratio"].split()[0]) / 32.0
+            extra["l2_hit_rate_ncu"] = float(summ["lts__t_sector_hit_rate.pct"].split()[0]) / 100.0
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -297,7 +308,7 @@ def run_ours(args):
                          if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_ray": bpr, "counts_per_ray": counts,
                          "avg_launch_ms": launch_s * 1e3, "launches": int(st["wave_launches"]),
-                         "k_trace_share_of_kernel_time": st["wave_ms"] / max(1e-9, st["kernel_ms"])},
+                         "k_trace_share_of_kernel_time": st["wave_ms"] / max(1e-9, st["kernel_ms"]), **extra},
         }
         try:
             from oracle import refrun
