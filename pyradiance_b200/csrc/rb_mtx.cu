@@ -4,8 +4,8 @@
 //
 // RGB triplets are interleaved, so this is three GEMMs that share their index
 // structure; a tile of the A rows / B columns is contiguous in memory for all three
-// channels.  Hand-written fp32 SIMT kernel: 64 x 64 output tile per CTA, 16-deep
-// k slices staged through shared memory, 4 x 4 x 3 accumulators per thread.
+// channels.  Hand-written fp32 SIMT kernel: one channel of a 128 x 128 output tile per
+// CTA, 16-deep double-buffered k slices in shared memory, 8 x 8 accumulators per thread.
 // fp32 on purpose: coefficients span many decades (TF32 / BF16 tensor-core inputs
 // would cost 3 digits), and to stay inside 1e-5 of the reference's double
 // accumulation the sums are two-level (128 products in one accumulator, then
@@ -18,94 +18,112 @@
 
 namespace rb {
 
-constexpr int MT_BM = 64, MT_BN = 64, MT_BK = 16, MT_THREADS = 256, MT_FOLD = 8;   // fold every 8 slices = 128 products
+constexpr int MT_BM = 128, MT_BN = 128, MT_BK = 16, MT_THREADS = 256, MT_FOLD = 8;   // fold every 8 slices = 128 products
+constexpr int MT_LD = MT_BM + 4;                 // padded row of a staged slice (the transposing stores of the A tile)
 
-// 64 x 64 output tile per CTA, 4 x 4 x 3 first-level accumulators per thread in registers; the second level
-// lives in shared memory (48 floats per thread, touched once per 128 products).
+// One colour channel of a 128 x 128 output tile per CTA (blockIdx.x = channel, so the three CTAs that share
+// the sectors of an interleaved output tile run side by side and their writes merge in L2).  256 threads,
+// 8 x 8 accumulators per thread as 2 x 2 groups of 4 x 4 (rows ty*4.. and 64+ty*4.., columns tx*4.. and
+// 64+tx*4..: every shared-memory read is a conflict-free LDS.128, 64 bytes per 64 FMAs -- the 4 x 4 x 3 tile
+// of the first version read 96 bytes per 48 and was bound by shared-memory bandwidth at 23 % of the FMA peak).
+// k slices of 16 are double-buffered: the next slice travels global -> registers while the current one is
+// multiplied, then registers -> the other buffer.  The second accumulation level lives in shared memory
+// (64 floats per thread, touched once per 128 products).
 #ifndef MT_MINB
 #define MT_MINB 2
 #endif
 __global__ void __launch_bounds__(MT_THREADS, MT_MINB) k_mtx3(const float* __restrict__ A, const float* __restrict__ B,
                                                         float* __restrict__ C, int nr, int ni, int nc) {
     extern __shared__ __align__(16) float smem[];
-    float (*As)[MT_BM * 3] = reinterpret_cast<float (*)[MT_BM * 3]>(smem);                       // [MT_BK][MT_BM*3]
-    float (*Bs)[MT_BN * 3] = reinterpret_cast<float (*)[MT_BN * 3]>(smem + MT_BK * MT_BM * 3);   // [MT_BK][MT_BN*3]
-    float* acc2 = smem + MT_BK * (MT_BM + MT_BN) * 3;                                            // [48][MT_THREADS]
+    float* As = smem;                               // [2][MT_BK][MT_LD]
+    float* Bs = smem + 2 * MT_BK * MT_LD;           // [2][MT_BK][MT_LD]
+    float* acc2 = smem + 4 * MT_BK * MT_LD;         // [64][MT_THREADS]
+    // (a warp as 2 row groups x 16 column groups; 8 x 4 saves shared-memory wavefronts but measured no faster)
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int r0 = blockIdx.y * MT_BM, c0 = blockIdx.x * MT_BN;
-    float acc[4][4][3];
+    const int ch = blockIdx.x;
+    const size_t r0 = (size_t)blockIdx.z * MT_BM, c0 = (size_t)blockIdx.y * MT_BN;
+    // accumulators as float2 pairs along the columns: the products go through the packed FFMA2 of sm_100
+    // (two FMAs per issue slot; with scalar FFMA the kernel sat at 62 % of its issue slots with the FMA pipe at 47 %)
+    float2 acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) { acc[i][j][k] = 0.f; acc2[((i * 4 + j) * 3 + k) * MT_THREADS + tid] = 0.f; }
-    int slice = 0;
-    for (int k0 = 0; k0 < ni; k0 += MT_BK, slice++) {
-        // A tile: MT_BM rows x (MT_BK * 3) contiguous floats each
-#pragma unroll
-        for (int t = 0; t < (MT_BM * MT_BK * 3) / MT_THREADS; t++) {
-            const int e = tid + t * MT_THREADS, row = e / (MT_BK * 3), rem = e % (MT_BK * 3);
-            const int k = rem / 3, ch = rem % 3;
-            float v = 0.f;
-            if (r0 + row < nr && k0 + k < ni) v = __ldg(&A[((size_t)(r0 + row) * ni + k0) * 3 + rem]);
-            As[k][row * 3 + ch] = v;
-        }
-        // B tile: MT_BK rows x (MT_BN * 3) contiguous floats each
-#pragma unroll
-        for (int t = 0; t < (MT_BK * MT_BN * 3) / MT_THREADS; t++) {
-            const int e = tid + t * MT_THREADS, k = e / (MT_BN * 3), rem = e % (MT_BN * 3);
-            float v = 0.f;
-            if (k0 + k < ni && c0 + rem / 3 < nc) v = __ldg(&B[((size_t)(k0 + k) * nc + c0) * 3 + rem]);
-            Bs[k][rem] = v;
-        }
-        __syncthreads();
-#pragma unroll 2
-        for (int kk = 0; kk < MT_BK; kk++) {
-            float a[4][3], b[4][3];
-            const float4* ap = reinterpret_cast<const float4*>(&As[kk][ty * 12]);
-            const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
-            a[0][0] = a0.x; a[0][1] = a0.y; a[0][2] = a0.z; a[1][0] = a0.w; a[1][1] = a1.x; a[1][2] = a1.y;
-            a[2][0] = a1.z; a[2][1] = a1.w; a[2][2] = a2.x; a[3][0] = a2.y; a[3][1] = a2.z; a[3][2] = a2.w;
-            const float4* bp = reinterpret_cast<const float4*>(&Bs[kk][tx * 12]);
-            const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2];
-            b[0][0] = b0.x; b[0][1] = b0.y; b[0][2] = b0.z; b[1][0] = b0.w; b[1][1] = b1.x; b[1][2] = b1.y;
-            b[2][0] = b1.z; b[2][1] = b1.w; b[2][2] = b2.x; b[3][0] = b2.y; b[3][1] = b2.z; b[3][2] = b2.w;
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-#pragma unroll
-                    for (int k = 0; k < 3; k++) acc[i][j][k] = fmaf(a[i][k], b[j][k], acc[i][j][k]);
-        }
-        __syncthreads();
-        if ((slice & (MT_FOLD - 1)) == MT_FOLD - 1) {
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        acc2[((i * 4 + j) * 3 + k) * MT_THREADS + tid] += acc[i][j][k];
-                        acc[i][j][k] = 0.f;
-                    }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int r = r0 + ty * 4 + i;
-        if (r >= nr) continue;
+    for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const int c = c0 + tx * 4 + j;
-            if (c >= nc) continue;
-            float* o = C + ((size_t)r * nc + c) * 3;
+            acc[i][j] = make_float2(0.f, 0.f);
+            acc2[(i * 8 + 2 * j) * MT_THREADS + tid] = 0.f; acc2[(i * 8 + 2 * j + 1) * MT_THREADS + tid] = 0.f;
+        }
+    // staging assignment: A element e -> row e / 16, k e % 16 (16 consecutive threads walk one row's k run);
+    // B element e -> k e / 128, column e % 128 (consecutive threads walk consecutive columns)
+    float ra[8], rb[8];
+    auto fetch = [&](int k0) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) o[k] = acc2[((i * 4 + j) * 3 + k) * MT_THREADS + tid] + acc[i][j][k];
+        for (int t = 0; t < 8; t++) {
+            const int e = tid + t * MT_THREADS;
+            const int row = e >> 4, k = e & 15;
+            ra[t] = (r0 + row < (size_t)nr && k0 + k < ni) ? __ldg(&A[((r0 + row) * ni + k0 + k) * 3 + ch]) : 0.f;
+            const int kb = e >> 7, col = e & 127;
+            rb[t] = (k0 + kb < ni && c0 + col < (size_t)nc) ? __ldg(&B[((size_t)(k0 + kb) * nc + c0 + col) * 3 + ch]) : 0.f;
+        }
+    };
+    auto stage = [&](int buf) {
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            const int e = tid + t * MT_THREADS;
+            As[(buf * MT_BK + (e & 15)) * MT_LD + (e >> 4)] = ra[t];
+            Bs[(buf * MT_BK + (e >> 7)) * MT_LD + (e & 127)] = rb[t];
+        }
+    };
+    fetch(0);
+    stage(0);
+    __syncthreads();
+    int slice = 0;
+    for (int k0 = 0; k0 < ni; k0 += MT_BK, slice++) {
+        const int buf = slice & 1;
+        const bool more = k0 + MT_BK < ni;
+        if (more) fetch(k0 + MT_BK);
+        const float* as = As + buf * MT_BK * MT_LD + ty * 4;
+        const float* bs = Bs + buf * MT_BK * MT_LD + tx * 4;
+#pragma unroll
+        for (int kk = 0; kk < MT_BK; kk++) {
+            const float4 a0 = *reinterpret_cast<const float4*>(as + kk * MT_LD);
+            const float4 a1 = *reinterpret_cast<const float4*>(as + kk * MT_LD + 64);
+            const float4 b0 = *reinterpret_cast<const float4*>(bs + kk * MT_LD);
+            const float4 b1 = *reinterpret_cast<const float4*>(bs + kk * MT_LD + 64);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float2 b[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float2 aa = make_float2(a[i], a[i]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = __ffma2_rn(aa, b[j], acc[i][j]);
+            }
+        }
+        if ((slice & (MT_FOLD - 1)) == MT_FOLD - 1) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    acc2[(i * 8 + 2 * j) * MT_THREADS + tid] += acc[i][j].x;
+                    acc2[(i * 8 + 2 * j + 1) * MT_THREADS + tid] += acc[i][j].y;
+                    acc[i][j] = make_float2(0.f, 0.f);
+                }
+        }
+        if (more) stage(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const size_t r = r0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (r >= (size_t)nr) continue;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const size_t c = c0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (c >= (size_t)nc) continue;
+            C[(r * nc + c) * 3 + ch] = acc2[(i * 8 + j) * MT_THREADS + tid] + ((j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x);
         }
     }
 }
-constexpr size_t MT_SMEM = (size_t)(MT_BK * (MT_BM + MT_BN) * 3 + 48 * MT_THREADS) * sizeof(float);   // 72 KB
+constexpr size_t MT_SMEM = (size_t)(4 * MT_BK * MT_LD + 64 * MT_THREADS) * sizeof(float);   // 33 KB of slices + 64 KB second level
 
 #define MCK(call)                                                                      \
     do {                                                                               \
@@ -133,10 +151,10 @@ bool mtx_multiply(int device, cudaStream_t stream, const float* A, size_t nr, si
         Bd = dB;
     }
     // rows per chunk: staging buffers of at most ~1 GiB each when a side lives on the host
-    size_t chunk = nr;
+    size_t chunk = std::min<size_t>(nr, (size_t)65535 * MT_BM);        // grid.z limit
     if (!a_dev || !c_dev) {
         size_t per_row = std::max(ni, nc) * 3 * sizeof(float);
-        chunk = std::max<size_t>(MT_BM, std::min<size_t>(nr, ((size_t)1 << 30) / per_row / MT_BM * MT_BM));
+        chunk = std::max<size_t>(MT_BM, std::min<size_t>(chunk, ((size_t)1 << 30) / per_row / MT_BM * MT_BM));
     }
     if (!a_dev) MCK(cudaMalloc(&dA, chunk * ni * 3 * sizeof(float)));
     if (!c_dev) MCK(cudaMalloc(&dC, chunk * nc * 3 * sizeof(float)));
@@ -145,7 +163,7 @@ bool mtx_multiply(int device, cudaStream_t stream, const float* A, size_t nr, si
         const float* Ad = a_dev ? A + r * ni * 3 : dA;
         float* Cd = c_dev ? C + r * nc * 3 : dC;
         if (!a_dev) MCK(cudaMemcpyAsync(dA, A + r * ni * 3, n * ni * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
-        dim3 grid((unsigned)((nc + MT_BN - 1) / MT_BN), (unsigned)((n + MT_BM - 1) / MT_BM));
+        dim3 grid(3, (unsigned)((nc + MT_BN - 1) / MT_BN), (unsigned)((n + MT_BM - 1) / MT_BM));
         MCK(cudaEventRecord(e0, stream));
         k_mtx3<<<grid, MT_THREADS, MT_SMEM, stream>>>(Ad, Bd, Cd, (int)n, (int)ni, (int)nc);
         MCK(cudaEventRecord(e1, stream));
