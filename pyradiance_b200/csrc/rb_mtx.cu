@@ -48,22 +48,31 @@ __global__ void __launch_bounds__(MT_THREADS, MT_MINB) k_mtx3(const float* __res
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            acc[i][j] = make_float2(0.f, 0.f);
-            acc2[(i * 8 + 2 * j) * MT_THREADS + tid] = 0.f; acc2[(i * 8 + 2 * j + 1) * MT_THREADS + tid] = 0.f;
-        }
+        for (int j = 0; j < 4; j++) acc[i][j] = make_float2(0.f, 0.f);
+    bool folded = false;                            // the second level is written by the first fold, not zeroed up front
     // staging assignment: A element e -> row e / 16, k e % 16 (16 consecutive threads walk one row's k run);
     // B element e -> k e / 128, column e % 128 (consecutive threads walk consecutive columns)
     float ra[8], rb[8];
+    // the 8 + 8 elements a thread stages per slice: element t of A is row (tid >> 4) + 16 t at k = tid & 15,
+    // element t of B is k = (tid >> 7) + 2 t at column tid & 127 -- two base pointers that advance by one
+    // slice per fetch, row validity as a mask, column validity as one flag, only the k bound changes
+    const int ka = tid & 15, kb0 = tid >> 7;
+    const float* pa = A + ((r0 + (tid >> 4)) * ni + ka) * 3 + ch;
+    const float* pb = B + ((size_t)kb0 * nc + c0 + (tid & 127)) * 3 + ch;
+    const size_t astep = (size_t)16 * ni * 3, bstep = (size_t)2 * nc * 3;
+    unsigned va = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+        if (r0 + (tid >> 4) + 16 * t < (size_t)nr) va |= 1u << t;
+    const bool vb = c0 + (tid & 127) < (size_t)nc;
     auto fetch = [&](int k0) {
+        const bool kin = k0 + ka < ni;
 #pragma unroll
         for (int t = 0; t < 8; t++) {
-            const int e = tid + t * MT_THREADS;
-            const int row = e >> 4, k = e & 15;
-            ra[t] = (r0 + row < (size_t)nr && k0 + k < ni) ? __ldg(&A[((r0 + row) * ni + k0 + k) * 3 + ch]) : 0.f;
-            const int kb = e >> 7, col = e & 127;
-            rb[t] = (k0 + kb < ni && c0 + col < (size_t)nc) ? __ldg(&B[((size_t)(k0 + kb) * nc + c0 + col) * 3 + ch]) : 0.f;
+            ra[t] = (kin && (va >> t & 1)) ? __ldg(pa + t * astep) : 0.f;
+            rb[t] = (vb && k0 + kb0 + 2 * t < ni) ? __ldg(pb + t * bstep) : 0.f;
         }
+        pa += MT_BK * 3; pb += (size_t)MT_BK * nc * 3;
     };
     auto stage = [&](int buf) {
 #pragma unroll
@@ -103,10 +112,13 @@ __global__ void __launch_bounds__(MT_THREADS, MT_MINB) k_mtx3(const float* __res
             for (int i = 0; i < 8; i++)
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    acc2[(i * 8 + 2 * j) * MT_THREADS + tid] += acc[i][j].x;
-                    acc2[(i * 8 + 2 * j + 1) * MT_THREADS + tid] += acc[i][j].y;
+                    float* p0 = &acc2[(i * 8 + 2 * j) * MT_THREADS + tid];
+                    float* p1 = &acc2[(i * 8 + 2 * j + 1) * MT_THREADS + tid];
+                    *p0 = folded ? *p0 + acc[i][j].x : acc[i][j].x;
+                    *p1 = folded ? *p1 + acc[i][j].y : acc[i][j].y;
                     acc[i][j] = make_float2(0.f, 0.f);
                 }
+            folded = true;
         }
         if (more) stage(buf ^ 1);
         __syncthreads();
@@ -119,7 +131,8 @@ __global__ void __launch_bounds__(MT_THREADS, MT_MINB) k_mtx3(const float* __res
         for (int j = 0; j < 8; j++) {
             const size_t c = c0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
             if (c >= (size_t)nc) continue;
-            C[(r * nc + c) * 3 + ch] = acc2[(i * 8 + j) * MT_THREADS + tid] + ((j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x);
+            const float v = (j & 1) ? acc[i][j >> 1].y : acc[i][j >> 1].x;
+            C[(r * nc + c) * 3 + ch] = folded ? acc2[(i * 8 + j) * MT_THREADS + tid] + v : v;
         }
     }
 }
