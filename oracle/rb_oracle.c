@@ -894,8 +894,13 @@ static int rayorigin(orc_scene* s, RAY* r, int rt, const RAY* ro, const float* r
 }
 
 static void raycontrib(float* rc, const RAY* r) {
+    double e[3] = {0, 0, 0}; int k;
     rc[0] = rc[1] = rc[2] = 1.f;
-    while (r != NULL && (r->crtype & PRIMARY)) { rc[0] *= r->rcoef[0]; rc[1] *= r->rcoef[1]; rc[2] *= r->rcoef[2]; r = r->parent; }
+    while (r != NULL && (r->crtype & PRIMARY)) {
+        for (k = 0; k < 3; k++) { rc[k] *= r->rcoef[k]; e[k] += r->rot * r->cext[k]; }      /* sum PM extinction (raytrace.c:431-434) */
+        r = r->parent;
+    }
+    for (k = 0; k < 3; k++) rc[k] *= (float)(e[k] <= FTINY ? 1. : e[k] > 92. ? 0. : exp(-e[k]));
 }
 
 static void trace_contrib(orc_scene* s, RAY* r) {

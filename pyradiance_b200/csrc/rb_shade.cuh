@@ -117,8 +117,9 @@ __device__ __noinline__ void medium_cext(const DScene& S, unsigned med, float ce
 }
 // rayparticipate() of a non-scattering medium for the ray being shaded, in the forward form: everything the
 // ray and its descendants will add is worth exp(-cext * rot) of it, so its cumulative coefficient is scaled
-// before anything is spawned.  Not for rcontrib: its coefficients are products of rcoef alone
-// (rcontrib.c:272-317 runs before rayparticipate).  `over` >= 0: the medium is replaced first, the way
+// before anything is spawned.  rcontrib's coefficients carry the same factor: raycontrib() multiplies the
+// product of rcoef by exp(-sum of cext * rot) over the chain, the contributing ray included
+// (raytrace.c:407-442).  `over` >= 0: the medium is replaced first, the way
 // m_dielectric() writes r->cext of a ray that arrives from inside (or at an interface from outside).
 // Also leaves min(cext) * rot for rayorigin()'s weight estimate (raytrace.c:96-107).
 __device__ __noinline__ void ray_medium(const WaveArgs& A, RayCtx& r, int over) {
@@ -134,7 +135,7 @@ __device__ __noinline__ void ray_medium(const WaveArgs& A, RayCtx& r, int over) 
     float cext[3];
     medium_cext(A.S, r.med, cext);
     r.re = (float)((double)fminf(cext[0], fminf(cext[1], cext[2])) * r.rot);
-    if (fmaxf(cext[0], fmaxf(cext[1], cext[2])) <= (float)(1. / RB_FHUGE) || A.acc) return;
+    if (fmaxf(cext[0], fmaxf(cext[1], cext[2])) <= (float)(1. / RB_FHUGE)) return;
     for (int k = 0; k < 3; k++) {
         const double e = r.rot * (double)cext[k];
         r.coef[k] *= (float)(e <= RB_FTINY ? 1. : e > 92. ? 0. : exp(-e));

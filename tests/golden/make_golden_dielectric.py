@@ -12,7 +12,8 @@ or are totally reflected), a clear dielectric ball (a lens), a box of `interface
 coloured plastic tiles, a distant sun, a local lamp and a glow sky.  Deterministic settings
 (-ab 0 -dt 0 -dj 0 -dc 1 -st 1 -lr 8 -lw 1e-3 -av .05 .05 .05; -lr > 0 so no Russian roulette):
 rtrace values, distances and names of 3000 view rays aimed at the three bodies, plus -I
-sensors under them (shadow rays refract and are attenuated, never reflected).
+sensors under them (shadow rays refract and are attenuated, never reflected), and rcontrib
+coefficients of the three emitters for 600 of the rays (they carry the path extinction too).
 """
 import os
 import subprocess
@@ -157,5 +158,9 @@ reps = 1200
 v = refrun.rtrace(S / "diel.oct", np.tile(rays[pick], (reps, 1)), st, outform="d").reshape(reps, len(pick), 3)
 out["rr_pick"], out["rr_args"] = pick, np.array(st)
 out["rr_mean"], out["rr_sem"] = v.mean(0), v.std(0, ddof=1) / np.sqrt(reps)
+# rcontrib coefficients per emitter: raycontrib() carries the extinction summed over the chain (raytrace.c:407-442)
+rc = ["-ab", "0", "-dt", "0", "-dj", "0", "-dc", "1", "-st", "1", "-lr", "8", "-lw", "1e-3"]
+out["rc_args"] = np.array(rc)
+out["rc"] = refrun.rcontrib(S / "diel.oct", rays[:600], rc + ["-m", "skyg", "-m", "lampl", "-m", "sunl"]).reshape(600, 3, 3)
 np.savez_compressed(HERE / "dielectric.npz", **out)
 print("irradiance range", out["irrad"].min(), out["irrad"].max(), "wrote", HERE / "dielectric.npz")

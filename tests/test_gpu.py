@@ -911,6 +911,14 @@ def test_dielectric_interface_vs_reference_golden(golden):
     ctx.set_options([str(a) for a in g["args"]])
     v, _ = ctx.rtrace(g["sensors"], flags=_lib.RB_IRRAD_RTRACE)
     np.testing.assert_allclose(v, g["irrad"], rtol=1e-5, atol=1e-9)
+    rc = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)           # rcontrib coefficients carry the path extinction (raycontrib)
+    rc.load_octree(octf)
+    rc.set_options([str(a) for a in g["rc_args"]])
+    for m in ("skyg", "lampl", "sunl"):
+        rc.add_modifier(m, "", "0", 1)
+    cm = rc.rcontrib(rays[:600], dtype=np.float64)
+    badc = ~np.isclose(cm, g["rc"], rtol=1e-5, atol=1e-9).reshape(600, -1).all(1)
+    assert badc.sum() <= 1, (badc.sum(), cm[badc][:3], g["rc"][badc][:3])
     pick, reps = g["rr_pick"], 1200
     ctx.set_options([str(a) for a in g["rr_args"]])
     v, _ = ctx.rtrace(np.tile(rays[pick], (reps, 1)))

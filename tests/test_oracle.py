@@ -185,6 +185,10 @@ def test_oracle_dielectric_interface_vs_reference_golden(golden):
     for m in ("tinted", "clear", "water_in_glass"):
         assert (g["mod"] == m).sum() > 500
     np.testing.assert_allclose(s.rtrace(g["sensors"], irrad=1)["value"], g["irrad"], rtol=1e-5, atol=1e-9)
+    s = port.Scene(octf, rcontrib=True, ambounce=0, dstrsrc=0.0, specthresh=1.0, maxdepth=8, minweight=1e-3)
+    for m in ("skyg", "lampl", "sunl"):
+        s.add_modifier(m)
+    np.testing.assert_allclose(s.rcontrib(g["rays"][:600]), g["rc"], rtol=1e-5, atol=1e-9)   # coefficients carry the extinction
     s = port.Scene(octf, ambounce=0, dstrsrc=0.0, specthresh=1.0, ambval=(.05, .05, .05), maxdepth=-10, minweight=2e-2, seed=9)
     pick, reps = g["rr_pick"], 300
     v = s.rtrace(np.tile(g["rays"][pick], (reps, 1)))["value"].reshape(reps, len(pick), 3)
