@@ -530,3 +530,19 @@ def test_rmtxop_host_operations_match_reference_bytes(golden, monkeypatch):
         mtx.rmtxop_main(["rmtxop", "A.mtx", "+", "B.mtx"])
     with pytest.raises(_lib.RBError, match="missing matrix argument"):
         mtx.rmtxop_main(["rmtxop", "A.mtx", "+"])
+
+
+@pytest.mark.parametrize("sub,name", [("aniso", "aniso"), ("aniso", "anisoxf"), ("dielectric", "diel")])
+def test_own_oconv_and_loader_on_new_material_scenes(golden, workdir, sub, name):
+    """The scenes of the anisotropic / dielectric fixtures: our octree builder writes the reference oconv's file
+    (everything after the header's command line), and the loader resolves the new material types."""
+    rad, ref = golden / sub / f"{name}.rad", golden / sub / f"{name}.oct"
+    out = workdir / f"{name}_own.oct"
+    scenegen.build_octree(rad, out)
+    a, b = out.read_bytes(), ref.read_bytes()
+    assert a[a.index(b"\n\n"):] == b[b.index(b"\n\n"):]
+    c = _lib.Context(0)
+    err = c.parse_octree(ref)
+    assert err is None or "no CUDA device" in err
+    types = {c.object_type(i) for i in range(c.num_objects())}
+    assert ({"plastic2", "metal2", "trans2"} if sub == "aniso" else {"dielectric", "interface"}) <= types
