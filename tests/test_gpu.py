@@ -959,3 +959,29 @@ def test_rmtxop_products_vs_reference(golden, monkeypatch):
     chain = mtx.Rmtxop(outform="d").add_input("V.mtx", transform="Y").add_input("S.mtx", transform="Y")()
     w = mtx._rmx_parse(chain, "chain").m
     assert w.shape == (40, 24, 1)
+
+
+def test_smooth_mesh_new_materials_vs_reference_golden(golden):
+    """RAY.pert through the materials added after the first smooth-mesh fixture: plastic2 / metal2 / trans2
+    (perturbed normal in getacoords and diraniso, bent transmission with its guard, the "Phong" exemption)
+    and dielectric (perturbed Fresnel angle, the accidental-reflection / penetration guards), on smooth mesh
+    triangles placed three ways, against the reference rtrace (tests/golden/make_golden_smooth2.py):
+    names, distance, -oN / -on normals and the deterministic value (-st 1)."""
+    g0, g = np.load(golden / "smooth.npz"), np.load(golden / "smooth2.npz")
+    rays = g0["rays"]
+    out = pr.rtrace(rays.tobytes(), str(golden / "smooth" / "smoothroom2.oct"), header=False, inform="d", outform="a",
+                    outspec="vNnLsm", params=[str(a) for a in g["args"]]).decode()
+    rows = [ln.split("\t") for ln in out.splitlines()]
+    assert len(rows) == len(rays)
+    surf = np.array([r[10] for r in rows]); mod = np.array([r[11] for r in rows])
+    assert (surf == g["surf"]).all() and (mod == g["mod"]).all()
+    val = np.array([[float(x) for x in r[0:3]] for r in rows])
+    pn = np.array([[float(x) for x in r[6:9]] for r in rows])
+    np.testing.assert_allclose([float(r[9]) for r in rows], g["dist"], rtol=2e-6)
+    np.testing.assert_allclose(pn, g["pnorm"], atol=2e-6)
+    smooth = np.abs(np.abs(g["pnorm"]) - np.abs(g["fnorm"])).max(1) > 1e-6
+    bad = ~np.isclose(val, g["value"], rtol=2e-5, atol=1e-7).all(1)
+    assert bad.sum() <= 3, (bad.sum(), np.flatnonzero(bad)[:10], mod[bad][:10], val[bad][:5], g["value"][bad][:5])
+    for m in ("sm_plastic", "sm_metal", "sm_glass", "sm_trans", "Phong"):
+        k = (mod == m) & smooth
+        assert k.sum() > 100 and (~bad[k]).mean() > 0.98, m
