@@ -131,7 +131,7 @@ def run_reference(args):
     from oracle import refrun
     from pyradiance_b200 import scenegen
     if not refrun.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref not built (needs /root/reference at build time)"})
         return 0
     octf = ensure_scene()
     sens = scenegen.office_sensors(NSENS)
@@ -157,14 +157,14 @@ def run_reference(args):
     sample = (f"{n} of {NSENS} sensors per step, reference rcontrib -n {cores} (oracle/_ref, unmodified, "
               f"-O3 -ffast-math), process start-up and scene load included; rays/sensor = {rays_per_sensor:.0f} "
               f"counted by the oracle port on 6 sensors")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
     return 0
 
 
@@ -325,14 +325,30 @@ def run_ours(args):
                                         "sample": "oracle/_ref not present on this box"}
         except Exception as e:      # never lose the GPU numbers to a baseline hiccup
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_OUT = None
+
+
+def emit(obj):
+    """The one JSON line of the contract, on the process's real stdout."""
+    f = _OUT or sys.stdout
+    f.write(json.dumps(obj) + "\n")
+    f.flush()
+
+
 def main():
+    # Libraries print to stdout too (NCCL's version banner under NCCL_DEBUG=VERSION/INFO): keep the real
+    # stdout for the JSON line and send everything else written to fd 1 to stderr.
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
