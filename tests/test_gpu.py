@@ -576,6 +576,33 @@ def test_instances_and_meshes_vs_reference_golden(G, golden, name):
     assert m1.shape == (1, 1, 3) and m1[0, 0, 0] > 0
 
 
+GEOM_CASES = [("curved", "curved.oct", "curved_rays"), ("curvedtext", "curved_text.oct", "curved_rays"),
+              ("coinc", "coinc.oct", "coinc_rays"), ("coincfine", "coinc_fine.oct", "coinc_rays")]
+
+
+@pytest.mark.parametrize("tag,octf,rk", GEOM_CASES)
+def test_cone_family_and_rayreject_vs_reference_golden(golden, monkeypatch, tag, octf, rk):
+    """SURVEY 8a a5 / a7 / a8 on the device: cone, cup, cylinder, tube, ring, sphere, bubble (inside and
+    outside hits, rays across the end-cap rims: `cand_other`, the cone normal of `hit_frame`) and
+    rayreject()'s tie rules on coincident surfaces (also with the surfaces spread over many leaves,
+    where this engine re-tests them), against the unmodified reference rtrace
+    (tests/golden/make_golden_geom.py).  Surface and modifier names exact, distance 1e-9, normal 1e-9,
+    -ab 0 value 1e-5.  `curvedtext` loads the NOT frozen octree (readoct.c:90-100: scene read as text)."""
+    g = np.load(golden / "geom.npz")
+    monkeypatch.chdir(golden / "geom")
+    ctx = _lib.Context(0)
+    ctx.load_octree(octf)
+    ctx.set_options([str(a) for a in g["args"]])
+    v, res = ctx.rtrace(g[rk])
+    surf, mod = np.array(names(ctx, res["robj"])), np.array(names(ctx, res["omod"]))
+    assert np.array_equal(surf, g[tag + "_surf"]), [(i, surf[i], g[tag + "_surf"][i]) for i in np.flatnonzero(surf != g[tag + "_surf"])[:10]]
+    assert np.array_equal(mod, g[tag + "_mod"])
+    loc = g[tag + "_dist"] < 1e9
+    np.testing.assert_allclose(res["rot"][loc], g[tag + "_dist"][loc], rtol=1e-9)
+    np.testing.assert_allclose(res["ron"][loc], g[tag + "_norm"][loc], atol=1e-9)     # -oN: flips undone (rtrace.c:787-804)
+    np.testing.assert_allclose(v, g[tag + "_value"], rtol=1e-5, atol=1e-9)
+
+
 def test_sun_matrix_config5_miniature(G, golden, workdir):
     """BASELINE config 5 in miniature (5-phase direct-sun matrix): 145 `light`
     suns sharing modifier `solar`, reinhart.cal rbin with -e MF:1, louvre

@@ -48,6 +48,21 @@ def test_scene_loader_reads_reference_octree(golden):
     assert c.object_modifier(13) == 0 and c.object_modifier(14) == 7 and c.object_modifier(0) == -1
 
 
+def test_loader_reads_text_octree(golden, monkeypatch):
+    """A NOT frozen octree names its scene files (common/readoct.c:90-100): the loader reads them as text
+    (readobj.c grammar) and must end up with the objects of the frozen twin, reals at full precision."""
+    monkeypatch.chdir(golden / "geom")
+    a, b = _lib.Context(0), _lib.Context(0)
+    for c, f in ((a, "curved_text.oct"), (b, "curved.oct")):
+        err = c.parse_octree(f)
+        assert err is None or "no CUDA device" in err, err
+    assert a.num_objects() == b.num_objects() > 25
+    for i in range(a.num_objects()):
+        assert (a.object_type(i), a.object_name(i), a.object_modifier(i)) == (b.object_type(i), b.object_name(i), b.object_modifier(i))
+    kinds = {a.object_type(i) for i in range(a.num_objects())}
+    assert {"cone", "cup", "cylinder", "tube", "ring", "sphere", "bubble", "polygon", "source"} <= kinds
+
+
 def test_loader_errors():
     c = _lib.Context(0)
     assert "cannot open octree" in c.parse_octree("/nonexistent/scene.oct")

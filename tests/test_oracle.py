@@ -194,3 +194,26 @@ def test_oracle_dielectric_interface_vs_reference_golden(golden):
     v = s.rtrace(np.tile(g["rays"][pick], (reps, 1)))["value"].reshape(reps, len(pick), 3)
     sem = np.sqrt(v.var(0, ddof=1) / reps + g["rr_sem"] ** 2)
     assert (np.abs(v.mean(0) - g["rr_mean"]) <= 5 * sem + 1e-5 * g["rr_mean"]).all()
+
+
+GEOM_CASES = [("curved", "curved.oct", "curved_rays"), ("coinc", "coinc.oct", "coinc_rays"),
+              ("coincfine", "coinc_fine.oct", "coinc_rays")]
+
+
+@pytest.mark.parametrize("tag,octf,rk", GEOM_CASES)
+def test_oracle_cone_family_and_rayreject_vs_reference_golden(golden, tag, octf, rk):
+    """every member of the cone family (cone, cup, cylinder, tube, ring),
+    sphere and bubble from inside and outside with rays across the end-cap rims, and the tie rules
+    of rayreject() (raytrace.c:535-575) on coincident surfaces -- against the unmodified reference
+    rtrace (tests/golden/make_golden_geom.py): names exact, distance 1e-9, normal, -ab 0 value 1e-5."""
+    g = np.load(golden / "geom.npz")
+    s = port.Scene(golden / "geom" / octf, dstrsrc=0.0, ambval=(.1, .1, .1), specthresh=1.0, maxdepth=6, minweight=1e-3)
+    r = s.rtrace(g[rk])
+    surf = np.array([s.name(i) for i in r["robj"]])
+    mod = np.array([s.name(i) for i in r["omod"]])
+    assert np.array_equal(surf, g[tag + "_surf"]), np.flatnonzero(surf != g[tag + "_surf"])[:10]
+    assert np.array_equal(mod, g[tag + "_mod"])
+    loc = g[tag + "_dist"] < 1e9
+    np.testing.assert_allclose(r["rot"][loc], g[tag + "_dist"][loc], rtol=1e-9)
+    np.testing.assert_allclose(r["ron"][loc], g[tag + "_norm"][loc], atol=1e-9)
+    np.testing.assert_allclose(r["value"], g[tag + "_value"], rtol=1e-5, atol=1e-9)
