@@ -2,6 +2,7 @@
 // calcomp stand-in for the known bin files, modifier table, compute calls.
 #include "../../include/rb200.h"
 
+#include <algorithm>
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -354,18 +355,50 @@ static DParams device_params(const rb_ctx* c, bool contrib, bool need_values) {
     return P;
 }
 
-static int check_params(rb_ctx* c) {
-    const rb_params& p = c->prm;
+// Options that would change the reference's result and are not restated fail BY NAME (no silent
+// change of meaning, no CPU fallback).  `p` = the parameters in effect for this call (rcontrib's
+// forced -dt 0 -as 0 -aa 0 of rt/rcmain.c:164-171 already applied).
+static int check_params(rb_ctx* c, const rb_params& p) {
     if (p.ambounce > 0 && p.ambacc > 1e-6)
         return fail(c, "unsupported option: the irradiance cache (-aa > 0) is not built; use -aa 0 with -ab > 0");
     if (p.cextinction[0] > 0 || p.cextinction[1] > 0 || p.cextinction[2] > 0)
         return fail(c, "unsupported option: participating media (-me) are not built");
-    if (p.ambounce > 0 && p.ambssamp > 0 && p.ambacc > 1e-6)
-        return fail(c, "unsupported option: ambient super-sampling (-as) is not built");
     if (p.maxdepth <= 0 && p.minweight <= 0)
         return fail(c, "zero ray weight in Russian roulette");
     if (p.specjitter > 1.5)
         return fail(c, "unsupported option: -ss > 1.5 (several specular samples per hit, normal.c:374-386) is not built");
+    // rlvl and rdepth travel in 6 bits each (pack_info, rb_shade.cuh)
+    if (p.maxdepth > 63 || p.maxdepth < -63)
+        return fail(c, "unsupported option: -lr beyond +-63 (the ray level is carried in 6 bits)");
+    if (p.ambounce > 63)
+        return fail(c, "unsupported option: -ab above 63");
+    // ambsupersamp() (rt/ambcomp.c:323-346) runs when ns*ns > MINADIV^2 = 49 and ambssamp*wt + .5 >= 4*ns
+    // (ambcomp.c:413-420); both sides shrink with the ray weight, the left one faster, so a setting
+    // that does not trigger at wt = 1 never triggers.  It needs the values of the first pass, which a
+    // forward wavefront does not have: reject instead of silently skipping it.
+    if (p.ambounce > 0 && p.ambssamp > 0 && p.ambdiv > 0) {
+        const int ns = std::max(1, (int)(sqrt((double)p.ambdiv) + .5));
+        if (ns * ns > 49 && (int)(p.ambssamp + .5) >= 4 * ns)
+            return fail(c, "unsupported option: ambient super-sampling (-as " + std::to_string(p.ambssamp) +
+                           " with -ad " + std::to_string(p.ambdiv) + ") is not built; pass -as 0");
+    }
+    // direct()'s adaptive shadow testing (rt/source.c:461-556): sources are sorted by potential and
+    // tested until the untested tail falls below -dt times the value accumulated so far, the rest is
+    // added by running hit statistics -- order dependent and tied to the recursion.  The first
+    // MINSHADCNT = 2 candidates are always tested (source.c:490), so with at most two candidates
+    // per shading point the threshold never acts and every setting gives the -dt 0 result.
+    if (p.shadthresh > 0 && c->loaded) {
+        int ncand = 0;
+        for (const SrcRec& sr : c->flat.srcs) {
+            if (sr.flags & SF_SKIP) continue;
+            // a local source splits into partitions when -ds > 0 (srcsamp.c:36-144)
+            ncand += ((sr.flags & SF_DISTANT) || p.srcsizerat <= 1e-6) ? 1 : 3;
+        }
+        if (ncand > 2)
+            return fail(c, "unsupported option: -dt " + std::to_string(p.shadthresh) +
+                           " with more than two light-source candidates per point (adaptive shadow testing, "
+                           "source.c:461-556, is not built: every source is tested); pass -dt 0");
+    }
     return 0;
 }
 
@@ -561,7 +594,10 @@ int rb_rcontrib(rb_ctx* c, const double* rays, size_t nrays, int accum, unsigned
     if (!c->loaded) return fail(c, "no octree loaded");
     if (c->mods.empty()) return fail(c, "missing required modifier argument");
     if (accum <= 0) return fail(c, "unsupported option: -c 0 (single accumulated record) is not built yet");
-    if (check_params(c) < 0) return -1;
+    // rcontrib overrides (rt/rcmain.c:164-171, rxcmain.cpp:154-156): -dt 0 -as 0 -aa 0, whatever the caller set
+    rb_params eff = c->prm;
+    eff.shadthresh = 0; eff.ambssamp = 0; eff.ambacc = 0;
+    if (check_params(c, eff) < 0) return -1;
     std::string err;
     if (c->bins_dirty && !rebuild_bins(c, err)) return fail(c, err);
     size_t nrec = (nrays + accum - 1) / (size_t)accum;
@@ -573,9 +609,8 @@ int rb_rcontrib(rb_ctx* c, const double* rays, size_t nrays, int accum, unsigned
     job.cmat_double = flags & RB_FLAG_OUT_DOUBLE;
     job.irrad = flags & RB_FLAG_IRRAD_MASK; job.lim_dist = flags & RB_FLAG_LIMDIST;
     job.row_base = row_base;
-    // rcontrib overrides (rt/rcmain.c:164-171): -dt 0 -as 0 -aa 0
     rb_params saved = c->prm;
-    c->prm.shadthresh = 0; c->prm.ambssamp = 0; c->prm.ambacc = 0;
+    c->prm = eff;
     DParams P = device_params(c, flags & RB_FLAG_CONTRIB, flags & RB_FLAG_CONTRIB);
     c->prm = saved;
     if (!c->eng->run(job, P, err)) return fail(c, err);
@@ -585,7 +620,7 @@ int rb_rcontrib(rb_ctx* c, const double* rays, size_t nrays, int accum, unsigned
 int rb_rtrace(rb_ctx* c, const double* rays, size_t nrays, unsigned flags, double* values, rb_ray_result* results) {
     if (!c->cuda_ok) return fail(c, c->cuda_err);
     if (!c->loaded) return fail(c, "no octree loaded");
-    if (check_params(c) < 0) return -1;
+    if (check_params(c, c->prm) < 0) return -1;
     static_assert(sizeof(rb_ray_result) == sizeof(RayResult), "result layout");
     TraceJob job;
     job.rays = rays; job.nrays = nrays; job.accum = 1;
@@ -615,6 +650,7 @@ int rb_reset_stats(rb_ctx* c) { if (c->eng) c->eng->stats = EngineStats(); retur
 int rb_set_stream(rb_ctx* c, void* s) {
     if (!c->eng) return fail(c, c->cuda_err);
     c->eng->set_stream((cudaStream_t)s);
+    c->user_stream = s;
     return 0;
 }
 

@@ -134,6 +134,6 @@ struct DCounters {
     unsigned nd_out;               // parked direct() jobs (keep right after next_ray: reset together)
 };
 enum : unsigned { RB_ERR_UNSUP_MAT = 1, RB_ERR_UNSUP_PRIM = 2, RB_ERR_UNSUP_MOD = 4,
-                  RB_ERR_LOCAL_SRC = 8, RB_ERR_DEPTH = 16 };
+                  RB_ERR_LOCAL_SRC = 8, RB_ERR_DEPTH = 16, RB_ERR_CONTRIB_VALUE = 32 };
 
 }  // namespace rb

@@ -536,11 +536,19 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         cur ^= 1;
         nq = h_cnt_->nq_out; nh = h_cnt_->nh_out; nd = h_cnt_->nd_out;
     }
+    if (!h_cnt_->errflag && (nq > 0 || nh > 0 || nd > 0)) {
+        err = "ray generations did not end after 4096 waves (" + std::to_string(nq) + " rays still queued)";
+        return false;
+    }
     if (h_cnt_->errflag) {
         unsigned f = h_cnt_->errflag;
         std::string what = describe_obj(h_cnt_->errobj);
         if (f & RB_ERR_LOCAL_SRC) err = "unsupported: local light source material " + what + " (only distant sources are built)";
         else if (f & RB_ERR_UNSUP_MAT) err = "unsupported material " + what + " reached by a ray (no CPU fallback)";
+        else if (f & RB_ERR_CONTRIB_VALUE)
+            err = "unsupported: -V+ (contributions) with the tracked modifier on " + what +
+                  ", which does not emit: the value a reflecting / transmitting surface returns is not available "
+                  "to this engine (coefficients, -V-, are)";
         else if (f & RB_ERR_UNSUP_PRIM) err = "unsupported surface " + what + " reached by a ray (no CPU fallback)";
         else err = "unsupported modifier on " + what + " reached by a ray (patterns/textures/mixtures are not built)";
         return false;
@@ -612,6 +620,13 @@ bool Engine::run(const TraceJob& job, const DParams& P, std::string& err) {
         if (!ensure_queues(err, (size_t)(per_rec * want_rec / 0.45)) || !size_trace_grid(err)) return false;
     }
     size_t batch = (size_t)std::max(1.0, (double)qcap_ * 0.45 / per_rec);
+    if (job.cmat && ncols_ > 0) {          // the batch's accumulators (double) and output rows must fit too
+        size_t freeb = 0, totalb = 0;
+        CK(cudaMemGetInfo(&freeb, &totalb));
+        const size_t per_row = (size_t)ncols_ * 3 * (sizeof(double) + (job.cmat_on_device ? 0 : (job.cmat_double ? 8 : 4)));
+        const size_t budget = (freeb + acc_bytes_ + out_bytes_) / 2;
+        batch = std::min(batch, std::max<size_t>(1, budget / per_row));
+    }
     if (accum <= 0) batch = 1;
     size_t rec = 0;
     while (rec < nrec_total) {

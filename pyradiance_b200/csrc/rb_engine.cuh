@@ -45,7 +45,10 @@ public:
     bool upload_scene(const FlatScene& fs, const Scene& sc, std::string& err);
     bool set_bins(const std::vector<DBinSpec>& bins, const std::vector<int>& otrack, int ncols, std::string& err);
     bool run(const TraceJob& job, const DParams& P, std::string& err);
-    void set_stream(cudaStream_t s) { stream_ = s; user_stream_ = true; }
+    void set_stream(cudaStream_t s) {          // the stream the constructor made is released when it is replaced
+        if (stream_ && !user_stream_ && stream_ != s) { cudaSetDevice(dev_); cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
+        stream_ = s; user_stream_ = true;
+    }
     void set_queue_capacity(size_t nrays) { qcap_req_ = nrays; }
     EngineStats stats;
     int device() const { return dev_; }

@@ -311,7 +311,9 @@ __device__ __forceinline__ void trace_contrib(const WaveArgs& A, const RayCtx& r
     if (rcoef_zeroed) return;
     float c[3] = {r.coef[0], r.coef[1], r.coef[2]};
     if (A.P.contrib) {
-        if (!have_rcol) { atomicOr(&A.C->errflag, RB_ERR_UNSUP_MOD); A.C->errobj = (unsigned)r.robj; return; }
+        // -V+ multiplies by the radiance the ray RETURNS (rcontrib.c:296-301): known here for emitters
+        // only -- a forward wavefront has no returned value for a surface that reflects or transmits
+        if (!have_rcol) { atomicOr(&A.C->errflag, RB_ERR_CONTRIB_VALUE); A.C->errobj = (unsigned)r.robj; return; }
         c[0] *= rcol[0]; c[1] *= rcol[1]; c[2] *= rcol[2];
         // reference tests rcoef*rcol of the ray itself; the chain product has the same zero set
         if (!(c[0] > 0.f || c[1] > 0.f || c[2] > 0.f)) return;
@@ -1335,6 +1337,10 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
         if (rv == 1) {
             have_rcol = true;
             add_value(A, r.row, r.coef, rcol[0], rcol[1], rcol[2]);
+        } else if (rv == 0 && !(r.rod < 0.0 && !A.P.backvis)) {
+            // the emitter answered black (seen from behind, outside its spot cone, wrong source ...):
+            // the reference multiplies by rcol = 0 and adds nothing (rcontrib.c trace_contrib)
+            have_rcol = true;
         } else if (rv == 2) {           // passed illum: alternate material or straight through
             if (m->alt >= 0) { m = &S.mats[m->alt]; continue; }
             raytrans(A, r);

@@ -202,6 +202,7 @@ def rtrace_main(argv: Sequence[str], stdin: bytes, device: int = 0, _shard=None)
             res = np.concatenate([p[1] for p in parts])
         else:
             values, res = ctx.rtrace(rays, flags=flags, want_values=want_values, want_results=True)
+        _report_warnings(ctx, "rtrace")
         out = bytearray()
         ncomp = 0
         for ch in outvals:
@@ -215,6 +216,22 @@ def rtrace_main(argv: Sequence[str], stdin: bytes, device: int = 0, _shard=None)
         return bytes(out)
     finally:
         ctx.close()
+
+
+def _report_warnings(ctx, prog):
+    """The reference prints its warnings on stderr ("warning - bad bin number (ignored)", rcontrib.c:306;
+    the loader's notes about what it skipped): so does the mirror, once per call."""
+    import sys
+    try:
+        w = ctx.warnings()
+        for line in [x for x in w.splitlines() if x.strip()]:
+            print(f"{prog}: warning - {line}", file=sys.stderr)
+        bad = ctx.stats().get("badbin", 0)
+        if bad:
+            print(f"{prog}: warning - bad bin number (ignored) for {bad} contributions: -bn is smaller than the bin "
+                  "function's range (was -bn given before the -p / -e that sets MF?)", file=sys.stderr)
+    except Exception:       # noqa: BLE001 - reporting must never fail a finished run
+        pass
 
 
 def _raynormal(res, rdir):
@@ -570,6 +587,7 @@ def rcontrib_main(argv: Sequence[str], stdin: bytes, device: int = 0, return_arr
                 part = live[k:k + chunk]
                 tot += ctx.rcontrib(part, accum=part.shape[0], flags=flags, row_base=k, dtype=np.float64) * part.shape[0]
             mat = tot.astype(dt)
+        _report_warnings(ctx, "rcontrib")
         if return_array:
             return mat
         # ---- output streams (rc2.c:150-254 getostream, :339-356 mod_output) ----

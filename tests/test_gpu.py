@@ -348,6 +348,28 @@ def test_explicit_rejections(workdir, golden):
     ctx2.set_options(["-ab", "2"])                            # rtrace default -aa .1
     with pytest.raises(_lib.RBError, match="irradiance cache"):
         ctx2.rtrace(np.array([[2, 2, 0, 0, 0, 1.0]]))
+    ctx2.set_options(["-ab", "1", "-aa", "0", "-ad", "2048"])  # rtrace default -as 512: ambsupersamp() would run
+    with pytest.raises(_lib.RBError, match="super-sampling.*-as 0"):
+        ctx2.rtrace(np.array([[2, 2, 0, 0, 0, 1.0]]))
+    ctx2.set_options(["-ad", "16"])                           # 16 divisions never super-sample (MINADIV, ambcomp.c:413)
+    ctx2.rtrace(np.array([[2, 2, 0, 0, 0, 1.0]]))
+    ctx2.set_options(["-ab", "0", "-lr", "80"])
+    with pytest.raises(_lib.RBError, match="-lr beyond"):
+        ctx2.rtrace(np.array([[2, 2, 0, 0, 0, 1.0]]))
+    ctx7 = _lib.Context(0)                                    # rtrace's default -dt .03 on a scene with many lamps:
+    ctx7.load_octree(golden / "lights" / "lights.oct")        # adaptive shadow testing is not built -> by name
+    ctx7.set_options(["-ab", "0"])
+    with pytest.raises(_lib.RBError, match="-dt 0.03.*pass -dt 0"):
+        ctx7.rtrace(np.array([[2, 2, 1, 0, 0, -1.0]]))
+    ctx7.set_options(["-dt", "0"])
+    ctx7.rtrace(np.array([[2, 2, 1, 0, 0, -1.0]]))
+    ctx8 = _lib.Context(0)                                    # one sun + a glow sky: at most MINSHADCNT candidates,
+    ctx8.load_octree(golden / "trace.oct")                    # the threshold never acts (source.c:490) -> accepted
+    ctx8.set_options(["-ab", "0", "-dt", ".5"])
+    a, _ = ctx8.rtrace(np.array([[20, 20, 9.5, 0, 0, 1.0]]), flags=_lib.RB_IRRAD_RTRACE)
+    ctx8.set_options(["-dt", "0"])
+    b, _ = ctx8.rtrace(np.array([[20, 20, 9.5, 0, 0, 1.0]]), flags=_lib.RB_IRRAD_RTRACE)
+    assert np.array_equal(a, b) and a[0, 0] > 100
     rad5 = workdir / "dirtsky.rad"                            # only the two sky .cal functions are native code
     rad5.write_text("void brightfunc dirt\n2 dirtfn dirt.cal\n0\n0\n\ndirt glow skyglow\n0\n0\n4 1 1 1 0\n\n"
                     "skyglow source sky\n0\n0\n4 0 0 1 180\n\n")
@@ -378,6 +400,42 @@ def test_explicit_rejections(workdir, golden):
 
 
 # ------------------------------------------------------ Python boundaries ---
+def test_rcontrib_forces_its_overrides_and_contributions_of_black_emitters(golden, workdir):
+    """rcontrib forces -dt 0 -as 0 -aa 0 whatever the caller set (rcmain.c:164-171, rxcmain.cpp:154-156): a
+    context carrying rtrace's defaults (-aa .1 -as 512 -dt .03) must run, with the result of the forced
+    values.  -V+ on a tracked emitter seen from behind multiplies by rcol = 0 and adds nothing
+    (rcontrib.c:296-301); on a tracked NON-emitter it fails by name (no returned value in a forward engine)."""
+    up = np.load(golden / "bin_dirs.npy")[:200]
+    want = rc_ctx(golden / "contrib.oct", ["-ab", "0"]).rcontrib(up)
+    c = _lib.Context(0, _lib.RB_PROGRAM_RTRACE)               # rtrace defaults: -aa .1 -as 512 -dt .03
+    c.load_octree(golden / "contrib.oct")
+    c.set_options(["-ab", "1", "-ad", "2048", "-lw", "1e-4"])
+    c.cal_load("reinhartb.cal"); c.cal_set(RB_P)
+    c.add_modifier("skyglow", RB_P, "rbin", 145)
+    m = c.rcontrib(np.array([[20, 20, 12, 0, 0, 1.0]]), flags=_lib.RB_IRRAD_RCONTRIB)
+    assert abs(float(m[0, :, 0].sum()) - np.pi) < 1e-4
+    c.set_options(["-ab", "0"])
+    assert np.array_equal(c.rcontrib(up), want)
+    rad = workdir / "backglow.rad"
+    rad.write_text(scenegen.MATERIALS + scenegen.SKY + "void glow winglow\n0\n0\n4 2 3 4 0\n\n"
+                   "winglow polygon win\n0\n0\n12 0 0 1  4 0 1  4 4 1  0 4 1\n\n"         # normal +z
+                   "floor_mat polygon slab\n0\n0\n12 6 0 1  10 0 1  10 4 1  6 4 1\n\n")
+    octf = workdir / "backglow.oct"
+    scenegen.build_octree(rad, octf)
+    v = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+    v.load_octree(octf)
+    v.set_options(["-ab", "0"])
+    v.add_modifier("winglow", "", "0", 1)
+    rays = np.array([[2, 2, 3, 0, 0, -1.0], [2, 2, 0, 0, 0, 1.0]])       # front, then from behind
+    cm = v.rcontrib(rays, flags=_lib.RB_FLAG_CONTRIB, dtype=np.float64)
+    np.testing.assert_allclose(cm[0, 0], [2, 3, 4], rtol=1e-6)
+    assert not cm[1].any()
+    v.add_modifier("floor_mat", "", "0", 1)
+    with pytest.raises(_lib.RBError, match="-V\\+.*does not emit"):
+        v.rcontrib(np.array([[8, 2, 3, 0, 0, -1.0]]), flags=_lib.RB_FLAG_CONTRIB)
+    assert v.rcontrib(np.array([[8, 2, 3, 0, 0, -1.0]]))[0, 1, 0] == 1.0     # coefficients (-V-) are fine
+
+
 def test_rcontrib_class_matches_reference_layout(golden):
     rays = b"10 10 3 0 0 1\n4 5 3 0 0 1\n"
     rc = pr.Rcontrib(rays, golden / "contrib.oct", yres=2, params=["-I", "-ab", "0"])
@@ -723,7 +781,7 @@ def test_sky_brightness_patterns(golden):
     big = np.tile(sens, (16, 1))
     ctx = _lib.Context(0)
     ctx.load_octree(golden / "trace.oct")
-    ctx.set_options(["-ab", "1", "-aa", "0", "-ad", "2048", "-lw", "1e-4", "-dt", "0", "-dj", "0", "-dc", "1"])
+    ctx.set_options(["-ab", "1", "-aa", "0", "-as", "0", "-ad", "2048", "-lw", "1e-4", "-dt", "0", "-dj", "0", "-dc", "1"])
     g, _ = ctx.rtrace(big, flags=_lib.RB_IRRAD_RTRACE)
     g = g.reshape(16, 4, 3).mean(0)
     s = port.Scene(golden / "trace.oct", ambounce=1, ambdiv=2048, minweight=1e-4, dstrsrc=0.0, seed=4)
