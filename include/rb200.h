@@ -184,6 +184,17 @@ int rb_device_sync(rb_ctx* ctx);
 int rb_host_register(rb_ctx* ctx, void* p, size_t bytes);
 int rb_host_unregister(rb_ctx* ctx, void* p);
 
+/* Peer-memory window for the one exchange of the path, the gather of matrix rows (the reference hands
+ * every child's rows to one caller, rt/RcontribSimulManager.cpp:677-689, rt/rc3.c:598-622).  The gathering rank
+ * allocates the whole [nrecords][ncols][3] matrix with rb_device_alloc and exports it; every other rank (one
+ * process per GPU) opens the 64-byte handle and passes `window + its row offset` as `out` of rb_rcontrib with
+ * RB_FLAG_OUT_ON_DEVICE: the kernel that finishes a batch of records stores its rows straight into the gathering
+ * GPU's HBM over NVLink, batch by batch while the next batch is traced -- no separate gather step. */
+#define RB_IPC_HANDLE_BYTES 64
+int rb_ipc_export(rb_ctx* ctx, void* device_ptr, void* handle_out /* RB_IPC_HANDLE_BYTES */);
+int rb_ipc_open(rb_ctx* ctx, const void* handle, void** device_ptr_out);
+int rb_ipc_close(rb_ctx* ctx, void* device_ptr);
+
 /* own octree builder for synthetic scenes (next-row f3): text scene -> frozen .oct */
 int rb_oconv(const char* rad_path, const char* oct_path, int objlim, int maxres,
              char* errbuf, size_t errlen);

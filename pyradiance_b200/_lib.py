@@ -97,6 +97,9 @@ SYMBOLS = [
     ("rb_device_sync", C.c_int, [_P]),
     ("rb_host_register", C.c_int, [_P, _P, C.c_size_t]),
     ("rb_host_unregister", C.c_int, [_P, _P]),
+    ("rb_ipc_export", C.c_int, [_P, _P, _P]),
+    ("rb_ipc_open", C.c_int, [_P, _P, C.POINTER(C.c_void_p)]),
+    ("rb_ipc_close", C.c_int, [_P, _P]),
     ("rb_oconv", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_size_t]),
     ("rb_mtx_multiply", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint,
                                   C.POINTER(C.c_double)]),
@@ -339,6 +342,20 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.rb_device_sync(self.h))
+
+    # ---- peer-memory window (the row gather of SURVEY 8e, see include/rb200.h) ----
+    def ipc_export(self, dptr) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.rb_ipc_export(self.h, dptr, buf))
+        return buf.raw
+
+    def ipc_open(self, handle: bytes):
+        p = C.c_void_p(0)
+        self._ck(self.lib.rb_ipc_open(self.h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return p.value
+
+    def ipc_close(self, dptr):
+        self._ck(self.lib.rb_ipc_close(self.h, dptr))
 
 
 def device_count() -> int:

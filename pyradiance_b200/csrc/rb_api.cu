@@ -684,6 +684,34 @@ int rb_mtx_multiply(rb_ctx* c, const float* a, size_t nrows, size_t ninner, cons
     return 0;
 }
 
+int rb_ipc_export(rb_ctx* c, void* dptr, void* handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == RB_IPC_HANDLE_BYTES, "handle size");
+    if (!c->cuda_ok) return fail(c, c->cuda_err);
+    cudaSetDevice(c->device);
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, dptr);
+    if (e != cudaSuccess) return fail(c, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+int rb_ipc_open(rb_ctx* c, const void* handle, void** dptr_out) {
+    if (!c->cuda_ok) return fail(c, c->cuda_err);
+    cudaSetDevice(c->device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(c, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)); }
+    *dptr_out = p;
+    return 0;
+}
+int rb_ipc_close(rb_ctx* c, void* dptr) {
+    if (!c->cuda_ok) return fail(c, c->cuda_err);
+    cudaSetDevice(c->device);
+    cudaError_t e = cudaIpcCloseMemHandle(dptr);
+    return e == cudaSuccess ? 0 : fail(c, std::string("cudaIpcCloseMemHandle: ") + cudaGetErrorString(e));
+}
+
 int rb_host_register(rb_ctx* c, void* p, size_t bytes) {
     if (!c->cuda_ok) return fail(c, c->cuda_err);
     cudaSetDevice(c->device);

@@ -241,25 +241,39 @@ def test_shard_ranges_cover_all_rows():
 _GLOO_WORKER = r"""
 import os, sys
 import numpy as np
+import torch
 import torch.distributed as dist
 sys.path.insert(0, os.environ["RB_ROOT"])
 from pyradiance_b200 import dist as rbd
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["RB_PORT"],
                         rank=int(os.environ["RANK"]), world_size=2)
 rank = dist.get_rank()
-n, ncols = 11, 5
-rays = np.arange(n * 6, dtype=np.float64).reshape(n, 6)
-mine, r0, r1 = rbd.local_rays(rays, 1, rank, 2)
-assert mine.shape[0] == r1 - r0
-# stand-in for the traced rows: a function of the GLOBAL record index only
-rows = np.stack([np.full((ncols, 3), float(g), dtype=np.float32) for g in range(r0, r1)])
-full = rbd.gather_rows(rows, n)
+ncols = 5
+for n in (11, 2, 1):                 # uneven blocks; n = 1 leaves rank 1 with an empty block
+    rays = np.arange(n * 6, dtype=np.float64).reshape(n, 6)
+    mine, r0, r1 = rbd.local_rays(rays, 1, rank, 2)
+    assert mine.shape[0] == r1 - r0
+    # stand-in for the traced rows: a function of the GLOBAL record index only
+    rows = np.stack([np.full((ncols, 3), float(g), dtype=np.float32) for g in range(r0, r1)]) if r1 > r0 \
+        else np.zeros((0, ncols, 3), dtype=np.float32)
+    full = rbd.gather_rows(rows, n)                      # numpy in, numpy out
+    fullt = rbd.gather_rows(torch.from_numpy(rows), n)   # tensor in (device blocks under NCCL), tensor out
+    # the shared pinned host matrix: every rank writes its slice in place, the gatherer reads the whole
+    h = rbd.SharedHostMatrix(None, n, ncols)
+    sl, a, b = h.rows()
+    assert (a, b) == (r0, r1)
+    sl[...] = rows
+    h.complete()
+    if rank == 0:
+        want = np.arange(n, dtype=np.float32)
+        assert full.shape == (n, ncols, 3) and np.array_equal(full[:, 0, 0], want)
+        assert isinstance(fullt, torch.Tensor) and np.array_equal(fullt.numpy()[:, 4, 2], want)
+        assert np.array_equal(h.array[:, 2, 1], want)
+    else:
+        assert full is None and fullt is None
+    h.close()
 if rank == 0:
-    assert full.shape == (n, ncols, 3)
-    assert np.array_equal(full[:, 0, 0], np.arange(n, dtype=np.float32))
     print("GATHER_OK")
-else:
-    assert full is None
 dist.barrier()
 dist.destroy_process_group()
 """
