@@ -59,6 +59,9 @@ def lib():
                               C.POINTER(C.c_double)]
         L.orc_get_counters.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_reset_counters.argtypes = [C.c_void_p]
+        L.orc_set_walker.argtypes = [C.c_void_p, C.c_int]
+        L.orc_dev_nodes.restype = C.c_uint64
+        L.orc_dev_nodes.argtypes = [C.c_void_p]
         L.orc_last_error.restype = C.c_char_p
         L.orc_last_error.argtypes = [C.c_void_p]
         _lib = L
@@ -92,6 +95,10 @@ class Scene:
             else:
                 setattr(self.p, k, v)
         lib().orc_set_params(self.h, C.byref(self.p))
+
+    def set_walker(self, mode):
+        """1: the device's integer walk restated on the CPU; 0: the recursive restatement of the reference."""
+        lib().orc_set_walker(self.h, int(mode))
 
     def close(self):
         if self.h:

@@ -90,6 +90,8 @@ struct orc_scene {
     char err[512];
     int failed;
     unsigned short xs[3];                 /* erand48 state */
+    /* the DEVICE walk restated on the CPU (orc_set_walker(s, 1); localhit_dev() below) */
+    int walker, depth, topK; int* top; unsigned long long dev_nodes;
 };
 
 typedef struct ray {
@@ -505,6 +507,7 @@ orc_scene* orc_load(const char* path, char* err, size_t errlen) {
 }
 
 void orc_free(orc_scene* s) {
+    if (s && s->top) { free(s->top); s->top = NULL; }
     int i, k;
     if (!s) return;
     for (i = 0; i < s->nobjs; i++) {
@@ -816,8 +819,10 @@ static int raymove(orc_scene* s, double* pos, int* cxs, int dirf, RAY* r, const 
     return ax;
 }
 
+static int localhit_dev(orc_scene* s, RAY* r);
 static int localhit(orc_scene* s, RAY* r) {
     static int cxset[MAXCSET + 1];
+    if (s->walker) return localhit_dev(s, r);
     double curpos[3], t, dt; int sflags = 0, i; CUBE scene;
     s->C.nrays++;
     for (i = 0; i < 3; i++) {
@@ -844,6 +849,132 @@ static int localhit(orc_scene* s, RAY* r) {
     cxset[0] = 0;
     raymove(s, curpos, cxset, sflags, r, &scene);
     return r->ro >= 0;
+}
+
+/* -------------------------------------------- the device walk, on the CPU ---- */
+/* TEST INFRASTRUCTURE.  pyradiance_b200/csrc/rb_geom.cuh walks the octree iteratively with INTEGER cell
+ * coordinates: the ray's position is kept as three D-bit integers (D = octree depth; cell at level L =
+ * ip >> (D - L)), the descend picks a child by bit D-1-L of each coordinate instead of comparing the
+ * position with the cube's mid-planes (raytrace.c:673-687), the step to the neighbour cube
+ * (raytrace.c:688-706) is an integer increment whose carry gives the level of the common ancestor,
+ * ancestors at levels >= K wait in a per-ray stack and everything above level K comes from ONE lookup in a
+ * dense table of the level-K cells (word and level of the cube that holds the cell).  Surfaces that
+ * straddle leaves are re-tested (no checked-object set).  This function is that walk line by line in
+ * plain C so that its DECISIONS can be compared, on the CPU and over millions of rays, with the
+ * recursive restatement of the reference above (tests/test_oracle.py); hit distances never come from
+ * the walk (hit_obj() computes them from the ray origin). */
+static int tree_depth(const orc_scene* s, int w, int lvl) {
+    int i, d = lvl;
+    if (w < 0) return lvl;
+    for (i = 0; i < 8; i++) { int k = tree_depth(s, s->nodes[(size_t)w * 8 + i], lvl + 1); if (k > d) d = k; }
+    return d;
+}
+static void build_top(orc_scene* s) {
+    int K, n, c;
+    s->depth = tree_depth(s, s->root, 0);
+    if (s->depth < 1) s->depth = 1;
+    K = getenv("ORC_TOPK") ? atoi(getenv("ORC_TOPK")) : 5;
+    if (K > s->depth) K = s->depth;
+    if (K < 1) K = 1;
+    s->topK = K;
+    n = 1 << (3 * K);
+    s->top = (int*)malloc(sizeof(int) * 2 * (size_t)n);
+    for (c = 0; c < n; c++) {           /* c = ix | iy << K | iz << 2K at level K */
+        int ix = c & ((1 << K) - 1), iy = (c >> K) & ((1 << K) - 1), iz = c >> (2 * K), w = s->root, L = 0;
+        while (w >= 0 && L < K) {
+            int b = K - 1 - L, br = ((ix >> b) & 1) | (((iy >> b) & 1) << 1) | (((iz >> b) & 1) << 2);
+            w = s->nodes[(size_t)w * 8 + br]; L++;
+        }
+        s->top[2 * c] = w; s->top[2 * c + 1] = L;
+    }
+}
+void orc_set_walker(orc_scene* s, int mode) {
+    s->walker = mode;
+    if (mode && !s->top) build_top(s);
+}
+unsigned long long orc_dev_nodes(const orc_scene* s) { return s->dev_nodes; }
+
+static int localhit_dev(orc_scene* s, RAY* r) {
+    const int D = s->depth, K = s->topK;
+    const double cs = s->cusize, inv = (double)(1u << D) / cs;
+    double pos[3], t, dt, rcp[3]; int dirf = 0, i, L, w, stk[64];
+    unsigned ip[3];
+    s->C.nrays++;
+    for (i = 0; i < 3; i++) {
+        pos[i] = r->rorg[i];
+        if (r->rdir[i] > 1e-7) dirf |= 1 << i; else if (r->rdir[i] < -1e-7) dirf |= 0x10 << i;
+        rcp[i] = fabs(r->rdir[i]) > 1e-7 ? 1.0 / r->rdir[i] : 1.0;
+    }
+    if (!dirf) return 0;
+    r->aft = 0;
+    if (r->rmax > FTINY) { r->aft = 1; r->rot = r->rmax; for (i = 0; i < 3; i++) r->rop[i] = r->rorg[i] + r->rdir[i] * r->rot; }
+    {   CUBE scene; for (i = 0; i < 3; i++) scene.org[i] = s->cuorg[i]; scene.size = cs;
+        if (!incube(&scene, pos)) {
+            t = 0.0;
+            for (i = 0; i < 3; i++) {
+                if (dirf & 1 << i) dt = scene.org[i]; else if (dirf & 0x10 << i) dt = scene.org[i] + cs; else continue;
+                dt = (dt - r->rorg[i]) / r->rdir[i];
+                if (dt > t) t = dt;
+            }
+            t += FTINY;
+            if (t >= r->rot) return 0;
+            for (i = 0; i < 3; i++) pos[i] += r->rdir[i] * t;
+            if (!incube(&scene, pos)) return 0;
+        }
+    }
+    for (i = 0; i < 3; i++) {
+        double q = floor((pos[i] - s->cuorg[i]) * inv);
+        ip[i] = q < 0 ? 0u : q >= (double)(1u << D) ? (1u << D) - 1 : (unsigned)q;
+    }
+#define TOPLOOK() do { int sh = D - K; unsigned c = (ip[0] >> sh) | ((ip[1] >> sh) << K) | ((ip[2] >> sh) << (2 * K)); \
+                       w = s->top[2 * c]; L = s->top[2 * c + 1]; s->dev_nodes++; } while (0)
+    TOPLOOK();
+    for (;;) {
+        while (w >= 0) {                 /* descend: child = bit D-1-L of the integer position */
+            int b = D - 1 - L, br = ((ip[0] >> b) & 1) | (((ip[1] >> b) & 1) << 1) | (((ip[2] >> b) & 1) << 2);
+            stk[L] = w;
+            w = s->nodes[(size_t)w * 8 + br]; L++;
+            s->C.nodes++; s->dev_nodes++;
+        }
+        {
+            const int sh = D - L;
+            CUBE cu; int ax = 0, positive, La; unsigned c, ipn, diff;
+            cu.size = ldexp(cs, -L); cu.tree = w;
+            for (i = 0; i < 3; i++) cu.org[i] = fma((double)(ip[i] >> sh), cu.size, s->cuorg[i]);
+            if (w < -1) {
+                const int* set = s->pool + (-w - 2);
+                s->C.leafents += set[0] + 1;
+                for (i = set[0]; i > 0; i--) if (hit_obj(s, set[i], r)) r->robj = set[i];     /* re-tests included */
+                if (r->robj >= 0 && incube(&cu, r->rop)) return 1;
+            } else if (r->aft && r->ro < 0 && incube(&cu, r->rop)) return 0;
+            /* step (raytrace.c:712-738), plane distances through the ray's reciprocal direction */
+            if (dirf & 0x11) { dt = dirf & 1 ? cu.org[0] + cu.size : cu.org[0]; t = (dt - pos[0]) * rcp[0]; ax = 0; } else t = FHUGE;
+            if (dirf & 0x22) { dt = dirf & 2 ? cu.org[1] + cu.size : cu.org[1]; dt = (dt - pos[1]) * rcp[1]; if (dt < t) { t = dt; ax = 1; } }
+            if (dirf & 0x44) { dt = dirf & 4 ? cu.org[2] + cu.size : cu.org[2]; dt = (dt - pos[2]) * rcp[2]; if (dt < t) { t = dt; ax = 2; } }
+            for (i = 0; i < 3; i++) pos[i] += r->rdir[i] * t;
+            positive = dirf & (1 << ax);
+            c = ip[ax] >> sh;
+            if (positive) { c++; if (c >> L) return r->ro >= 0; ipn = c << sh; }      /* left the scene cube */
+            else { if (c == 0) return r->ro >= 0; ipn = (c << sh) - 1; }
+            diff = ipn ^ ip[ax];
+            La = D - 1 - (31 - __builtin_clz(diff));         /* level of the common ancestor */
+            for (i = 0; i < 3; i++) {
+                if (i == ax) ip[i] = ipn;
+                else {                      /* position inside the old leaf cell, at full depth */
+                    const unsigned lo = (ip[i] >> sh) << sh, hi = lo + ((1u << sh) - 1);
+                    double q = floor((pos[i] - s->cuorg[i]) * inv);
+                    unsigned v = q < 0 ? 0u : q >= 4294967295.0 ? 0xffffffffu : (unsigned)q;
+                    ip[i] = v < lo ? lo : v > hi ? hi : v;
+                }
+            }
+            if (La >= K) {
+                int b = D - 1 - La, br = ((ip[0] >> b) & 1) | (((ip[1] >> b) & 1) << 1) | (((ip[2] >> b) & 1) << 2);
+                w = s->nodes[(size_t)stk[La] * 8 + br]; L = La + 1;
+                s->C.nodes++; s->dev_nodes++;
+            } else TOPLOOK();
+        }
+    }
+#undef TOPLOOK
 }
 
 /* ----------------------------------------------------------- shading ---- */

@@ -58,6 +58,10 @@ double orc_bin(int fn, int mf, const double n[3], const double u[3], double rhs,
 void orc_get_counters(const orc_scene* s, orc_counters* c);
 void orc_reset_counters(orc_scene* s);
 const char* orc_last_error(const orc_scene* s);
+/* mode 1: localhit() runs the DEVICE walk restated on the CPU (integer cell coordinates, top-level cell
+ * table, no checked-object set) instead of the recursive restatement of the reference: same answers expected */
+void orc_set_walker(orc_scene* s, int mode);
+unsigned long long orc_dev_nodes(const orc_scene* s);
 
 #ifdef __cplusplus
 }

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -66,6 +67,29 @@ struct rb_ctx {
     void* user_stream = nullptr;
     std::string tmp;
 };
+
+// Engines of closed contexts, per device: streams, events, pinned counters, small queues and small scene tables
+// survive the context, so a program that opens a context per call (pyradiance.rtrace() is one process per call in
+// the reference) pays for them once.  Engine::recycle() decides what is worth keeping.
+static std::mutex g_pool_mutex;
+// (never destroyed: at process exit the CUDA runtime may be gone before static destructors run)
+static std::map<int, std::vector<std::unique_ptr<Engine>>>& g_pool = *new std::map<int, std::vector<std::unique_ptr<Engine>>>();
+static const size_t kPoolPerDevice = 4;
+
+static std::unique_ptr<Engine> pool_take(int device) {
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    auto& v = g_pool[device];
+    if (v.empty()) return nullptr;
+    std::unique_ptr<Engine> e = std::move(v.back());
+    v.pop_back();
+    return e;
+}
+static void pool_give(int device, std::unique_ptr<Engine> e) {
+    if (!e || !e->recycle()) return;           // destroyed here when not worth keeping
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    auto& v = g_pool[device];
+    if (v.size() < kPoolPerDevice) v.push_back(std::move(e));
+}
 
 static int fail(rb_ctx* c, const std::string& msg) {
     c->error = msg;
@@ -428,12 +452,17 @@ rb_ctx* rb_create(int cuda_device) {
         c->cuda_err = "CUDA device " + std::to_string(cuda_device) + " out of range";
     } else {
         c->cuda_ok = true;
-        c->eng.reset(new Engine(cuda_device));
+        c->eng = pool_take(cuda_device);
+        if (!c->eng) c->eng.reset(new Engine(cuda_device));
     }
     return c;
 }
 
-void rb_destroy(rb_ctx* c) { delete c; }
+void rb_destroy(rb_ctx* c) {
+    if (!c) return;
+    if (c->eng) pool_give(c->device, std::move(c->eng));
+    delete c;
+}
 
 const char* rb_last_error(rb_ctx* c) { return c ? c->error.c_str() : "null context"; }
 

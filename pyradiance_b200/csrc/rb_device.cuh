@@ -43,6 +43,12 @@ struct DScene {
     const SrcRec* __restrict__ srcs;
     const PatRec* __restrict__ pats;
     const int* __restrict__ otrack;
+    // integer walk (rb_geom.cuh): positions are maxdepth-bit integers, inv_cell = 2^maxdepth / cusize; top[] holds,
+    // for every cell of level topk (x | y << topk | z << 2 topk), the node word and the level of the cube that
+    // contains the cell (an interior node at level topk, or the leaf / empty cube above it)
+    const int2* __restrict__ top;
+    int topk;
+    double inv_cell;
 };
 
 // render options (rt/ray.h:157-190 RAYPARAMS subset used by this path)

@@ -29,6 +29,8 @@ namespace rb {
 #define RB_MINBLOCKS 5
 #endif
 
+static const size_t kDefaultQueue = (size_t)48 << 20;      // rays per queue of a large job
+
 #define CK(call)                                                                     \
     do {                                                                             \
         cudaError_t e_ = (call);                                                     \
@@ -262,6 +264,7 @@ __global__ void k_finish(const double* __restrict__ acc, T* __restrict__ out, si
 Engine::Engine(int device) : dev_(device) {
     cudaSetDevice(dev_);
     cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking);
+    own_stream_ = stream_;
     cudaEventCreate(&ev0_);
     cudaEventCreate(&ev1_);
     cudaEventCreate(&ev2_);
@@ -273,7 +276,7 @@ Engine::Engine(int device) : dev_(device) {
 Engine::~Engine() {
     cudaSetDevice(dev_);
     cudaDeviceSynchronize();
-    void* ptrs[] = {d_nodes_, d_leaf_, d_hdr_, d_geom_, d_mats_, d_srcs_, d_pats_, d_otrack_, d_bins_, q_[0], q_[1],
+    void* ptrs[] = {d_nodes_, d_leaf_, d_hdr_, d_geom_, d_mats_, d_srcs_, d_pats_, d_otrack_, d_top_, d_bins_, q_[0], q_[1],
                     h_[0], h_[1], d_hits_, dq_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_cnt_) cudaFreeHost(h_cnt_);
@@ -281,38 +284,98 @@ Engine::~Engine() {
     if (ev1_) cudaEventDestroy(ev1_);
     if (ev2_) cudaEventDestroy(ev2_);
     if (ev3_) cudaEventDestroy(ev3_);
-    if (stream_ && !user_stream_) cudaStreamDestroy(stream_);
+    if (own_stream_) cudaStreamDestroy(own_stream_);
+}
+
+bool Engine::recycle() {
+    cudaSetDevice(dev_);
+    if (cudaStreamSynchronize(stream_) != cudaSuccess) { cudaGetLastError(); return false; }
+    stream_ = own_stream_; user_stream_ = false;
+    stats = EngineStats();
+    qcap_req_ = 0; nbins_ = 0; ncols_ = 0;
+    objdesc.clear();
+    // keep what is cheap to hold: queues up to 1 M rays (~250 MB) and scene tables up to 64 MB
+    const size_t scene_bytes = cap_nodes_ + cap_leaf_ + cap_hdr_ + cap_geom_ + cap_top_;
+    if (qcap_ > ((size_t)1 << 20) || scene_bytes > ((size_t)64 << 20) ||
+        acc_bytes_ + out_bytes_ + vacc_bytes_ + rays_bytes_ + res_bytes_ > ((size_t)64 << 20))
+        return false;
+    return true;
 }
 
 template <class T>
-static bool upload(void*& dptr, const std::vector<T>& v, std::string& err) {
-    if (dptr) { cudaFree(dptr); dptr = nullptr; }
+static bool upload(void*& dptr, size_t& cap, const std::vector<T>& v, std::string& err) {
     size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
-    CK(cudaMalloc(&dptr, bytes));
+    if (!dptr || cap < bytes) {              // an engine taken from the pool re-uses what it has
+        if (dptr) { cudaFree(dptr); dptr = nullptr; cap = 0; }
+        CK(cudaMalloc(&dptr, bytes));
+        cap = bytes;
+    }
     if (!v.empty()) CK(cudaMemcpy(dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     return true;
 }
 
 bool Engine::upload_scene(const FlatScene& fs, const Scene& sc, std::string& err) {
     CK(cudaSetDevice(dev_));
-    if (sc.maxdepth > RB_MAXDEPTH) {
-        err = "octree is " + std::to_string(sc.maxdepth) + " levels deep; this engine walks at most " +
-              std::to_string(RB_MAXDEPTH);
-        return false;
-    }
-    if (!upload(d_nodes_, fs.nodes, err) || !upload(d_leaf_, fs.leaf2, err) ||
-        !upload(d_hdr_, fs.objhdr, err) || !upload(d_geom_, fs.geom, err) ||
-        !upload(d_mats_, fs.mats, err) || !upload(d_srcs_, fs.srcs, err) || !upload(d_pats_, fs.pats, err))
+    if (!upload(d_nodes_, cap_nodes_, fs.nodes, err) || !upload(d_leaf_, cap_leaf_, fs.leaf2, err) ||
+        !upload(d_hdr_, cap_hdr_, fs.objhdr, err) || !upload(d_geom_, cap_geom_, fs.geom, err) ||
+        !upload(d_mats_, cap_mats_, fs.mats, err) || !upload(d_srcs_, cap_srcs_, fs.srcs, err) ||
+        !upload(d_pats_, cap_pats_, fs.pats, err))
         return false;
     std::vector<int> ot(sc.objs.size(), -1);
-    if (!upload(d_otrack_, ot, err)) return false;
+    if (!upload(d_otrack_, cap_otrack_, ot, err)) return false;
+    // ---- level-K cell table of the integer walk ----
+    int depth = 0;
+    {   // deepest cube level (root = 0), from the flat node array itself
+        std::vector<std::pair<int, int>> st;
+        if (fs.root >= 0) st.push_back({fs.root, 0});
+        while (!st.empty()) {
+            auto [nd, l] = st.back(); st.pop_back();
+            depth = std::max(depth, l + 1);
+            for (int k = 0; k < 8; k++) { int w = fs.nodes[(size_t)nd * 8 + k]; if (w >= 0) st.push_back({w, l + 1}); }
+        }
+    }
+    depth = std::max(depth, 1);
+    if (depth > RB_MAXDEPTH) {
+        err = "octree is " + std::to_string(depth) + " levels deep; this engine walks at most " + std::to_string(RB_MAXDEPTH);
+        return false;
+    }
+    int K = 7;                                  // 8^7 cells x 8 B = 16 MB, L2-resident
+    if (const char* e = getenv("RB_TOPK")) K = std::max(1, std::min(8, atoi(e)));      // developer knob
+    K = std::min(K, depth);
+    {
+        const size_t ncell = (size_t)1 << (3 * K);
+        std::vector<int2> top(ncell);
+        // fill by walking the tree once: a cube at level l <= K covers 8^(K-l) cells
+        struct It { int w, l; unsigned x, y, z; };
+        std::vector<It> st;
+        st.push_back({fs.root, 0, 0u, 0u, 0u});
+        while (!st.empty()) {
+            It t = st.back(); st.pop_back();
+            if (t.w >= 0 && t.l < K) {
+                for (int k = 0; k < 8; k++)
+                    st.push_back({fs.nodes[(size_t)t.w * 8 + k], t.l + 1, (t.x << 1) | (unsigned)(k & 1),
+                                  (t.y << 1) | (unsigned)((k >> 1) & 1), (t.z << 1) | (unsigned)((k >> 2) & 1)});
+                continue;
+            }
+            const int s = K - t.l;
+            const unsigned n = 1u << s;
+            for (unsigned z = 0; z < n; z++)
+                for (unsigned y = 0; y < n; y++)
+                    for (unsigned x = 0; x < n; x++)
+                        top[(size_t)((t.x << s) + x) | ((size_t)((t.y << s) + y) << K) | ((size_t)((t.z << s) + z) << (2 * K))] =
+                            make_int2(t.w, t.l);
+        }
+        if (!upload(d_top_, cap_top_, top, err)) return false;
+    }
+    S_.top = (const int2*)d_top_; S_.topk = K;
+    S_.inv_cell = (double)(1u << depth) / sc.cusize;
     for (int k = 0; k < 3; k++) S_.cuorg[k] = sc.cuorg[k];
     S_.cusize = sc.cusize;
     S_.root = fs.root; S_.nobjs = (int)sc.objs.size(); S_.nsrcs = (int)fs.srcs.size();
     nsrc_active_ = 0;
     for (const SrcRec& sr : fs.srcs)              // local sources: a few partitions each on average
         nsrc_active_ += (sr.flags & SF_SKIP) ? 0 : (sr.flags & SF_DISTANT) ? 1 : 4;
-    S_.maxdepth = sc.maxdepth;
+    S_.maxdepth = depth;
     S_.nodes = (const int*)d_nodes_; S_.leafpool = (const int*)d_leaf_;
     S_.objhdr = (const int4*)d_hdr_; S_.geom = (const double*)d_geom_;
     S_.mats = (const MatRec*)d_mats_; S_.srcs = (const SrcRec*)d_srcs_; S_.pats = (const PatRec*)d_pats_;
@@ -334,7 +397,7 @@ std::string Engine::describe_obj(unsigned idx) const {
 bool Engine::set_bins(const std::vector<DBinSpec>& bins, const std::vector<int>& otrack, int ncols,
                       std::string& err) {
     CK(cudaSetDevice(dev_));
-    if (!upload(d_bins_, bins, err)) return false;
+    if (!upload(d_bins_, cap_bins_, bins, err)) return false;
     if ((int)otrack.size() != S_.nobjs) { err = "internal: otrack size"; return false; }
     if (!otrack.empty()) CK(cudaMemcpy(d_otrack_, otrack.data(), otrack.size() * sizeof(int), cudaMemcpyHostToDevice));
     nbins_ = (int)bins.size();
@@ -349,7 +412,7 @@ bool Engine::ensure_queues(std::string& err, size_t hint) {
     if (park_direct() && !dq_ && q_[0]) {   // a many-source scene loaded after the queues were made
         CK(cudaMalloc(&dq_, dcap_ * sizeof(DirectJob)));
     }
-    size_t want = qcap_req_ ? qcap_req_ : std::max<size_t>((size_t)48 << 20, hint);     // rays per queue
+    size_t want = qcap_req_ ? qcap_req_ : (hint ? hint : kDefaultQueue);     // rays per queue
     if (q_[0] && want <= qcap_) return true;
     if (q_[0]) {                            // grow: drop the old queues first
         CK(cudaStreamSynchronize(stream_));
@@ -380,7 +443,8 @@ bool Engine::ensure_queues(std::string& err, size_t hint) {
 // depth through the dynamic shared memory of the ancestor stack.
 bool Engine::size_trace_grid(std::string& err) {
     int per_sm = 0, nsm = 0;
-    trace_smem_ = (size_t)(S_.maxdepth + 1) * WAVE_THREADS * sizeof(int);
+    // ancestor stack of the levels below the cell table: interior nodes at levels topk .. maxdepth - 1
+    trace_smem_ = (size_t)std::max(1, S_.maxdepth - S_.topk + 1) * WAVE_THREADS * sizeof(int);
     if (const char* e = getenv("RB_TRACE_CARVEOUT"))      // developer knob: shared-memory share of the SM's 256 KB, percent
         CK(cudaFuncSetAttribute(k_trace, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace, WAVE_THREADS, trace_smem_));
@@ -615,9 +679,14 @@ bool Engine::run(const TraceJob& job, const DParams& P, std::string& err) {
     // widest wave is the first-bounce one (about half the sources face a surface)
     per_rec = per_rec * (1.0 + 0.6 * nsrc_active_) + nsrc_active_;
     per_rec *= (accum > 0 ? accum : 1);
-    {   // queues wide enough for ~256 records per batch (or the whole job), memory permitting
+    {   // queues wide enough for the whole job when it is small (a 10 k-ray rtrace call must not pay for
+        // 10 GB of cudaMalloc), else for ~256 records per batch or the default 2 x 48 M rays, memory permitting
+        const double whole = per_rec * (double)nrec_total / 0.45 * 1.25;
         const double want_rec = (double)std::min<size_t>(nrec_total, 256);
-        if (!ensure_queues(err, (size_t)(per_rec * want_rec / 0.45)) || !size_trace_grid(err)) return false;
+        size_t hint = (size_t)(per_rec * want_rec / 0.45);
+        if (whole < (double)kDefaultQueue) hint = std::max<size_t>((size_t)whole, (size_t)1 << 16);
+        else hint = std::max<size_t>(hint, kDefaultQueue);
+        if (!ensure_queues(err, hint) || !size_trace_grid(err)) return false;
     }
     size_t batch = (size_t)std::max(1.0, (double)qcap_ * 0.45 / per_rec);
     if (job.cmat && ncols_ > 0) {          // the batch's accumulators (double) and output rows must fit too
@@ -635,6 +704,12 @@ bool Engine::run(const TraceJob& job, const DParams& P, std::string& err) {
         if (!run_batch(job, P, rec, n, err, ovf)) return false;
         if (ovf) {
             stats.retries++;
+            if (!qcap_req_ && qcap_ < kDefaultQueue) {       // a small job's queues were sized by an estimate: grow them first
+                if (!ensure_queues(err, std::min<size_t>(kDefaultQueue, qcap_ * 4)) || !size_trace_grid(err)) return false;
+                batch = (size_t)std::max(1.0, (double)qcap_ * 0.45 / per_rec);
+                if (accum <= 0) batch = 1;
+                continue;
+            }
             if (n <= 1) { err = "ray queue overflow on a single record; raise the queue capacity"; return false; }
             batch = std::max<size_t>(1, n / 2);
             continue;

@@ -45,11 +45,15 @@ public:
     bool upload_scene(const FlatScene& fs, const Scene& sc, std::string& err);
     bool set_bins(const std::vector<DBinSpec>& bins, const std::vector<int>& otrack, int ncols, std::string& err);
     bool run(const TraceJob& job, const DParams& P, std::string& err);
-    void set_stream(cudaStream_t s) {          // the stream the constructor made is released when it is replaced
-        if (stream_ && !user_stream_ && stream_ != s) { cudaSetDevice(dev_); cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
+    void set_stream(cudaStream_t s) {          // launch on the caller's stream (the engine's own one stays for later)
+        if (stream_ && stream_ != s) { cudaSetDevice(dev_); cudaStreamSynchronize(stream_); }
         stream_ = s; user_stream_ = true;
     }
     void set_queue_capacity(size_t nrays) { qcap_req_ = nrays; }
+    // A closed context hands its engine to a per-device pool (rb_api.cu) so that the next context does not pay for
+    // streams, events, pinned counters and small queues again: recycle() forgets everything that belonged to the
+    // old context and says whether the engine is worth keeping (large queues / scenes are released instead).
+    bool recycle();
     EngineStats stats;
     int device() const { return dev_; }
     const std::vector<std::string>* objnames = nullptr;
@@ -65,7 +69,10 @@ private:
     bool user_stream_ = false;
     DScene S_{};
     void *d_nodes_ = nullptr, *d_leaf_ = nullptr, *d_hdr_ = nullptr, *d_geom_ = nullptr,
-         *d_mats_ = nullptr, *d_srcs_ = nullptr, *d_pats_ = nullptr, *d_otrack_ = nullptr, *d_bins_ = nullptr;
+         *d_mats_ = nullptr, *d_srcs_ = nullptr, *d_pats_ = nullptr, *d_otrack_ = nullptr, *d_bins_ = nullptr, *d_top_ = nullptr;
+    size_t cap_nodes_ = 0, cap_leaf_ = 0, cap_hdr_ = 0, cap_geom_ = 0, cap_mats_ = 0, cap_srcs_ = 0, cap_pats_ = 0,
+           cap_otrack_ = 0, cap_bins_ = 0, cap_top_ = 0;      // bytes behind the scene pointers (re-used by the next upload)
+    cudaStream_t own_stream_ = nullptr;    // the stream this engine created (stream_ may be the caller's)
     int nbins_ = 0, ncols_ = 0;
     QRay* q_[2] = {nullptr, nullptr};
     QHemi* h_[2] = {nullptr, nullptr};

@@ -72,6 +72,13 @@ namespace rb {
 #ifndef RB_STEP_RCP
 #define RB_STEP_RCP 0            // 1: the step to the next cube multiplies by 1/dir (kept per ray) instead of dividing
 #endif
+#ifndef RB_INTWALK
+#define RB_INTWALK 1             // 1: integer cell coordinates + top-level cell table (see walk_rays); 0: the round-1 walk
+#endif
+#if RB_INTWALK
+#undef RB_STEP_RCP
+#define RB_STEP_RCP 1            // the integer walk steps with the ray's reciprocal direction
+#endif
 #ifndef RB_PAIR_ILP
 #define RB_PAIR_ILP 1            // (ray, surface) pairs a lane has in flight in the pair loop
 #endif
@@ -318,7 +325,8 @@ struct WalkSmem {
 #endif
     double pos[3][NT];           // current position along the ray (raymove's pos)
     double rot[NT];              // current best distance
-    unsigned cell[3][NT];        // integer coordinates of the current cube at its level
+    unsigned cell[3][NT];        // integer walk: the position as depth-bit integers (cube at level L = cell >> (depth - L));
+                                 // round-1 walk: integer coordinates of the current cube at its level
     int robj[NT];                // current best object << 1 | front-facing, or -1
     unsigned ridx[NT];           // queue slot of the ray
     int lvl[NT];                 // level of the current cube | direction flags << 8
@@ -527,8 +535,24 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 sm.pos[0][tid] = px; sm.pos[1][tid] = py; sm.pos[2][tid] = pz;
                 sm.rot[tid] = rot;
                 sm.robj[tid] = -1;
+#if RB_INTWALK
+                // integer position at full depth and the cube that holds it, from the level-K cell table
+                ix = __double2uint_rd((px - S.cuorg[0]) * S.inv_cell);
+                iy = __double2uint_rd((py - S.cuorg[1]) * S.inv_cell);
+                iz = __double2uint_rd((pz - S.cuorg[2]) * S.inv_cell);
+                const unsigned top = (1u << S.maxdepth) - 1u;
+                ix = min(ix, top); iy = min(iy, top); iz = min(iz, top);
+                if (done) { w = -1; Ld = dirf << 8; }
+                else {
+                    const int sh = S.maxdepth - S.topk;
+                    const int2 e = __ldg(&S.top[(ix >> sh) | ((iy >> sh) << S.topk) | ((iz >> sh) << (2 * S.topk))]);
+                    w = e.x; Ld = (dirf << 8) | e.y;
+                    RB_STAT(ws.nodes++;)
+                }
+#else
                 ix = iy = iz = 0;
                 w = S.root; Ld = dirf << 8;
+#endif
             }
             if (last) fl |= WF_EXHAUSTED;
         }
@@ -546,6 +570,28 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
 #endif
         // ---- phase A: descend towards a leaf (raymove, raytrace.c:668-687); at most
         //      RB_DITERS levels per round ----
+#if RB_INTWALK
+        {
+            int L = Ld & 0xff;
+            const int D = S.maxdepth, K = S.topk;
+#pragma unroll 1
+            for (int it = 0; it < RB_DITERS; it++) {
+                const bool d = act & (w >= 0);
+                if (!__any_sync(FULL, d)) break;
+                if (d) {                 // the child is named by bit D-1-L of the three coordinates
+                    stk[(L - K) * NT + tid] = w;
+                    const int b = D - 1 - L;
+                    const int br = ((ix >> b) & 1) | (((iy >> b) & 1) << 1) | (((iz >> b) & 1) << 2);
+                    w = __ldg(&S.nodes[(size_t)w * 8 + br]);
+                    RB_STAT(ws.nodes++;)
+                    L++;
+                }
+            }
+            Ld = (Ld & ~0xff) | L;
+            sm.cell[0][tid] = ix; sm.cell[1][tid] = iy; sm.cell[2][tid] = iz;
+            sm.lvl[tid] = Ld;
+        }
+#else
         {
             int L = Ld & 0xff;
             double size = cube_size(cs, L);
@@ -573,6 +619,7 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
             sm.cell[0][tid] = ix; sm.cell[1][tid] = iy; sm.cell[2][tid] = iz;
             sm.lvl[tid] = Ld;
         }
+#endif
         act &= (w < 0);                          // still inside the tree: continue next round
         const bool full = act & (w < -1);
         int kleft = 0, setoff = 0;
@@ -720,9 +767,16 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
 #pragma unroll 1
             for (int cstep = 0;; cstep++) {
                 const double size = cube_size(cs, L);
+#if RB_INTWALK
+                const int sh = S.maxdepth - L;
+                const double lox = fma((double)(ix >> sh), size, S.cuorg[0]);
+                const double loy = fma((double)(iy >> sh), size, S.cuorg[1]);
+                const double loz = fma((double)(iz >> sh), size, S.cuorg[2]);
+#else
                 const double lox = fma((double)ix, size, S.cuorg[0]);
                 const double loy = fma((double)iy, size, S.cuorg[1]);
                 const double loz = fma((double)iz, size, S.cuorg[2]);
+#endif
                 const double hix = lox + size, hiy = loy + size, hiz = loz + size;
                 if (fullc ? (ro >= 0) : ((fl & WF_AFT) && ro < 0)) {
                     // checkhit (raytrace.c:756-759) / aft-plane point in an empty leaf (:709-710)
@@ -779,6 +833,41 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 }
 #endif
                 pos[0] = pos[0] + dir[0] * t; pos[1] = pos[1] + dir[1] * t; pos[2] = pos[2] + dir[2] * t;
+#if RB_INTWALK
+                // step to the neighbour (raytrace.c:688-706) on the integers: along the exit axis the position becomes
+                // the first / last depth-level cell of the neighbour cube (the carry of the increment IS the climb: the
+                // highest bit that changes names the common ancestor); along the other two axes it is the cell the new
+                // position falls in, kept inside the cube just left (the position can only be an ulp outside it)
+                {
+                    const int D = S.maxdepth, K = S.topk;
+                    const bool positive = dirf & (1 << ax);
+                    const unsigned ia = ax == 0 ? ix : ax == 1 ? iy : iz;
+                    unsigned c = ia >> sh, ipn;
+                    bool left;
+                    if (positive) { c++; left = (c >> L) != 0; ipn = c << sh; }
+                    else { left = c == 0; ipn = (c << sh) - 1u; }
+                    if (left) { done = true; if (ro >= 0) fl |= WF_RESULT; break; }    // left the scene cube
+                    const int La = D - 1 - (31 - __clz((int)(ipn ^ ia)));             // level of the common ancestor
+                    const unsigned cm = (1u << sh) - 1u;
+                    const unsigned qx = __double2uint_rd((pos[0] - S.cuorg[0]) * S.inv_cell);
+                    const unsigned qy = __double2uint_rd((pos[1] - S.cuorg[1]) * S.inv_cell);
+                    const unsigned qz = __double2uint_rd((pos[2] - S.cuorg[2]) * S.inv_cell);
+                    ix = ax == 0 ? ipn : min(max(qx, ix & ~cm), ix | cm);
+                    iy = ax == 1 ? ipn : min(max(qy, iy & ~cm), iy | cm);
+                    iz = ax == 2 ? ipn : min(max(qz, iz & ~cm), iz | cm);
+                    if (La >= K) {
+                        const int b = D - 1 - La;
+                        const int br = ((ix >> b) & 1) | (((iy >> b) & 1) << 1) | (((iz >> b) & 1) << 2);
+                        w = __ldg(&S.nodes[(size_t)stk[(La - K) * NT + tid] * 8 + br]);
+                        L = La + 1;
+                    } else {
+                        const int s2 = D - K;
+                        const int2 e = __ldg(&S.top[(ix >> s2) | ((iy >> s2) << K) | ((iz >> s2) << (2 * K))]);
+                        w = e.x; L = e.y;
+                    }
+                    RB_STAT(ws.nodes++;)
+                }
+#else
                 // step to the neighbour, ascending on overflow (raytrace.c:688-706):
                 // climb while the cell coordinate along ax cannot move that way
                 const bool positive = dirf & (1 << ax);
@@ -791,6 +880,7 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 const int br = (ix & 1) | ((iy & 1) << 1) | ((iz & 1) << 2);
                 w = __ldg(&S.nodes[(size_t)stk[(L - 1) * NT + tid] * 8 + br]);
                 RB_STAT(ws.nodes++;)
+#endif
                 if ((w != -1) | (cstep + 1 >= RB_CSTEPS)) break;
                 fullc = false;
             }

@@ -217,3 +217,30 @@ def test_oracle_cone_family_and_rayreject_vs_reference_golden(golden, tag, octf,
     np.testing.assert_allclose(r["rot"][loc], g[tag + "_dist"][loc], rtol=1e-9)
     np.testing.assert_allclose(r["ron"][loc], g[tag + "_norm"][loc], atol=1e-9)
     np.testing.assert_allclose(r["value"], g[tag + "_value"], rtol=1e-5, atol=1e-9)
+
+
+def test_device_walk_restated_on_cpu_equals_reference_walk(golden, office2k, workdir):
+    """The CUDA kernel walks the octree with integer cell coordinates, a level-K cell table in place of the
+    upper levels, the ray's reciprocal direction in the step and no checked-object set (rb_geom.cuh).
+    oracle/rb_oracle.c restates THAT walk in plain C (localhit_dev); here its answers are compared, ray by
+    ray and bit for bit, with the recursive restatement of the reference's localhit/raymove/checkhit --
+    random rays through the 2k and a 30k-surface office, the cone-family and coincident-surface fixtures
+    and the reference's own test octree (rays from outside the scene cube included)."""
+    rad, big = workdir / "off30k.rad", workdir / "off30k.oct"
+    scenegen.write_office(rad, npolys=30000, seed=9)
+    scenegen.build_octree(rad, big)
+    g = np.load(golden / "geom.npz")
+    cases = [(office2k, scenegen.random_rays(60000, seed=12)), (big, scenegen.random_rays(120000, seed=13)),
+             (golden / "geom" / "curved.oct", g["curved_rays"]), (golden / "geom" / "coinc.oct", g["coinc_rays"]),
+             (golden / "geom" / "coinc_fine.oct", g["coinc_rays"]),
+             (golden / "trace.oct", scenegen.random_rays(40000, seed=5, lo=(-5, -5, -1), hi=(45, 50, 12)))]
+    for octf, rays in cases:
+        s = port.Scene(octf)
+        a = s.rtrace(rays)
+        na = s.counters()["nodes"]
+        s.reset_counters()
+        s.set_walker(1)
+        b = s.rtrace(rays)
+        assert np.array_equal(a["robj"], b["robj"]) and np.array_equal(a["rot"], b["rot"]), octf
+        assert np.array_equal(a["ron"], b["ron"]) and np.array_equal(a["value"], b["value"])
+        assert s.counters()["nodes"] <= na            # the table replaces the upper levels: fewer node words read
