@@ -242,5 +242,5 @@ def test_device_walk_restated_on_cpu_equals_reference_walk(golden, office2k, wor
         s.set_walker(1)
         b = s.rtrace(rays)
         assert np.array_equal(a["robj"], b["robj"]) and np.array_equal(a["rot"], b["rot"]), octf
-        assert np.array_equal(a["ron"], b["ron"]) and np.array_equal(a["value"], b["value"])
+        assert np.array_equal(a["ron"], b["ron"]) and np.array_equal(a["rop"], b["rop"])     # (values draw random numbers)
         assert s.counters()["nodes"] <= na            # the table replaces the upper levels: fewer node words read
