@@ -339,7 +339,7 @@ bool Engine::upload_scene(const FlatScene& fs, const Scene& sc, std::string& err
         err = "octree is " + std::to_string(depth) + " levels deep; this engine walks at most " + std::to_string(RB_MAXDEPTH);
         return false;
     }
-    int K = 7;                                  // 8^7 cells x 8 B = 16 MB, L2-resident
+    int K = 8;                                  // 8^8 cells x 8 B = 134 MB; only the cells rays cross are ever read
     if (const char* e = getenv("RB_TOPK")) K = std::max(1, std::min(8, atoi(e)));      // developer knob
     K = std::min(K, depth);
     {

@@ -333,9 +333,22 @@ struct WalkSmem {
     unsigned pair[NT / 32][RB_PAIRS];   // (ray, surface) pairs of this round: leaf-set entry << 5 | owner lane
     int ndef[NT / 32];           // deferred (non-polygon) pairs of this round
     unsigned short defer[NT / 32][RB_PAIRS];   // their pair indices
-    double ct[NT / 32][RB_PAIRS];   // candidate distance per (ray, surface) pair
-    int cid[NT / 32][RB_PAIRS];     // candidate: object id << 1 | front, or -1
+    double ct[NT / 32][RB_PAIRS];   // candidate distance per (ray, surface) pair (written for real candidates only)
+    int cid[NT / 32][RB_PAIRS];     // candidate: object id << 1 | front
+    unsigned cmask[NT];             // per owner: bit j set = its j-th pair of this pass produced a candidate
+    unsigned char e0[NT];           // per owner: index of its first pair in the pass
 };
+static_assert(RB_OPR <= 7 && RB_PAIRS <= 255, "pair bookkeeping: 3-bit counts, byte offsets");
+
+// 1 / x to double precision without the IEEE division sequence: the hardware's 20-bit estimate and two Newton
+// steps.  Only used where the last bit does not matter (the walker's plane distances).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    r = fma(r, fma(-x, r, 1.0), r);
+    return r;
+}
 
 // One (ray, surface) pair: polygon candidates are computed here, the rare
 // other kinds are queued for the warp's second pass.
@@ -353,9 +366,11 @@ __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, uns
         const double tmax = sm.rot[own] + 8 * RB_FTINY;      // ties may raise rot by < FTINY each
         double t = 0;
         bool fr = true;
-        const bool ok = cand_face(hot, g, n01, n2o, box, org, rd, tmax, t, fr);
-        sm.ct[wid][p] = t;
-        sm.cid[wid][p] = ok ? ((RB_ENT_ID(ent.x) << 1) | (int)fr) : -1;
+        if (cand_face(hot, g, n01, n2o, box, org, rd, tmax, t, fr)) {
+            sm.ct[wid][p] = t;
+            sm.cid[wid][p] = (RB_ENT_ID(ent.x) << 1) | (int)fr;
+            atomicOr(&sm.cmask[own], 1u << (p - sm.e0[own]));
+        }
 #if RB_SPHERE_INLINE
     } else if ((kind == PK_SPHERE) | (kind == PK_BUBBLE)) {
         // o_sphere (sphere.c:16-83) on the record words the pair loop already holds (centre, radius):
@@ -377,15 +392,34 @@ __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, uns
         double t = 0.0; int i = 0;
         if (nroots >= 1 && r0 > RB_FTINY) { t = r0; i = 0; }
         else if (nroots >= 2 && r1 > RB_FTINY) { t = r1; i = 1; }
-        const bool ok = (t > 0.0) & (t <= sm.rot[own] + 8 * RB_FTINY);
-        const bool fr = !((i > 0) ^ (kind == PK_BUBBLE));
-        sm.ct[wid][p] = t;
-        sm.cid[wid][p] = ok ? ((RB_ENT_ID(ent.x) << 1) | (int)fr) : -1;
+        if ((t > 0.0) & (t <= sm.rot[own] + 8 * RB_FTINY)) {
+            const bool fr = !((i > 0) ^ (kind == PK_BUBBLE));
+            sm.ct[wid][p] = t;
+            sm.cid[wid][p] = (RB_ENT_ID(ent.x) << 1) | (int)fr;
+            atomicOr(&sm.cmask[own], 1u << (p - sm.e0[own]));
+        }
 #endif
     } else {                         // rare kinds: second pass, again with all lanes
-        sm.cid[wid][p] = -1;
         if (kind == PK_UNSUPPORTED) { atomicOr(errflag, RB_ERR_UNSUP_PRIM); *errobj = (unsigned)RB_ENT_ID(ent.x); }
         else if (kind != PK_NONE) {
+            if ((kind == PK_CYL) | (kind == PK_TUBE)) {
+                // Most rays that cross a leaf holding a thin cylinder pass it by, and the out-of-line pass below costs
+                // ~400 instructions at 2-3 live lanes.  A ray misses the INFINITE cylinder iff its distance from the axis
+                // exceeds the radius: with n = dir x axis and e = org - p0, (e.n)^2 > |n|^2 r^2 -- which is o_cone()'s own
+                // discriminant, -(b^2 - a c) > 0, written in world space (the cylinder's transform is a rotation and a
+                // translation).  Decided here only when the margin is a million times the rounding error of either
+                // form; everything closer, and every ray parallel to the axis, goes to the exact pass.
+                const double2* g2 = reinterpret_cast<const double2*>(g);
+                const double2 p01 = __ldg(&g2[2]), p2s = __ldg(&g2[3]), r01 = __ldg(&g2[4]);
+                const double dx = sm.ray[3][own], dy = sm.ray[4][own], dz = sm.ray[5][own];
+                const double ex = sm.ray[0][own] - p01.x, ey = sm.ray[1][own] - p01.y, ez = sm.ray[2][own] - p2s.x;
+                const double ax_ = n01.x, ay_ = n01.y, az_ = n2o.x;
+                const double nx = dy * az_ - dz * ay_, ny = dz * ax_ - dx * az_, nz = dx * ay_ - dy * ax_;
+                const double nn = nx * nx + ny * ny + nz * nz;
+                const double tp = ex * nx + ey * ny + ez * nz;
+                const double ee = ex * ex + ey * ey + ez * ez;
+                if (tp * tp > nn * (r01.x * r01.x) * (1.0 + 1e-6) + 1e-9 * (ee * nn) + 1e-12) return;
+            }
 #if RB_CONE_BSPHERE
             // the loader left a bounding sphere (4 floats, rounded outward) in the record's spare words: a ray
             // that passes it by, points away from it, or ends before it cannot have a candidate there
@@ -487,7 +521,7 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 sm.ray[3][tid] = dir[0]; sm.ray[4][tid] = dir[1]; sm.ray[5][tid] = dir[2];
 #if RB_STEP_RCP
 #pragma unroll
-                for (int i = 0; i < 3; i++) sm.inv[i][tid] = (fabs(dir[i]) > 1e-7) ? 1.0 / dir[i] : 1.0;
+                for (int i = 0; i < 3; i++) sm.inv[i][tid] = (fabs(dir[i]) > 1e-7) ? fast_rcp(dir[i]) : 1.0;
 #endif
                 sm.ridx[tid] = my;
                 // ---- localhit() prologue (raytrace.c:604-651) ----
@@ -648,19 +682,18 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
         for (;;) {
             if (!__any_sync(FULL, kleft > 0)) break;
             const int m0 = min(kleft, RB_OPR);
-            int incl = m0;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int v = __shfl_up_sync(FULL, incl, d);
-                if ((int)lane >= d) incl += v;
-            }
-            const int total = min(__shfl_sync(FULL, incl, 31), RB_PAIRS);
+            // exclusive prefix sum of the 3-bit counts: one ballot per bit instead of a five-step shuffle scan
+            const unsigned b0 = __ballot_sync(FULL, m0 & 1), b1 = __ballot_sync(FULL, m0 & 2), b2 = __ballot_sync(FULL, m0 & 4);
+            const unsigned lt = (1u << lane) - 1u;
+            const int e0 = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+            const int total = min(__popc(b0) + 2 * __popc(b1) + 4 * __popc(b2), RB_PAIRS);
             if (total == 0) break;
             const unsigned wbase = wid * 32;
-            const int e0 = incl - m0;
             const int m = min(m0, max(0, RB_PAIRS - e0));     // the pair table holds RB_PAIRS per pass
             for (int j = 0; j < m; j++)               // owners publish their pairs, descending set index
                 sm.pair[wid][e0 + j] = ((unsigned)(setoff + kleft - j) << 5) | lane;
+            sm.cmask[tid] = 0u;
+            sm.e0[tid] = (unsigned char)min(e0, 255);
             if (lane == 0) sm.ndef[wid] = 0;
             __syncwarp();
 #if RB_PAIR_ILP == 2
@@ -710,16 +743,18 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 if (t != 0.0) {
                     sm.ct[wid][p] = fabs(t);
                     sm.cid[wid][p] = (RB_ENT_ID(ent.x) << 1) | (int)(t > 0.0);
+                    atomicOr(&sm.cmask[own], 1u << (p - sm.e0[own]));
                 }
             }
             __syncwarp();
             // owners apply rayreject() in the reference's order (raytrace.c:535-575)
-            if (m > 0) {
+            unsigned cm = m > 0 ? sm.cmask[tid] : 0u;
+            if (cm) {
                 double rot = sm.rot[tid];
                 int ro = sm.robj[tid];
-                for (int j = 0; j < m; j++) {
+                for (; cm; cm &= cm - 1u) {           // candidates in pair order = descending object index
+                    const int j = __ffs(cm) - 1;
                     const int c = sm.cid[wid][e0 + j];
-                    if (c < 0) continue;
                     const double t = sm.ct[wid][e0 + j];
                     if ((t <= RB_FTINY) | (t > rot + RB_FTINY)) continue;
                     if (!(t < rot - RB_FTINY)) {              // coincident point, so decide...
