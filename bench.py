@@ -385,7 +385,7 @@ def run_ours(args):
         sens0 = scenegen.office_sensors(NSENS, seed=42)            # the N = 1 job
         mine, r0, r1 = rbd.local_rays(sens0, 1, rank, world)
         d_mine = torch.from_numpy(np.ascontiguousarray(mine)).to("cuda")
-        h_in = np.ascontiguousarray(mine)
+        h_in = mine.copy()                 # (its own buffer: pinning a slice of sens0 would leave sens0 half page-locked)
         ctx.pin(h_in)
         swin = rbd.RowWindow(ctx, NSENS, ncols)
         shost = rbd.SharedHostMatrix(ctx, NSENS, ncols)

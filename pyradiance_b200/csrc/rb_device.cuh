@@ -138,6 +138,7 @@ struct DCounters {
     unsigned badbin;               // bin >= nbins warnings
     unsigned next_ray;             // k_trace's persistent-thread fetch counter
     unsigned nd_out;               // parked direct() jobs (keep right after next_ray: reset together)
+    unsigned nslow;                // rays k_shade_fast left to the general k_shade (reset with the two above)
 };
 enum : unsigned { RB_ERR_UNSUP_MAT = 1, RB_ERR_UNSUP_PRIM = 2, RB_ERR_UNSUP_MOD = 4,
                   RB_ERR_LOCAL_SRC = 8, RB_ERR_DEPTH = 16, RB_ERR_CONTRIB_VALUE = 32 };

@@ -82,29 +82,60 @@ __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const Wave
 #ifndef RB_SHADE_THREADS
 #define RB_SHADE_THREADS 128
 #endif
-__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(const __grid_constant__ WaveArgs A) {
+// One queued ray -> RayCtx (hit frame included).
+__device__ __forceinline__ void load_ray(const WaveArgs& A, const QRay& q, const HitRec& hr, RayCtx& r) {
+    for (int k = 0; k < 3; k++) { r.org[k] = q.org[k]; r.dir[k] = q.dir[k]; r.coef[k] = q.coef[k]; }
+    r.rmax = q.rmax; r.rweight = q.rweight; r.row = q.row;
+    r.crtype = q.info & 0x3ff; r.rlvl = (q.info >> 10) & 0x3f; r.rdepth = (q.info >> 16) & 0x3f;
+    r.rsrc = q.rsrc;
+    r.key = ((unsigned long long)q.key_hi << 32) | q.key_lo;
+    r.nchild = 0;
+    r.med = q.med; r.re = 0.f;
+    r.robj = hr.robj; r.rot = hr.rot; r.rod = hr.rod; r.flat = false; r.xfl = 0;
+    if (hr.local) {
+        hit_frame(A.S, hr.robj, hr.rot, r.org, r.dir, r.rop, r.ron, r.rod);
+        const int hx = __ldg(&A.S.objhdr[hr.robj]).x;
+        const int kind = hx & 0xff;
+        r.flat = ((kind == PK_FACE) | (kind == PK_RING)) & !(hx & PX_NOTFLAT);
+        r.xfl = (unsigned char)((hx >> 13) & 3);          // PX_SMOOTH, PX_PHONG
+    } else {
+        for (int k = 0; k < 3; k++) { r.rop[k] = r.org[k]; r.ron[k] = -r.dir[k]; }
+    }
+}
+
+// The lean shading kernel: plastic / metal / trans without a sampled highlight, glass, plain emitters, misses --
+// nearly every ray of a daylight job -- with the rest of the material set compiled out (shade_ray<true>): no
+// out-of-line callee takes the ray by reference, so it lives in registers.  What it may not shade
+// (shade_is_simple) is left, by queue slot, to the general kernel below.
+#ifndef RB_FAST_MINBLOCKS
+#define RB_FAST_MINBLOCKS 6
+#endif
+__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_FAST_MINBLOCKS) k_shade_fast(const __grid_constant__ WaveArgs A) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < A.nin) {
+    if (i >= A.nin) return;
+    const QRay q = A.qin[i];
+    const HitRec hr = A.hits[i];
+    if (!shade_is_simple(A, q, hr)) {
+        const unsigned slot = reserve_slot(&A.C->nslow);
+        A.slow[slot] = i;
+        return;
+    }
+    if (hr.robj < 0) return;
+    RayCtx r;
+    load_ray(A, q, hr, r);
+    shade_ray<true>(A, r);
+}
+
+// The general shading kernel: every material.  With A.slow it takes the queue slots k_shade_fast left over
+// (grid-stride over a count that only the device knows), else the whole queue.
+__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(const __grid_constant__ WaveArgs A) {
+    const unsigned n = A.slow ? A.C->nslow : A.nin;
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const unsigned i = A.slow ? A.slow[j] : j;
         const QRay q = A.qin[i];
         const HitRec hr = A.hits[i];
         RayCtx r;
-        for (int k = 0; k < 3; k++) { r.org[k] = q.org[k]; r.dir[k] = q.dir[k]; r.coef[k] = q.coef[k]; }
-        r.rmax = q.rmax; r.rweight = q.rweight; r.row = q.row;
-        r.crtype = q.info & 0x3ff; r.rlvl = (q.info >> 10) & 0x3f; r.rdepth = (q.info >> 16) & 0x3f;
-        r.rsrc = q.rsrc;
-        r.key = ((unsigned long long)q.key_hi << 32) | q.key_lo;
-        r.nchild = 0;
-        r.med = q.med; r.re = 0.f;
-        r.robj = hr.robj; r.rot = hr.rot; r.rod = hr.rod; r.flat = false; r.xfl = 0;
-        if (hr.local) {
-            hit_frame(A.S, hr.robj, hr.rot, r.org, r.dir, r.rop, r.ron, r.rod);
-            const int hx = __ldg(&A.S.objhdr[hr.robj]).x;
-            const int kind = hx & 0xff;
-            r.flat = ((kind == PK_FACE) | (kind == PK_RING)) & !(hx & PX_NOTFLAT);
-            r.xfl = (unsigned char)((hx >> 13) & 3);          // PX_SMOOTH, PX_PHONG
-        } else {
-            for (int k = 0; k < 3; k++) { r.rop[k] = r.org[k]; r.ron[k] = -r.dir[k]; }
-        }
+        load_ray(A, q, hr, r);
         if (A.res && r.crtype == RT_PRIMARY) {
             RayResult& o = A.res[r.row - A.row0];
             for (int k = 0; k < 3; k++) { o.rop[k] = r.rop[k]; o.ron[k] = r.ron[k]; }
@@ -117,7 +148,7 @@ __global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(
         if (r.robj >= 0) {
             const bool front = r.rod > 0.0;
             if (r.med) ray_medium(A, r, -1);          // path extinction of an absorbing medium (rayparticipate)
-            shade_ray(A, r);
+            shade_ray<false>(A, r);
             // the material reversed a surface hit from behind (flipsurface): rtrace -on reports it that way
             if (A.res && r.crtype == RT_PRIMARY && front != (r.rod > 0.0)) A.res[r.row - A.row0].pad = 1;
         }
@@ -277,7 +308,7 @@ Engine::~Engine() {
     cudaSetDevice(dev_);
     cudaDeviceSynchronize();
     void* ptrs[] = {d_nodes_, d_leaf_, d_hdr_, d_geom_, d_mats_, d_srcs_, d_pats_, d_otrack_, d_top_, d_bins_, q_[0], q_[1],
-                    h_[0], h_[1], d_hits_, dq_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_};
+                    h_[0], h_[1], d_hits_, dq_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_, d_slow_};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_cnt_) cudaFreeHost(h_cnt_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -416,9 +447,9 @@ bool Engine::ensure_queues(std::string& err, size_t hint) {
     if (q_[0] && want <= qcap_) return true;
     if (q_[0]) {                            // grow: drop the old queues first
         CK(cudaStreamSynchronize(stream_));
-        void* old[] = {q_[0], q_[1], h_[0], h_[1], d_hits_, dq_};
+        void* old[] = {q_[0], q_[1], h_[0], h_[1], d_hits_, dq_, d_slow_};
         for (void* p : old) if (p) cudaFree(p);
-        q_[0] = q_[1] = nullptr; h_[0] = h_[1] = nullptr; d_hits_ = nullptr; dq_ = nullptr;
+        q_[0] = q_[1] = nullptr; h_[0] = h_[1] = nullptr; d_hits_ = nullptr; dq_ = nullptr; d_slow_ = nullptr;
     }
     size_t freeb = 0, totalb = 0;
     CK(cudaMemGetInfo(&freeb, &totalb));
@@ -432,6 +463,7 @@ bool Engine::ensure_queues(std::string& err, size_t hint) {
     CK(cudaMalloc(&h_[0], hcap_ * sizeof(QHemi)));
     CK(cudaMalloc(&h_[1], hcap_ * sizeof(QHemi)));
     CK(cudaMalloc(&d_hits_, qcap_ * sizeof(HitRec)));
+    CK(cudaMalloc(&d_slow_, qcap_ * sizeof(unsigned)));
     dcap_ = std::max<size_t>(qcap_ / 32, 4096);
     if (park_direct()) {      // many or local sources: direct() runs as its own kernel from a job queue
         CK(cudaMalloc(&dq_, dcap_ * sizeof(DirectJob)));
@@ -510,6 +542,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
     A.qcap = (unsigned)qcap_; A.hcap = (unsigned)hcap_;
     A.hits = d_hits_;
     A.dout = park_direct() ? dq_ : nullptr; A.dcap = (unsigned)dcap_;
+    A.slow = getenv("RB_NO_SHADE_SPLIT") ? nullptr : d_slow_;
 
     auto sync_counters = [&](std::string& err) -> bool {
         CK(cudaMemcpyAsync(h_cnt_, d_cnt_, sizeof(DCounters), cudaMemcpyDeviceToHost, stream_));
@@ -574,7 +607,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         if (nq == 0) break;
         // reset the out counters, keep the statistics
         CK(cudaMemsetAsync(&d_cnt_->nq_out, 0, 3 * sizeof(unsigned), stream_));
-        CK(cudaMemsetAsync(&d_cnt_->next_ray, 0, 2 * sizeof(unsigned), stream_));    // next_ray, nd_out
+        CK(cudaMemsetAsync(&d_cnt_->next_ray, 0, 3 * sizeof(unsigned), stream_));    // next_ray, nd_out, nslow
         A.qin = q_[cur]; A.nin = nq; A.qout = q_[cur ^ 1]; A.hout = h_[cur ^ 1];
         unsigned grid = (nq + WAVE_THREADS - 1) / WAVE_THREADS;
         unsigned tgrid = std::min<unsigned>(grid, (unsigned)trace_blocks_);
@@ -582,7 +615,12 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         k_trace<<<tgrid, WAVE_THREADS, trace_smem_, stream_>>>(A);
         CK(cudaEventRecord(ev1_, stream_));
         CK(cudaEventRecord(ev2_, stream_));
-        k_shade<<<(nq + RB_SHADE_THREADS - 1) / RB_SHADE_THREADS, RB_SHADE_THREADS, 0, stream_>>>(A);
+        if (A.slow) {
+            k_shade_fast<<<(nq + RB_SHADE_THREADS - 1) / RB_SHADE_THREADS, RB_SHADE_THREADS, 0, stream_>>>(A);
+            k_shade<<<std::min<unsigned>((nq + RB_SHADE_THREADS - 1) / RB_SHADE_THREADS, 148u * 4u), RB_SHADE_THREADS, 0, stream_>>>(A);
+            stats.launches++;
+        } else
+            k_shade<<<(nq + RB_SHADE_THREADS - 1) / RB_SHADE_THREADS, RB_SHADE_THREADS, 0, stream_>>>(A);
         CK(cudaEventRecord(ev3_, stream_));
         stats.launches += 2; stats.wave_launches++; stats.waves++;
         batch_rays += nq;                       // every queued ray is traced exactly once

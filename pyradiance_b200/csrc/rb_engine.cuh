@@ -88,6 +88,7 @@ private:
     RayResult* d_res_ = nullptr; size_t res_bytes_ = 0;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev2_ = nullptr, ev3_ = nullptr;
     HitRec* d_hits_ = nullptr;
+    unsigned* d_slow_ = nullptr;          // queue slots left to the general shading kernel
     int trace_blocks_ = 148;
     size_t trace_smem_ = 0;      // dynamic shared memory of k_trace (ancestor stack)
     bool has_local_sources_ = false;

@@ -64,6 +64,7 @@ struct WaveArgs {
     DCounters* C;
     int inline_hemi_max;    // hemispheres with n*n <= this are expanded in-thread
     DirectJob* dout; unsigned dcap;   // parked direct() calculations (null: sources are walked in-thread)
+    unsigned* slow;         // [qcap] queue slots k_shade_fast leaves to the general k_shade (null: no split)
 };
 
 struct RayCtx {             // the ray being shaded (a subset of RAY, rt/ray.h:48-83)
@@ -827,6 +828,10 @@ __device__ __forceinline__ double raynormal(double norm[3], const RayCtx& r, con
     return newdot;
 }
 
+// FAST (k_shade_fast): the caller guarantees a PURE-specular material (roughness^2 <= FTINY) on a surface without
+// vertex normals, so the sampled-highlight code and the normal perturbation are compiled out; everything a FAST
+// instantiation does execute is the same code, on the same values, as the general one.
+template <bool FAST = false>
 __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind, const float* a) {
     const DParams& P = A.P;
     if ((r.crtype & RT_SHADOW) && mkind != MK_TRANS) return;      // easy shadow test
@@ -843,8 +848,8 @@ __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind
     if ((nd.alpha2 *= nd.alpha2) <= RB_FTINY) nd.specfl |= SP_PURE;
     nd.pnorm[0] = r.ron[0]; nd.pnorm[1] = r.ron[1]; nd.pnorm[2] = r.ron[2];
     nd.pdot = r.rod;
-    double pert[3];
-    const bool hastexture = ray_pert(A.S, r, flipped, pert);       // normal.c:221-226
+    double pert[3] = {0., 0., 0.};
+    const bool hastexture = FAST ? false : ray_pert(A.S, r, flipped, pert);       // normal.c:221-226
     if (hastexture) nd.pdot = raynormal(nd.pnorm, r, pert);
     if (!hastexture && r.robj >= 0 && r.flat) nd.specfl |= SP_FLAT;
     if (nd.pdot < .001) nd.pdot = .001;
@@ -907,7 +912,7 @@ __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind
         }
     }
     if ((nd.specfl & SP_PURE) && nd.rdiff <= RB_FTINY && nd.tdiff <= RB_FTINY) return;
-    if (!(nd.specfl & SP_PURE)) {
+    if (!FAST && !(nd.specfl & SP_PURE)) {
         // gaussamp(), normal.c:363-495, single-sample form (-ss <= 1.5)
         unsigned long long gkey = child_key(r.key, r.nchild++);
         double u[3], v[3];
@@ -1163,6 +1168,7 @@ __device__ __noinline__ void m_dielectric(const WaveArgs& A, RayCtx& r, int mkin
 }
 
 // glass.c:46-165
+template <bool FAST = false>
 __device__ __forceinline__ void m_glass(const WaveArgs& A, RayCtx& r, const float* a, int nargs) {
     const DParams& P = A.P;
     double rindex = (nargs == 4) ? (double)a[3] : 1.52;
@@ -1174,8 +1180,8 @@ __device__ __forceinline__ void m_glass(const WaveArgs& A, RayCtx& r, const floa
     bool flipped = false;
     if (r.rod < 0.0) { r.rod = -r.rod; r.ron[0] = -r.ron[0]; r.ron[1] = -r.ron[1]; r.ron[2] = -r.ron[2]; flipped = true; }
     double pdot = r.rod;
-    double pnorm[3] = {r.ron[0], r.ron[1], r.ron[2]}, pert[3];
-    const bool hastexture = ray_pert(A.S, r, flipped, pert);       // glass.c:91-98
+    double pnorm[3] = {r.ron[0], r.ron[1], r.ron[2]}, pert[3] = {0., 0., 0.};
+    const bool hastexture = FAST ? false : ray_pert(A.S, r, flipped, pert);       // glass.c:91-98
     if (hastexture) pdot = raynormal(pnorm, r, pert);
     double cos2 = sqrt((1.0 - 1.0 / (rindex * rindex)) + pdot * pdot / (rindex * rindex));
     if (hastrans)
@@ -1253,6 +1259,7 @@ __device__ __noinline__ double sky_pattern(const PatRec& p, const double dir[3])
 
 // source.c:749-793 m_light.  Returns 1 and sets rcol when the ray sees the
 // emitter, 0 when its coefficient is zeroed / it is passed on.
+template <bool FAST = false>
 __device__ __forceinline__ int m_light(const WaveArgs& A, RayCtx& r, const MatRec& m, float rcol[3], bool& zeroed) {
     const DScene& S = A.S;
     zeroed = false;
@@ -1290,11 +1297,11 @@ __device__ __forceinline__ int m_light(const WaveArgs& A, RayCtx& r, const MatRe
             if (spotout(sp, r.org, r.dir)) return 0;
         }
     }
-    if ((m.flags & 1) && A.P.need_values) {       // pattern under an emitter only matters for values
+    if (!FAST && (m.flags & 1) && A.P.need_values) {       // pattern under an emitter only matters for values
         atomicOr(&A.C->errflag, RB_ERR_UNSUP_MOD); A.C->errobj = (unsigned)m.obj;
     }
     rcol[0] = m.a[0]; rcol[1] = m.a[1]; rcol[2] = m.a[2];
-    if (m.pat >= 0) {                             // raytexture(r, m->omod): sky brightness functions
+    if (!FAST && m.pat >= 0) {                    // raytexture(r, m->omod): sky brightness functions
         float pcol = 1.f;
         for (int pi = m.pat; pi >= 0; pi = S.pats[pi].next) pcol *= (float)sky_pattern(S.pats[pi], r.dir);
         rcol[0] *= pcol; rcol[1] *= pcol; rcol[2] *= pcol;
@@ -1303,6 +1310,7 @@ __device__ __forceinline__ int m_light(const WaveArgs& A, RayCtx& r, const MatRe
 }
 
 // rayshade() + trace callback for one traced ray (raytrace.c:162-179,210-256)
+template <bool FAST = false>
 __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
     const DScene& S = A.S;
     int4 hd = __ldg(&S.objhdr[r.robj]);
@@ -1330,10 +1338,12 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
             if (!(k >= MK_LIGHT && k <= MK_SPOT)) { nk = MK_PLASTIC; for (int j = 0; j < 7; j++) na[j] = j < 3 ? (float)RB_PI : 0.f; break; }
         }
         if (k == MK_PLASTIC || k == MK_METAL || k == MK_TRANS) { nk = k; for (int j = 0; j < 7; j++) na[j] = m->a[j]; break; }
-        if (k == MK_GLASS) { m_glass(A, r, m->a, m->nargs); break; }
-        if (k >= MK_PLASTIC2 && k <= MK_TRANS2) { m_aniso(A, r, k, m->a, m->u); break; }
-        if (k == MK_DIELECTRIC || k == MK_INTERFACE) { m_dielectric(A, r, k, (int)(m - S.mats), m->a); break; }
-        int rv = m_light(A, r, *m, rcol, zeroed);
+        if (k == MK_GLASS) { m_glass<FAST>(A, r, m->a, m->nargs); break; }
+        if (!FAST) {
+            if (k >= MK_PLASTIC2 && k <= MK_TRANS2) { m_aniso(A, r, k, m->a, m->u); break; }
+            if (k == MK_DIELECTRIC || k == MK_INTERFACE) { m_dielectric(A, r, k, (int)(m - S.mats), m->a); break; }
+        }
+        int rv = m_light<FAST>(A, r, *m, rcol, zeroed);
         if (rv == 1) {
             have_rcol = true;
             add_value(A, r.row, r.coef, rcol[0], rcol[1], rcol[2]);
@@ -1347,8 +1357,29 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
         }
         break;
     }
-    if (nk >= 0) m_normal(A, r, nk, na);
+    if (nk >= 0) m_normal<FAST>(A, r, nk, na);
     trace_contrib(A, r, zeroed, rcol, have_rcol);
+}
+
+// Which queued rays the lean kernel may shade: exactly those whose shading never enters the code it leaves out
+// (mirrors the decisions of shade_ray() / m_normal() above; anything unusual says "no").
+__device__ __forceinline__ bool shade_is_simple(const WaveArgs& A, const QRay& q, const HitRec& hr) {
+    if (q.med) return false;                                  // absorbing medium: ray_medium()
+    const int crtype = q.info & 0x3ff;
+    if (A.res && crtype == RT_PRIMARY) return false;          // primary-hit report (smooth_pert, flip flag)
+    if (hr.robj < 0) return true;                             // nothing to shade
+    const int4 hd = __ldg(&A.S.objhdr[hr.robj]);
+    if (hr.local && ((hd.x >> 13) & 3)) return false;         // vertex normals / Phong modifier
+    if (hd.z < 0) return true;                                // no material: raytrans()
+    const MatRec& m = A.S.mats[hd.z];
+    const int k = m.kind;
+    if (k == MK_UNSUPPORTED || (m.flags & 3)) return false;   // error paths and patterns
+    const bool emitter = k >= MK_LIGHT && k <= MK_SPOT;
+    if (A.P.do_irrad && !(crtype & ~(RT_PRIMARY | RT_TRANS)) && !emitter) return true;    // raytirrad(): passes through or Lambertian
+    if (k == MK_PLASTIC || k == MK_METAL || k == MK_TRANS) { double a2 = m.a[4]; a2 *= a2; return a2 <= RB_FTINY; }
+    if (k == MK_GLASS) return true;
+    if (emitter) return k != MK_ILLUM && m.pat < 0;
+    return false;
 }
 
 }  // namespace rb
