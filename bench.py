@@ -357,7 +357,9 @@ def run_ours(args):
     sampler.start()
     ms = timed(step_device, args.steps)
     st = ctx.stats()
+    ctx.reset_stats()
     ms_e2e = timed(step_host, args.steps)
+    st_e2e = ctx.stats()
     sampler.stop_.set()
     sampler.join(timeout=2)
     if world > 1:
@@ -373,8 +375,13 @@ def run_ours(args):
 
     rays_local = st["nrays"]
     tot = torch.tensor([float(rays_local)], device="cuda", dtype=torch.float64)
+    per_rank = torch.tensor([st["kernel_ms"] / args.steps, st["wave_ms"] / args.steps, float(st["launches"]) / args.steps],
+                            device="cuda", dtype=torch.float64)
+    per_rank_all = [per_rank.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_gather(per_rank_all, per_rank)
+    per_rank_all = [[float(x) for x in t.tolist()] for t in per_rank_all]
     rays_all = float(tot.item())
     value = rays_all / (ms / 1e3)
     e2e_value = rays_all / (ms_e2e / 1e3)
@@ -504,8 +511,12 @@ def run_ours(args):
             "sensors_per_s": NSENS * world * args.steps / (ms / 1e3),
             "rays_per_sensor": rays_local / args.steps / NSENS, "rays_per_sensor_oracle": oc["rays_per_sensor"],
             "rays_per_step_per_gpu": rays_local / args.steps, "dc_matrix_wall_ms": ms / args.steps,
+            "per_rank": {"kernel_ms_per_step": [r[0] for r in per_rank_all], "k_trace_ms_per_step": [r[1] for r in per_rank_all],
+                         "launches_per_step": [r[2] for r in per_rank_all],
+                         "outside_kernels_ms_per_step": ms / args.steps - max(r[0] for r in per_rank_all)},
             "librb200_sha16": file_sha16(_lib.LIB_PATH),
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "kernel_ms_per_step": st_e2e["kernel_ms"] / args.steps, "batches_per_step": st_e2e["batches"] / args.steps,
                     "h2d_bytes_per_step": int(h_rays.nbytes) * world, "d2h_bytes_per_step": int(NSENS * ncols * 12) * world,
                     "path": "pinned host rays -> rb_rcontrib -> rows D2H into " +
                             ("one shared pinned host matrix (dist.SharedHostMatrix), barrier" if world > 1 else "a pinned host matrix")},

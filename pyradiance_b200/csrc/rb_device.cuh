@@ -139,6 +139,11 @@ struct DCounters {
     unsigned next_ray;             // k_trace's persistent-thread fetch counter
     unsigned nd_out;               // parked direct() jobs (keep right after next_ray: reset together)
     unsigned nslow;                // rays k_shade_fast left to the general k_shade (reset with the two above)
+    // wave chaining without the host (rb_engine.cu k_gate / k_prepare): what the kernels of the current wave read
+    unsigned nin;                  // rays in the input queue of this wave
+    unsigned nh_in, nd_in;         // hemispheres / parked direct() jobs to expand before it
+    unsigned long long rays_traced;   // sum of nin over the waves of the batch
+    unsigned wave_nin[64];         // nin of the last waves (slot = wave index & 63), for the host's statistics
 };
 enum : unsigned { RB_ERR_UNSUP_MAT = 1, RB_ERR_UNSUP_PRIM = 2, RB_ERR_UNSUP_MOD = 4,
                   RB_ERR_LOCAL_SRC = 8, RB_ERR_DEPTH = 16, RB_ERR_CONTRIB_VALUE = 32 };

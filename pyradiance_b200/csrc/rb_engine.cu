@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const Wave
     __shared__ WalkSmem<WAVE_THREADS> sm;
     extern __shared__ int stk_dyn[];         // [maxdepth + 1][WAVE_THREADS]
     TraceIO io;
-    io.qin = A.qin; io.nin = A.nin; io.hits = A.hits; io.next = &A.C->next_ray;
+    io.qin = A.qin; io.nin = A.C->nin; io.hits = A.hits; io.next = &A.C->next_ray;
     WalkStats ws = {0, 0, 0};
     walk_rays<WAVE_THREADS>(A.S, io, sm, stk_dyn, ws, &A.C->errflag, &A.C->errobj);
 #if RB_WALK_STATS
@@ -110,9 +110,9 @@ __device__ __forceinline__ void load_ray(const WaveArgs& A, const QRay& q, const
 #ifndef RB_FAST_MINBLOCKS
 #define RB_FAST_MINBLOCKS 6
 #endif
-__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_FAST_MINBLOCKS) k_shade_fast(const __grid_constant__ WaveArgs A) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.nin) return;
+// (the body is a function of its own so that the grid-stride loop around it -- the ray count is known only on the
+//  device -- does not add to the register pressure of the shading code: inlined, the loop tripled the spills)
+__device__ __noinline__ void shade_fast_one(const WaveArgs& A, unsigned i) {
     const QRay q = A.qin[i];
     const HitRec hr = A.hits[i];
     if (!shade_is_simple(A, q, hr)) {
@@ -125,11 +125,15 @@ __global__ void __launch_bounds__(RB_SHADE_THREADS, RB_FAST_MINBLOCKS) k_shade_f
     load_ray(A, q, hr, r);
     shade_ray<true>(A, r);
 }
+__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_FAST_MINBLOCKS) k_shade_fast(const __grid_constant__ WaveArgs A) {
+    const unsigned n = A.C->nin;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) shade_fast_one(A, i);
+}
 
 // The general shading kernel: every material.  With A.slow it takes the queue slots k_shade_fast left over
 // (grid-stride over a count that only the device knows), else the whole queue.
 __global__ void __launch_bounds__(RB_SHADE_THREADS, RB_SHADE_MINBLOCKS) k_shade(const __grid_constant__ WaveArgs A) {
-    const unsigned n = A.slow ? A.C->nslow : A.nin;
+    const unsigned n = A.slow ? A.C->nslow : A.C->nin;
     for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
         const unsigned i = A.slow ? A.slow[j] : j;
         const QRay q = A.qin[i];
@@ -226,13 +230,13 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_init(const WaveArgs A, const I
 // source per thread and pass (source.c:398-556 with every source tested).
 struct DirectArgs {
     const DirectJob* din;
-    unsigned nd;
 };
 
 __global__ void __launch_bounds__(256) k_direct(const __grid_constant__ WaveArgs A, const DirectArgs D) {
     __shared__ DirectJob sj;
     const int ns = A.S.nsrcs;
-    for (unsigned job = blockIdx.x; job < D.nd; job += gridDim.x) {
+    const unsigned njobs = A.C->nd_in;
+    for (unsigned job = blockIdx.x; job < njobs; job += gridDim.x) {
         __syncthreads();
         {   // cooperative copy of the job record
             const unsigned* src = reinterpret_cast<const unsigned*>(D.din + job);
@@ -250,11 +254,32 @@ __global__ void __launch_bounds__(256) k_direct(const __grid_constant__ WaveArgs
 
 struct ExpandArgs {
     const QHemi* hin;
-    unsigned nh;
 };
 
+// The wave loop runs on the device's own counters: the host queues the kernels of several waves ahead and looks at
+// the counters once per chunk (run_batch).  k_gate opens a wave: what the previous wave's shading produced becomes
+// this wave's hemispheres / parked direct() jobs, unless the rays they will expand into would not fit the queue
+// (then the batch stops with the overflow flag and the host retries it smaller).  k_prepare, after the expansion,
+// turns the filled queue into the wave's input.
+__global__ void k_gate(DCounters* C, unsigned qcap) {
+    if (C->overflow || C->errflag || (size_t)C->nq_out + C->hemi_rays > qcap) {
+        if (!C->errflag && !C->overflow) C->overflow = 1;
+        C->nh_in = 0; C->nd_in = 0; C->nq_out = 0;
+    } else {
+        C->nh_in = C->nh_out; C->nd_in = C->nd_out;
+    }
+    C->nh_out = 0; C->nd_out = 0; C->hemi_rays = 0;
+}
+__global__ void k_prepare(DCounters* C, unsigned wave) {
+    const unsigned n = (C->overflow || C->errflag) ? 0u : C->nq_out;
+    C->nin = n; C->nq_out = 0; C->next_ray = 0; C->nslow = 0;
+    C->rays_traced += n;
+    C->wave_nin[wave & 63] = n;
+}
+
 __global__ void __launch_bounds__(256) k_expand(const WaveArgs A, const ExpandArgs E) {
-    for (unsigned job = blockIdx.x; job < E.nh; job += gridDim.x) {
+    const unsigned nh = A.C->nh_in;
+    for (unsigned job = blockIdx.x; job < nh; job += gridDim.x) {
         const QHemi h = E.hin[job];
         unsigned long long hkey = ((unsigned long long)h.key_hi << 32) | h.key_lo;
         double onrm[3] = {h.onrm[0], h.onrm[1], h.onrm[2]}, ux[3], uy[3];
@@ -315,6 +340,7 @@ Engine::~Engine() {
     if (ev1_) cudaEventDestroy(ev1_);
     if (ev2_) cudaEventDestroy(ev2_);
     if (ev3_) cudaEventDestroy(ev3_);
+    for (auto& e : wev_) if (e) cudaEventDestroy(e);
     if (own_stream_) cudaStreamDestroy(own_stream_);
 }
 
@@ -572,72 +598,80 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         CK(cudaEventRecord(ev1_, stream_));
         stats.launches++;
         CK(cudaGetLastError());
-        if (!sync_counters(err) || !timed(stats.kernel_ms, err)) return false;
     }
-    unsigned nq = h_cnt_->nq_out, nh = h_cnt_->nh_out, nd = h_cnt_->nd_out;
-    for (int wave = 0; wave < 4096; wave++) {
-        if (h_cnt_->overflow || (size_t)nq + h_cnt_->hemi_rays > qcap_) { overflow = true; return true; }
+    // ---- waves ----
+    // Every kernel of a wave takes its counts from the device (k_gate / k_prepare), so the host may queue waves ahead.
+    // It does so for SMALL waves, where a host round trip per wave would be most of the time (chunks of up to 8 waves,
+    // grid-stride launches).  A LARGE wave is launched alone, with the one-thread-per-ray grid its known upper bound
+    // gives (27 % faster shading than the grid-stride form) and one look at the counters after it.
+    const int kChunkMax = 8;
+    const size_t kSmallWave = (size_t)1 << 19;
+    if (!wev_[0]) for (auto& e : wev_) CK(cudaEventCreate(&e));
+    unsigned fgrid = 148u * 12u;                   // grid-stride kernels: the count is only known on the device
+    if (const char* e = getenv("RB_FGRID")) fgrid = 148u * (unsigned)std::max(1, atoi(e));      // developer knob
+    if (!sync_counters(err)) return false;         // what k_init produced
+    { float ms = 0; CK(cudaEventElapsedTime(&ms, ev0_, ev1_)); stats.kernel_ms += ms; }
+    bool finished = h_cnt_->nq_out == 0 && h_cnt_->nh_out == 0 && h_cnt_->nd_out == 0;
+    int wave = 0;
+    while (!finished && wave < 4096) {
+        if (h_cnt_->overflow) { overflow = true; return true; }
         if (h_cnt_->errflag) break;
-        if (nh > 0) {                         // expand hemispheres into the current queue
-            ExpandArgs E; E.hin = h_[cur]; E.nh = nh;
+        // upper bound of the coming wave: queued rays + the rays its hemispheres reserved + a shadow ray per parked
+        // direct() job and source sample (local sources split into at most 64 partitions, srcsamp.c MAXSPART)
+        size_t ub = (size_t)h_cnt_->nq_out + h_cnt_->hemi_rays +
+                    (size_t)h_cnt_->nd_out * (size_t)std::max(1, S_.nsrcs) * (has_local_sources_ ? 64 : 1);
+        ub = std::min(ub, qcap_);
+        const bool big = ub >= kSmallWave;
+        const int chunk = big ? 1 : kChunkMax;
+        const unsigned sgrid = big ? (unsigned)((ub + RB_SHADE_THREADS - 1) / RB_SHADE_THREADS) : fgrid;
+        const unsigned egrid = std::max(1u, std::min<unsigned>(big ? h_cnt_->nh_out : 148u * 8u, 148u * 8u));
+        const unsigned dgrid = std::max(1u, std::min<unsigned>(big ? h_cnt_->nd_out : 148u * 8u, 148u * 8u));
+        const int w0 = wave;
+        for (int k = 0; k < chunk; k++, wave++) {
+            CK(cudaEventRecord(wev_[4 * k + 3], stream_));
+            k_gate<<<1, 1, 0, stream_>>>(d_cnt_, (unsigned)qcap_);
+            ExpandArgs E; E.hin = h_[cur];
             A.qout = q_[cur];
-            unsigned grid = std::min<unsigned>(nh, 148u * 8u);
-            CK(cudaEventRecord(ev0_, stream_));
-            k_expand<<<grid, 256, 0, stream_>>>(A, E);
-            CK(cudaEventRecord(ev1_, stream_));
-            stats.launches++;
-            CK(cudaGetLastError());
-            if (!sync_counters(err) || !timed(stats.kernel_ms, err)) return false;
-            if (h_cnt_->overflow) { overflow = true; return true; }
-            nq = h_cnt_->nq_out;
+            k_expand<<<egrid, 256, 0, stream_>>>(A, E);
+            stats.launches += 2;
+            if (park_direct()) {
+                DirectArgs D; D.din = dq_;
+                k_direct<<<dgrid, 256, 0, stream_>>>(A, D);
+                stats.launches++;
+            }
+            k_prepare<<<1, 1, 0, stream_>>>(d_cnt_, (unsigned)wave);
+            A.qin = q_[cur]; A.nin = 0; A.qout = q_[cur ^ 1]; A.hout = h_[cur ^ 1];
+            CK(cudaEventRecord(wev_[4 * k + 0], stream_));
+            k_trace<<<(unsigned)trace_blocks_, WAVE_THREADS, trace_smem_, stream_>>>(A);
+            CK(cudaEventRecord(wev_[4 * k + 1], stream_));
+            if (A.slow) {
+                k_shade_fast<<<sgrid, RB_SHADE_THREADS, 0, stream_>>>(A);
+                k_shade<<<148u * 4u, RB_SHADE_THREADS, 0, stream_>>>(A);
+                stats.launches++;
+            } else
+                k_shade<<<sgrid, RB_SHADE_THREADS, 0, stream_>>>(A);
+            CK(cudaEventRecord(wev_[4 * k + 2], stream_));
+            stats.launches += 3;
+            cur ^= 1;
         }
-        if (nd > 0) {                         // parked direct() calculations: shadow rays into the current queue
-            DirectArgs D; D.din = dq_; D.nd = nd;
-            A.qout = q_[cur];
-            unsigned grid = std::min<unsigned>(nd, 148u * 8u);
-            CK(cudaEventRecord(ev0_, stream_));
-            k_direct<<<grid, 256, 0, stream_>>>(A, D);
-            CK(cudaEventRecord(ev1_, stream_));
-            stats.launches++;
-            CK(cudaGetLastError());
-            if (!sync_counters(err) || !timed(stats.kernel_ms, err)) return false;
-            if (h_cnt_->overflow) { overflow = true; return true; }
-            nq = h_cnt_->nq_out;
-        }
-        if (nq == 0) break;
-        // reset the out counters, keep the statistics
-        CK(cudaMemsetAsync(&d_cnt_->nq_out, 0, 3 * sizeof(unsigned), stream_));
-        CK(cudaMemsetAsync(&d_cnt_->next_ray, 0, 3 * sizeof(unsigned), stream_));    // next_ray, nd_out, nslow
-        A.qin = q_[cur]; A.nin = nq; A.qout = q_[cur ^ 1]; A.hout = h_[cur ^ 1];
-        unsigned grid = (nq + WAVE_THREADS - 1) / WAVE_THREADS;
-        unsigned tgrid = std::min<unsigned>(grid, (unsigned)trace_blocks_);
-        CK(cudaEventRecord(ev0_, stream_));
-        k_trace<<<tgrid, WAVE_THREADS, trace_smem_, stream_>>>(A);
-        CK(cudaEventRecord(ev1_, stream_));
-        CK(cudaEventRecord(ev2_, stream_));
-        if (A.slow) {
-            k_shade_fast<<<(nq + RB_SHADE_THREADS - 1) / RB_SHADE_THREADS, RB_SHADE_THREADS, 0, stream_>>>(A);
-            k_shade<<<std::min<unsigned>((nq + RB_SHADE_THREADS - 1) / RB_SHADE_THREADS, 148u * 4u), RB_SHADE_THREADS, 0, stream_>>>(A);
-            stats.launches++;
-        } else
-            k_shade<<<(nq + RB_SHADE_THREADS - 1) / RB_SHADE_THREADS, RB_SHADE_THREADS, 0, stream_>>>(A);
-        CK(cudaEventRecord(ev3_, stream_));
-        stats.launches += 2; stats.wave_launches++; stats.waves++;
-        batch_rays += nq;                       // every queued ray is traced exactly once
         CK(cudaGetLastError());
         if (!sync_counters(err)) return false;
-        {
-            float ms = 0, ms2 = 0;
-            CK(cudaEventElapsedTime(&ms, ev0_, ev1_));
-            CK(cudaEventElapsedTime(&ms2, ev2_, ev3_));
-            stats.kernel_ms += ms + ms2; stats.wave_ms += ms; stats.shade_ms += ms2;
+        for (int k = 0; k < chunk; k++) {
+            const unsigned n = h_cnt_->wave_nin[(w0 + k) & 63];
+            float ms = 0, ms2 = 0, ms0 = 0;
+            CK(cudaEventElapsedTime(&ms0, wev_[4 * k + 3], wev_[4 * k + 0]));     // gate, expand, direct, prepare
+            CK(cudaEventElapsedTime(&ms, wev_[4 * k + 0], wev_[4 * k + 1]));
+            CK(cudaEventElapsedTime(&ms2, wev_[4 * k + 1], wev_[4 * k + 2]));
+            stats.kernel_ms += ms0 + ms + ms2;
+            if (n) { stats.wave_ms += ms; stats.shade_ms += ms2; stats.wave_launches++; stats.waves++; }
             if (getenv("RB_DEBUG_WAVES"))
-                fprintf(stderr, "[rb] wave %d: %u rays trace %.3f ms shade %.3f ms -> %u rays, %u hemis\n", wave, nq, ms, ms2,
-                        h_cnt_->nq_out, h_cnt_->nh_out);
+                fprintf(stderr, "[rb] wave %d: %u rays (bound %zu) trace %.3f ms shade %.3f ms\n", w0 + k, n, ub, ms, ms2);
         }
-        cur ^= 1;
-        nq = h_cnt_->nq_out; nh = h_cnt_->nh_out; nd = h_cnt_->nd_out;
+        finished = h_cnt_->nq_out == 0 && h_cnt_->nh_out == 0 && h_cnt_->nd_out == 0;
     }
+    if (h_cnt_->overflow) { overflow = true; return true; }
+    batch_rays = h_cnt_->rays_traced;
+    const unsigned nq = h_cnt_->nq_out, nh = h_cnt_->nh_out, nd = h_cnt_->nd_out;
     if (!h_cnt_->errflag && (nq > 0 || nh > 0 || nd > 0)) {
         err = "ray generations did not end after 4096 waves (" + std::to_string(nq) + " rays still queued)";
         return false;

@@ -87,6 +87,7 @@ private:
     char* d_out_ = nullptr; size_t out_bytes_ = 0;
     RayResult* d_res_ = nullptr; size_t res_bytes_ = 0;
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr, ev2_ = nullptr, ev3_ = nullptr;
+    cudaEvent_t wev_[32] = {};            // per-wave events of a chunk of queued-ahead waves (4 per wave)
     HitRec* d_hits_ = nullptr;
     unsigned* d_slow_ = nullptr;          // queue slots left to the general shading kernel
     int trace_blocks_ = 148;
