@@ -74,6 +74,12 @@ __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const Wave
     flush_stats(A.C, ws);
 #endif
 }
+#if RB_WALK_STATS
+__global__ void k_dbg_print() {
+    printf("[rb dbg] cyl pairs %llu, after the axis test %llu, after the end test %llu, candidates %llu; sphere pairs %llu, with roots %llu\n",
+           g_dbg[0], g_dbg[1], g_dbg[5], g_dbg[2], g_dbg[3], g_dbg[4]);
+}
+#endif
 
 // Shade: material evaluation, contribution accumulation, child-ray emission.
 #ifndef RB_SHADE_MINBLOCKS
@@ -689,6 +695,9 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
         else err = "unsupported modifier on " + what + " reached by a ray (patterns/textures/mixtures are not built)";
         return false;
     }
+#if RB_WALK_STATS
+    if (getenv("RB_DEBUG_DBG")) { k_dbg_print<<<1, 1, 0, stream_>>>(); cudaStreamSynchronize(stream_); }
+#endif
     stats.nrays += batch_rays; stats.nodes += h_cnt_->nodes; stats.leafents += h_cnt_->leafents;
     stats.prims += h_cnt_->prims; stats.contribs += h_cnt_->contribs; stats.badbin += h_cnt_->badbin;
     // ---- outputs ----

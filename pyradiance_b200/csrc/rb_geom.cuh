@@ -301,6 +301,12 @@ __device__ __forceinline__ void hit_frame(const DScene& S, int robj, double rot,
 }
 
 struct WalkStats { unsigned nodes, leafents, prims; };
+#if RB_WALK_STATS
+__device__ unsigned long long g_dbg[8];     // developer counters: cylinder pairs, after the in-line miss test, candidates; sphere pairs, candidates
+#define RB_DBG(i) atomicAdd(&g_dbg[i], 1ULL)
+#else
+#define RB_DBG(i)
+#endif
 
 // sourcehit() lives in rb_shade.cuh; declared here for the retire step
 __device__ __forceinline__ int sourcehit(const DScene& S, const double dir[3], int rsrc, int crtype);
@@ -389,6 +395,7 @@ __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, uns
         c -= n2o.y * n2o.y;
         double r0, r1;
         const int nroots = quadratic(r0, r1, a, b, c);
+        RB_DBG(3); if (nroots) RB_DBG(4);
         double t = 0.0; int i = 0;
         if (nroots >= 1 && r0 > RB_FTINY) { t = r0; i = 0; }
         else if (nroots >= 2 && r1 > RB_FTINY) { t = r1; i = 1; }
@@ -403,6 +410,7 @@ __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, uns
         if (kind == PK_UNSUPPORTED) { atomicOr(errflag, RB_ERR_UNSUP_PRIM); *errobj = (unsigned)RB_ENT_ID(ent.x); }
         else if (kind != PK_NONE) {
             if ((kind == PK_CYL) | (kind == PK_TUBE)) {
+                RB_DBG(0);
                 // Most rays that cross a leaf holding a thin cylinder pass it by, and the out-of-line pass below costs
                 // ~400 instructions at 2-3 live lanes.  A ray misses the INFINITE cylinder iff its distance from the axis
                 // exceeds the radius: with n = dir x axis and e = org - p0, (e.n)^2 > |n|^2 r^2 -- which is o_cone()'s own
@@ -419,6 +427,21 @@ __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, uns
                 const double tp = ex * nx + ey * ny + ez * nz;
                 const double ee = ex * ex + ey * ey + ez * ez;
                 if (tp * tp > nn * (r01.x * r01.x) * (1.0 + 1e-6) + 1e-9 * (ee * nn) + 1e-12) return;
+                RB_DBG(1);
+                // ... and the ends: both roots lie within r / |n| of the ray's closest approach to the axis (t_c), so
+                // their heights along the axis lie within |d.axis| r / |n| of the height there.  With everything scaled
+                // by |n|^2 = nn (and sqrt(nn) <= 1 bounding the half width from above): a ray whose whole root interval
+                // is below the base or above the top (o_cone()'s `0 <= b <= al` test) misses.
+                {
+                    const double al = n2o.y;                                    // g[3]: length of the axis
+                    const double da = dx * ax_ + dy * ay_ + dz * az_;           // dir . axis
+                    const double ea = ex * ax_ + ey * ay_ + ez * az_;           // height of the origin above the base
+                    const double ed = ex * dx + ey * dy + ez * dz;
+                    const double zc = ea * nn - (ed - ea * da) * da;            // height at t_c, times nn
+                    const double hw = fabs(da) * r01.x * (1.0 + 1e-6) + 1e-9 * (ee + al + 1.0) + 1e-12;
+                    if ((zc + hw < 0.0) | (zc - hw > al * nn)) return;
+                }
+                RB_DBG(5);
             }
 #if RB_CONE_BSPHERE
             // the loader left a bounding sphere (4 floats, rounded outward) in the record's spare words: a ray
@@ -741,6 +764,7 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 const double t = cand_other(kind, g, sm.ray[0][own], sm.ray[1][own], sm.ray[2][own], sm.ray[3][own],
                                             sm.ray[4][own], sm.ray[5][own], sm.rot[own] + 8 * RB_FTINY);
                 if (t != 0.0) {
+                    RB_DBG(2);
                     sm.ct[wid][p] = fabs(t);
                     sm.cid[wid][p] = (RB_ENT_ID(ent.x) << 1) | (int)(t > 0.0);
                     atomicOr(&sm.cmask[own], 1u << (p - sm.e0[own]));
