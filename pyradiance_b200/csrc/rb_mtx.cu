@@ -144,10 +144,18 @@ constexpr size_t MT_SMEM = (size_t)(4 * MT_BK * MT_LD + 64 * MT_THREADS) * sizeo
         if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); goto done; } \
     } while (0)
 
+// rb_mtx_tc.cu: the same product on the tensor cores (3xTF32, tcgen05 / TMEM / TMA)
+bool mtx_multiply_tc(cudaStream_t stream, const float* A, size_t n, size_t ni, const float* Bplanes, size_t Np, int Kp,
+                     size_t nc, float* C, float* Aplanes, size_t Mp_cap, double* kernel_ms, std::string& err);
+bool tc_prepare_b(cudaStream_t stream, const float* B, size_t ni, size_t nc, float** planes, size_t* Np_out, int* Kp_out,
+                  std::string& err);
+
 // C[nr][nc][3] = A[nr][ni][3] x B[ni][nc][3], channel by channel.  Host or device buffers.
+// Products large enough to fill tensor-core tiles go to k_mtx_tc (rb_mtx_tc.cu); small ones (rmtxop on a few rows,
+// inner dimension below 8) stay on the SIMT kernel above, where the operand pre-pass would cost more than it saves.
 bool mtx_multiply(int device, cudaStream_t stream, const float* A, size_t nr, size_t ni, const float* B, size_t nc,
                   float* C, bool a_dev, bool b_dev, bool c_dev, double* kernel_ms, std::string& err) {
-    float *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    float *dA = nullptr, *dB = nullptr, *dC = nullptr, *Bpl = nullptr, *Apl = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     bool ok = false;
     double ms_total = 0;
@@ -169,6 +177,15 @@ bool mtx_multiply(int device, cudaStream_t stream, const float* A, size_t nr, si
         size_t per_row = std::max(ni, nc) * 3 * sizeof(float);
         chunk = std::max<size_t>(MT_BM, std::min<size_t>(chunk, ((size_t)1 << 30) / per_row / MT_BM * MT_BM));
     }
+    const bool tc = !getenv("RB_MTX_SIMT") && ni >= 8 && nr >= 64 && nc >= 64;
+    size_t Np = 0, Mp_cap = 0; int Kp = 0;
+    if (tc) {
+        if (!tc_prepare_b(stream, Bd, ni, nc, &Bpl, &Np, &Kp, err)) goto done;
+        // operand planes of a chunk of rows: at most ~2 GiB
+        chunk = std::max<size_t>(128, std::min(chunk, ((size_t)2 << 30) / ((size_t)24 * Kp) / 128 * 128));
+        Mp_cap = (std::min(chunk, nr) + 127) / 128 * 128;
+        MCK(cudaMalloc(&Apl, 6 * Mp_cap * (size_t)Kp * sizeof(float)));
+    }
     if (!a_dev) MCK(cudaMalloc(&dA, chunk * ni * 3 * sizeof(float)));
     if (!c_dev) MCK(cudaMalloc(&dC, chunk * nc * 3 * sizeof(float)));
     for (size_t r = 0; r < nr; r += chunk) {
@@ -176,6 +193,12 @@ bool mtx_multiply(int device, cudaStream_t stream, const float* A, size_t nr, si
         const float* Ad = a_dev ? A + r * ni * 3 : dA;
         float* Cd = c_dev ? C + r * nc * 3 : dC;
         if (!a_dev) MCK(cudaMemcpyAsync(dA, A + r * ni * 3, n * ni * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+        if (tc) {
+            if (!mtx_multiply_tc(stream, Ad, n, ni, Bpl, Np, Kp, nc, Cd, Apl, Mp_cap, &ms_total, err)) goto done;
+            if (!c_dev) MCK(cudaMemcpyAsync(C + r * nc * 3, dC, n * nc * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+            MCK(cudaStreamSynchronize(stream));
+            continue;
+        }
         dim3 grid(3, (unsigned)((nc + MT_BN - 1) / MT_BN), (unsigned)((n + MT_BM - 1) / MT_BM));
         MCK(cudaEventRecord(e0, stream));
         k_mtx3<<<grid, MT_THREADS, MT_SMEM, stream>>>(Ad, Bd, Cd, (int)n, (int)ni, (int)nc);
@@ -191,6 +214,8 @@ done:
     if (dA) cudaFree(dA);
     if (dB) cudaFree(dB);
     if (dC) cudaFree(dC);
+    if (Bpl) cudaFree(Bpl);
+    if (Apl) cudaFree(Apl);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
     if (kernel_ms) *kernel_ms = ms_total;

@@ -1,0 +1,334 @@
+// rb_mtx_tc.cu -- the matrix consumer on the 5th-generation tensor cores.
+//
+// result[s][t][c] = sum_b DC[s][b][c] * sky[b][t][c]  (util/cmatrix.c:420-475 cm_multiply: float in, double
+// accumulation, float out) as three GEMMs, one per colour channel, with fp32 accuracy from TF32 hardware:
+//
+//   * split precision (3xTF32): every operand x is stored as hi = tf32(x) (round to nearest, 10-bit mantissa) and
+//     lo = x - hi (exact in fp32; the hardware drops its last 2 of 13 bits), and the product is
+//     hi*hi + hi*lo + lo*hi -- what is left out, lo*lo and the dropped bits, is below 2^-20 of the product;
+//   * a pre-pass (k_split_*) writes the operands channel-planar and K-major: A planes [hi|lo][3][Mp][Kp], B planes
+//     transposed [hi|lo][3][Np][Kp], zero padded to the tile sizes, so that a TMA box of 32 floats (128 bytes, the
+//     swizzle atom) x 128 rows is one operand tile;
+//   * k_mtx_tc: one CTA per 128 x 128 output tile and ALL THREE channels.  Warp 0 (one lane) feeds a 3-stage
+//     ring of {A hi, A lo, B hi, B lo} tiles with cp.async.bulk.tensor (TMA, 128-byte swizzle, mbarrier
+//     complete_tx); warp 1 (one lane) issues tcgen05.mma kind::tf32, M = 128, N = 128, K = 8 per instruction,
+//     12 per ring stage (4 k-steps x 3 products), accumulating channel c in TMEM columns [128 c, 128 c + 128),
+//     and releases each stage with tcgen05.commit; warps 2-5 wait for the last commit, read the three
+//     accumulators with tcgen05.ld (32 lanes x 16 columns per instruction), interleave the channels in registers,
+//     stage rows through the (now idle) ring memory and write them to HBM as whole contiguous runs of
+//     [column][channel] floats -- the output, 10.5 GB at BASELINE configs[1] size, is what bounds the kernel.
+// Nothing of a library GEMM is used; descriptors are built by hand (bit layouts: PTX ISA "tcgen05 matrix / instruction
+// descriptor").  Every mbarrier wait is bounded: a protocol error traps instead of hanging the GPU.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdint>
+#include <string>
+#include "rb_engine.cuh"
+
+namespace rb {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
+constexpr int TC_TILE_BYTES = 128 * TC_BK * 4;               // one operand tile: 128 rows of 128 bytes
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;            // A hi, A lo, B hi, B lo
+constexpr int TC_RING_BYTES = TC_STAGES * TC_STAGE_BYTES;    // 192 KB
+constexpr int TC_SMEM_BYTES = TC_RING_BYTES + 256 + 1024;    // + barriers + alignment slack
+constexpr int TC_STG_ROW = 64 * 3 * 4 + 16;                  // staged row: 64 columns x 3 channels, padded (conflict-free STS.128)
+
+// ------------------------------------------------------------------ PTX ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (unsigned spin = 0;; spin++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1u << 26)) __trap();              // a protocol error must not hang the device
+    }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], M = 128, N = 128, K = 8 (TF32), one thread issues for the CTA
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor of a K-major tile stored by TMA with the 128-byte swizzle: rows of 128 bytes,
+// 8-row groups 1024 bytes apart (stride byte offset), descriptor version 1, layout type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);                  // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                                   // leading byte offset (unused with swizzle), [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;                         // stride byte offset, [32,46)
+    d |= (uint64_t)1 << 46;                                   // version, [46,48)
+    d |= (uint64_t)2 << 61;                                   // layout type, [61,64)
+    return d;
+}
+// instruction descriptor: D = F32 [4,6) = 1, A = B = TF32 [7,10), [10,13) = 2, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+
+// ------------------------------------------------------------ pre-pass ----
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// A[nr][K][3] -> planes [hi|lo][3][Mp][Kp] (zeroed beforehand)
+__global__ void k_split_a(const float* __restrict__ A, float* __restrict__ P, size_t nr, int K, size_t Mp, int Kp) {
+    const size_t n = nr * (size_t)K * 3;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % 3);
+        const size_t rk = i / 3;
+        const int k = (int)(rk % K);
+        const size_t r = rk / K;
+        const float x = A[i], hi = tf32_rn(x);
+        const size_t o = ((size_t)ch * Mp + r) * Kp + k;
+        P[o] = hi;
+        P[o + 3 * Mp * (size_t)Kp] = x - hi;
+    }
+}
+// B[K][nc][3] -> planes [hi|lo][3][Np][Kp], transposed to K-major (zeroed beforehand); a 32 x 32 tile per CTA and channel
+__global__ void k_split_b(const float* __restrict__ B, float* __restrict__ P, int K, size_t nc, size_t Np, int Kp) {
+    __shared__ float t[32][33];
+    const int ch = blockIdx.z;
+    const size_t c0 = (size_t)blockIdx.x * 32;
+    const int k0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int k = k0 + j;
+        const size_t c = c0 + threadIdx.x;
+        t[j][threadIdx.x] = (k < K && c < nc) ? B[((size_t)k * nc + c) * 3 + ch] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const size_t c = c0 + j;
+        const int k = k0 + threadIdx.x;
+        if (c < nc && k < K) {
+            const float x = t[threadIdx.x][j], hi = tf32_rn(x);
+            const size_t o = ((size_t)ch * Np + c) * Kp + k;
+            P[o] = hi;
+            P[o + 3 * Np * (size_t)Kp] = x - hi;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- GEMM ----
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+         size_t nr, size_t nc, int nkb) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_RING_BYTES);       // full[3], empty[3], acc_full
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), acc_full = smem_u32(bars + 2 * TC_STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
+    const int iters = 3 * nkb;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        mbar_init(acc_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {                                  // the whole tensor memory: 3 accumulators of 128 columns (512 allocated)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            for (int it = 0; it < iters; it++) {
+                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                const int ch = it / nkb, kb = it % nkb;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                mbar_expect_tx(full0 + 8 * s, TC_STAGE_BYTES);
+                const uint32_t st = ring + s * TC_STAGE_BYTES;
+                tma_load_3d(st, &tmA, full0 + 8 * s, kb * TC_BK, m0, ch);
+                tma_load_3d(st + TC_TILE_BYTES, &tmA, full0 + 8 * s, kb * TC_BK, m0, 3 + ch);
+                tma_load_3d(st + 2 * TC_TILE_BYTES, &tmB, full0 + 8 * s, kb * TC_BK, n0, ch);
+                tma_load_3d(st + 3 * TC_TILE_BYTES, &tmB, full0 + 8 * s, kb * TC_BK, n0, 3 + ch);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc_idesc(TC_BM, TC_BN);
+            for (int it = 0; it < iters; it++) {
+                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                const int ch = it / nkb, kb = it % nkb;
+                mbar_wait(full0 + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t st = ring + s * TC_STAGE_BYTES;
+                const uint64_t ah = tc_smem_desc(st), al = tc_smem_desc(st + TC_TILE_BYTES);
+                const uint64_t bh = tc_smem_desc(st + 2 * TC_TILE_BYTES), bl = tc_smem_desc(st + 3 * TC_TILE_BYTES);
+                const uint32_t d = tmem + (uint32_t)(ch * TC_BN);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; k++) {
+                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 8 TF32 = 32 bytes along K inside the swizzle atom
+                    tc_mma_tf32(d, ah + adv, bh + adv, idesc, (kb | k) ? 1u : 0u);
+                    tc_mma_tf32(d, ah + adv, bl + adv, idesc, 1u);
+                    tc_mma_tf32(d, al + adv, bh + adv, idesc, 1u);
+                }
+                tc_commit(empty0 + 8 * s);              // the stage is free once these MMAs have read it
+            }
+            tc_commit(acc_full);                        // ... and the accumulators complete once all have finished
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue: TMEM -> registers -> staged rows -> HBM ----------------
+        const int q = warp & 3;                         // the TMEM lane quarter this warp may read
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        uint8_t* stg = smem + (size_t)q * 32 * TC_STG_ROW;       // the ring is idle now: 32 staged rows per warp
+        const bool vec_ok = (nc % 4) == 0;              // 16-byte aligned rows
+        for (int h = 0; h < 2; h++) {
+            const size_t cbase = (size_t)n0 + 64 * h;
+            if (cbase >= nc) break;
+            for (int c16 = 0; c16 < 4; c16++) {
+                uint32_t v0[16], v1[16], v2[16];
+                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 * h + 16 * c16);
+                tmem_ld16(ta, v0);
+                tmem_ld16(ta + TC_BN, v1);
+                tmem_ld16(ta + 2 * TC_BN, v2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float4* dst = reinterpret_cast<float4*>(stg + (size_t)lane * TC_STG_ROW + (size_t)(16 * c16) * 12);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    dst[0] = make_float4(__uint_as_float(v0[j]), __uint_as_float(v1[j]), __uint_as_float(v2[j]), __uint_as_float(v0[j + 1]));
+                    dst[1] = make_float4(__uint_as_float(v1[j + 1]), __uint_as_float(v2[j + 1]), __uint_as_float(v0[j + 2]), __uint_as_float(v1[j + 2]));
+                    dst[2] = make_float4(__uint_as_float(v2[j + 2]), __uint_as_float(v0[j + 3]), __uint_as_float(v1[j + 3]), __uint_as_float(v2[j + 3]));
+                    dst += 3;
+                }
+            }
+            __syncwarp();
+            const int ncol = (int)std::min<size_t>(64, nc - cbase);
+            const int nflt = ncol * 3;
+            for (int rr = 0; rr < 32; rr++) {
+                const size_t row = (size_t)m0 + q * 32 + rr;
+                if (row >= nr) break;
+                const float* src = reinterpret_cast<const float*>(stg + (size_t)rr * TC_STG_ROW);
+                float* out = C + (row * nc + cbase) * 3;
+                if (vec_ok && (nflt % 4) == 0) {
+                    for (int i = lane; i < nflt / 4; i += 32)
+                        reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(src)[i];
+                } else {
+                    for (int i = lane; i < nflt; i += 32) out[i] = src[i];
+                }
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool make_plane_map(EncodeTiledFn enc, CUtensorMap* map, float* base, size_t rows, int Kp, std::string& err) {
+    const cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, 6};
+    const cuuint64_t strides[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)rows * Kp * 4};
+    const cuuint32_t box[3] = {TC_BK, 128, 1}, es[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return false; }
+    return true;
+}
+
+#define TCK(call)                                                                      \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(e_); goto done; } \
+    } while (0)
+
+// C[n][nc][3] = A[n][ni][3] x B[ni][nc][3]; all three buffers in device memory.  kernel_ms += device time of the
+// pre-pass of A and of the GEMM (the pre-pass of B is done once per call by the caller through tc_prepare_b).
+bool mtx_multiply_tc(cudaStream_t stream, const float* A, size_t n, size_t ni, const float* Bplanes, size_t Np, int Kp,
+                     size_t nc, float* C, float* Aplanes, size_t Mp_cap, double* kernel_ms, std::string& err) {
+    static EncodeTiledFn enc = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool ok = false;
+    {
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        TCK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) { err = "cuTensorMapEncodeTiled is not available in this driver"; goto done; }
+        enc = (EncodeTiledFn)fn;
+    }
+    const size_t Mp = (n + TC_BM - 1) / TC_BM * TC_BM;
+    if (Mp > Mp_cap) { err = "internal: A plane buffer too small"; goto done; }
+    TCK(cudaEventCreate(&e0)); TCK(cudaEventCreate(&e1));
+    TCK(cudaFuncSetAttribute(k_mtx_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CUtensorMap tmA, tmB;
+    if (!make_plane_map(enc, &tmA, Aplanes, Mp, Kp, err) || !make_plane_map(enc, &tmB, const_cast<float*>(Bplanes), Np, Kp, err)) goto done;
+    TCK(cudaEventRecord(e0, stream));
+    TCK(cudaMemsetAsync(Aplanes, 0, 6 * Mp * (size_t)Kp * sizeof(float), stream));
+    k_split_a<<<148 * 16, 256, 0, stream>>>(A, Aplanes, n, (int)ni, Mp, Kp);
+    dim3 grid((unsigned)((nc + TC_BN - 1) / TC_BN), (unsigned)(Mp / TC_BM));
+    k_mtx_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmB, C, n, nc, Kp / TC_BK);
+    TCK(cudaEventRecord(e1, stream));
+    TCK(cudaGetLastError());
+    TCK(cudaStreamSynchronize(stream));
+    float ms = 0; TCK(cudaEventElapsedTime(&ms, e0, e1));
+    if (kernel_ms) *kernel_ms += ms;
+    ok = true;
+    }
+done:
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return ok;
+}
+
+// B[ni][nc][3] (device) -> planes; returns the device buffer (caller frees) and its padded sizes
+bool tc_prepare_b(cudaStream_t stream, const float* B, size_t ni, size_t nc, float** planes, size_t* Np_out, int* Kp_out,
+                  std::string& err) {
+    const int Kp = (int)((ni + TC_BK - 1) / TC_BK * TC_BK);
+    const size_t Np = (nc + TC_BN - 1) / TC_BN * TC_BN;
+    float* P = nullptr;
+    cudaError_t e = cudaMalloc(&P, 6 * Np * (size_t)Kp * sizeof(float));
+    if (e != cudaSuccess) { err = std::string("cudaMalloc (B planes): ") + cudaGetErrorString(e); return false; }
+    cudaMemsetAsync(P, 0, 6 * Np * (size_t)Kp * sizeof(float), stream);
+    dim3 grid((unsigned)((nc + 31) / 32), (unsigned)((ni + 31) / 32), 3);
+    k_split_b<<<grid, dim3(32, 8), 0, stream>>>(B, P, (int)ni, nc, Np, Kp);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { err = std::string("k_split_b: ") + cudaGetErrorString(e); cudaFree(P); return false; }
+    *planes = P; *Np_out = Np; *Kp_out = Kp;
+    return true;
+}
+
+}  // namespace rb

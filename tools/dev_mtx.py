@@ -10,6 +10,7 @@ import torch
 from pyradiance_b200 import _lib
 from oracle import refrun
 nr, ni, nc = int(os.environ.get("NR", 100000)), int(os.environ.get("NI", 145)), int(os.environ.get("NC", 8760))
+print("shape", nr, ni, nc)
 g = torch.Generator(device="cuda").manual_seed(1)
 a = torch.rand((nr, ni, 3), device="cuda", generator=g) ** 6 * 0.05
 b = torch.rand((ni, nc, 3), device="cuda", generator=g) ** 3 * 2e4
