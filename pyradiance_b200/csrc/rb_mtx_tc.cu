@@ -9,14 +9,19 @@
 //   * a pre-pass (k_split_*) writes the operands channel-planar and K-major: A planes [hi|lo][3][Mp][Kp], B planes
 //     transposed [hi|lo][3][Np][Kp], zero padded to the tile sizes, so that a TMA box of 32 floats (128 bytes, the
 //     swizzle atom) x 128 rows is one operand tile;
-//   * k_mtx_tc: one CTA per 128 x 128 output tile and ALL THREE channels.  Warp 0 (one lane) feeds a 3-stage
-//     ring of {A hi, A lo, B hi, B lo} tiles with cp.async.bulk.tensor (TMA, 128-byte swizzle, mbarrier
-//     complete_tx); warp 1 (one lane) issues tcgen05.mma kind::tf32, M = 128, N = 128, K = 8 per instruction,
-//     12 per ring stage (4 k-steps x 3 products), accumulating channel c in TMEM columns [128 c, 128 c + 128),
-//     and releases each stage with tcgen05.commit; warps 2-5 wait for the last commit, read the three
-//     accumulators with tcgen05.ld (32 lanes x 16 columns per instruction), interleave the channels in registers,
-//     stage rows through the (now idle) ring memory and write them to HBM as whole contiguous runs of
-//     [column][channel] floats -- the output, 10.5 GB at BASELINE configs[1] size, is what bounds the kernel.
+//   * k_mtx_tc: one CTA per 128 x 64 output tile and ALL THREE channels, two CTAs per SM (96 KB of shared memory and
+//     256 TMEM columns each) so that one CTA's epilogue overlaps the other's MMAs.  Warp 0 (one lane) feeds a
+//     2-stage ring of {A hi, A lo, B hi, B lo} tiles with cp.async.bulk.tensor (TMA, 128-byte swizzle, mbarrier
+//     complete_tx); warp 1 (one lane) issues tcgen05.mma kind::tf32, M = 128, N = 64, K = 8 per instruction, 12 per
+//     ring stage (4 k-steps x 3 products), and releases each stage with tcgen05.commit.
+//   * two-level accumulation: the tensor core's fp32 accumulator loses ~2e-8 of the sum per product (measured:
+//     3e-5 after 2305 non-negative products), so the MMAs accumulate SEGMENTS of 128 products in TMEM columns
+//     [0, 64); warps 2-5 fold each finished segment into per-thread fp32 registers (round to nearest) with
+//     tcgen05.ld, hand the segment buffer back (mbarrier), and park a finished channel in TMEM columns
+//     [64 + 64 c, 128 + 64 c) with tcgen05.st.  Relative error stays at ~3e-6 for any inner dimension.
+//   * epilogue: the three channel sums are read back, interleaved in registers, staged through the (now idle)
+//     ring memory and written to HBM as contiguous runs of [column][channel] floats -- the output, 10.5 GB at
+//     BASELINE configs[1] size, is what the kernel has to stream.
 // Nothing of a library GEMM is used; descriptors are built by hand (bit layouts: PTX ISA "tcgen05 matrix / instruction
 // descriptor").  Every mbarrier wait is bounded: a protocol error traps instead of hanging the GPU.
 #include <cuda.h>
@@ -28,12 +33,14 @@
 
 namespace rb {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3, TC_THREADS = 192;
-constexpr int TC_TILE_BYTES = 128 * TC_BK * 4;               // one operand tile: 128 rows of 128 bytes
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;            // A hi, A lo, B hi, B lo
-constexpr int TC_RING_BYTES = TC_STAGES * TC_STAGE_BYTES;    // 192 KB
+constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 32, TC_STAGES = 2, TC_THREADS = 192;
+constexpr int TC_SEG_KB = 4;                                 // k-blocks per accumulation segment (128 products)
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4, TC_B_BYTES = TC_BN * TC_BK * 4;     // operand tiles: rows of 128 bytes
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;                   // A hi, A lo, B hi, B lo = 48 KB
+constexpr int TC_RING_BYTES = TC_STAGES * TC_STAGE_BYTES;    // 96 KB
 constexpr int TC_SMEM_BYTES = TC_RING_BYTES + 256 + 1024;    // + barriers + alignment slack
-constexpr int TC_STG_ROW = 64 * 3 * 4 + 16;                  // staged row: 64 columns x 3 channels, padded (conflict-free STS.128)
+constexpr int TC_TMEM_COLS = 256;                            // segment [0,64) + three channel sums
+constexpr int TC_STG_ROW = 32 * 3 * 4 + 16;                  // staged row: 32 columns x 3 channels, padded (conflict-free STS.128)
 
 // ------------------------------------------------------------------ PTX ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,6 +88,14 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t addr) {
 // instruction descriptor: D = F32 [4,6) = 1, A = B = TF32 [7,10), [10,13) = 2, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
 __host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]),
+                   "f"(v[8]), "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -134,26 +149,27 @@ __global__ void k_split_b(const float* __restrict__ B, float* __restrict__ P, in
 }
 
 // ---------------------------------------------------------------- GEMM ----
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
          size_t nr, size_t nc, int nkb) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_RING_BYTES);       // full[3], empty[3], acc_full
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_RING_BYTES);       // full[S], empty[S], seg_full, seg_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2);
     const uint32_t ring = smem_u32(smem);
-    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES), acc_full = smem_u32(bars + 2 * TC_STAGES);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES);
+    const uint32_t seg_full = smem_u32(bars + 2 * TC_STAGES), seg_empty = smem_u32(bars + 2 * TC_STAGES + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
-    const int iters = 3 * nkb;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-        mbar_init(acc_full, 1);
+        mbar_init(seg_full, 1);
+        mbar_init(seg_empty, 4);                      // one arrival per folding warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {                                  // the whole tensor memory: 3 accumulators of 128 columns (512 allocated)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -164,6 +180,7 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     if (warp == 0) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
+            const int iters = 3 * nkb;
             for (int it = 0; it < iters; it++) {
                 const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
                 const int ch = it / nkb, kb = it % nkb;
@@ -171,9 +188,9 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                 mbar_expect_tx(full0 + 8 * s, TC_STAGE_BYTES);
                 const uint32_t st = ring + s * TC_STAGE_BYTES;
                 tma_load_3d(st, &tmA, full0 + 8 * s, kb * TC_BK, m0, ch);
-                tma_load_3d(st + TC_TILE_BYTES, &tmA, full0 + 8 * s, kb * TC_BK, m0, 3 + ch);
-                tma_load_3d(st + 2 * TC_TILE_BYTES, &tmB, full0 + 8 * s, kb * TC_BK, n0, ch);
-                tma_load_3d(st + 3 * TC_TILE_BYTES, &tmB, full0 + 8 * s, kb * TC_BK, n0, 3 + ch);
+                tma_load_3d(st + TC_A_BYTES, &tmA, full0 + 8 * s, kb * TC_BK, m0, 3 + ch);
+                tma_load_3d(st + 2 * TC_A_BYTES, &tmB, full0 + 8 * s, kb * TC_BK, n0, ch);
+                tma_load_3d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmB, full0 + 8 * s, kb * TC_BK, n0, 3 + ch);
             }
         }
         __syncwarp();
@@ -181,40 +198,72 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             constexpr uint32_t idesc = tc_idesc(TC_BM, TC_BN);
-            for (int it = 0; it < iters; it++) {
-                const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
-                const int ch = it / nkb, kb = it % nkb;
-                mbar_wait(full0 + 8 * s, ph);
-                tc_fence_after();
-                const uint32_t st = ring + s * TC_STAGE_BYTES;
-                const uint64_t ah = tc_smem_desc(st), al = tc_smem_desc(st + TC_TILE_BYTES);
-                const uint64_t bh = tc_smem_desc(st + 2 * TC_TILE_BYTES), bl = tc_smem_desc(st + 3 * TC_TILE_BYTES);
-                const uint32_t d = tmem + (uint32_t)(ch * TC_BN);
+            int it = 0, seg = 0;
+            for (int ch = 0; ch < 3; ch++)
+                for (int s0 = 0; s0 < nkb; s0 += TC_SEG_KB, seg++) {
+                    mbar_wait(seg_empty, (seg & 1) ^ 1);      // the folding warps have read the previous segment
+                    tc_fence_after();
+                    const int s1 = min(s0 + TC_SEG_KB, nkb);
+                    for (int kb = s0; kb < s1; kb++, it++) {
+                        const int s = it % TC_STAGES, ph = (it / TC_STAGES) & 1;
+                        mbar_wait(full0 + 8 * s, ph);
+                        tc_fence_after();
+                        const uint32_t st = ring + s * TC_STAGE_BYTES;
+                        const uint64_t ah = tc_smem_desc(st), al = tc_smem_desc(st + TC_A_BYTES);
+                        const uint64_t bh = tc_smem_desc(st + 2 * TC_A_BYTES), bl = tc_smem_desc(st + 2 * TC_A_BYTES + TC_B_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; k++) {
-                    const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 8 TF32 = 32 bytes along K inside the swizzle atom
-                    tc_mma_tf32(d, ah + adv, bh + adv, idesc, (kb | k) ? 1u : 0u);
-                    tc_mma_tf32(d, ah + adv, bl + adv, idesc, 1u);
-                    tc_mma_tf32(d, al + adv, bh + adv, idesc, 1u);
+                        for (int k = 0; k < TC_BK / 8; k++) {
+                            const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);      // 8 TF32 = 32 bytes along K inside the swizzle atom
+                            tc_mma_tf32(tmem, ah + adv, bh + adv, idesc, (kb > s0 || k) ? 1u : 0u);
+                            tc_mma_tf32(tmem, ah + adv, bl + adv, idesc, 1u);
+                            tc_mma_tf32(tmem, al + adv, bh + adv, idesc, 1u);
+                        }
+                        tc_commit(empty0 + 8 * s);          // the stage is free once these MMAs have read it
+                    }
+                    tc_commit(seg_full);                    // ... and the segment is complete once they have finished
                 }
-                tc_commit(empty0 + 8 * s);              // the stage is free once these MMAs have read it
-            }
-            tc_commit(acc_full);                        // ... and the accumulators complete once all have finished
         }
         __syncwarp();
     } else {
-        // ---------------- epilogue: TMEM -> registers -> staged rows -> HBM ----------------
-        const int q = warp & 3;                         // the TMEM lane quarter this warp may read
-        mbar_wait(acc_full, 0);
-        tc_fence_after();
-        uint8_t* stg = smem + (size_t)q * 32 * TC_STG_ROW;       // the ring is idle now: 32 staged rows per warp
+        // ---------------- fold segments (TMEM -> registers), then TMEM -> staged rows -> HBM ----------------
+        const int q = warp & 3;                         // the TMEM lane quarter this warp may touch
+        const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+        int seg = 0;
+        for (int ch = 0; ch < 3; ch++) {
+            float acc[4][16];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int j = 0; j < 16; j++) acc[c][j] = 0.f;
+            for (int s0 = 0; s0 < nkb; s0 += TC_SEG_KB, seg++) {
+                mbar_wait(seg_full, seg & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    uint32_t v[16];
+                    tmem_ld16(tq + 16 * c, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; j++) acc[c][j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(seg_empty);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) tmem_st16(tq + (uint32_t)(TC_BN + TC_BN * ch + 16 * c), acc[c]);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        // all MMAs have completed (the last segment was folded), so the ring is idle: 32 staged rows per warp
+        uint8_t* stg = smem + (size_t)q * 32 * TC_STG_ROW;
         const bool vec_ok = (nc % 4) == 0;              // 16-byte aligned rows
         for (int h = 0; h < 2; h++) {
-            const size_t cbase = (size_t)n0 + 64 * h;
+            const size_t cbase = (size_t)n0 + 32 * h;
             if (cbase >= nc) break;
-            for (int c16 = 0; c16 < 4; c16++) {
+#pragma unroll
+            for (int c16 = 0; c16 < 2; c16++) {
                 uint32_t v0[16], v1[16], v2[16];
-                const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 * h + 16 * c16);
+                const uint32_t ta = tq + (uint32_t)(TC_BN + 32 * h + 16 * c16);
                 tmem_ld16(ta, v0);
                 tmem_ld16(ta + TC_BN, v1);
                 tmem_ld16(ta + 2 * TC_BN, v2);
@@ -229,18 +278,21 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                 }
             }
             __syncwarp();
-            const int ncol = (int)std::min<size_t>(64, nc - cbase);
+            const int ncol = (int)min((size_t)32, nc - cbase);
             const int nflt = ncol * 3;
-            for (int rr = 0; rr < 32; rr++) {
-                const size_t row = (size_t)m0 + q * 32 + rr;
-                if (row >= nr) break;
-                const float* src = reinterpret_cast<const float*>(stg + (size_t)rr * TC_STG_ROW);
-                float* out = C + (row * nc + cbase) * 3;
-                if (vec_ok && (nflt % 4) == 0) {
-                    for (int i = lane; i < nflt / 4; i += 32)
-                        reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(src)[i];
-                } else {
-                    for (int i = lane; i < nflt; i += 32) out[i] = src[i];
+            const size_t row0 = (size_t)m0 + q * 32;
+            const int nrow = (int)min((size_t)32, nr > row0 ? nr - row0 : 0);
+            if (vec_ok && (nflt % 4) == 0) {
+                const int per = nflt / 4;               // float4 per row (24 for a full tile)
+                for (int i = lane; i < nrow * per; i += 32) {
+                    const int rr = i / per, f = i - rr * per;
+                    reinterpret_cast<float4*>(C + ((row0 + rr) * nc + cbase) * 3)[f] =
+                        reinterpret_cast<const float4*>(stg + (size_t)rr * TC_STG_ROW)[f];
+                }
+            } else {
+                for (int i = lane; i < nrow * nflt; i += 32) {
+                    const int rr = i / nflt, f = i - rr * nflt;
+                    C[((row0 + rr) * nc + cbase) * 3 + f] = reinterpret_cast<const float*>(stg + (size_t)rr * TC_STG_ROW)[f];
                 }
             }
             __syncwarp();
@@ -250,7 +302,7 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
     }
 }
 
@@ -259,10 +311,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static bool make_plane_map(EncodeTiledFn enc, CUtensorMap* map, float* base, size_t rows, int Kp, std::string& err) {
+static bool make_plane_map(EncodeTiledFn enc, CUtensorMap* map, float* base, size_t rows, int Kp, int box_rows, std::string& err) {
     const cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, 6};
     const cuuint64_t strides[2] = {(cuuint64_t)Kp * 4, (cuuint64_t)rows * Kp * 4};
-    const cuuint32_t box[3] = {TC_BK, 128, 1}, es[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_rows, 1}, es[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"; return false; }
@@ -295,7 +347,8 @@ bool mtx_multiply_tc(cudaStream_t stream, const float* A, size_t n, size_t ni, c
     TCK(cudaEventCreate(&e0)); TCK(cudaEventCreate(&e1));
     TCK(cudaFuncSetAttribute(k_mtx_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     CUtensorMap tmA, tmB;
-    if (!make_plane_map(enc, &tmA, Aplanes, Mp, Kp, err) || !make_plane_map(enc, &tmB, const_cast<float*>(Bplanes), Np, Kp, err)) goto done;
+    if (!make_plane_map(enc, &tmA, Aplanes, Mp, Kp, TC_BM, err) ||
+        !make_plane_map(enc, &tmB, const_cast<float*>(Bplanes), Np, Kp, TC_BN, err)) goto done;
     TCK(cudaEventRecord(e0, stream));
     TCK(cudaMemsetAsync(Aplanes, 0, 6 * Mp * (size_t)Kp * sizeof(float), stream));
     k_split_a<<<148 * 16, 256, 0, stream>>>(A, Aplanes, n, (int)ni, Mp, Kp);
