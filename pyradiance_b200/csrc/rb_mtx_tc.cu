@@ -34,12 +34,14 @@
 namespace rb {
 
 constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 32, TC_STAGES = 2, TC_THREADS = 192;
-constexpr int TC_SEG_KB = 4;                                 // k-blocks per accumulation segment (128 products)
+#ifndef RB_TC_SEG_KB
+#define RB_TC_SEG_KB 4
+#endif
+constexpr int TC_SEG_KB = RB_TC_SEG_KB;                      // k-blocks per accumulation segment (4 = 128 products)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4, TC_B_BYTES = TC_BN * TC_BK * 4;     // operand tiles: rows of 128 bytes
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;                   // A hi, A lo, B hi, B lo = 48 KB
 constexpr int TC_RING_BYTES = TC_STAGES * TC_STAGE_BYTES;    // 96 KB
 constexpr int TC_SMEM_BYTES = TC_RING_BYTES + 256 + 1024;    // + barriers + alignment slack
-constexpr int TC_TMEM_COLS = 256;                            // segment [0,64) + three channel sums
 constexpr int TC_STG_ROW = 32 * 3 * 4 + 16;                  // staged row: 32 columns x 3 channels, padded (conflict-free STS.128)
 
 // ------------------------------------------------------------------ PTX ----
@@ -282,8 +284,22 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
             const int nflt = ncol * 3;
             const size_t row0 = (size_t)m0 + q * 32;
             const int nrow = (int)min((size_t)32, nr > row0 ? nr - row0 : 0);
-            if (vec_ok && (nflt % 4) == 0) {
-                const int per = nflt / 4;               // float4 per row (24 for a full tile)
+            if (vec_ok && nflt == 96) {
+                // full tile: 24 float4 per row; a warp instruction covers 4 rows x 8 float4 ... written as 3 float4
+                // columns per lane group so that every store instruction fills whole 128-byte lines
+                const int sub = lane >> 3, f0 = lane & 7;             // 4 rows per pass, 8 lanes per row
+#pragma unroll 2
+                for (int r4 = 0; r4 < nrow; r4 += 4) {
+                    const int rr = r4 + sub;
+                    if (rr < nrow) {
+                        const float4* src = reinterpret_cast<const float4*>(stg + (size_t)rr * TC_STG_ROW);
+                        float4* dst = reinterpret_cast<float4*>(C + ((row0 + rr) * nc + cbase) * 3);
+                        const float4 a = src[f0], b = src[f0 + 8], c = src[f0 + 16];
+                        dst[f0] = a; dst[f0 + 8] = b; dst[f0 + 16] = c;
+                    }
+                }
+            } else if (vec_ok && (nflt % 4) == 0) {
+                const int per = nflt / 4;               // float4 per row
                 for (int i = lane; i < nrow * per; i += 32) {
                     const int rr = i / per, f = i - rr * per;
                     reinterpret_cast<float4*>(C + ((row0 + rr) * nc + cbase) * 3)[f] =
