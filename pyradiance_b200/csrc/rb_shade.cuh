@@ -285,6 +285,10 @@ __device__ __forceinline__ void add_value(const WaveArgs& A, unsigned row, const
 // (Scalars by value: reference arguments of a real call live in local memory.
 // Moving m_glass / gaussamp / raytrans out of line the same way made k_shade 70 %
 // SLOWER -- they take the whole RayCtx by reference.)
+// Accumulation is WARP-AGGREGATED: the lanes that arrive here together and add to the same coefficient (same record,
+// same bin: neighbouring rays of one sensor usually do) are found with __match_any_sync, their values are summed
+// by the group's first lane in double, and that lane alone issues the three atomics.  A sun-coefficient matrix adds
+// hundreds of millions of contributions, many of a warp's to one (row, sun) cell.
 __device__ __noinline__ void add_contrib(const DBinSpec* b, double* row, DCounters* C, double dx, double dy,
                                          double dz, float c0, float c1, float c2) {
     const double D[3] = {dx, dy, dz};
@@ -293,10 +297,22 @@ __device__ __noinline__ void add_contrib(const DBinSpec* b, double* row, DCounte
     int bn = (int)(bval + .5);
     if (bn >= b->nbins) { atomicAdd(&C->badbin, 1u); return; }
     double* d = row + (size_t)(b->col0 + bn) * 3;
-    atomicAdd(d + 0, (double)c0);
-    atomicAdd(d + 1, (double)c1);
-    atomicAdd(d + 2, (double)c2);
-    atomicAdd(&C->contribs, 1ULL);
+    const unsigned active = __activemask();
+    const unsigned grp = __match_any_sync(active, (unsigned long long)(size_t)d);
+    const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
+    double s0 = 0., s1 = 0., s2 = 0.;
+    for (unsigned m = grp; m; m &= m - 1) {           // every member runs the same loop: shuffles stay convergent within the group
+        const int j = __ffs(m) - 1;
+        s0 += (double)__shfl_sync(grp, c0, j);
+        s1 += (double)__shfl_sync(grp, c1, j);
+        s2 += (double)__shfl_sync(grp, c2, j);
+    }
+    if (lane == leader) {
+        atomicAdd(d + 0, s0);
+        atomicAdd(d + 1, s1);
+        atomicAdd(d + 2, s2);
+        atomicAdd(&C->contribs, (unsigned long long)__popc(grp));
+    }
 }
 
 // rcontrib.c:272-317.  `rcoef_ok`: the ray's own coefficient was not zeroed by

@@ -280,14 +280,127 @@ class RtraceSimulManager:
 
 
 class RcontribOutput:
-    def __init__(self, name, nrows, ncols):
+    """One output channel (rt/RcontribSimulManager.h:26-110 RcontribOutput): a file that holds a Radiance header,
+    `n_rows` rows of `row_bytes` bytes each, and the count of finished rows in its NROWS= field, or -- for an
+    empty output specification -- memory only."""
+    ROWZERO = "NROWS=0000000000000000\n"           # RcontribSimulManager.cpp:31
+
+    def __init__(self, name, nrows, ncols, dtype=np.float32):
         self._name = name
         self.n_rows = nrows
-        self.row_bytes = ncols * 3 * 4
+        self.ncols = ncols                          # coefficient triplets per row
+        self.dtype = np.dtype(dtype)
+        self.row_bytes = ncols * 3 * self.dtype.itemsize
         self.cur_row = 0
+        self.omod = None
+        self.obin = -1
+        self.beg_data = 0
+        self.cols = []                              # (first column in the context's row, count) per modifier
+        self._row_count_pos = 0
+        self._mm = None
+        self.array = None
 
     def get_name(self):
         return self._name
+
+    # ---- RcontribOutput::NewHeader(), RcontribSimulManager.cpp:452-519 ----
+    def _new_header(self, mgr) -> bytes:
+        h = "#?RADIANCE\n" + mgr.get_head_str()
+        if self.omod:
+            h += f"MODIFIER={self.omod}\n"
+        if self.obin >= 0:
+            h += f"BIN={self.obin}\n"
+        self._row_count_pos = len(h) + 6
+        h += self.ROWZERO
+        esiz = 3 * self.dtype.itemsize
+        if (not mgr.xres) or self.row_bytes > esiz:
+            h += f"NCOLS={self.row_bytes // esiz}\n"
+        h += "NCOMP=3\n"
+        h += "BigEndian=0\n"
+        h += "FORMAT=" + ("float" if self.dtype == np.float32 else "double")
+        align = self.dtype.itemsize
+        while (len(h) + 2) % align:                 # data aligned at the end of the header
+            h += " "
+        h += "\n\n"
+        if mgr.xres > 0 and self.row_bytes == esiz:
+            h += f"-Y {mgr.yres} +X {mgr.xres}\n"
+        self.beg_data = len(h)
+        return h.encode("latin-1")
+
+    def open(self, mgr, op):
+        """PrepOutput() for this channel; returns the number of rows already there (RECOVER) or 0."""
+        done = 0
+        if not self._name:                          # memory only
+            self.array = np.zeros((max(self.n_rows, 0), self.ncols * 3), dtype=self.dtype)
+            return 0
+        import os
+        path = self._name
+        if op == RcOutputOp.RECOVER:
+            if not os.path.exists(path):
+                raise RuntimeError(f"cannot recover '{path}': no such file")
+            done = self._check_header(mgr, path)
+        else:
+            if op == RcOutputOp.NEW and os.path.exists(path):
+                raise RuntimeError(f"cannot open '{path}' for writing (file exists; use RcOutputOp.FORCE or RECOVER)")
+            hdr = self._new_header(mgr)
+            with open(path, "wb") as f:
+                f.write(hdr)
+                f.truncate(len(hdr) + self.n_rows * self.row_bytes)
+        if self.n_rows > 0:
+            self._mm = np.memmap(path, mode="r+", dtype=self.dtype, offset=self.beg_data, shape=(self.n_rows, self.ncols * 3))
+            self.array = self._mm
+        else:
+            self.array = np.zeros((0, self.ncols * 3), dtype=self.dtype)
+        return min(done, self.n_rows)
+
+    # ---- RcontribOutput::CheckHeader(), RcontribSimulManager.cpp:537-596 ----
+    def _check_header(self, mgr, path) -> int:
+        raw = open(path, "rb").read(mgr.get_head_len() + 1024)
+        end = raw.find(b"\n\n")
+        if end < 0:
+            raise RuntimeError(f"cannot find end of header in '{path}'")
+        hdr = raw[:end + 1].decode("latin-1")
+
+        def arg(key):
+            for line in hdr.split("\n"):
+                if line.startswith(key):
+                    return line[len(key):]
+            return None
+        if int(arg("NCOMP=") or 3) != 3:
+            raise RuntimeError(f"expected NCOMP=3 in '{path}'")
+        fmt = "float" if self.dtype == np.float32 else "double"
+        if not (arg("FORMAT=") or "").startswith(fmt):
+            raise RuntimeError(f"expected FORMAT={fmt} in '{path}'")
+        esiz = 3 * self.dtype.itemsize
+        nc = arg("NCOLS=")
+        if (int(nc) * esiz != self.row_bytes) if nc is not None else ((not mgr.xres) or self.row_bytes > esiz):
+            raise RuntimeError(f"expected NCOLS={self.row_bytes // esiz} in '{path}'")
+        nr = arg("NROWS=")
+        if nr is None:
+            raise RuntimeError(f"missing NROWS in '{path}'")
+        self._row_count_pos = hdr.index("NROWS=") + 6
+        self.beg_data = end + 2
+        if mgr.xres > 0 and self.row_bytes == esiz:
+            res = f"-Y {mgr.yres} +X {mgr.xres}\n".encode()
+            if raw[self.beg_data:self.beg_data + len(res)] != res:
+                raise RuntimeError(f"bad resolution string in '{path}'")
+            self.beg_data += len(res)
+        return int(nr)
+
+    def rows_done(self, n):
+        """Record the number of finished rows in the header (the file is valid at any time)."""
+        self.cur_row = n
+        if self._mm is not None:
+            self._mm.flush()
+            with open(self._name, "r+b") as f:
+                f.seek(self._row_count_pos)
+                f.write(b"%016d" % n)
+
+    def close(self):
+        if self._mm is not None:
+            self._mm.flush()
+            self._mm = None
+        self.array = None
 
 
 class RcontribSimulManager:
@@ -305,10 +418,80 @@ class RcontribSimulManager:
         self._mods = []             # (modn, outspec, prms, binval, bincnt, cal_ops snapshot)
         self._loaded = False
         self._out = None
+        self._outputs = []          # RcontribOutput per distinct output specification
         self._rows_done = 0
         self._device = device
+        self._header = ""
         if octn:
             self.load_octree(octn)
+
+    # ---- header (rt/RtraceSimulManager.cpp:46-171 RadSimulManager::NewHeader / AddHeader / GetHeadStr) ----
+    def new_header(self, inspec=None) -> bool:
+        """Prepare the header from a previous input (a file with a Radiance header, or `!command`), or clear it."""
+        self._header = ""
+        if not inspec:
+            return False
+        if inspec[0] == "!":
+            return self.add_header(inspec[1:])
+        try:
+            with open(inspec, "rb") as f:
+                for raw in f:
+                    line = raw.decode("latin-1")
+                    if line in ("\n", "\r\n"):
+                        break
+                    if line.startswith("#?") or line.startswith("FORMAT="):
+                        continue
+                    self.add_header(line)
+        except OSError:
+            return False
+        return True
+
+    def add_header(self, s) -> bool:
+        """Add a line (a string; a newline is added if missing) or a program line (a list of arguments, quoted
+        where they hold blanks or quotes) to the header."""
+        if s is None:
+            return False
+        if not isinstance(s, str):
+            words = []
+            for a in s:
+                a = str(a)
+                if a == "" or any(c.isspace() for c in a) or '"' in a or "'" in a:
+                    qc = "'" if '"' in a else '"'
+                    words.append(qc + a + qc)
+                else:
+                    words.append(a)
+            if not words:
+                return False
+            self._header += " ".join(words) + "\n"
+            return True
+        s = s.rstrip("\r\n")
+        if not s:
+            return False
+        self._header += s + "\n"
+        return True
+
+    def get_head_len(self) -> int:
+        return len(self._header.encode("latin-1"))
+
+    def get_head_str(self, key=None, inOK: bool = False):
+        """The header lines, or -- with `key` -- what follows the first line that starts with it (None if absent)."""
+        if key is None:
+            return self._header
+        if not key or not self._header or "\n" in key:
+            return None
+        if inOK:
+            key = key.lstrip()
+        if not key:
+            return None
+        for line in self._header.split("\n"):
+            probe = line.lstrip() if inOK else line
+            if probe.startswith(key):
+                return probe[len(key):]
+        return None
+
+    def get_format(self, siz=None) -> int:
+        """Current data format as the reference's character code ('f' or 'd')."""
+        return ord("f") if self._dtype == np.float32 else ord("d")
 
     def __enter__(self):
         return self
@@ -340,9 +523,15 @@ class RcontribSimulManager:
         except RBError as e:
             raise RuntimeError(str(e)) from e
         self._loaded = True
+        self._header = ""               # NewHeader(octn): the octree's header without its id and FORMAT lines
+        for line in self._ctx.header_lines():
+            if not (line.startswith("#?") or line.startswith("FORMAT=")):
+                self.add_header(line)
         return True
 
     def add_modifier(self, modn, outspec, prms="", binval="", bincnt=1) -> bool:
+        if outspec and "%d" in outspec:
+            raise RuntimeError("unsupported output specification: one file per bin ('%d') is not built in this manager")
         try:
             # bin functions come from the global cal context at the time of the call
             scratch = _lib.Context(self._device, _lib.RB_PROGRAM_RCONTRIB)
@@ -366,9 +555,29 @@ class RcontribSimulManager:
         self._mods = []
         self._ctx.clear_modifiers()
 
+    def _output_plan(self):
+        """Output channels in order of first use: modifiers that name the same file share its rows (their bins side
+        by side, RcontribSimulManager.cpp AddModifier / getOutput); `%s` in the name stands for the modifier."""
+        plan, col0 = [], 0
+        for modn, outspec, prms, binval, bincnt, ops in self._mods:
+            name = (outspec or "").replace("%s", modn)
+            op = next((o for o in plan if o._name == name), None)
+            if op is None:
+                op = RcontribOutput(name, self.get_row_max(), 0, self._dtype)
+                op.omod = modn if (outspec and "%s" in outspec) else None
+                plan.append(op)
+            op.cols.append((col0, int(bincnt)))
+            op.ncols += int(bincnt)
+            op.row_bytes = op.ncols * 3 * op.dtype.itemsize
+            col0 += int(bincnt)
+        return plan
+
     def get_output(self, nm=None):
-        ncols = sum(m[4] for m in self._mods)
-        return RcontribOutput(nm or (self._mods[0][1] if self._mods else None), self.get_row_max(), ncols)
+        """The named output channel, or the first one (the head of the reference's list)."""
+        outs = self._outputs or self._output_plan()
+        if nm is None:
+            return outs[0] if outs else None
+        return next((o for o in outs if o._name == nm), None)
 
     def get_row_max(self) -> int:
         return self.yres * (self.xres if self.xres else 1) if self.yres else 0
@@ -396,9 +605,16 @@ class RcontribSimulManager:
         except RBError as e:
             raise RuntimeError(str(e)) from e
         nrows = self.get_row_max()
+        for o in self._outputs:
+            o.close()
+        self._outputs = self._output_plan()
+        done = None
+        for o in self._outputs:                 # RECOVER: resume after the rows every channel already holds
+            d = o.open(self, self.out_op)
+            done = d if done is None else min(done, d)
         self._out = np.zeros((max(nrows, 0), self._ctx.num_columns() * 3), dtype=self._dtype)
-        self._rows_done = 0
-        return nrows
+        self._rows_done = done or 0
+        return self._rows_done
 
     def ready(self) -> bool:
         return self._loaded and self._out is not None
@@ -434,6 +650,7 @@ class RcontribSimulManager:
             raise RuntimeError(str(e)) from e
         self._out[:nrec] = m.reshape(nrec, -1)
         self._rows_done = nrec
+        self._store_rows(0, nrec)
 
     def compute_record(self, orig_direc) -> int:
         od = np.ascontiguousarray(orig_direc, dtype=np.float64).reshape(-1, 6)
@@ -450,7 +667,23 @@ class RcontribSimulManager:
             raise RuntimeError(str(e)) from e
         self._out[row] = m.reshape(-1)
         self._rows_done += 1
+        self._store_rows(row, row + 1)
         return 1
+
+    def _store_rows(self, r0, r1):
+        """Rows [r0, r1) of the context's result into the output channels (files or memory)."""
+        for o in self._outputs:
+            if o.array is None:
+                continue
+            if o.array.shape[0] < r1:
+                if o._mm is not None:
+                    raise RuntimeError(f"output '{o.get_name()}' holds {o.array.shape[0]} rows (set yres before prep_output)")
+                o.array = np.concatenate([o.array, np.zeros((r1 - o.array.shape[0], o.array.shape[1]), dtype=o.dtype)])
+            c = 0
+            for col0, n in o.cols:
+                o.array[r0:r1, 3 * c:3 * (c + n)] = self._out[r0:r1, 3 * col0:3 * (col0 + n)]
+                c += n
+            o.rows_done(self._rows_done)
 
     def flush_queue(self) -> int:
         return 0
@@ -460,11 +693,19 @@ class RcontribSimulManager:
         return True
 
     def get_output_array(self, nm=None) -> np.ndarray:
+        """[nRows, ncols * 3] view of the named channel's data (the first channel by default), as the reference's
+        binding exposes the mapped file (radiance_ext.cpp:357-361)."""
         if self._out is None:
             raise RuntimeError("no output prepared")
-        return self._out
+        o = self.get_output(nm)
+        if o is None or o.array is None:
+            return self._out
+        return o.array
 
     def cleanup(self, everything: bool = False) -> int:
+        for o in self._outputs:
+            o.close()
+        self._outputs = []
         if everything:
             self._ctx.close()
             self._loaded = False

@@ -454,8 +454,11 @@ def test_rcontrib_class_matches_reference_layout(golden):
         pr.Rcontrib(rays, golden / "contrib.oct").add_modifier("skyglow", calfile="tregenza.cal", binv="tbin")()
 
 
-def test_rcontrib_simul_manager_like_reference_test(golden):
-    """Mirror of /root/reference/tests/test_rcontrib.py:9-75."""
+def test_rcontrib_simul_manager_like_reference_test(golden, workdir):
+    """Mirror of /root/reference/tests/test_rcontrib.py:9-75, then what the reference's managers add around it:
+    the header calls (radiance_ext.cpp:305-317), the output file the two modifiers share (a Radiance matrix file,
+    RcontribSimulManager.cpp:452-519) and RcOutputOp.RECOVER (:426-438, 537-596)."""
+    outfile = str(workdir / "test.mtx")
     rays = np.array([[10, 10, 3], [0.0, 0.0, 1.0], [4.0, 5.0, 3.0], [0.0, 0.0, 1.0]])
     pr.initfunc()
     pr.calcontext(pr.RCCONTEXT)
@@ -470,18 +473,53 @@ def test_rcontrib_simul_manager_like_reference_test(golden):
     assert bincnt == 145
     mgr.yres = rays.shape[0] // 2
     mgr.set_flag(pr.RTimmIrrad, True)
-    mgr.add_modifier(modn="groundglow", outspec="test.mtx", binval="if(-Dx*0-Dy*0-Dz*-1,0,-1)", bincnt=1)
-    mgr.add_modifier(modn="skyglow", outspec="test.mtx", prms=RB_P, binval="rbin", bincnt=bincnt)
+    mgr.add_modifier(modn="groundglow", outspec=outfile, binval="if(-Dx*0-Dy*0-Dz*-1,0,-1)", bincnt=1)
+    mgr.add_modifier(modn="skyglow", outspec=outfile, prms=RB_P, binval="rbin", bincnt=bincnt)
+    out = mgr.get_output()
+    assert out.get_name() == outfile and out.row_bytes == 146 * 3 * 4
     pr.set_ray_params(rp)
     mgr.load_octree(str(golden / "contrib.oct"))
+    assert "oconv" in mgr.get_head_str() and mgr.get_head_len() == len(mgr.get_head_str())
+    mgr.add_header(["rcontrib", "-ab", "6", "a b"])
+    mgr.add_header("SOFTWARE= test")
+    assert mgr.get_head_str("SOFTWARE=") == " test" and mgr.get_head_str("NOPE=") is None
+    assert mgr.get_format() == ord("f")
     mgr.out_op = pr.RcOutputOp.FORCE
-    assert mgr.prep_output() == 2
+    assert mgr.prep_output() == 0                # rows already there
     mgr.set_thread_count(1)
     mgr.rcontrib(rays)
-    result = mgr.get_output_array()
+    result = np.array(mgr.get_output_array())
     assert result.shape == (2, 146 * 3) and result.dtype == np.float32
     assert result.sum() > 5.0                    # the reference's own assertion
+    mgr.cleanup(False)
+    raw = open(outfile, "rb").read()
+    head, _, body = raw.partition(b"\n\n")
+    assert head.startswith(b"#?RADIANCE\n") and b'rcontrib -ab 6 "a b"\n' in head and b"NROWS=0000000000000002\n" in head
+    assert b"NCOLS=146\nNCOMP=3\nBigEndian=0\nFORMAT=float" in head and (len(head) + 2) % 4 == 0
+    assert np.array_equal(np.frombuffer(body, dtype=np.float32).reshape(2, -1), result)
+    if refrun.available():                       # the file is a matrix any Radiance tool reads
+        txt = refrun.run("rmtxop", ["-fa", outfile]).decode()
+        assert "NROWS=2" in txt and "NCOLS=146" in txt
+    with pytest.raises(RuntimeError, match="file exists"):
+        mgr.out_op = pr.RcOutputOp.NEW
+        mgr.prep_output()
+    # RECOVER: pretend the job died after the first row; the second row is computed into the same file
+    with open(outfile, "r+b") as f:
+        f.seek(raw.index(b"NROWS=") + 6)
+        f.write(b"%016d" % 1)
+        f.seek(len(head) + 2 + 146 * 12)
+        f.write(b"\0" * (146 * 12))
+    mgr.out_op = pr.RcOutputOp.RECOVER
+    assert mgr.prep_output() == 1 and mgr.get_row_count() == 1
+    mgr.compute_record(rays[2:4])
+    assert mgr.get_row_finished() == 2
+    rec = np.array(mgr.get_output_array())
+    assert np.array_equal(rec[0], result[0])
+    assert rec[1].sum() == pytest.approx(result[1].sum(), rel=0.25) and rec[1].sum() > 0      # a new stochastic estimate of row 1
     mgr.cleanup(True)
+    assert b"NROWS=0000000000000002\n" in open(outfile, "rb").read(600)
+    with pytest.raises(RuntimeError, match="one file per bin"):
+        pr.RcontribSimulManager().add_modifier("skyglow", "bin%d.mtx", binval="rbin", bincnt=145)
     pr.set_ray_params(None)
 
 
