@@ -778,6 +778,10 @@ bool Engine::run(const TraceJob& job, const DParams& P, std::string& err) {
         batch = std::min(batch, std::max<size_t>(1, budget / per_row));
     }
     if (accum <= 0) batch = 1;
+    if (batch < nrec_total) {              // equal batches: a short last batch would run its waves on a half-empty GPU
+        const size_t nb = (nrec_total + batch - 1) / batch;
+        batch = (nrec_total + nb - 1) / nb;
+    }
     size_t rec = 0;
     while (rec < nrec_total) {
         size_t n = std::min(batch, nrec_total - rec);

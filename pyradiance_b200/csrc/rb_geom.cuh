@@ -393,6 +393,19 @@ __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, uns
             c += d * d;
         }
         c -= n2o.y * n2o.y;
+#if RB_SPHERE_INLINE == 2
+        // only the discriminant in line (the same expression quadratic() forms, with its own tolerance widened a
+        // thousandfold): a ray that cannot have a root is done here; the square root and the two divisions run in
+        // the out-of-line pass, together with the cone family's, so that one pass of heavy code serves both kinds
+        {
+            const double hb = b * 0.5, disc = hb * hb - a * c;
+            if (disc < -1e-9 * (1.0 + hb * hb)) return;
+            // both roots behind the origin (the centre lies behind and the origin is outside): no candidate either
+            if ((hb > 0.0) & (c > 1e-9 * (1.0 + c))) return;
+            sm.defer[wid][atomicAdd(&sm.ndef[wid], 1)] = (unsigned short)p;
+            return;
+        }
+#endif
         double r0, r1;
         const int nroots = quadratic(r0, r1, a, b, c);
         RB_DBG(3); if (nroots) RB_DBG(4);
@@ -498,7 +511,9 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
     const double cs = S.cusize;
     const int2* __restrict__ pool = reinterpret_cast<const int2*>(S.leafpool);
     unsigned fl = WF_DONE;       // WF_* flags of this lane's ray
+#if RB_SLOW_MIN > 0
     unsigned round = 0;
+#endif
     // cube the ray stands in: set by the refill or by phase C, consumed by phase A
     // (registers only between those two; parked in shared memory across phase B)
     unsigned ix = 0, iy = 0, iz = 0;

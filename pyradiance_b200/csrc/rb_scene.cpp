@@ -589,6 +589,18 @@ bool Scene::expand_volumes(const std::string& basedir, int depth) {
         nexpanded++;
     }
     index_modifiers();
+    // Instances and meshes are FLATTENED (one world-space copy of every inner surface per instance): memory grows
+    // with instances x inner surfaces where the reference's nested traversal (o_instance.c:16-71) does not.  A forest
+    // of heavy instances is refused by name instead of exhausting the host.
+    {
+        const char* e = getenv("RB_MAX_EXPANDED_SURFACES");
+        const size_t limit = e ? (size_t)atoll(e) : (size_t)200000000;
+        if (objs.size() > limit) {
+            error = "instance / mesh expansion gives " + std::to_string(objs.size()) + " surfaces (limit " + std::to_string(limit) +
+                    ", RB_MAX_EXPANDED_SURFACES): nested instance traversal is not built, instances are flattened at load";
+            return false;
+        }
+    }
     std::string err;
     if (!rebuild_octree(*this, 6, 16384, err)) { error = err; return false; }
     return true;

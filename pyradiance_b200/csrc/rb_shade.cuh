@@ -1248,29 +1248,31 @@ __device__ __noinline__ double sky_pattern(const PatRec& p, const double dir[3])
     const double Dy = dir[0] * p.xb[1] + dir[1] * p.xb[4] + dir[2] * p.xb[7];
     const double Dz = dir[0] * p.xb[2] + dir[1] * p.xb[5] + dir[2] * p.xb[8];
     auto Acos = [](double x) { return acos(x < -1 ? -1 : x > 1 ? 1 : x); };
-    const double* A = p.a - 1;                    // A[1]..A[10]
+    const double* const pa = p.a;
+#define A(i) pa[(i) - 1]                         /* the function file's A1..A10 */
     double sky, ground;
     if (p.kind == PAT_SKYBRIGHT) {
-        const double cosgamma = Dx * A[5] + Dy * A[6] + Dz * A[7];
-        const double gamma = Acos(cosgamma), zt = Acos(A[7]), eta = Acos(Dz);
-        const int sel = (int)(A[1] + .5);
+        const double cosgamma = Dx * A(5) + Dy * A(6) + Dz * A(7);
+        const double gamma = Acos(cosgamma), zt = Acos(A(7)), eta = Acos(Dz);
+        const int sel = (int)(A(1) + .5);
         if (sel == 1)
-            sky = A[2] * (.91 + 10 * exp(-3 * gamma) + .45 * cosgamma * cosgamma) * (Dz - .01 > 0 ? 1.0 - exp(-.32 / Dz) : 1.0) / A[4];
-        else if (sel == 2) sky = A[2] * (1 + 2 * Dz) / 3;
-        else if (sel == 3) sky = A[2];
+            sky = A(2) * (.91 + 10 * exp(-3 * gamma) + .45 * cosgamma * cosgamma) * (Dz - .01 > 0 ? 1.0 - exp(-.32 / Dz) : 1.0) / A(4);
+        else if (sel == 2) sky = A(2) * (1 + 2 * Dz) / 3;
+        else if (sel == 3) sky = A(2);
         else
-            sky = A[2] * ((1.35 * sin(5.631 - 3.59 * eta) + 3.12) * sin(4.396 - 2.6 * zt) + 6.37 - eta) / 2.326 *
-                  exp(gamma * -.563 * ((2.629 - eta) * (1.562 - zt) + .812)) / A[4];
-        ground = A[3];
+            sky = A(2) * ((1.35 * sin(5.631 - 3.59 * eta) + 3.12) * sin(4.396 - 2.6 * zt) + 6.37 - eta) / 2.326 *
+                  exp(gamma * -.563 * ((2.629 - eta) * (1.562 - zt) + .812)) / A(4);
+        ground = A(3);
     } else {
-        const double cosgamma = Dx * A[8] + Dy * A[9] + Dz * A[10];
+        const double cosgamma = Dx * A(8) + Dy * A(9) + Dz * A(10);
         const double gamma = Acos(cosgamma);
         const double dz = (Dz - 0.01 > 0) ? Dz : 0.01;
-        sky = A[1] * (1 + A[3] * exp(A[4] / dz)) * (1 + A[5] * exp(A[6] * gamma) + A[7] * cosgamma * cosgamma);
-        ground = A[2];
+        sky = A(1) * (1 + A(3) * exp(A(4) / dz)) * (1 + A(5) * exp(A(6) * gamma) + A(7) * cosgamma * cosgamma);
+        ground = A(2);
     }
     const double a = pow(Dz + 1.01, 10.0), b = pow(Dz + 1.01, -10.0);
     return (a * sky + b * ground) / (a + b);
+#undef A
 }
 
 // source.c:749-793 m_light.  Returns 1 and sets rcol when the ray sees the

@@ -159,6 +159,19 @@ class RowWindow:
         self.ctx.sync()
         dist.barrier(self.group)
 
+    def as_tensor(self):
+        """dst only: the matrix as a torch tensor over the window's memory (no copy; CUDA array interface)."""
+        if not self.owner:
+            return None
+        import torch
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": (self.nrecords, self.ncols, 3), "typestr": self.dtype.str,
+                                      "data": (int(self.base), False), "version": 2, "strides": None}
+        return torch.as_tensor(v, device="cuda")
+
     def download(self, out=None):
         """dst only: the matrix as a host array (one D2H over the gathering GPU's link)."""
         if not self.owner:

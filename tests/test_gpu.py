@@ -647,6 +647,34 @@ def test_full_size_properties(office100k):
     np.testing.assert_allclose(sub, m[500:600], rtol=1e-12, atol=1e-15)
 
 
+@pytest.mark.skipif(not refrun.available(), reason="oracle/_ref not built")
+def test_full_size_per_bin_vs_reference(office100k):
+    """BASELINE configs[1] AS CONFIGURED (the 100 k-polygon office, -ab 3 -ad 4096 -lw 1/4096, Reinhart MF:1) on a
+    stratified sample of its sensors, per bin against the unmodified reference on the same sensors: the statistical
+    protocol of SURVEY 8(d) with the reference's own repetitions as the truth (8 repetitions of each sensor, `-c 8`
+    accumulation of the same rays, on both sides).  Per bin with >= 30 expected first-level hits: within 4 sigma of
+    the two estimates for all but 0.1 %, nothing beyond 6 sigma; row sums within 1 % + 4 sigma."""
+    import os
+    n, acc = 24, 8
+    allsens = scenegen.office_sensors(100_000)
+    sens = allsens[((np.arange(n) + 0.5) * len(allsens) / n).astype(int)]
+    opts = ["-ab", "3", "-ad", "4096", "-lw", f"{1 / 4096:.4e}"]
+    w = np.pi / 4096
+    rep = np.repeat(sens, acc, axis=0)
+    ref = refrun.rcontrib(office100k, rep, ["-I+", "-c", str(acc)] + opts + RB_ARGS, nproc=os.cpu_count() or 8).reshape(n, 145, 3)[..., 0]
+    ctx = rc_ctx(office100k, opts)
+    g = ctx.rcontrib(rep, flags=_lib.RB_IRRAD_RCONTRIB, accum=acc).astype(np.float64)[:, :, 0]
+    cstar = 0.5 * (ref + g)                          # pooled estimate of the expectation (both are acc-x runs)
+    sel = cstar * acc >= 30 * w
+    assert sel.sum() >= 100
+    sig = np.sqrt(2 * cstar * w / acc)               # difference of two independent acc-x estimates
+    z = np.abs(g - ref)[sel] / sig[sel]
+    assert (z > 4).sum() <= max(1, int(1e-3 * sel.sum())) and z.max() <= 6, (z.max(), int((z > 4).sum()), int(sel.sum()))
+    rs_g, rs_r = g.sum(1), ref.sum(1)
+    assert np.all(np.abs(rs_g - rs_r) <= 0.01 * rs_r + 4 * np.sqrt(2 * np.maximum(rs_r, rs_g) * w / acc)), (rs_g, rs_r)
+    assert abs(rs_g.sum() - rs_r.sum()) <= 0.02 * rs_r.sum()
+
+
 @pytest.mark.parametrize("name", ["room", "meshroom"])
 def test_instances_and_meshes_vs_reference_golden(G, golden, name):
     """Config-5 ingredients: octree instances and triangle meshes, against the
