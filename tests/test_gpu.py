@@ -665,11 +665,16 @@ def test_full_size_per_bin_vs_reference(office100k):
     ctx = rc_ctx(office100k, opts)
     g = ctx.rcontrib(rep, flags=_lib.RB_IRRAD_RCONTRIB, accum=acc).astype(np.float64)[:, :, 0]
     cstar = 0.5 * (ref + g)                          # pooled estimate of the expectation (both are acc-x runs)
-    sel = cstar * acc >= 30 * w
-    assert sel.sum() >= 100
+    sel = cstar * acc >= 30 * w                      # (deep-plan sensors see little sky: a few dozen such bins)
+    assert sel.sum() >= 10, int(sel.sum())
     sig = np.sqrt(2 * cstar * w / acc)               # difference of two independent acc-x estimates
     z = np.abs(g - ref)[sel] / sig[sel]
     assert (z > 4).sum() <= max(1, int(1e-3 * sel.sum())) and z.max() <= 6, (z.max(), int((z > 4).sum()), int(sel.sum()))
+    # chi^2 over every bin with >= 5 expected hits: the normalised squared differences average to ~1 (they are a sum
+    # of weighted samples, not pure counts, hence the slack)
+    sel5 = cstar * acc >= 5 * w
+    chi = (((g - ref) ** 2)[sel5] / (sig[sel5] ** 2)).mean()
+    assert sel5.sum() >= 50 and chi <= 2.0, (int(sel5.sum()), chi)
     rs_g, rs_r = g.sum(1), ref.sum(1)
     assert np.all(np.abs(rs_g - rs_r) <= 0.01 * rs_r + 4 * np.sqrt(2 * np.maximum(rs_r, rs_g) * w / acc)), (rs_g, rs_r)
     assert abs(rs_g.sum() - rs_r.sum()) <= 0.02 * rs_r.sum()
