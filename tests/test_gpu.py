@@ -705,6 +705,31 @@ def test_instances_and_meshes_vs_reference_golden(G, golden, name):
     assert m1.shape == (1, 1, 3) and m1[0, 0, 0] > 0
 
 
+def test_device_octree_build_equals_host_build(workdir, monkeypatch):
+    """the level-by-level octree build on the GPU (rb_octbuild_gpu.cu: every surface / child-cube
+    overlap test of the reference, ot/o_face.c, ot/sphere.c, ot/o_cone.c, as device code) gives the file the
+    threaded host builder gives -- which tests/test_host.py pins byte for byte to the reference `oconv -f`."""
+    import hashlib
+    import time
+    for npoly, seed in ((30_000, 5), (200_000, 6)):
+        rad = workdir / f"devoct{npoly}.rad"
+        scenegen.write_office(rad, npolys=npoly, seed=seed)
+        monkeypatch.setenv("RB_OCTBUILD_DEVICE_STRICT", "1")
+        t = time.time(); _lib.oconv_file(rad, workdir / "dev.oct"); t_dev = time.time() - t
+        monkeypatch.setenv("RB_OCTBUILD_HOST", "1")
+        t = time.time(); _lib.oconv_file(rad, workdir / "host.oct"); t_host = time.time() - t
+        monkeypatch.delenv("RB_OCTBUILD_HOST")
+        a, b = (workdir / "dev.oct").read_bytes(), (workdir / "host.oct").read_bytes()
+        assert hashlib.sha256(a).hexdigest() == hashlib.sha256(b).hexdigest(), (npoly, len(a), len(b))
+        print(f"octree of {npoly} polygons: device path {t_dev:.2f} s, host path {t_host:.2f} s (parse and write included)")
+    monkeypatch.setenv("RB_OCTBUILD_DEVICE_STRICT", "1")          # other octree parameters: -n 3 -r 2048
+    rad = workdir / "devoct30000.rad"
+    _lib.oconv_file(rad, workdir / "dev2.oct", objlim=3, maxres=2048)
+    monkeypatch.setenv("RB_OCTBUILD_HOST", "1")
+    _lib.oconv_file(rad, workdir / "host2.oct", objlim=3, maxres=2048)
+    assert (workdir / "dev2.oct").read_bytes() == (workdir / "host2.oct").read_bytes()
+
+
 GEOM_CASES = [("curved", "curved.oct", "curved_rays"), ("curvedtext", "curved_text.oct", "curved_rays"),
               ("coinc", "coinc.oct", "coinc_rays"), ("coincfine", "coinc_fine.oct", "coinc_rays")]
 
