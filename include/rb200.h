@@ -195,6 +195,23 @@ int rb_ipc_export(rb_ctx* ctx, void* device_ptr, void* handle_out /* RB_IPC_HAND
 int rb_ipc_open(rb_ctx* ctx, const void* handle, void** device_ptr_out);
 int rb_ipc_close(rb_ctx* ctx, void* device_ptr);
 
+/* View rays on the device: util/vwrays.c:245-300 putrays() over common/image.c:214-305 viewray() -- the step before
+ * the path when the rays are the pixels of a view (the three-phase view matrix, BASELINE configs[3]: 2048 x 2048
+ * rays that never need to exist in host memory).  `view` is a VIEW after setview() (common/image.c:24-127):
+ * type letter ('v' perspective, 'l' parallel, 'c' cylinder, 'h' hemispherical, 'a' angular, 's' stereographic
+ * fisheye), unit vdir, hvec / vvec already scaled, hn2 / vn2 squared.  Writes xres * yres * repeat rays, scanlines
+ * from the top like vwrays (-Y yres +X xres), origin then direction, direction scaled by the aft distance when the
+ * view has an aft plane (pass RB_FLAG_LIMDIST to the tracer then), zeros where the view has no ray.  pj = pixel
+ * jitter (-pj), drawn from a counter-based generator keyed by `seed` and the ray index.  `out` is host memory, or
+ * device memory with RB_FLAG_OUT_ON_DEVICE. */
+typedef struct rb_view {
+    int type;
+    double vp[3], vdir[3], hvec[3], vvec[3];
+    double horiz, vert, hoff, voff, vfore, vaft, hn2, vn2;
+} rb_view;
+int rb_view_rays(rb_ctx* ctx, const rb_view* view, int xres, int yres, int repeat, double pj, uint64_t seed,
+                 double* out, unsigned flags);
+
 /* own octree builder for synthetic scenes (next-row f3): text scene -> frozen .oct */
 int rb_oconv(const char* rad_path, const char* oct_path, int objlim, int maxres,
              char* errbuf, size_t errlen);

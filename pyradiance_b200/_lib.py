@@ -31,6 +31,12 @@ class rb_params(C.Structure):
     ]
 
 
+class rb_view(C.Structure):
+    _fields_ = [("type", C.c_int), ("vp", C.c_double * 3), ("vdir", C.c_double * 3), ("hvec", C.c_double * 3),
+                ("vvec", C.c_double * 3), ("horiz", C.c_double), ("vert", C.c_double), ("hoff", C.c_double),
+                ("voff", C.c_double), ("vfore", C.c_double), ("vaft", C.c_double), ("hn2", C.c_double), ("vn2", C.c_double)]
+
+
 class rb_stats(C.Structure):
     _fields_ = [
         ("nrays", C.c_uint64), ("nodes", C.c_uint64), ("leafents", C.c_uint64),
@@ -97,6 +103,7 @@ SYMBOLS = [
     ("rb_device_sync", C.c_int, [_P]),
     ("rb_host_register", C.c_int, [_P, _P, C.c_size_t]),
     ("rb_host_unregister", C.c_int, [_P, _P]),
+    ("rb_view_rays", C.c_int, [_P, C.POINTER(rb_view), C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, _P, C.c_uint]),
     ("rb_ipc_export", C.c_int, [_P, _P, _P]),
     ("rb_ipc_open", C.c_int, [_P, _P, C.POINTER(C.c_void_p)]),
     ("rb_ipc_close", C.c_int, [_P, _P]),
@@ -342,6 +349,26 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.rb_device_sync(self.h))
+
+    # ---- view rays on the device (C ABI rb_view_rays) ----
+    def view_rays(self, view, xres, yres, repeat=1, pj=0.0, seed=0, out_ptr=None):
+        """`view`: a pyradiance_b200.views.View after set_view().  Returns a float64 [n, 6] array, or -- with
+        out_ptr, a device pointer with room for xres * yres * repeat rays -- writes there and returns the count."""
+        v = rb_view()
+        v.type = ord(view.type)
+        for k in range(3):
+            v.vp[k], v.vdir[k], v.hvec[k], v.vvec[k] = float(view.vp[k]), float(view.vdir[k]), float(view.hvec[k]), float(view.vvec[k])
+        v.horiz, v.vert, v.hoff, v.voff = view.horiz, view.vert, view.hoff, view.voff
+        v.vfore, v.vaft, v.hn2, v.vn2 = view.vfore, view.vaft, view.hn2, view.vn2
+        n = int(xres) * int(yres) * int(repeat)
+        if out_ptr is not None:
+            self._ck(self.lib.rb_view_rays(self.h, C.byref(v), int(xres), int(yres), int(repeat), float(pj), int(seed), out_ptr,
+                                           RB_FLAG_OUT_ON_DEVICE))
+            return n
+        out = np.empty((n, 6), dtype=np.float64)
+        self._ck(self.lib.rb_view_rays(self.h, C.byref(v), int(xres), int(yres), int(repeat), float(pj), int(seed),
+                                       out.ctypes.data, 0))
+        return out
 
     # ---- peer-memory window (the row gather of SURVEY 8e, see include/rb200.h) ----
     def ipc_export(self, dptr) -> bytes:

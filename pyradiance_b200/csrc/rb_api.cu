@@ -713,6 +713,18 @@ int rb_mtx_multiply(rb_ctx* c, const float* a, size_t nrows, size_t ninner, cons
     return 0;
 }
 
+int rb_view_rays(rb_ctx* c, const rb_view* view, int xres, int yres, int repeat, double pj, uint64_t seed, double* out,
+                 unsigned flags) {
+    if (!c->cuda_ok) return fail(c, c->cuda_err);
+    if (!view || xres <= 0 || yres <= 0 || repeat <= 0 || !out) return fail(c, "rb_view_rays: bad arguments");
+    if (!strchr("vlchas", view->type)) return fail(c, "unknown view type");
+    std::string err;
+    if (!rb::view_rays(c->device, (cudaStream_t)c->user_stream, *view, xres, yres, repeat, pj, seed, out,
+                       (flags & RB_FLAG_OUT_ON_DEVICE) != 0, err))
+        return fail(c, err);
+    return 0;
+}
+
 int rb_ipc_export(rb_ctx* c, void* dptr, void* handle_out) {
     static_assert(sizeof(cudaIpcMemHandle_t) == RB_IPC_HANDLE_BYTES, "handle size");
     if (!c->cuda_ok) return fail(c, c->cuda_err);

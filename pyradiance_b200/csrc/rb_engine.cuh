@@ -3,6 +3,7 @@
 #include <string>
 #include <vector>
 #include "rb_device.cuh"
+#include "../../include/rb200.h"
 
 namespace rb {
 struct DirectJob;
@@ -97,6 +98,10 @@ private:
     int nsrc_active_ = 0;       // distant sources direct() samples (not glow skies)
     std::string local_source_note_;
 };
+
+// rb_views.cu: view rays on the device (vwrays)
+bool view_rays(int device, cudaStream_t stream, const struct ::rb_view& v, int xres, int yres, int repeat, double pj,
+               unsigned long long seed, double* out, bool out_dev, std::string& err);
 
 // rb_mtx.cu: C[nr][nc][3] = A[nr][ni][3] x B[ni][nc][3] per colour channel (dctimestep's cm_multiply)
 bool mtx_multiply(int device, cudaStream_t stream, const float* A, size_t nr, size_t ni, const float* B, size_t nc,

@@ -281,6 +281,17 @@ def vwrays_main(argv: Sequence[str], stdin: bytes | None = None, seed=None) -> b
         yr = int(xr * va / pa + .5)
     if getdim:
         return (f"-x {xr} -y {yr}" + (" -ld+" if v.vaft > FTINY else "") + "\n").encode()
+    import os
+    from . import _lib
+    if not fromstdin and not os.environ.get("RB_VWRAYS_HOST") and _lib.device_count() > 0:
+        # the rays of a whole view come from the device kernel (C ABI rb_view_rays: one thread per ray, same
+        # expressions); the numpy code below stays for pixel lists on stdin and for machines without a GPU
+        ctx = _lib.Context(0)
+        try:
+            rays = ctx.view_rays(v, xr, yr, repeat, pj, 0 if seed is None else int(seed))
+        finally:
+            ctx.close()
+        return _format_rays(rays, outform)
     if fromstdin:
         vals = np.array((stdin or b"").split(), dtype=np.float64)
         vals = vals[:(vals.size // 2) * 2].reshape(-1, 2)
@@ -303,11 +314,40 @@ def vwrays_main(argv: Sequence[str], stdin: bytes | None = None, seed=None) -> b
     org = np.where(bad[:, None], 0.0, org)
     direc = np.where(bad[:, None], 0.0, direc)
     rays = np.concatenate([org, direc], axis=1)
+    return _format_rays(rays, outform)
+
+
+def _format_rays(rays, outform) -> bytes:
     if outform == "d":
         return np.ascontiguousarray(rays, dtype=np.float64).tobytes()
     if outform == "f":
         return np.ascontiguousarray(rays, dtype=np.float32).tobytes()
     return "".join("%.5e %.5e %.5e %.5e %.5e %.5e\n" % tuple(r) for r in rays).encode()
+
+
+def view_from_args(view_args: Sequence[str], xres: int, yres: int, pixel_aspect: float = 1.0):
+    """View options -> (View after set_view(), xres, yres after the aspect normalisation of vwrays): what
+    Context.view_rays() takes to generate the rays of a view straight into device memory."""
+    v = View()
+    words = [str(a) for a in view_args]
+    k = 0
+    while k < len(words):
+        if words[k] == "-vf":
+            if not view_from_file(words[k + 1], v):
+                raise RBError(f"{words[k + 1]}: no view in file")
+            k += 2
+        else:
+            k += 1 + get_view_opts(v, words[k:])
+    set_view(v)
+    va = math.sqrt(v.vn2 / v.hn2)
+    pa = pixel_aspect
+    if pa <= FTINY:
+        pass
+    elif va * xres > pa * yres:
+        xres = int(yres / va * pa + .5)
+    else:
+        yres = int(xres * va / pa + .5)
+    return v, xres, yres
 
 
 def vwrays(pixpos: bytes | None = None, unbuf: bool = False, outform: str = "a", ray_count: int = 1,

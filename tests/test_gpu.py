@@ -705,6 +705,43 @@ def test_instances_and_meshes_vs_reference_golden(G, golden, name):
     assert m1.shape == (1, 1, 3) and m1[0, 0, 0] > 0
 
 
+def test_view_rays_on_device_equal_host_vwrays(monkeypatch):
+    """vwrays on the device (C ABI rb_view_rays, csrc/rb_views.cu) against the numpy restatement
+    of util/vwrays.c + common/image.c (which tests/test_host.py pins to the reference binary): all six view types,
+    offsets, fore / aft planes (directions scaled by the aft distance), pixels without a ray, several rays per
+    pixel; then straight into device memory and traced from there."""
+    from pyradiance_b200 import views
+    cases = [["-vtv", "-vp", "1", "2", "1.5", "-vd", ".3", "1", "-.1", "-vu", "0", "0", "1", "-vh", "60", "-vv", "40"],
+             ["-vtl", "-vp", "5", "5", "9", "-vd", "0", "0", "-1", "-vu", "0", "1", "0", "-vh", "12", "-vv", "8", "-vo", ".5", "-va", "6"],
+             ["-vtc", "-vp", "1", "2", "1.5", "-vd", "0", "1", "0", "-vu", "0", "0", "1", "-vh", "200", "-vv", "50", "-vs", ".1", "-vl", "-.2"],
+             ["-vth", "-vp", "1", "2", "1.5", "-vd", "0", "0", "1", "-vu", "0", "1", "0", "-vh", "180", "-vv", "180"],
+             ["-vta", "-vp", "1", "2", "1.5", "-vd", "0", "-1", "0", "-vu", "0", "0", "1", "-vh", "180", "-vv", "180", "-vo", ".1", "-va", "30"],
+             ["-vts", "-vp", "1", "2", "1.5", "-vd", "1", "0", "0", "-vu", "0", "0", "1", "-vh", "160", "-vv", "120"]]
+    for view in cases:
+        for rep in (1, 3):
+            monkeypatch.setenv("RB_VWRAYS_HOST", "1")
+            host = np.frombuffer(pr.vwrays(outform="d", ray_count=rep, xres=97, yres=64, view=view), dtype=np.float64).reshape(-1, 6)
+            monkeypatch.delenv("RB_VWRAYS_HOST")
+            dev = np.frombuffer(pr.vwrays(outform="d", ray_count=rep, xres=97, yres=64, view=view), dtype=np.float64).reshape(-1, 6)
+            assert dev.shape == host.shape and dev.shape[0] > 1000
+            np.testing.assert_allclose(dev, host, rtol=0, atol=2e-12, err_msg=" ".join(view))
+    # into device memory, and traced from there: the 3-phase view matrix never holds its rays on the host
+    v, xr, yr = views.view_from_args(cases[3], 64, 64)
+    ctx = _lib.Context(0)
+    n = xr * yr
+    d_rays = ctx.device_alloc(n * 48)
+    assert ctx.view_rays(v, xr, yr, out_ptr=d_rays) == n
+    back = np.empty((n, 6))
+    ctx.device_download(back, d_rays)
+    np.testing.assert_array_equal(back, ctx.view_rays(v, xr, yr))
+    ctx.device_free(d_rays)
+    # jitter: inside the pixel, different per ray, reproducible per seed
+    j1 = ctx.view_rays(v, xr, yr, repeat=2, pj=1.0, seed=5)
+    j2 = ctx.view_rays(v, xr, yr, repeat=2, pj=1.0, seed=5)
+    j3 = ctx.view_rays(v, xr, yr, repeat=2, pj=1.0, seed=6)
+    assert np.array_equal(j1, j2) and not np.array_equal(j1, j3) and not np.array_equal(j1[0::2], j1[1::2])
+
+
 def test_device_octree_build_equals_host_build(workdir, monkeypatch):
     """the level-by-level octree build on the GPU (rb_octbuild_gpu.cu: every surface / child-cube
     overlap test of the reference, ot/o_face.c, ot/sphere.c, ot/o_cone.c, as device code) gives the file the
