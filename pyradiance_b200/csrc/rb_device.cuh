@@ -43,6 +43,9 @@ struct DScene {
     const SrcRec* __restrict__ srcs;
     const PatRec* __restrict__ pats;
     const int* __restrict__ otrack;
+    const BsdfRec* __restrict__ bsdfs;          // BSDF / aBSDF materials: Klems-matrix data (rb_bsdf.cuh)
+    const BsdfBasis* __restrict__ bsdfbases;
+    const unsigned* __restrict__ bsdfpool;
     // integer walk (rb_geom.cuh): positions are maxdepth-bit integers, inv_cell = 2^maxdepth / cusize; top[] holds,
     // for every cell of level topk (x | y << topk | z << 2 topk), the node word and the level of the cube that
     // contains the cell (an interior node at level topk, or the leaf / empty cube above it)

@@ -338,7 +338,7 @@ Engine::Engine(int device) : dev_(device) {
 Engine::~Engine() {
     cudaSetDevice(dev_);
     cudaDeviceSynchronize();
-    void* ptrs[] = {d_nodes_, d_leaf_, d_hdr_, d_geom_, d_mats_, d_srcs_, d_pats_, d_otrack_, d_top_, d_bins_, q_[0], q_[1],
+    void* ptrs[] = {d_nodes_, d_leaf_, d_hdr_, d_geom_, d_mats_, d_srcs_, d_pats_, d_bsdfs_, d_bsdfbases_, d_bsdfpool_, d_otrack_, d_top_, d_bins_, q_[0], q_[1],
                     h_[0], h_[1], d_hits_, dq_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_, d_slow_};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_cnt_) cudaFreeHost(h_cnt_);
@@ -382,7 +382,8 @@ bool Engine::upload_scene(const FlatScene& fs, const Scene& sc, std::string& err
     if (!upload(d_nodes_, cap_nodes_, fs.nodes, err) || !upload(d_leaf_, cap_leaf_, fs.leaf2, err) ||
         !upload(d_hdr_, cap_hdr_, fs.objhdr, err) || !upload(d_geom_, cap_geom_, fs.geom, err) ||
         !upload(d_mats_, cap_mats_, fs.mats, err) || !upload(d_srcs_, cap_srcs_, fs.srcs, err) ||
-        !upload(d_pats_, cap_pats_, fs.pats, err))
+        !upload(d_pats_, cap_pats_, fs.pats, err) || !upload(d_bsdfs_, cap_bsdfs_, fs.bsdfs, err) ||
+        !upload(d_bsdfbases_, cap_bsdfbases_, fs.bsdfbases, err) || !upload(d_bsdfpool_, cap_bsdfpool_, fs.bsdfpool, err))
         return false;
     std::vector<int> ot(sc.objs.size(), -1);
     if (!upload(d_otrack_, cap_otrack_, ot, err)) return false;
@@ -442,6 +443,7 @@ bool Engine::upload_scene(const FlatScene& fs, const Scene& sc, std::string& err
     S_.nodes = (const int*)d_nodes_; S_.leafpool = (const int*)d_leaf_;
     S_.objhdr = (const int4*)d_hdr_; S_.geom = (const double*)d_geom_;
     S_.mats = (const MatRec*)d_mats_; S_.srcs = (const SrcRec*)d_srcs_; S_.pats = (const PatRec*)d_pats_;
+    S_.bsdfs = (const BsdfRec*)d_bsdfs_; S_.bsdfbases = (const BsdfBasis*)d_bsdfbases_; S_.bsdfpool = (const unsigned*)d_bsdfpool_;
     S_.otrack = (const int*)d_otrack_;
     has_local_sources_ = false;                  // local emitters: direct() always runs in k_direct
     for (const auto& s : fs.srcs)

@@ -70,8 +70,8 @@ private:
     bool user_stream_ = false;
     DScene S_{};
     void *d_nodes_ = nullptr, *d_leaf_ = nullptr, *d_hdr_ = nullptr, *d_geom_ = nullptr,
-         *d_mats_ = nullptr, *d_srcs_ = nullptr, *d_pats_ = nullptr, *d_otrack_ = nullptr, *d_bins_ = nullptr, *d_top_ = nullptr;
-    size_t cap_nodes_ = 0, cap_leaf_ = 0, cap_hdr_ = 0, cap_geom_ = 0, cap_mats_ = 0, cap_srcs_ = 0, cap_pats_ = 0,
+         *d_mats_ = nullptr, *d_srcs_ = nullptr, *d_pats_ = nullptr, *d_bsdfs_ = nullptr, *d_bsdfbases_ = nullptr, *d_bsdfpool_ = nullptr, *d_otrack_ = nullptr, *d_bins_ = nullptr, *d_top_ = nullptr;
+    size_t cap_nodes_ = 0, cap_leaf_ = 0, cap_hdr_ = 0, cap_geom_ = 0, cap_mats_ = 0, cap_srcs_ = 0, cap_pats_ = 0, cap_bsdfs_ = 0, cap_bsdfbases_ = 0, cap_bsdfpool_ = 0,
            cap_otrack_ = 0, cap_bins_ = 0, cap_top_ = 0;      // bytes behind the scene pointers (re-used by the next upload)
     cudaStream_t own_stream_ = nullptr;    // the stream this engine created (stream_ may be the caller's)
     int nbins_ = 0, ncols_ = 0;

@@ -35,7 +35,7 @@ static const TypeInfo kTypes[] = {
     {"plastic2", OT_PLASTIC2}, {"metal2", OT_METAL2},
     {"plasfunc", OT_OTHER_MATERIAL}, {"metfunc", OT_OTHER_MATERIAL},
     {"mirror", OT_OTHER_MATERIAL}, {"transfunc", OT_OTHER_MATERIAL},
-    {"BRTDfunc", OT_OTHER_MATERIAL}, {"BSDF", OT_OTHER_MATERIAL},
+    {"BRTDfunc", OT_OTHER_MATERIAL}, {"BSDF", OT_BSDF},
     {"WGMDfunc", OT_OTHER_MATERIAL}, {"plasdata", OT_OTHER_MATERIAL},
     {"metdata", OT_OTHER_MATERIAL}, {"transdata", OT_OTHER_MATERIAL},
     {"prism1", OT_OTHER_MATERIAL}, {"prism2", OT_OTHER_MATERIAL},
@@ -69,7 +69,7 @@ bool ot_is_material(int t) {
     case OT_PLASTIC: case OT_METAL: case OT_GLASS: case OT_TRANS: case OT_GLOW:
     case OT_LIGHT: case OT_ILLUM: case OT_SPOTLIGHT: case OT_DIELECTRIC:
     case OT_INTERFACE: case OT_MIST: case OT_ABSDF: case OT_TRANS2:
-    case OT_ANTIMATTER: case OT_OTHER_MATERIAL: case OT_PLASTIC2: case OT_METAL2:
+    case OT_ANTIMATTER: case OT_OTHER_MATERIAL: case OT_PLASTIC2: case OT_METAL2: case OT_BSDF:
         return true;
     }
     return false;
@@ -264,6 +264,7 @@ bool Scene::load_octree(const std::string& path) {
         std::string dir;
         size_t sl = path.rfind('/');
         if (sl != std::string::npos) dir = path.substr(0, sl + 1);
+        basedir = dir;
         if (!expand_volumes(dir)) return false;
     }
     return true;
@@ -1040,6 +1041,8 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
     fs.leafpool = sc.leafpool;
     fs.objhdr.assign((size_t)n * 4, 0);
     std::vector<int> matslot(n, -2);    // object -> material slot (-2 unknown)
+    std::unordered_map<std::string, int> bsdf_index;     // BSDF file name -> slot in fs.bsdfs (loaded once, like SDcacheFile)
+    bool load_failed = false;
     auto note_unsupported = [&](const std::string& s) {
         if (fs.unsupported_note.empty()) fs.unsupported_note = s;
     };
@@ -1102,6 +1105,55 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
                 break;
             }
             for (int k = 0; k < 3; k++) r.u[k] = u[0] * x.m[0][k] + u[1] * x.m[1][k] + u[2] * x.m[2][k];   // multv3
+            break;
+        }
+        case OT_BSDF: case OT_ABSDF: {
+            // m_bsdf.c:58-71,641-654,704-716.  BSDF: thick file ux uy uz funcfile [xf]; aBSDF: file ux uy uz funcfile [xf];
+            // 0, 3, 6 or 9 reals (diffuse colours added to the file's front / back reflection and its transmission).
+            // Thickness and up vector must be numeric constants; the function file's transform is applied here.
+            const int ht = m.otype == OT_BSDF ? 1 : 0;
+            r.kind = ht ? MK_BSDF : MK_ABSDF;
+            if (ht && !m.sargs.empty() && m.sargs[0] != "0") r.flags |= 8;       // isBSDFproxy() (rt/otspecial.h:34-35)
+            if ((int)m.sargs.size() < ht + 5 || m.fargs.size() > 9 || m.fargs.size() % 3) {
+                r.kind = MK_UNSUPPORTED; note_unsupported("bad # arguments for " + m.tname + " \"" + m.name + "\"");
+                break;
+            }
+            r.nargs = (int)m.fargs.size();
+            if (m.fargs.size() == 9) { const float f8 = (float)m.fargs[8]; memcpy(&r.pad[1], &f8, 4); }
+            double cv[4] = {0, 0, 0, 0};         // thick, ux, uy, uz
+            bool konst = true;
+            for (int k = 0; k < 4; k++) {
+                if (k == 0 && !ht) continue;
+                const char* b = m.sargs[k == 0 ? 0 : ht + k].c_str(); char* e = nullptr;
+                cv[k] = strtod(b, &e);
+                if (e == b || *e) konst = false;
+            }
+            if (!konst) {
+                r.kind = MK_UNSUPPORTED;
+                note_unsupported("thickness / up vector of " + m.tname + " \"" + m.name + "\" is not a numeric constant (.cal expressions are not built)");
+                break;
+            }
+            Xf x; std::string xe;
+            if (!parse_xf(m.sargs, ht + 5, x, xe)) {
+                r.kind = MK_UNSUPPORTED; note_unsupported(xe + " for " + m.tname + " \"" + m.name + "\"");
+                break;
+            }
+            for (int k = 0; k < 3; k++) r.u[k] = cv[1] * x.m[0][k] + cv[2] * x.m[1][k] + cv[3] * x.m[2][k];   // multv3
+            double thick = cv[0];
+            if ((-1e-6 <= thick) & (thick <= 1e-6)) thick = 0;
+            r.pad2 = thick * x.sca;
+            const std::string& fname = m.sargs[ht];
+            auto it = bsdf_index.find(fname);
+            if (it == bsdf_index.end()) {
+                const std::string path = find_radiance_file(fname, sc.basedir);
+                int bi = -1; std::string be;
+                if (path.empty()) be = "cannot find BSDF file \"" + fname + "\"";
+                else load_klems_bsdf(path, fs, bi, be);
+                if (bi < 0) { err = be + " (" + m.tname + " \"" + m.name + "\")"; load_failed = true; }
+                it = bsdf_index.emplace(fname, bi).first;
+            }
+            if (it->second < 0) { r.kind = MK_UNSUPPORTED; break; }
+            r.pad[0] = it->second;
             break;
         }
         case OT_DIELECTRIC: r.kind = MK_DIELECTRIC; need(5); break;      // dielectric.c (built without DISPERSE)
@@ -1426,6 +1478,7 @@ bool flatten_scene(const Scene& sc, FlatScene& fs, std::string& err) {
         }
         fs.srcs.push_back(s);
     }
+    if (load_failed) return false;               // a BSDF file that a used material names could not be loaded (err says which)
     return true;
 }
 

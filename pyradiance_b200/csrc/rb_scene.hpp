@@ -31,6 +31,7 @@ enum OType : int {
     OT_DIELECTRIC, OT_INTERFACE, OT_MIST, OT_ABSDF, OT_TRANS2, OT_ANTIMATTER,
     OT_OTHER_MATERIAL, OT_PATTERN, OT_TEXTURE, OT_MIXTURE,
     OT_PLASTIC2, OT_METAL2,      // anisotropic (rt/aniso.c), with OT_TRANS2 above
+    OT_BSDF,                     // BSDF (rt/m_bsdf.c), with OT_ABSDF above
     OT_NTYPES
 };
 
@@ -67,6 +68,7 @@ struct Scene {
     std::vector<int> leafpool;
     int maxdepth = 0;
     std::string error;
+    std::string basedir;        // directory of the octree file: where auxiliary files (BSDF XML) are looked for last
 
     bool load_octree(const std::string& path);
     // last modifier named `name` defined before object `before` (-1: any)
@@ -100,7 +102,8 @@ enum : int {            // device primitive kinds (x & 0xff)
 // material kinds on device
 enum : int {
     MK_NONE = 0, MK_PLASTIC, MK_METAL, MK_TRANS, MK_GLASS, MK_LIGHT, MK_GLOW,
-    MK_ILLUM, MK_SPOT, MK_UNSUPPORTED, MK_PLASTIC2, MK_METAL2, MK_TRANS2, MK_DIELECTRIC, MK_INTERFACE
+    MK_ILLUM, MK_SPOT, MK_UNSUPPORTED, MK_PLASTIC2, MK_METAL2, MK_TRANS2, MK_DIELECTRIC, MK_INTERFACE,
+    MK_BSDF, MK_ABSDF
 };
 
 struct MatRec {          // 96 bytes
@@ -111,9 +114,10 @@ struct MatRec {          // 96 bytes
     float a[8];          // real args (as given)
     int alt;             // illum: alternate material slot (-1 = void/none)
     int pat;             // first pattern record under the material (-1 = none)
-    int pad[2];
-    double u[3];         // plastic2 / metal2 / trans2: orientation vector, function transform applied (aniso.c:305-313)
-    double pad2;
+    int pad[2];          // BSDF / aBSDF: pad[0] = index into bsdfs[], pad[1] = bits of the ninth real (a[] holds eight)
+    double u[3];         // plastic2 / metal2 / trans2: orientation vector, function transform applied (aniso.c:305-313);
+                         // BSDF / aBSDF: the up vector, likewise (m_bsdf.c:705-712)
+    double pad2;         // BSDF: thickness, scaled by the function transform
 };
 static_assert(sizeof(MatRec) == 96, "MatRec must be 96 bytes");
 
@@ -128,6 +132,28 @@ struct PatRec {
                          // D' = D . xb (func.c:455-458)
 };
 enum : int { PAT_SKYBRIGHT = 1, PAT_PEREZLUM = 2 };
+
+// ---- BSDF / aBSDF materials: Klems-matrix data of one XML file (common/bsdf_m.c), rb_bsdf.cpp builds these ----
+#define RB_BSDF_MAXLATS 46
+struct BsdfBasis {       // bsdf_m.h ANGLE_BASIS
+    int nangles, nlat;
+    double tmin[RB_BSDF_MAXLATS + 1];   // lower polar bound of each latitude in degrees; tmin[nlat] closes the last one
+    int nphis[RB_BSDF_MAXLATS + 1];     // azimuth count per latitude; nphis[nlat] = 0
+    int pad;
+};
+struct BsdfComp {        // one SDSpectralDF with its single matrix component (SDMat)
+    int present, ninc, nout;
+    int ib, ob;          // incident / exiting basis (index into bsdfbases[])
+    unsigned mtx;        // offsets into bsdfpool[] (32-bit words): float value[o * ninc + i] = mBSDF_value(o, i)
+    unsigned cdf, ctot;  // unsigned cdf[ninc][nout + 1], double ctot[ninc]: make_cdist() of every incident direction
+    unsigned rcdf, rctot;// unsigned rcdf[nout][ninc + 1], double rctot[nout]: the same through reciprocity
+    double minProjSA, maxHemi;
+};
+struct BsdfRec {
+    BsdfComp c[4];       // rf, rb, tf, tb (SDData; XML front / back already swapped)
+    double lamb[4];      // cieY of rLambFront, rLambBack, tLambFront, tLambBack
+};
+enum : int { BC_RF = 0, BC_RB, BC_TF, BC_TB };
 
 struct SrcRec {          // distant & local sources (source.h SRCREC subset)
     double sloc[3];      // direction (distant) or position
@@ -153,6 +179,9 @@ struct FlatScene {
     std::vector<MatRec>  mats;
     std::vector<SrcRec>  srcs;
     std::vector<PatRec>  pats;
+    std::vector<BsdfRec> bsdfs;      // one per BSDF file named by a BSDF / aBSDF material
+    std::vector<BsdfBasis> bsdfbases;
+    std::vector<uint32_t> bsdfpool;  // matrices and cumulative tables
     std::vector<int>     nodes;      // same encoding as Scene
     std::vector<int>     leafpool;
     std::vector<int>     leaf2;      // (count,0),(id, geom offset)... pairs; nodes[] index these
@@ -167,5 +196,7 @@ bool rebuild_octree(Scene& sc, int objlim, int maxres, std::string& err);
 bool build_octree_file(const Scene& sc, const std::string& cmdline, const std::string& oct_path, int objlim,
                        int maxres, std::string& err);
 std::string find_radiance_file(const std::string& name, const std::string& basedir);
+// Klems-matrix BSDF XML file -> fs.bsdfs / bsdfbases / bsdfpool (rb_bsdf.cpp); index = its slot in fs.bsdfs
+bool load_klems_bsdf(const std::string& path, FlatScene& fs, int& index, std::string& err);
 
 }  // namespace rb

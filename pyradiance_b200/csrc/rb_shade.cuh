@@ -23,6 +23,7 @@
 #include "rb_device.cuh"
 #include "rb_bins.cuh"
 #include "rb_geom.cuh"
+#include "rb_bsdf.cuh"
 
 namespace rb {
 namespace cg = cooperative_groups;
@@ -367,9 +368,17 @@ struct NormDat {           // normal.c:53-67 NORMDAT
     double pnorm[3], pdot;
     // plastic2 / metal2 / trans2 only (aniso.c:46-62 ANISODAT), valid when specfl & SP_ANISO
     double u[3], v[3], u_alpha, v_alpha;
+    // BSDF / aBSDF only (m_bsdf.c:80-96 BSDFDAT), valid when specfl & SP_BSDF: mcolor = rdiff, scolor = tdiff,
+    // prdir = vray, u / v / w = the rows of toloc, pnorm as handed to direct() (turned towards the hit side)
+    double w[3];
+    float cthru[3], cthru_surr[3];
+    int bsdf, dmode;       // dmode: 0 dir_bsdf, 1 dir_brdf, 2 dir_btdf
 };
 struct DirectJob { RayCtx r; NormDat nd; };
-enum : int { SP_REFL = 01, SP_TRAN = 02, SP_PURE = 04, SP_FLAT = 010, SP_RBLT = 020, SP_TBLT = 040, SP_ANISO = 0100 };
+enum : int { SP_REFL = 01, SP_TRAN = 02, SP_PURE = 04, SP_FLAT = 010, SP_RBLT = 020, SP_TBLT = 040, SP_ANISO = 0100,
+             SP_BSDF = 0200 };
+__device__ void dir_bsdf(float scval[3], const WaveArgs& A, const NormDat& np, const RayCtx& r, const double ldir[3], double omega,
+                         unsigned long long jkey);
 
 // aniso.c:64-182 diraniso(): source coefficient of the anisotropic Gaussian (Ward / Geisler-Moroder-Duer)
 __device__ __forceinline__ void diraniso(float scval[3], const NormDat& np, const RayCtx& r, const double ldir[3],
@@ -422,9 +431,15 @@ __device__ __forceinline__ void diraniso(float scval[3], const NormDat& np, cons
 }
 
 // normal.c:71-173
-__device__ __forceinline__ void dirnorm(float scval[3], const NormDat& np, const RayCtx& r, const double ldir[3],
-                        double omega, double dstrsrc) {
-    if (np.specfl & SP_ANISO) { diraniso(scval, np, r, ldir, omega, dstrsrc); return; }
+// `jkey`: random key of the shadow ray being set up (the BSDF materials jitter their evaluation, m_bsdf.c:309-329)
+// FAST (k_shade_fast): isotropic materials only -- the other two are not in that kernel's code at all.
+template <bool FAST = false>
+__device__ __forceinline__ void dirnorm(float scval[3], const WaveArgs& A, const NormDat& np, const RayCtx& r, const double ldir[3],
+                        double omega, double dstrsrc, unsigned long long jkey) {
+    if (!FAST) {
+        if (np.specfl & SP_BSDF) { dir_bsdf(scval, A, np, r, ldir, omega, jkey); return; }
+        if (np.specfl & SP_ANISO) { diraniso(scval, np, r, ldir, omega, dstrsrc); return; }
+    }
     scval[0] = scval[1] = scval[2] = 0.f;
     double ldot = dot3(np.pnorm, ldir);
     if (ldot < 0.0 ? np.trans <= RB_FTINY : np.trans >= 1.0 - RB_FTINY) return;
@@ -469,6 +484,7 @@ __device__ __forceinline__ void dirnorm(float scval[3], const NormDat& np, const
 // behaviour, which rcontrib forces: rcmain.c:164-171).  One source -> one
 // shadow ray; its random key is child (nchild0 + sn) of the shaded ray, so the
 // serial and the warp-cooperative forms below emit identical rays.
+template <bool FAST = false>
 __device__ __forceinline__ void direct_one(const WaveArgs& A, const RayCtx& r, const NormDat& nd, int sn,
                                            unsigned nchild0) {
     const SrcRec& s = A.S.srcs[sn];
@@ -497,7 +513,7 @@ __device__ __forceinline__ void direct_one(const WaveArgs& A, const RayCtx& r, c
     if (normalize3(ldir) == 0.0) return;
     double dom = s.ss2;                              // nopart: whole source
     float scval[3];
-    dirnorm(scval, nd, r, ldir, dom, A.P.dstrsrc);
+    dirnorm<FAST>(scval, A, nd, r, ldir, dom, A.P.dstrsrc, key);
     if (!(max3(scval) > 0.f)) return;
     // shadow test ray: TSHADOW if through the surface (ray.h:87 thrudir)
     bool thru = (r.rod > 0) ^ (dot3(r.ron, ldir) > 0);
@@ -518,9 +534,10 @@ __device__ __forceinline__ void direct_one(const WaveArgs& A, const RayCtx& r, c
     push_ray(A, q);
 }
 
+template <bool FAST = false>
 __device__ __forceinline__ void direct(const WaveArgs& A, RayCtx& r, const NormDat& nd) {
     const int ns = A.S.nsrcs;
-    for (int sn = 0; sn < ns; sn++) direct_one(A, r, nd, sn, r.nchild);
+    for (int sn = 0; sn < ns; sn++) direct_one<FAST>(A, r, nd, sn, r.nchild);
     r.nchild += (unsigned)ns;
 }
 
@@ -592,7 +609,7 @@ __device__ __noinline__ void local_sample(const WaveArgs& A, const RayCtx& r, co
         dom *= d * d; d += (double)s.spot_flen; dom /= d * d;
     }
     float scval[3];
-    dirnorm(scval, nd, r, ldir, dom, dj);
+    dirnorm(scval, A, nd, r, ldir, dom, dj, key);
     if (!(max3(scval) > 0.f)) return;
     // srcvalue(): the sample must hit the source surface, on its emitting side
     {
@@ -723,6 +740,7 @@ __device__ void direct_local(const WaveArgs& A, const RayCtx& r, const NormDat& 
 #define RB_COOP_SRC_MIN 64
 #endif
 
+template <bool FAST = false>
 __device__ __forceinline__ void direct_or_park(const WaveArgs& A, RayCtx& r, const NormDat& nd) {
     if (A.dout) {
         unsigned slot = reserve_slot(&A.C->nd_out);
@@ -731,7 +749,7 @@ __device__ __forceinline__ void direct_or_park(const WaveArgs& A, RayCtx& r, con
         A.dout[slot].nd = nd;
         return;
     }
-    direct(A, r, nd);
+    direct<FAST>(A, r, nd);
 }
 
 // ambient.c:229-297 (aa = 0 branch) + ambcomp.c:350-422
@@ -988,7 +1006,7 @@ __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind
         double bn[3] = {-nd.pnorm[0], -nd.pnorm[1], -nd.pnorm[2]};
         multambient(A, r, sct, bn);
     }
-    direct_or_park(A, r, nd);
+    direct_or_park<FAST>(A, r, nd);
 }
 
 // fvect.c:159-196 getperpendicular() with randomize = 0
@@ -1183,6 +1201,299 @@ __device__ __noinline__ void m_dielectric(const WaveArgs& A, RayCtx& r, int mkin
     }
 }
 
+// ---- BSDF / aBSDF (rt/m_bsdf.c) on Klems-matrix data ----
+// m_bsdf.c:116-219 compute_through(): the "through" (unscattered) component an aBSDF lets view and shadow rays see.
+__device__ __noinline__ void bsdf_compute_through(const BsdfRef& B, const NormDat& nd, bool hitfront, float cthru[3], float cthru_surr[3]) {
+    const float dir2check[29][2] = {
+        {0, 0}, {-0.6f, 0}, {0, 0.6f}, {0, -0.6f}, {0.6f, 0}, {-0.6f, 0.6f}, {-0.6f, -0.6f}, {0.6f, 0.6f}, {0.6f, -0.6f},
+        {-1.2f, 0}, {0, 1.2f}, {0, -1.2f}, {1.2f, 0}, {-1.2f, 1.2f}, {-1.2f, -1.2f}, {1.2f, 1.2f}, {1.2f, -1.2f}, {-1.8f, 0},
+        {0, 1.8f}, {0, -1.8f}, {1.8f, 0}, {-1.8f, 1.8f}, {-1.8f, -1.8f}, {1.8f, 1.8f}, {1.8f, -1.8f}, {-2.4f, 0}, {0, 2.4f},
+        {0, -2.4f}, {2.4f, 0}};
+    const BsdfRec& R = *B.rec;
+    const int tk = bsdf_tcomp(R, hitfront);
+    if (tk < 0) return;                              // no specular transmission
+    const double minProjSA = R.c[tk].minProjSA;
+    const double srchrad = sqrt(minProjSA);          // evaluate peak
+    const double* vray = nd.prdir;
+    double vy[29]; signed char ord[29];
+    auto tdir_of = [&](int i, double t[3]) {
+        t[0] = -vray[0] + (double)dir2check[i][0] * srchrad;
+        t[1] = -vray[1] + (double)dir2check[i][1] * srchrad;
+        t[2] = -vray[2];
+        bsdf_normalize(t);
+    };
+    for (int i = 0; i < 29; i++) {
+        double t[3];
+        tdir_of(i, t);
+        vy[i] = sd_eval(B, vray, t);
+        int j = i;                                   // near-peak values in descending order (stable)
+        while (j > 0 && vy[ord[j - 1]] < vy[i]) { ord[j] = ord[j - 1]; j--; }
+        ord[j] = (signed char)i;
+    }
+    if (vy[ord[0]] <= RB_FTINY) return;              // zero BTDF here
+    float vpeak = 0.f, vsurr = 0.f;                  // grayscale data: one channel, expanded at the end
+    double vypeak = 0, tomsum = 0, tomsurr = 0;
+    int ns = 0;
+    for (int i = 0; i < 29; i++) {                   // combine top unique values
+        const double y = vy[ord[i]];
+        if (i && y == vy[ord[i - 1]]) continue;      // assume duplicate sample
+        double t[3], tomega[2];
+        tdir_of(ord[i], t);
+        sd_size(B, tomega, vray, t, SDQ_MIN);
+        float vcol = (float)y;
+        vcol = (float)(vcol * tomega[0]);
+        if (tomega[0] > 1.5 * minProjSA || vypeak > 8. * y * ns) {      // not part of peak?
+            if (!i) return;                          // abort
+            vsurr += vcol;
+            tomsurr += tomega[0];
+            continue;
+        }
+        vpeak += vcol;
+        tomsum += tomega[0];
+        vypeak += y;
+        ++ns;
+    }
+    if (tomsurr < 0.2 * tomsum) return;              // insufficient surround?
+    vsurr = (float)(vsurr * (1. / tomsurr));         // surround is avg. BTDF
+    float btdiff = (float)(vray[2] > 0 ? R.lamb[2] : R.lamb[3]);      // get diffuse BTDF
+    btdiff = (float)(btdiff * (1. / RB_PI));
+    if ((vpeak -= (float)(tomsum * btdiff)) < 0) vpeak = 0;            // remove diffuse contrib.
+    if ((vsurr -= btdiff) < 0) vsurr = 0;
+    if (vpeak < .0005f) return;                      // < 0.05% specular?
+    bsdf_gray(cthru_surr, vsurr);
+    bsdf_gray(cthru, vpeak);
+}
+
+// m_bsdf.c:222-233 bsdf_jitter()
+__device__ __forceinline__ void bsdf_jitter(double vres[3], const double vray[3], double sr_psa, double specjitter,
+                                            unsigned long long key, unsigned dim) {
+    vres[0] = vray[0]; vres[1] = vray[1]; vres[2] = vray[2];
+    if (specjitter < 1.) sr_psa *= specjitter;
+    if (sr_psa <= RB_FTINY) return;
+    vres[0] += sr_psa * (.5 - rnd01(key, dim));
+    vres[1] += sr_psa * (.5 - rnd01(key, dim + 1));
+    bsdf_normalize(vres);
+}
+
+// m_bsdf.c:236-342 direct_specular_OK(): the BSDF's non-diffuse value towards a light source
+__device__ __noinline__ bool bsdf_direct_specular(float scval[3], const BsdfRef& B, const NormDat& np, const RayCtx& r,
+                                                  const double ldir[3], double omega, double specjitter, unsigned long long jkey) {
+    scval[0] = scval[1] = scval[2] = 0.f;
+    const double toloc[3][3] = {{np.u[0], np.u[1], np.u[2]}, {np.v[0], np.v[1], np.v[2]}, {np.w[0], np.w[1], np.w[2]}};
+    const double* vray = np.prdir;
+    const BsdfRec& R = *B.rec;
+    double vsrc[3];
+    if (!sd_map_dir(vsrc, toloc, ldir)) return false;
+    if (((vsrc[2] > 0) ^ (vray[2] > 0)) && max3(np.cthru) > (float)RB_FTINY) {      // check indirect over-counting
+        const double dx = vsrc[0] + vray[0], dy = vsrc[1] + vray[1];
+        const int tk = bsdf_tcomp(R, r.rod > 0);
+        const double mpsa = R.c[tk].minProjSA;
+        const double tomega = omega * fabs(vsrc[2]);
+        if (dx * dx + dy * dy <= (2.5 * 4. / RB_PI) * (tomega + mpsa + 2. * sqrt(tomega * mpsa))) {
+            if (max3(np.cthru_surr) <= (float)RB_FTINY) return false;
+            scval[0] = np.cthru_surr[0]; scval[1] = np.cthru_surr[1]; scval[2] = np.cthru_surr[2];
+            return true;                             // return non-zero surround BTDF
+        }
+    }
+    double svY;                                      // will discount diffuse portion
+    const bool anyt = R.c[BC_TF].present | R.c[BC_TB].present;
+    switch ((vsrc[2] > 0) << 1 | (vray[2] > 0)) {
+    case 3: if (!R.c[BC_RF].present) return false; svY = R.lamb[0]; break;
+    case 0: if (!R.c[BC_RB].present) return false; svY = R.lamb[1]; break;
+    case 1: if (!anyt) return false; svY = R.lamb[2]; break;
+    default: if (!anyt) return false; svY = R.lamb[3]; break;
+    }
+    double diffY = 0;
+    float cdiff[3] = {0.f, 0.f, 0.f};
+    if (svY > RB_FTINY) { diffY = svY *= 1. / RB_PI; bsdf_gray(cdiff, svY); }
+    double tomega[2];
+    sd_size(B, tomega, vray, vsrc, SDQ_MIN);
+    int nsamp = 1, scnt = 0;
+    const double tsr = sqrt(tomega[0]);
+    if (tsr > 0) {                                   // check if sampling BSDF
+        nsamp = (int)(4. * specjitter * r.rweight + .5);
+        nsamp += !nsamp;
+    }
+    for (int i = nsamp; i--;) {                      // jitter to fuzz BSDF cells
+        double vjit[3];
+        bsdf_jitter(vjit, vray, tsr, specjitter, jkey, 40u + 2u * (unsigned)i);
+        const double y = sd_eval(B, vjit, vsrc);
+        if (y - diffY <= RB_FTINY) { ++scnt; continue; }      // still counts as 0 contribution
+        double tomega2[2];
+        sd_size(B, tomega2, vjit, vsrc, SDQ_MIN);              // check for variable resolution
+        if (tomega2[0] < .12 * tomega[0]) continue;            // not safe to include
+        float csmp[3];
+        bsdf_gray(csmp, y);
+        scval[0] += csmp[0]; scval[1] += csmp[1]; scval[2] += csmp[2];
+        ++scnt;
+    }
+    if (!scnt) return false;                         // no valid specular samples?
+    for (int k = 0; k < 3; k++) scval[k] = (float)(scval[k] * (1. / scnt));       // weighted average BSDF
+    if (diffY > RB_FTINY)                            // subtract diffuse contribution
+        for (int k = 0; k < 3; k++) if ((scval[k] -= cdiff[k]) < 0) scval[k] = 0;
+    return true;
+}
+
+// m_bsdf.c:345-482 dir_bsdf() / dir_brdf() / dir_btdf(), chosen by np.dmode (patterns are not built: pcol = 1)
+__device__ __noinline__ void dir_bsdf(float scval[3], const WaveArgs& A, const NormDat& np, const RayCtx& r, const double ldir[3],
+                                      double omega, unsigned long long jkey) {
+    scval[0] = scval[1] = scval[2] = 0.f;
+    const double ldot = dot3(np.pnorm, ldir);
+    if (np.dmode == 0) { if ((-RB_FTINY <= ldot) & (ldot <= RB_FTINY)) return; }
+    else if (np.dmode == 1) { if (ldot <= RB_FTINY) return; }
+    else if (ldot >= -RB_FTINY) return;
+    if (np.dmode != 2 && ldot > 0 && max3(np.mcolor) > (float)RB_FTINY) {           // diffuse reflected component
+        const double d = ldot * omega * (1. / RB_PI);
+        for (int k = 0; k < 3; k++) scval[k] += (float)(np.mcolor[k] * d);
+    }
+    if (np.dmode != 1 && ldot < 0 && max3(np.scolor) > (float)RB_FTINY) {           // diffuse transmission
+        const double d = -ldot * omega * (1. / RB_PI);
+        for (int k = 0; k < 3; k++) scval[k] += (float)(np.scolor[k] * d);
+    }
+    const BsdfRef B = {A.S.bsdfs + np.bsdf, A.S.bsdfbases, A.S.bsdfpool};
+    float sct[3];
+    if (!bsdf_direct_specular(sct, B, np, r, ldir, omega, A.P.specjitter, jkey)) return;
+    const double d = (ldot < 0 ? -ldot : ldot) * omega;
+    for (int k = 0; k < 3; k++) scval[k] += (float)(sct[k] * d);
+}
+
+// m_bsdf.c:625-804 m_bsdf() with sample_sdf() :555-623 and sample_sdcomp() :484-553 in their single-sample form
+// (-ss <= 1.5).  mkind = MK_BSDF (thickness: proxy surface) or MK_ABSDF (through component).
+__device__ __noinline__ void m_bsdf(const WaveArgs& A, RayCtx& r, const MatRec& m) {
+    const DParams& P = A.P;
+    const bool hasthick = m.kind == MK_BSDF;
+    const bool hitfront = r.rod > 0;
+    if (!hitfront & !P.backvis) { raytrans(A, r); return; }       // check backface visibility
+    const double thick = hasthick ? m.pad2 : 0.;
+    if (thick != 0 && ((r.crtype & RT_SHADOW) || !(r.crtype & (RT_SPECULAR | RT_AMBIENT)) || ((thick > 0) ^ hitfront))) {
+        raytrans(A, r);                              // hide our proxy
+        return;
+    }
+    if (hasthick && (r.crtype & RT_SHADOW)) return;  // early shadow check #1
+    const BsdfRef B = {A.S.bsdfs + m.pad[0], A.S.bsdfbases, A.S.bsdfpool};
+    const BsdfRec& R = *B.rec;
+    const bool anyt = R.c[BC_TF].present | R.c[BC_TB].present;
+    if ((r.crtype & RT_SHADOW) && !anyt) return;     // early shadow check #2
+    NormDat nd;
+    nd.specfl = SP_BSDF; nd.bsdf = m.pad[0]; nd.dmode = 0;
+    float a8 = 0.f;
+    if (m.nargs >= 9) a8 = __int_as_float(m.pad[1]);
+    // diffuse components (nd.mcolor = rdiff, nd.scolor = tdiff)
+    bsdf_gray(nd.mcolor, hitfront ? R.lamb[0] : R.lamb[1]);
+    if (hitfront) { if (m.nargs >= 3) for (int k = 0; k < 3; k++) nd.mcolor[k] += m.a[k]; }
+    else if (m.nargs >= 6) for (int k = 0; k < 3; k++) nd.mcolor[k] += m.a[3 + k];
+    bsdf_gray(nd.scolor, hitfront ? R.lamb[2] : R.lamb[3]);
+    if (m.nargs >= 9) { nd.scolor[0] += m.a[6]; nd.scolor[1] += m.a[7]; nd.scolor[2] += a8; }
+    // local BSDF coordinates
+    double pert[3] = {0., 0., 0.};
+    ray_pert(A.S, r, false, pert);
+    raynormal(nd.pnorm, r, pert);
+    double toloc[3][3], fromloc[3][3];
+    bool ok = sd_comp_xform(toloc, nd.pnorm, m.u);
+    if (ok) {
+        const double nv[3] = {-r.dir[0], -r.dir[1], -r.dir[2]};
+        ok = sd_map_dir(nd.prdir, toloc, nv);
+    }
+    if (!ok) return;                                 // "Illegal orientation vector" (a warning in the reference)
+    for (int k = 0; k < 3; k++) { nd.u[k] = toloc[0][k]; nd.v[k] = toloc[1][k]; nd.w[k] = toloc[2][k]; }
+    const double* vray = nd.prdir;
+    for (int k = 0; k < 3; k++) nd.cthru[k] = nd.cthru_surr[k] = 0.f;
+    if (m.kind == MK_ABSDF) {                        // consider through component
+        bsdf_compute_through(B, nd, hitfront, nd.cthru, nd.cthru_surr);
+        if (r.crtype & RT_SHADOW) {                  // attempt to pass shadow ray
+            float rc[3] = {nd.cthru[0], nd.cthru[1], nd.cthru[2]};
+            QRay q;
+            if (rayorigin(P, r, RT_TRANS, rc, true, q)) {
+                q.dir[0] = r.dir[0]; q.dir[1] = r.dir[1]; q.dir[2] = r.dir[2];
+                push_ray(A, q);
+            }
+            return;
+        }
+    }
+    if (!sd_inv_xform(fromloc, toloc)) return;
+    double sr_vpsa[2];
+    sd_size(B, sr_vpsa, vray, nullptr, SDQ_MIN + SDQ_MAX);        // determine BSDF resolution
+    sr_vpsa[0] = sqrt(sr_vpsa[0]); sr_vpsa[1] = sqrt(sr_vpsa[1]);
+    if (!hitfront) { nd.pnorm[0] = -nd.pnorm[0]; nd.pnorm[1] = -nd.pnorm[1]; nd.pnorm[2] = -nd.pnorm[2]; }   // perturb normal towards hit
+    const unsigned long long bkey = child_key(r.key, r.nchild++);
+    float unsamp[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};      // runsamp, tunsamp
+    for (int xmit = 0; xmit < 2; xmit++) {           // sample_sdf(SDsampSpR), then sample_sdf(SDsampSpT)
+        const int ck = xmit ? bsdf_tcomp(R, hitfront) : bsdf_rcomp(R, hitfront);
+        if (ck < 0) continue;                        // no specular component?
+        bool hasthru = xmit && !(r.crtype & (RT_SPECULAR | RT_AMBIENT)) && max3(nd.cthru) > (float)RB_FTINY;
+        const bool hasthru0 = hasthru;
+        double b = 0;
+        if (hasthru) {                               // separate view sample?
+            float rc[3] = {nd.cthru[0], nd.cthru[1], nd.cthru[2]};
+            QRay q;
+            if (rayorigin(P, r, RT_TRANS, rc, true, q)) {
+                q.dir[0] = r.dir[0]; q.dir[1] = r.dir[1]; q.dir[2] = r.dir[2];
+                push_ray(A, q);
+                b = 0.2651058201058201 * nd.cthru[0] + 0.6701058201058201 * nd.cthru[1] + 0.0647883597883598 * nd.cthru[2];     // pbright(), color.h CIE_rf/gf/bf
+            } else
+                hasthru = false;
+        }
+        if (R.c[ck].maxHemi - b <= RB_FTINY) b = 0;  // have specular to sample?
+        else {
+            double vjit[3];
+            bsdf_jitter(vjit, vray, sr_vpsa[1], P.specjitter, bkey, 10u + 20u * (unsigned)xmit);
+            b = sd_direct_hemi(B, vjit, xmit != 0) - b;
+            b *= (b > 0);
+        }
+        if (b <= P.specthresh + RB_FTINY) {          // below sampling threshold?
+            if (b > RB_FTINY) unsamp[xmit][0] = unsamp[xmit][1] = unsamp[xmit][2] = (float)b;     // XXX no color from BSDF
+            continue;
+        }
+        // sample_sdcomp(), one sample
+        double xrand = rnd01(bkey, 12u + 20u * (unsigned)xmit);
+        if (P.specjitter < 1.) xrand = .5 + P.specjitter * (xrand - .5);
+        double vsmp[3];
+        bsdf_jitter(vsmp, vray, sr_vpsa[0], P.specjitter, bkey, 13u + 20u * (unsigned)xmit);
+        const double vinc[3] = {vsmp[0], vsmp[1], vsmp[2]};
+        const double cieY = comp_sample(B, ck, vsmp, xrand, rnd01(bkey, 15u + 20u * (unsigned)xmit), rnd01(bkey, 16u + 20u * (unsigned)xmit));
+        if (cieY <= RB_FTINY) continue;              // zero component?
+        if (hasthru0) {                              // check for view ray
+            const double dx = vinc[0] + vsmp[0], dy = vinc[1] + vsmp[1];
+            if (dx * dx + dy * dy <= sr_vpsa[0] * sr_vpsa[0]) continue;            // exclude view sample
+        }
+        double sdir[3];
+        if (!sd_map_dir(sdir, fromloc, vsmp)) continue;
+        float rc[3];
+        bsdf_gray(rc, cieY);
+        QRay q;
+        if (!rayorigin(P, r, xmit ? RT_TSPECULAR : RT_RSPECULAR, rc, true, q)) continue;
+        q.dir[0] = sdir[0]; q.dir[1] = sdir[1]; q.dir[2] = sdir[2];
+        if (xmit && thick != 0) for (int k = 0; k < 3; k++) q.org[k] += r.ron[k] * -thick;      // need to offset origin?
+        push_ray(A, q);
+    }
+    // compute indirect diffuse
+    float sct[3];
+    for (int k = 0; k < 3; k++) sct[k] = nd.mcolor[k] + unsamp[0][k];
+    if (max3(sct) > (float)RB_FTINY) multambient(A, r, sct, nd.pnorm);            // ambient from reflection
+    for (int k = 0; k < 3; k++) sct[k] = nd.scolor[k] + unsamp[1][k];
+    if (max3(sct) > (float)RB_FTINY) {               // ambient from other side
+        const double bnorm[3] = {-nd.pnorm[0], -nd.pnorm[1], -nd.pnorm[2]};
+        if (thick != 0) {                            // proxy with offset?
+            const double keep[3] = {r.rop[0], r.rop[1], r.rop[2]};
+            for (int k = 0; k < 3; k++) r.rop[k] = keep[k] + r.ron[k] * thick;
+            multambient(A, r, sct, bnorm);
+            for (int k = 0; k < 3; k++) r.rop[k] = keep[k];
+        } else
+            multambient(A, r, sct, bnorm);
+    }
+    // add direct component
+    if (!anyt && max3(nd.scolor) <= (float)RB_FTINY) { nd.dmode = 1; direct_or_park(A, r, nd); }           // reflection only
+    else if (thick == 0) { nd.dmode = 0; direct_or_park(A, r, nd); }                                   // thin surface scattering
+    else {
+        nd.dmode = 1; direct_or_park(A, r, nd);      // reflection first
+        if (A.dout) r.nchild += (unsigned)A.S.nsrcs; // (a parked job numbers its shadow rays from the count it was parked with)
+        const double keep[3] = {r.rop[0], r.rop[1], r.rop[2]};
+        for (int k = 0; k < 3; k++) r.rop[k] = keep[k] + r.ron[k] * -thick;        // offset for transmitted
+        nd.dmode = 2; direct_or_park(A, r, nd);      // separate transmission
+        for (int k = 0; k < 3; k++) r.rop[k] = keep[k];
+    }
+}
+
 // glass.c:46-165
 template <bool FAST = false>
 __device__ __forceinline__ void m_glass(const WaveArgs& A, RayCtx& r, const float* a, int nargs) {
@@ -1352,7 +1663,8 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
             return;
         }
         if (tst_irrad) {                // raytirrad(), raytrace.c:210-228
-            if (k == MK_TRANS || k == MK_GLASS || k == MK_TRANS2 || k == MK_DIELECTRIC || k == MK_INTERFACE) { raytrans(A, r); break; }
+            if (k == MK_TRANS || k == MK_GLASS || k == MK_TRANS2 || k == MK_DIELECTRIC || k == MK_INTERFACE || k == MK_ABSDF ||
+                (k == MK_BSDF && (m->flags & 8))) { raytrans(A, r); break; }      // istransp(m) || isBSDFproxy(m)
             if (!(k >= MK_LIGHT && k <= MK_SPOT)) { nk = MK_PLASTIC; for (int j = 0; j < 7; j++) na[j] = j < 3 ? (float)RB_PI : 0.f; break; }
         }
         if (k == MK_PLASTIC || k == MK_METAL || k == MK_TRANS) { nk = k; for (int j = 0; j < 7; j++) na[j] = m->a[j]; break; }
@@ -1360,6 +1672,7 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
         if (!FAST) {
             if (k >= MK_PLASTIC2 && k <= MK_TRANS2) { m_aniso(A, r, k, m->a, m->u); break; }
             if (k == MK_DIELECTRIC || k == MK_INTERFACE) { m_dielectric(A, r, k, (int)(m - S.mats), m->a); break; }
+            if (k == MK_BSDF || k == MK_ABSDF) { m_bsdf(A, r, *m); break; }
         }
         int rv = m_light<FAST>(A, r, *m, rcol, zeroed);
         if (rv == 1) {
@@ -1392,6 +1705,7 @@ __device__ __forceinline__ bool shade_is_simple(const WaveArgs& A, const QRay& q
     const MatRec& m = A.S.mats[hd.z];
     const int k = m.kind;
     if (k == MK_UNSUPPORTED || (m.flags & 3)) return false;   // error paths and patterns
+    if (k == MK_BSDF || k == MK_ABSDF) return false;          // m_bsdf() is compiled into the general kernel only
     const bool emitter = k >= MK_LIGHT && k <= MK_SPOT;
     if (A.P.do_irrad && !(crtype & ~(RT_PRIMARY | RT_TRANS)) && !emitter) return true;    // raytirrad(): passes through or Lambertian
     if (k == MK_PLASTIC || k == MK_METAL || k == MK_TRANS) { double a2 = m.a[4]; a2 *= a2; return a2 <= RB_FTINY; }

@@ -1187,6 +1187,82 @@ def test_anisotropic_materials_vs_reference_golden(golden):
     assert (np.abs(m.mean(0) - g["rc_mean"]) <= 5 * sem + 0.02 * g["rc_mean"] + 1e-9).all()
 
 
+def test_bsdf_materials_vs_reference_golden(golden, workdir):
+    """the BSDF and aBSDF materials (rt/m_bsdf.c over Klems-matrix XML data, common/bsdf_m.c) on the
+    device, against the unmodified reference (tests/golden/make_golden_bsdfmat.py): three synthetic BSDF files (Klems
+    full with all four blocks, Klems half with one transmission block -> reciprocity, a file-defined basis in Rows
+    order, reflection only); aBSDF with its through component, BSDF proxies of both thickness signs over detail
+    geometry, an opaque and a thin BSDF, up vectors with and without a function transform, extra diffuse reals.
+    (1) nothing sampled (-st 1 -ss 0): surface, modifier, distance and value of 2400 view rays from both sides and -I
+    values under / over the panels within 1e-5, with the distant sun only (direct() in the shading thread) and with
+    local lamps (k_direct); (2) -ss 1 -st 0: per-ray means of 200 view rays x 1200 repetitions, -I -ab 1 sensors x 150
+    and rcontrib coefficients per emitter within 5 combined standard errors of the reference run with -u+;
+    (3) what is not built fails by name."""
+    g = np.load(golden / "bsdfmat.npz")
+    rays = g["rays"]
+    D = golden / "bsdfmat"
+    for tag, octf in (("", "bsdfmat.oct"), ("lamp_", "bsdflamp.oct")):
+        out = pr.rtrace(rays.tobytes(), str(D / octf), header=False, inform="d", outform="a", outspec="vLsm",
+                        params=[str(a) for a in g["args"]]).decode()
+        rows = [ln.split("\t") for ln in out.splitlines()]
+        assert len(rows) == len(rays)
+        assert [r[4] for r in rows] == list(g[tag + "surf"]) and [r[5] for r in rows] == list(g[tag + "mod"])
+        np.testing.assert_allclose([float(r[3]) for r in rows], g[tag + "dist"], rtol=2e-6)
+        val = np.array([[float(x) for x in r[0:3]] for r in rows])
+        np.testing.assert_allclose(val, g[tag + "value"], rtol=1e-5, atol=1e-9)
+        ctx = _lib.Context(0)
+        ctx.load_octree(D / octf)
+        ctx.set_options([str(a) for a in g["args"]])
+        v, _ = ctx.rtrace(g["sensors"], flags=_lib.RB_IRRAD_RTRACE)
+        np.testing.assert_allclose(v, g[tag + "irrad"], rtol=1e-5, atol=1e-9)
+    for m in ("awin", "ablind", "prox", "nprox", "opaque", "thin", "avert"):
+        assert (g["mod"] == m).sum() >= 80
+    # (2) sampled
+    pick, reps = g["st_pick"], 1200
+    ctx = _lib.Context(0)
+    ctx.load_octree(D / "bsdfmat.oct")
+    ctx.set_options([str(a) for a in g["st_args"]])
+    v, _ = ctx.rtrace(np.tile(rays[pick], (reps, 1)))
+    v = v.reshape(reps, len(pick), 3)
+    sem = np.sqrt(v.var(0, ddof=1) / reps + g["st_sem"] ** 2)
+    assert (np.abs(v.mean(0) - g["st_mean"]) <= 5 * sem + 1e-5 * g["st_mean"]).all()
+    assert (v.std(0)[:, 1] > 1e-3 * v.mean(0)[:, 1]).mean() > 0.5         # the samples do vary
+    s2, reps2 = g["ab1_sensors"], 150
+    ctx = _lib.Context(0)
+    ctx.load_octree(D / "bsdfmat.oct")
+    ctx.set_options([str(a) for a in g["ab1_args"]])
+    v, _ = ctx.rtrace(np.tile(s2, (reps2, 1)), flags=_lib.RB_IRRAD_RTRACE)
+    v = v.reshape(reps2, len(s2), 3)
+    sem = np.sqrt(v.var(0, ddof=1) / reps2 + g["ab1_sem"] ** 2)
+    assert (np.abs(v.mean(0) - g["ab1_mean"]) <= 5 * sem).all()
+    rc = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+    rc.load_octree(D / "bsdfmat.oct")
+    rc.set_options([str(a) for a in g["rc_args"]])
+    for m in ("skyg", "sunl", "gndg"):
+        rc.add_modifier(m, "", "0", 1)
+    m = rc.rcontrib(np.tile(s2, (reps2, 1)), flags=_lib.RB_IRRAD_RCONTRIB, dtype=np.float64).reshape(reps2, len(s2), 3, 3)
+    sem = np.sqrt(m.var(0, ddof=1) / reps2 + g["rc_sem"] ** 2)
+    assert (np.abs(m.mean(0) - g["rc_mean"]) <= 5 * sem + 0.004 * g["rc_mean"] + 1e-9).all()
+    assert (g["rc_mean"][:, 0] > 0).all() and (g["rc_mean"][:, 1] > 0).any()
+    # (3) refusals by name: a tensor-tree file, colour blocks, a missing file, a thickness given as an expression
+    xml = (D / "fabric.xml").read_text()
+    (workdir / "tt.xml").write_text(xml.replace("<IncidentDataStructure>Columns", "<IncidentDataStructure>TensorTree4"))
+    (workdir / "col.xml").write_text(xml.replace(">Visible</Wavelength>", ">CIE-X</Wavelength>", 1))
+    for k, (mat, pat) in enumerate(((f"void aBSDF w\n5 {workdir}/tt.xml 0 1 0 .\n0\n0\n", "tensor-tree"),
+                                    (f"void aBSDF w\n5 {workdir}/col.xml 0 1 0 .\n0\n0\n", "CIE-X"),
+                                    ("void aBSDF w\n5 nosuchfile.xml 0 1 0 .\n0\n0\n", "cannot find BSDF file"),
+                                    (f"void BSDF w\n6 thick {D}/fabric.xml 0 1 0 bsdf.cal\n0\n0\n", "unsupported material.*BSDF"))):
+        rad = workdir / f"badbsdf{k}.rad"
+        rad.write_text(scenegen.MATERIALS + scenegen.SKY + mat + "\nw polygon pane\n0\n0\n12 0 0 1  4 0 1  4 4 1  0 4 1\n\n")
+        octf = workdir / f"badbsdf{k}.oct"
+        scenegen.build_octree(rad, octf)
+        c = _lib.Context(0)
+        with pytest.raises(_lib.RBError, match=pat):
+            c.load_octree(octf)
+            c.set_options(["-ab", "0"])
+            c.rtrace(np.array([[2, 2, 3, 0, 0, -1.0]]))
+
+
 def test_dielectric_interface_vs_reference_golden(golden):
     """dielectric / interface on the device (m_dielectric: Fresnel terms, total
     reflection, refracted direction and solid-angle ratio; the medium id carried by every ray,
