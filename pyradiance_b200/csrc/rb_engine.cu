@@ -109,10 +109,13 @@ __device__ __forceinline__ void load_ray(const WaveArgs& A, const QRay& q, const
     }
 }
 
-// The lean shading kernel: plastic / metal / trans without a sampled highlight, glass, plain emitters, misses --
-// nearly every ray of a daylight job -- with the rest of the material set compiled out (shade_ray<true>): no
-// out-of-line callee takes the ray by reference, so it lives in registers.  What it may not shade
-// (shade_is_simple) is left, by queue slot, to the general kernel below.
+// Shading is split three ways by what a ray hit (shade_class(), rb_shade.cuh):
+//   k_shade_fast  one thread per queued ray: reads the ray and its hit, classifies it, and shades the LEAN class itself --
+//                 plastic / metal without a sampled highlight, plain emitters, surfaces without a material: nearly
+//                 every ray of a daylight job -- with the rest of the material set compiled out (shade_ray<true, true>);
+//                 rays that end without effect (SC_NONE) stop right there;
+//   k_shade_mid   glass, trans without a sampled highlight, spotlights (shade_ray<true, false>), by queue slot;
+//   k_shade       every material, by queue slot.
 #ifndef RB_FAST_MINBLOCKS
 #define RB_FAST_MINBLOCKS 6
 #endif
@@ -121,19 +124,32 @@ __device__ __forceinline__ void load_ray(const WaveArgs& A, const QRay& q, const
 __device__ __noinline__ void shade_fast_one(const WaveArgs& A, unsigned i) {
     const QRay q = A.qin[i];
     const HitRec hr = A.hits[i];
-    if (!shade_is_simple(A, q, hr)) {
-        const unsigned slot = reserve_slot(&A.C->nslow);
-        A.slow[slot] = i;
+    const int cls = shade_class(A, q, hr);
+    if (cls == SC_NONE) return;
+    if (cls != SC_LEAN) {
+        const bool mid = cls == SC_MID;
+        const unsigned slot = reserve_slot(mid ? &A.C->nmid : &A.C->nslow);
+        (mid ? A.mid : A.slow)[slot] = i;
         return;
     }
-    if (hr.robj < 0) return;
     RayCtx r;
     load_ray(A, q, hr, r);
-    shade_ray<true>(A, r);
+    shade_ray<true, true>(A, r);
 }
 __global__ void __launch_bounds__(RB_SHADE_THREADS, RB_FAST_MINBLOCKS) k_shade_fast(const __grid_constant__ WaveArgs A) {
     const unsigned n = A.C->nin;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) shade_fast_one(A, i);
+}
+__device__ __noinline__ void shade_mid_one(const WaveArgs& A, unsigned i) {
+    const QRay q = A.qin[i];
+    const HitRec hr = A.hits[i];
+    RayCtx r;
+    load_ray(A, q, hr, r);
+    shade_ray<true, false>(A, r);
+}
+__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_FAST_MINBLOCKS) k_shade_mid(const __grid_constant__ WaveArgs A) {
+    const unsigned n = A.C->nmid;
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) shade_mid_one(A, A.mid[j]);
 }
 
 // The general shading kernel: every material.  With A.slow it takes the queue slots k_shade_fast left over
@@ -278,7 +294,7 @@ __global__ void k_gate(DCounters* C, unsigned qcap) {
 }
 __global__ void k_prepare(DCounters* C, unsigned wave) {
     const unsigned n = (C->overflow || C->errflag) ? 0u : C->nq_out;
-    C->nin = n; C->nq_out = 0; C->next_ray = 0; C->nslow = 0;
+    C->nin = n; C->nq_out = 0; C->next_ray = 0; C->nslow = 0; C->nmid = 0;
     C->rays_traced += n;
     C->wave_nin[wave & 63] = n;
 }
@@ -339,7 +355,7 @@ Engine::~Engine() {
     cudaSetDevice(dev_);
     cudaDeviceSynchronize();
     void* ptrs[] = {d_nodes_, d_leaf_, d_hdr_, d_geom_, d_mats_, d_srcs_, d_pats_, d_bsdfs_, d_bsdfbases_, d_bsdfpool_, d_otrack_, d_top_, d_bins_, q_[0], q_[1],
-                    h_[0], h_[1], d_hits_, dq_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_, d_slow_};
+                    h_[0], h_[1], d_hits_, dq_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_, d_slow_, d_mid_};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_cnt_) cudaFreeHost(h_cnt_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -481,9 +497,9 @@ bool Engine::ensure_queues(std::string& err, size_t hint) {
     if (q_[0] && want <= qcap_) return true;
     if (q_[0]) {                            // grow: drop the old queues first
         CK(cudaStreamSynchronize(stream_));
-        void* old[] = {q_[0], q_[1], h_[0], h_[1], d_hits_, dq_, d_slow_};
+        void* old[] = {q_[0], q_[1], h_[0], h_[1], d_hits_, dq_, d_slow_, d_mid_};
         for (void* p : old) if (p) cudaFree(p);
-        q_[0] = q_[1] = nullptr; h_[0] = h_[1] = nullptr; d_hits_ = nullptr; dq_ = nullptr; d_slow_ = nullptr;
+        q_[0] = q_[1] = nullptr; h_[0] = h_[1] = nullptr; d_hits_ = nullptr; dq_ = nullptr; d_slow_ = nullptr; d_mid_ = nullptr;
     }
     size_t freeb = 0, totalb = 0;
     CK(cudaMemGetInfo(&freeb, &totalb));
@@ -498,6 +514,7 @@ bool Engine::ensure_queues(std::string& err, size_t hint) {
     CK(cudaMalloc(&h_[1], hcap_ * sizeof(QHemi)));
     CK(cudaMalloc(&d_hits_, qcap_ * sizeof(HitRec)));
     CK(cudaMalloc(&d_slow_, qcap_ * sizeof(unsigned)));
+    CK(cudaMalloc(&d_mid_, qcap_ * sizeof(unsigned)));
     dcap_ = std::max<size_t>(qcap_ / 32, 4096);
     if (park_direct()) {      // many or local sources: direct() runs as its own kernel from a job queue
         CK(cudaMalloc(&dq_, dcap_ * sizeof(DirectJob)));
@@ -577,6 +594,8 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
     A.hits = d_hits_;
     A.dout = park_direct() ? dq_ : nullptr; A.dcap = (unsigned)dcap_;
     A.slow = getenv("RB_NO_SHADE_SPLIT") ? nullptr : d_slow_;
+    A.mid = d_mid_;
+    A.nodirect = nsrc_active_ == 0 ? 1 : 0;
 
     auto sync_counters = [&](std::string& err) -> bool {
         CK(cudaMemcpyAsync(h_cnt_, d_cnt_, sizeof(DCounters), cudaMemcpyDeviceToHost, stream_));
@@ -654,8 +673,9 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
             CK(cudaEventRecord(wev_[4 * k + 1], stream_));
             if (A.slow) {
                 k_shade_fast<<<sgrid, RB_SHADE_THREADS, 0, stream_>>>(A);
+                k_shade_mid<<<148u * 6u, RB_SHADE_THREADS, 0, stream_>>>(A);
                 k_shade<<<148u * 4u, RB_SHADE_THREADS, 0, stream_>>>(A);
-                stats.launches++;
+                stats.launches += 2;
             } else
                 k_shade<<<sgrid, RB_SHADE_THREADS, 0, stream_>>>(A);
             CK(cudaEventRecord(wev_[4 * k + 2], stream_));

@@ -91,6 +91,7 @@ private:
     cudaEvent_t wev_[32] = {};            // per-wave events of a chunk of queued-ahead waves (4 per wave)
     HitRec* d_hits_ = nullptr;
     unsigned* d_slow_ = nullptr;          // queue slots left to the general shading kernel
+    unsigned* d_mid_ = nullptr;           // queue slots left to k_shade_mid
     int trace_blocks_ = 148;
     size_t trace_smem_ = 0;      // dynamic shared memory of k_trace (ancestor stack)
     bool has_local_sources_ = false;

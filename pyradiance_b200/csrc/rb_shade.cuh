@@ -66,6 +66,8 @@ struct WaveArgs {
     int inline_hemi_max;    // hemispheres with n*n <= this are expanded in-thread
     DirectJob* dout; unsigned dcap;   // parked direct() calculations (null: sources are walked in-thread)
     unsigned* slow;         // [qcap] queue slots k_shade_fast leaves to the general k_shade (null: no split)
+    unsigned* mid;          // [qcap] queue slots it leaves to k_shade_mid (glass, trans, spotlights)
+    int nodirect;           // direct() has no source to sample in this scene (every source is a glow that is skipped)
 };
 
 struct RayCtx {             // the ray being shaded (a subset of RAY, rt/ray.h:48-83)
@@ -862,12 +864,14 @@ __device__ __forceinline__ double raynormal(double norm[3], const RayCtx& r, con
     return newdot;
 }
 
-// FAST (k_shade_fast): the caller guarantees a PURE-specular material (roughness^2 <= FTINY) on a surface without
-// vertex normals, so the sampled-highlight code and the normal perturbation are compiled out; everything a FAST
+// FAST (k_shade_mid / k_shade_fast): the caller guarantees a PURE-specular material (roughness^2 <= FTINY) on a surface
+// without vertex normals, so the sampled-highlight code and the normal perturbation are compiled out; LEAN
+// (k_shade_fast) also guarantees that the material is not `trans`, and that code goes too.  Everything an
 // instantiation does execute is the same code, on the same values, as the general one.
-template <bool FAST = false>
-__device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind, const float* a) {
+template <bool FAST = false, bool LEAN = false>
+__device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind_, const float* a) {
     const DParams& P = A.P;
+    const int mkind = LEAN ? (mkind_ == MK_METAL ? MK_METAL : MK_PLASTIC) : mkind_;
     if ((r.crtype & RT_SHADOW) && mkind != MK_TRANS) return;      // easy shadow test
     bool flipped = false;
     if (r.rod < 0.0) {
@@ -893,7 +897,7 @@ __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind
         fest = exp(-5.85 * nd.pdot) - 0.00202943064;
         nd.rspec += fest * (1. - nd.rspec);
     }
-    if (mkind == MK_TRANS) {
+    if (!LEAN && mkind == MK_TRANS) {
         nd.trans = a[5] * (1.0 - nd.rspec);
         nd.tspec = nd.trans * a[6];
         nd.tdiff = nd.trans - nd.tspec;
@@ -913,7 +917,7 @@ __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind
         nd.tdiff = nd.tspec = nd.trans = 0.0;
     nd.rdiff = 1.0 - nd.trans - nd.rspec;
     // transmitted ray
-    if ((nd.specfl & (SP_TRAN | SP_PURE | SP_TBLT)) == (SP_TRAN | SP_PURE)) {
+    if (!LEAN && (nd.specfl & (SP_TRAN | SP_PURE | SP_TBLT)) == (SP_TRAN | SP_PURE)) {
         float rc[3] = {(float)(nd.mcolor[0] * nd.tspec), (float)(nd.mcolor[1] * nd.tspec), (float)(nd.mcolor[2] * nd.tspec)};
         QRay q;
         if (rayorigin(P, r, RT_TRANS, rc, true, q)) {
@@ -999,7 +1003,7 @@ __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind
         if (nd.specfl & SP_RBLT) for (int k = 0; k < 3; k++) sct[k] += nd.scolor[k];
         multambient(A, r, sct, nd.pnorm);
     }
-    if (nd.tdiff > RB_FTINY) {
+    if (!LEAN && nd.tdiff > RB_FTINY) {
         float sct[3];
         double f = (nd.specfl & SP_TBLT) ? nd.trans : nd.tdiff;
         for (int k = 0; k < 3; k++) sct[k] = (float)(nd.mcolor[k] * f);
@@ -1588,7 +1592,7 @@ __device__ __noinline__ double sky_pattern(const PatRec& p, const double dir[3])
 
 // source.c:749-793 m_light.  Returns 1 and sets rcol when the ray sees the
 // emitter, 0 when its coefficient is zeroed / it is passed on.
-template <bool FAST = false>
+template <bool FAST = false, bool LEAN = false>
 __device__ __forceinline__ int m_light(const WaveArgs& A, RayCtx& r, const MatRec& m, float rcol[3], bool& zeroed) {
     const DScene& S = A.S;
     zeroed = false;
@@ -1615,7 +1619,7 @@ __device__ __forceinline__ int m_light(const WaveArgs& A, RayCtx& r, const MatRe
         if (!A.P.backvis) raytrans(A, r);
         return 0;
     }
-    if (m.kind == MK_SPOT) {                      // check for outside spot (source.c:778-779)
+    if (!LEAN && m.kind == MK_SPOT) {             // check for outside spot (source.c:778-779)
         if (r.rsrc >= 0 && (S.srcs[r.rsrc].flags & SF_SPOT)) {
             if (spotout(S.srcs[r.rsrc], r.org, r.dir)) return 0;
         } else {                                  // seen directly: makespot() from the material's reals
@@ -1639,7 +1643,9 @@ __device__ __forceinline__ int m_light(const WaveArgs& A, RayCtx& r, const MatRe
 }
 
 // rayshade() + trace callback for one traced ray (raytrace.c:162-179,210-256)
-template <bool FAST = false>
+// FAST: the materials of k_shade_mid / k_shade_fast only (shade_class() decides which rays may come here); LEAN
+// (k_shade_fast): without glass, trans and spotlights as well.
+template <bool FAST = false, bool LEAN = false>
 __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
     const DScene& S = A.S;
     int4 hd = __ldg(&S.objhdr[r.robj]);
@@ -1668,13 +1674,13 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
             if (!(k >= MK_LIGHT && k <= MK_SPOT)) { nk = MK_PLASTIC; for (int j = 0; j < 7; j++) na[j] = j < 3 ? (float)RB_PI : 0.f; break; }
         }
         if (k == MK_PLASTIC || k == MK_METAL || k == MK_TRANS) { nk = k; for (int j = 0; j < 7; j++) na[j] = m->a[j]; break; }
-        if (k == MK_GLASS) { m_glass<FAST>(A, r, m->a, m->nargs); break; }
+        if (!LEAN && k == MK_GLASS) { m_glass<FAST>(A, r, m->a, m->nargs); break; }
         if (!FAST) {
             if (k >= MK_PLASTIC2 && k <= MK_TRANS2) { m_aniso(A, r, k, m->a, m->u); break; }
             if (k == MK_DIELECTRIC || k == MK_INTERFACE) { m_dielectric(A, r, k, (int)(m - S.mats), m->a); break; }
             if (k == MK_BSDF || k == MK_ABSDF) { m_bsdf(A, r, *m); break; }
         }
-        int rv = m_light<FAST>(A, r, *m, rcol, zeroed);
+        int rv = m_light<FAST, LEAN>(A, r, *m, rcol, zeroed);
         if (rv == 1) {
             have_rcol = true;
             add_value(A, r.row, r.coef, rcol[0], rcol[1], rcol[2]);
@@ -1688,30 +1694,55 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
         }
         break;
     }
-    if (nk >= 0) m_normal<FAST>(A, r, nk, na);
+    if (nk >= 0) m_normal<FAST, LEAN>(A, r, nk, na);
     trace_contrib(A, r, zeroed, rcol, have_rcol);
 }
 
-// Which queued rays the lean kernel may shade: exactly those whose shading never enters the code it leaves out
-// (mirrors the decisions of shade_ray() / m_normal() above; anything unusual says "no").
-__device__ __forceinline__ bool shade_is_simple(const WaveArgs& A, const QRay& q, const HitRec& hr) {
-    if (q.med) return false;                                  // absorbing medium: ray_medium()
+// Which kernel shades a queued ray (mirrors the decisions of shade_ray() / m_normal() above; anything unusual goes
+// to the general kernel):
+//   SC_NONE  nothing to do: no hit, or a ray that provably adds nothing and spawns nothing (below)
+//   SC_LEAN  k_shade_fast itself: plastic / metal without a sampled highlight, plain light / glow emitters, surfaces
+//            without a material, the Lambertian stand-in of an irradiance ray (raytirrad)
+//   SC_MID   k_shade_mid: glass, trans without a sampled highlight, spotlights -- shade_ray<FAST>
+//   SC_SLOW  k_shade: everything else
+enum : int { SC_NONE = 0, SC_LEAN, SC_MID, SC_SLOW };
+__device__ __forceinline__ int shade_class(const WaveArgs& A, const QRay& q, const HitRec& hr) {
+    if (q.med) return SC_SLOW;                                // absorbing medium: ray_medium()
     const int crtype = q.info & 0x3ff;
-    if (A.res && crtype == RT_PRIMARY) return false;          // primary-hit report (smooth_pert, flip flag)
-    if (hr.robj < 0) return true;                             // nothing to shade
+    if (A.res && crtype == RT_PRIMARY) return SC_SLOW;        // primary-hit report (smooth_pert, flip flag)
+    if (hr.robj < 0) return SC_NONE;                          // nothing to shade
     const int4 hd = __ldg(&A.S.objhdr[hr.robj]);
-    if (hr.local && ((hd.x >> 13) & 3)) return false;         // vertex normals / Phong modifier
-    if (hd.z < 0) return true;                                // no material: raytrans()
+    if (hr.local && ((hd.x >> 13) & 3)) return SC_SLOW;       // vertex normals / Phong modifier
+    if (hd.z < 0) return SC_LEAN;                             // no material: raytrans()
     const MatRec& m = A.S.mats[hd.z];
     const int k = m.kind;
-    if (k == MK_UNSUPPORTED || (m.flags & 3)) return false;   // error paths and patterns
-    if (k == MK_BSDF || k == MK_ABSDF) return false;          // m_bsdf() is compiled into the general kernel only
+    if (k == MK_UNSUPPORTED || (m.flags & 3)) return SC_SLOW; // error paths and patterns
+    if (k == MK_BSDF || k == MK_ABSDF) return SC_SLOW;        // m_bsdf() is compiled into the general kernel only
     const bool emitter = k >= MK_LIGHT && k <= MK_SPOT;
-    if (A.P.do_irrad && !(crtype & ~(RT_PRIMARY | RT_TRANS)) && !emitter) return true;    // raytirrad(): passes through or Lambertian
-    if (k == MK_PLASTIC || k == MK_METAL || k == MK_TRANS) { double a2 = m.a[4]; a2 *= a2; return a2 <= RB_FTINY; }
-    if (k == MK_GLASS) return true;
-    if (emitter) return k != MK_ILLUM && m.pat < 0;
-    return false;
+    const bool tirrad = A.P.do_irrad && !(crtype & ~(RT_PRIMARY | RT_TRANS));
+    if (tirrad && !emitter) return SC_LEAN;                   // raytirrad(): passes through or Lambertian
+    if (k == MK_PLASTIC || k == MK_METAL) {
+        double a2 = m.a[4]; a2 *= a2;
+        if (!(a2 <= RB_FTINY)) return SC_SLOW;
+        // A ray that ends on such a surface, adds nothing and spawns nothing -- a shadow ray (normal.c:190-191), or
+        // a ray past the last ambient bounce on a surface without specular reflection in a scene whose sources are
+        // all glow -- needs neither its hit frame nor m_normal(): multambient() is "dumb" with a black -av,
+        // direct() has no source to test, and trace_contrib() returns for an untracked modifier.  (Back faces with
+        // -bv- go through raytrans(), hence the test.)
+        const bool untracked = !A.acc || __ldg(&A.S.otrack[hr.robj]) < 0;
+        if (untracked && A.P.backvis) {
+            if (crtype & RT_SHADOW) return SC_NONE;
+            const int rdepth = (q.info >> 16) & 0x3f;
+            const bool dumb = (A.P.ambdiv <= 0) | (rdepth >= A.P.ambounce);
+            const bool black_av = !A.vacc || !(A.P.ambval[0] > 0.f || A.P.ambval[1] > 0.f || A.P.ambval[2] > 0.f);
+            if (dumb && black_av && A.nodirect && m.a[3] == 0.f) return SC_NONE;
+        }
+        return SC_LEAN;
+    }
+    if (k == MK_TRANS) { double a2 = m.a[4]; a2 *= a2; return a2 <= RB_FTINY ? SC_MID : SC_SLOW; }
+    if (k == MK_GLASS) return SC_MID;
+    if (emitter) return (k == MK_ILLUM || m.pat >= 0) ? SC_SLOW : k == MK_SPOT ? SC_MID : SC_LEAN;
+    return SC_SLOW;
 }
 
 }  // namespace rb
