@@ -122,9 +122,12 @@ __device__ __forceinline__ void load_ray(const WaveArgs& A, const QRay& q, const
 // (the body is a function of its own so that the grid-stride loop around it -- the ray count is known only on the
 //  device -- does not add to the register pressure of the shading code: inlined, the loop tripled the spills)
 __device__ __noinline__ void shade_fast_one(const WaveArgs& A, unsigned i) {
-    const QRay q = A.qin[i];
+    // classification needs the last 32-byte sector of the queued ray only (type, depth, medium): a ray that ends here
+    // never has the other two read
+    const QRay* qp = A.qin + i;
+    const unsigned qinfo = __ldg(&qp->info), qmed = __ldg(&qp->med);
     const HitRec hr = A.hits[i];
-    const int cls = shade_class(A, q, hr);
+    const int cls = shade_class(A, qinfo, qmed, hr);
     if (cls == SC_NONE) return;
     if (cls != SC_LEAN) {
         const bool mid = cls == SC_MID;
@@ -132,6 +135,7 @@ __device__ __noinline__ void shade_fast_one(const WaveArgs& A, unsigned i) {
         (mid ? A.mid : A.slow)[slot] = i;
         return;
     }
+    const QRay q = *qp;
     RayCtx r;
     load_ray(A, q, hr, r);
     shade_ray<true, true>(A, r);

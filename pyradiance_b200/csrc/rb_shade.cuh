@@ -751,6 +751,7 @@ __device__ __forceinline__ void direct_or_park(const WaveArgs& A, RayCtx& r, con
         A.dout[slot].nd = nd;
         return;
     }
+    if (A.nodirect) return;                          // every source is a glow that direct() skips (srcskip)
     direct<FAST>(A, r, nd);
 }
 
@@ -803,12 +804,17 @@ __device__ __forceinline__ void multambient(const WaveArgs& A, RayCtx& r, const 
     uy[0] = onrm[1] * ux[2] - onrm[2] * ux[1];
     uy[1] = onrm[2] * ux[0] - onrm[0] * ux[2];
     uy[2] = onrm[0] * ux[1] - onrm[1] * ux[0];
-    RayCtx par = r; par.key = hkey; par.nchild = 0;
+    // the samples are children of the hemisphere's key, numbered from 0: the ray stands in for its own copy
+    // (rayorigin() reads the parent and only counts its children)
+    const unsigned long long rkey = r.key;
+    const unsigned rn = r.nchild;
+    r.key = hkey; r.nchild = 0;
     for (int i = n; i--;)
         for (int j = n; j--;) {
             QRay q;
-            if (ambsample(P, par, atyp, acoef, onrm, ux, uy, n, i, j, q)) push_ray(A, q);
+            if (ambsample(P, r, atyp, acoef, onrm, ux, uy, n, i, j, q)) push_ray(A, q);
         }
+    r.key = rkey; r.nchild = rn;
 }
 
 // raytrace.c:196-207 raytrans(): continue the ray unchanged
@@ -1706,9 +1712,9 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
 //   SC_MID   k_shade_mid: glass, trans without a sampled highlight, spotlights -- shade_ray<FAST>
 //   SC_SLOW  k_shade: everything else
 enum : int { SC_NONE = 0, SC_LEAN, SC_MID, SC_SLOW };
-__device__ __forceinline__ int shade_class(const WaveArgs& A, const QRay& q, const HitRec& hr) {
-    if (q.med) return SC_SLOW;                                // absorbing medium: ray_medium()
-    const int crtype = q.info & 0x3ff;
+__device__ __forceinline__ int shade_class(const WaveArgs& A, unsigned qinfo, unsigned qmed, const HitRec& hr) {
+    if (qmed) return SC_SLOW;                                 // absorbing medium: ray_medium()
+    const int crtype = qinfo & 0x3ff;
     if (A.res && crtype == RT_PRIMARY) return SC_SLOW;        // primary-hit report (smooth_pert, flip flag)
     if (hr.robj < 0) return SC_NONE;                          // nothing to shade
     const int4 hd = __ldg(&A.S.objhdr[hr.robj]);
@@ -1732,7 +1738,7 @@ __device__ __forceinline__ int shade_class(const WaveArgs& A, const QRay& q, con
         const bool untracked = !A.acc || __ldg(&A.S.otrack[hr.robj]) < 0;
         if (untracked && A.P.backvis) {
             if (crtype & RT_SHADOW) return SC_NONE;
-            const int rdepth = (q.info >> 16) & 0x3f;
+            const int rdepth = (qinfo >> 16) & 0x3f;
             const bool dumb = (A.P.ambdiv <= 0) | (rdepth >= A.P.ambounce);
             const bool black_av = !A.vacc || !(A.P.ambval[0] > 0.f || A.P.ambval[1] > 0.f || A.P.ambval[2] > 0.f);
             if (dumb && black_av && A.nodirect && m.a[3] == 0.f) return SC_NONE;
