@@ -143,6 +143,7 @@ struct DCounters {
     unsigned nd_out;               // parked direct() jobs (keep right after next_ray: reset together)
     unsigned nslow;                // rays k_shade_fast left to the general k_shade (reset with the two above)
     unsigned nmid;                 // rays it left to k_shade_mid
+    unsigned nlean;                // rays it left to k_shade_lean
     // wave chaining without the host (rb_engine.cu k_gate / k_prepare): what the kernels of the current wave read
     unsigned nin;                  // rays in the input queue of this wave
     unsigned nh_in, nd_in;         // hemispheres / parked direct() jobs to expand before it

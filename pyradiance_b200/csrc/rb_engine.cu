@@ -109,40 +109,54 @@ __device__ __forceinline__ void load_ray(const WaveArgs& A, const QRay& q, const
     }
 }
 
-// Shading is split three ways by what a ray hit (shade_class(), rb_shade.cuh):
-//   k_shade_fast  one thread per queued ray: reads the ray and its hit, classifies it, and shades the LEAN class itself --
-//                 plastic / metal without a sampled highlight, plain emitters, surfaces without a material: nearly
-//                 every ray of a daylight job -- with the rest of the material set compiled out (shade_ray<true, true>);
-//                 rays that end without effect (SC_NONE) stop right there;
-//   k_shade_mid   glass, trans without a sampled highlight, spotlights (shade_ray<true, false>), by queue slot;
-//   k_shade       every material, by queue slot.
+// Shading is split by what a ray hit (shade_class(), rb_shade.cuh):
+//   k_shade_fast  one thread per queued ray: reads the ray's type and its hit, classifies it, and shades the commonest
+//                 class itself -- a diffuse polygon in a scene lit by glow sources only, where the material comes down
+//                 to multambient() (shade_diffuse()); rays that end without effect (SC_NONE) stop right there; the
+//                 others go, by queue slot, to
+//   k_shade_lean  plastic / metal without a sampled highlight, plain emitters, surfaces without a material
+//                 (shade_ray<true, true>: the rest of the material set compiled out);
+//   k_shade_mid   glass, trans without a sampled highlight, spotlights (shade_ray<true, false>);
+//   k_shade       every material.
 #ifndef RB_FAST_MINBLOCKS
 #define RB_FAST_MINBLOCKS 6
 #endif
-// (the body is a function of its own so that the grid-stride loop around it -- the ray count is known only on the
-//  device -- does not add to the register pressure of the shading code: inlined, the loop tripled the spills)
+#ifndef RB_DIFF_MINBLOCKS
+#define RB_DIFF_MINBLOCKS 8
+#endif
+// (the bodies are functions of their own so that the grid-stride loop around them -- the ray count is known only on
+//  the device -- does not add to the register pressure of the shading code: inlined, the loop tripled the spills)
 __device__ __noinline__ void shade_fast_one(const WaveArgs& A, unsigned i) {
     // classification needs the last 32-byte sector of the queued ray only (type, depth, medium): a ray that ends here
     // never has the other two read
     const QRay* qp = A.qin + i;
     const unsigned qinfo = __ldg(&qp->info), qmed = __ldg(&qp->med);
     const HitRec hr = A.hits[i];
-    const int cls = shade_class(A, qinfo, qmed, hr);
+    int geomoff = 0;
+    const MatRec* mat = nullptr;
+    const int cls = shade_class(A, qinfo, qmed, hr, geomoff, mat);
     if (cls == SC_NONE) return;
-    if (cls != SC_LEAN) {
-        const bool mid = cls == SC_MID;
-        const unsigned slot = reserve_slot(mid ? &A.C->nmid : &A.C->nslow);
-        (mid ? A.mid : A.slow)[slot] = i;
-        return;
-    }
+    // (one branch per class: reserve_slot() aggregates over the lanes that arrive together, which must share a counter)
+    if (cls == SC_LEAN) { A.lean[reserve_slot(&A.C->nlean)] = i; return; }
+    if (cls == SC_MID) { A.mid[reserve_slot(&A.C->nmid)] = i; return; }
+    if (cls == SC_SLOW) { A.slow[reserve_slot(&A.C->nslow)] = i; return; }
     const QRay q = *qp;
+    shade_diffuse(A, q, hr, geomoff, *mat);
+}
+__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_DIFF_MINBLOCKS) k_shade_fast(const __grid_constant__ WaveArgs A) {
+    const unsigned n = A.C->nin;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) shade_fast_one(A, i);
+}
+__device__ __noinline__ void shade_lean_one(const WaveArgs& A, unsigned i) {
+    const QRay q = A.qin[i];
+    const HitRec hr = A.hits[i];
     RayCtx r;
     load_ray(A, q, hr, r);
     shade_ray<true, true>(A, r);
 }
-__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_FAST_MINBLOCKS) k_shade_fast(const __grid_constant__ WaveArgs A) {
-    const unsigned n = A.C->nin;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) shade_fast_one(A, i);
+__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_FAST_MINBLOCKS) k_shade_lean(const __grid_constant__ WaveArgs A) {
+    const unsigned n = A.C->nlean;
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) shade_lean_one(A, A.lean[j]);
 }
 __device__ __noinline__ void shade_mid_one(const WaveArgs& A, unsigned i) {
     const QRay q = A.qin[i];
@@ -298,7 +312,7 @@ __global__ void k_gate(DCounters* C, unsigned qcap) {
 }
 __global__ void k_prepare(DCounters* C, unsigned wave) {
     const unsigned n = (C->overflow || C->errflag) ? 0u : C->nq_out;
-    C->nin = n; C->nq_out = 0; C->next_ray = 0; C->nslow = 0; C->nmid = 0;
+    C->nin = n; C->nq_out = 0; C->next_ray = 0; C->nslow = 0; C->nmid = 0; C->nlean = 0;
     C->rays_traced += n;
     C->wave_nin[wave & 63] = n;
 }
@@ -359,7 +373,7 @@ Engine::~Engine() {
     cudaSetDevice(dev_);
     cudaDeviceSynchronize();
     void* ptrs[] = {d_nodes_, d_leaf_, d_hdr_, d_geom_, d_mats_, d_srcs_, d_pats_, d_bsdfs_, d_bsdfbases_, d_bsdfpool_, d_otrack_, d_top_, d_bins_, q_[0], q_[1],
-                    h_[0], h_[1], d_hits_, dq_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_, d_slow_, d_mid_};
+                    h_[0], h_[1], d_hits_, dq_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_, d_slow_, d_mid_, d_lean_};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_cnt_) cudaFreeHost(h_cnt_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -501,9 +515,9 @@ bool Engine::ensure_queues(std::string& err, size_t hint) {
     if (q_[0] && want <= qcap_) return true;
     if (q_[0]) {                            // grow: drop the old queues first
         CK(cudaStreamSynchronize(stream_));
-        void* old[] = {q_[0], q_[1], h_[0], h_[1], d_hits_, dq_, d_slow_, d_mid_};
+        void* old[] = {q_[0], q_[1], h_[0], h_[1], d_hits_, dq_, d_slow_, d_mid_, d_lean_};
         for (void* p : old) if (p) cudaFree(p);
-        q_[0] = q_[1] = nullptr; h_[0] = h_[1] = nullptr; d_hits_ = nullptr; dq_ = nullptr; d_slow_ = nullptr; d_mid_ = nullptr;
+        q_[0] = q_[1] = nullptr; h_[0] = h_[1] = nullptr; d_hits_ = nullptr; dq_ = nullptr; d_slow_ = nullptr; d_mid_ = nullptr; d_lean_ = nullptr;
     }
     size_t freeb = 0, totalb = 0;
     CK(cudaMemGetInfo(&freeb, &totalb));
@@ -519,6 +533,7 @@ bool Engine::ensure_queues(std::string& err, size_t hint) {
     CK(cudaMalloc(&d_hits_, qcap_ * sizeof(HitRec)));
     CK(cudaMalloc(&d_slow_, qcap_ * sizeof(unsigned)));
     CK(cudaMalloc(&d_mid_, qcap_ * sizeof(unsigned)));
+    CK(cudaMalloc(&d_lean_, qcap_ * sizeof(unsigned)));
     dcap_ = std::max<size_t>(qcap_ / 32, 4096);
     if (park_direct()) {      // many or local sources: direct() runs as its own kernel from a job queue
         CK(cudaMalloc(&dq_, dcap_ * sizeof(DirectJob)));
@@ -598,7 +613,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
     A.hits = d_hits_;
     A.dout = park_direct() ? dq_ : nullptr; A.dcap = (unsigned)dcap_;
     A.slow = getenv("RB_NO_SHADE_SPLIT") ? nullptr : d_slow_;
-    A.mid = d_mid_;
+    A.mid = d_mid_; A.lean = d_lean_;
     A.nodirect = nsrc_active_ == 0 ? 1 : 0;
 
     auto sync_counters = [&](std::string& err) -> bool {
@@ -677,9 +692,10 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
             CK(cudaEventRecord(wev_[4 * k + 1], stream_));
             if (A.slow) {
                 k_shade_fast<<<sgrid, RB_SHADE_THREADS, 0, stream_>>>(A);
+                k_shade_lean<<<big ? 148u * 24u : 148u * 6u, RB_SHADE_THREADS, 0, stream_>>>(A);
                 k_shade_mid<<<148u * 6u, RB_SHADE_THREADS, 0, stream_>>>(A);
                 k_shade<<<148u * 4u, RB_SHADE_THREADS, 0, stream_>>>(A);
-                stats.launches += 2;
+                stats.launches += 3;
             } else
                 k_shade<<<sgrid, RB_SHADE_THREADS, 0, stream_>>>(A);
             CK(cudaEventRecord(wev_[4 * k + 2], stream_));

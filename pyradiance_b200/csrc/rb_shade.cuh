@@ -67,6 +67,7 @@ struct WaveArgs {
     DirectJob* dout; unsigned dcap;   // parked direct() calculations (null: sources are walked in-thread)
     unsigned* slow;         // [qcap] queue slots k_shade_fast leaves to the general k_shade (null: no split)
     unsigned* mid;          // [qcap] queue slots it leaves to k_shade_mid (glass, trans, spotlights)
+    unsigned* lean;         // [qcap] queue slots it leaves to k_shade_lean
     int nodirect;           // direct() has no source to sample in this scene (every source is a glow that is skipped)
 };
 
@@ -1707,12 +1708,16 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
 // Which kernel shades a queued ray (mirrors the decisions of shade_ray() / m_normal() above; anything unusual goes
 // to the general kernel):
 //   SC_NONE  nothing to do: no hit, or a ray that provably adds nothing and spawns nothing (below)
-//   SC_LEAN  k_shade_fast itself: plastic / metal without a sampled highlight, plain light / glow emitters, surfaces
-//            without a material, the Lambertian stand-in of an irradiance ray (raytirrad)
+//   SC_DIFF  k_shade_fast itself: a polygon of plastic / metal without specular reflection, in a scene whose sources
+//            are all glow: all the material does is multambient() (shade_diffuse())
+//   SC_LEAN  k_shade_lean: plastic / metal without a sampled highlight, plain light / glow emitters, surfaces
+//            without a material, the Lambertian stand-in of an irradiance ray (raytirrad) -- shade_ray<FAST, LEAN>
 //   SC_MID   k_shade_mid: glass, trans without a sampled highlight, spotlights -- shade_ray<FAST>
 //   SC_SLOW  k_shade: everything else
-enum : int { SC_NONE = 0, SC_LEAN, SC_MID, SC_SLOW };
-__device__ __forceinline__ int shade_class(const WaveArgs& A, unsigned qinfo, unsigned qmed, const HitRec& hr) {
+enum : int { SC_NONE = 0, SC_DIFF, SC_LEAN, SC_MID, SC_SLOW };
+// (geomoff / mat: the hit object's record and material, for shade_diffuse())
+__device__ __forceinline__ int shade_class(const WaveArgs& A, unsigned qinfo, unsigned qmed, const HitRec& hr, int& geomoff,
+                                           const MatRec*& mat) {
     if (qmed) return SC_SLOW;                                 // absorbing medium: ray_medium()
     const int crtype = qinfo & 0x3ff;
     if (A.res && crtype == RT_PRIMARY) return SC_SLOW;        // primary-hit report (smooth_pert, flip flag)
@@ -1721,6 +1726,7 @@ __device__ __forceinline__ int shade_class(const WaveArgs& A, unsigned qinfo, un
     if (hr.local && ((hd.x >> 13) & 3)) return SC_SLOW;       // vertex normals / Phong modifier
     if (hd.z < 0) return SC_LEAN;                             // no material: raytrans()
     const MatRec& m = A.S.mats[hd.z];
+    geomoff = hd.w; mat = &m;
     const int k = m.kind;
     if (k == MK_UNSUPPORTED || (m.flags & 3)) return SC_SLOW; // error paths and patterns
     if (k == MK_BSDF || k == MK_ABSDF) return SC_SLOW;        // m_bsdf() is compiled into the general kernel only
@@ -1742,6 +1748,9 @@ __device__ __forceinline__ int shade_class(const WaveArgs& A, unsigned qinfo, un
             const bool dumb = (A.P.ambdiv <= 0) | (rdepth >= A.P.ambounce);
             const bool black_av = !A.vacc || !(A.P.ambval[0] > 0.f || A.P.ambval[1] > 0.f || A.P.ambval[2] > 0.f);
             if (dumb && black_av && A.nodirect && m.a[3] == 0.f) return SC_NONE;
+            // no specular reflection, no Fresnel term (normal.c:229-235 needs rspec >= .018), nothing for direct() to do:
+            // what is left of m_normal() is multambient() with the material's colour
+            if (A.nodirect && m.a[3] == 0.f && hr.local && (hd.x & 0xff) == PK_FACE) return SC_DIFF;
         }
         return SC_LEAN;
     }
@@ -1749,6 +1758,30 @@ __device__ __forceinline__ int shade_class(const WaveArgs& A, unsigned qinfo, un
     if (k == MK_GLASS) return SC_MID;
     if (emitter) return (k == MK_ILLUM || m.pat >= 0) ? SC_SLOW : k == MK_SPOT ? SC_MID : SC_LEAN;
     return SC_SLOW;
+}
+
+// SC_DIFF: m_normal() of a polygon whose material is plastic / metal with rspec = 0 and roughness = 0, hit by a ray that
+// is not a shadow ray, in a scene without sources for direct(), modifier untracked, back faces visible: flipsurface(),
+// rdiff = 1, and multambient(mcolor * rdiff, ron) is all that happens (normal.c:192-200,215-248,337-345).
+__device__ __forceinline__ void shade_diffuse(const WaveArgs& A, const QRay& q, const HitRec& hr, int geomoff, const MatRec& m) {
+    RayCtx r;
+    for (int k = 0; k < 3; k++) r.coef[k] = q.coef[k];
+    r.rmax = q.rmax; r.rweight = q.rweight; r.row = q.row;
+    r.crtype = q.info & 0x3ff; r.rlvl = (q.info >> 10) & 0x3f; r.rdepth = (q.info >> 16) & 0x3f;
+    r.rsrc = q.rsrc;
+    r.key = ((unsigned long long)q.key_hi << 32) | q.key_lo;
+    r.nchild = 0; r.med = 0; r.re = 0.f;
+    r.robj = hr.robj; r.rot = hr.rot;
+    const double* g = A.S.geom + geomoff;
+    double rod = 0.0;
+    for (int k = 0; k < 3; k++) {                   // hit_frame() of a polygon
+        r.rop[k] = q.org[k] + hr.rot * q.dir[k];
+        r.ron[k] = g[k];
+    }
+    rod = -(q.dir[0] * r.ron[0] + q.dir[1] * r.ron[1] + q.dir[2] * r.ron[2]);
+    if (rod < 0.0) { r.ron[0] = -r.ron[0]; r.ron[1] = -r.ron[1]; r.ron[2] = -r.ron[2]; }       // flipsurface
+    const float sct[3] = {m.a[0], m.a[1], m.a[2]};
+    multambient(A, r, sct, r.ron);
 }
 
 }  // namespace rb
