@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const Wave
 __global__ void k_dbg_print() {
     printf("[rb dbg] cyl pairs %llu, after the axis test %llu, after the end test %llu, candidates %llu; sphere pairs %llu, with roots %llu\n",
            g_dbg[0], g_dbg[1], g_dbg[5], g_dbg[2], g_dbg[3], g_dbg[4]);
+    printf("[rb dbg] steps %llu, of which out of full leaves %llu; mean level of the leaf stepped out of %.2f\n", g_dbg[8], g_dbg[9],
+           (double)g_dbg[10] / (double)(g_dbg[8] ? g_dbg[8] : 1));
 }
 #endif
 

@@ -302,10 +302,12 @@ __device__ __forceinline__ void hit_frame(const DScene& S, int robj, double rot,
 
 struct WalkStats { unsigned nodes, leafents, prims; };
 #if RB_WALK_STATS
-__device__ unsigned long long g_dbg[8];     // developer counters: cylinder pairs, after the in-line miss test, candidates; sphere pairs, candidates
+__device__ unsigned long long g_dbg[16];     // developer counters: cylinder pairs, after the in-line miss test, candidates; sphere pairs, candidates
 #define RB_DBG(i) atomicAdd(&g_dbg[i], 1ULL)
+#define RB_DBG2(i, v) atomicAdd(&g_dbg[i], (unsigned long long)(v))
 #else
 #define RB_DBG(i)
+#define RB_DBG2(i, v)
 #endif
 
 // sourcehit() lives in rb_shade.cuh; declared here for the retire step
@@ -865,6 +867,7 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                     }
                 }
                 // advance to next cube (raytrace.c:712-738)
+                RB_DBG(8); if (fullc) RB_DBG(9); RB_DBG2(10, L);
 #if RB_STEP_RCP
                 // raymove() walks the ray with t = (plane - pos) / dir; here the quotient is a product with the
                 // ray's reciprocal direction.  pos may differ from the reference's in the last bit, which only

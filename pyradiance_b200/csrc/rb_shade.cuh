@@ -1708,7 +1708,7 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
 // Which kernel shades a queued ray (mirrors the decisions of shade_ray() / m_normal() above; anything unusual goes
 // to the general kernel):
 //   SC_NONE  nothing to do: no hit, or a ray that provably adds nothing and spawns nothing (below)
-//   SC_DIFF  k_shade_fast itself: a polygon of plastic / metal without specular reflection, in a scene whose sources
+//   SC_DIFF  k_shade_fast itself: a surface of plastic / metal without specular reflection, in a scene whose sources
 //            are all glow: all the material does is multambient() (shade_diffuse())
 //   SC_LEAN  k_shade_lean: plastic / metal without a sampled highlight, plain light / glow emitters, surfaces
 //            without a material, the Lambertian stand-in of an irradiance ray (raytirrad) -- shade_ray<FAST, LEAN>
@@ -1750,7 +1750,9 @@ __device__ __forceinline__ int shade_class(const WaveArgs& A, unsigned qinfo, un
             if (dumb && black_av && A.nodirect && m.a[3] == 0.f) return SC_NONE;
             // no specular reflection, no Fresnel term (normal.c:229-235 needs rspec >= .018), nothing for direct() to do:
             // what is left of m_normal() is multambient() with the material's colour
-            if (A.nodirect && m.a[3] == 0.f && hr.local && (hd.x & 0xff) == PK_FACE) return SC_DIFF;
+#ifndef RB_NO_DIFF
+            if (A.nodirect && m.a[3] == 0.f && hr.local) return SC_DIFF;
+#endif
         }
         return SC_LEAN;
     }
@@ -1760,7 +1762,7 @@ __device__ __forceinline__ int shade_class(const WaveArgs& A, unsigned qinfo, un
     return SC_SLOW;
 }
 
-// SC_DIFF: m_normal() of a polygon whose material is plastic / metal with rspec = 0 and roughness = 0, hit by a ray that
+// SC_DIFF: m_normal() of a surface whose material is plastic / metal with rspec = 0 and roughness = 0, hit by a ray that
 // is not a shadow ray, in a scene without sources for direct(), modifier untracked, back faces visible: flipsurface(),
 // rdiff = 1, and multambient(mcolor * rdiff, ron) is all that happens (normal.c:192-200,215-248,337-345).
 __device__ __forceinline__ void shade_diffuse(const WaveArgs& A, const QRay& q, const HitRec& hr, int geomoff, const MatRec& m) {
@@ -1772,13 +1774,8 @@ __device__ __forceinline__ void shade_diffuse(const WaveArgs& A, const QRay& q, 
     r.key = ((unsigned long long)q.key_hi << 32) | q.key_lo;
     r.nchild = 0; r.med = 0; r.re = 0.f;
     r.robj = hr.robj; r.rot = hr.rot;
-    const double* g = A.S.geom + geomoff;
-    double rod = 0.0;
-    for (int k = 0; k < 3; k++) {                   // hit_frame() of a polygon
-        r.rop[k] = q.org[k] + hr.rot * q.dir[k];
-        r.ron[k] = g[k];
-    }
-    rod = -(q.dir[0] * r.ron[0] + q.dir[1] * r.ron[1] + q.dir[2] * r.ron[2]);
+    double rod;
+    hit_frame(A.S, hr.robj, hr.rot, q.org, q.dir, r.rop, r.ron, rod);
     if (rod < 0.0) { r.ron[0] = -r.ron[0]; r.ron[1] = -r.ron[1]; r.ron[2] = -r.ron[2]; }       // flipsurface
     const float sct[3] = {m.a[0], m.a[1], m.a[2]};
     multambient(A, r, sct, r.ron);

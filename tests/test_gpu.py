@@ -680,6 +680,17 @@ def test_full_size_per_bin_vs_reference(office100k):
     assert abs(rs_g.sum() - rs_r.sum()) <= 0.02 * rs_r.sum()
 
 
+def test_instance_expansion_limit_is_refused_by_name(golden, monkeypatch):
+    """Instances and meshes are flattened at load: the memory that costs is bounded, and a scene beyond
+    the bound is refused naming the limit -- nested traversal (o_instance.c:16-71) is not built."""
+    monkeypatch.setenv("RB_MAX_EXPANDED_SURFACES", "3")
+    ctx = _lib.Context(0)
+    with pytest.raises(_lib.RBError, match="RB_MAX_EXPANDED_SURFACES.*nested instance traversal is not built"):
+        ctx.load_octree(golden / "volumes" / "room.oct")
+    monkeypatch.delenv("RB_MAX_EXPANDED_SURFACES")
+    _lib.Context(0).load_octree(golden / "volumes" / "room.oct")
+
+
 @pytest.mark.parametrize("name", ["room", "meshroom"])
 def test_instances_and_meshes_vs_reference_golden(G, golden, name):
     """Config-5 ingredients: octree instances and triangle meshes, against the
