@@ -22,6 +22,7 @@
  *   m_light, m_normal+dirnorm+gaussamp, m_glass   rt/source.c:749-793, rt/normal.c, rt/glass.c
  *   m_aniso+diraniso+getacoords+agaussamp (plastic2/metal2/trans2)   rt/aniso.c
  *   m_dielectric (dielectric/interface, no DISPERSE), rayparticipate (albedo 0)   rt/dielectric.c, rt/raytrace.c:259-295
+ *   m_bsdf (BSDF / aBSDF on Klems-matrix XML data) + the BSDF library calls it makes   rt/m_bsdf.c, common/bsdf.c, common/bsdf_m.c
  *   multambient(aa=0)/doambient/samp_hemi/ambsample   rt/ambient.c:229-297, rt/ambcomp.c:177-248,350-422
  *   trace_contrib, eval_irrad     rt/rcontrib.c:272-339
  *   rbin/kbin bin functions       util/reinhartb.cal, cal/cal/reinhart.cal, util/klems_*.cal
@@ -39,6 +40,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <strings.h>
 
 #define FTINY 1e-6
 #define FHUGE 1e10
@@ -55,7 +57,7 @@ enum { PRIMARY = 01, RSHADOW = 02, REFLECTED = 04, REFRACTED = 010, TRANS = 020,
 
 enum { T_OTHER = 0, T_POLYGON, T_CONE, T_SPHERE, T_RING, T_CYLINDER, T_CUP, T_BUBBLE, T_TUBE, T_SOURCE, T_INSTANCE,
        T_MESH, T_ALIAS, T_PLASTIC, T_METAL, T_GLASS, T_TRANS, T_GLOW, T_LIGHT, T_ILLUM, T_SPOT, T_TRANSP_MAT,
-       T_OTHER_MAT, T_PATTERN, T_BRIGHTFUNC, T_PLASTIC2, T_METAL2, T_TRANS2, T_DIELECTRIC, T_INTERFACE };
+       T_OTHER_MAT, T_PATTERN, T_BRIGHTFUNC, T_PLASTIC2, T_METAL2, T_TRANS2, T_DIELECTRIC, T_INTERFACE, T_BSDF, T_ABSDF };
 
 typedef struct {
     int omod, otype;
@@ -78,6 +80,7 @@ typedef struct {
 
 typedef struct { char* name; int fn, mf, nbins, col0; double n[3], u[3], rhs; } MOD;
 
+struct orc_bsdf;
 struct orc_scene {
     double cuorg[3], cusize;
     int nobjs; OBJ* objs;
@@ -92,6 +95,8 @@ struct orc_scene {
     unsigned short xs[3];                 /* erand48 state */
     /* the DEVICE walk restated on the CPU (orc_set_walker(s, 1); localhit_dev() below) */
     int walker, depth, topK; int* top; unsigned long long dev_nodes;
+    struct orc_bsdf* bsdfs;               /* loaded BSDF files (m_bsdf, below) */
+    char dir[1024];                       /* directory of the octree: where BSDF files are looked for last */
 };
 
 typedef struct ray {
@@ -157,9 +162,9 @@ static int type_of(const char* n) {
         {"mesh", T_MESH}, {"alias", T_ALIAS}, {"plastic", T_PLASTIC}, {"metal", T_METAL}, {"glass", T_GLASS},
         {"trans", T_TRANS}, {"glow", T_GLOW}, {"light", T_LIGHT}, {"illum", T_ILLUM}, {"spotlight", T_SPOT},
         {"dielectric", T_DIELECTRIC}, {"interface", T_INTERFACE}, {"mist", T_TRANSP_MAT}, {"trans2", T_TRANS2},
-        {"aBSDF", T_TRANSP_MAT}, {"plastic2", T_PLASTIC2}, {"metal2", T_METAL2}, {"plasfunc", T_OTHER_MAT},
+        {"aBSDF", T_ABSDF}, {"plastic2", T_PLASTIC2}, {"metal2", T_METAL2}, {"plasfunc", T_OTHER_MAT},
         {"metfunc", T_OTHER_MAT}, {"mirror", T_OTHER_MAT}, {"transfunc", T_OTHER_MAT}, {"BRTDfunc", T_OTHER_MAT},
-        {"BSDF", T_OTHER_MAT}, {"WGMDfunc", T_OTHER_MAT}, {"plasdata", T_OTHER_MAT}, {"metdata", T_OTHER_MAT},
+        {"BSDF", T_BSDF}, {"WGMDfunc", T_OTHER_MAT}, {"plasdata", T_OTHER_MAT}, {"metdata", T_OTHER_MAT},
         {"transdata", T_OTHER_MAT}, {"antimatter", T_OTHER_MAT}, {"prism1", T_OTHER_MAT}, {"prism2", T_OTHER_MAT},
         {"ashik2", T_OTHER_MAT}, {"brightfunc", T_BRIGHTFUNC}, {NULL, 0}};
     int i;
@@ -167,10 +172,10 @@ static int type_of(const char* n) {
     return T_PATTERN;     /* patterns, textures, mixtures: anything else is a non-material modifier */
 }
 static int is_surface(int t) { return t >= T_POLYGON && t <= T_SOURCE; }
-static int is_material(int t) { return (t >= T_PLASTIC && t <= T_SPOT) || t == T_TRANSP_MAT || t == T_OTHER_MAT || (t >= T_PLASTIC2 && t <= T_INTERFACE); }
+static int is_material(int t) { return (t >= T_PLASTIC && t <= T_SPOT) || t == T_TRANSP_MAT || t == T_OTHER_MAT || (t >= T_PLASTIC2 && t <= T_ABSDF); }
 static int is_modifier(int t) { return !(t >= T_POLYGON && t <= T_MESH); }
 static int is_light(int t) { return t >= T_GLOW && t <= T_SPOT; }
-static int is_transp(int t) { return t == T_TRANS || t == T_GLASS || t == T_TRANSP_MAT || t == T_TRANS2 || t == T_DIELECTRIC || t == T_INTERFACE; }
+static int is_transp(int t) { return t == T_TRANS || t == T_GLASS || t == T_TRANSP_MAT || t == T_TRANS2 || t == T_DIELECTRIC || t == T_INTERFACE || t == T_ABSDF; }
 
 static int lastmod(const orc_scene* s, int before, const char* name) {
     int i;
@@ -452,6 +457,7 @@ orc_scene* orc_load(const char* path, char* err, size_t errlen) {
     }
     if (!gotfmt) { free(buf); snprintf(err, errlen, "(%s): not an octree", path); return NULL; }
     s = (orc_scene*)calloc(1, sizeof(orc_scene));
+    { const char* sl = strrchr(path, '/'); size_t n = sl ? (size_t)(sl - path + 1) : 0; if (n >= sizeof s->dir) n = sizeof s->dir - 1; memcpy(s->dir, path, n); s->dir[n] = 0; }
     r.p = p; r.e = buf + sz; r.bad = 0;
     objsize = (int)rgetint(&r, 2) - (4 * 8 + 251);
     if (objsize <= 0 || objsize > 8) { free(buf); free(s); snprintf(err, errlen, "incompatible octree format"); return NULL; }
@@ -506,8 +512,10 @@ orc_scene* orc_load(const char* path, char* err, size_t errlen) {
     return s;
 }
 
+static void free_bsdfs(orc_scene* s);
 void orc_free(orc_scene* s) {
     if (s && s->top) { free(s->top); s->top = NULL; }
+    if (s) free_bsdfs(s);
     int i, k;
     if (!s) return;
     for (i = 0; i < s->nobjs; i++) {
@@ -1098,14 +1106,18 @@ static void rayvalue(orc_scene* s, RAY* r) { raytrace(s, r); }
 typedef struct {
     RAY* rp; int specfl; float mcolor[3], scolor[3]; double prdir[3], alpha2, rdiff, rspec, trans, tdiff, tspec, pnorm[3], pdot;
     int aniso; double u[3], v[3], u_alpha, v_alpha;      /* plastic2 / metal2 / trans2 (aniso.c ANISODAT) */
+    /* BSDF / aBSDF (m_bsdf.c BSDFDAT): mcolor = rdiff, scolor = tdiff */
+    const struct orc_bsdf* bsdf; double toloc[3][3], vray[3]; float cthru[3], cthru_surr[3]; int dmode;
 } NORMDAT;
 enum { SP_REFL = 01, SP_TRAN = 02, SP_PURE = 04, SP_FLAT = 010, SP_RBLT = 020, SP_TBLT = 040 };
 #define FRESNE(ci) (exp(-5.85 * (ci)) - 0.00202943064)
 #define FRESTHRESH 0.017999
 
 static void diraniso(orc_scene* s, float* scval, NORMDAT* np, const double* ldir, double omega);
+static void dir_bsdf(orc_scene* s, float* scval, NORMDAT* np, const double* ldir, double omega);
 static void dirnorm(orc_scene* s, float* scval, NORMDAT* np, const double* ldir, double omega) {
     double ldot, lrdiff, ltdiff, dtmp, d2, d3, d4, vtmp[3]; int k;
+    if (np->bsdf) { dir_bsdf(s, scval, np, ldir, omega); return; }
     if (np->aniso) { diraniso(s, scval, np, ldir, omega); return; }
     scval[0] = scval[1] = scval[2] = 0;
     ldot = dot(np->pnorm, ldir);
@@ -1397,7 +1409,7 @@ static int m_normal(orc_scene* s, int mtype, const double* a, RAY* r, int ro_fla
         r->rod = -r->rod; for (k = 0; k < 3; k++) r->ron[k] = -r->ron[k];
         r->rflips++;
     }
-    nd.rp = r; nd.aniso = 0;
+    nd.rp = r; nd.aniso = 0; nd.bsdf = NULL;
     for (k = 0; k < 3; k++) nd.mcolor[k] = (float)a[k];
     nd.specfl = 0; nd.alpha2 = a[4];
     if ((nd.alpha2 *= nd.alpha2) <= FTINY) nd.specfl |= SP_PURE;
@@ -1566,7 +1578,7 @@ static int m_aniso(orc_scene* s, const OBJ* m, RAY* r, int ro_flat) {
         r->rod = -r->rod; for (k = 0; k < 3; k++) r->ron[k] = -r->ron[k];
         r->rflips++;
     }
-    nd.rp = r; nd.aniso = 1; nd.alpha2 = 0; nd.specfl = 0;
+    nd.rp = r; nd.aniso = 1; nd.bsdf = NULL; nd.alpha2 = 0; nd.specfl = 0;
     for (k = 0; k < 3; k++) { nd.mcolor[k] = (float)a[k]; nd.scolor[k] = 0; nd.pnorm[k] = r->ron[k]; nd.prdir[k] = r->rdir[k]; }
     nd.u_alpha = a[4]; nd.v_alpha = a[5];
     if ((nd.u_alpha <= FTINY) | (nd.v_alpha <= FTINY)) { fail(s, "roughness too small for", m->name); return 1; }
@@ -1792,6 +1804,558 @@ static int m_light(orc_scene* s, const OBJ* m, RAY* r) {
 #undef distglow
 }
 
+/* ---- BSDF / aBSDF (rt/m_bsdf.c) over Klems-matrix XML data (common/bsdf.c, common/bsdf_m.c) ----
+ * Restated: SDloadFile / SDloadMtx / load_angle_basis / load_bsdf_data / get_extrema / extract_diffuse /
+ * subtract_min / mBSDF_color (grayscale), fo_getndx / fo_getvec / io_getohm and their fi / bi / bo variants,
+ * SDgetMtxBSDF, SDqueryMtxProjSA, make_cdist (computed on demand, no cache list), SDsampMtxCDist, SDsizeBSDF,
+ * SDevalBSDF, SDdirectHemi, SDsampComponent, SDcompXform / SDinvXform / SDmapDir, and m_bsdf.c in full for
+ * -ss <= 1.5 (compute_through, bsdf_jitter, direct_specular_OK, dir_bsdf / dir_brdf / dir_btdf, sample_sdcomp,
+ * sample_sdf, m_bsdf).  The file is read with a scanner of its own (the schema nests uniquely named elements).
+ * Not restated: SDmultiSamp()'s Hilbert-curve split (two independent uniforms), tensor-tree and colour data. */
+#define KMAXLATS 46
+typedef struct { char name[64]; int nangles, nlat; double tmin[KMAXLATS + 1]; int nphis[KMAXLATS + 1]; } KBASIS;
+typedef struct { int present, ninc, nout, ib, ob; float* v; double minProjSA, maxHemi; } KCOMP;     /* v[o * ninc + i] */
+enum { K_RF = 0, K_RB, K_TF, K_TB };
+struct orc_bsdf { char* file; KBASIS bases[8]; int nbases; KCOMP c[4]; double lamb[4]; struct orc_bsdf* next; };
+
+static const char* x_find(const char* p, const char* e, const char* tag, const char** cend) {
+    /* content of the first <tag ...>...</tag> inside [p, e): returns its start, *cend its end; NULL if absent */
+    size_t n = strlen(tag);
+    while (p < e) {
+        const char* q = (const char*)memchr(p, '<', e - p);
+        if (!q || q + n + 1 >= e) return NULL;
+        if (!strncmp(q + 1, tag, n) && (q[n + 1] == '>' || q[n + 1] == ' ' || q[n + 1] == '\t' || q[n + 1] == '\n' || q[n + 1] == '/')) {
+            const char* c0 = (const char*)memchr(q, '>', e - q); const char* c1;
+            char close[80];
+            if (!c0) return NULL;
+            if (c0[-1] == '/') { *cend = c0 + 1; return c0 + 1; }
+            snprintf(close, sizeof close, "</%s", tag);
+            for (c1 = c0 + 1; c1 + n + 2 < e; c1++) if (*c1 == '<' && !strncmp(c1, close, n + 2) && (c1[n + 2] == '>' || c1[n + 2] == ' ')) break;
+            if (c1 + n + 2 >= e) return NULL;
+            *cend = c1; return c0 + 1;
+        }
+        p = q + 1;
+    }
+    return NULL;
+}
+static void x_text(const char* p, const char* e, char* out, size_t n) {
+    while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++;
+    while (e > p && (e[-1] == ' ' || e[-1] == '\n' || e[-1] == '\t' || e[-1] == '\r')) e--;
+    if ((size_t)(e - p) >= n) e = p + n - 1;
+    memcpy(out, p, e - p); out[e - p] = 0;
+}
+static double kb_ohm(const KBASIS* ab, int ndx) {            /* io_getohm */
+    int li; double c0, c1;
+    if ((ndx < 0) | (ndx >= ab->nangles)) return -1.;
+    for (li = 0; ndx >= ab->nphis[li]; li++) ndx -= ab->nphis[li];
+    c0 = cos(PI / 180. * ab->tmin[li]); c1 = cos(PI / 180. * ab->tmin[li + 1]);
+    return PI * (c0 * c0 - c1 * c1) / (double)ab->nphis[li];
+}
+static double safe_acos(double x) { return x <= -1. + FTINY * FTINY ? PI : x >= 1. - FTINY * FTINY ? 0. : acos(x); }
+static int kb_ndx(const KBASIS* ab, double vx, double vy, double vz) {     /* fo_getndx */
+    int li, ndx; double pol, azi;
+    if ((vz < 0) | (vz > 1.00001)) return -1;
+    pol = 180.0 / PI * safe_acos(vz);
+    azi = 180.0 / PI * atan2(vy, vx);
+    if (azi < 0.0) azi += 360.0;
+    for (li = 1; ab->tmin[li] <= pol; li++) if (!ab->nphis[li]) return -1;
+    --li;
+    ndx = (int)((1. / 360.) * azi * ab->nphis[li] + 0.5);
+    if (ndx >= ab->nphis[li]) ndx = 0;
+    while (li--) ndx += ab->nphis[li];
+    return ndx;
+}
+static void kb_vec(orc_scene* s, const KBASIS* ab, int ndx, double* v) {    /* fo_getvec, two fresh uniforms for the patch */
+    int li; double c0, c1, d, azi, rx0 = frandom(s), rx1 = frandom(s);
+    for (li = 0; ndx >= ab->nphis[li]; li++) ndx -= ab->nphis[li];
+    c0 = cos(PI / 180. * ab->tmin[li]); c1 = cos(PI / 180. * ab->tmin[li + 1]);
+    d = (1. - rx0) * c0 * c0 + rx0 * c1 * c1;
+    v[2] = d = sqrt(d);
+    azi = 2. * PI * (ndx + rx1 - .5) / ab->nphis[li];
+    d = sqrt(1. - d * d);
+    v[0] = cos(azi) * d; v[1] = sin(azi) * d;
+}
+static int k_infront(int k) { return k == K_TF || k == K_RF; }
+static int k_outfront(int k) { return k == K_TB || k == K_RF; }
+static int kc_incndx(const struct orc_bsdf* b, int k, const double* v) {
+    const KBASIS* ab = &b->bases[b->c[k].ib];
+    return k_infront(k) ? kb_ndx(ab, -v[0], -v[1], v[2]) : kb_ndx(ab, -v[0], -v[1], -v[2]);
+}
+static int kc_outndx(const struct orc_bsdf* b, int k, const double* v) {
+    const KBASIS* ab = &b->bases[b->c[k].ob];
+    return k_outfront(k) ? kb_ndx(ab, v[0], v[1], v[2]) : kb_ndx(ab, v[0], v[1], -v[2]);
+}
+static float kc_color(const KCOMP* c, int i, int o) {        /* mBSDF_color, grayscale */
+    float coef = c->v[(size_t)o * c->ninc + i];
+    double d = 2 * c->ninc / (i + .22545) + 4 * c->nout / (o + .70281);
+    d -= (int)d;
+    coef *= 1. + 6e-4 * (d - .5);
+    return coef;
+}
+static int kc_get(const struct orc_bsdf* b, int k, const double* in, const double* out, float* coef) {   /* SDgetMtxBSDF */
+    int i = kc_incndx(b, k, in), o = kc_outndx(b, k, out);
+    if ((i < 0) & (o < 0)) { i = kc_incndx(b, k, out); o = kc_outndx(b, k, in); }
+    if ((i < 0) | (o < 0)) return 0;
+    *coef = kc_color(&b->c[k], i, o);
+    return 1;
+}
+static void kc_query(const struct orc_bsdf* b, int k, double* psa, const double* v1, const double* v2, int minmax) {
+    const KCOMP* c = &b->c[k]; int same = v2 == NULL; double out_psa, inc_psa;
+    if (same) v2 = v1;
+    out_psa = kb_ohm(&b->bases[c->ob], kc_outndx(b, k, v1));
+    inc_psa = kb_ohm(&b->bases[c->ib], kc_incndx(b, k, v2));
+    if (!same & (out_psa <= 0) & (inc_psa <= 0)) {
+        inc_psa = kb_ohm(&b->bases[c->ob], kc_outndx(b, k, v2));
+        out_psa = kb_ohm(&b->bases[c->ib], kc_incndx(b, k, v1));
+    }
+    if (minmax) { if (inc_psa > psa[1]) psa[1] = inc_psa; if (out_psa > psa[1]) psa[1] = out_psa; }
+    if ((inc_psa > 0) & (inc_psa < psa[0])) psa[0] = inc_psa;
+    if ((out_psa > 0) & (out_psa < psa[0])) psa[0] = out_psa;
+}
+static int sd_tcomp(const struct orc_bsdf* b, int front) {
+    if (front) return b->c[K_TF].present ? K_TF : b->c[K_TB].present ? K_TB : -1;
+    return b->c[K_TB].present ? K_TB : b->c[K_TF].present ? K_TF : -1;
+}
+static int sd_rcomp(const struct orc_bsdf* b, int front) { int k = front ? K_RF : K_RB; return b->c[k].present ? k : -1; }
+static void sd_size(const struct orc_bsdf* b, double* psa, const double* v1, const double* v2, int minmax) {   /* SDsizeBSDF */
+    int front = v1[2] > 0, rk = sd_rcomp(b, front), tk = sd_tcomp(b, front);
+    if (minmax) psa[1] = .0;
+    psa[0] = 10.;
+    if (v2 != NULL) { if ((v1[2] > 0) ^ (v2[2] > 0)) rk = -1; else tk = -1; }
+    if (rk >= 0) kc_query(b, rk, psa, v1, v2, minmax);
+    if (tk >= 0) kc_query(b, tk, psa, v1, v2, minmax);
+    if ((rk < 0) & (tk < 0)) { psa[0] = PI; if (minmax) psa[1] = PI; }
+    else if (minmax && psa[0] > psa[1]) psa[0] = psa[1];
+}
+static double sd_eval(const struct orc_bsdf* b, const double* in, const double* out) {      /* SDevalBSDF: cieY */
+    int inF = in[2] > 0, outF = out[2] > 0, k; double y; float coef;
+    if (inF & outF) { y = b->lamb[0]; k = sd_rcomp(b, 1); }
+    else if (!(inF | outF)) { y = b->lamb[1]; k = sd_rcomp(b, 0); }
+    else if (inF) { y = b->lamb[2]; k = sd_tcomp(b, 1); }
+    else { y = b->lamb[3]; k = sd_tcomp(b, 0); }
+    y *= 1. / PI;
+    if (k >= 0 && kc_get(b, k, in, out, &coef)) y += coef;
+    return y;
+}
+/* make_cdist(): cumulative table of one incident (or, reversed, exiting) direction; returns cTotal */
+static double kc_cdist(const struct orc_bsdf* b, int k, const double* in, int* indx, int* rev, unsigned* carr) {
+    const KCOMP* c = &b->c[k]; int calen, o; double cm[2310], scale; const KBASIS* ob;
+    *indx = kc_incndx(b, k, in); *rev = 0;
+    if (*indx < 0) { *indx = kc_outndx(b, k, in); *rev = 1; if (*indx < 0) return -1.; }
+    calen = *rev ? c->ninc : c->nout;
+    ob = &b->bases[*rev ? c->ib : c->ob];
+    cm[0] = .0;
+    for (o = 0; o < calen; o++) {
+        cm[o + 1] = (*rev ? c->v[(size_t)*indx * c->ninc + o] : c->v[(size_t)o * c->ninc + *indx]) * kb_ohm(ob, o);
+        cm[o + 1] += cm[o];
+    }
+    if (carr) {
+        scale = 4294967295.0 / cm[calen];
+        carr[0] = 0;
+        for (o = 1; o < calen; o++) carr[o] = (unsigned)(scale * cm[o] + .5);
+        carr[calen] = 0xffffffffu;
+    }
+    return cm[calen];
+}
+static double sd_direct_hemi(const struct orc_bsdf* b, const double* in, int xmit) {       /* SDdirectHemi, Sp only */
+    int k = xmit ? sd_tcomp(b, in[2] > 0) : sd_rcomp(b, in[2] > 0), indx, rev; double t;
+    if (k < 0) return 0.;
+    t = kc_cdist(b, k, in, &indx, &rev, NULL);
+    return t < 0 ? 0. : t;
+}
+static double kc_sample(orc_scene* s, const struct orc_bsdf* b, int k, double* io, double randX) {    /* SDsampComponent */
+    unsigned carr[2310], target; int indx, rev, i, ilower, iupper, calen, front; const KCOMP* c = &b->c[k];
+    double cieY = kc_cdist(b, k, io, &indx, &rev, carr);
+    if (cieY <= 1e-6) { io[0] = io[1] = io[2] = 0; return 0.; }
+    calen = rev ? c->ninc : c->nout;
+    target = (unsigned)(randX * 4294967295.0);
+    ilower = 0; iupper = calen;
+    while ((i = (iupper + ilower) >> 1) != ilower) if (target >= carr[i]) ilower = i; else iupper = i;
+    kb_vec(s, &b->bases[rev ? c->ib : c->ob], i, io);
+    front = rev ? k_infront(k) : k_outfront(k);
+    if (rev) { io[0] = -io[0]; io[1] = -io[1]; if (!front) io[2] = -io[2]; }
+    else if (!front) io[2] = -io[2];
+    return cieY;
+}
+static int sd_map_dir(double* res, double m[3][3], const double* in) {
+    double t[3]; int a;
+    for (a = 0; a < 3; a++) t[a] = m[a][0] * in[0] + m[a][1] * in[1] + m[a][2] * in[2];
+    if (normalize(t) == 0) return 0;
+    res[0] = t[0]; res[1] = t[1]; res[2] = t[2];
+    return 1;
+}
+static void gray2rgb(float* col, double y) {          /* ccy2scolor(&c_dfcolor, y): float chromaticity (1/3, 1/3) through xyz2rgbmat */
+    col[0] = (float)y; col[1] = (float)y; col[2] = (float)(y * 0.9999998807907104);
+}
+
+static struct orc_bsdf* load_bsdf(orc_scene* s, const char* fname, const char* dir) {
+    struct orc_bsdf* b; FILE* fp = NULL; char path[1024], txt[256]; char* buf; long sz; const char *e, *lay, *laye, *dd, *dde, *p, *pe, *q, *qe;
+    int row_in, k, i;
+    for (b = s->bsdfs; b; b = b->next) if (!strcmp(b->file, fname)) return b;
+    {   /* getpath(): as given, then RAYPATH, then next to the octree */
+        const char* rp = getenv("RAYPATH"); char* cp; char* tok; char rpc[4096];
+        if (fname[0] == '/' || fname[0] == '.') { snprintf(path, sizeof path, "%s", fname); fp = fopen(path, "rb"); }
+        else {
+            snprintf(rpc, sizeof rpc, "%s", rp ? rp : ".");
+            for (tok = strtok_r(rpc, ":", &cp); tok && !fp; tok = strtok_r(NULL, ":", &cp)) { snprintf(path, sizeof path, "%s/%s", tok, fname); fp = fopen(path, "rb"); }
+        }
+        if (!fp) { snprintf(path, sizeof path, "%s%s", dir, fname); fp = fopen(path, "rb"); }
+    }
+    if (!fp) { fail(s, "cannot find BSDF file", fname); return NULL; }
+    fseek(fp, 0, SEEK_END); sz = ftell(fp); fseek(fp, 0, SEEK_SET);
+    buf = (char*)malloc(sz + 1);
+    if (fread(buf, 1, sz, fp) != (size_t)sz) sz = 0;
+    fclose(fp); buf[sz] = 0; e = buf + sz;
+    b = (struct orc_bsdf*)calloc(1, sizeof *b);
+    b->file = strdup(fname);
+    {
+        static const KBASIS kl[3] = {
+            {"LBNL/Klems Full", 145, 9, {0., 5., 15., 25., 35., 45., 55., 65., 75., 90.}, {1, 8, 16, 20, 24, 24, 24, 16, 12, 0}},
+            {"LBNL/Klems Half", 77, 7, {0., 6.5, 19.5, 32.5, 45.5, 58.5, 71.5, 90.}, {1, 8, 12, 16, 20, 12, 8, 0}},
+            {"LBNL/Klems Quarter", 41, 5, {0., 9., 27., 45., 63., 90.}, {1, 8, 12, 12, 8, 0}}};
+        memcpy(b->bases, kl, sizeof kl); b->nbases = 3;
+    }
+    p = x_find(buf, e, "Optical", &pe);
+    lay = p ? x_find(p, pe, "Layer", &laye) : NULL;
+    dd = lay ? x_find(lay, laye, "DataDefinition", &dde) : NULL;
+    q = dd ? x_find(dd, dde, "IncidentDataStructure", &qe) : NULL;
+    if (!q) { fail(s, "BSDF: missing IncidentDataStructure in", fname); goto bad; }
+    x_text(q, qe, txt, sizeof txt);
+    if (!strncasecmp(txt, "TensorTree", 10)) { fail(s, "oracle: tensor-tree BSDF data is not built:", fname); goto bad; }
+    if (!strcasecmp(txt, "Rows")) row_in = 1; else if (!strcasecmp(txt, "Columns")) row_in = 0;
+    else { fail(s, "BSDF: unsupported IncidentDataStructure in", fname); goto bad; }
+    for (p = dd; (q = x_find(p, dde, "AngleBasis", &qe)) != NULL; p = qe + 1) {        /* load_angle_basis() */
+        const char *n0, *n1, *bp, *b0, *b1; KBASIS* kb; int known = 0;
+        n0 = x_find(q, qe, "AngleBasisName", &n1);
+        if (!n0) continue;
+        x_text(n0, n1, txt, sizeof txt);
+        if (!*txt) continue;
+        for (i = b->nbases; i--;) if (!strcasecmp(txt, b->bases[i].name)) known = 1;
+        if (known) continue;
+        if (b->nbases >= 8) { fail(s, "BSDF: out of angle bases reading", fname); goto bad; }
+        kb = &b->bases[b->nbases]; memset(kb, 0, sizeof *kb);
+        snprintf(kb->name, sizeof kb->name, "%s", txt);
+        i = 0;
+        for (bp = q; (b0 = x_find(bp, qe, "AngleBasisBlock", &b1)) != NULL; bp = b1 + 1, i++) {
+            const char *t0, *t1, *u0, *u1; char num[64];
+            if (i >= KMAXLATS) { fail(s, "BSDF: too many latitudes in", fname); goto bad; }
+            t0 = x_find(b0, b1, "ThetaBounds", &t1);
+            u0 = t0 ? x_find(t0, t1, "UpperTheta", &u1) : NULL;
+            if (!u0) { fail(s, "BSDF: bad angle basis in", fname); goto bad; }
+            x_text(u0, u1, num, sizeof num); kb->tmin[i + 1] = atof(num);
+            if (!i) kb->tmin[0] = 0;
+            u0 = x_find(b0, b1, "nPhis", &u1);
+            if (!u0) { fail(s, "BSDF: bad angle basis in", fname); goto bad; }
+            x_text(u0, u1, num, sizeof num);
+            kb->nangles += kb->nphis[i] = atoi(num);
+            if (kb->nphis[i] <= 0 || (kb->nphis[i] == 1 && kb->tmin[i] > FTINY)) { fail(s, "BSDF: illegal phi count in", fname); goto bad; }
+        }
+        kb->nphis[i] = 0; kb->nlat = i;
+        b->nbases++;
+    }
+    for (p = lay; (q = x_find(p, laye, "WavelengthData", &qe)) != NULL; p = qe + 1) {
+        const char *w0, *w1, *bp, *b0, *b1;
+        w0 = x_find(q, qe, "Wavelength", &w1);
+        if (!w0) continue;
+        x_text(w0, w1, txt, sizeof txt);
+        if (!strcasecmp(txt, "CIE-X") || !strcasecmp(txt, "CIE-Z")) { fail(s, "oracle: colour BSDF data is not built:", fname); goto bad; }
+        if (strcasecmp(txt, "Visible")) continue;
+        for (bp = q; (b0 = x_find(bp, qe, "WavelengthDataBlock", &b1)) != NULL; bp = b1 + 1) {      /* load_bsdf_data() */
+            const char *d0, *d1; KCOMP* c; int ib = -1, ob = -1, o; char* sp; double* ohma;
+            d0 = x_find(b0, b1, "WavelengthDataDirection", &d1);
+            if (!d0) continue;
+            x_text(d0, d1, txt, sizeof txt);
+            if (!strcasecmp(txt, "Transmission Front")) k = K_TB;          /* front and back are reversed from WINDOW 6 */
+            else if (!strcasecmp(txt, "Transmission Back")) k = K_TF;
+            else if (!strcasecmp(txt, "Reflection Front")) k = K_RB;
+            else if (!strcasecmp(txt, "Reflection Back")) k = K_RF;
+            else continue;
+            d0 = x_find(b0, b1, "ColumnAngleBasis", &d1);
+            if (d0) { x_text(d0, d1, txt, sizeof txt); for (i = b->nbases; i--;) if (!strcasecmp(txt, b->bases[i].name)) { ib = i; break; } }
+            d0 = x_find(b0, b1, "RowAngleBasis", &d1);
+            if (d0) { x_text(d0, d1, txt, sizeof txt); for (i = b->nbases; i--;) if (!strcasecmp(txt, b->bases[i].name)) { ob = i; break; } }
+            if ((ib < 0) | (ob < 0)) { fail(s, "BSDF: undefined angle basis in", fname); goto bad; }
+            c = &b->c[k];
+            free(c->v); memset(c, 0, sizeof *c);
+            c->present = 1; c->ib = ib; c->ob = ob; c->ninc = b->bases[ib].nangles; c->nout = b->bases[ob].nangles;
+            c->v = (float*)calloc((size_t)c->ninc * c->nout, sizeof(float));
+            d0 = x_find(b0, b1, "ScatteringData", &d1);
+            if (!d0) { fail(s, "BSDF: missing ScatteringData in", fname); goto bad; }
+            sp = (char*)d0;
+            for (i = 0; i < c->ninc * c->nout; i++) {
+                char* ep; double val = strtod(sp, &ep);
+                if (ep == sp || ep > d1) { fail(s, "BSDF: bad ScatteringData in", fname); goto bad; }
+                sp = ep;
+                while (sp < d1 && (*sp == ' ' || *sp == '\n' || *sp == '\t' || *sp == '\r')) sp++;
+                if (*sp == ',') sp++;
+                if (val < 0) val = 0;
+                if (row_in) { int r = i / c->nout, cc = i - r * c->nout; c->v[(size_t)cc * c->ninc + r] = (float)val; }
+                else c->v[i] = (float)val;
+            }
+            c->minProjSA = PI; c->maxHemi = .0;                 /* get_extrema() */
+            ohma = (double*)malloc(c->nout * sizeof(double));
+            for (o = c->nout; o--;) if ((ohma[o] = kb_ohm(&b->bases[ob], o)) < c->minProjSA) c->minProjSA = ohma[o];
+            for (i = c->ninc; i--;) {
+                double hemi = .0;
+                for (o = c->nout; o--;) hemi += ohma[o] * c->v[(size_t)o * c->ninc + i];
+                if (hemi > c->maxHemi) c->maxHemi = hemi;
+            }
+            free(ohma);
+            if (ib != ob) for (i = c->ninc; i--;) { double ohm = kb_ohm(&b->bases[ib], i); if (ohm < c->minProjSA) c->minProjSA = ohm; }
+        }
+    }
+    for (k = 0; k < 4; k++) {                                       /* extract_diffuse() in SDloadMtx()'s order: rf, rb, tf, tb */
+        KCOMP* c = &b->c[k]; float ymin = 1e10f; int o; size_t n;
+        if (!c->present) continue;
+        for (i = 0; i < c->ninc; i++) for (o = 0; o < c->nout; o++) { float v = kc_color(c, i, o); if (v < ymin) ymin = v; }
+        if (ymin <= .01 / PI) continue;
+        for (n = (size_t)c->ninc * c->nout; n--;) c->v[n] -= ymin;
+        b->lamb[k] = PI * ymin;
+        c->maxHemi -= b->lamb[k];
+    }
+    if (b->c[K_TB].present) { if (!b->c[K_TF].present) b->lamb[K_TF] = b->lamb[K_TB]; }
+    else if (b->c[K_TF].present) b->lamb[K_TB] = b->lamb[K_TF];
+    for (k = 0; k < 4; k++) if (b->c[k].present && b->c[k].maxHemi <= .001) { free(b->c[k].v); memset(&b->c[k], 0, sizeof(KCOMP)); }
+    free(buf);
+    b->next = s->bsdfs; s->bsdfs = b;
+    return b;
+bad:
+    free(buf); for (k = 0; k < 4; k++) free(b->c[k].v); free(b->file); free(b);
+    return NULL;
+}
+
+static void free_bsdfs(orc_scene* s) {
+    while (s->bsdfs) { struct orc_bsdf* b = s->bsdfs; int k; s->bsdfs = b->next; for (k = 0; k < 4; k++) free(b->c[k].v); free(b->file); free(b); }
+}
+
+/* m_bsdf.c:116-219 */
+static void compute_through(orc_scene* s, NORMDAT* nd, const struct orc_bsdf* b) {
+    static const float d2c[29][2] = {{0, 0}, {-0.6f, 0}, {0, 0.6f}, {0, -0.6f}, {0.6f, 0}, {-0.6f, 0.6f}, {-0.6f, -0.6f}, {0.6f, 0.6f}, {0.6f, -0.6f},
+        {-1.2f, 0}, {0, 1.2f}, {0, -1.2f}, {1.2f, 0}, {-1.2f, 1.2f}, {-1.2f, -1.2f}, {1.2f, 1.2f}, {1.2f, -1.2f}, {-1.8f, 0},
+        {0, 1.8f}, {0, -1.8f}, {1.8f, 0}, {-1.8f, 1.8f}, {-1.8f, -1.8f}, {1.8f, 1.8f}, {1.8f, -1.8f}, {-2.4f, 0}, {0, 2.4f}, {0, -2.4f}, {2.4f, 0}};
+    struct { double vy, tdir[3]; float vcol; } ps[29], tmp; int tk = sd_tcomp(b, nd->rp->rod > 0), i, j, ns = 0; double srch, vypeak = 0, tomsum = 0, tomsurr = 0, tom[2];
+    float vpeak = 0, vsurr = 0, btdiff;
+    (void)s;
+    if (tk < 0) return;
+    srch = sqrt(b->c[tk].minProjSA);
+    for (i = 0; i < 29; i++) {
+        ps[i].tdir[0] = -nd->vray[0] + d2c[i][0] * srch; ps[i].tdir[1] = -nd->vray[1] + d2c[i][1] * srch; ps[i].tdir[2] = -nd->vray[2];
+        normalize(ps[i].tdir);
+        ps[i].vy = sd_eval(b, nd->vray, ps[i].tdir); ps[i].vcol = (float)ps[i].vy;
+    }
+    for (i = 1; i < 29; i++) { tmp = ps[i]; for (j = i; j > 0 && ps[j - 1].vy < tmp.vy; j--) ps[j] = ps[j - 1]; ps[j] = tmp; }   /* descending, stable */
+    if (ps[0].vy <= FTINY) return;
+    for (i = 0; i < 29; i++) {
+        if (i && ps[i].vy == ps[i - 1].vy) continue;
+        sd_size(b, tom, nd->vray, ps[i].tdir, 0);
+        ps[i].vcol = (float)(ps[i].vcol * tom[0]);
+        if (tom[0] > 1.5 * b->c[tk].minProjSA || vypeak > 8. * ps[i].vy * ns) {
+            if (!i) return;
+            vsurr += ps[i].vcol; tomsurr += tom[0];
+            continue;
+        }
+        vpeak += ps[i].vcol; tomsum += tom[0]; vypeak += ps[i].vy; ++ns;
+    }
+    if (tomsurr < 0.2 * tomsum) return;
+    vsurr = (float)(vsurr * (1. / tomsurr));
+    btdiff = (float)(nd->vray[2] > 0 ? b->lamb[K_TF] : b->lamb[K_TB]);
+    btdiff = (float)(btdiff * (1. / PI));
+    if ((vpeak -= (float)(tomsum * btdiff)) < 0) vpeak = 0;
+    if ((vsurr -= btdiff) < 0) vsurr = 0;
+    if (vpeak < .0005f) return;
+    gray2rgb(nd->cthru_surr, vsurr); gray2rgb(nd->cthru, vpeak);
+}
+static void bsdf_jitter(orc_scene* s, double* vres, const double* vray, double sr_psa) {     /* m_bsdf.c:222-233 */
+    vres[0] = vray[0]; vres[1] = vray[1]; vres[2] = vray[2];
+    if (s->P.specjitter < 1.) sr_psa *= s->P.specjitter;
+    if (sr_psa <= FTINY) return;
+    vres[0] += sr_psa * (.5 - frandom(s)); vres[1] += sr_psa * (.5 - frandom(s));
+    normalize(vres);
+}
+static int direct_specular_ok(orc_scene* s, float* scval, const double* ldir, double omega, NORMDAT* nd) {     /* m_bsdf.c:236-342 */
+    const struct orc_bsdf* b = nd->bsdf; double vsrc[3], tom[2], tom2[2], tsr, diffY = 0, svY; float cdiff[3] = {0, 0, 0}, csmp[3]; int nsamp = 1, scnt = 0, i, k, anyt;
+    scval[0] = scval[1] = scval[2] = 0;
+    if (!sd_map_dir(vsrc, nd->toloc, ldir)) return 0;
+    if (((vsrc[2] > 0) ^ (nd->vray[2] > 0)) && max3f(nd->cthru) > FTINY) {
+        double dx = vsrc[0] + nd->vray[0], dy = vsrc[1] + nd->vray[1], mp = b->c[sd_tcomp(b, nd->rp->rod > 0)].minProjSA, tomega = omega * fabs(vsrc[2]);
+        if (dx * dx + dy * dy <= (2.5 * 4. / PI) * (tomega + mp + 2. * sqrt(tomega * mp))) {
+            if (max3f(nd->cthru_surr) <= FTINY) return 0;
+            for (k = 0; k < 3; k++) scval[k] = nd->cthru_surr[k];
+            return 1;
+        }
+    }
+    anyt = b->c[K_TF].present | b->c[K_TB].present;
+    switch ((vsrc[2] > 0) << 1 | (nd->vray[2] > 0)) {
+    case 3: if (!b->c[K_RF].present) return 0; svY = b->lamb[0]; break;
+    case 0: if (!b->c[K_RB].present) return 0; svY = b->lamb[1]; break;
+    case 1: if (!anyt) return 0; svY = b->lamb[2]; break;
+    default: if (!anyt) return 0; svY = b->lamb[3]; break;
+    }
+    if (svY > FTINY) { diffY = svY *= 1. / PI; gray2rgb(cdiff, svY); }
+    sd_size(b, tom, nd->vray, vsrc, 0);
+    if ((tsr = sqrt(tom[0])) > 0) { nsamp = (int)(4. * s->P.specjitter * nd->rp->rweight + .5); nsamp += !nsamp; }
+    for (i = nsamp; i--;) {
+        double vjit[3], y;
+        bsdf_jitter(s, vjit, nd->vray, tsr);
+        y = sd_eval(b, vjit, vsrc);
+        if (y - diffY <= FTINY) { ++scnt; continue; }
+        sd_size(b, tom2, vjit, vsrc, 0);
+        if (tom2[0] < .12 * tom[0]) continue;
+        gray2rgb(csmp, y);
+        for (k = 0; k < 3; k++) scval[k] += csmp[k];
+        ++scnt;
+    }
+    if (!scnt) return 0;
+    for (k = 0; k < 3; k++) scval[k] = (float)(scval[k] * (1. / scnt));
+    if (diffY > FTINY) for (k = 0; k < 3; k++) if ((scval[k] -= cdiff[k]) < 0) scval[k] = 0;
+    return 1;
+}
+static void dir_bsdf(orc_scene* s, float* scval, NORMDAT* np, const double* ldir, double omega) {       /* m_bsdf.c:345-482, mode 0 / 1 / 2 */
+    double ldot = dot(np->pnorm, ldir), d; float sct[3]; int k;
+    scval[0] = scval[1] = scval[2] = 0;
+    if (np->dmode == 0) { if ((-FTINY <= ldot) & (ldot <= FTINY)) return; }
+    else if (np->dmode == 1) { if (ldot <= FTINY) return; }
+    else if (ldot >= -FTINY) return;
+    if (np->dmode != 2 && ldot > 0 && max3f(np->mcolor) > FTINY) { d = ldot * omega * (1. / PI); for (k = 0; k < 3; k++) scval[k] += (float)(np->mcolor[k] * d); }
+    if (np->dmode != 1 && ldot < 0 && max3f(np->scolor) > FTINY) { d = -ldot * omega * (1. / PI); for (k = 0; k < 3; k++) scval[k] += (float)(np->scolor[k] * d); }
+    if (!direct_specular_ok(s, sct, ldir, omega, np)) return;
+    d = (ldot < 0 ? -ldot : ldot) * omega;
+    for (k = 0; k < 3; k++) scval[k] += (float)(sct[k] * d);
+}
+static int m_bsdf(orc_scene* s, const OBJ* m, RAY* r) {              /* m_bsdf.c:625-804, sample_sdf :555-623, sample_sdcomp :484-553 */
+    const int hasthick = m->otype == T_BSDF, hitfront = r->rod > 0; NORMDAT nd; const struct orc_bsdf* b; double thick = 0, up[3], sr_vpsa[2], vtmp[3];
+    double fromloc[3][3]; float unsamp[2][3] = {{0, 0, 0}, {0, 0, 0}}, sct[3]; int k, xmit, anyt; char* end;
+    if (!hitfront & !s->P.backvis) { raytrans(s, r); return 1; }
+    if ((m->nsargs < hasthick + 5) | (m->nfargs > 9) | (m->nfargs % 3)) { fail(s, "bad # arguments for", m->name); return 1; }
+    if (m->nsargs < hasthick + 5) { fail(s, "bad # arguments for", m->name); return 1; }
+    for (k = 0; k < 3 + hasthick; k++) {          /* BSDF: thick file ux uy uz funcfile; aBSDF: file ux uy uz funcfile */
+        const char* a = (hasthick && k == 0) ? m->sargs[0] : m->sargs[hasthick + 1 + (k - hasthick)];
+        double v = strtod(a, &end);
+        if (end == a || *end) { fail(s, "oracle: thickness / up vector is not a numeric constant in", m->name); return 1; }
+        if (hasthick && k == 0) thick = v; else up[k - hasthick] = v;
+    }
+    if ((-FTINY <= thick) & (thick <= FTINY)) thick = 0;
+    {   /* the function file's transform (common/xf.c:38-139): rotations and a scale only; multv3(up, up, xfm), thick *= sca */
+        double xm[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, sca = 1.0; int i = hasthick + 5, a, c, e;
+        while (i < m->nsargs) {
+            double m4[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, t[3][3], ang; const char* o = m->sargs[i];
+            if (o[0] == '-' && o[1] == 'r' && (o[2] == 'x' || o[2] == 'y' || o[2] == 'z') && !o[3] && i + 1 < m->nsargs) {
+                ang = atof(m->sargs[++i]) * (PI / 180.);
+                if (o[2] == 'x') { m4[1][1] = m4[2][2] = cos(ang); m4[2][1] = -(m4[1][2] = sin(ang)); }
+                else if (o[2] == 'y') { m4[0][0] = m4[2][2] = cos(ang); m4[0][2] = -(m4[2][0] = sin(ang)); }
+                else { m4[0][0] = m4[1][1] = cos(ang); m4[1][0] = -(m4[0][1] = sin(ang)); }
+            } else if (o[0] == '-' && o[1] == 's' && !o[2] && i + 1 < m->nsargs) { ang = atof(m->sargs[++i]); sca *= m4[0][0] = m4[1][1] = m4[2][2] = ang; }
+            else { fail(s, "oracle: transform option not built for", m->name); return 1; }
+            for (a = 0; a < 3; a++) for (c = 0; c < 3; c++) { t[a][c] = 0; for (e = 0; e < 3; e++) t[a][c] += xm[a][e] * m4[e][c]; }
+            memcpy(xm, t, sizeof t);
+            i++;
+        }
+        { double u0[3] = {up[0], up[1], up[2]}; for (c = 0; c < 3; c++) up[c] = u0[0] * xm[0][c] + u0[1] * xm[1][c] + u0[2] * xm[2][c]; }
+        thick *= sca;
+    }
+    if (thick != 0 && (r->crtype & SHADOW || !(r->crtype & (SPECULAR | AMBIENT)) || (thick > 0) ^ hitfront)) { raytrans(s, r); return 1; }
+    if (hasthick && r->crtype & SHADOW) return 1;
+    b = load_bsdf(s, m->sargs[hasthick], s->dir);
+    if (!b) return 1;
+    anyt = b->c[K_TF].present | b->c[K_TB].present;
+    if (r->crtype & SHADOW && !anyt) return 1;
+    memset(&nd, 0, sizeof nd);
+    nd.rp = r; nd.bsdf = b;
+    gray2rgb(nd.mcolor, hitfront ? b->lamb[0] : b->lamb[1]);                /* rdiff */
+    if (hitfront) { if (m->nfargs >= 3) for (k = 0; k < 3; k++) nd.mcolor[k] += (float)m->fargs[k]; }
+    else if (m->nfargs >= 6) for (k = 0; k < 3; k++) nd.mcolor[k] += (float)m->fargs[3 + k];
+    gray2rgb(nd.scolor, hitfront ? b->lamb[2] : b->lamb[3]);                /* tdiff */
+    if (m->nfargs >= 9) for (k = 0; k < 3; k++) nd.scolor[k] += (float)m->fargs[6 + k];
+    for (k = 0; k < 3; k++) nd.pnorm[k] = r->ron[k];                        /* raynormal() without a texture */
+    {   /* SDcompXform() */
+        for (k = 0; k < 3; k++) nd.toloc[2][k] = nd.pnorm[k];
+        if (normalize(nd.toloc[2]) == 0) return 1;
+        cross(nd.toloc[0], up, nd.toloc[2]);
+        if (normalize(nd.toloc[0]) == 0) return 1;          /* "Illegal orientation vector" */
+        cross(nd.toloc[1], nd.toloc[2], nd.toloc[0]);
+    }
+    for (k = 0; k < 3; k++) vtmp[k] = -r->rdir[k];
+    if (!sd_map_dir(nd.vray, nd.toloc, vtmp)) return 1;
+    if (m->otype == T_ABSDF) {
+        compute_through(s, &nd, b);
+        if (r->crtype & SHADOW) {
+            RAY tr;
+            if (rayorigin(s, &tr, TRANS, r, nd.cthru) < 0) return 1;
+            for (k = 0; k < 3; k++) tr.rdir[k] = r->rdir[k];
+            rayvalue(s, &tr);
+            for (k = 0; k < 3; k++) r->rcol[k] = tr.rcol[k] * tr.rcoef[k];
+            return 1;
+        }
+    }
+    {   /* SDinvXform(): the inverse of an orthonormal matrix, computed the general way */
+        double (*v)[3] = nd.toloc, t[3][3], d;
+        t[0][0] = v[2][2] * v[1][1] - v[2][1] * v[1][2]; t[0][1] = v[2][1] * v[0][2] - v[2][2] * v[0][1]; t[0][2] = v[1][2] * v[0][1] - v[1][1] * v[0][2];
+        d = v[0][0] * t[0][0] + v[1][0] * t[0][1] + v[2][0] * t[0][2];
+        if (d == 0) return 1;
+        d = 1. / d;
+        t[0][0] *= d; t[0][1] *= d; t[0][2] *= d;
+        t[1][0] = d * (v[2][0] * v[1][2] - v[2][2] * v[1][0]); t[1][1] = d * (v[2][2] * v[0][0] - v[2][0] * v[0][2]); t[1][2] = d * (v[1][0] * v[0][2] - v[1][2] * v[0][0]);
+        t[2][0] = d * (v[2][1] * v[1][0] - v[2][0] * v[1][1]); t[2][1] = d * (v[2][0] * v[0][1] - v[2][1] * v[0][0]); t[2][2] = d * (v[1][1] * v[0][0] - v[1][0] * v[0][1]);
+        memcpy(fromloc, t, sizeof t);
+    }
+    sd_size(b, sr_vpsa, nd.vray, NULL, 1);
+    sr_vpsa[0] = sqrt(sr_vpsa[0]); sr_vpsa[1] = sqrt(sr_vpsa[1]);
+    if (!hitfront) for (k = 0; k < 3; k++) nd.pnorm[k] = -nd.pnorm[k];
+    for (xmit = 0; xmit < 2; xmit++) {               /* sample_sdf(SDsampSpR), sample_sdf(SDsampSpT) */
+        int ck = xmit ? sd_tcomp(b, hitfront) : sd_rcomp(b, hitfront);
+        int hasthru = xmit && !(r->crtype & (SPECULAR | AMBIENT)) && max3f(nd.cthru) > FTINY, hasthru0 = hasthru;
+        double bb = 0, vjit[3], xrand, vsmp[3], vinc[3], cieY; RAY sr;
+        if (ck < 0) continue;
+        if (hasthru) {
+            RAY tr;
+            if (rayorigin(s, &tr, TRANS, r, nd.cthru) == 0) {
+                for (k = 0; k < 3; k++) tr.rdir[k] = r->rdir[k];
+                rayvalue(s, &tr);
+                for (k = 0; k < 3; k++) r->rcol[k] += tr.rcol[k] * tr.rcoef[k];
+                bb = 0.2651058201058201 * nd.cthru[0] + 0.6701058201058201 * nd.cthru[1] + 0.0647883597883598 * nd.cthru[2];
+            } else hasthru = 0;
+        }
+        if (b->c[ck].maxHemi - bb <= FTINY) bb = 0;
+        else { bsdf_jitter(s, vjit, nd.vray, sr_vpsa[1]); bb = sd_direct_hemi(b, vjit, xmit) - bb; bb *= (bb > 0); }
+        if (bb <= s->P.specthresh + FTINY) { if (bb > FTINY) unsamp[xmit][0] = unsamp[xmit][1] = unsamp[xmit][2] = (float)bb; continue; }
+        xrand = frandom(s);
+        if (s->P.specjitter < 1.) xrand = .5 + s->P.specjitter * (xrand - .5);
+        bsdf_jitter(s, vsmp, nd.vray, sr_vpsa[0]);
+        for (k = 0; k < 3; k++) vinc[k] = vsmp[k];
+        cieY = kc_sample(s, b, ck, vsmp, xrand);
+        if (cieY <= FTINY) continue;
+        if (hasthru0) { double dx = vinc[0] + vsmp[0], dy = vinc[1] + vsmp[1]; if (dx * dx + dy * dy <= sr_vpsa[0] * sr_vpsa[0]) continue; }
+        if (!sd_map_dir(sr.rdir, fromloc, vsmp)) continue;
+        for (k = 0; k < 3; k++) vtmp[k] = sr.rdir[k];
+        gray2rgb(sr.rcoef, cieY);
+        if (rayorigin(s, &sr, xmit ? TSPECULAR : RSPECULAR, r, sr.rcoef) < 0) continue;
+        for (k = 0; k < 3; k++) sr.rdir[k] = vtmp[k];
+        if (xmit && thick != 0) for (k = 0; k < 3; k++) sr.rorg[k] += r->ron[k] * -thick;
+        rayvalue(s, &sr);
+        for (k = 0; k < 3; k++) r->rcol[k] += sr.rcol[k] * sr.rcoef[k];
+    }
+    for (k = 0; k < 3; k++) sct[k] = nd.mcolor[k] + unsamp[0][k];
+    if (max3f(sct) > FTINY) { multambient(s, sct, r, nd.pnorm); for (k = 0; k < 3; k++) r->rcol[k] += sct[k]; }
+    for (k = 0; k < 3; k++) sct[k] = nd.scolor[k] + unsamp[1][k];
+    if (max3f(sct) > FTINY) {
+        double bnorm[3], keep[3];
+        for (k = 0; k < 3; k++) { bnorm[k] = -nd.pnorm[k]; keep[k] = r->rop[k]; }
+        if (thick != 0) for (k = 0; k < 3; k++) r->rop[k] = keep[k] + r->ron[k] * thick;
+        multambient(s, sct, r, bnorm);
+        for (k = 0; k < 3; k++) { r->rop[k] = keep[k]; r->rcol[k] += sct[k]; }
+    }
+    if (!anyt && max3f(nd.scolor) <= FTINY) { nd.dmode = 1; direct(s, r, &nd); }
+    else if (thick == 0) { nd.dmode = 0; direct(s, r, &nd); }
+    else {
+        double keep[3];
+        nd.dmode = 1; direct(s, r, &nd);
+        for (k = 0; k < 3; k++) { keep[k] = r->rop[k]; r->rop[k] = keep[k] + r->ron[k] * -thick; }
+        nd.dmode = 2; direct(s, r, &nd);
+        for (k = 0; k < 3; k++) r->rop[k] = keep[k];
+    }
+    return 1;
+}
+
 static int rayshade(orc_scene* s, RAY* r, int mod) {
     int tst_irrad = s->P.do_irrad && !(r->crtype & ~(PRIMARY | TRANS));
     static const double lamb[5] = {PI, PI, PI, 0, 0};
@@ -1800,7 +2364,7 @@ static int rayshade(orc_scene* s, RAY* r, int mod) {
         int flat = r->ro >= 0 && (s->objs[r->ro].otype == T_POLYGON || s->objs[r->ro].otype == T_RING);
         if (t == T_ALIAS) { if (m->nsargs) { int tgt = findmaterial(s, mod); if (tgt < 0) return 0; m = &s->objs[tgt]; t = m->otype; } else continue; }
         if (tst_irrad && is_material(t)) {
-            if (is_transp(t)) { raytrans(s, r); return 1; }
+            if (is_transp(t) || (t == T_BSDF && m->nsargs > 0 && strcmp(m->sargs[0], "0"))) { raytrans(s, r); return 1; }      /* istransp(m) || isBSDFproxy(m) */
             if (!is_light(t)) return m_normal(s, T_PLASTIC, lamb, r, flat);
         }
         switch (t) {
@@ -1809,6 +2373,7 @@ static int rayshade(orc_scene* s, RAY* r, int mod) {
         case T_PLASTIC2: case T_METAL2: case T_TRANS2: return m_aniso(s, m, r, flat);
         case T_DIELECTRIC: case T_INTERFACE: return m_dielectric(s, m, r);
         case T_GLASS: return m_glass(s, m, r);
+        case T_BSDF: case T_ABSDF: return m_bsdf(s, m, r);
         case T_GLOW: case T_LIGHT: case T_ILLUM: case T_SPOT: return m_light(s, m, r);
         default: fail(s, "unsupported modifier reached by the oracle:", m->name); return 1;
         }

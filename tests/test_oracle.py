@@ -169,6 +169,28 @@ def test_oracle_anisotropic_materials_vs_reference_golden(golden):
     assert (np.abs(v.mean(0) - g["st_mean"]) <= 5 * sem + 1e-5 * g["st_mean"]).all()
 
 
+def test_oracle_bsdf_materials_vs_reference_golden(golden, monkeypatch):
+    """BSDF / aBSDF (rt/m_bsdf.c over common/bsdf.c, bsdf_m.c on Klems-matrix XML data) restated in
+    the oracle -- its own XML scanner and loader, the BSDF library's queries, m_bsdf() in its recursive form.
+    Nothing sampled (-st 1 -ss 0): names, and every view-ray value and -I value of both fixture scenes (sun only /
+    with local lamps) equal the reference's to 1e-5; sampled (-st 0 -ss 1): per-ray means over 300 repetitions
+    within 5 combined standard errors of the reference's 1200-repetition means (reference run with -u+)."""
+    g = np.load(golden / "bsdfmat.npz")
+    D = golden / "bsdfmat"
+    for tag, octf in (("", "bsdfmat.oct"), ("lamp_", "bsdflamp.oct")):
+        s = port.Scene(D / octf, ambounce=0, dstrsrc=0.0, specthresh=1.0, specjitter=0.0, ambval=(.02, .03, .04))
+        r = s.rtrace(g["rays"])
+        assert [s.name(i) for i in r["robj"]] == list(g[tag + "surf"]) and [s.name(i) for i in r["omod"]] == list(g[tag + "mod"])
+        np.testing.assert_allclose(r["value"], g[tag + "value"], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(r["rot"], g[tag + "dist"], rtol=2e-6)
+        np.testing.assert_allclose(s.rtrace(g["sensors"], irrad=1)["value"], g[tag + "irrad"], rtol=1e-5, atol=1e-9)
+    s = port.Scene(D / "bsdfmat.oct", ambounce=0, dstrsrc=0.0, specthresh=0.0, specjitter=1.0, ambval=(.02, .03, .04), seed=9)
+    pick, reps = g["st_pick"][::2], 300
+    v = s.rtrace(np.tile(g["rays"][pick], (reps, 1)))["value"].reshape(reps, len(pick), 3)
+    sem = np.sqrt(v.var(0, ddof=1) / reps + g["st_sem"][::2] ** 2)
+    assert (np.abs(v.mean(0) - g["st_mean"][::2]) <= 5 * sem + 1e-5 * g["st_mean"][::2]).all()
+
+
 def test_oracle_dielectric_interface_vs_reference_golden(golden):
     """dielectric / interface (rt/dielectric.c, no DISPERSE) and the path
     extinction they switch on (rayparticipate, the weight estimate of rayorigin, the distant
