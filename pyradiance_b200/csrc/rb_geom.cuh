@@ -63,6 +63,14 @@ namespace rb {
 #ifndef RB_SLOW_MIN
 #define RB_SLOW_MIN 0            // lanes in curved-surface leaves that gather before their round runs (0: off; measured slower)
 #endif
+#ifndef RB_WAIT_MIN
+#define RB_WAIT_MIN 0            // (measured: 4 / 6 / 8 lanes, 8 / 16 rounds all 4-5 % SLOWER than 0) > 0: a ray whose leaf holds a curved surface that SURVIVES the in-line miss tests waits in that
+                                 // leaf (WF_WAIT) until this many lanes of its warp wait, then the leaf is redone in a round that
+                                 // runs the exact out-of-line pass for all of them (see walk_rays)
+#endif
+#ifndef RB_WAIT_ROUNDS
+#define RB_WAIT_ROUNDS 8         // ... or until this many rounds have passed (power of two)
+#endif
 #ifndef RB_PREFETCH
 #define RB_PREFETCH 0            // bit 0: prefetch the next leaf's set entries at the end of the step; bit 1: the next node's words
 #endif
@@ -365,7 +373,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
 template <int NT>
 __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, unsigned wid, int p, unsigned own,
                                           int2 ent, const double* __restrict__ g, double2 n01, double2 n2o,
-                                          float4 box, unsigned* errflag, unsigned* errobj) {
+                                          float4 box, unsigned* errflag, unsigned* errobj, bool exact = true) {
+    // `exact` false (RB_WAIT_MIN): the round does not run the out-of-line pass; a pair that needs it marks its owner
+    // (bit 31 of the candidate mask), who then waits in the leaf and redoes it in a round that does
+#define RB_DEFER(p_) do { if (exact) sm.defer[wid][atomicAdd(&sm.ndef[wid], 1)] = (unsigned short)(p_); \
+                          else atomicOr(&sm.cmask[own], 0x80000000u); } while (0)
     const int hot = RB_ENT_HOT(ent.x);
     const int kind = hot & 0xf;
     if (kind == PK_FACE) {
@@ -404,7 +416,7 @@ __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, uns
             if (disc < -1e-9 * (1.0 + hb * hb)) return;
             // both roots behind the origin (the centre lies behind and the origin is outside): no candidate either
             if ((hb > 0.0) & (c > 1e-9 * (1.0 + c))) return;
-            sm.defer[wid][atomicAdd(&sm.ndef[wid], 1)] = (unsigned short)p;
+            RB_DEFER(p);
             return;
         }
 #endif
@@ -470,9 +482,10 @@ __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, uns
                               (b - R * 1.000001 > (sm.rot[own] + 8 * RB_FTINY) * 1.000001);
             if (!miss)
 #endif
-            sm.defer[wid][atomicAdd(&sm.ndef[wid], 1)] = (unsigned short)p;
+            RB_DEFER(p);
         }
     }
+#undef RB_DEFER
 }
 
 // cusize * 2^-L, exactly what L halvings of the root cube size give
@@ -503,7 +516,7 @@ __device__ __forceinline__ double cube_size(double cs, int L) {
 // Registers carry only what a phase is working on: between phases a lane's
 // state is {flags, node word, level} plus the shared-memory columns above.
 // MUST be called by all threads of the CTA.
-enum : unsigned { WF_HAVE = 1, WF_DONE = 2, WF_RESULT = 4, WF_AFT = 8, WF_EXHAUSTED = 16 };
+enum : unsigned { WF_HAVE = 1, WF_DONE = 2, WF_RESULT = 4, WF_AFT = 8, WF_EXHAUSTED = 16, WF_WAIT = 32 };
 
 template <int NT>
 __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, WalkSmem<NT>& sm, int* __restrict__ stk,
@@ -513,7 +526,7 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
     const double cs = S.cusize;
     const int2* __restrict__ pool = reinterpret_cast<const int2*>(S.leafpool);
     unsigned fl = WF_DONE;       // WF_* flags of this lane's ray
-#if RB_SLOW_MIN > 0
+#if RB_SLOW_MIN > 0 || RB_WAIT_MIN > 0
     unsigned round = 0;
 #endif
     // cube the ray stands in: set by the refill or by phase C, consumed by phase A
@@ -717,6 +730,24 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
             if (slow & !go) { act = false; kleft = 0; }
         }
 #endif
+#if RB_WAIT_MIN > 0
+        // A ray that met a curved surface it could not dismiss in line waits in its leaf (WF_WAIT: no pairs, no step)
+        // until RB_WAIT_MIN lanes of the warp wait, nothing else is runnable, or RB_WAIT_ROUNDS rounds have passed; that
+        // round runs the exact out-of-line pass (~450 instructions) for all of them at once instead of once per
+        // round for a lane or two.  The waiting ray redoes its whole leaf then (rayreject() makes re-tests no-ops,
+        // as for surfaces that straddle leaves), so what a ray computes does not change, only when.
+        bool exact;
+        {
+            const bool waiting = act && (fl & WF_WAIT);
+            const unsigned mwait = __ballot_sync(FULL, waiting);
+            const unsigned mrun = __ballot_sync(FULL, act && !(fl & WF_WAIT));
+            exact = (__popc(mwait) >= RB_WAIT_MIN) | (mrun == 0) | ((++round & (RB_WAIT_ROUNDS - 1)) == 0);
+            if (waiting & !exact) { act = false; kleft = 0; }
+            if (exact) fl &= ~WF_WAIT;
+        }
+#else
+        const bool exact = true;
+#endif
         RB_STAT(if (act & full) { ws.leafents += kleft + 1; ws.prims += kleft; })
         // ---- phase B: the warp tests the leaves' surfaces as (ray, surface) pairs ----
         for (;;) {
@@ -766,7 +797,7 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 const double2* g2 = reinterpret_cast<const double2*>(g);
                 const double2 n01 = __ldg(&g2[0]), n2o = __ldg(&g2[1]);
                 const float4 box = __ldg(reinterpret_cast<const float4*>(g + 4));
-                pair_test(S, sm, wid, p, own, ent, g, n01, n2o, box, errflag, errobj);
+                pair_test(S, sm, wid, p, own, ent, g, n01, n2o, box, errflag, errobj, exact);
             }
 #endif
             __syncwarp();
@@ -790,6 +821,11 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
             __syncwarp();
             // owners apply rayreject() in the reference's order (raytrace.c:535-575)
             unsigned cm = m > 0 ? sm.cmask[tid] : 0u;
+#if RB_WAIT_MIN > 0
+            if (cm & 0x80000000u) {                   // a surviving curved pair in a round without the exact pass: wait here
+                fl |= WF_WAIT; act = false; cm = 0u; kleft = m;       // (kleft = m: nothing more to publish this round)
+            }
+#endif
             if (cm) {
                 double rot = sm.rot[tid];
                 int ro = sm.robj[tid];
