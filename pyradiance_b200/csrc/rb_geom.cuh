@@ -63,6 +63,13 @@ namespace rb {
 #ifndef RB_SLOW_MIN
 #define RB_SLOW_MIN 0            // lanes in curved-surface leaves that gather before their round runs (0: off; measured slower)
 #endif
+#ifndef RB_CURVED_PASS
+#define RB_CURVED_PASS 0         // (measured: 2 % SLOWER -- the kernel is bound by the length of a round's dependent chain, which
+                                 // a second loop lengthens, not by the instructions the grouping saves)
+                                 // 1: the pair loop tests polygons only and lists the other pairs; one more loop then runs the
+                                 // in-line sphere / cylinder tests for all of them together (instead of in every iteration of
+                                 // the pair loop, for the two or three lanes that happen to hold one)
+#endif
 #ifndef RB_WAIT_MIN
 #define RB_WAIT_MIN 0            // (measured: 4 / 6 / 8 lanes, 8 / 16 rounds all 4-5 % SLOWER than 0) > 0: a ray whose leaf holds a curved surface that SURVIVES the in-line miss tests waits in that
                                  // leaf (WF_WAIT) until this many lanes of its warp wait, then the leaf is redone in a round that
@@ -349,6 +356,10 @@ struct WalkSmem {
     unsigned pair[NT / 32][RB_PAIRS];   // (ray, surface) pairs of this round: leaf-set entry << 5 | owner lane
     int ndef[NT / 32];           // deferred (non-polygon) pairs of this round
     unsigned short defer[NT / 32][RB_PAIRS];   // their pair indices
+#if RB_CURVED_PASS
+    int ncur[NT / 32];           // non-polygon pairs of this pass, waiting for the curved-surface loop
+    unsigned short cur[NT / 32][RB_PAIRS];
+#endif
     double ct[NT / 32][RB_PAIRS];   // candidate distance per (ray, surface) pair (written for real candidates only)
     int cid[NT / 32][RB_PAIRS];     // candidate: object id << 1 | front
     unsigned cmask[NT];             // per owner: bit j set = its j-th pair of this pass produced a candidate
@@ -370,7 +381,8 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // other kinds are queued for the warp's second pass.
 #define RB_ENT_ID(e) ((e) & 0x1ffffff)
 #define RB_ENT_HOT(e) ((int)((unsigned)(e) >> 25))
-template <int NT>
+// PART: 0 = every kind (one loop), 1 = polygons, the rest is listed for the curved-surface loop, 2 = that loop
+template <int NT, int PART = 0>
 __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, unsigned wid, int p, unsigned own,
                                           int2 ent, const double* __restrict__ g, double2 n01, double2 n2o,
                                           float4 box, unsigned* errflag, unsigned* errobj, bool exact = true) {
@@ -380,7 +392,13 @@ __device__ __forceinline__ void pair_test(const DScene& S, WalkSmem<NT>& sm, uns
                           else atomicOr(&sm.cmask[own], 0x80000000u); } while (0)
     const int hot = RB_ENT_HOT(ent.x);
     const int kind = hot & 0xf;
-    if (kind == PK_FACE) {
+#if RB_CURVED_PASS
+    if (PART == 1 && kind != PK_FACE) {
+        if (kind != PK_NONE) sm.cur[wid][atomicAdd(&sm.ncur[wid], 1)] = (unsigned short)p;
+        return;
+    }
+#endif
+    if (PART != 2 && kind == PK_FACE) {
         const double org[3] = {sm.ray[0][own], sm.ray[1][own], sm.ray[2][own]};
         const double rd[3] = {sm.ray[3][own], sm.ray[4][own], sm.ray[5][own]};
         const double tmax = sm.rot[own] + 8 * RB_FTINY;      // ties may raise rot by < FTINY each
@@ -765,7 +783,11 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 sm.pair[wid][e0 + j] = ((unsigned)(setoff + kleft - j) << 5) | lane;
             sm.cmask[tid] = 0u;
             sm.e0[tid] = (unsigned char)min(e0, 255);
-            if (lane == 0) sm.ndef[wid] = 0;
+            if (lane == 0) { sm.ndef[wid] = 0;
+#if RB_CURVED_PASS
+                sm.ncur[wid] = 0;
+#endif
+            }
             __syncwarp();
 #if RB_PAIR_ILP == 2
             // two pairs per lane and pass: both records are in flight together
@@ -797,8 +819,26 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 const double2* g2 = reinterpret_cast<const double2*>(g);
                 const double2 n01 = __ldg(&g2[0]), n2o = __ldg(&g2[1]);
                 const float4 box = __ldg(reinterpret_cast<const float4*>(g + 4));
-                pair_test(S, sm, wid, p, own, ent, g, n01, n2o, box, errflag, errobj, exact);
+                pair_test<NT, RB_CURVED_PASS ? 1 : 0>(S, sm, wid, p, own, ent, g, n01, n2o, box, errflag, errobj, exact);
             }
+#if RB_CURVED_PASS
+            // the pairs that are not polygons, together: the in-line sphere test and the cylinder's miss tests run once
+            // per pass for all of them, not once per iteration of the loop above for a lane or two
+            __syncwarp();
+            {
+                const int ncur = sm.ncur[wid];
+                for (int q = lane; q < ncur; q += 32) {
+                    const int p = sm.cur[wid][q];
+                    const unsigned pr = sm.pair[wid][p];
+                    const unsigned own = wbase + (pr & 31);
+                    const int2 ent = __ldg(&pool[pr >> 5]);
+                    const double* g = S.geom + ent.y;
+                    const double2* g2 = reinterpret_cast<const double2*>(g);
+                    const double2 n01 = __ldg(&g2[0]), n2o = __ldg(&g2[1]);
+                    pair_test<NT, 2>(S, sm, wid, p, own, ent, g, n01, n2o, make_float4(0.f, 0.f, 0.f, 0.f), errflag, errobj, exact);
+                }
+            }
+#endif
 #endif
             __syncwarp();
             const int ndef = sm.ndef[wid];
