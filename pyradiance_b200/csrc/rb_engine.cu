@@ -123,6 +123,9 @@ __device__ __forceinline__ void load_ray(const WaveArgs& A, const QRay& q, const
 #ifndef RB_FAST_MINBLOCKS
 #define RB_FAST_MINBLOCKS 6
 #endif
+#ifndef RB_SHADE_EAGER
+#define RB_SHADE_EAGER 0
+#endif
 #ifndef RB_DIFF_MINBLOCKS
 #define RB_DIFF_MINBLOCKS 8
 #endif
@@ -132,7 +135,12 @@ __device__ __noinline__ void shade_fast_one(const WaveArgs& A, unsigned i) {
     // classification needs the last 32-byte sector of the queued ray only (type, depth, medium): a ray that ends here
     // never has the other two read
     const QRay* qp = A.qin + i;
+#if RB_SHADE_EAGER
+    const QRay q = *qp;                       // all three sectors at once: the chain below is latency, not bandwidth
+    const unsigned qinfo = q.info, qmed = q.med;
+#else
     const unsigned qinfo = __ldg(&qp->info), qmed = __ldg(&qp->med);
+#endif
     const HitRec hr = A.hits[i];
     int geomoff = 0;
     const MatRec* mat = nullptr;
@@ -142,7 +150,9 @@ __device__ __noinline__ void shade_fast_one(const WaveArgs& A, unsigned i) {
     if (cls == SC_LEAN) { A.lean[reserve_slot(&A.C->nlean)] = i; return; }
     if (cls == SC_MID) { A.mid[reserve_slot(&A.C->nmid)] = i; return; }
     if (cls == SC_SLOW) { A.slow[reserve_slot(&A.C->nslow)] = i; return; }
+#if !RB_SHADE_EAGER
     const QRay q = *qp;
+#endif
     shade_diffuse(A, q, hr, geomoff, *mat);
 }
 __global__ void __launch_bounds__(RB_SHADE_THREADS, RB_DIFF_MINBLOCKS) k_shade_fast(const __grid_constant__ WaveArgs A) {
