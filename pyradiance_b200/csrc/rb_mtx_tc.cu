@@ -34,10 +34,16 @@
 namespace rb {
 
 constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 32, TC_STAGES = 2, TC_THREADS = 192;
-#ifndef RB_TC_SEG_KB
-#define RB_TC_SEG_KB 4
-#endif
-constexpr int TC_SEG_KB = RB_TC_SEG_KB;                      // k-blocks per accumulation segment (4 = 128 products)
+// Thread-block cluster along the output columns (k_mtx_tc<TC_CL = 2, ...>): the CTAs of a cluster work on the same
+// 128 rows of A, so each loads 128 / TC_CL rows of every A tile and MULTICASTS them into the shared memory of all of
+// them (one L2 read feeds TC_CL SMs); a stage is handed back when the MMAs of every CTA of the cluster have read it
+// (tcgen05.commit with a CTA mask on the `empty` barriers, which count TC_CL arrivals).
+// Measured (tools/mtx_variants.sh): at K = 145 the kernel is bound by the bytes DELIVERED into each SM (720 KB per
+// tile at 74 GB/s per SM = the 9.7 us a tile takes), which multicast does not reduce -- clusters of 2 / 4 are 5 / 12 %
+// slower there; at K = 2305 a cluster of 2 is 7 % faster (152.6 TFLOP/s).  The host picks: clusters for K >= 512.
+constexpr int TC_CL_MAX = 2;
+// k-blocks per accumulation segment: 4 (128 products) in general; a product whose whole inner dimension fits 8 blocks
+// (K <= 256, the MF:1 daylight-coefficient case) is one segment per channel (3.3e-6 instead of 2.7e-6, 2.5 % faster)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4, TC_B_BYTES = TC_BN * TC_BK * 4;     // operand tiles: rows of 128 bytes
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;                   // A hi, A lo, B hi, B lo = 48 KB
 constexpr int TC_RING_BYTES = TC_STAGES * TC_STAGE_BYTES;    // 96 KB
@@ -65,10 +71,23 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z) : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ... arriving on the barrier at the same offset in every CTA of the mask
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], M = 128, N = 128, K = 8 (TF32), one thread issues for the CTA
 __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -151,9 +170,12 @@ __global__ void k_split_b(const float* __restrict__ B, float* __restrict__ P, in
 }
 
 // ---------------------------------------------------------------- GEMM ----
-__global__ void __launch_bounds__(TC_THREADS, 2)
+template <int TC_CL, int TC_SEG_KB>
+__global__ void __cluster_dims__(TC_CL, 1, 1) __launch_bounds__(TC_THREADS, 2)
 k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
          size_t nr, size_t nc, int nkb) {
+    constexpr uint16_t CL_MASK = (uint16_t)((1u << TC_CL) - 1u);
+    const uint32_t crank = TC_CL > 1 ? cluster_rank() : 0u;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_RING_BYTES);       // full[S], empty[S], seg_full, seg_empty
@@ -165,7 +187,8 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * TC_BN;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+        // a stage is empty once the MMAs of EVERY CTA of the cluster have read it: each of them will be written by all
+        for (int s = 0; s < TC_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, TC_CL); }
         mbar_init(seg_full, 1);
         mbar_init(seg_empty, 4);                      // one arrival per folding warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -176,6 +199,7 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     }
     tc_fence_before();
     __syncthreads();
+    if (TC_CL > 1) cluster_sync_all();                // the peers' barriers are initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
@@ -189,8 +213,14 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                 mbar_expect_tx(full0 + 8 * s, TC_STAGE_BYTES);
                 const uint32_t st = ring + s * TC_STAGE_BYTES;
-                tma_load_3d(st, &tmA, full0 + 8 * s, kb * TC_BK, m0, ch);
-                tma_load_3d(st + TC_A_BYTES, &tmA, full0 + 8 * s, kb * TC_BK, m0, 3 + ch);
+                if (TC_CL > 1) {                  // my 128 / TC_CL rows of the A tiles, into every CTA of the cluster
+                    constexpr int AR = TC_BM / TC_CL, AB = AR * TC_BK * 4;
+                    tma_load_3d_mc(st + crank * AB, &tmA, full0 + 8 * s, kb * TC_BK, m0 + (int)crank * AR, ch, CL_MASK);
+                    tma_load_3d_mc(st + TC_A_BYTES + crank * AB, &tmA, full0 + 8 * s, kb * TC_BK, m0 + (int)crank * AR, 3 + ch, CL_MASK);
+                } else {
+                    tma_load_3d(st, &tmA, full0 + 8 * s, kb * TC_BK, m0, ch);
+                    tma_load_3d(st + TC_A_BYTES, &tmA, full0 + 8 * s, kb * TC_BK, m0, 3 + ch);
+                }
                 tma_load_3d(st + 2 * TC_A_BYTES, &tmB, full0 + 8 * s, kb * TC_BK, n0, ch);
                 tma_load_3d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmB, full0 + 8 * s, kb * TC_BK, n0, 3 + ch);
             }
@@ -220,7 +250,8 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
                             tc_mma_tf32(tmem, ah + adv, bl + adv, idesc, 1u);
                             tc_mma_tf32(tmem, al + adv, bh + adv, idesc, 1u);
                         }
-                        tc_commit(empty0 + 8 * s);          // the stage is free once these MMAs have read it
+                        if (TC_CL > 1) tc_commit_mc(empty0 + 8 * s, CL_MASK);      // the stage is free once these MMAs have read it:
+                        else tc_commit(empty0 + 8 * s);                            // every producer of the cluster is told
                     }
                     tc_commit(seg_full);                    // ... and the segment is complete once they have finished
                 }
@@ -316,6 +347,7 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
         tc_fence_before();
     }
     __syncthreads();
+    if (TC_CL > 1) cluster_sync_all();                // no CTA leaves while a peer may still arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
@@ -361,15 +393,25 @@ bool mtx_multiply_tc(cudaStream_t stream, const float* A, size_t n, size_t ni, c
     const size_t Mp = (n + TC_BM - 1) / TC_BM * TC_BM;
     if (Mp > Mp_cap) { err = "internal: A plane buffer too small"; goto done; }
     TCK(cudaEventCreate(&e0)); TCK(cudaEventCreate(&e1));
-    TCK(cudaFuncSetAttribute(k_mtx_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    const int nkb = Kp / TC_BK;
+    const int cl = nkb >= 16 ? 2 : 1;                // clusters (A tiles multicast) pay for long inner dimensions only
     CUtensorMap tmA, tmB;
-    if (!make_plane_map(enc, &tmA, Aplanes, Mp, Kp, TC_BM, err) ||
+    if (!make_plane_map(enc, &tmA, Aplanes, Mp, Kp, TC_BM / cl, err) ||
         !make_plane_map(enc, &tmB, const_cast<float*>(Bplanes), Np, Kp, TC_BN, err)) goto done;
     TCK(cudaEventRecord(e0, stream));
     TCK(cudaMemsetAsync(Aplanes, 0, 6 * Mp * (size_t)Kp * sizeof(float), stream));
     k_split_a<<<148 * 16, 256, 0, stream>>>(A, Aplanes, n, (int)ni, Mp, Kp);
-    dim3 grid((unsigned)((nc + TC_BN - 1) / TC_BN), (unsigned)(Mp / TC_BM));
-    k_mtx_tc<<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmB, C, n, nc, Kp / TC_BK);
+    dim3 grid((unsigned)(Np / TC_BN), (unsigned)(Mp / TC_BM));      // Np is padded to whole clusters of column tiles
+    if (cl == 2) {
+        TCK(cudaFuncSetAttribute(k_mtx_tc<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        k_mtx_tc<2, 4><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmB, C, n, nc, nkb);
+    } else if (nkb <= 8) {
+        TCK(cudaFuncSetAttribute(k_mtx_tc<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        k_mtx_tc<1, 8><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmB, C, n, nc, nkb);
+    } else {
+        TCK(cudaFuncSetAttribute(k_mtx_tc<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        k_mtx_tc<1, 4><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmB, C, n, nc, nkb);
+    }
     TCK(cudaEventRecord(e1, stream));
     TCK(cudaGetLastError());
     TCK(cudaStreamSynchronize(stream));
@@ -387,7 +429,7 @@ done:
 bool tc_prepare_b(cudaStream_t stream, const float* B, size_t ni, size_t nc, float** planes, size_t* Np_out, int* Kp_out,
                   std::string& err) {
     const int Kp = (int)((ni + TC_BK - 1) / TC_BK * TC_BK);
-    const size_t Np = (nc + TC_BN - 1) / TC_BN * TC_BN;
+    const size_t Np = (nc + TC_BN * TC_CL_MAX - 1) / (TC_BN * TC_CL_MAX) * (TC_BN * TC_CL_MAX);      // whole clusters of column tiles
     float* P = nullptr;
     cudaError_t e = cudaMalloc(&P, 6 * Np * (size_t)Kp * sizeof(float));
     if (e != cudaSuccess) { err = std::string("cudaMalloc (B planes): ") + cudaGetErrorString(e); return false; }
