@@ -59,6 +59,9 @@ __device__ __forceinline__ void flush_stats(DCounters* C, const WalkStats& ws) {
 // Trace: octree walk + intersection only (small code).  Persistent threads:
 // the grid is sized to fill the machine once and every warp pulls rays from
 // the queue until it is empty (rb_geom.cuh walk_rays).
+#ifndef RB_SHADOW_ANYHIT
+#define RB_SHADOW_ANYHIT 1
+#endif
 #ifdef RB_TRACE_MAXNREG        // developer knob: cap the registers directly (CTA sizes whose warps do not divide evenly)
 __global__ void __maxnreg__(RB_TRACE_MAXNREG) k_trace(const WaveArgs A) {
 #else
@@ -68,6 +71,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const Wave
     extern __shared__ int stk_dyn[];         // [maxdepth + 1][WAVE_THREADS]
     TraceIO io;
     io.qin = A.qin; io.nin = A.C->nin; io.hits = A.hits; io.next = &A.C->next_ray;
+    io.anyhit = RB_SHADOW_ANYHIT && !A.nodirect && A.P.backvis;
     WalkStats ws = {0, 0, 0};
     walk_rays<WAVE_THREADS>(A.S, io, sm, stk_dyn, ws, &A.C->errflag, &A.C->errobj);
 #if RB_WALK_STATS

@@ -333,6 +333,7 @@ struct TraceIO {
     unsigned nin;
     HitRec* __restrict__ hits;
     unsigned* next;              // global fetch counter
+    int anyhit;                  // 1: shadow rays towards distant sources end at ANY surface that is opaque to shadow rays
 };
 
 // Shared memory of one CTA of k_trace (per-thread columns, SoA).  Everything a
@@ -534,7 +535,7 @@ __device__ __forceinline__ double cube_size(double cs, int L) {
 // Registers carry only what a phase is working on: between phases a lane's
 // state is {flags, node word, level} plus the shared-memory columns above.
 // MUST be called by all threads of the CTA.
-enum : unsigned { WF_HAVE = 1, WF_DONE = 2, WF_RESULT = 4, WF_AFT = 8, WF_EXHAUSTED = 16, WF_WAIT = 32 };
+enum : unsigned { WF_HAVE = 1, WF_DONE = 2, WF_RESULT = 4, WF_AFT = 8, WF_EXHAUSTED = 16, WF_WAIT = 32, WF_ANYHIT = 64 };
 
 template <int NT>
 __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, WalkSmem<NT>& sm, int* __restrict__ stk,
@@ -636,6 +637,19 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                     }
                 }
                 if (done) fl |= WF_DONE;
+                // A shadow ray towards a DISTANT source adds nothing as soon as any surface stands in its way whose material
+                // returns at once for shadow rays (plastic, metal and the anisotropic kinds: normal.c:190-191,
+                // aniso.c:203-204): which of several blockers is the nearest does not matter -- a transparent surface in
+                // front only scales what is already zero, and trace_contrib() counts a shadow ray on its source alone
+                // (rcontrib.c:283-286).  Such a ray ends at the first candidate of that kind instead of walking on to the
+                // leaf that holds the hit point.  (Local sources have an aft plane and keep the nearest-hit rule.)
+                if (io.anyhit && !done && !(fl & WF_AFT)) {
+                    const int4 t4 = __ldg(reinterpret_cast<const int4*>(&io.qin[my]) + 4);      // bytes 64..79: coef[2], rweight, row, info
+                    if (t4.w & RT_SHADOW) {
+                        const int rsrc = __ldg(&io.qin[my].rsrc);
+                        if (rsrc >= 0 && (S.srcs[rsrc].flags & SF_DISTANT)) fl |= WF_ANYHIT;
+                    }
+                }
                 px = pos[0]; py = pos[1]; pz = pos[2];
                 sm.pos[0][tid] = px; sm.pos[1][tid] = py; sm.pos[2][tid] = pz;
                 sm.rot[tid] = rot;
@@ -900,6 +914,17 @@ __device__ __forceinline__ void walk_rays(const DScene& S, const TraceIO io, Wal
                 }
                 sm.rot[tid] = rot;
                 sm.robj[tid] = ro;
+                if ((fl & WF_ANYHIT) && ro >= 0) {
+                    const int ms = __ldg(&S.objhdr[ro >> 1]).z;
+                    if (ms >= 0) {
+                        const MatRec& mr = S.mats[ms];
+                        const int mk = mr.kind;
+                        if (((mk == MK_PLASTIC) | (mk == MK_METAL) | (mk >= MK_PLASTIC2 && mk <= MK_TRANS2)) && mr.flags == 0) {
+                            fl |= WF_DONE | WF_RESULT;        // blocked: retire with this hit
+                            act = false; kleft = m;
+                        }
+                    }
+                }
             }
             kleft -= m;
             __syncwarp();
