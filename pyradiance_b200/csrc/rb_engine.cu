@@ -131,7 +131,7 @@ __device__ __forceinline__ void load_ray(const WaveArgs& A, const QRay& q, const
 #define RB_SHADE_EAGER 0
 #endif
 #ifndef RB_DIFF_MINBLOCKS
-#define RB_DIFF_MINBLOCKS 8
+#define RB_DIFF_MINBLOCKS 6
 #endif
 // (the bodies are functions of their own so that the grid-stride loop around them -- the ray count is known only on
 //  the device -- does not add to the register pressure of the shading code: inlined, the loop tripled the spills)
