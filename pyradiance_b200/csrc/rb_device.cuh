@@ -144,6 +144,7 @@ struct DCounters {
     unsigned nslow;                // rays k_shade_fast left to the general k_shade (reset with the two above)
     unsigned nmid;                 // rays it left to k_shade_mid
     unsigned nlean;                // rays it left to k_shade_lean
+    unsigned nspec;                // rays it left to k_shade_spec
     // wave chaining without the host (rb_engine.cu k_gate / k_prepare): what the kernels of the current wave read
     unsigned nin;                  // rays in the input queue of this wave
     unsigned nh_in, nd_in;         // hemispheres / parked direct() jobs to expand before it

@@ -151,6 +151,7 @@ __device__ __noinline__ void shade_fast_one(const WaveArgs& A, unsigned i) {
     const int cls = shade_class(A, qinfo, qmed, hr, geomoff, mat);
     if (cls == SC_NONE) return;
     // (one branch per class: reserve_slot() aggregates over the lanes that arrive together, which must share a counter)
+    if (cls == SC_SPEC) { A.spec[reserve_slot(&A.C->nspec)] = i; return; }
     if (cls == SC_LEAN) { A.lean[reserve_slot(&A.C->nlean)] = i; return; }
     if (cls == SC_MID) { A.mid[reserve_slot(&A.C->nmid)] = i; return; }
     if (cls == SC_SLOW) { A.slow[reserve_slot(&A.C->nslow)] = i; return; }
@@ -162,6 +163,20 @@ __device__ __noinline__ void shade_fast_one(const WaveArgs& A, unsigned i) {
 __global__ void __launch_bounds__(RB_SHADE_THREADS, RB_DIFF_MINBLOCKS) k_shade_fast(const __grid_constant__ WaveArgs A) {
     const unsigned n = A.C->nin;
     for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) shade_fast_one(A, i);
+}
+__device__ __noinline__ void shade_spec_one(const WaveArgs& A, unsigned i) {
+    const QRay q = A.qin[i];
+    const HitRec hr = A.hits[i];
+    RayCtx r;
+    load_ray(A, q, hr, r);
+    const MatRec& m = A.S.mats[__ldg(&A.S.objhdr[hr.robj]).z];
+    float na[7];
+    for (int j = 0; j < 7; j++) na[j] = m.a[j];
+    m_normal<true, true, true>(A, r, m.kind, na);
+}
+__global__ void __launch_bounds__(RB_SHADE_THREADS, RB_FAST_MINBLOCKS) k_shade_spec(const __grid_constant__ WaveArgs A) {
+    const unsigned n = A.C->nspec;
+    for (unsigned j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) shade_spec_one(A, A.spec[j]);
 }
 __device__ __noinline__ void shade_lean_one(const WaveArgs& A, unsigned i) {
     const QRay q = A.qin[i];
@@ -328,7 +343,7 @@ __global__ void k_gate(DCounters* C, unsigned qcap) {
 }
 __global__ void k_prepare(DCounters* C, unsigned wave) {
     const unsigned n = (C->overflow || C->errflag) ? 0u : C->nq_out;
-    C->nin = n; C->nq_out = 0; C->next_ray = 0; C->nslow = 0; C->nmid = 0; C->nlean = 0;
+    C->nin = n; C->nq_out = 0; C->next_ray = 0; C->nslow = 0; C->nmid = 0; C->nlean = 0; C->nspec = 0;
     C->rays_traced += n;
     C->wave_nin[wave & 63] = n;
 }
@@ -389,7 +404,7 @@ Engine::~Engine() {
     cudaSetDevice(dev_);
     cudaDeviceSynchronize();
     void* ptrs[] = {d_nodes_, d_leaf_, d_hdr_, d_geom_, d_mats_, d_srcs_, d_pats_, d_bsdfs_, d_bsdfbases_, d_bsdfpool_, d_otrack_, d_top_, d_bins_, q_[0], q_[1],
-                    h_[0], h_[1], d_hits_, dq_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_, d_slow_, d_mid_, d_lean_};
+                    h_[0], h_[1], d_hits_, dq_, d_cnt_, d_acc_, d_vacc_, d_rays_, d_out_, d_res_, d_slow_, d_mid_, d_lean_, d_spec_};
     for (void* p : ptrs) if (p) cudaFree(p);
     if (h_cnt_) cudaFreeHost(h_cnt_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -531,9 +546,9 @@ bool Engine::ensure_queues(std::string& err, size_t hint) {
     if (q_[0] && want <= qcap_) return true;
     if (q_[0]) {                            // grow: drop the old queues first
         CK(cudaStreamSynchronize(stream_));
-        void* old[] = {q_[0], q_[1], h_[0], h_[1], d_hits_, dq_, d_slow_, d_mid_, d_lean_};
+        void* old[] = {q_[0], q_[1], h_[0], h_[1], d_hits_, dq_, d_slow_, d_mid_, d_lean_, d_spec_};
         for (void* p : old) if (p) cudaFree(p);
-        q_[0] = q_[1] = nullptr; h_[0] = h_[1] = nullptr; d_hits_ = nullptr; dq_ = nullptr; d_slow_ = nullptr; d_mid_ = nullptr; d_lean_ = nullptr;
+        q_[0] = q_[1] = nullptr; h_[0] = h_[1] = nullptr; d_hits_ = nullptr; dq_ = nullptr; d_slow_ = nullptr; d_mid_ = nullptr; d_lean_ = nullptr; d_spec_ = nullptr;
     }
     size_t freeb = 0, totalb = 0;
     CK(cudaMemGetInfo(&freeb, &totalb));
@@ -550,6 +565,7 @@ bool Engine::ensure_queues(std::string& err, size_t hint) {
     CK(cudaMalloc(&d_slow_, qcap_ * sizeof(unsigned)));
     CK(cudaMalloc(&d_mid_, qcap_ * sizeof(unsigned)));
     CK(cudaMalloc(&d_lean_, qcap_ * sizeof(unsigned)));
+    CK(cudaMalloc(&d_spec_, qcap_ * sizeof(unsigned)));
     dcap_ = std::max<size_t>(qcap_ / 32, 4096);
     if (park_direct()) {      // many or local sources: direct() runs as its own kernel from a job queue
         CK(cudaMalloc(&dq_, dcap_ * sizeof(DirectJob)));
@@ -629,7 +645,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
     A.hits = d_hits_;
     A.dout = park_direct() ? dq_ : nullptr; A.dcap = (unsigned)dcap_;
     A.slow = getenv("RB_NO_SHADE_SPLIT") ? nullptr : d_slow_;
-    A.mid = d_mid_; A.lean = d_lean_;
+    A.mid = d_mid_; A.lean = d_lean_; A.spec = d_spec_;
     A.nodirect = nsrc_active_ == 0 ? 1 : 0;
 
     auto sync_counters = [&](std::string& err) -> bool {
@@ -708,10 +724,11 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
             CK(cudaEventRecord(wev_[4 * k + 1], stream_));
             if (A.slow) {
                 k_shade_fast<<<sgrid, RB_SHADE_THREADS, 0, stream_>>>(A);
-                k_shade_lean<<<big ? 148u * 24u : 148u * 6u, RB_SHADE_THREADS, 0, stream_>>>(A);
+                k_shade_spec<<<big ? 148u * 24u : 148u * 6u, RB_SHADE_THREADS, 0, stream_>>>(A);
+                k_shade_lean<<<big ? 148u * 12u : 148u * 6u, RB_SHADE_THREADS, 0, stream_>>>(A);
                 k_shade_mid<<<148u * 6u, RB_SHADE_THREADS, 0, stream_>>>(A);
                 k_shade<<<148u * 4u, RB_SHADE_THREADS, 0, stream_>>>(A);
-                stats.launches += 3;
+                stats.launches += 4;
             } else
                 k_shade<<<sgrid, RB_SHADE_THREADS, 0, stream_>>>(A);
             CK(cudaEventRecord(wev_[4 * k + 2], stream_));
@@ -729,7 +746,8 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
             stats.kernel_ms += ms0 + ms + ms2;
             if (n) { stats.wave_ms += ms; stats.shade_ms += ms2; stats.wave_launches++; stats.waves++; }
             if (getenv("RB_DEBUG_WAVES"))
-                fprintf(stderr, "[rb] wave %d: %u rays (bound %zu) trace %.3f ms shade %.3f ms\n", w0 + k, n, ub, ms, ms2);
+                fprintf(stderr, "[rb] wave %d: %u rays (bound %zu) trace %.3f ms shade %.3f ms; last wave of the chunk: spec %u lean %u mid %u slow %u\n",
+                        w0 + k, n, ub, ms, ms2, h_cnt_->nspec, h_cnt_->nlean, h_cnt_->nmid, h_cnt_->nslow);
         }
         finished = h_cnt_->nq_out == 0 && h_cnt_->nh_out == 0 && h_cnt_->nd_out == 0;
     }

@@ -93,6 +93,7 @@ private:
     unsigned* d_slow_ = nullptr;          // queue slots left to the general shading kernel
     unsigned* d_mid_ = nullptr;           // queue slots left to k_shade_mid
     unsigned* d_lean_ = nullptr;          // queue slots left to k_shade_lean
+    unsigned* d_spec_ = nullptr;          // queue slots left to k_shade_spec
     int trace_blocks_ = 148;
     size_t trace_smem_ = 0;      // dynamic shared memory of k_trace (ancestor stack)
     bool has_local_sources_ = false;

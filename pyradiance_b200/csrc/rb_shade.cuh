@@ -68,6 +68,7 @@ struct WaveArgs {
     unsigned* slow;         // [qcap] queue slots k_shade_fast leaves to the general k_shade (null: no split)
     unsigned* mid;          // [qcap] queue slots it leaves to k_shade_mid (glass, trans, spotlights)
     unsigned* lean;         // [qcap] queue slots it leaves to k_shade_lean
+    unsigned* spec;         // [qcap] queue slots it leaves to k_shade_spec
     int nodirect;           // direct() has no source to sample in this scene (every source is a glow that is skipped)
 };
 
@@ -875,7 +876,8 @@ __device__ __forceinline__ double raynormal(double norm[3], const RayCtx& r, con
 // without vertex normals, so the sampled-highlight code and the normal perturbation are compiled out; LEAN
 // (k_shade_fast) also guarantees that the material is not `trans`, and that code goes too.  Everything an
 // instantiation does execute is the same code, on the same values, as the general one.
-template <bool FAST = false, bool LEAN = false>
+// NODIRECT (k_shade_spec): the scene has no source for direct() to sample, so the call and what only it needs go.
+template <bool FAST = false, bool LEAN = false, bool NODIRECT = false>
 __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind_, const float* a) {
     const DParams& P = A.P;
     const int mkind = LEAN ? (mkind_ == MK_METAL ? MK_METAL : MK_PLASTIC) : mkind_;
@@ -1017,7 +1019,7 @@ __device__ __forceinline__ void m_normal(const WaveArgs& A, RayCtx& r, int mkind
         double bn[3] = {-nd.pnorm[0], -nd.pnorm[1], -nd.pnorm[2]};
         multambient(A, r, sct, bn);
     }
-    direct_or_park<FAST>(A, r, nd);
+    if (!NODIRECT) direct_or_park<FAST>(A, r, nd);
 }
 
 // fvect.c:159-196 getperpendicular() with randomize = 0
@@ -1710,11 +1712,12 @@ __device__ __forceinline__ void shade_ray(const WaveArgs& A, RayCtx& r) {
 //   SC_NONE  nothing to do: no hit, or a ray that provably adds nothing and spawns nothing (below)
 //   SC_DIFF  k_shade_fast itself: a surface of plastic / metal without specular reflection, in a scene whose sources
 //            are all glow: all the material does is multambient() (shade_diffuse())
+//   SC_SPEC  k_shade_spec: the same surfaces with specular reflection: m_normal<FAST, LEAN, NODIRECT> alone
 //   SC_LEAN  k_shade_lean: plastic / metal without a sampled highlight, plain light / glow emitters, surfaces
 //            without a material, the Lambertian stand-in of an irradiance ray (raytirrad) -- shade_ray<FAST, LEAN>
 //   SC_MID   k_shade_mid: glass, trans without a sampled highlight, spotlights -- shade_ray<FAST>
 //   SC_SLOW  k_shade: everything else
-enum : int { SC_NONE = 0, SC_DIFF, SC_LEAN, SC_MID, SC_SLOW };
+enum : int { SC_NONE = 0, SC_DIFF, SC_SPEC, SC_LEAN, SC_MID, SC_SLOW };
 // (geomoff / mat: the hit object's record and material, for shade_diffuse())
 __device__ __forceinline__ int shade_class(const WaveArgs& A, unsigned qinfo, unsigned qmed, const HitRec& hr, int& geomoff,
                                            const MatRec*& mat) {
@@ -1752,6 +1755,9 @@ __device__ __forceinline__ int shade_class(const WaveArgs& A, unsigned qinfo, un
             // what is left of m_normal() is multambient() with the material's colour
 #ifndef RB_NO_DIFF
             if (A.nodirect && m.a[3] == 0.f && hr.local) return SC_DIFF;
+            // the same with a specular component (mirror ray, Fresnel term): m_normal() without direct() and
+            // trace_contrib(), in a kernel of its own (k_shade_spec)
+            if (A.nodirect && hr.local && !(crtype & RT_SHADOW)) return SC_SPEC;
 #endif
         }
         return SC_LEAN;
