@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(WAVE_THREADS, RB_MINBLOCKS) k_trace(const Wave
     extern __shared__ int stk_dyn[];         // [maxdepth + 1][WAVE_THREADS]
     TraceIO io;
     io.qin = A.qin; io.nin = A.C->nin; io.hits = A.hits; io.next = &A.C->next_ray;
-    io.anyhit = RB_SHADOW_ANYHIT && !A.nodirect && A.P.backvis;
+    io.anyhit = A.anyhit;
     WalkStats ws = {0, 0, 0};
     walk_rays<WAVE_THREADS>(A.S, io, sm, stk_dyn, ws, &A.C->errflag, &A.C->errobj);
 #if RB_WALK_STATS
@@ -647,6 +647,7 @@ bool Engine::run_batch(const TraceJob& job, const DParams& P, size_t rec0, size_
     A.slow = getenv("RB_NO_SHADE_SPLIT") ? nullptr : d_slow_;
     A.mid = d_mid_; A.lean = d_lean_; A.spec = d_spec_;
     A.nodirect = nsrc_active_ == 0 ? 1 : 0;
+    A.anyhit = (RB_SHADOW_ANYHIT && !A.nodirect && P.backvis && !getenv("RB_NO_ANYHIT")) ? 1 : 0;      // (the variable: for the test that both give one matrix)
 
     auto sync_counters = [&](std::string& err) -> bool {
         CK(cudaMemcpyAsync(h_cnt_, d_cnt_, sizeof(DCounters), cudaMemcpyDeviceToHost, stream_));

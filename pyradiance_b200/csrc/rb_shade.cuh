@@ -70,6 +70,7 @@ struct WaveArgs {
     unsigned* lean;         // [qcap] queue slots it leaves to k_shade_lean
     unsigned* spec;         // [qcap] queue slots it leaves to k_shade_spec
     int nodirect;           // direct() has no source to sample in this scene (every source is a glow that is skipped)
+    int anyhit;             // k_trace: shadow rays towards distant sources end at any surface opaque to shadow rays
 };
 
 struct RayCtx {             // the ray being shaded (a subset of RAY, rt/ray.h:48-83)

@@ -813,6 +813,30 @@ def test_cone_family_and_rayreject_vs_reference_golden(golden, monkeypatch, tag,
                                                             v[bad][:5], g_value[bad][:5])
 
 
+def test_shadow_rays_any_blocker_is_result_neutral(golden, monkeypatch):
+    """k_trace ends a shadow ray towards a DISTANT source at the first surface that is opaque to shadow rays instead of
+    its nearest hit: the coefficient matrix must not depend on that -- same random keys, so the matrices of
+    the miniature sun scene (145 suns, louvre instances, meshes, a glass skylight, -ab 1) with the rule on and off are
+    equal up to the order of the double-precision atomic additions."""
+    octf = golden / "volumes" / "sunroom.oct"
+    sens = np.load(golden / "sunroom_sensors.npy")
+    out = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("RB_NO_ANYHIT", "1")
+        ctx = _lib.Context(0, _lib.RB_PROGRAM_RCONTRIB)
+        ctx.load_octree(octf)
+        ctx.set_options(["-ab", "1", "-ad", "256", "-lw", "1e-3", "-dc", "1", "-dt", "0", "-dj", "0"])
+        ctx.cal_load("reinhart.cal")
+        ctx.cal_set("MF=1")
+        ctx.add_modifier("solar", "", "rbin", 146)
+        out.append((ctx.rcontrib(np.tile(sens, (4, 1)), flags=_lib.RB_IRRAD_RCONTRIB, dtype=np.float64), ctx.stats()["nrays"]))
+    monkeypatch.delenv("RB_NO_ANYHIT")
+    (a, na), (b, nb) = out
+    assert a.sum() > 0 and na <= nb                  # (a blocked ray no longer sends its transmitted child through glass in front)
+    np.testing.assert_allclose(a, b, rtol=1e-9, atol=1e-15)
+
+
 def test_sun_matrix_config5_miniature(G, golden, workdir):
     """BASELINE config 5 in miniature (5-phase direct-sun matrix): 145 `light`
     suns sharing modifier `solar`, reinhart.cal rbin with -e MF:1, louvre
