@@ -359,6 +359,8 @@ def run_ours(args):
     sampler.start()
     ms = timed(step_device, args.steps)
     st = ctx.stats()
+    for _ in range(args.warmup):           # the host path has first-call costs of its own (staging buffers for rays and rows)
+        step_host()
     ctx.reset_stats()
     ms_e2e = timed(step_host, args.steps)
     st_e2e = ctx.stats()
