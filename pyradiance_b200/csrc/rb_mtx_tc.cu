@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 #include "rb_engine.cuh"
 
@@ -354,6 +355,206 @@ k_mtx_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtens
     }
 }
 
+
+// ------------------------------------------------------- GEMM, CTA pairs ----
+// k_mtx_tc2 (EXPERIMENTAL, off unless RB_MTX_2CTA is set): the same product on PAIRS of CTAs (tcgen05 cta_group::2,
+// UMMA M = 256, N = 128) for inner dimensions of at most 8 k-blocks (K <= 256: one accumulation segment per channel,
+// accumulated in place).  CTA r of a pair holds 128 rows of A and 64 of the tile's 128 columns of B in its shared
+// memory; the leader's MMAs read both halves of B and write, in each CTA's tensor memory, that CTA's 128 x 128
+// accumulator (three channels: 384 columns).  Per byte delivered into an SM the pair computes twice what k_mtx_tc does.
+//   * every CTA: warp 0 feeds its own ring by TMA; warps 2-5 are the epilogue;
+//   * CTA 1: warp 1 relays "my stage is full" to the leader (remote mbarrier arrive);
+//   * CTA 0 (leader): warp 1 issues the MMAs when both halves of a stage are full, frees the stage in BOTH CTAs and
+//     finally signals both epilogues with multicast commits.
+// Measured at configs[1] size: identical results to k_mtx_tc<1, 8> (3.26e-6), 8.8 ms with a ring of 3 stages (10.0 with
+// 2, 9.0 with 4) against 6.8 ms: with the whole tensor memory taken by one CTA per SM nothing overlaps the epilogue
+// (196 KB of rows per CTA) or the per-tile set-up, which costs more than the halved operand stream saves.  What it
+// needs is a persistent tile loop whose epilogue runs under the next tile's loads -- kept as the base for that.
+constexpr int TC2_BN = 128;                       // columns of the pair's tile
+#ifndef RB_TC2_STAGES
+#define RB_TC2_STAGES 3
+#endif
+constexpr int TC2_STAGES = RB_TC2_STAGES;         // one CTA per SM: the whole shared memory is ring (bytes in flight are what the load pipeline lives on)
+constexpr int TC2_RING_BYTES = TC2_STAGES * TC_STAGE_BYTES;
+constexpr int TC2_SMEM_BYTES = TC2_RING_BYTES + 256 + 1024;
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    for (unsigned spin = 0;; spin++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1u << 26)) __trap();
+    }
+}
+__device__ __forceinline__ void tc_mma_tf32_2cta(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_mtx_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ C,
+          size_t nr, size_t nc, int nkb) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // barriers: full[S], empty[S], peerfull[S] (used in the leader), accfull
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC2_RING_BYTES);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TC2_STAGES + 1);
+    const uint32_t ring = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC2_STAGES), peer0 = smem_u32(bars + 2 * TC2_STAGES);
+    const uint32_t accfull = smem_u32(bars + 3 * TC2_STAGES);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t crank = cluster_rank();
+    const int m0 = (int)(blockIdx.x >> 1) * 256 + (int)crank * TC_BM;       // my 128 rows
+    const int n0 = (int)blockIdx.y * TC2_BN;                                // the pair's 128 columns
+    const int nb0 = n0 + (int)crank * TC_BN;                                // my half of B
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC2_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); mbar_init(peer0 + 8 * s, 1); }
+        mbar_init(accfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int iters = 3 * nkb;
+
+    if (warp == 0) {
+        if (lane == 0) {                              // TMA producer of this CTA's halves
+            for (int it = 0; it < iters; it++) {
+                const int s = it % TC2_STAGES, ph = (it / TC2_STAGES) & 1;
+                const int ch = it / nkb, kb = it % nkb;
+                mbar_wait_cluster(empty0 + 8 * s, ph ^ 1);
+                mbar_expect_tx(full0 + 8 * s, TC_STAGE_BYTES);
+                const uint32_t st = ring + s * TC_STAGE_BYTES;
+                tma_load_3d(st, &tmA, full0 + 8 * s, kb * TC_BK, m0, ch);
+                tma_load_3d(st + TC_A_BYTES, &tmA, full0 + 8 * s, kb * TC_BK, m0, 3 + ch);
+                tma_load_3d(st + 2 * TC_A_BYTES, &tmB, full0 + 8 * s, kb * TC_BK, nb0, ch);
+                tma_load_3d(st + 2 * TC_A_BYTES + TC_B_BYTES, &tmB, full0 + 8 * s, kb * TC_BK, nb0, 3 + ch);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            if (crank != 0) {                         // relay: my stage is full -> the leader's peerfull barrier
+                for (int it = 0; it < iters; it++) {
+                    const int s = it % TC2_STAGES, ph = (it / TC2_STAGES) & 1;
+                    mbar_wait(full0 + 8 * s, ph);
+                    mbar_arrive_remote(mapa_rank(peer0 + 8 * s, 0));
+                }
+            } else {                                  // MMA issuer for the pair
+                constexpr uint32_t idesc = tc_idesc(256, TC2_BN);
+                for (int it = 0; it < iters; it++) {
+                    const int s = it % TC2_STAGES, ph = (it / TC2_STAGES) & 1;
+                    const int ch = it / nkb, kb = it % nkb;
+                    mbar_wait(full0 + 8 * s, ph);
+                    mbar_wait_cluster(peer0 + 8 * s, ph);
+                    tc_fence_after();
+                    const uint32_t st = ring + s * TC_STAGE_BYTES;
+                    const uint64_t ah = tc_smem_desc(st), al = tc_smem_desc(st + TC_A_BYTES);
+                    const uint64_t bh = tc_smem_desc(st + 2 * TC_A_BYTES), bl = tc_smem_desc(st + 2 * TC_A_BYTES + TC_B_BYTES);
+                    const uint32_t d = tmem + (uint32_t)(TC2_BN * ch);
+#pragma unroll
+                    for (int k = 0; k < TC_BK / 8; k++) {
+                        const uint64_t adv = (uint64_t)((k * 8 * 4) >> 4);
+                        tc_mma_tf32_2cta(d, ah + adv, bh + adv, idesc, (kb || k) ? 1u : 0u);
+                        tc_mma_tf32_2cta(d, ah + adv, bl + adv, idesc, 1u);
+                        tc_mma_tf32_2cta(d, al + adv, bh + adv, idesc, 1u);
+                    }
+                    tc_commit_2cta(empty0 + 8 * s, 3);     // the stage is free in both CTAs once these MMAs have read it
+                }
+                tc_commit_2cta(accfull, 3);                // ... and both accumulators are complete once they have finished
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- epilogue: TMEM -> staged rows -> HBM (this CTA's 128 rows x 128 columns x 3 channels) ----------------
+        const int q = warp & 3;
+        const uint32_t tq = tmem + ((uint32_t)(q * 32) << 16);
+        mbar_wait_cluster(accfull, 0);
+        tc_fence_after();
+        uint8_t* stg = smem + (size_t)q * 32 * TC_STG_ROW;
+        const bool vec_ok = (nc % 4) == 0;
+        for (int h = 0; h < TC2_BN / 32; h++) {
+            const size_t cbase = (size_t)n0 + 32 * h;
+            if (cbase >= nc) break;
+#pragma unroll
+            for (int c16 = 0; c16 < 2; c16++) {
+                uint32_t v0[16], v1[16], v2[16];
+                const uint32_t ta = tq + (uint32_t)(32 * h + 16 * c16);
+                tmem_ld16(ta, v0);
+                tmem_ld16(ta + TC2_BN, v1);
+                tmem_ld16(ta + 2 * TC2_BN, v2);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float4* dst = reinterpret_cast<float4*>(stg + (size_t)lane * TC_STG_ROW + (size_t)(16 * c16) * 12);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    dst[0] = make_float4(__uint_as_float(v0[j]), __uint_as_float(v1[j]), __uint_as_float(v2[j]), __uint_as_float(v0[j + 1]));
+                    dst[1] = make_float4(__uint_as_float(v1[j + 1]), __uint_as_float(v2[j + 1]), __uint_as_float(v0[j + 2]), __uint_as_float(v1[j + 2]));
+                    dst[2] = make_float4(__uint_as_float(v2[j + 2]), __uint_as_float(v0[j + 3]), __uint_as_float(v1[j + 3]), __uint_as_float(v2[j + 3]));
+                    dst += 3;
+                }
+            }
+            __syncwarp();
+            const int ncol = (int)min((size_t)32, nc - cbase);
+            const int nflt = ncol * 3;
+            const size_t row0 = (size_t)m0 + q * 32;
+            const int nrow = (int)min((size_t)32, nr > row0 ? nr - row0 : 0);
+            if (vec_ok && nflt == 96) {
+                const int sub = lane >> 3, f0 = lane & 7;
+#pragma unroll 2
+                for (int r4 = 0; r4 < nrow; r4 += 4) {
+                    const int rr = r4 + sub;
+                    if (rr < nrow) {
+                        const float4* src = reinterpret_cast<const float4*>(stg + (size_t)rr * TC_STG_ROW);
+                        float4* dst = reinterpret_cast<float4*>(C + ((row0 + rr) * nc + cbase) * 3);
+                        const float4 a = src[f0], b = src[f0 + 8], c = src[f0 + 16];
+                        dst[f0] = a; dst[f0 + 8] = b; dst[f0 + 16] = c;
+                    }
+                }
+            } else if (vec_ok && (nflt % 4) == 0) {
+                const int per = nflt / 4;
+                for (int i = lane; i < nrow * per; i += 32) {
+                    const int rr = i / per, f = i - rr * per;
+                    reinterpret_cast<float4*>(C + ((row0 + rr) * nc + cbase) * 3)[f] =
+                        reinterpret_cast<const float4*>(stg + (size_t)rr * TC_STG_ROW)[f];
+                }
+            } else {
+                for (int i = lane; i < nrow * nflt; i += 32) {
+                    const int rr = i / nflt, f = i - rr * nflt;
+                    C[((row0 + rr) * nc + cbase) * 3 + f] = reinterpret_cast<const float*>(stg + (size_t)rr * TC_STG_ROW)[f];
+                }
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    cluster_sync_all();                               // neither CTA leaves while the other may still read its shared memory
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- host ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -405,6 +606,10 @@ bool mtx_multiply_tc(cudaStream_t stream, const float* A, size_t n, size_t ni, c
     if (cl == 2) {
         TCK(cudaFuncSetAttribute(k_mtx_tc<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         k_mtx_tc<2, 4><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmB, C, n, nc, nkb);
+    } else if (nkb <= 8 && getenv("RB_MTX_2CTA") && (Mp % 256) == 0 && (Np % TC2_BN) == 0) {
+        TCK(cudaFuncSetAttribute(k_mtx_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES));
+        dim3 grid2((unsigned)(2 * (Mp / 256)), (unsigned)(Np / TC2_BN));
+        k_mtx_tc2<<<grid2, TC_THREADS, TC2_SMEM_BYTES, stream>>>(tmA, tmB, C, n, nc, nkb);
     } else if (nkb <= 8) {
         TCK(cudaFuncSetAttribute(k_mtx_tc<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
         k_mtx_tc<1, 8><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(tmA, tmB, C, n, nc, nkb);

@@ -999,6 +999,30 @@ def test_rfluxmtx_front_end(golden):
         os.chdir(cwd)
 
 
+def test_matrix_product_on_cta_pairs_matches(monkeypatch):
+    """The experimental cta_group::2 form of the tcgen05 matrix product (k_mtx_tc2, RB_MTX_2CTA) gives what the
+    default kernel gives, to fp32 rounding, and float64 within the consumer's 1e-5 gate."""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    nr, ni, nc = 1024, 145, 640
+    a = (rng.random((nr, ni, 3)) ** 6 * 0.05).astype(np.float32)
+    b = (rng.random((ni, nc, 3)) ** 3 * 2e4).astype(np.float32)
+    ref = np.einsum("rik,ick->rck", a.astype(np.float64), b.astype(np.float64))
+    outs = []
+    for pair in (False, True):
+        if pair:
+            monkeypatch.setenv("RB_MTX_2CTA", "1")
+        ctx = _lib.Context(0)
+        out = np.empty((nr, nc, 3), dtype=np.float32)
+        ms = C.c_double(0)
+        assert ctx.lib.rb_mtx_multiply(ctx.h, a.ctypes.data, nr, ni, b.ctypes.data, nc, out.ctypes.data, 0, C.byref(ms)) == 0
+        outs.append(out)
+    monkeypatch.delenv("RB_MTX_2CTA")
+    for out in outs:
+        assert (np.abs(out - ref) / np.maximum(ref, 1e-30)).max() < 1e-5
+    np.testing.assert_allclose(outs[0], outs[1], rtol=2e-6)
+
+
 def test_dctimestep_matrix_consumer(G, golden):
     """the matrix product after the path (rb_mtx_multiply / dctimestep).  Against the reference
     dctimestep on the same files: ascii and float outputs, the -n headerless sky, the V.T.D.s chain -- all
