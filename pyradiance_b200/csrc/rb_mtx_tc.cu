@@ -39,9 +39,9 @@ constexpr int TC_BM = 128, TC_BN = 64, TC_BK = 32, TC_STAGES = 2, TC_THREADS = 1
 // 128 rows of A, so each loads 128 / TC_CL rows of every A tile and MULTICASTS them into the shared memory of all of
 // them (one L2 read feeds TC_CL SMs); a stage is handed back when the MMAs of every CTA of the cluster have read it
 // (tcgen05.commit with a CTA mask on the `empty` barriers, which count TC_CL arrivals).
-// Measured (tools/mtx_variants.sh): at K = 145 the kernel is bound by the bytes DELIVERED into each SM (720 KB per
-// tile at 74 GB/s per SM = the 9.7 us a tile takes), which multicast does not reduce -- clusters of 2 / 4 are 5 / 12 %
-// slower there; at K = 2305 a cluster of 2 is 7 % faster (152.6 TFLOP/s).  The host picks: clusters for K >= 512.
+// Measured (tools/mtx_variants.sh): at K = 145 clusters of 2 / 4 are 5 / 12 % slower (multicast does not reduce the
+// bytes delivered into each SM, and the kernel is not bound by the L2 reads); at K = 2305 a cluster of 2 is 7 % faster
+// (152.6 TFLOP/s).  The host picks: clusters for K >= 512.
 constexpr int TC_CL_MAX = 2;
 // k-blocks per accumulation segment: 4 (128 products) in general; a product whose whole inner dimension fits 8 blocks
 // (K <= 256, the MF:1 daylight-coefficient case) is one segment per channel (3.3e-6 instead of 2.7e-6, 2.5 % faster)
